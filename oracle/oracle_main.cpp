@@ -1,0 +1,189 @@
+// TEST INFRASTRUCTURE ONLY — see ngsep_oracle.hpp.
+// CLI + C API around the oracle.  The CLI accepts the option ids of the reference module
+// (main/CommandsDescriptor.xml:565-703, SingleSampleVariantsDetector) that affect the SNV/indel path:
+//   ngsep_oracle SingleSampleVariantsDetector -i in.sam -r ref.fa -o prefix [options]
+// Extra, oracle-only switches (not in the reference): --dump-counts FILE, --stats FILE.
+#include "ngsep_oracle.hpp"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+using namespace ngsep_oracle;
+
+namespace {
+
+struct RunResult { long n_records = 0, n_pileups = 0, n_nonempty = 0, n_events = 0; double seconds = 0; };
+
+RunResult run_ssvd(const ReferenceGenome& genome, std::istream& sam, std::ostream& vcf, const DetectorOptions& opt,
+                   std::vector<std::array<int, 6>>* dump) {
+    SingleSampleVariantsDetector det;
+    det.opt = opt;
+    det.genome = &genome;
+    det.out = &vcf;
+    det.var_listener.counts_dump = dump;
+    auto t0 = std::chrono::steady_clock::now();
+    det.begin();
+    std::string line;
+    SamRecord rec;
+    RunResult r;
+    while (std::getline(sam, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!parse_sam_line(line, rec)) continue;
+        r.n_records++;
+        det.add_record(rec);
+    }
+    det.finish();
+    auto t1 = std::chrono::steady_clock::now();
+    r.seconds = std::chrono::duration<double>(t1 - t0).count();
+    r.n_pileups = det.gen.n_pileups;
+    r.n_nonempty = det.gen.n_nonempty;
+    r.n_events = det.realigner.n_events;
+    return r;
+}
+
+int parse_options(int argc, char** argv, int start, DetectorOptions& opt, std::string& in, std::string& ref, std::string& out,
+                  std::string& dump, std::string& stats) {
+    for (int i = start; i < argc; i++) {
+        std::string a = argv[i];
+        auto need = [&](const char* what) -> const char* {
+            if (i + 1 >= argc) { std::fprintf(stderr, "missing value for %s\n", what); std::exit(1); }
+            return argv[++i];
+        };
+        if (a == "-i") in = need("-i");
+        else if (a == "-r") ref = need("-r");
+        else if (a == "-o") out = need("-o");
+        else if (a == "-sampleId") opt.sample_id = need("-sampleId");
+        else if (a == "-ploidy") opt.ploidy = (short)std::atoi(need("-ploidy"));
+        else if (a == "-psp") opt.psp = true;
+        else if (a == "-minMQ") opt.min_mq = std::atoi(need("-minMQ"));
+        else if (a == "-querySeq") { opt.query_seq = need("-querySeq"); opt.has_query = true; }
+        else if (a == "-first") opt.query_first = std::atoi(need("-first"));
+        else if (a == "-last") opt.query_last = std::atoi(need("-last"));
+        else if (a == "-ignoreLowerCaseRef") opt.ignore_lower = true;
+        else if (a == "-maxAlnsPerStartPos") opt.max_alns_per_start = std::atoi(need("-maxAlnsPerStartPos"));
+        else if (a == "-p") opt.non_unique_primary = true;
+        else if (a == "-s") opt.secondary = true;
+        else if (a == "-ignore5") opt.ignore5 = std::atoi(need("-ignore5"));
+        else if (a == "-ignore3") opt.ignore3 = std::atoi(need("-ignore3"));
+        else if (a == "-h") { opt.het_rate = std::atof(need("-h")); opt.het_modified = true; }
+        else if (a == "-maxBaseQS") opt.max_base_qs = std::atoi(need("-maxBaseQS"));
+        else if (a == "-minQuality") opt.min_quality = (short)std::atoi(need("-minQuality"));
+        else if (a == "-embeddedSNVs") opt.call_embedded = true;
+        else if (a == "-csb") opt.csb = true;
+        else if (a == "--dump-counts") dump = need("--dump-counts");
+        else if (a == "--stats") stats = need("--stats");
+        else { std::fprintf(stderr, "Unrecognized option %s\n", a.c_str()); return 1; }  // CommandsDescriptor.java:441-445
+    }
+    return 0;
+}
+
+}  // namespace
+
+#ifndef NGSEP_ORACLE_NO_MAIN
+int main(int argc, char** argv) {
+    if (argc < 2 || std::string(argv[1]) != "SingleSampleVariantsDetector") {
+        std::fprintf(stderr, "usage: ngsep_oracle SingleSampleVariantsDetector -i in.sam -r ref.fa -o prefix [options]\n");
+        return 1;
+    }
+    DetectorOptions opt;
+    std::string in, ref, out, dump, stats;
+    if (parse_options(argc, argv, 2, opt, in, ref, out, dump, stats)) return 1;
+    if (in.empty()) { std::fprintf(stderr, "The input file with alignments is a required parameter\n"); return 2; }   // SSVD:595
+    if (ref.empty()) { std::fprintf(stderr, "The reference genome file is a required parameter\n"); return 2; }      // SSVD:596
+    ReferenceGenome genome = ReferenceGenome::load_fasta(ref);
+    std::ifstream sam(in);
+    if (!sam) { std::fprintf(stderr, "cannot open %s\n", in.c_str()); return 2; }
+    std::ofstream vcf(out + ".vcf");   // SSVD:926
+    std::vector<std::array<int, 6>> counts;
+    RunResult r = run_ssvd(genome, sam, vcf, opt, dump.empty() ? nullptr : &counts);
+    vcf.close();
+    if (!dump.empty()) {
+        std::ofstream d(dump, std::ios::binary);
+        d.write((const char*)counts.data(), (std::streamsize)(counts.size() * sizeof(counts[0])));
+    }
+    if (!stats.empty()) {
+        std::ofstream s(stats);
+        s << "{\"records\": " << r.n_records << ", \"pileups\": " << r.n_pileups << ", \"genotyped_positions\": " << r.n_nonempty
+          << ", \"indel_events\": " << r.n_events << ", \"seconds\": " << r.seconds << "}\n";
+    }
+    return 0;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// C API (ctypes) — function-level access for the known-answer tests
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+// Evaluate the SNV path on a synthetic column: counts[b] calls of base b ("ACGT") all with phred+33 quality
+// char qual_char, plus n_lowq extra reference-base calls at quality '#' (q2).  discovery=1: VD.discoverSNV;
+// discovery=0: VD.genotypeSNV for the biallelic SNV ref>alt.  Outputs: gt[2] (allele indexes into {ref,alt}; -1 none),
+// pl[3], gq, qual, dp, called (0 = no call object).
+int oracle_snv_column(const int* counts, int qual_char, int n_lowq, char ref, char alt, double het_rate, int max_base_qs,
+                      int discovery, int* gt, int* pl, int* gq, int* qual, int* dp, char* alt_out) {
+    std::vector<PileupAlleleCall> calls;
+    for (int b = 0; b < 4; b++) for (int k = 0; k < counts[b]; k++) {
+        PileupAlleleCall c; c.seq = std::string(1, "ACGT"[b]); c.quals = std::string(1, (char)qual_char); calls.push_back(c);
+    }
+    for (int k = 0; k < n_lowq; k++) { PileupAlleleCall c; c.seq = std::string(1, ref); c.quals = "#"; calls.push_back(c); }
+    CountsHelper h = CountsHelper::snv(calls, (int8_t)max_base_qs, 0.5);
+    CalledVariant cv;
+    gt[0] = gt[1] = -1;
+    if (discovery) {
+        if (!discover_snv(h, "seq", 1, ref, het_rate, false, cv)) return 0;
+    } else {
+        GenomicVariant v; v.seq = "seq"; v.first = v.last = 1; v.len = 1; v.alleles = {std::string(1, ref), std::string(1, alt)};
+        v.type = TYPE_BIALLELIC_SNV; v.snv_class = true;
+        cv = genotype_snv(v, h, het_rate, false);
+    }
+    auto idx = cv.called_indexes();
+    if (idx.size() == 1) gt[0] = gt[1] = idx[0];
+    else if (idx.size() == 2) { gt[0] = idx[0]; gt[1] = idx[1]; }
+    const auto& al = cv.var.alleles;
+    int k = 0;
+    for (size_t j = 0; j < al.size() && j < 2; j++) for (size_t i = 0; i <= j; i++) pl[k++] = (int)java_round(-10 * cv.report_logc(al[i], al[j]));
+    *gq = cv.gq; *qual = cv.var.qs; *dp = cv.depth;
+    if (alt_out) *alt_out = al.size() > 1 ? al[1][0] : '.';
+    return 1;
+}
+
+double oracle_table_error(int q, int j) { return CountsHelper::table_error(q, j); }
+double oracle_table_gt(int f, int q, int j) { return CountsHelper::table_gt(f, q, j); }
+double oracle_fisher(int a, int b, int c, int d) { return fisher_pvalue(a, b, c, d); }
+int oracle_phred(double p) { return phred_score(p); }
+int oracle_mononucleotide(const char* s) { return check_mononucleotide(s); }
+
+// Whole-path run on in-memory text.  Returns malloc'ed VCF text (caller frees with oracle_free).
+// counts_out (optional): malloc'ed int32 [n][6] = pos,A,C,G,T,DP for every position where discoverSNV ran.
+char* oracle_run_ssvd(const char* fasta_path, const char* sam_path, int argc, char** argv, int** counts_out, long* n_counts,
+                      long* genotyped_positions, double* seconds) {
+    DetectorOptions opt;
+    std::string in, ref, out, dump, stats;
+    if (parse_options(argc, argv, 0, opt, in, ref, out, dump, stats)) return nullptr;
+    ReferenceGenome genome = ReferenceGenome::load_fasta(fasta_path);
+    std::ifstream sam(sam_path);
+    if (!sam) return nullptr;
+    std::ostringstream vcf;
+    std::vector<std::array<int, 6>> counts;
+    RunResult r = run_ssvd(genome, sam, vcf, opt, counts_out ? &counts : nullptr);
+    if (counts_out) {
+        *counts_out = (int*)std::malloc(counts.size() * 6 * sizeof(int) + 8);
+        std::memcpy(*counts_out, counts.data(), counts.size() * 6 * sizeof(int));
+        *n_counts = (long)counts.size();
+    }
+    if (genotyped_positions) *genotyped_positions = r.n_nonempty;
+    if (seconds) *seconds = r.seconds;
+    std::string s = vcf.str();
+    char* res = (char*)std::malloc(s.size() + 1);
+    std::memcpy(res, s.c_str(), s.size() + 1);
+    return res;
+}
+
+void oracle_free(void* p) { std::free(p); }
+
+}  // extern "C"
