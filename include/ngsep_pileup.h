@@ -1,0 +1,161 @@
+/*
+ * ngsep_pileup.h — C ABI of the B200-native pileup / SNVQ hot path (libngsep_pileup.so).
+ *
+ * This is the drop-in boundary for ONE path of NGSEP 4.3.2 (acastem15/NGSEPcore): the alignment->pileup walk,
+ * per-position allele / base-quality counting and the SNVQ genotype posterior.  The reference has no FFI of its
+ * own (it is 100 % Java); each entry point below names the Java interface it stands in for (paths relative to
+ * /root/reference/src/ngsep/).  The reference-side JNI / ctypes binding is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a negative NGSEP_E* code on failure; ngsep_last_error()
+ * gives a context-owned UTF-8 message.  No exception, exit() or CPU fallback crosses this boundary: without a
+ * usable CUDA device ngsep_ctx_create fails with NGSEP_ENODEVICE.  A context is bound to one GPU and one host
+ * thread.  The caller owns every host buffer it passes; the library owns all device memory.
+ */
+#ifndef NGSEP_PILEUP_H
+#define NGSEP_PILEUP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGSEP_OK 0
+#define NGSEP_EINVAL (-1)
+#define NGSEP_ENODEVICE (-2)
+#define NGSEP_ECUDA (-3)
+#define NGSEP_ENOMEM (-4)
+#define NGSEP_ESTATE (-5)
+#define NGSEP_EOVERFLOW (-6)
+
+/* ngsep_params.flags */
+#define NGSEP_F_STRAND_BIAS 0x1u      /* -csb            discovery/SingleSampleVariantsDetector.java:480 (calcStrandBias)   */
+#define NGSEP_F_IGNORE_LOWER_REF 0x2u /* -ignoreLowerCaseRef  discovery/SingleSampleVariantPileupListener.java:198          */
+#define NGSEP_F_EMIT_ALL 0x8u         /* test hook: also return A,C,G,T,DP for every tile position (counts_dbg)             */
+
+/* Options of main/CommandsDescriptor.xml:565-703 that change what the device computes. */
+typedef struct ngsep_params {
+    int32_t max_base_qs;  /* -maxBaseQS, default 30      discovery/CountsHelper.java:47,217-219                  */
+    int32_t min_quality;  /* -minQuality, default 40     discovery/SingleSampleVariantPileupListener.java:50,223 */
+    double het_rate;      /* -h, 1e-3 diploid / 1e-6 haploid   discovery/CountsHelper.java:42-43                 */
+    int32_t ploidy;       /* -ploidy, default 2 (device path supports ploidy < 3, SSVPL:238)                    */
+    uint32_t flags;       /* NGSEP_F_*                                                                          */
+    int32_t n_samples;    /* 1 = SingleSampleVariantsDetector; >1 = MultisampleVariantsDetector sample axis      */
+    int32_t reserved;
+} ngsep_params;
+
+/*
+ * Log-probability tables, computed by the HOST (the JVM's Math.log10 in the reference deployment) so that libm
+ * differences cannot leak into the device arithmetic.  Layout: tables[3*q + k], q = 0..30:
+ *   k=0  a_q = logProbCacheGT[250][q][0]   log10(1-e_q)                      CountsHelper.java:175
+ *   k=1  b_q = logProbCacheError[q][4]     -0.1q - log10(3)                  CountsHelper.java:149-153
+ *   k=2  c_q = logProbCacheGT[250][q][4]   log10(.5(1-e_q) + .5 e_q/3)       CountsHelper.java:177-178
+ * followed by tables[93] = log10((1-h)/4) and tables[94] = log10(h/12)       CountsHelper.java:414-415
+ */
+#define NGSEP_N_TABLES 95
+
+/* One read record (or one VERSION of a read, see valid window below), 16 bytes, admission order
+ * (discovery/AlignmentsPileupGenerator.java:407-433: start ascending, primaries before secondaries, file order). */
+typedef struct ngsep_read_hdr {
+    int32_t first;       /* 1-based start used for ordering (ReadAlignment.first at admission); non-decreasing */
+    uint32_t meta;       /* bits 0-15 read length (incl. soft clips), 16-23 number of CIGAR words, NGSEP_M_* flags */
+    int16_t ign_start;   /* ReadAlignment.basesToIgnoreStart after the strand mapping of RA:613-644             */
+    int16_t ign_end;     /* ReadAlignment.basesToIgnoreEnd                                                      */
+    uint32_t off;        /* offset of this record's payload in 32-bit words                                     */
+} ngsep_read_hdr;
+
+#define NGSEP_M_NEG 0x01000000u    /* negative strand (SAM 0x10)                                               */
+#define NGSEP_M_NMASK 0x02000000u  /* payload carries a 1-bit/base "not ACGT" mask                             */
+#define NGSEP_M_WINDOW 0x04000000u /* payload starts with {valid_from, valid_to, first}: the record describes the
+                                      read only for reference positions valid_from <= p < valid_to, with its own
+                                      start `first` (versions written by the indel-realigner pre-pass)          */
+#define NGSEP_M_SAMPLE_SHIFT 27    /* unused in single-sample runs                                             */
+
+/* Payload of one record, 32-bit words, in this order:
+ *   [valid_from, valid_to, first]      only with NGSEP_M_WINDOW
+ *   cigar[n_cigar]                     len*8+op, op codes H0 D1 I2 M3 P4 N5 S6 X7 (ReadAlignment.java:60-69,1180-1198)
+ *   bases2[ceil(L/16)]                 2-bit A0 C1 G2 T3, base k in bits 2*(k%16) of word k/16
+ *   nmask[ceil(L/32)]                  only with NGSEP_M_NMASK
+ *   qual[ceil(L/4)]                    phred+33 bytes, little endian (ReadAlignment.qualityScores, RA:581-595)
+ */
+
+/* A region tile: every admitted read overlapping [tile_first, tile_last] on one sequence (halo included); calls
+ * are produced only for positions inside the tile.  Stands in for the per-position loop
+ * AlignmentsPileupGenerator.processPileups/processCurrentPosition (APG:453-504) over that region. */
+typedef struct ngsep_tile {
+    int32_t seq_idx;
+    int32_t tile_first, tile_last; /* 1-based inclusive */
+    int32_t n_reads;
+    int32_t max_span;              /* max over records of (last reference position of the record - hdr.first + 1) */
+    int32_t max_back;              /* max over records of (hdr.first - record's own first), >= 0                   */
+    uint64_t n_words;              /* payload length in words                                                      */
+    const ngsep_read_hdr* hdr;     /* [n_reads]                                                                    */
+    const uint32_t* payload;       /* [n_words]                                                                    */
+    const uint16_t* sample;        /* [n_reads] sample index, NULL when n_samples == 1                             */
+} ngsep_tile;
+
+/* One SNV-path decision for one position.  Field semantics follow VariantDiscoverySNVQAlgorithm.discoverSNV
+ * (VD:100-222) and the filter of SingleSampleVariantPileupListener.discoverVariant (SSVPL:223). */
+typedef struct ngsep_snv_call {
+    int32_t seq_idx;
+    int32_t pos;
+    int32_t count[4];     /* CountsHelper.counts, A C G T                          CH:223      */
+    int32_t depth;        /* CountsHelper.totalCount                               CH:210      */
+    int32_t strand[8];    /* countsStrand[b][0 = negative, 1 = positive]           CH:226-227  */
+    double logcond[16];   /* logConditionalProbs[i][j], summed in pileup order     CH:231-249  */
+    double post_ref;      /* posterior of the homozygous-reference genotype        VD:120      */
+    double post_max;      /* posterior of the called genotype                      VD:122-123  */
+    int16_t gq;           /* genotype quality                                      VD:124      */
+    int16_t qual;         /* variant quality = phred(post_ref)                     VD:212      */
+    int8_t a0, a1;        /* allele indexes (A0 C1 G2 T3) of the called genotype, a0 <= a1     */
+    int8_t ref;           /* reference allele index                                            */
+    int8_t kind;          /* NGSEP_CALL_*                                                      */
+    int32_t sample;       /* sample index (0 in single-sample runs)                            */
+} ngsep_snv_call;
+
+#define NGSEP_CALL_HET 1      /* 0/1   CalledSNV heterozygous     VD:181-188 */
+#define NGSEP_CALL_HOMALT 2   /* 1/1   CalledSNV homozygous alt   VD:189-193 */
+#define NGSEP_CALL_TRIALLELIC 3 /* 1/2 MULTISNV                   VD:128-177; a0 = alt, a1 = third allele as ordered by VD:133-139 */
+
+/* Counters of the last completed tile. */
+typedef struct ngsep_tile_stats {
+    uint64_t covered_positions;  /* positions with >= 1 covering admitted read ("genotyped positions")   */
+    uint64_t candidate_positions;/* positions that went through the exact SNVQ evaluation                */
+    uint64_t calls;              /* records written                                                      */
+    uint64_t aligned_bases;      /* sum of read lengths of the tile's records                            */
+    float kernel_ms;             /* device time of the tile's kernels (CUDA events on the context stream) */
+    uint32_t kernel_launches;    /* kernels launched for the tile                                        */
+} ngsep_tile_stats;
+
+/* Context = one GPU + one stream + device-resident reference.  Replaces the construction of
+ * AlignmentsPileupGenerator + CountsHelper's static caches (APG:38-69, CH:135-187). */
+int ngsep_ctx_create(int device, const ngsep_params* params, const double* tables, size_t n_tables, void** ctx);
+int ngsep_ctx_destroy(void* ctx);
+const char* ngsep_last_error(void* ctx);
+
+/* Uploads one reference sequence (ASCII, case kept, any length); packed on the device to 2 bits/base + masks.
+ * Replaces ReferenceGenome.getReference for the path (genome/ReferenceGenome.java:222-245). */
+int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t length);
+
+/* Asynchronous: copies the tile's host buffers to the device and launches the kernels on the context stream.
+ * The host buffers must stay valid until ngsep_tile_fetch returns. */
+int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
+
+/* Waits for the submitted tile and copies its calls (unordered) into out[0..cap).  counts_dbg, when not NULL and
+ * NGSEP_F_EMIT_ALL is set, receives [tile_last-tile_first+1][5] = A,C,G,T,DP. */
+int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
+
+/* Device-resident variant for measurement: stage a tile in HBM once, then run the kernels over it repeatedly
+ * without host<->device copies (bench.py "value"); results are fetched with ngsep_tile_fetch as usual. */
+int ngsep_tile_stage(void* ctx, const ngsep_tile* tile);
+int ngsep_tile_run_staged(void* ctx);
+
+/* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
+int ngsep_abi_version(void);
+int ngsep_built_sm(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSEP_PILEUP_H */

@@ -1,0 +1,162 @@
+"""ctypes binding of libngsep_pileup.so (include/ngsep_pileup.h) — the same stub INTEGRATION.md shows.
+
+No fallback: importing works without a GPU (so CPU-only CI can check the exported symbols), but every compute
+entry point raises ``NgsepError`` when the library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libngsep_pileup.so")
+
+N_TABLES = 95
+F_STRAND_BIAS, F_IGNORE_LOWER_REF, F_EMIT_ALL = 0x1, 0x2, 0x8
+M_NEG, M_NMASK, M_WINDOW = 0x01000000, 0x02000000, 0x04000000
+CALL_HET, CALL_HOMALT, CALL_TRIALLELIC = 1, 2, 3
+
+
+class NgsepError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("max_base_qs", C.c_int32), ("min_quality", C.c_int32), ("het_rate", C.c_double), ("ploidy", C.c_int32),
+                ("flags", C.c_uint32), ("n_samples", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Tile(C.Structure):
+    _fields_ = [("seq_idx", C.c_int32), ("tile_first", C.c_int32), ("tile_last", C.c_int32), ("n_reads", C.c_int32),
+                ("max_span", C.c_int32), ("max_back", C.c_int32), ("n_words", C.c_uint64), ("hdr", C.c_void_p),
+                ("payload", C.c_void_p), ("sample", C.c_void_p)]
+
+
+class TileStats(C.Structure):
+    _fields_ = [("covered_positions", C.c_uint64), ("candidate_positions", C.c_uint64), ("calls", C.c_uint64),
+                ("aligned_bases", C.c_uint64), ("kernel_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+
+
+HDR_DTYPE = np.dtype([("first", "<i4"), ("meta", "<u4"), ("ign_start", "<i2"), ("ign_end", "<i2"), ("off", "<u4")])
+CALL_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("strand", "<i4", (8,)),
+                       ("logcond", "<f8", (16,)), ("post_ref", "<f8"), ("post_max", "<f8"), ("gq", "<i2"), ("qual", "<i2"),
+                       ("a0", "i1"), ("a1", "i1"), ("ref", "i1"), ("kind", "i1"), ("sample", "<i4")], align=True)
+
+EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_ref_upload", "ngsep_tile_submit",
+           "ngsep_tile_fetch", "ngsep_tile_stage", "ngsep_tile_run_staged", "ngsep_abi_version", "ngsep_built_sm"]
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads the CUDA library; raises NgsepError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NgsepError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    lib.ngsep_ctx_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.ngsep_ctx_destroy.argtypes = [C.c_void_p]
+    lib.ngsep_last_error.argtypes = [C.c_void_p]
+    lib.ngsep_last_error.restype = C.c_char_p
+    lib.ngsep_ref_upload.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    lib.ngsep_tile_submit.argtypes = [C.c_void_p, C.POINTER(Tile)]
+    lib.ngsep_tile_stage.argtypes = [C.c_void_p, C.POINTER(Tile)]
+    lib.ngsep_tile_run_staged.argtypes = [C.c_void_p]
+    lib.ngsep_tile_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(TileStats)]
+    _lib = lib
+    return lib
+
+
+def host_tables(het_rate: float = 0.001) -> np.ndarray:
+    """The 95 doubles of include/ngsep_pileup.h (NGSEP_N_TABLES), restating CountsHelper.updateProbabilitiesCache
+    (reference: src/ngsep/discovery/CountsHelper.java:135-187, 414-415) with the host libm."""
+    import math
+    t = np.zeros(N_TABLES, np.float64)
+    for q in range(3, 31):
+        e = math.pow(10.0, -0.1 * q)          # PhredScoreHelper.calculateProbability
+        s = 1 - e
+        af = 250.0 / 500.0
+        t[3 * q] = math.log10(s)
+        t[3 * q + 1] = -0.1 * q - math.log10(3.0)
+        t[3 * q + 2] = math.log10(af * s + (1 - af) * e / 3)
+    t[93] = math.log10((1 - het_rate) / 4)
+    t[94] = math.log10(het_rate / 12)
+    return t
+
+
+class Context:
+    """One GPU context (ngsep_ctx_create .. ngsep_ctx_destroy)."""
+
+    def __init__(self, device: int = 0, max_base_qs: int = 30, min_quality: int = 40, het_rate: float = 0.001, ploidy: int = 2,
+                 flags: int = 0, tables: np.ndarray | None = None):
+        self.lib = load_library()
+        self.params = Params(max_base_qs, min_quality, het_rate, ploidy, flags, 1, 0)
+        tab = np.ascontiguousarray(host_tables(het_rate) if tables is None else tables, np.float64)
+        self.h = C.c_void_p()
+        rc = self.lib.ngsep_ctx_create(device, C.byref(self.params), tab.ctypes.data_as(C.POINTER(C.c_double)), tab.size, C.byref(self.h))
+        if rc != 0:
+            raise NgsepError(f"ngsep_ctx_create failed ({rc}): {self.lib.ngsep_last_error(None).decode()}")
+        self._keep = []
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise NgsepError(f"{what} failed ({rc}): {self.lib.ngsep_last_error(self.h).decode()}")
+
+    def ref_upload(self, seq_idx: int, bases: np.ndarray) -> None:
+        b = np.ascontiguousarray(bases, np.uint8)
+        self._check(self.lib.ngsep_ref_upload(self.h, seq_idx, b.ctypes.data, b.size), "ngsep_ref_upload")
+
+    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back) -> Tile:
+        hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
+        payload = np.ascontiguousarray(payload, np.uint32)
+        self._keep = [hdr, payload]
+        return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
+                    hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None, None)
+
+    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back)
+        self._n_pos = tile_last - tile_first + 1
+        self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
+
+    def stage(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back)
+        self._n_pos = tile_last - tile_first + 1
+        self._check(self.lib.ngsep_tile_stage(self.h, C.byref(t)), "ngsep_tile_stage")
+
+    def run_staged(self) -> None:
+        self._check(self.lib.ngsep_tile_run_staged(self.h), "ngsep_tile_run_staged")
+
+    def fetch(self, cap: int = 1 << 16, want_counts: bool = False):
+        """Returns (calls structured array sorted by pos, counts [n_pos,5] or None, TileStats)."""
+        stats = TileStats()
+        counts = np.zeros((self._n_pos, 5), np.int32) if want_counts else None
+        while True:
+            out = np.zeros(cap, CALL_DTYPE)
+            n = C.c_size_t(0)
+            rc = self.lib.ngsep_tile_fetch(self.h, out.ctypes.data, cap, C.byref(n), counts.ctypes.data if want_counts else None, C.byref(stats))
+            if rc == -6 and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            self._check(rc, "ngsep_tile_fetch")
+            break
+        calls = out[: n.value]
+        calls = calls[np.argsort(calls["pos"], kind="stable")]
+        return calls, counts, stats
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.ngsep_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+assert CALL_DTYPE.itemsize == 224 and HDR_DTYPE.itemsize == 16, (CALL_DTYPE.itemsize, HDR_DTYPE.itemsize)

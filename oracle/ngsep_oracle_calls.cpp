@@ -5,7 +5,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <mutex>
 #include <stdexcept>
 
 namespace ngsep_oracle {
@@ -80,8 +79,7 @@ constexpr int NQ = 31, NJ = MAX_NUM_ALLELES + 1, NF = 501;
 double g_err[NQ][NJ];
 double g_freq[NF][2];
 std::vector<double> g_gt;  // [f][q][j]
-std::once_flag g_tables_once;
-void build_tables() {
+bool build_tables() {
     std::memset(g_err, 0, sizeof(g_err));
     for (int i = 3; i < NQ; i++) {
         g_err[i][0] = -0.1 * i;
@@ -102,17 +100,19 @@ void build_tables() {
             }
         }
     }
+    return true;
 }
+inline void ensure_tables() { static const bool built = build_tables(); (void)built; }
 inline double GT(int f, int q, int j) { return g_gt[((size_t)f * NQ + q) * NJ + j]; }
 const double LOG_ERR_INDEL = std::log10(0.0001);  // CH:48
 }  // namespace
 
-double CountsHelper::table_error(int q, int j) { std::call_once(g_tables_once, build_tables); return g_err[q][j]; }
-double CountsHelper::table_gt(int f, int q, int j) { std::call_once(g_tables_once, build_tables); return GT(f, q, j); }
-double CountsHelper::table_freq(int f, int k) { std::call_once(g_tables_once, build_tables); return g_freq[f][k]; }
+double CountsHelper::table_error(int q, int j) { ensure_tables(); return g_err[q][j]; }
+double CountsHelper::table_gt(int f, int q, int j) { ensure_tables(); return GT(f, q, j); }
+double CountsHelper::table_freq(int f, int k) { ensure_tables(); return g_freq[f][k]; }
 
 CountsHelper::CountsHelper(const std::vector<std::string>& al) : alleles(al) {  // CH:125-134
-    std::call_once(g_tables_once, build_tables);
+    ensure_tables();
     size_t n = al.size();
     counts.assign(n, 0);
     strand.assign(n, {0, 0});

@@ -1,0 +1,79 @@
+"""Helpers around the CPU oracle (oracle/) — the checker, never the thing under test."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_SO = os.path.join(ORACLE_DIR, "build", "libngsep_oracle.so")
+ORACLE_BIN = os.path.join(ORACLE_DIR, "build", "ngsep_oracle")
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def load_oracle():
+    if not os.path.exists(ORACLE_SO):
+        build_oracle()
+    lib = C.CDLL(ORACLE_SO)
+    ip = C.POINTER(C.c_int)
+    lib.oracle_snv_column.argtypes = [ip, C.c_int, C.c_int, C.c_char, C.c_char, C.c_double, C.c_int, C.c_int, ip, ip, ip, ip, ip, C.c_char_p]
+    lib.oracle_table_error.restype = C.c_double
+    lib.oracle_table_error.argtypes = [C.c_int, C.c_int]
+    lib.oracle_table_gt.restype = C.c_double
+    lib.oracle_table_gt.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.oracle_fisher.restype = C.c_double
+    lib.oracle_fisher.argtypes = [C.c_int] * 4
+    lib.oracle_phred.argtypes = [C.c_double]
+    lib.oracle_mononucleotide.argtypes = [C.c_char_p]
+    lib.oracle_run_ssvd.restype = C.c_void_p
+    lib.oracle_run_ssvd.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_int)),
+                                    C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    lib.oracle_free.argtypes = [C.c_void_p]
+    return lib
+
+
+def snv_column(lib, counts, qual_char="?", n_lowq=0, ref="A", alt="C", het_rate=0.001, max_qs=30, discovery=True):
+    cnt = (C.c_int * 4)(*counts)
+    gt = (C.c_int * 2)()
+    pl = (C.c_int * 3)()
+    gq, qual, dp = C.c_int(), C.c_int(), C.c_int()
+    alt_out = C.create_string_buffer(2)
+    called = lib.oracle_snv_column(cnt, ord(qual_char), n_lowq, ref.encode(), alt.encode(), het_rate, max_qs, 1 if discovery else 0,
+                                   gt, pl, C.byref(gq), C.byref(qual), C.byref(dp), alt_out)
+    return dict(called=bool(called), gt=(gt[0], gt[1]), pl=tuple(pl), gq=gq.value, qual=qual.value, dp=dp.value,
+                alt=alt_out.raw[:1].decode())
+
+
+def run_ssvd(lib, fasta, sam, args=(), want_counts=False):
+    """Runs the oracle detector; returns (vcf_text, counts[n,6] or None, genotyped_positions, seconds)."""
+    argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+    cptr = C.POINTER(C.c_int)()
+    n_counts, gp, sec = C.c_long(0), C.c_long(0), C.c_double(0)
+    res = lib.oracle_run_ssvd(fasta.encode(), sam.encode(), len(args), argv, C.byref(cptr) if want_counts else None,
+                              C.byref(n_counts), C.byref(gp), C.byref(sec))
+    if not res:
+        raise RuntimeError("oracle run failed")
+    text = C.string_at(res).decode()
+    lib.oracle_free(res)
+    counts = None
+    if want_counts:
+        counts = np.ctypeslib.as_array(cptr, shape=(n_counts.value, 6)).copy() if n_counts.value else np.zeros((0, 6), np.int32)
+        lib.oracle_free(cptr)
+    return text, counts, gp.value, sec.value
+
+
+def parse_vcf(text):
+    """-> list of dict(chrom,pos,ref,alt,qual,info,fmt,gt,pl,gq,dp,cnt,acn) for single-sample VCF text."""
+    out = []
+    for line in text.splitlines():
+        if not line or line[0] == "#":
+            continue
+        t = line.split("\t")
+        s = t[9].split(":")
+        out.append(dict(chrom=t[0], pos=int(t[1]), ref=t[3], alt=t[4], qual=int(t[5]), info=t[7], fmt=t[8], gt=s[0], pl=s[1],
+                        gq=int(s[2]), dp=int(s[3]), cnt=s[4], acn=s[5], line=line))
+    return out
