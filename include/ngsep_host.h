@@ -1,0 +1,86 @@
+/*
+ * ngsep_host.h — C entry points of libngsep_host.so, the host pipeline that sits ABOVE the device C ABI
+ * (ngsep_pileup.h).  It mirrors, for this path only, the reference's detector surface
+ *   src/ngsep/discovery/SingleSampleVariantsDetector.java   (setters :141-560, run() :589-656, findSNVs :896-931)
+ *   src/ngsep/discovery/AlignmentsPileupGenerator.java      (APG:71-193, processAlignments APG:334-361)
+ * over decoded alignment records (what htsjdk hands to ReadAlignmentFileReader.loadAlignment, RAFR:219-272).
+ * In a JVM deployment the Java host does this work itself and binds ngsep_pileup.h directly;
+ * this library exists because no JVM is available in the build image.
+ */
+#ifndef NGSEP_HOST_H
+#define NGSEP_HOST_H
+
+#include "ngsep_pileup.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Decoded, coordinate-sorted alignment records, struct-of-arrays. */
+typedef struct ngsep_host_batch {
+    int64_t n;
+    const int32_t* seq_idx;     /* index into the genome set with ngsep_ssvd_set_genome                 */
+    const int32_t* first;       /* SAMRecord.getAlignmentStart, 1-based                                  */
+    const uint16_t* flags;      /* SAM flags                                                             */
+    const uint8_t* mapq;
+    const int16_t* rg;          /* read-group index, -1 = no RG tag (read group "" in the reference)     */
+    const int16_t* nh;          /* NH tag, -1 = absent (RAFR:284-291)                                    */
+    const int64_t* cigar_off;   /* [n+1]                                                                 */
+    const uint32_t* cigar;      /* len*8+op, op codes H0 D1 I2 M3 P4 N5 S6 X7 ('=' is 3), RA:60-69       */
+    const int64_t* base_off;    /* [n+1]                                                                 */
+    const uint8_t* bases;       /* SEQ, ASCII                                                            */
+    const uint8_t* quals;       /* QUAL, phred+33; a missing QUAL is passed as '+' bytes (RA:1025)       */
+    const uint64_t* name_hash;  /* optional hash of QNAME for the duplicate-record rule (RAFR:292-306)   */
+} ngsep_host_batch;
+
+/* Option ids of main/CommandsDescriptor.xml:565-703 that affect this path, plus device plumbing. */
+typedef struct ngsep_detector_options {
+    const char* sample_id;          /* -sampleId, NULL = "Sample"   */
+    int32_t ploidy;                 /* -ploidy, 2                   */
+    int32_t print_sample_ploidy;    /* -psp                         */
+    int32_t min_mq;                 /* -minMQ, 20                   */
+    const char* query_seq;          /* -querySeq, NULL = none       */
+    int32_t query_first, query_last;/* -first / -last               */
+    int32_t ignore_lower_case_ref;  /* -ignoreLowerCaseRef          */
+    int32_t max_alns_per_start_pos; /* -maxAlnsPerStartPos, 5       */
+    int32_t process_non_unique_primary; /* -p                       */
+    int32_t process_secondary;      /* -s                           */
+    int32_t ignore5, ignore3;       /* -ignore5 / -ignore3          */
+    double het_rate;                /* -h, 0.001                    */
+    int32_t het_rate_set;           /* 1 when -h was given (SSVD:591-593 haploid default otherwise) */
+    int32_t max_base_qs;            /* -maxBaseQS, 30               */
+    int32_t min_quality;            /* -minQuality, 40              */
+    int32_t call_embedded_snvs;     /* -embeddedSNVs                */
+    int32_t calc_strand_bias;       /* -csb                         */
+    int32_t device;                 /* CUDA device index            */
+    int32_t tile_len;               /* 0 = one tile per sequence    */
+    int32_t shard, n_shards;        /* region sharding across ranks: tile t belongs to rank t % n_shards */
+    int32_t host_only;              /* test hook: admission + event pre-pass only; output holds just the host-made indel/STR records */
+} ngsep_detector_options;
+
+typedef struct ngsep_run_stats {
+    uint64_t records, admitted, versions, events, indel_calls, snv_calls;
+    uint64_t covered_positions, candidate_positions, aligned_bases, tiles, kernel_launches;
+    double kernel_ms, prepass_s, pack_s, device_s, total_s;
+} ngsep_run_stats;
+
+void ngsep_detector_options_default(ngsep_detector_options* o);
+int ngsep_ssvd_create(const ngsep_detector_options* o, void** det);
+int ngsep_ssvd_destroy(void* det);
+const char* ngsep_ssvd_error(void* det);
+/* setGenome (SSVD:161-163): sequence names, lengths and bases exactly as in the FASTA (case kept). */
+int ngsep_ssvd_set_genome(void* det, int n, const char* const* names, const int64_t* lengths, const char* const* bases);
+/* findSNVs over the batch; the VCF text (header when with_header != 0) is kept in the handle. */
+int ngsep_ssvd_run(void* det, const ngsep_host_batch* batch, int with_header);
+const char* ngsep_ssvd_vcf(void* det, size_t* len);
+int ngsep_ssvd_stats(void* det, ngsep_run_stats* stats);
+
+/* Admission + packing of one sequence without the event pre-pass (device-resident benchmarking, packer tests). */
+int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_alns_per_start, int ignore5, int ignore3,
+                    ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads, uint64_t* n_words, int* max_span, uint64_t* aligned_bases);
+void ngsep_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSEP_HOST_H */

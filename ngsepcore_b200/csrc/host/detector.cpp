@@ -1,0 +1,250 @@
+// GpuSingleSampleVariantsDetector: drop-in for SingleSampleVariantsDetector.findSNVs (SSVD:896-968) over in-memory,
+// coordinate-sorted alignment records.  Per sequence:
+//   1. admission            (RAFR filters, APG:407-433 cap)                               host, O(reads)
+//   2. event pre-pass       indel realigner + span>1 calls at the sparse event positions  host, O(events x depth)
+//   3. pack + ngsep_tile_submit / ngsep_tile_fetch per region tile                        device: every position
+//   4. ordered merge        embedded / indel suppression (SSVPL:150-160), sort, VCF text  host, O(calls)
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <queue>
+#include <set>
+
+#include "pipeline.hpp"
+
+namespace ngsep_b200 {
+namespace host {
+
+namespace {
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}
+
+GpuSingleSampleVariantsDetector::GpuSingleSampleVariantsDetector(const DetectorOptions& o) : opt_(o) {
+    if (!opt_.het_modified && opt_.ploidy == 1) opt_.het_rate = 0.000001;  // SSVD:591-593
+}
+
+GpuSingleSampleVariantsDetector::~GpuSingleSampleVariantsDetector() {
+    if (ctx_) ngsep_ctx_destroy(ctx_);
+}
+
+void GpuSingleSampleVariantsDetector::set_genome(const Genome* g) {
+    genome_ = g;
+    ref_uploaded_.assign(g->seqs.size(), false);
+}
+
+int GpuSingleSampleVariantsDetector::ensure_ctx() {
+    if (ctx_) return NGSEP_OK;
+    ngsep_params p{};
+    p.max_base_qs = opt_.max_base_qs;
+    p.min_quality = opt_.min_quality;
+    p.het_rate = opt_.het_rate;
+    p.ploidy = opt_.ploidy;
+    p.flags = (opt_.csb ? NGSEP_F_STRAND_BIAS : 0u) | (opt_.ignore_lower ? NGSEP_F_IGNORE_LOWER_REF : 0u);
+    p.n_samples = 1;
+    double tables[NGSEP_N_TABLES];
+    host_tables(opt_.het_rate, tables);
+    int rc = ngsep_ctx_create(opt_.device, &p, tables, NGSEP_N_TABLES, &ctx_);
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(nullptr); ctx_ = nullptr; }
+    return rc;
+}
+
+int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, bool with_header) {
+    double t0 = now_s();
+    if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
+    int rc = opt_.host_only ? NGSEP_OK : ensure_ctx();
+    if (rc != NGSEP_OK) return rc;
+    if (with_header) out += vcf_header(opt_.sample_id, opt_.ploidy, opt_.print_sample_ploidy);
+    stats_.records += (uint64_t)b.n;
+    bool query_found = false;
+    int64_t i = 0;
+    while (i < b.n) {
+        int seq = b.seq_idx[i];
+        int64_t j = i;
+        while (j < b.n && b.seq_idx[j] == seq) j++;
+        bool take = true;
+        if (opt_.has_query) {  // APG:310-322
+            bool is_q = seq >= 0 && seq < (int)genome_->names.size() && genome_->names[seq] == opt_.query_seq;
+            if (is_q) query_found = true;
+            else if (query_found) break;
+            take = is_q;
+        }
+        if (take && seq >= 0 && seq < (int)genome_->seqs.size()) {
+            rc = run_sequence(b, seq, i, j, out);
+            if (rc != NGSEP_OK) return rc;
+        }
+        i = j;
+    }
+    stats_.total_s += now_s() - t0;
+    return NGSEP_OK;
+}
+
+int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) {
+    const std::string& chrom = genome_->names[seq];
+    const int seq_len = (int)genome_->seqs[seq].size();
+    double t0 = now_s();
+    // ---- 1. admission -------------------------------------------------------------------------------------------
+    AdmissionOptions ao;
+    ao.min_mq = opt_.min_mq; ao.max_alns_per_start = opt_.max_alns_per_start; ao.secondary = opt_.secondary;
+    ao.non_unique_primary = opt_.non_unique_primary; ao.ignore5 = opt_.ignore5; ao.ignore3 = opt_.ignore3;
+    int64_t q_lo = lo, q_hi = hi;
+    if (opt_.has_query) {  // records starting after queryLast end the run (APG:315); earlier ones are filtered below
+        while (q_hi > q_lo && b.first[q_hi - 1] > opt_.query_last) q_hi--;
+    }
+    if (opt_.has_query) ao.query_first = opt_.query_first;
+    std::vector<HostRead> reads = admit_sequence(b, q_lo, q_hi, ao);
+    for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { err_ = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
+    stats_.admitted += reads.size();
+    if (reads.empty()) return NGSEP_OK;
+    const int win_first = opt_.has_query ? std::max(1, opt_.query_first) : 1;
+    const int win_last = opt_.has_query ? std::min(seq_len, opt_.query_last) : seq_len;
+
+    // ---- 2. event pre-pass ----------------------------------------------------------------------------------------
+    Realigner realigner;
+    realigner.genome = genome_;
+    realigner.seq = seq;
+    IndelCallerOptions io;
+    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
+    std::vector<IndelRecord> indels;
+    std::set<int> suppressed;                         // positions where the device's SNV decision must not be reported
+    std::vector<std::pair<int, int>> embedded;        // (from, to] style closed intervals [a,b] of embedded positions
+    int last_indel_end = 0;                           // SSVPL:143
+    {
+        std::priority_queue<int, std::vector<int>, std::greater<int>> heap;
+        std::vector<HostRead*> active, pileup;
+        std::vector<ReadState> before;
+        size_t next = 0;
+        while (next < reads.size() || !heap.empty()) {
+            int s = next < reads.size() ? reads[next].admit_first : INT_MAX;
+            int e = heap.empty() ? INT_MAX : heap.top();
+            if (s <= e) {  // every read starting at or before an event is pending when the event is processed (APG:377-403)
+                HostRead& r = reads[next++];
+                r.derive();
+                active.push_back(&r);
+                for (auto& a : r.anchors) heap.push(a.pos);
+                continue;
+            }
+            while (!heap.empty() && heap.top() == e) heap.pop();
+            if (e < win_first || e > win_last) continue;  // no pileup outside the query window (APG:481-484)
+            size_t w = 0;
+            for (size_t k = 0; k < active.size(); k++) if (active[k]->st.last >= e) active[w++] = active[k];  // APG:464-471
+            active.resize(w);
+            pileup.clear();
+            for (HostRead* r : active) if (r->st.first <= e && e <= r->st.last) pileup.push_back(r);       // PR:154-156
+            bool any = false;
+            for (HostRead* r : pileup) if (r->anchor_at(e)) { any = true; break; }
+            if (!any) continue;
+            before.clear();
+            for (HostRead* r : pileup) before.push_back(r->st);
+            EventOutcome ev = realigner.on_event(e, pileup);
+            if (!ev.fired) continue;
+            stats_.events++;
+            for (size_t k = 0; k < pileup.size(); k++) {
+                HostRead* r = pileup[k];
+                if (!r->derived) r->derive();
+                if (r->st == before[k]) continue;
+                if (r->cur_from == e) continue;  // cannot happen (one event per position); keeps windows well formed
+                r->closed.push_back(Version{r->cur_from, e, before[k]});
+                r->cur_from = e;
+                stats_.versions++;
+                for (auto& a : r->anchors) if (a.pos > e) heap.push(a.pos);
+            }
+            // ---- SingleSampleVariantPileupListener.onPileup at the event (SSVPL:146-161) ----
+            bool emb = e <= last_indel_end;
+            if (emb && !opt_.call_embedded) continue;     // SSVPL:193 — nothing is called here (interval already recorded)
+            std::string ref;
+            if (!genome_->get(seq, e, e + ev.span - 1, ref)) { suppressed.insert(e); continue; }   // SSVPL:195-196
+            if (opt_.ignore_lower && ref[0] >= 'a' && ref[0] <= 'z') { suppressed.insert(e); continue; }
+            if (emb || ev.span <= 1) continue;            // SNV path: the device decides
+            IndelRecord rec;
+            if (call_indel_at(e, upper(ref), ev.str, pileup, io, rec)) {
+                suppressed.insert(e);
+                last_indel_end = rec.last;                 // SSVPL:157-158
+                if (rec.last > e) embedded.push_back({e + 1, rec.last});
+                indels.push_back(std::move(rec));
+                stats_.indel_calls++;
+            }
+        }
+    }
+    stats_.prepass_s += now_s() - t0;
+
+    // ---- 3. device: region tiles ------------------------------------------------------------------------------------
+    if (!opt_.host_only && !ref_uploaded_[seq]) {
+        int rc = ngsep_ref_upload(ctx_, seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
+        if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+        ref_uploaded_[seq] = true;
+    }
+    std::vector<ngsep_snv_call> snvs;
+    if (!opt_.host_only) {
+        // reach of every read over all of its versions, to pick the records of a tile (halo = read span)
+        int max_reach = 1, max_back = 0;
+        std::vector<int> reach(reads.size());
+        for (size_t k = 0; k < reads.size(); k++) {
+            const HostRead& r = reads[k];
+            int lastp = r.st.last, firstp = r.st.first;
+            for (auto& v : r.closed) { lastp = std::max(lastp, v.st.last); firstp = std::min(firstp, v.st.first); }
+            reach[k] = lastp;
+            max_reach = std::max(max_reach, lastp - r.admit_first + 1);
+            max_back = std::max(max_back, r.admit_first - firstp);
+        }
+        const int tile_len = opt_.tile_len > 0 ? opt_.tile_len : INT_MAX;
+        PackedTile tile;
+        std::vector<ngsep_snv_call> buf;
+        int tile_no = 0;
+        for (int64_t tf = win_first; tf <= win_last; tf += tile_len, tile_no++) {
+            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
+            int tl = (int)std::min<int64_t>(win_last, tf + (int64_t)tile_len - 1);
+            // records whose ordering start can reach the tile
+            size_t r_lo = std::lower_bound(reads.begin(), reads.end(), (int)tf - max_reach + 1, [](const HostRead& r, int v) { return r.admit_first < v; }) - reads.begin();
+            size_t r_hi = std::upper_bound(reads.begin(), reads.end(), tl + max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
+            if (r_lo >= r_hi) continue;
+            double tp = now_s();
+            pack_reads(reads, r_lo, r_hi, tile);
+            stats_.pack_s += now_s() - tp;
+            if (tile.hdr.empty()) continue;
+            double td = now_s();
+            ngsep_tile tv = tile.view(seq, (int)tf, tl);
+            int rc = ngsep_tile_submit(ctx_, &tv);
+            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+            size_t n = 0;
+            ngsep_tile_stats ts{};
+            buf.resize(std::max<size_t>(buf.size(), 65536));
+            rc = ngsep_tile_fetch(ctx_, buf.data(), buf.size(), &n, nullptr, &ts);
+            if (rc == NGSEP_EOVERFLOW && n > buf.size()) { buf.resize(n + 16); rc = ngsep_tile_fetch(ctx_, buf.data(), buf.size(), &n, nullptr, &ts); }
+            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+            stats_.device_s += now_s() - td;
+            stats_.covered_positions += ts.covered_positions;
+            stats_.candidate_positions += ts.candidate_positions;
+            stats_.aligned_bases += ts.aligned_bases;
+            stats_.kernel_ms += ts.kernel_ms;
+            stats_.kernel_launches += ts.kernel_launches;
+            stats_.tiles++;
+            snvs.insert(snvs.end(), buf.begin(), buf.begin() + n);
+        }
+        (void)reach;
+    }
+
+    // ---- 4. ordered merge + text (SSVD:933-968) -------------------------------------------------------------------------
+    std::sort(snvs.begin(), snvs.end(), [](const ngsep_snv_call& a, const ngsep_snv_call& c) { return a.pos < c.pos; });
+    struct Line { int first, last, order; std::string text; };
+    std::vector<Line> lines;
+    size_t ei = 0;
+    for (auto& c : snvs) {
+        if (suppressed.count(c.pos)) continue;
+        while (ei < embedded.size() && embedded[ei].second < c.pos) ei++;
+        bool emb = ei < embedded.size() && embedded[ei].first <= c.pos && c.pos <= embedded[ei].second;
+        if (emb && !opt_.call_embedded) continue;
+        lines.push_back({c.pos, c.pos, (int)lines.size(), snv_vcf_line(c, chrom, opt_.ploidy, opt_.csb, emb)});
+        stats_.snv_calls++;
+    }
+    for (auto& r : indels) {
+        bool mine = true;
+        if (opt_.n_shards > 1 && opt_.tile_len > 0) mine = (((r.pos - win_first) / opt_.tile_len) % opt_.n_shards) == opt_.shard;
+        if (mine) lines.push_back({r.pos, r.last, (int)lines.size(), indel_vcf_line(r, chrom, opt_.ploidy)});
+    }
+    std::stable_sort(lines.begin(), lines.end(), [](const Line& a, const Line& c) { return a.first != c.first ? a.first < c.first : a.last < c.last; });
+    for (auto& l : lines) out += l.text;
+    return NGSEP_OK;
+}
+
+}  // namespace host
+}  // namespace ngsep_b200

@@ -1,0 +1,135 @@
+// C entry points of libngsep_host.so: the host pipeline (C++ mirror of the reference's Java detector) for callers
+// without a C++ toolchain — the Python harness (ctypes) and, in a JVM deployment, the JNI glue of INTEGRATION.md.
+// The device work goes through the C ABI of include/ngsep_pileup.h; nothing here computes the hot path on the CPU.
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "../../../include/ngsep_host.h"
+#include "pipeline.hpp"
+
+using namespace ngsep_b200::host;
+
+namespace {
+
+struct Handle {
+    DetectorOptions opt;
+    Genome genome;
+    GpuSingleSampleVariantsDetector* det = nullptr;
+    std::string vcf, err;
+    ~Handle() { delete det; }
+};
+
+BatchView view_of(const ngsep_host_batch* b) {
+    BatchView v;
+    v.n = b->n; v.seq_idx = b->seq_idx; v.first = b->first; v.flags = b->flags; v.mapq = b->mapq; v.rg = b->rg; v.nh = b->nh;
+    v.cigar_off = b->cigar_off; v.cigar = b->cigar; v.base_off = b->base_off; v.bases = b->bases; v.quals = b->quals; v.name_hash = b->name_hash;
+    return v;
+}
+
+DetectorOptions convert(const ngsep_detector_options* o) {
+    DetectorOptions d;
+    if (o->sample_id) d.sample_id = o->sample_id;
+    d.ploidy = o->ploidy; d.print_sample_ploidy = o->print_sample_ploidy != 0; d.min_mq = o->min_mq;
+    if (o->query_seq && o->query_seq[0]) { d.query_seq = o->query_seq; d.has_query = true; }
+    d.query_first = o->query_first; d.query_last = o->query_last;
+    d.ignore_lower = o->ignore_lower_case_ref != 0; d.max_alns_per_start = o->max_alns_per_start_pos;
+    d.non_unique_primary = o->process_non_unique_primary != 0; d.secondary = o->process_secondary != 0;
+    d.ignore5 = o->ignore5; d.ignore3 = o->ignore3; d.het_rate = o->het_rate; d.het_modified = o->het_rate_set != 0;
+    d.max_base_qs = o->max_base_qs; d.min_quality = o->min_quality; d.call_embedded = o->call_embedded_snvs != 0; d.csb = o->calc_strand_bias != 0;
+    d.device = o->device; d.tile_len = o->tile_len; d.shard = o->shard; d.n_shards = o->n_shards < 1 ? 1 : o->n_shards; d.host_only = o->host_only != 0;
+    return d;
+}
+
+}  // namespace
+
+extern "C" {
+
+void ngsep_detector_options_default(ngsep_detector_options* o) {
+    std::memset(o, 0, sizeof(*o));
+    o->ploidy = 2; o->min_mq = 20; o->query_last = 1000000000; o->max_alns_per_start_pos = 5; o->het_rate = 0.001;
+    o->max_base_qs = 30; o->min_quality = 40; o->n_shards = 1;
+}
+
+int ngsep_ssvd_create(const ngsep_detector_options* o, void** out) {
+    if (!o || !out) return NGSEP_EINVAL;
+    Handle* h = new Handle();
+    h->opt = convert(o);
+    *out = h;
+    return NGSEP_OK;
+}
+
+int ngsep_ssvd_destroy(void* p) { delete (Handle*)p; return NGSEP_OK; }
+
+const char* ngsep_ssvd_error(void* p) { return p ? ((Handle*)p)->err.c_str() : ""; }
+
+int ngsep_ssvd_set_genome(void* p, int n, const char* const* names, const int64_t* lengths, const char* const* bases) {
+    Handle* h = (Handle*)p;
+    if (!h || n <= 0) return NGSEP_EINVAL;
+    h->genome.names.clear(); h->genome.seqs.clear();
+    for (int i = 0; i < n; i++) { h->genome.names.emplace_back(names[i]); h->genome.seqs.emplace_back(bases[i], (size_t)lengths[i]); }
+    delete h->det;
+    h->det = new GpuSingleSampleVariantsDetector(h->opt);
+    h->det->set_genome(&h->genome);
+    return NGSEP_OK;
+}
+
+int ngsep_ssvd_run(void* p, const ngsep_host_batch* b, int with_header) {
+    Handle* h = (Handle*)p;
+    if (!h || !b) return NGSEP_EINVAL;
+    if (!h->det) { h->err = "The reference genome file is a required parameter"; return NGSEP_ESTATE; }
+    h->vcf.clear();
+    int rc = h->det->run(view_of(b), h->vcf, with_header != 0);
+    if (rc != NGSEP_OK) h->err = h->det->error();
+    return rc;
+}
+
+const char* ngsep_ssvd_vcf(void* p, size_t* len) {
+    Handle* h = (Handle*)p;
+    if (len) *len = h->vcf.size();
+    return h->vcf.c_str();
+}
+
+int ngsep_ssvd_stats(void* p, ngsep_run_stats* s) {
+    Handle* h = (Handle*)p;
+    if (!h || !h->det || !s) return NGSEP_EINVAL;
+    const RunStats& r = h->det->stats();
+    s->records = r.records; s->admitted = r.admitted; s->versions = r.versions; s->events = r.events; s->indel_calls = r.indel_calls;
+    s->snv_calls = r.snv_calls; s->covered_positions = r.covered_positions; s->candidate_positions = r.candidate_positions;
+    s->aligned_bases = r.aligned_bases; s->tiles = r.tiles; s->kernel_launches = r.kernel_launches; s->kernel_ms = r.kernel_ms;
+    s->prepass_s = r.prepass_s; s->pack_s = r.pack_s; s->device_s = r.device_s; s->total_s = r.total_s;
+    return NGSEP_OK;
+}
+
+// Pack-only entry (no device): admission + event pre-pass versions are NOT applied here; it packs the admitted
+// records of one sequence exactly as the detector would for an indel-free input.  Used by bench.py to build
+// device-resident tiles and by tests that compare the C++ packer with the numpy one.
+int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_alns_per_start, int ignore5, int ignore3,
+                    ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads, uint64_t* n_words, int* max_span, uint64_t* aligned_bases) {
+    if (!b || !hdr || !payload) return NGSEP_EINVAL;
+    BatchView v = view_of(b);
+    int64_t lo = 0;
+    while (lo < v.n && v.seq_idx[lo] != seq_idx) lo++;
+    int64_t hi = lo;
+    while (hi < v.n && v.seq_idx[hi] == seq_idx) hi++;
+    AdmissionOptions ao;
+    ao.min_mq = min_mq; ao.max_alns_per_start = max_alns_per_start; ao.ignore5 = ignore5; ao.ignore3 = ignore3;
+    std::vector<HostRead> reads = admit_sequence(v, lo, hi, ao);
+    PackedTile t;
+    pack_reads(reads, 0, reads.size(), t);
+    *n_reads = (int64_t)t.hdr.size();
+    *n_words = t.payload.size();
+    *max_span = t.max_span;
+    if (aligned_bases) *aligned_bases = t.aligned_bases;
+    *hdr = (ngsep_read_hdr*)std::malloc(t.hdr.size() * sizeof(ngsep_read_hdr) + 16);
+    *payload = (uint32_t*)std::malloc(t.payload.size() * 4 + 64);
+    if (!*hdr || !*payload) return NGSEP_ENOMEM;
+    std::memcpy(*hdr, t.hdr.data(), t.hdr.size() * sizeof(ngsep_read_hdr));
+    std::memcpy(*payload, t.payload.data(), t.payload.size() * 4);
+    return NGSEP_OK;
+}
+
+void ngsep_host_free(void* p) { std::free(p); }
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+// Host indel / STR caller for event positions with a reference span > 1.  Restates
+//   PileupRecord.getAlleleCalls(span)                    PR   = discovery/PileupRecord.java:126-152
+//   AlleleCallClustersBuilder.clusterAlleleCalls          ACCB = discovery/AlleleCallClustersBuilder.java:72-261
+//   CountsHelper.calculateCountsIndel / updateCountsIndel CH   = discovery/CountsHelper.java:96-105,253-304,384-396
+//   VariantDiscoverySNVQAlgorithm.callIndel               VD   = discovery/VariantDiscoverySNVQAlgorithm.java:265-361
+// (paths under /root/reference/src/ngsep/).  Events are ~1e-4 of positions, so this stays on the host in round 1
+// (SURVEY.md section 8f rank 1 moves it to the device).
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <set>
+
+#include "pipeline.hpp"
+
+namespace ngsep_b200 {
+namespace host {
+
+long jround(double x) { double f = std::floor(x); return (long)((x - f >= 0.5) ? f + 1.0 : f); }
+
+int phred(double p) {
+    if (p == 0) return 255;
+    double s = -10 * std::log10(p);
+    if (s > 255) return 255;
+    return (int)(short)jround(s);
+}
+
+double fisher_pvalue(int a, int b, int c, int d) {
+    static std::vector<double> lf;
+    auto exact = [&](int a, int b, int c, int d) {
+        int n = a + b + c + d;
+        if ((int)lf.size() <= n) {
+            int m = std::max(n, 10000);
+            lf.assign(m + 1, 0.0);
+            for (int i = 2; i <= m; i++) lf[i] = lf[i - 1] + std::log10((double)i);
+        }
+        double v = lf[a + b];
+        v += lf[c + d]; v += lf[a + c]; v += lf[b + d];
+        v -= lf[a]; v -= lf[b]; v -= lf[c]; v -= lf[d]; v -= lf[n];
+        return std::pow(10.0, v);
+    };
+    if (a > b) { std::swap(a, b); std::swap(c, d); }
+    if (a > c) { std::swap(a, c); std::swap(b, d); }
+    int e = std::min(a, d);
+    double ans = 0;
+    while (a >= 0 && d >= 0) {
+        double p = exact(a, b, c, d);
+        if (e >= 10 && ans > 100.0 * e * p) break;
+        ans += p;
+        a--; b++; c++; d--; e++;
+    }
+    return ans;
+}
+
+namespace {
+
+struct SpanCall { std::string allele, quals; bool neg; };
+
+struct QTables {   // the slices of CountsHelper's caches this caller needs
+    double match[31], err4[31], lf251_0, lf251_1, log_err_indel;
+    double a250[31], c250[31];
+    QTables() {
+        for (int q = 0; q < 31; q++) match[q] = err4[q] = a250[q] = c250[q] = 0;
+        for (int q = 3; q < 31; q++) {
+            double e = std::pow(10.0, -0.1 * q), s = 1 - e;
+            match[q] = std::log10(s);                        // logProbCacheGT[0][q][0]
+            err4[q] = -0.1 * q - std::log10(3.0);             // logProbCacheError[q][4]
+            a250[q] = match[q];
+            c250[q] = std::log10(0.5 * s + 0.5 * e / 3);
+        }
+        double af = 251.0 / 500.0;                            // f = round(0.5 * 501), CH:256
+        lf251_0 = std::log10(af);
+        lf251_1 = std::log10(1 - af);
+        log_err_indel = std::log10(0.0001);
+    }
+};
+const QTables& qt() { static const QTables t; return t; }
+
+double log_sum(double a, double b) {  // math/LogMath.java:38-44
+    if (a - b > 20) return a;
+    if (b - a > 20) return b;
+    return a + std::log10(1 + std::pow(10.0, b - a));
+}
+
+std::string column_consensus(const std::vector<std::string>& seqs) {
+    std::string out;
+    for (size_t i = 0; i < seqs[0].size(); i++) {
+        int cnt[256] = {0};
+        for (auto& s : seqs) cnt[(unsigned char)s[i]]++;
+        int best = 0;
+        for (int c = 1; c < 256; c++) if (cnt[c] > cnt[best]) best = c;
+        out.push_back((char)best);
+    }
+    return out;
+}
+
+// 16-event posterior of CH:410-495 for n alleles
+std::vector<std::vector<double>> posteriors(const std::vector<std::vector<double>>& L, double het_rate) {
+    int n = (int)L.size();
+    double lp_het = std::log10(het_rate / (n * (n - 1)));
+    double lp_hom = std::log10((1 - het_rate) / n);
+    std::vector<double> ev;
+    for (int i = 0; i < n; i++) {
+        ev.push_back(L[i][i] + lp_hom);
+        for (int j = 0; j < n; j++) if (i != j) ev.push_back(L[i][j] + lp_het);
+    }
+    double mx = 1;
+    for (double e : ev) if (mx > 0 || mx < e) mx = e;
+    double tot = 0;
+    for (double& e : ev) { e -= mx; e = (e < -20) ? 0.0 : std::pow(10.0, e); tot += e; }
+    for (double& e : ev) e /= tot;
+    std::vector<std::vector<double>> P(n, std::vector<double>(n, 0.0));
+    int k = 0;
+    for (int i = 0; i < n; i++) { P[i][i] = ev[k++]; for (int j = 0; j < n; j++) if (i != j) P[i][j] = ev[k++]; }
+    return P;
+}
+
+// ACCB.calculateHetPosteriors (ACCB:223-261): a 4-allele SNV column per consensus position
+double het_posterior_column(const std::vector<const SpanCall*>& calls, size_t i, int idx_c, int max_qs) {
+    const QTables& t = qt();
+    std::vector<std::vector<double>> L(4, std::vector<double>(4, 0.0));
+    for (auto* c : calls) {
+        int q = std::min(max_qs, (int)(unsigned char)c->quals[i] - 33);
+        q = (int)(int8_t)q;
+        if (q <= 3) continue;              // CH:214-216
+        if (q > 30) q = 30;                // fresh CountsHelper: maxBaseQS 30 (CH:56)
+        int b = -1;
+        switch (c->allele[i]) { case 'A': b = 0; break; case 'C': b = 1; break; case 'G': b = 2; break; case 'T': b = 3; break; }
+        if (b < 0) continue;
+        for (int x = 0; x < 4; x++) {
+            L[x][x] += (x == b) ? t.a250[q] : t.err4[q];
+            for (int y = 0; y < 4; y++) if (x != y) L[x][y] += (y == b || x == b) ? t.c250[q] : t.err4[q];
+        }
+    }
+    auto P = posteriors(L, 0.001);
+    double best = 0;
+    for (int k = 0; k < 4; k++) { double hp = P[idx_c][k] + P[k][idx_c]; if (k != idx_c && hp > best) best = hp; }
+    return best;
+}
+
+std::set<std::string> split_by_variant_sites(const std::vector<const SpanCall*>& calls, const std::string& consensus, int max_qs) {  // ACCB:165-221
+    std::set<std::string> out;
+    std::vector<int> sites;
+    for (size_t i = 0; i < consensus.size(); i++) {
+        int idx_c = (consensus[i] < 'a') ? dna_index(consensus[i]) : -1;
+        if (idx_c < 0) continue;
+        bool variable = false;
+        for (auto* c : calls) if (c->allele[i] != consensus[i]) { variable = true; break; }
+        if (!variable) continue;
+        if (het_posterior_column(calls, i, idx_c, max_qs) >= 0.51) sites.push_back((int)i);
+    }
+    if (sites.empty()) { out.insert(consensus); return out; }
+    std::vector<std::string> haps(calls.size());
+    for (size_t i = 0; i < calls.size(); i++) for (int s : sites) haps[i].push_back(calls[i]->allele[s]);
+    std::map<std::string, int> counts;
+    for (auto& h : haps) counts[h]++;
+    std::vector<std::pair<std::string, int>> ranked(counts.begin(), counts.end());
+    std::stable_sort(ranked.begin(), ranked.end(), [](const auto& a, const auto& b) { return a.second > b.second; });
+    int max_haps = 2;
+    if (sites.size() > 3) max_haps = std::min(10, (int)sites.size() / 2 + 1);
+    std::vector<std::string> chosen;
+    for (int i = 0; i < max_haps && i < (int)ranked.size(); i++) chosen.push_back(ranked[i].first);
+    std::vector<std::vector<std::string>> groups(chosen.size());
+    for (size_t i = 0; i < calls.size(); i++) {
+        auto it = std::find(chosen.begin(), chosen.end(), haps[i]);
+        if (it != chosen.end()) groups[it - chosen.begin()].push_back(calls[i]->allele);
+    }
+    for (auto& g : groups) if (!g.empty()) out.insert(column_consensus(g));
+    return out;
+}
+
+std::vector<std::string> cluster_alleles(const std::vector<SpanCall>& calls, const std::string& ref, int max_qs) {  // ACCB:72-141
+    std::map<int, std::vector<const SpanCall*>> by_len;
+    for (auto& c : calls) by_len[(int)c.allele.size()].push_back(&c);
+    if (by_len.size() >= 3) {  // filterLengthClusters, ACCB:147-157
+        double min_count = 0.2 * (double)calls.size();
+        for (auto it = by_len.begin(); it != by_len.end();) { if (min_count <= (double)it->second.size()) ++it; else it = by_len.erase(it); }
+    }
+    std::set<std::string> all;
+    for (auto& kv : by_len) {
+        auto& cl = kv.second;
+        std::set<std::string> suggested;
+        if (kv.first == (int)ref.size()) suggested.insert(ref);
+        if (cl.size() < 5 * suggested.size()) { all.insert(suggested.begin(), suggested.end()); continue; }
+        std::vector<std::string> seqs;
+        for (auto* c : cl) seqs.push_back(c->allele);
+        std::string consensus = column_consensus(seqs);
+        suggested.insert(consensus);
+        if (kv.first < 4 || cl.size() < 10) all.insert(suggested.begin(), suggested.end());
+        else { auto s = split_by_variant_sites(cl, consensus, max_qs); all.insert(s.begin(), s.end()); }
+    }
+    all.insert(ref);
+    std::vector<std::string> out = {ref};
+    for (auto& a : all) if (a != ref) out.push_back(a);
+    return out;
+}
+
+}  // namespace
+
+bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out) {
+    const QTables& t = qt();
+    const int span = (int)ref_allele.size();
+    std::vector<SpanCall> calls;
+    for (HostRead* r : pileup) {
+        SpanCall c;
+        if (!r->span_call(pos, pos + span - 1, c.allele, c.quals)) continue;
+        c.allele = upper(c.allele);
+        c.neg = r->neg;
+        calls.push_back(std::move(c));
+    }
+    std::vector<std::string> alleles = cluster_alleles(calls, ref_allele, opt.max_base_qs);
+    const int n = (int)alleles.size();
+    std::vector<int> counts(n, 0);
+    std::vector<std::array<int, 2>> strand(n, {0, 0});
+    std::vector<std::vector<double>> L(n, std::vector<double>(n, 0.0));
+    int total = 0;
+    for (auto& c : calls) {  // updateCountsIndel, CH:253-304
+        total++;
+        int index = -1;
+        for (int i = 0; i < n; i++) if (alleles[i] == c.allele) { index = i; break; }
+        std::vector<double> lc(n, t.log_err_indel);
+        int best = -1;
+        for (int i = 0; i < n; i++) {
+            if (alleles[i].size() != c.allele.size()) continue;
+            double v = 0;
+            for (size_t k = 0; k < alleles[i].size(); k++) {  // calculateLogCond, CH:384-396
+                int q = (int)(int8_t)std::min(opt.max_base_qs, (int)(unsigned char)c.quals[k] - 33);
+                if (q < 3) continue;
+                v += (alleles[i][k] == c.allele[k]) ? t.match[q] : t.err4[q];
+            }
+            lc[i] = std::max(t.log_err_indel, v);
+            if (lc[i] > t.log_err_indel && (best == -1 || lc[best] < lc[i])) best = i;
+        }
+        if (index >= 0 && best >= 0 && best != index) index = std::min(index, best);
+        else if (index < 0 && best >= 0) index = best;
+        if (index >= 0) { counts[index]++; strand[index][c.neg ? 0 : 1]++; }
+        for (int i = 0; i < n; i++) {
+            L[i][i] += lc[i];
+            for (int j = 0; j < n; j++) {
+                if (i == j) continue;
+                if (j == index) L[i][j] += log_sum(t.lf251_0 + lc[index], t.lf251_1 + t.log_err_indel);
+                else if (i == index) L[i][j] += log_sum(t.lf251_1 + lc[index], t.lf251_0 + t.log_err_indel);
+                else L[i][j] += t.log_err_indel;
+            }
+        }
+    }
+    // callIndel, VD:265-361 (variant == null)
+    auto P = posteriors(L, opt.het_rate);
+    if (total == 0) return false;
+    int m0 = 0, m1 = 0;
+    double pmax = P[0][0];
+    for (int i = 0; i < n; i++) for (int j = i; j < n; j++) {
+        double gp = P[i][j];
+        if (i != j) gp += P[j][i];
+        if (gp > pmax + 0.01) { pmax = gp; m0 = i; m1 = j; }
+    }
+    std::vector<int> idx = {0};
+    std::vector<std::string> va = {alleles[0]};
+    bool length_change = false;
+    if (m0 > 0) { va.push_back(alleles[m0]); idx.push_back(m0); if (alleles[m0].size() != alleles[0].size()) length_change = true; }
+    if (m1 > 0 && m1 != m0) {
+        va.push_back(alleles[m1]); idx.push_back(m1);
+        if (alleles[m1].size() != alleles[0].size()) length_change = true;
+        if (va.size() == 3 && alleles[m1].size() != va[1].size()) length_change = true;
+    }
+    if (!length_change) return false;  // (no input STRs in this mode)
+    out = IndelRecord();
+    out.pos = pos;
+    out.last = pos + span - 1;
+    out.alleles = va;
+    out.str = is_str;
+    out.qual = phred(P[0][0]);
+    for (int i : idx) out.counts.push_back(counts[i]);
+    out.logc.assign(idx.size(), std::vector<double>(idx.size(), 0.0));
+    for (size_t i = 0; i < idx.size(); i++) for (size_t j = 0; j < idx.size(); j++) out.logc[i][j] = L[idx[i]][idx[j]];
+    if (m1 != m0) out.called = (va.size() == 3) ? std::vector<int>{1, 2} : std::vector<int>{0, 1};
+    else out.called = {m0 == 0 ? 0 : 1};
+    double max_p = P[m0][m1];
+    if (m0 != m1) max_p += P[m1][m0];
+    out.gq = phred(1 - max_p);
+    out.depth = total;
+    if (opt.csb) {
+        // CountsHelper.getScoreStrandBiasFisher is indexed with the positions in calledAlleles (VD:356-357), i.e. into the
+        // helper's allele list, not the reduced list — restated as is.
+        auto score = [&](int i1, int i2) {
+            double p = fisher_pvalue(strand[i1][0], strand[i2][0], strand[i1][1], strand[i2][1]);
+            return std::min(100, phred(p));
+        };
+        if (out.called.size() == 1 && out.called[0] != 0) out.strand_bias = score(0, out.called[0]);
+        else if (out.called.size() == 2) out.strand_bias = score(out.called[0], out.called[1]);
+    }
+    // filter of SSVPL:263: undecided / homozygous reference / low quality
+    bool hom_ref = out.called.size() == 1 && out.called[0] == 0;
+    if (hom_ref || opt.min_quality > out.gq) return false;
+    return true;
+}
+
+}  // namespace host
+}  // namespace ngsep_b200

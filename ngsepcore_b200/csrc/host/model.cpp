@@ -1,0 +1,318 @@
+// Host read model: block-table queries, realigner mutations and admission.  See model.hpp.
+#include "model.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <unordered_map>
+
+namespace ngsep_b200 {
+namespace host {
+
+bool Genome::get(int seq, int first, int last, std::string& out) const {  // genome/ReferenceGenome.java:238-243
+    if (seq < 0 || seq >= (int)seqs.size()) return false;
+    const std::string& s = seqs[seq];
+    if (first < 1 || last > (int)s.size() || last < first - 1) return false;
+    out.assign(s, first - 1, last - first + 1);
+    for (auto& c : out) if (!std::strchr("AaCcNngGtT", c) || c == 0) c = 'N';  // sequences/DNAMaskedSequence.java:33,57-59
+    return true;
+}
+
+namespace {
+
+// Walks the blocks of a read state.  f(block_index, ref0, read0, len, op) -> true to stop.
+template <typename F>
+inline void walk(const ReadState& st, F&& f) {
+    int ref = st.first, rd = 0;
+    for (size_t i = 0; i < st.cigar.size(); i++) {
+        uint32_t v = st.cigar[i];
+        int len = cig_len(v);
+        if (f((int)i, ref, rd, len, cig_op(v))) return;
+        if (cig_ref(v)) ref += len;
+        if (cig_read(v)) rd += len;
+    }
+}
+
+// Skip decision of RA:782-795 for base j of a match block.  anchor_ok: out, whether the anchor (j == len-1 before an
+// indel) survives.  Returns true when the base is skipped.
+inline bool skipped(const HostRead& r, int i, int rd, int j, int len) {
+    const auto& cg = r.st.cigar;
+    bool prev_indel = i > 0 && op_is_indel(cig_op(cg[i - 1]));
+    bool next_indel = false;
+    int next_cons = 0;
+    if (i + 1 < (int)cg.size()) {
+        next_indel = op_is_indel(cig_op(cg[i + 1]));
+        next_cons = cig_read(cg[i + 1]) ? cig_len(cg[i + 1]) : 0;
+    }
+    int rp = rd + j;
+    if (rp < r.st.ign_s) return true;
+    if (r.L - rp <= r.st.ign_e) return true;
+    if (prev_indel && j < 2) return true;
+    if (next_indel && j < len - 1 && j >= len - 2) return true;
+    if (next_indel && j == len - 1) {
+        if (rp < 2 || r.L - rp - next_cons < 2) return true;
+        if (r.L - (rp + next_cons + 1) < r.st.ign_e) return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+void HostRead::derive() {
+    anchors.clear();
+    const auto& cg = st.cigar;
+    walk(st, [&](int i, int ref, int rd, int len, int op) {
+        (void)op;
+        if (!cig_both(cg[i]) || len == 0) return false;
+        if (i + 1 >= (int)cg.size()) return false;
+        int nop = cig_op(cg[i + 1]);
+        if (!op_is_indel(nop)) return false;
+        int j = len - 1;
+        if (rd + j >= L) return false;
+        if (skipped(*this, i, rd, j, len)) return false;
+        int nlen = cig_len(cg[i + 1]);
+        Anchor a;
+        a.pos = ref + j;
+        a.ins = nop == kOpI;
+        a.len = nlen;
+        a.last = a.pos + 1 + (a.ins ? 0 : nlen);
+        a.read_off = rd + j;
+        // TreeMap.put: a later anchor at the same reference position replaces the earlier one
+        for (auto& e : anchors) if (e.pos == a.pos) { e = a; return false; }
+        anchors.push_back(a);
+        return false;
+    });
+    std::sort(anchors.begin(), anchors.end(), [](const Anchor& x, const Anchor& y) { return x.pos < y.pos; });
+    derived = true;
+}
+
+int HostRead::read_offset(int pos) const {
+    if (pos < st.first || pos > st.last) return -1;
+    int ans = -1;
+    bool done = false;
+    walk(st, [&](int i, int ref, int rd, int len, int op) {
+        (void)op;
+        if (!cig_both(st.cigar[i])) return false;
+        if (pos < ref) { done = true; return true; }
+        if (ref + len > pos) {
+            int a = rd + pos - ref;
+            ans = (a < 0 || a >= L) ? -1 : a;
+            done = true;
+            return true;
+        }
+        return false;
+    });
+    (void)done;
+    return ans;
+}
+
+int HostRead::call_length(int pos, int* off_out) const {
+    if (pos < st.first || pos > st.last) return 0;
+    int result = 0;
+    walk(st, [&](int i, int ref, int rd, int len, int op) {
+        (void)op;
+        if (!cig_both(st.cigar[i])) return false;
+        if (pos < ref) return true;
+        if (ref + len > pos) {
+            int j = pos - ref;
+            int rp = rd + j;
+            if (rp < 0 || rp >= L) return true;
+            if (off_out) *off_out = rp;
+            if (skipped(*this, i, rd, j, len)) return true;
+            bool next_indel = i + 1 < (int)st.cigar.size() && op_is_indel(cig_op(st.cigar[i + 1]));
+            if (j == len - 1 && next_indel) {
+                uint32_t nv = st.cigar[i + 1];
+                result = cig_op(nv) == kOpI ? cig_len(nv) + 2 : 2;
+            } else {
+                result = 1;
+            }
+            return true;
+        }
+        return false;
+    });
+    return result;
+}
+
+const Anchor* HostRead::anchor_at(int pos) const {
+    for (auto& a : anchors) if (a.pos == pos) return &a;
+    return nullptr;
+}
+
+bool HostRead::has_anchor_in(int lo, int hi) const {
+    for (auto& a : anchors) if (a.pos >= lo && a.pos <= hi) return true;
+    return false;
+}
+
+bool HostRead::span_call(int pos, int last_pos, std::string& al, std::string& qs) const {
+    if (call_length(pos) == 0) return false;                 // PR:135-137
+    int rf = read_offset(pos), rl = read_offset(last_pos);
+    if (rf < 0 || rl < 0 || rl < rf) return false;
+    if (rf < st.ign_s || L - rl <= st.ign_e) return false;    // RA:1042-1044
+    al.assign((const char*)bases + rf, rl - rf + 1);
+    qs.assign((const char*)quals + rf, rl - rf + 1);
+    return true;
+}
+
+bool HostRead::move_indel(int anchor_pos, int new_pos) {
+    int disp = new_pos - anchor_pos;
+    if (disp == 0) return true;
+    auto& cg = st.cigar;
+    int n = (int)cg.size();
+    std::vector<uint32_t> out(n, 0u);
+    int next_idx = -1;
+    int ref = st.first;
+    for (int i = 0; i < n; i++) {
+        int len = cig_len(cg[i]), op = cig_op(cg[i]);
+        if (op_is_indel(op) && ref == anchor_pos + 1) {
+            if (i == 0 || i == n - 1) return false;
+            uint32_t b = cg[i - 1], a = cg[i + 1];
+            if (!cig_both(b) || cig_len(b) <= -disp) return false;
+            if (!cig_both(a) || cig_len(a) <= disp) return false;
+            out[i - 1] = cig_make(cig_len(b) + disp, cig_op(b));
+            out[i] = cg[i];
+            out[i + 1] = cig_make(cig_len(a) - disp, cig_op(a));
+            next_idx = i + 1;
+        } else if (i != next_idx) {
+            out[i] = cg[i];
+        }
+        if (cig_ref(cg[i])) ref += len;
+    }
+    if (next_idx < 0) return false;
+    cg.swap(out);
+    derived = false;
+    return true;
+}
+
+static void push_gap(std::vector<uint32_t>& v, int unk_read, int unk_ref) {
+    int diff = unk_read - unk_ref;
+    if (diff == 0) { if (unk_read > 0) v.push_back(cig_make(unk_read, kOpM)); }
+    else if (diff > 0) { v.push_back(cig_make(diff, kOpI)); if (unk_ref > 0) v.push_back(cig_make(unk_ref, kOpM)); }
+    else { v.push_back(cig_make(-diff, kOpD)); if (unk_read > 0) v.push_back(cig_make(unk_read, kOpM)); }
+}
+
+void HostRead::realign_start(int new_first, int first_match, int ref_after, int read_after) {
+    std::vector<uint32_t> v;
+    v.push_back(cig_make(first_match, kOpM));
+    int unk_read = read_after - first_match;
+    int unk_ref = ref_after - (new_first + first_match);
+    if (unk_ref < 0 || unk_read < 0) return;
+    push_gap(v, unk_read, unk_ref);
+    int rd = 0;
+    bool copy = false;
+    for (uint32_t c : st.cigar) {
+        int len = cig_len(c);
+        if (copy) v.push_back(c);
+        if (cig_read(c)) {
+            if (!copy && read_after < rd + len) { copy = true; v.push_back(cig_make(rd + len - read_after, cig_op(c))); }
+            rd += len;
+        }
+    }
+    st.first = new_first;
+    st.cigar.swap(v);
+    derived = false;
+}
+
+void HostRead::realign_end(int ref_before, int read_before, int final_ref_start, int final_match) {
+    int bp_end = L - read_before - 1;
+    std::vector<uint32_t> v;
+    int rd = 0;
+    bool copy = true;
+    for (uint32_t c : st.cigar) {
+        int len = cig_len(c);
+        if (cig_read(c)) {
+            if (copy && read_before < rd + len) {
+                int d = rd + len - read_before - 1;
+                v.push_back(cig_make(len - d, cig_op(c)));
+                copy = false;
+            }
+            rd += len;
+        }
+        if (copy) v.push_back(c);
+    }
+    int unk_ref = final_ref_start - ref_before - 1;
+    int unk_read = bp_end - final_match;
+    if (unk_ref < 0 || unk_read < 0) return;
+    push_gap(v, unk_read, unk_ref);
+    v.push_back(cig_make(final_match, kOpM));
+    st.cigar.swap(v);
+    st.last = final_ref_start + final_match - 1;
+    derived = false;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// admission
+// ------------------------------------------------------------------------------------------------------------
+std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt) {
+    std::vector<HostRead> out;
+    out.reserve((size_t)(hi - lo));
+    int filter = 0x4;
+    if (!opt.secondary) { filter |= 0x100; if (!opt.non_unique_primary) filter |= 0x1000; }
+    int64_t last_seen = -1;
+    std::vector<HostRead> prim, sec;
+    int group_start = INT_MIN;
+    std::unordered_map<int, int> per_rg;
+    auto flush = [&]() {
+        per_rg.clear();
+        for (auto* lst : {&prim, &sec}) {
+            for (auto& r : *lst) {
+                auto it = per_rg.find(r.rg);
+                if (it == per_rg.end()) per_rg[r.rg] = 1;
+                else if (opt.max_alns_per_start <= 0 || it->second < opt.max_alns_per_start) it->second++;
+                else continue;
+                // 5' end is the alignment start for + strand reads, the end for - strand reads (RA:613-644)
+                if (r.neg) { r.st.ign_e = opt.ignore5; r.st.ign_s = opt.ignore3; } else { r.st.ign_s = opt.ignore5; r.st.ign_e = opt.ignore3; }
+                out.push_back(std::move(r));
+            }
+        }
+        prim.clear();
+        sec.clear();
+    };
+    for (int64_t i = lo; i < hi; i++) {
+        int flags = b.flags[i];
+        // duplicate record (RAFR:292-306): compared with the previous record of the file, whatever its fate
+        if (last_seen >= 0 && b.name_hash) {
+            int pf = b.flags[last_seen];
+            bool same = b.first[last_seen] == b.first[i] && ((pf & 1) == (flags & 1)) && (!(pf & 1) || ((pf & 0x40) == (flags & 0x40))) &&
+                        b.name_hash[last_seen] == b.name_hash[i];
+            if (same) continue;
+        }
+        last_seen = i;
+        bool multiple;
+        int nh = b.nh ? b.nh[i] : -1;
+        if (flags & 0x100) multiple = true;
+        else if (nh > 1) multiple = true;
+        else if (nh == 1) multiple = false;
+        else multiple = b.mapq[i] < opt.min_mq;
+        if (multiple) flags |= 0x1000;
+        if (flags & filter) continue;
+        int64_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+        if (c1 <= c0) continue;  // mapped record without CIGAR: the reference's conversion throws and the record is skipped
+        HostRead r;
+        r.rec = i;
+        r.L = (int)(b.base_off[i + 1] - b.base_off[i]);
+        r.neg = (flags & 0x10) != 0;
+        r.rg = b.rg ? b.rg[i] : -1;
+        r.bases = b.bases + b.base_off[i];
+        r.quals = b.quals + b.base_off[i];
+        r.admit_first = r.st.first = b.first[i];
+        // collapse equal neighbouring operations (RA:1296-1312) and derive read/reference extents
+        int read_len = 0, ref_len = 0;
+        for (int64_t k = c0; k < c1; k++) {
+            uint32_t v = b.cigar[k];
+            if (!r.st.cigar.empty() && cig_op(r.st.cigar.back()) == cig_op(v)) r.st.cigar.back() = cig_make(cig_len(r.st.cigar.back()) + cig_len(v), cig_op(v));
+            else if (cig_len(v) > 0 || true) r.st.cigar.push_back(v);
+            if (cig_read(v)) read_len += cig_len(v);
+            if (cig_ref(v)) ref_len += cig_len(v);
+        }
+        if (read_len != r.L || r.L == 0) continue;  // SEQ '*' or inconsistent with the CIGAR: outside the supported input
+        r.st.last = r.st.first + ref_len - 1;
+        if (opt.query_first > r.st.last) continue;  // APG:316
+        if (r.st.first != group_start) { flush(); group_start = r.st.first; }
+        if (flags & 0x100) sec.push_back(std::move(r)); else prim.push_back(std::move(r));
+    }
+    flush();
+    return out;
+}
+
+}  // namespace host
+}  // namespace ngsep_b200

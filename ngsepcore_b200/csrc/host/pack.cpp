@@ -1,0 +1,91 @@
+// Tile packer: host reads (with their realigner versions) -> the header / payload layout of include/ngsep_pileup.h.
+#include <algorithm>
+#include <climits>
+#include <cstring>
+
+#include "pipeline.hpp"
+
+namespace ngsep_b200 {
+namespace host {
+
+namespace {
+
+struct CodeLut {
+    uint8_t v[256];
+    CodeLut() {
+        std::memset(v, 4, sizeof(v));
+        v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3;
+    }
+};
+const CodeLut& lut() { static const CodeLut l; return l; }
+
+inline int ref_last_of(const ReadState& st) {
+    int ref = st.first;
+    for (uint32_t c : st.cigar) if (cig_ref(c)) ref += cig_len(c);
+    return ref - 1;
+}
+
+void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from, int to, PackedTile& out) {
+    const CodeLut& L = lut();
+    const int len = r.L;
+    const int nc = (int)st.cigar.size();
+    if (len > 0xffff || nc > 0xff) return;  // rejected earlier by the detector; kept as a guard
+    bool has_n = false;
+    for (int i = 0; i < len; i++) if (L.v[r.bases[i]] > 3) { has_n = true; break; }
+    ngsep_read_hdr h;
+    h.first = r.admit_first;
+    h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
+    h.ign_start = (int16_t)st.ign_s;
+    h.ign_end = (int16_t)st.ign_e;
+    h.off = (uint32_t)out.payload.size();
+    out.hdr.push_back(h);
+    auto& p = out.payload;
+    if (windowed) { p.push_back((uint32_t)from); p.push_back((uint32_t)to); p.push_back((uint32_t)st.first); }
+    for (uint32_t c : st.cigar) p.push_back(c);
+    size_t b2 = p.size();
+    p.resize(b2 + (len + 15) / 16, 0u);
+    for (int i = 0; i < len; i++) p[b2 + (i >> 4)] |= (uint32_t)(L.v[r.bases[i]] & 3u) << ((i & 15) * 2);
+    if (has_n) {
+        size_t nm = p.size();
+        p.resize(nm + (len + 31) / 32, 0u);
+        for (int i = 0; i < len; i++) if (L.v[r.bases[i]] > 3) p[nm + (i >> 5)] |= 1u << (i & 31);
+    }
+    size_t q = p.size();
+    p.resize(q + (len + 3) / 4, 0u);
+    std::memcpy(&p[q], r.quals, (size_t)len);
+    out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
+    out.max_back = std::max(out.max_back, r.admit_first - st.first);
+    out.aligned_bases += (uint64_t)len;
+}
+
+}  // namespace
+
+void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out) {
+    out.hdr.clear();
+    out.payload.clear();
+    out.max_span = 1;
+    out.max_back = 0;
+    out.aligned_bases = 0;
+    out.hdr.reserve(hi - lo);
+    for (size_t i = lo; i < hi; i++) {
+        const HostRead& r = reads[i];
+        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, false, 0, 0, out); continue; }
+        for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, out);
+        emit_record(r, r.st, true, r.cur_from, INT_MAX, out);
+    }
+}
+
+ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
+    ngsep_tile t;
+    t.seq_idx = seq_idx; t.tile_first = first; t.tile_last = last;
+    t.n_reads = (int)hdr.size();
+    t.max_span = max_span; t.max_back = max_back;
+    t.n_words = payload.size();
+    t.hdr = hdr.data();
+    t.payload = payload.data();
+    t.sample = nullptr;
+    return t;
+}
+
+}  // namespace host
+}  // namespace ngsep_b200

@@ -1,0 +1,157 @@
+"""ctypes binding of libngsep_host.so (include/ngsep_host.h): the host pipeline around the device C ABI.
+
+``Detector`` mirrors the public surface of the reference's SingleSampleVariantsDetector for this path
+(reference: src/ngsep/discovery/SingleSampleVariantsDetector.java — option setters :141-560, run() :589-656):
+same option names, same defaults, VCF text out.  There is no CPU fallback: without the built libraries or a B200
+every call raises NgsepError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .capi import HDR_DTYPE, NgsepError
+from .simulate import AlignmentBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
+EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
+           "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_host_pack", "ngsep_host_free"]
+
+
+class HostBatch(C.Structure):
+    _fields_ = [("n", C.c_int64), ("seq_idx", C.c_void_p), ("first", C.c_void_p), ("flags", C.c_void_p), ("mapq", C.c_void_p),
+                ("rg", C.c_void_p), ("nh", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p), ("base_off", C.c_void_p),
+                ("bases", C.c_void_p), ("quals", C.c_void_p), ("name_hash", C.c_void_p)]
+
+
+class DetectorOptions(C.Structure):
+    _fields_ = [("sample_id", C.c_char_p), ("ploidy", C.c_int32), ("print_sample_ploidy", C.c_int32), ("min_mq", C.c_int32),
+                ("query_seq", C.c_char_p), ("query_first", C.c_int32), ("query_last", C.c_int32), ("ignore_lower_case_ref", C.c_int32),
+                ("max_alns_per_start_pos", C.c_int32), ("process_non_unique_primary", C.c_int32), ("process_secondary", C.c_int32),
+                ("ignore5", C.c_int32), ("ignore3", C.c_int32), ("het_rate", C.c_double), ("het_rate_set", C.c_int32),
+                ("max_base_qs", C.c_int32), ("min_quality", C.c_int32), ("call_embedded_snvs", C.c_int32), ("calc_strand_bias", C.c_int32),
+                ("device", C.c_int32), ("tile_len", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("host_only", C.c_int32)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("records", "admitted", "versions", "events", "indel_calls", "snv_calls", "covered_positions",
+                                          "candidate_positions", "aligned_bases", "tiles", "kernel_launches")] + \
+               [(n, C.c_double) for n in ("kernel_ms", "prepass_s", "pack_s", "device_s", "total_s")]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NgsepError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    lib.ngsep_detector_options_default.argtypes = [C.POINTER(DetectorOptions)]
+    lib.ngsep_ssvd_create.argtypes = [C.POINTER(DetectorOptions), C.POINTER(C.c_void_p)]
+    lib.ngsep_ssvd_destroy.argtypes = [C.c_void_p]
+    lib.ngsep_ssvd_error.argtypes = [C.c_void_p]
+    lib.ngsep_ssvd_error.restype = C.c_char_p
+    lib.ngsep_ssvd_set_genome.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]
+    lib.ngsep_ssvd_run.argtypes = [C.c_void_p, C.POINTER(HostBatch), C.c_int]
+    lib.ngsep_ssvd_vcf.argtypes = [C.c_void_p, C.POINTER(C.c_size_t)]
+    lib.ngsep_ssvd_vcf.restype = C.c_void_p
+    lib.ngsep_ssvd_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
+    lib.ngsep_host_pack.argtypes = [C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.ngsep_host_free.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _host_batch(b: AlignmentBatch):
+    keep = [np.ascontiguousarray(b.seq_idx, np.int32), np.ascontiguousarray(b.first, np.int32), np.ascontiguousarray(b.flags, np.uint16),
+            np.ascontiguousarray(b.mapq, np.uint8), np.ascontiguousarray(b.rg, np.int16), np.ascontiguousarray(b.nh, np.int16),
+            np.ascontiguousarray(b.cigar_off, np.int64), np.ascontiguousarray(b.cigar, np.uint32), np.ascontiguousarray(b.base_off, np.int64),
+            np.ascontiguousarray(b.bases, np.uint8), np.ascontiguousarray(b.quals, np.uint8)]
+    hb = HostBatch(b.n, *[a.ctypes.data for a in keep], None)
+    return hb, keep
+
+
+def pack_sequence(batch: AlignmentBatch, seq_idx: int, min_mq: int = 20, max_alns_per_start: int = 5, ignore5: int = 0, ignore3: int = 0):
+    """C++ admission + packing of one sequence (no event pre-pass) -> (hdr, payload, max_span, aligned_bases)."""
+    lib = load_library()
+    hb, keep = _host_batch(batch)
+    hdr_p, pay_p = C.c_void_p(), C.c_void_p()
+    n_reads, n_words, span, bases = C.c_int64(), C.c_uint64(), C.c_int(), C.c_uint64()
+    rc = lib.ngsep_host_pack(C.byref(hb), seq_idx, min_mq, max_alns_per_start, ignore5, ignore3, C.byref(hdr_p), C.byref(pay_p),
+                             C.byref(n_reads), C.byref(n_words), C.byref(span), C.byref(bases))
+    if rc != 0:
+        raise NgsepError(f"ngsep_host_pack failed ({rc})")
+    hdr = np.ctypeslib.as_array(C.cast(hdr_p, C.POINTER(C.c_uint8)), shape=(n_reads.value * 16,)).view(HDR_DTYPE).copy() if n_reads.value else np.zeros(0, HDR_DTYPE)
+    pay = np.ctypeslib.as_array(C.cast(pay_p, C.POINTER(C.c_uint32)), shape=(n_words.value,)).copy() if n_words.value else np.zeros(0, np.uint32)
+    lib.ngsep_host_free(hdr_p)
+    lib.ngsep_host_free(pay_p)
+    return hdr, pay, span.value, bases.value
+
+
+class Detector:
+    """GPU drop-in for SingleSampleVariantsDetector (discovery mode).  Keyword names are the reference's option ids."""
+
+    def __init__(self, sampleId: str = "Sample", ploidy: int = 2, psp: bool = False, minMQ: int = 20, querySeq: str | None = None,
+                 first: int = 0, last: int = 1000000000, ignoreLowerCaseRef: bool = False, maxAlnsPerStartPos: int = 5, p: bool = False,
+                 s: bool = False, ignore5: int = 0, ignore3: int = 0, h: float | None = None, maxBaseQS: int = 30, minQuality: int = 40,
+                 embeddedSNVs: bool = False, csb: bool = False, device: int = 0, tile_len: int = 0, shard: int = 0, n_shards: int = 1, host_only: bool = False):
+        self.lib = load_library()
+        o = DetectorOptions()
+        self.lib.ngsep_detector_options_default(C.byref(o))
+        self._sid = sampleId.encode()
+        self._qs = querySeq.encode() if querySeq else None
+        o.sample_id, o.ploidy, o.print_sample_ploidy, o.min_mq = self._sid, ploidy, int(psp), minMQ
+        o.query_seq, o.query_first, o.query_last = self._qs, first, last
+        o.ignore_lower_case_ref, o.max_alns_per_start_pos = int(ignoreLowerCaseRef), maxAlnsPerStartPos
+        o.process_non_unique_primary, o.process_secondary, o.ignore5, o.ignore3 = int(p), int(s), ignore5, ignore3
+        if h is not None:
+            o.het_rate, o.het_rate_set = h, 1
+        o.max_base_qs, o.min_quality, o.call_embedded_snvs, o.calc_strand_bias = maxBaseQS, minQuality, int(embeddedSNVs), int(csb)
+        o.device, o.tile_len, o.shard, o.n_shards, o.host_only = device, tile_len, shard, n_shards, int(host_only)
+        self.h = C.c_void_p()
+        if self.lib.ngsep_ssvd_create(C.byref(o), C.byref(self.h)) != 0:
+            raise NgsepError("ngsep_ssvd_create failed")
+        self._keep = []
+
+    def set_genome(self, genome: dict) -> None:
+        names = [n.encode() for n in genome]
+        arrs = [np.ascontiguousarray(v, np.uint8) for v in genome.values()]
+        n = len(names)
+        c_names = (C.c_char_p * n)(*names)
+        c_len = (C.c_int64 * n)(*[a.size for a in arrs])
+        c_bases = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        rc = self.lib.ngsep_ssvd_set_genome(self.h, n, c_names, c_len, c_bases)
+        if rc != 0:
+            raise NgsepError(f"ngsep_ssvd_set_genome failed ({rc})")
+
+    def run(self, batch: AlignmentBatch, with_header: bool = True) -> str:
+        hb, keep = _host_batch(batch)
+        rc = self.lib.ngsep_ssvd_run(self.h, C.byref(hb), int(with_header))
+        if rc != 0:
+            raise NgsepError(f"ngsep_ssvd_run failed ({rc}): {self.lib.ngsep_ssvd_error(self.h).decode()}")
+        n = C.c_size_t()
+        p = self.lib.ngsep_ssvd_vcf(self.h, C.byref(n))
+        return C.string_at(p, n.value).decode()
+
+    def stats(self) -> RunStats:
+        s = RunStats()
+        self.lib.ngsep_ssvd_stats(self.h, C.byref(s))
+        return s
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.ngsep_ssvd_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,66 @@
+"""CPU-side checks of the C++ host pipeline (libngsep_host.so) that need no GPU: packer equality with the numpy
+packer, and the event pre-pass (indel realigner + host indel/STR caller) against the oracle's indel records."""
+import numpy as np
+import pytest
+
+from ngsepcore_b200 import hostapi, pypack, simulate
+from tests import oracle_util as ou
+
+
+def test_host_symbols():
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "ngsep_host.h")).read()
+    declared = set(re.findall(r"\b(ngsep_[a-z_]+)\s*\(", hdr))
+    assert declared == set(hostapi.EXPORTS)
+    lib = hostapi.load_library()
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_cpp_packer_equals_numpy_packer():
+    genome, batch, _ = simulate.simulate(contigs=[("a", 30000), ("b", 20000)], depth=12, seeds=(3, 4, 5), n_frac=0.02, low_mapq_frac=0.1)
+    for ci in range(2):
+        idx = pypack.admit(batch, max_alns_per_start=2)
+        idx = idx[batch.seq_idx[idx] == ci]
+        h1, p1, s1 = pypack.pack_tile(batch, idx, ignore5=2, ignore3=4)
+        h2, p2, s2, nb = hostapi.pack_sequence(batch, ci, max_alns_per_start=2, ignore5=2, ignore3=4)
+        assert s1 == s2 and nb == int((h1["meta"] & 0xFFFF).sum())
+        assert np.array_equal(h1, h2)
+        assert np.array_equal(p1, p2)
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (1, dict(indel_rate=1e-3, depth=30)),
+    (2, dict(indel_rate=2e-3, depth=12, indel_jitter=0.6)),
+    (3, dict(indel_rate=1e-3, depth=45, ungapped_end_bp=12)),
+])
+def test_event_prepass_indel_records_match_oracle(oracle, tmp_path, seed, kw):
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 120000)], seeds=(seed * 10, seed * 10 + 1, seed * 10 + 2), **kw)
+    fa, sam = str(tmp_path / "r.fa"), str(tmp_path / "r.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam)
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    det = hostapi.Detector(host_only=True)
+    det.set_genome(genome)
+    got_lines = det.run(batch, with_header=False).splitlines()
+    assert len(want_lines) > 20
+    assert got_lines == want_lines
+    assert det.stats().events >= len(want_lines)
+
+
+def test_header_text_matches_oracle(oracle, tmp_path):
+    genome, batch, _ = simulate.simulate(contigs=[("c", 3000)], depth=3)
+    fa, sam = str(tmp_path / "r.fa"), str(tmp_path / "r.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-sampleId", "S1", "-psp"))
+    det = hostapi.Detector(host_only=True, sampleId="S1", psp=True)
+    det.set_genome(genome)
+    got = det.run(batch)
+    hdr = lambda t: [l for l in t.splitlines() if l.startswith("#")]
+    assert hdr(got) == hdr(want)
+    # fixed parts of the header are the reference's own (training/yeastDemo_...vcf.gz carries the same lines)
+    assert hdr(got)[0] == "##fileformat=VCFv4.2"
+    assert '##FORMAT=<ID=BSDP,Number=4,Type=Integer,Description="Number of base calls (depth) for the 4 nucleotides in called SNVs sorted as A,C,G,T">' in hdr(got)
