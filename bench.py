@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — genotyped positions/s of the pileup / SNVQ hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host cores
+
+A "step" = one pass of the hot path over the whole workload: BASELINE configs[1], a yeast-like 12.16 Mb genome at
+30x (2x100 bp), simulated with planted SNVs/indels (ngsepcore_b200/simulate.py), one region tile per sequence.
+  value  = positions with >= 1 covering admitted read / device time, tiles resident in HBM (CUDA events on the context
+           stream; every tile's payload is read from HBM each step: 540 MB per step > 126 MB L2);
+  e2e    = the same metric through the C ABI with HOST buffers: ngsep_tile_submit (H2D from page-locked memory +
+           kernels) + ngsep_tile_fetch (D2H of the calls) per tile, all inside the timed region;
+  roofline.achieved = algorithmic bytes (sum_reads(16 + 4 n_cigar + ceil(L/4) + L) + 1 B/reference
+           base + 64 B/call) / time spent in k_pileup_windows (CUDA events around every launch, summed).
+N > 1 (torchrun): every rank owns one GPU and an independent, equally sized region shard (weak scaling, no data-path
+collective — SURVEY.md 8e); value = positions of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genotyped_positions_per_sec"
+UNIT = "positions/s"
+WORKLOAD = "yeast-like 12.16 Mb x 30x, 2x100 bp simulated alignments with planted SNVs/indels (BASELINE configs[1]), one tile per sequence"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _workload(rank: int, depth: float, scale: float):
+    from ngsepcore_b200 import simulate
+    contigs = simulate.YEAST_CONTIGS
+    if scale != 1.0:
+        contigs = [(n, max(20000, int(l * scale))) for n, l in contigs]
+    seeds = (1001 + 17 * rank, 2002 + 17 * rank, 3003 + 17 * rank)
+    return simulate.simulate(contigs=contigs, depth=depth, seeds=seeds)
+
+
+def _algorithmic_bytes(batch, admitted_hdrs, genome_len, n_calls):
+    """per admitted record 16 + 4 n_cigar + ceil(L/4) + L, + 1 byte per reference base + 64 per call."""
+    tot = 0
+    for hdr in admitted_hdrs:
+        L = (hdr["meta"] & 0xFFFF).astype(np.int64)
+        nc = ((hdr["meta"] >> 16) & 0xFF).astype(np.int64)
+        tot += int((16 + 4 * nc + (L + 3) // 4 + L).sum())
+    return tot + genome_len + 64 * n_calls
+
+
+class _ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f:
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 8:
+                continue
+            try:
+                sm.append(float(t[1])); mx.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def _dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    return rank, world, local, dist
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CUDA arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    rank, world, local, dist = _dist_setup(args.gpus)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from ngsepcore_b200 import capi, hostapi
+    device = local if world > 1 else 0
+
+    t_sim = time.time()
+    genome, batch, _ = _workload(rank, args.depth, args.scale)
+    names = list(genome)
+    t_sim = time.time() - t_sim
+
+    # host stages once (admission + event pre-pass + packing): the very tiles the detector submits
+    t_pack = time.time()
+    det = hostapi.Detector(device=device, host_only=True)
+    det.set_genome(genome)
+    tiles = [det.pack(batch, ci) for ci in range(len(names))]
+    t_pack = time.time() - t_pack
+    for t in tiles:  # page-lock the host buffers, as a JVM host does for its direct ByteBuffers
+        if t["hdr"].size:
+            capi.host_register(t["hdr"]); capi.host_register(t["payload"])
+    h2d_bytes = sum(t["hdr"].nbytes + t["payload"].nbytes for t in tiles)
+    aligned_bases = sum(t["aligned_bases"] for t in tiles)
+    genome_len = sum(len(v) for v in genome.values())
+
+    ctx = capi.Context(device=device)
+    for ci, n in enumerate(names):
+        ctx.ref_upload(ci, genome[n])
+    slots = []
+    for ci, t in enumerate(tiles):
+        if t["hdr"].size:
+            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["max_span"], t["max_back"]))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- resident (HBM) measurement: every tile of the genome in ONE launch per step ---------------------------------------
+    for _ in range(max(3, args.warmup)):
+        ctx.resident_run(-1)
+    st = ctx.resident_stats()
+    covered, calls, cand = st.covered_positions, st.calls, st.candidate_positions
+    launches = st.kernel_launches
+    sampler = _ClockSampler(device) if rank == 0 else None
+    barrier()
+    pileup_ms = 0.0
+    step_ms = []
+    for _ in range(args.steps):
+        ctx.timer_start()
+        ctx.resident_run(-1)
+        step_ms.append(ctx.timer_stop())
+        pileup_ms += ctx.resident_stats().kernel_ms   # device time of the launch itself (events around it on the same stream)
+    barrier()
+    total_ms = float(sum(step_ms))
+    # ---- end-to-end through the C ABI with host buffers ------------------------------------------------------------------
+    def e2e_step():
+        n_calls = 0
+        for ci, t in enumerate(tiles):
+            if not t["hdr"].size:
+                continue
+            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["max_span"], t["max_back"])
+            c, _, st = ctx.fetch(sort=False)
+            n_calls += len(c)
+        return n_calls
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_calls_e2e = e2e_step()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- whole detector from decoded records (host stages + device + VCF text), informational --------------------------------
+    det2 = hostapi.Detector(device=device)
+    det2.set_genome(genome)
+    t0 = time.perf_counter()
+    vcf = det2.run(batch)
+    pipeline_s = time.perf_counter() - t0
+    st2 = det2.stats()
+
+    if dist is not None:
+        import torch
+        v = torch.tensor([total_ms, e2e_s, pileup_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, pileup_ms = [float(x) for x in v.tolist()]
+        w = torch.tensor([covered, aligned_bases, h2d_bytes, calls, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        covered_all, bases_all, h2d_all, calls_all, launches_all = [float(x) for x in w.tolist()]
+    else:
+        covered_all, bases_all, h2d_all, calls_all, launches_all = covered, aligned_bases, h2d_bytes, calls, launches
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        alg_bytes = _algorithmic_bytes(batch, [t["hdr"] for t in tiles], genome_len, calls)
+        ms_per_step = total_ms / args.steps
+        achieved = alg_bytes * args.steps / (pileup_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": covered_all / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "depth": args.depth, "genome_bp": genome_len, "reads": int(batch.n), "tiles": len(slots),
+                       "genotyped_positions_per_gpu": int(covered), "candidate_positions": int(cand), "calls": int(calls),
+                       "l2": "inputs larger than L2 (%.0f MB of tile payload read per step)" % (h2d_bytes / 1e6),
+                       "parallelism": f"region shards x{world}, no collective"},
+            "aligned_bases_per_sec": bases_all / (ms_per_step / 1e3),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_pileup_windows", "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": pileup_ms / args.steps,
+                         "launches_per_step": int(launches), "peak_source": peak_src},
+            "e2e": {"value": covered_all * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+                    "d2h_bytes_per_step": int(calls_all * 224 + 36 * len(slots) * world), "ms_per_step": e2e_s / args.steps * 1e3},
+            "pipeline": {"value": st2.covered_positions / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s,
+                         "pack_s": st2.pack_s, "device_s": st2.device_s, "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
+                         "note": "whole detector from decoded records on 1 host thread: admission + realigner pre-pass + packing + device + VCF text"},
+            "gpu_launches": int(launches_all * args.steps),
+            "clocks": clocks,
+            "host": {"simulate_s": t_sim, "pack_s": t_pack},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(genome, batch, names)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (C++ port of the reference's Java path) on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def _sample_batch(batch, names, max_bp):
+    """First sequences of the workload up to ~max_bp reference bases."""
+    take, tot = [], 0
+    for ci, l in enumerate(batch.contig_lengths):
+        if tot and tot + l > max_bp:
+            break
+        take.append(ci); tot += l
+    idx = np.nonzero(np.isin(batch.seq_idx, take))[0]
+    return batch.select(idx), take, tot
+
+
+def cpu_baseline(genome, batch, names, max_bp: int = 1_500_000):
+    """Oracle, one thread, on a bounded sample of the same workload (about 10-30 s of CPU work)."""
+    from ngsepcore_b200 import simulate
+    from tests import oracle_util as ou
+    sub, take, tot = _sample_batch(batch, names, max_bp)
+    with tempfile.TemporaryDirectory() as d:
+        fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+        simulate.write_fasta(fa, genome)
+        simulate.write_sam(sam, sub)
+        _, _, gp, sec = ou.run_ssvd(ou.load_oracle(), fa, sam)
+    return {"value": gp / sec, "unit": UNIT, "cores": 1, "kind": "port", "seconds": sec,
+            "sample": f"first {len(take)} sequences of the workload ({tot} bp, {sub.n} records), C++ restatement of NGSEP 4.3.2 (no JVM in the image)"}
+
+
+def _ref_worker(job):
+    fa, sam, seq, first, last = job
+    from tests import oracle_util as ou
+    args = ("-querySeq", seq, "-first", str(first), "-last", str(last))
+    _, _, gp, sec = ou.run_ssvd(ou.load_oracle(), fa, sam, args=args)
+    return gp, sec
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on all host cores.  The reference's only parallel mode is region
+    splitting (-querySeq/-first/-last): the sample is cut into one region per core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build()
+    from ngsepcore_b200 import simulate
+    genome, batch, _ = _workload(0, args.depth, args.scale)
+    names = list(genome)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    sub, take, tot = _sample_batch(batch, names, args.reference_sample_bp)
+    d = tempfile.mkdtemp(prefix="ngsep_ref_")
+    fa = os.path.join(d, "r.fa")
+    simulate.write_fasta(fa, genome)
+    # one region per core, balanced by reference length; each worker reads only the records that can reach its region
+    per = max(20000, -(-tot // cores))
+    jobs = []
+    for ci in take:
+        L = batch.contig_lengths[ci]
+        sel = np.nonzero(sub.seq_idx == ci)[0]
+        first_arr = sub.first[sel]
+        for f in range(1, L + 1, per):
+            l = min(L, f + per - 1)
+            keep = sel[(first_arr >= f - 1000) & (first_arr <= l)]
+            sam = os.path.join(d, f"{names[ci]}_{f}.sam")
+            simulate.write_sam(sam, sub.select(keep))
+            jobs.append((fa, sam, names[ci], f, l))
+    pool = mp.get_context("fork").Pool(cores)
+    times, positions = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            positions = sum(r[0] for r in res)
+    pool.close()
+    total = sum(times)
+    value = positions * len(times) / total
+    sample = f"first {len(take)} sequences of the workload ({tot} bp, {sub.n} records) cut into {len(jobs)} regions, oracle port on {cores} processes"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "depth": args.depth, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ngsepcore_b200", choices=["ngsepcore_b200", "reference"])
+    ap.add_argument("--depth", type=float, default=30.0)
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the sequence lengths (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-sample-bp", type=int, default=4_000_000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

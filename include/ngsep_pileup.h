@@ -124,7 +124,9 @@ typedef struct ngsep_tile_stats {
     uint64_t candidate_positions;/* positions that went through the exact SNVQ evaluation                */
     uint64_t calls;              /* records written                                                      */
     uint64_t aligned_bases;      /* sum of read lengths of the tile's records                            */
-    float kernel_ms;             /* device time of the tile's kernels (CUDA events on the context stream) */
+    float kernel_ms;             /* device time of the launch that processed the tile (CUDA events on the context stream;
+                                    a batched run reports the whole batch's launch for every tile in it)  */
+    float pileup_ms;             /* of which: the window kernel (k_pileup_windows)                        */
     uint32_t kernel_launches;    /* kernels launched for the tile                                        */
 } ngsep_tile_stats;
 
@@ -146,10 +148,25 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
  * NGSEP_F_EMIT_ALL is set, receives [tile_last-tile_first+1][5] = A,C,G,T,DP. */
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 
-/* Device-resident variant for measurement: stage a tile in HBM once, then run the kernels over it repeatedly
- * without host<->device copies (bench.py "value"); results are fetched with ngsep_tile_fetch as usual. */
-int ngsep_tile_stage(void* ctx, const ngsep_tile* tile);
-int ngsep_tile_run_staged(void* ctx);
+/* Device-resident tiles: stage any number of tiles in HBM once (slots 1..n; slot 0 is the submit/fetch slot), then
+ * run the kernels over them repeatedly without host<->device copies.  ngsep_resident_run(slot = -1) walks the windows
+ * of EVERY resident tile in ONE kernel launch on the context stream (all sequences of a genome = one launch); results
+ * are read per slot with ngsep_resident_fetch, or summed over the batch with ngsep_resident_stats (kernel_ms = device
+ * time of that one launch, CUDA events on the context stream). */
+int ngsep_resident_add(void* ctx, const ngsep_tile* tile, int* slot);
+int ngsep_resident_clear(void* ctx);
+int ngsep_resident_run(void* ctx, int slot);
+int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
+int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
+
+/* CUDA-event stopwatch on the context stream (the stream every kernel of this context is launched on). */
+int ngsep_timer_start(void* ctx);
+int ngsep_timer_stop(void* ctx, float* elapsed_ms);   /* synchronises the stream */
+
+/* Page-locks / releases a caller-owned host buffer (what a JVM host does for its direct ByteBuffers) so that
+ * ngsep_tile_submit copies asynchronously at full PCIe rate. */
+int ngsep_host_register(void* ptr, size_t bytes);
+int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
 int ngsep_abi_version(void);

@@ -36,7 +36,7 @@ class Tile(C.Structure):
 
 class TileStats(C.Structure):
     _fields_ = [("covered_positions", C.c_uint64), ("candidate_positions", C.c_uint64), ("calls", C.c_uint64),
-                ("aligned_bases", C.c_uint64), ("kernel_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+                ("aligned_bases", C.c_uint64), ("kernel_ms", C.c_float), ("pileup_ms", C.c_float), ("kernel_launches", C.c_uint32)]
 
 
 HDR_DTYPE = np.dtype([("first", "<i4"), ("meta", "<u4"), ("ign_start", "<i2"), ("ign_end", "<i2"), ("off", "<u4")])
@@ -45,7 +45,8 @@ CALL_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)
                        ("a0", "i1"), ("a1", "i1"), ("ref", "i1"), ("kind", "i1"), ("sample", "<i4")], align=True)
 
 EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_ref_upload", "ngsep_tile_submit",
-           "ngsep_tile_fetch", "ngsep_tile_stage", "ngsep_tile_run_staged", "ngsep_abi_version", "ngsep_built_sm"]
+           "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
+           "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm"]
 
 _lib = None
 
@@ -64,11 +65,29 @@ def load_library() -> C.CDLL:
     lib.ngsep_last_error.restype = C.c_char_p
     lib.ngsep_ref_upload.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.ngsep_tile_submit.argtypes = [C.c_void_p, C.POINTER(Tile)]
-    lib.ngsep_tile_stage.argtypes = [C.c_void_p, C.POINTER(Tile)]
-    lib.ngsep_tile_run_staged.argtypes = [C.c_void_p]
+    lib.ngsep_resident_add.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(C.c_int)]
+    lib.ngsep_resident_clear.argtypes = [C.c_void_p]
+    lib.ngsep_resident_run.argtypes = [C.c_void_p, C.c_int]
+    lib.ngsep_resident_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(TileStats)]
+    lib.ngsep_resident_stats.argtypes = [C.c_void_p, C.POINTER(TileStats)]
+    lib.ngsep_timer_start.argtypes = [C.c_void_p]
+    lib.ngsep_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    lib.ngsep_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    lib.ngsep_host_unregister.argtypes = [C.c_void_p]
     lib.ngsep_tile_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(TileStats)]
     _lib = lib
     return lib
+
+
+def host_register(arr: np.ndarray) -> None:
+    """Page-locks a numpy buffer (ngsep_host_register)."""
+    rc = load_library().ngsep_host_register(arr.ctypes.data, arr.nbytes)
+    if rc != 0:
+        raise NgsepError(f"ngsep_host_register failed ({rc}): {load_library().ngsep_last_error(None).decode()}")
+
+
+def host_unregister(arr: np.ndarray) -> None:
+    load_library().ngsep_host_unregister(arr.ctypes.data)
 
 
 def host_tables(het_rate: float = 0.001) -> np.ndarray:
@@ -101,6 +120,7 @@ class Context:
         if rc != 0:
             raise NgsepError(f"ngsep_ctx_create failed ({rc}): {self.lib.ngsep_last_error(None).decode()}")
         self._keep = []
+        self._slot_npos = {}
 
     def _check(self, rc: int, what: str) -> None:
         if rc != 0:
@@ -122,29 +142,52 @@ class Context:
         self._n_pos = tile_last - tile_first + 1
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
 
-    def stage(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> None:
+    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> int:
+        """Stages a tile in HBM for repeated runs; returns its slot."""
         t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back)
-        self._n_pos = tile_last - tile_first + 1
-        self._check(self.lib.ngsep_tile_stage(self.h, C.byref(t)), "ngsep_tile_stage")
+        slot = C.c_int(0)
+        self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
+        self._slot_npos[slot.value] = tile_last - tile_first + 1
+        return slot.value
 
-    def run_staged(self) -> None:
-        self._check(self.lib.ngsep_tile_run_staged(self.h), "ngsep_tile_run_staged")
+    def resident_run(self, slot: int = -1) -> None:
+        self._check(self.lib.ngsep_resident_run(self.h, slot), "ngsep_resident_run")
 
-    def fetch(self, cap: int = 1 << 16, want_counts: bool = False):
+    def resident_stats(self) -> TileStats:
+        """Counters of the last batched run summed over every resident tile; kernel_ms = device time of its one launch."""
+        st = TileStats()
+        self._check(self.lib.ngsep_resident_stats(self.h, C.byref(st)), "ngsep_resident_stats")
+        return st
+
+    def resident_clear(self) -> None:
+        self._check(self.lib.ngsep_resident_clear(self.h), "ngsep_resident_clear")
+        self._slot_npos = {}
+
+    def timer_start(self) -> None:
+        self._check(self.lib.ngsep_timer_start(self.h), "ngsep_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._check(self.lib.ngsep_timer_stop(self.h, C.byref(ms)), "ngsep_timer_stop")
+        return ms.value
+
+    def fetch(self, cap: int = 1 << 16, want_counts: bool = False, slot: int = 0, sort: bool = True):
         """Returns (calls structured array sorted by pos, counts [n_pos,5] or None, TileStats)."""
         stats = TileStats()
-        counts = np.zeros((self._n_pos, 5), np.int32) if want_counts else None
+        n_pos = self._n_pos if slot == 0 else self._slot_npos[slot]
+        counts = np.zeros((n_pos, 5), np.int32) if want_counts else None
         while True:
             out = np.zeros(cap, CALL_DTYPE)
             n = C.c_size_t(0)
-            rc = self.lib.ngsep_tile_fetch(self.h, out.ctypes.data, cap, C.byref(n), counts.ctypes.data if want_counts else None, C.byref(stats))
+            rc = self.lib.ngsep_resident_fetch(self.h, slot, out.ctypes.data, cap, C.byref(n), counts.ctypes.data if want_counts else None, C.byref(stats))
             if rc == -6 and n.value > cap:
                 cap = int(n.value) + 16
                 continue
             self._check(rc, "ngsep_tile_fetch")
             break
         calls = out[: n.value]
-        calls = calls[np.argsort(calls["pos"], kind="stable")]
+        if sort:
+            calls = calls[np.argsort(calls["pos"], kind="stable")]
         return calls, counts, stats
 
     def close(self) -> None:

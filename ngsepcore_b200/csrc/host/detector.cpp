@@ -78,10 +78,13 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     return NGSEP_OK;
 }
 
-int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) {
-    const std::string& chrom = genome_->names[seq];
+int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan) {
     const int seq_len = (int)genome_->seqs[seq].size();
     double t0 = now_s();
+    std::vector<HostRead>& reads = plan.reads;
+    std::vector<IndelRecord>& indels = plan.indels;
+    std::set<int>& suppressed = plan.suppressed;
+    std::vector<std::pair<int, int>>& embedded = plan.embedded;
     // ---- 1. admission -------------------------------------------------------------------------------------------
     AdmissionOptions ao;
     ao.min_mq = opt_.min_mq; ao.max_alns_per_start = opt_.max_alns_per_start; ao.secondary = opt_.secondary;
@@ -91,12 +94,12 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
         while (q_hi > q_lo && b.first[q_hi - 1] > opt_.query_last) q_hi--;
     }
     if (opt_.has_query) ao.query_first = opt_.query_first;
-    std::vector<HostRead> reads = admit_sequence(b, q_lo, q_hi, ao);
+    reads = admit_sequence(b, q_lo, q_hi, ao);
     for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { err_ = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
     stats_.admitted += reads.size();
-    if (reads.empty()) return NGSEP_OK;
-    const int win_first = opt_.has_query ? std::max(1, opt_.query_first) : 1;
-    const int win_last = opt_.has_query ? std::min(seq_len, opt_.query_last) : seq_len;
+    if (reads.empty()) { plan.win_first = 1; plan.win_last = seq_len; return NGSEP_OK; }
+    const int win_first = plan.win_first = opt_.has_query ? std::max(1, opt_.query_first) : 1;
+    const int win_last = plan.win_last = opt_.has_query ? std::min(seq_len, opt_.query_last) : seq_len;
 
     // ---- 2. event pre-pass ----------------------------------------------------------------------------------------
     Realigner realigner;
@@ -104,9 +107,6 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
     realigner.seq = seq;
     IndelCallerOptions io;
     io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
-    std::vector<IndelRecord> indels;
-    std::set<int> suppressed;                         // positions where the device's SNV decision must not be reported
-    std::vector<std::pair<int, int>> embedded;        // (from, to] style closed intervals [a,b] of embedded positions
     int last_indel_end = 0;                           // SSVPL:143
     {
         std::priority_queue<int, std::vector<int>, std::greater<int>> heap;
@@ -166,6 +166,35 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
         }
     }
     stats_.prepass_s += now_s() - t0;
+    // reach of every read over all of its versions, to pick the records of a tile (halo = read span)
+    plan.max_reach = 1;
+    plan.max_back = 0;
+    for (const HostRead& r : reads) {
+        int lastp = r.st.last, firstp = r.st.first;
+        for (auto& v : r.closed) { lastp = std::max(lastp, v.st.last); firstp = std::min(firstp, v.st.first); }
+        plan.max_reach = std::max(plan.max_reach, lastp - r.admit_first + 1);
+        plan.max_back = std::max(plan.max_back, r.admit_first - firstp);
+    }
+    return NGSEP_OK;
+}
+
+void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const {
+    const auto& reads = plan.reads;
+    r_lo = std::lower_bound(reads.begin(), reads.end(), tf - plan.max_reach + 1, [](const HostRead& r, int v) { return r.admit_first < v; }) - reads.begin();
+    r_hi = std::upper_bound(reads.begin(), reads.end(), tl + plan.max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
+}
+
+int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) {
+    const std::string& chrom = genome_->names[seq];
+    SeqPlan plan;
+    int prc = plan_sequence(b, seq, lo, hi, plan);
+    if (prc != NGSEP_OK) return prc;
+    if (plan.reads.empty()) return NGSEP_OK;
+    std::vector<HostRead>& reads = plan.reads;
+    std::vector<IndelRecord>& indels = plan.indels;
+    std::set<int>& suppressed = plan.suppressed;
+    std::vector<std::pair<int, int>>& embedded = plan.embedded;
+    const int win_first = plan.win_first, win_last = plan.win_last;
 
     // ---- 3. device: region tiles ------------------------------------------------------------------------------------
     if (!opt_.host_only && !ref_uploaded_[seq]) {
@@ -175,17 +204,6 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
     }
     std::vector<ngsep_snv_call> snvs;
     if (!opt_.host_only) {
-        // reach of every read over all of its versions, to pick the records of a tile (halo = read span)
-        int max_reach = 1, max_back = 0;
-        std::vector<int> reach(reads.size());
-        for (size_t k = 0; k < reads.size(); k++) {
-            const HostRead& r = reads[k];
-            int lastp = r.st.last, firstp = r.st.first;
-            for (auto& v : r.closed) { lastp = std::max(lastp, v.st.last); firstp = std::min(firstp, v.st.first); }
-            reach[k] = lastp;
-            max_reach = std::max(max_reach, lastp - r.admit_first + 1);
-            max_back = std::max(max_back, r.admit_first - firstp);
-        }
         const int tile_len = opt_.tile_len > 0 ? opt_.tile_len : INT_MAX;
         PackedTile tile;
         std::vector<ngsep_snv_call> buf;
@@ -193,9 +211,8 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
         for (int64_t tf = win_first; tf <= win_last; tf += tile_len, tile_no++) {
             if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
             int tl = (int)std::min<int64_t>(win_last, tf + (int64_t)tile_len - 1);
-            // records whose ordering start can reach the tile
-            size_t r_lo = std::lower_bound(reads.begin(), reads.end(), (int)tf - max_reach + 1, [](const HostRead& r, int v) { return r.admit_first < v; }) - reads.begin();
-            size_t r_hi = std::upper_bound(reads.begin(), reads.end(), tl + max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
+            size_t r_lo, r_hi;   // records whose ordering start can reach the tile
+            tile_records(plan, (int)tf, tl, r_lo, r_hi);
             if (r_lo >= r_hi) continue;
             double tp = now_s();
             pack_reads(reads, r_lo, r_hi, tile);
@@ -220,7 +237,6 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
             stats_.tiles++;
             snvs.insert(snvs.end(), buf.begin(), buf.begin() + n);
         }
-        (void)reach;
     }
 
     // ---- 4. ordered merge + text (SSVD:933-968) -------------------------------------------------------------------------
@@ -246,5 +262,25 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
     return NGSEP_OK;
 }
 
+}  // namespace host
+}  // namespace ngsep_b200
+
+namespace ngsep_b200 {
+namespace host {
+// Admission + event pre-pass + packing of one whole sequence: exactly the tile run_sequence submits when tile_len == 0.
+int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, PackedTile& tile, int& tile_first, int& tile_last) {
+    if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }
+    int64_t lo = 0;
+    while (lo < b.n && b.seq_idx[lo] != seq) lo++;
+    int64_t hi = lo;
+    while (hi < b.n && b.seq_idx[hi] == seq) hi++;
+    SeqPlan plan;
+    int rc = plan_sequence(b, seq, lo, hi, plan);
+    if (rc != NGSEP_OK) return rc;
+    pack_reads(plan.reads, 0, plan.reads.size(), tile);
+    tile_first = plan.win_first;
+    tile_last = plan.win_last;
+    return NGSEP_OK;
+}
 }  // namespace host
 }  // namespace ngsep_b200

@@ -130,6 +130,27 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
     return NGSEP_OK;
 }
 
+// The tile the detector itself would submit for a whole sequence (admission + event pre-pass versions + packing).
+int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads,
+                    uint64_t* n_words, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases) {
+    Handle* h = (Handle*)p;
+    if (!h || !h->det || !b || !hdr || !payload) return NGSEP_EINVAL;
+    PackedTile t;
+    int rc = h->det->pack_sequence(view_of(b), seq_idx, t, *tile_first, *tile_last);
+    if (rc != NGSEP_OK) { h->err = h->det->error(); return rc; }
+    *n_reads = (int64_t)t.hdr.size();
+    *n_words = t.payload.size();
+    *max_span = t.max_span;
+    *max_back = t.max_back;
+    if (aligned_bases) *aligned_bases = t.aligned_bases;
+    *hdr = (ngsep_read_hdr*)std::malloc(t.hdr.size() * sizeof(ngsep_read_hdr) + 16);
+    *payload = (uint32_t*)std::malloc(t.payload.size() * 4 + 64);
+    if (!*hdr || !*payload) return NGSEP_ENOMEM;
+    std::memcpy(*hdr, t.hdr.data(), t.hdr.size() * sizeof(ngsep_read_hdr));
+    std::memcpy(*payload, t.payload.data(), t.payload.size() * 4);
+    return NGSEP_OK;
+}
+
 void ngsep_host_free(void* p) { std::free(p); }
 
 }  // extern "C"

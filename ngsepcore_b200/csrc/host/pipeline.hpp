@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <functional>
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -85,6 +86,15 @@ struct RunStats {
     double kernel_ms = 0, prepass_s = 0, pack_s = 0, device_s = 0, total_s = 0;
 };
 
+// Outcome of the host stages for one sequence (admission + event pre-pass).
+struct SeqPlan {
+    std::vector<HostRead> reads;                 // pileup order, with versions
+    std::vector<IndelRecord> indels;             // host-made indel / STR calls
+    std::set<int> suppressed;                    // positions whose device SNV decision must not be reported
+    std::vector<std::pair<int, int>> embedded;   // closed intervals of embedded positions (SSVPL:150-151)
+    int win_first = 1, win_last = 0, max_reach = 1, max_back = 0;
+};
+
 // Drop-in for SingleSampleVariantsDetector.findSNVs over in-memory alignments.
 class GpuSingleSampleVariantsDetector {
 public:
@@ -105,6 +115,10 @@ private:
     std::string err_;
     int ensure_ctx();
     int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out);
+    int plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan);
+    void tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const;
+public:
+    int pack_sequence(const BatchView& b, int seq, PackedTile& tile, int& tile_first, int& tile_last);
 };
 
 std::string snv_vcf_line(const ngsep_snv_call& c, const std::string& chrom, int ploidy, bool csb, bool embedded);

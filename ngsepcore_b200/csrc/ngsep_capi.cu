@@ -3,7 +3,9 @@
 // every entry point fails with NGSEP_ENODEVICE / NGSEP_ECUDA when the device cannot do the work.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <climits>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,7 +18,14 @@ using namespace ngsep_b200;
 
 namespace {
 
-struct RefSeq { uint32_t* ref2 = nullptr; uint32_t* ref_n = nullptr; uint32_t* ref_l = nullptr; int64_t len = 0; };
+struct RefSeq {   // ref2 / ref_n / ref_l point INSIDE the allocations (front padding for the TMA halo of window 0)
+    uint32_t* ref2 = nullptr; uint32_t* ref_n = nullptr; uint32_t* ref_l = nullptr; int64_t len = 0;
+    uint32_t *a_ref2 = nullptr, *a_refn = nullptr, *a_refl = nullptr;
+    void release() { if (a_ref2) cudaFree(a_ref2); if (a_refn) cudaFree(a_refn); if (a_refl) cudaFree(a_refl); *this = RefSeq(); }
+};
+constexpr size_t kRefFrontWords = 16;                       // 64 B in front of word 0
+constexpr size_t kRefTailWords2 = kMaxWindow / 16 + 64;     // the last window is staged whole, whatever the sequence length
+constexpr size_t kRefTailWords1 = kMaxWindow / 32 + 64;
 
 template <typename T>
 struct DevBuf {
@@ -33,28 +42,53 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-struct Ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    ngsep_params params{};
-    DevParams* d_prm = nullptr;
-    std::vector<RefSeq> refs;
+constexpr size_t kMetaStride = 32;      // per slot: counters[2] (u64) | n_calls (u32) | pad
+constexpr size_t kMaxSlots = 65536;
+
+struct Slot {
     DevBuf<ngsep_read_hdr> d_hdr;
     DevBuf<uint32_t> d_pay;
-    DevBuf<uint16_t> d_sample;
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
     DevBuf<int32_t> d_counts;
-    unsigned int* d_ncalls = nullptr;         // [1]
-    unsigned long long* d_counters = nullptr; // [4]
+    TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches
+    unsigned int* d_ncalls = nullptr;         // inside Ctx::d_meta
+    unsigned long long* d_counters = nullptr; // inside Ctx::d_meta
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     TileDev tile{};
-    bool staged = false, launched = false;
-    int grid = 0; size_t smem = 0;
+    ngsep_read_hdr sentinel{};
+    bool staged = false, launched = false, in_batch = false;
+    int grid = 0;
     uint64_t aligned_bases = 0;
     unsigned int launches = 0;
+    void release() {
+        d_hdr.release(); d_pay.release(); d_win.release(); d_calls.release(); d_counts.release();
+        if (d_tile) cudaFree(d_tile);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        d_tile = nullptr; e0 = e1 = nullptr;
+    }
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;   // stopwatch
+    cudaEvent_t b0 = nullptr, b1 = nullptr;   // around the batched launch
+    ngsep_params params{};
+    DevParams* d_prm = nullptr;
+    unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
+    std::vector<RefSeq> refs;
+    std::vector<Slot*> slots;                 // slot 0 = submit/fetch, 1.. = resident tiles
+    // batched launch over every resident slot
+    DevBuf<TileDev> d_btiles;
+    DevBuf<WinRange> d_bwin;
+    int b_windows = 0, b_grid = 0;
+    bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
-    int window = 1024; unsigned int pay_cap_words = 14336;
+    LaunchCfg cfg{512, 7424u, 1, 4};
+    size_t smem = 0;
+    int ctas_per_sm = 1;
     std::string err;
 };
 
@@ -66,24 +100,189 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
 
 std::string g_global_err;
 
-int launch_staged(Ctx* c) {
-    if (!c->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
-    CK(cudaMemsetAsync(c->d_ncalls, 0, sizeof(unsigned int), c->stream), "memset n_calls");
-    CK(cudaMemsetAsync(c->d_counters, 0, 4 * sizeof(unsigned long long), c->stream), "memset counters");
-    c->launches = 0;
-    if (c->tile.counts_dbg) {
-        size_t n = (size_t)(c->tile.tile_last - c->tile.tile_first + 1) * 5;
-        CK(cudaMemsetAsync(c->tile.counts_dbg, 0, n * sizeof(int32_t), c->stream), "memset counts");
+int new_slot(Ctx* c, Slot** out) {
+    if (c->slots.size() >= kMaxSlots) return fail(c, NGSEP_ENOMEM, "too many resident tiles");
+    Slot* s = new Slot();
+    const size_t id = c->slots.size();
+    s->d_counters = (unsigned long long*)(c->d_meta + id * kMetaStride);
+    s->d_ncalls = (unsigned int*)(c->d_meta + id * kMetaStride + 16);
+    cudaError_t e = cudaMalloc((void**)&s->d_tile, sizeof(TileDev));
+    if (e == cudaSuccess) e = cudaEventCreate(&s->e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->e1);
+    if (e != cudaSuccess) { s->release(); delete s; return cuda_fail(c, e, "slot setup"); }
+    *out = s;
+    return NGSEP_OK;
+}
+
+int clear_counts_dbg(Ctx* c, Slot* s) {
+    if (s->tile.counts_dbg) {
+        size_t n = (size_t)(s->tile.tile_last - s->tile.tile_first + 1) * 5;
+        CK(cudaMemsetAsync(s->tile.counts_dbg, 0, n * sizeof(int32_t), c->stream), "memset counts");
     }
-    CK(cudaEventRecord(c->ev0, c->stream), "event record");
-    if (c->tile.n_windows > 0) {
-        launch_window_index(c->tile, c->stream);
-        launch_pileup(c->tile, c->d_prm, c->grid, c->smem, c->stream);
-        c->launches = 2;
+    return NGSEP_OK;
+}
+
+// one tile, one launch
+int launch_slot(Ctx* c, Slot* s) {
+    if (!s->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
+    CK(cudaMemsetAsync(s->d_counters, 0, kMetaStride, c->stream), "memset counters");
+    s->launches = 0;
+    int rc = clear_counts_dbg(c, s);
+    if (rc != NGSEP_OK) return rc;
+    CK(cudaEventRecord(s->e0, c->stream), "event record");
+    if (s->tile.n_windows > 0) {
+        launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, c->cfg, s->grid, c->smem, c->stream);
+        s->launches = 1;
     }
-    CK(cudaEventRecord(c->ev1, c->stream), "event record");
+    CK(cudaEventRecord(s->e1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
-    c->launched = true;
+    s->launched = true;
+    s->in_batch = false;
+    return NGSEP_OK;
+}
+
+// every resident tile, ONE launch: the windows of all tiles form one list walked by persistent CTAs
+int launch_batch(Ctx* c) {
+    const size_t n = c->slots.size();
+    if (n <= 1) return fail(c, NGSEP_ESTATE, "no resident tiles");
+    if (c->batch_dirty) {
+        std::vector<TileDev> tiles;
+        size_t n_win = 0;
+        for (size_t i = 1; i < n; i++) { tiles.push_back(c->slots[i]->tile); n_win += (size_t)c->slots[i]->tile.n_windows; }
+        if (n_win > 0x7fffffffull) return fail(c, NGSEP_EINVAL, "too many windows in one batch");
+        CK(c->d_btiles.reserve(tiles.size()), "batch tiles alloc");
+        CK(c->d_bwin.reserve(n_win + 1), "batch windows alloc");
+        CK(cudaMemcpyAsync(c->d_btiles.p, tiles.data(), tiles.size() * sizeof(TileDev), cudaMemcpyHostToDevice, c->stream), "batch tiles copy");
+        size_t off = 0;
+        for (size_t i = 1; i < n; i++) {
+            launch_window_index(c->slots[i]->tile, c->d_bwin.p + off, (int)(i - 1), c->stream);
+            off += (size_t)c->slots[i]->tile.n_windows;
+        }
+        CK(cudaGetLastError(), "window index launch");
+        CK(cudaStreamSynchronize(c->stream), "batch staging");   // `tiles` lives on this stack frame
+        c->b_windows = (int)n_win;
+        c->b_grid = (int)std::min<size_t>(n_win, (size_t)c->sm_count * (size_t)c->ctas_per_sm);
+        c->batch_dirty = false;
+    }
+    CK(cudaMemsetAsync(c->d_meta + kMetaStride, 0, (n - 1) * kMetaStride, c->stream), "memset counters");
+    for (size_t i = 1; i < n; i++) { int rc = clear_counts_dbg(c, c->slots[i]); if (rc != NGSEP_OK) return rc; }
+    CK(cudaEventRecord(c->b0, c->stream), "event record");
+    if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, c->cfg, c->b_grid, c->smem, c->stream);
+    CK(cudaEventRecord(c->b1, c->stream), "event record");
+    CK(cudaGetLastError(), "kernel launch");
+    for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
+    c->batch_ran = true;
+    return NGSEP_OK;
+}
+
+int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
+    if (!t) return fail(c, NGSEP_EINVAL, "null argument");
+    if (t->n_reads < 0 || t->tile_first < 1 || t->tile_last < t->tile_first) return fail(c, NGSEP_EINVAL, "bad tile extents");
+    if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
+    if (t->n_reads > 0 && (!t->hdr || !t->payload)) return fail(c, NGSEP_EINVAL, "null tile buffers");
+    if (c->params.n_samples > 1) return fail(c, NGSEP_EINVAL, "multi-sample tiles are not supported by this build");
+    if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
+    CK(cudaSetDevice(c->device), "set device");
+    const RefSeq& ref = c->refs[t->seq_idx];
+    // the copies start first; the host-side validation below runs while they are in flight
+    CK(s->d_hdr.reserve((size_t)t->n_reads + 1), "hdr alloc");
+    CK(s->d_pay.reserve((size_t)t->n_words + 16), "payload alloc");
+    if (t->n_reads > 0) {
+        CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
+        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
+    }
+    s->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
+    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
+    // validate ordering + stage fit (a record must fit one staged chunk)
+    uint64_t bases = 0;
+    const char* bad = nullptr;
+    for (int i = 0; i < t->n_reads && !bad; i++) {
+        const ngsep_read_hdr& h = t->hdr[i];
+        if (i > 0 && h.first < t->hdr[i - 1].first) bad = "records are not sorted by start";
+        uint64_t next = (i + 1 < t->n_reads) ? t->hdr[i + 1].off : t->n_words;
+        if (next < h.off || next > t->n_words) bad = "payload offsets are not monotone";
+        else if (next - h.off + 4 > c->cfg.pay_cap_words) bad = "record payload exceeds the device window (read too long)";
+        bases += h.meta & 0xffffu;
+    }
+    if (bad) { cudaStreamSynchronize(c->stream); s->staged = false; return fail(c, NGSEP_EINVAL, bad); }   // the caller may free its buffers
+    s->aligned_bases = bases;
+    // window length: a multiple of 128, shrunk while an average window would not fit one stage
+    int T = c->cfg.T_lay;
+    int64_t tile_len = (int64_t)t->tile_last - t->tile_first + 1;
+    double words_per_pos = (double)t->n_words / (double)tile_len;
+    double recs_per_pos = (double)t->n_reads / (double)tile_len;
+    const int span = t->max_span < 1 ? 1 : t->max_span;
+    while (T > 128 && (words_per_pos * (T + span) > 0.85 * c->cfg.pay_cap_words || recs_per_pos * (T + span) > 0.85 * (c->cfg.pay_cap_words / 24)))
+        T = std::max(128, (T / 2) & ~127);
+    TileDev& d = s->tile;
+    d = TileDev{};
+    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.sample = nullptr;
+    d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
+    d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
+    d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
+    d.T = T;
+    d.win0 = (t->tile_first - 1) / T;
+    d.n_windows = (t->n_reads == 0) ? 0 : ((t->tile_last - 1) / T - d.win0 + 1);
+    CK(s->d_win.reserve((size_t)d.n_windows + 1), "window alloc");
+    size_t cap_calls = (size_t)(tile_len / 16) + 65536;
+    if (s->d_calls.cap < cap_calls) CK(s->d_calls.reserve(cap_calls), "calls alloc");
+    d.calls = s->d_calls.p; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_calls.cap;
+    d.counts_dbg = nullptr;
+    if (c->params.flags & NGSEP_F_EMIT_ALL) {
+        CK(s->d_counts.reserve((size_t)tile_len * 5), "counts alloc");
+        d.counts_dbg = s->d_counts.p;
+    }
+    d.counters = s->d_counters;
+    s->grid = std::min(d.n_windows, c->sm_count * c->ctas_per_sm);   // persistent CTAs
+    CK(cudaMemcpyAsync(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice, c->stream), "tile descriptor copy");
+    launch_window_index(d, s->d_win.p, 0, c->stream);   // depends on the staged records only: built once per staging
+    CK(cudaGetLastError(), "window index launch");
+    s->staged = true;
+    s->launched = false;
+    return NGSEP_OK;
+}
+
+int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
+    if (!n_out) return fail(c, NGSEP_EINVAL, "null argument");
+    if (!s->launched) return fail(c, NGSEP_ESTATE, "no tile in flight");
+    CK(cudaSetDevice(c->device), "set device");
+    struct Meta { unsigned long long ctr[2]; unsigned int n_calls, pad[3]; } meta;
+    static_assert(sizeof(Meta) == kMetaStride, "meta layout");
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(cudaStreamSynchronize(c->stream), "tile kernels");
+        CK(cudaMemcpy(&meta, s->d_counters, sizeof(meta), cudaMemcpyDeviceToHost), "counters copy");
+        if (meta.n_calls <= s->tile.cap_calls) break;
+        if (attempt == 1) return fail(c, NGSEP_EOVERFLOW, "call buffer overflow");
+        CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");   // grow and rerun the staged tile
+        s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
+        CK(cudaMemcpy(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice), "tile descriptor copy");
+        c->batch_dirty = true;
+        int rc = launch_slot(c, s);
+        if (rc != NGSEP_OK) return rc;
+    }
+    const unsigned int n = meta.n_calls;
+    if (stats) {
+        float ms = 0.f;
+        if (s->in_batch) CK(cudaEventElapsedTime(&ms, c->b0, c->b1), "event elapsed");   // the whole batch: tiles share one launch
+        else CK(cudaEventElapsedTime(&ms, s->e0, s->e1), "event elapsed");
+        stats->covered_positions = meta.ctr[0];
+        stats->candidate_positions = meta.ctr[1];
+        stats->calls = n;
+        stats->aligned_bases = s->aligned_bases;
+        stats->kernel_ms = ms;
+        stats->pileup_ms = ms;
+        stats->kernel_launches = s->launches;
+    }
+    *n_out = n;
+    if (n > cap) return fail(c, NGSEP_EOVERFLOW, "caller's call buffer is too small; n_out holds the required capacity");
+    if (n > 0) {
+        if (!out) return fail(c, NGSEP_EINVAL, "null output buffer");
+        CK(cudaMemcpy(out, s->d_calls.p, (size_t)n * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost), "calls copy");
+    }
+    if (counts_dbg && s->tile.counts_dbg) {
+        size_t m = (size_t)(s->tile.tile_last - s->tile.tile_first + 1) * 5;
+        CK(cudaMemcpy(counts_dbg, s->tile.counts_dbg, m * sizeof(int32_t), cudaMemcpyDeviceToHost), "counts copy");
+    }
     return NGSEP_OK;
 }
 
@@ -116,16 +315,29 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     c->device = device;
     c->params = *params;
     c->sm_count = prop.multiProcessorCount;
-    if (const char* s = std::getenv("NGSEP_WINDOW")) { int v = std::atoi(s); if (v >= 64 && (v & (v - 1)) == 0 && v <= 8192) c->window = v; }
-    if (const char* s = std::getenv("NGSEP_PAY_CAP_WORDS")) { int v = std::atoi(s); if (v >= 1024 && v <= 50000) c->pay_cap_words = (unsigned)v; }
+    // launch shape (tunable for experiments; the defaults are what bench.py measures)
+    if (const char* s = std::getenv("NGSEP_WINDOW")) { int v = std::atoi(s); if (v >= 128 && (v % 128) == 0 && v <= kMaxWindow) c->cfg.T_lay = v; }
+    if (const char* s = std::getenv("NGSEP_PAY_CAP_WORDS")) { int v = std::atoi(s); if (v >= 1024 && v <= 50000) c->cfg.pay_cap_words = (unsigned)(v & ~3); }
+    if (const char* s = std::getenv("NGSEP_STAGES")) { int v = std::atoi(s); if (v == 1 || v == 2) c->cfg.n_stages = v; }
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
-    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->t1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->b0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->b1);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_prm, sizeof(DevParams));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_ncalls, sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_meta, kMaxSlots * kMetaStride);
+    if (e == cudaSuccess) e = cudaMemset(c->d_meta, 0, kMaxSlots * kMetaStride);
     if (e != cudaSuccess) { g_global_err = std::string("context setup: ") + cudaGetErrorString(e); delete c; return NGSEP_ECUDA; }
+    c->smem = pileup_smem_bytes(c->cfg);
+    if (c->smem > (size_t)prop.sharedMemPerBlockOptin) { g_global_err = "window / stage configuration exceeds the shared memory of one SM"; delete c; return NGSEP_EINVAL; }
+    if (const char* s = std::getenv("NGSEP_MIN_BLOCKS")) { int v = std::atoi(s); if (v >= 3 && v <= 5) c->cfg.min_blocks = v; }
+    c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.min_blocks);
+    if (c->ctas_per_sm < 1) { g_global_err = "the pileup kernel cannot be made resident with this configuration"; delete c; return NGSEP_ECUDA; }
+    if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
+    Slot* s0 = nullptr;
+    if (new_slot(c, &s0) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }
+    c->slots.push_back(s0);
     DevParams hp{};
     hp.max_base_qs = params->max_base_qs;
     hp.min_quality = params->min_quality;
@@ -135,6 +347,28 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     // dominates: a_q > c_q > b_q for every q in 4..30 and log prior(hom) - log prior(het) comfortably positive.
     hp.fast_homref = (tables[93] - tables[94] > 1.0) ? 1 : 0;
     for (int q = 4; q <= 30 && hp.fast_homref; q++) if (!(tables[3 * q] > tables[3 * q + 2] && tables[3 * q + 2] > tables[3 * q + 1])) hp.fast_homref = 0;
+    // Proven skip: with k counted reference bases and m counted non-reference bases, the 15 events other
+    // than (ref,ref) sum, relative to it, to at most
+    //   B(k,m) = 6*10^(-k*dca + m*gcb + D) + 3*10^(-k*dab + m*gab) + 6*10^(-k*dab + m*gcb + D)
+    // with dca = min_q(a_q - c_q), gcb = max_q(c_q - b_q), dab = min_q(a_q - b_q), gab = max_q(a_q - b_q) over the
+    // qualities that can be counted (4..maxBaseQS) and D = log prior(het) - log prior(hom).  B <= 0.9 gives
+    // P(ref,ref) >= 0.526 and every other genotype <= 0.474 < P(ref,ref) + 0.01: VD.getIndexesMaxGenotype keeps (ref,ref).
+    {
+        double dca = 1e300, gcb = -1e300, dab = 1e300, gab = -1e300;
+        for (int q = 4; q <= params->max_base_qs; q++) {
+            double a = tables[3 * q], b = tables[3 * q + 1], cc = tables[3 * q + 2];
+            dca = std::min(dca, a - cc); gcb = std::max(gcb, cc - b); dab = std::min(dab, a - b); gab = std::max(gab, a - b);
+        }
+        const double D = tables[94] - tables[93];
+        for (int m = 0; m < 16; m++) {
+            hp.k_min[m] = INT_MAX;
+            if (!hp.fast_homref || !(dca > 0 && dab > 0)) continue;
+            for (int k = 0; k <= 200000; k++) {
+                double B = 6 * std::pow(10.0, -k * dca + m * gcb + D) + 3 * std::pow(10.0, -k * dab + m * gab) + 6 * std::pow(10.0, -k * dab + m * gcb + D);
+                if (B <= 0.9) { hp.k_min[m] = k; break; }
+            }
+        }
+    }
     e = cudaMemcpy(c->d_prm, &hp, sizeof(hp), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { g_global_err = std::string("params upload: ") + cudaGetErrorString(e); delete c; return NGSEP_ECUDA; }
     *out = c;
@@ -146,13 +380,15 @@ int ngsep_ctx_destroy(void* ctx) {
     if (!c) return NGSEP_EINVAL;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (auto& r : c->refs) { if (r.ref2) cudaFree(r.ref2); if (r.ref_n) cudaFree(r.ref_n); if (r.ref_l) cudaFree(r.ref_l); }
-    c->d_hdr.release(); c->d_pay.release(); c->d_sample.release(); c->d_win.release(); c->d_calls.release(); c->d_counts.release();
+    for (auto& r : c->refs) r.release();
+    for (Slot* s : c->slots) { s->release(); delete s; }
+    c->d_btiles.release(); c->d_bwin.release();
     if (c->d_prm) cudaFree(c->d_prm);
-    if (c->d_ncalls) cudaFree(c->d_ncalls);
-    if (c->d_counters) cudaFree(c->d_counters);
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->d_meta) cudaFree(c->d_meta);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->b0) cudaEventDestroy(c->b0);
+    if (c->b1) cudaEventDestroy(c->b1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NGSEP_OK;
@@ -164,139 +400,143 @@ int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t leng
     CK(cudaSetDevice(c->device), "set device");
     if ((size_t)seq_idx >= c->refs.size()) c->refs.resize(seq_idx + 1);
     RefSeq& r = c->refs[seq_idx];
-    if (r.ref2) { cudaFree(r.ref2); cudaFree(r.ref_n); cudaFree(r.ref_l); r = RefSeq(); }
+    r.release();
+    c->batch_dirty = true;
     int64_t n32 = (length + 31) / 32;
+    const size_t w2 = kRefFrontWords + (size_t)n32 * 2 + kRefTailWords2, w1 = kRefFrontWords + (size_t)n32 + kRefTailWords1;
     char* d_ascii = nullptr;
     CK(cudaMalloc((void**)&d_ascii, (size_t)length), "ref ascii alloc");
-    cudaError_t e = cudaMalloc((void**)&r.ref2, (size_t)(n32 * 2 + 4) * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r.ref_n, (size_t)(n32 + 4) * 4);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&r.ref_l, (size_t)(n32 + 4) * 4);
+    cudaError_t e = cudaMalloc((void**)&r.a_ref2, w2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r.a_refn, w1 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r.a_refl, w1 * 4);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ascii, bases, (size_t)length, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(r.ref2, 0, (size_t)(n32 * 2 + 4) * 4, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(r.ref_n, 0xff, (size_t)(n32 + 4) * 4, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(r.ref_l, 0, (size_t)(n32 + 4) * 4, c->stream);
-    if (e == cudaSuccess) { launch_ref_pack(d_ascii, length, r.ref2, r.ref_n, r.ref_l, c->stream); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_ref2, 0, w2 * 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_refn, 0xff, w1 * 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_refl, 0, w1 * 4, c->stream);
+    if (e == cudaSuccess) {
+        r.ref2 = r.a_ref2 + kRefFrontWords; r.ref_n = r.a_refn + kRefFrontWords; r.ref_l = r.a_refl + kRefFrontWords;
+        launch_ref_pack(d_ascii, length, r.ref2, r.ref_n, r.ref_l, c->stream);
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_ascii);
-    if (e != cudaSuccess) return cuda_fail(c, e, "reference upload");
+    if (e != cudaSuccess) { r.release(); return cuda_fail(c, e, "reference upload"); }
     r.len = length;
     return NGSEP_OK;
 }
 
-int ngsep_tile_stage(void* ctx, const ngsep_tile* t) {
-    Ctx* c = (Ctx*)ctx;
-    if (!c || !t) return fail(c, NGSEP_EINVAL, "null argument");
-    if (t->n_reads < 0 || t->tile_first < 1 || t->tile_last < t->tile_first) return fail(c, NGSEP_EINVAL, "bad tile extents");
-    if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
-    if (t->n_reads > 0 && (!t->hdr || !t->payload)) return fail(c, NGSEP_EINVAL, "null tile buffers");
-    if (c->params.n_samples > 1) return fail(c, NGSEP_EINVAL, "multi-sample tiles are not supported by this build");
-    CK(cudaSetDevice(c->device), "set device");
-    const RefSeq& ref = c->refs[t->seq_idx];
-    // validate ordering + chunk fit (a record must fit one staged chunk)
-    uint64_t bases = 0;
-    for (int i = 0; i < t->n_reads; i++) {
-        const ngsep_read_hdr& h = t->hdr[i];
-        if (i > 0 && h.first < t->hdr[i - 1].first) return fail(c, NGSEP_EINVAL, "records are not sorted by start");
-        uint64_t next = (i + 1 < t->n_reads) ? t->hdr[i + 1].off : t->n_words;
-        if (next < h.off || next > t->n_words) return fail(c, NGSEP_EINVAL, "payload offsets are not monotone");
-        if (next - h.off + 4 > c->pay_cap_words) return fail(c, NGSEP_EINVAL, "record payload exceeds the device window (read too long)");
-        bases += h.meta & 0xffffu;
-    }
-    c->aligned_bases = bases;
-    if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
-    // window size: shrink while an average window would not fit one chunk
-    int T = c->window;
-    int64_t tile_len = (int64_t)t->tile_last - t->tile_first + 1;
-    double words_per_pos = (double)t->n_words / (double)tile_len;
-    while (T > 64 && words_per_pos * (T + t->max_span) > 0.8 * c->pay_cap_words) T >>= 1;
-    TileDev& d = c->tile;
-    d = TileDev{};
-    CK(c->d_hdr.reserve((size_t)t->n_reads + 1), "hdr alloc");
-    CK(c->d_pay.reserve((size_t)t->n_words + 16), "payload alloc");
-    if (t->n_reads > 0) {
-        CK(cudaMemcpyAsync(c->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
-        CK(cudaMemcpyAsync(c->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
-    }
-    ngsep_read_hdr sentinel{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
-    CK(cudaMemcpyAsync(c->d_hdr.p + t->n_reads, &sentinel, sizeof(sentinel), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
-    CK(cudaStreamSynchronize(c->stream), "stage sync");  // sentinel lives on this stack frame
-    d.hdr = c->d_hdr.p; d.payload = c->d_pay.p; d.sample = nullptr;
-    d.n_reads = t->n_reads; d.max_span = t->max_span < 1 ? 1 : t->max_span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
-    d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
-    d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
-    d.T = T;
-    d.win0 = (t->tile_first - 1) / T;
-    d.n_windows = (t->n_reads == 0) ? 0 : ((t->tile_last - 1) / T - d.win0 + 1);
-    CK(c->d_win.reserve((size_t)d.n_windows + 1), "window alloc");
-    d.win = c->d_win.p;
-    size_t cap_calls = (size_t)(tile_len / 16) + 65536;
-    if (c->d_calls.cap < cap_calls) CK(c->d_calls.reserve(cap_calls), "calls alloc");
-    d.calls = c->d_calls.p; d.n_calls = c->d_ncalls; d.cap_calls = (unsigned)c->d_calls.cap;
-    d.counts_dbg = nullptr;
-    if (c->params.flags & NGSEP_F_EMIT_ALL) {
-        CK(c->d_counts.reserve((size_t)tile_len * 5), "counts alloc");
-        d.counts_dbg = c->d_counts.p;
-    }
-    d.counters = c->d_counters;
-    d.pay_cap_words = c->pay_cap_words;
-    c->smem = pileup_smem_bytes(T, c->pay_cap_words);
-    c->grid = d.n_windows;
-    c->staged = true;
-    c->launched = false;
-    return NGSEP_OK;
-}
-
-int ngsep_tile_run_staged(void* ctx) {
+int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
-    CK(cudaSetDevice(c->device), "set device");
-    return launch_staged(c);
-}
-
-int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
-    int rc = ngsep_tile_stage(ctx, t);
+    int rc = stage_slot(c, c->slots[0], t);
     if (rc != NGSEP_OK) return rc;
-    return launch_staged((Ctx*)ctx);
+    return launch_slot(c, c->slots[0]);
 }
 
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
     Ctx* c = (Ctx*)ctx;
-    if (!c || !n_out) return fail(c, NGSEP_EINVAL, "null argument");
-    if (!c->launched) return fail(c, NGSEP_ESTATE, "no tile in flight");
+    if (!c) return NGSEP_EINVAL;
+    return fetch_slot(c, c->slots[0], out, cap, n_out, counts_dbg, stats);
+}
+
+int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !slot) return NGSEP_EINVAL;
     CK(cudaSetDevice(c->device), "set device");
-    unsigned int n = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        CK(cudaStreamSynchronize(c->stream), "tile kernels");
-        CK(cudaMemcpy(&n, c->d_ncalls, sizeof(n), cudaMemcpyDeviceToHost), "n_calls copy");
-        if (n <= c->tile.cap_calls) break;
-        if (attempt == 1) return fail(c, NGSEP_EOVERFLOW, "call buffer overflow");
-        CK(c->d_calls.reserve((size_t)n + 1024), "calls realloc");   // grow and rerun the staged tile
-        c->tile.calls = c->d_calls.p; c->tile.cap_calls = (unsigned)c->d_calls.cap;
-        int rc = launch_staged(c);
-        if (rc != NGSEP_OK) return rc;
+    Slot* s = nullptr;
+    int rc = new_slot(c, &s);
+    if (rc != NGSEP_OK) return rc;
+    rc = stage_slot(c, s, t);
+    if (rc != NGSEP_OK) { s->release(); delete s; return rc; }
+    c->slots.push_back(s);
+    c->batch_dirty = true;
+    *slot = (int)c->slots.size() - 1;
+    return NGSEP_OK;
+}
+
+int ngsep_resident_clear(void* ctx) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    CK(cudaSetDevice(c->device), "set device");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    while (c->slots.size() > 1) { c->slots.back()->release(); delete c->slots.back(); c->slots.pop_back(); }
+    c->batch_dirty = true;
+    c->batch_ran = false;
+    return NGSEP_OK;
+}
+
+int ngsep_resident_run(void* ctx, int slot) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    CK(cudaSetDevice(c->device), "set device");
+    if (slot >= 0) {
+        if ((size_t)slot >= c->slots.size()) return fail(c, NGSEP_EINVAL, "bad slot");
+        return launch_slot(c, c->slots[slot]);
     }
-    *n_out = n;
-    if (n > cap) return fail(c, NGSEP_EOVERFLOW, "caller's call buffer is too small; n_out holds the required capacity");
-    if (n > 0) {
-        if (!out) return fail(c, NGSEP_EINVAL, "null output buffer");
-        CK(cudaMemcpy(out, c->d_calls.p, (size_t)n * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost), "calls copy");
+    return launch_batch(c);
+}
+
+int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !stats) return NGSEP_EINVAL;
+    if (!c->batch_ran) return fail(c, NGSEP_ESTATE, "no batched run to report");
+    CK(cudaSetDevice(c->device), "set device");
+    CK(cudaStreamSynchronize(c->stream), "tile kernels");
+    const size_t n = c->slots.size();
+    std::vector<unsigned char> meta(n * kMetaStride);
+    CK(cudaMemcpy(meta.data(), c->d_meta, meta.size(), cudaMemcpyDeviceToHost), "counters copy");
+    *stats = ngsep_tile_stats{};
+    for (size_t i = 1; i < n; i++) {
+        const unsigned long long* ctr = (const unsigned long long*)(meta.data() + i * kMetaStride);
+        stats->covered_positions += ctr[0];
+        stats->candidate_positions += ctr[1];
+        stats->calls += *(const unsigned int*)(meta.data() + i * kMetaStride + 16);
+        stats->aligned_bases += c->slots[i]->aligned_bases;
     }
-    if (counts_dbg && c->tile.counts_dbg) {
-        size_t m = (size_t)(c->tile.tile_last - c->tile.tile_first + 1) * 5;
-        CK(cudaMemcpy(counts_dbg, c->tile.counts_dbg, m * sizeof(int32_t), cudaMemcpyDeviceToHost), "counts copy");
-    }
-    if (stats) {
-        unsigned long long ctr[4] = {0, 0, 0, 0};
-        CK(cudaMemcpy(ctr, c->d_counters, sizeof(ctr), cudaMemcpyDeviceToHost), "counters copy");
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1), "event elapsed");
-        stats->covered_positions = ctr[0];
-        stats->candidate_positions = ctr[1];
-        stats->calls = n;
-        stats->aligned_bases = c->aligned_bases;
-        stats->kernel_ms = ms;
-        stats->kernel_launches = c->launches;
-    }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->b0, c->b1), "event elapsed");
+    stats->kernel_ms = ms;
+    stats->pileup_ms = ms;
+    stats->kernel_launches = c->b_windows > 0 ? 1u : 0u;
+    return NGSEP_OK;
+}
+
+int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (slot < 0 || (size_t)slot >= c->slots.size()) return fail(c, NGSEP_EINVAL, "bad slot");
+    return fetch_slot(c, c->slots[slot], out, cap, n_out, counts_dbg, stats);
+}
+
+int ngsep_timer_start(void* ctx) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    CK(cudaSetDevice(c->device), "set device");
+    CK(cudaEventRecord(c->t0, c->stream), "timer start");
+    return NGSEP_OK;
+}
+
+int ngsep_timer_stop(void* ctx, float* ms) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !ms) return NGSEP_EINVAL;
+    CK(cudaSetDevice(c->device), "set device");
+    CK(cudaEventRecord(c->t1, c->stream), "timer stop");
+    CK(cudaEventSynchronize(c->t1), "timer sync");
+    CK(cudaEventElapsedTime(ms, c->t0, c->t1), "timer elapsed");
+    return NGSEP_OK;
+}
+
+int ngsep_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return NGSEP_EINVAL;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { g_global_err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return NGSEP_ECUDA; }
+    return NGSEP_OK;
+}
+
+int ngsep_host_unregister(void* ptr) {
+    if (!ptr) return NGSEP_EINVAL;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { g_global_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return NGSEP_ECUDA; }
     return NGSEP_OK;
 }
 

@@ -1,7 +1,7 @@
 // sm_100a kernels of libngsep_pileup.so — see pileup_kernels.cuh for the design summary.
 // Reference citations are relative to /root/reference/src/ngsep/ (RA = alignments/ReadAlignment.java,
 // PR = discovery/PileupRecord.java, CH = discovery/CountsHelper.java, VD = discovery/VariantDiscoverySNVQAlgorithm.java,
-// SSVPL = discovery/SingleSampleVariantPileupListener.java).
+// SSVPL = discovery/SingleSampleVariantPileupListener.java, APG = discovery/AlignmentsPileupGenerator.java).
 #include "pileup_kernels.cuh"
 
 #include <climits>
@@ -11,29 +11,47 @@ namespace ngsep_b200 {
 // ------------------------------------------------------------------------------------------------------------
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
-struct SmemLayout { unsigned bar, tab, ref2, refn, refl, cand, cov, list, misc, hdr, pay, total, max_reads; };
+struct SmemLayout {
+    unsigned bar, tab, kmin, misc, bm, list, wmax, rare;   // CTA-wide arrays
+    unsigned stage0, stage_stride;                          // staged windows
+    unsigned o_hdr, o_pay, o_ref2, o_refn, o_refl;          // offsets inside a stage
+    unsigned total, max_reads;
+};
 
-__host__ __device__ inline SmemLayout make_layout(int T, unsigned pay_cap_words) {
+// s_misc holds two sets of kMiscSet ints (one per window parity)
+constexpr int kMiscSet = 16;
+constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7;
+constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
+
+__host__ __device__ inline SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     SmemLayout L;
+    L.max_reads = pay_cap_words / 24;
     unsigned o = 0;
     L.bar = o; o += 16;
     L.tab = o; o += 96 * 8;
-    L.ref2 = o; o += (T / 16 + 2) * 4;
-    L.refn = o; o += (T / 32 + 1) * 4;
-    L.refl = o; o += (T / 32 + 1) * 4;
-    L.cand = o; o += (T / 32 + 1) * 4;
-    L.cov = o; o += (T / 32 + 1) * 4;
-    L.list = o; o += T * 2;
-    L.misc = o; o += 64;
-    o = (o + 15u) & ~15u;
-    L.max_reads = pay_cap_words / 16;
-    L.hdr = o; o += (L.max_reads + 1) * 16;
-    L.pay = o; o += (pay_cap_words + 8) * 4;
-    L.total = o;
+    L.kmin = o; o += kSkipTable * 4;
+    L.misc = o; o += 2 * kMiscSet * 4;
+    L.bm = o; o += (T / 32 + 1) * 4;
+    L.list = o; o += ((T * 2 + 3) & ~3u);
+    L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
+    o = (o + 7u) & ~7u;
+    L.rare = o; o += (L.max_reads + 1) * 8;
+    o = (o + 127u) & ~127u;
+    L.stage0 = o;
+    unsigned s = 0;
+    L.o_hdr = s; s += (L.max_reads + 1) * 16;
+    L.o_pay = s; s += (pay_cap_words + 8) * 4;
+    s = (s + 15u) & ~15u;
+    L.o_ref2 = s; s += (T + 2 * kRefLeft) / 4;            // T/4 + 32 bytes
+    L.o_refn = s; s += T / 8;
+    L.o_refl = s; s += T / 8;
+    s = (s + 127u) & ~127u;
+    L.stage_stride = s;
+    L.total = L.stage0 + (unsigned)n_stages * s;
     return L;
 }
 
-size_t pileup_smem_bytes(int T, unsigned int pay_cap_words) { return make_layout(T, pay_cap_words).total; }
+size_t pileup_smem_bytes(const LaunchCfg& cfg) { return make_layout(cfg.T_lay, cfg.pay_cap_words, cfg.n_stages).total; }
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX helpers: mbarrier + TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
@@ -67,27 +85,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// small bit helpers
+// record views
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t range_mask32(int lo, int hi) {  // bits [lo,hi), 0 <= lo < hi <= 32
     uint32_t m = (hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u);
     return m & ~((1u << lo) - 1u);
-}
-__device__ __forceinline__ void mark_bits(uint32_t* bm, int a, int b) {  // set bits [a,b) of a shared bitmap
-    if (a >= b) return;
-    int w0 = a >> 5, w1 = (b - 1) >> 5;
-    for (int w = w0; w <= w1; w++) {
-        int lo = (w == w0) ? (a & 31) : 0;
-        int hi = (w == w1) ? ((b - 1) & 31) + 1 : 32;
-        atomicOr(&bm[w], range_mask32(lo, hi));
-    }
-}
-__device__ __forceinline__ uint32_t extract16(const uint32_t* b2, int roff) {  // 16 packed bases starting at read offset roff
-    if (roff >= 0) {
-        int w = roff >> 4;
-        return __funnelshift_r(b2[w], b2[w + 1], (roff & 15) * 2);
-    }
-    return b2[0] << ((-roff) * 2);
 }
 
 struct RecView {
@@ -117,40 +119,98 @@ __device__ __forceinline__ RecView view_record(const ngsep_read_hdr& h, const ui
     return r;
 }
 
+__device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h, const uint32_t* pay) {
+    // one CIGAR word that is a match block, no N mask, no valid window: the vast majority
+    return (h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && (pay[0] & 7u) == 3u;
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// screen: candidate + coverage bits of one record inside the window
+// screen: positions of one window where a read base that may be counted differs from the reference
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void screen_record(const ngsep_read_hdr& h, const uint32_t* pay, int g_lo, int g_hi, int wbeg,
-                                              const uint32_t* s_ref2, uint32_t* s_cand, uint32_t* s_cov) {
-    RecView r = view_record(h, pay);
-    // 0-based index range of this window/tile/version intersection
-    int lo = max(g_lo, (r.vfrom == INT_MIN) ? INT_MIN : r.vfrom - 1);
-    int hi = min(g_hi, (r.vto == INT_MAX) ? INT_MAX : r.vto - 1);
-    if (lo >= hi) return;
+struct WinCtx {
+    int wbeg, g_lo, g_hi;        // 0-based index of the window start; [g_lo,g_hi) = the window inside tile and sequence
+    const uint32_t* s_ref2;      // staged reference, base index wbeg - kRefLeft at bit 0 of word 0
+    uint32_t* s_bm;              // candidate bitmap of the window
+    uint16_t* s_list;            // candidate list
+    int* mset;                   // counters of this window
+    bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
+};
+
+__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx) {
+    const int li = idx - w.wbeg;
+    const uint32_t bit = 1u << (li & 31);
+    const uint32_t old = atomicOr(&w.s_bm[li >> 5], bit);
+    if (!(old & bit)) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint16_t)li;
+}
+
+// 16 read bases (one payload word) against the reference at 0-based index `idx0` of the word's first base
+__device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
+    const int r = idx0 - w.wbeg + kRefLeft;   // >= 0: callers only ask for words that intersect [g_lo, g_hi)
+    return __funnelshift_r(w.s_ref2[r >> 4], w.s_ref2[(r >> 4) + 1], (r & 15) * 2);
+}
+
+// Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
+__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+    const int L = (int)(h.meta & 0xffffu);
+    const int mlen = (int)(pay[0] >> 3);
+    const int ref0 = h.first - 1;                  // 0-based index of read offset 0
+    const int a = max(ref0, w.g_lo), b = min(ref0 + mlen, w.g_hi);
+    if (a < b && w.collect) {
+        const uint32_t* b2 = pay + 1;
+        const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;
+        const int r0 = ref0 + 16 * j0 - w.wbeg + kRefLeft;
+        const int sh = (r0 & 15) * 2;
+        const uint32_t* rp = w.s_ref2 + (r0 >> 4);
+        uint32_t wlo = rp[0];
+        for (int j = j0; j <= j1; j++) {
+            const uint32_t whi = rp[j - j0 + 1];
+            const uint32_t x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
+            wlo = whi;
+            uint32_t m = (x | (x >> 1)) & 0x55555555u;
+            if (m == 0) continue;
+            // rare: a mismatch (or the padding of the last word / a base outside the window)
+            const int o_lo = max(a - ref0, 16 * j) - 16 * j, o_hi = min(b - ref0, 16 * j + 16) - 16 * j;
+            m &= range_mask32(2 * o_lo, 2 * o_hi);
+            if (m == 0) continue;
+            const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
+            const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);   // callable offsets (RA:782-784)
+            while (m) {
+                const int bit = __ffs(m) - 1;
+                m &= m - 1;
+                const int off = 16 * j + (bit >> 1);
+                if (off >= c_lo && off < c_hi && q[off] > 36) flag_candidate(w, ref0 + off);   // q = char - 33 > 3 (CH:214)
+            }
+        }
+    }
+    return ref0 + mlen;
+}
+
+// General record (indels, clips, N mask, realigner versions): every aligned base that differs from the reference
+// is flagged (a superset of the counted ones).  Returns the last covered position, or INT_MIN for a version record
+// (its coverage goes through the bitmap fallback).
+__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+    const RecView r = view_record(h, pay);
+    const int lo = max(w.g_lo, (r.vfrom == INT_MIN) ? INT_MIN : r.vfrom - 1);
+    const int hi = min(w.g_hi, (r.vto == INT_MAX) ? INT_MAX : r.vto - 1);
     int ref_idx = r.first - 1, rpos = 0;
-    const int cov_lo = ref_idx;
     for (int c = 0; c < r.nc; c++) {
-        uint32_t v = r.cig[c];
-        int len = (int)(v >> 3);
-        if ((v & 3u) == 3u) {  // consumes reference and read: M(3) or X(7)
-            int a = max(ref_idx, lo), b = min(ref_idx + len, hi);
-            if (a < b) {
-                const int delta = rpos - ref_idx;  // read offset = index + delta
-                for (int k = a >> 4; k <= (b - 1) >> 4; k++) {
-                    int gbase = k << 4;
-                    uint32_t refw = s_ref2[k - (wbeg >> 4)];
-                    uint32_t rd = extract16(r.b2, gbase + delta);
-                    uint32_t x = rd ^ refw;
+        const uint32_t v = r.cig[c];
+        const int len = (int)(v >> 3);
+        if ((v & 3u) == 3u) {   // consumes reference and read: M(3) or X(7)
+            const int a = max(ref_idx, lo), b = min(ref_idx + len, hi);
+            if (a < b && w.collect) {
+                const int delta = rpos - ref_idx;   // read offset = index + delta
+                // walk 16 bases at a time on the READ grid
+                for (int o = (a + delta) & ~15; o < b + delta; o += 16) {
+                    const int wi = o >> 4;
+                    uint32_t x = r.b2[wi] ^ ref16(w, o - delta);
                     uint32_t m = (x | (x >> 1)) & 0x55555555u;
-                    int vlo = max(a, gbase) - gbase, vhi = min(b, gbase + 16) - gbase;
-                    m &= range_mask32(2 * vlo, 2 * vhi);
-                    if (m) {
-                        m = (m | (m >> 1)) & 0x33333333u;
-                        m = (m | (m >> 2)) & 0x0f0f0f0fu;
-                        m = (m | (m >> 4)) & 0x00ff00ffu;
-                        m = (m | (m >> 8)) & 0x0000ffffu;
-                        int bit = gbase - wbeg;
-                        atomicOr(&s_cand[bit >> 5], m << (bit & 31));
+                    const int o_lo = max(a + delta, o) - o, o_hi = min(b + delta, o + 16) - o;
+                    m &= range_mask32(2 * o_lo, 2 * o_hi);
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        flag_candidate(w, o + (bit >> 1) - delta);
                     }
                 }
             }
@@ -161,23 +221,23 @@ __device__ __forceinline__ void screen_record(const ngsep_read_hdr& h, const uin
             if (v & 2u) rpos += len;
         }
     }
-    mark_bits(s_cov, max(cov_lo, lo) - wbeg, min(ref_idx, hi) - wbeg);  // PR.addAlignment: first <= pos <= last (PR:154-156)
+    if (h.meta & NGSEP_M_WINDOW) { w.mset[M_HASVER] = 1; return INT_MIN; }
+    return ref_idx;   // 1-based last covered position (0-based exclusive end)
+}
+
+// Coverage interval [s,e] (1-based, inclusive) of any record: own start .. last reference position, cut by the valid window.
+__device__ __forceinline__ void record_interval(const ngsep_read_hdr& h, const uint32_t* pay, int& s, int& e) {
+    const RecView r = view_record(h, pay);
+    int ref_len = 0;
+    for (int c = 0; c < r.nc; c++) { const uint32_t v = r.cig[c]; if (v & 1u) ref_len += (int)(v >> 3); }
+    s = r.first; e = r.first + ref_len - 1;
+    if (r.vfrom != INT_MIN) s = max(s, r.vfrom);
+    if (r.vto != INT_MAX) e = min(e, r.vto - 1);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// exact: per-candidate state and the restatement of getAlleleCalls(1) + updateCounts
+// exact: restatement of getAlleleCalls(1) + updateCounts for one (record, position)
 // ------------------------------------------------------------------------------------------------------------
-struct ColState {
-    int c0, c1, c2, c3, depth;
-    int sn0, sn1, sn2, sn3, sp0, sp1, sp2, sp3;  // negative / positive strand per allele
-    double d0, d1, d2, d3, o01, o02, o03, o12, o13, o23;
-};
-__device__ __forceinline__ void col_init(ColState& s) {
-    s.c0 = s.c1 = s.c2 = s.c3 = s.depth = 0;
-    s.sn0 = s.sn1 = s.sn2 = s.sn3 = s.sp0 = s.sp1 = s.sp2 = s.sp3 = 0;
-    s.d0 = s.d1 = s.d2 = s.d3 = s.o01 = s.o02 = s.o03 = s.o12 = s.o13 = s.o23 = 0.0;
-}
-
 // Read offset aligned to reference position pos when that base is SNV evidence, else -1.
 // Restates RA.getAlignedReadPosition (RA:842-871) and the skip rules of RA.updateAlleleCallsInfo (RA:782-795);
 // an indel anchor has allele-call length > 1 and is dropped by PR.getAlleleCalls (PR:145).
@@ -202,19 +262,16 @@ __device__ __forceinline__ int resolve_offset(const RecView& r, int ign_s, int i
                 int rp = read_pos + j;
                 if (rp < 0 || rp >= r.L) return -1;
                 bool next_indel = false;
-                int next_cons = 0;
                 if (c + 1 < r.nc) {
                     uint32_t nv = r.cig[c + 1];
                     uint32_t nop = nv & 7u;
                     next_indel = (nop == 1u || nop == 2u);
-                    next_cons = (nv & 2u) ? (int)(nv >> 3) : 0;
                 }
                 bool skip = rp < ign_s;
                 skip = skip || (r.L - rp) <= ign_e;
                 skip = skip || (prev_indel && j < 2);
                 skip = skip || (next_indel && j < len - 1 && j >= len - 2);
                 if (next_indel && j == len - 1) return -1;  // anchor: either skipped or an indel call (length > 1)
-                (void)next_cons;
                 return skip ? -1 : rp;
             }
         }
@@ -225,30 +282,21 @@ __device__ __forceinline__ int resolve_offset(const RecView& r, int ign_s, int i
     return -1;
 }
 
-__device__ __forceinline__ void col_add(ColState& s, const RecView& r, int off, const double* s_tab, int max_qs) {
-    s.depth++;  // CH:210 totalCount counts every call returned by getAlleleCalls(1), whatever its quality or base
+// One lane = one record.  code: bits 0-1 allele, 2-6 quality, 7 negative strand, 8 counted (CH:223), 9 call returned
+// by getAlleleCalls(1) (counts for totalCount, CH:210).
+constexpr uint32_t kCodeNeg = 1u << 7, kCodeCounted = 1u << 8, kCodeCall = 1u << 9;
+
+__device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, int pos, int max_qs) {
+    const RecView r = view_record(h, pay);
+    const int off = resolve_offset(r, h.ign_start, h.ign_end, pos);
+    if (off < 0) return 0u;
     int q = (int)r.q[off] - 33;
     q = min(30, q);                                   // CH:91
-    if (q <= 3) return;                               // CH:214-216
+    if (q <= 3) return kCodeCall;                     // CH:214-216
     if (q > max_qs) q = max_qs;                       // CH:217-219
-    if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) return;  // allele not in ACGT: CH:220-221
-    int b = (int)((r.b2[off >> 4] >> ((off & 15) * 2)) & 3u);
-    bool neg = (r.meta & NGSEP_M_NEG) != 0;
-    s.c0 += (b == 0); s.c1 += (b == 1); s.c2 += (b == 2); s.c3 += (b == 3);
-    s.sn0 += (neg && b == 0); s.sn1 += (neg && b == 1); s.sn2 += (neg && b == 2); s.sn3 += (neg && b == 3);
-    s.sp0 += (!neg && b == 0); s.sp1 += (!neg && b == 1); s.sp2 += (!neg && b == 2); s.sp3 += (!neg && b == 3);
-    const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
-    // CH:231-249 with f == g == 250: one add per genotype per call, in pileup order
-    s.d0 += (b == 0) ? ta : tb;
-    s.d1 += (b == 1) ? ta : tb;
-    s.d2 += (b == 2) ? ta : tb;
-    s.d3 += (b == 3) ? ta : tb;
-    s.o01 += (b == 0 || b == 1) ? tc : tb;
-    s.o02 += (b == 0 || b == 2) ? tc : tb;
-    s.o03 += (b == 0 || b == 3) ? tc : tb;
-    s.o12 += (b == 1 || b == 2) ? tc : tb;
-    s.o13 += (b == 1 || b == 3) ? tc : tb;
-    s.o23 += (b == 2 || b == 3) ? tc : tb;
+    if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) return kCodeCall;  // allele not in ACGT: CH:220-221
+    const uint32_t b = (r.b2[off >> 4] >> ((off & 15) * 2)) & 3u;
+    return kCodeCall | kCodeCounted | b | ((uint32_t)q << 2) | ((r.meta & NGSEP_M_NEG) ? kCodeNeg : 0u);
 }
 
 __device__ __forceinline__ int dev_phred(double p) {  // math/PhredScoreHelper.java:31-40
@@ -259,53 +307,50 @@ __device__ __forceinline__ int dev_phred(double p) {  // math/PhredScoreHelper.j
     return (int)((score - f >= 0.5) ? f + 1.0 : f);  // Math.round
 }
 
-// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223
-__device__ void col_finalize(const ColState& s, int pos, int ref, const TileDev& d, const DevParams& prm, const double* s_tab) {
-    double Lm[16];
-    Lm[0] = s.d0; Lm[5] = s.d1; Lm[10] = s.d2; Lm[15] = s.d3;
-    Lm[1] = Lm[4] = s.o01; Lm[2] = Lm[8] = s.o02; Lm[3] = Lm[12] = s.o03;
-    Lm[6] = Lm[9] = s.o12; Lm[7] = Lm[13] = s.o13; Lm[11] = Lm[14] = s.o23;
-    const double lp_hom = s_tab[93], lp_het = s_tab[94];
-    double ev[16];
-    {
-        int k = 0;
-        for (int i = 0; i < 4; i++) {
-            ev[k++] = Lm[i * 5] + lp_hom;
-            for (int j = 0; j < 4; j++) if (i != j) ev[k++] = Lm[i * 4 + j] + lp_het;
-        }
-    }
-    double log_max = 1.0;  // CH:474-479, quirk kept: starts at 1 and is replaced by the first event
-    for (int k = 0; k < 16; k++) if (log_max > 0.0 || log_max < ev[k]) log_max = ev[k];
+constexpr unsigned kFull = 0xffffffffu;
+
+// index of the ordered event (i,j) in CH.getPosteriorProbabilities' enumeration (CH:416-430): per first allele i, the
+// homozygous event, then the heterozygous ones with j ascending
+__device__ __forceinline__ int ev_index(int i, int j) { return i * 4 + ((i == j) ? 0 : ((j < i) ? j + 1 : j)); }
+
+struct ColCounts { int c[4], sn[4], depth; };
+
+// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223, one warp per column.
+// `acc` is lane-owned: lanes 0-3 hold L[i][i], lanes 4-9 hold L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3].
+__device__ __forceinline__ void finalize_warp(double acc, const ColCounts& cc, int lane, int pos, int ref, const TileDev& d, const DevParams& prm,
+                                              const double* s_tab) {
+    const int k = lane & 15;
+    const int i = k >> 2, r = k & 3;
+    const int j = (r == 0) ? i : ((r - 1 < i) ? r - 1 : r);
+    const int lo = min(i, j), hi = max(i, j);
+    const int owner = (i == j) ? i : ((lo == 0) ? 3 + hi : ((lo == 1) ? 5 + hi : 9));
+    const double Lij = __shfl_sync(kFull, acc, owner);
+    const double ev = Lij + ((i == j) ? s_tab[93] : s_tab[94]);
+    double mx = ev;   // CH:474-479: the quirk "starts at 1 and is replaced by the first event" reduces to the maximum
+    for (int o = 8; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+    double e = ev - mx;
+    e = (e < -20.0) ? 0.0 : exp10(e);
     double total = 0.0;
-    for (int k = 0; k < 16; k++) {
-        double e = ev[k] - log_max;
-        e = (e < -20.0) ? 0.0 : exp10(e);
-        ev[k] = e;
-        total += e;
-    }
-    double post[16];
-    {
-        int k = 0;
-        for (int i = 0; i < 4; i++) {
-            post[i * 5] = ev[k++] / total;
-            for (int j = 0; j < 4; j++) if (i != j) post[i * 4 + j] = ev[k++] / total;
-        }
-    }
-    // VD.getIndexesMaxGenotype (VD:223-243)
+    for (int t = 0; t < 16; t++) total += __shfl_sync(kFull, e, t);   // CH:480-486, same order
+    const double post = e / total;
+    // VD.getIndexesMaxGenotype (VD:223-243), every lane redundantly
+    const double p_ref = __shfl_sync(kFull, post, ev_index(ref, ref));
     int ii = ref, jj = ref;
-    double pmax = post[ref * 5];
-    for (int i = 0; i < 4; i++) for (int j = i; j < 4; j++) {
-        double gp = post[i * 4 + j];
-        if (i != j) gp += post[j * 4 + i];
-        if (gp > pmax + 0.01) { pmax = gp; ii = i; jj = j; }
-    }
-    double max_p = post[ii * 4 + jj];
-    if (ii != jj) max_p += post[jj * 4 + ii];
-    int gq = dev_phred(1.0 - max_p);
+    double pmax = p_ref;
+    for (int a = 0; a < 4; a++)
+        for (int b = a; b < 4; b++) {
+            double gp = __shfl_sync(kFull, post, ev_index(a, b));
+            if (a != b) gp += __shfl_sync(kFull, post, ev_index(b, a));
+            if (gp > pmax + 0.01) { pmax = gp; ii = a; jj = b; }
+        }
+    double max_p = __shfl_sync(kFull, post, ev_index(ii, jj));
+    if (ii != jj) max_p += __shfl_sync(kFull, post, ev_index(jj, ii));
+    const double p_ii = __shfl_sync(kFull, post, ev_index(ii, ii));
+    const double p_jj = __shfl_sync(kFull, post, ev_index(jj, jj));
     int kind, a0, a1;
     if (ii != jj && ii != ref && jj != ref) {  // VD:128-177
         kind = NGSEP_CALL_TRIALLELIC;
-        if (post[ii * 5] > post[jj * 5] + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
+        if (p_ii > p_jj + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
     } else if (ii != jj) {
         kind = NGSEP_CALL_HET; a0 = ref; a1 = (ref != ii) ? ii : jj;
     } else if (ii != ref) {
@@ -313,205 +358,391 @@ __device__ void col_finalize(const ColState& s, int pos, int ref, const TileDev&
     } else {
         return;  // homozygous reference: dropped by SSVPL:223
     }
+    const int gq = dev_phred(1.0 - max_p);
     if (prm.min_quality > gq) return;  // SSVPL:223
-    unsigned int slot = atomicAdd(d.n_calls, 1u);
-    if (slot >= d.cap_calls) return;   // host sees n_calls > cap and reports NGSEP_EOVERFLOW
+    unsigned int slot = 0;
+    if (lane == 0) slot = atomicAdd(d.n_calls, 1u);
+    slot = __shfl_sync(kFull, slot, 0);
+    if (slot >= d.cap_calls) return;   // host sees n_calls > cap and reports NGSEP_EOVERFLOW (or grows and reruns)
     ngsep_snv_call* o = &d.calls[slot];
-    o->seq_idx = d.seq_idx; o->pos = pos;
-    o->count[0] = s.c0; o->count[1] = s.c1; o->count[2] = s.c2; o->count[3] = s.c3;
-    o->depth = s.depth;
-    o->strand[0] = s.sn0; o->strand[1] = s.sp0; o->strand[2] = s.sn1; o->strand[3] = s.sp1;
-    o->strand[4] = s.sn2; o->strand[5] = s.sp2; o->strand[6] = s.sn3; o->strand[7] = s.sp3;
-    for (int k = 0; k < 16; k++) o->logcond[k] = Lm[k];
-    o->post_ref = post[ref * 5];
-    o->post_max = max_p;
-    o->gq = (int16_t)gq;
-    o->qual = (int16_t)dev_phred(post[ref * 5]);
-    o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
-    o->sample = 0;
+    if (lane < 16) o->logcond[i * 4 + j] = Lij;
+    if (lane == 16) {
+        o->seq_idx = d.seq_idx; o->pos = pos;
+        o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
+        o->depth = cc.depth;
+        for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
+    }
+    if (lane == 17) {
+        o->post_ref = p_ref;
+        o->post_max = max_p;
+        o->gq = (int16_t)gq;
+        o->qual = (int16_t)dev_phred(p_ref);
+        o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
+        o->sample = 0;
+    }
+}
+
+// Records of the window as the exact phase sees them: the staged copy in shared memory, or (windows too deep to stage
+// in one piece) the tile's arrays in global memory through L2.
+template <bool kGlobal>
+struct Recs {
+    const ngsep_read_hdr* hdr;   // record 0 = first record of the window
+    const uint32_t* pay;         // payload word 0 = word `pay_base` of the tile
+    uint32_t pay_base;
+    int n;
+    __device__ __forceinline__ ngsep_read_hdr header(int i) const {
+        int4 v;
+        if (kGlobal) v = __ldg((const int4*)(hdr + i)); else v = *(const int4*)(hdr + i);
+        ngsep_read_hdr h;
+        h.first = v.x; h.meta = (uint32_t)v.y; h.ign_start = (int16_t)(v.z & 0xffff); h.ign_end = (int16_t)((uint32_t)v.z >> 16); h.off = (uint32_t)v.w;
+        return h;
+    }
+    __device__ __forceinline__ int first(int i) const { return kGlobal ? __ldg(&hdr[i].first) : hdr[i].first; }
+    __device__ __forceinline__ const uint32_t* payload(const ngsep_read_hdr& h) const { return pay + (h.off - pay_base); }
+};
+
+// first record index whose ordering start is >= want (warp-cooperative 32-ary search; every lane returns the result)
+template <bool kGlobal>
+__device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want, int lane) {
+    int lo = 0, hi = R.n;
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) >> 5;
+        const int idx = lo + lane * step;
+        const bool lt = idx < hi && R.first(idx) < want;
+        const int kk = __popc(__ballot_sync(kFull, lt));   // lanes 0..kk-1 probe records below `want` (monotone)
+        if (kk == 0) { hi = lo; break; }
+        const int nlo = lo + (kk - 1) * step + 1;
+        hi = min(hi, lo + kk * step);
+        lo = nlo;
+    }
+    if (hi > lo) {
+        const int idx = lo + lane;
+        const bool lt = idx < hi && R.first(idx) < want;
+        lo += __popc(__ballot_sync(kFull, lt));
+    }
+    return lo;
+}
+
+struct ExactCtx {
+    int wbeg, n_cand, max_span, max_back;
+    const uint16_t* s_list;
+    const uint32_t *s_ref2, *s_refn, *s_refl;
+    const double* s_tab;
+    const int* s_kmin;
+    bool emit_all, ignore_lower;
+};
+
+template <bool kGlobal>
+__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const TileDev& d, const DevParams& prm, int warp, int lane) {
+    const int max_qs = prm.max_base_qs;
+    for (int ci = warp; ci < x.n_cand; ci += kWarps) {
+        const int li = (int)x.s_list[ci];
+        const int pos = x.wbeg + li + 1;
+        if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) continue;   // SSVPL:198: no discovery at all
+        const bool ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
+        if (ref_bad && !x.emit_all) continue;                                       // VD:101-107
+        const int rr = li + kRefLeft;
+        const int ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
+        const int i_lo = warp_lower_bound(R, pos - x.max_span + 1, lane);
+        const int last_key = pos + x.max_back;
+        // ---- pass 1: exact integer counts ---------------------------------------------------------------------
+        ColCounts cc;
+        for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
+        cc.depth = 0;
+        for (int base = i_lo; base < R.n; base += 32) {
+            const int idx = base + lane;
+            uint32_t code = 0u;
+            bool in = false;
+            if (idx < R.n) {
+                const ngsep_read_hdr h = R.header(idx);
+                in = h.first <= last_key;
+                if (in) code = lane_eval(h, R.payload(h), pos, max_qs);
+            }
+            const unsigned inm = __ballot_sync(kFull, in);
+            cc.depth += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));
+            const unsigned ng = __ballot_sync(kFull, (code & kCodeNeg) != 0u);
+            const bool counted = (code & kCodeCounted) != 0u;
+            for (int b = 0; b < 4; b++) {
+                const unsigned mb = __ballot_sync(kFull, counted && (int)(code & 3u) == b);
+                cc.c[b] += __popc(mb);
+                cc.sn[b] += __popc(mb & ng);
+            }
+            if (inm != kFull) break;   // sorted by start: nothing further can cover pos
+        }
+        if (x.emit_all && d.counts_dbg && lane == 0) {
+            int32_t* o = d.counts_dbg + (int64_t)(pos - d.tile_first) * 5;
+            o[0] = cc.c[0]; o[1] = cc.c[1]; o[2] = cc.c[2]; o[3] = cc.c[3]; o[4] = cc.depth;
+        }
+        if (ref_bad || cc.depth == 0) continue;   // VD:101-107
+        const int tot = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
+        const int k_ref = (ref == 0) ? cc.c[0] : ((ref == 1) ? cc.c[1] : ((ref == 2) ? cc.c[2] : cc.c[3]));
+        const int m_alt = tot - k_ref;
+        // Proven hom-ref: no counted non-reference base, or k >= k_min[m] counted reference bases:
+        // P(ref,ref) > 1/2, VD.discoverSNV returns the homozygous-reference call that SSVPL:223 drops.
+        if (prm.fast_homref && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= x.s_kmin[m_alt]))) continue;
+        // ---- pass 2: the 10 distinct log-likelihoods, one per lane, summed in pileup order (CH:231-249) --------------------
+        const int pa = (lane < 4) ? lane : ((lane < 7) ? 0 : ((lane < 9) ? 1 : 2));
+        const int pb = (lane < 4) ? lane : ((lane < 7) ? lane - 3 : ((lane < 9) ? lane - 5 : 3));
+        double acc = 0.0;
+        for (int base = i_lo; base < R.n; base += 32) {
+            const int idx = base + lane;
+            uint32_t code = 0u;
+            bool in = false;
+            if (idx < R.n) {
+                const ngsep_read_hdr h = R.header(idx);
+                in = h.first <= last_key;
+                if (in) code = lane_eval(h, R.payload(h), pos, max_qs);
+            }
+            const unsigned inm = __ballot_sync(kFull, in);
+            unsigned cm = __ballot_sync(kFull, (code & kCodeCounted) != 0u);
+            while (cm) {
+                const int src = __ffs(cm) - 1;
+                cm &= cm - 1;
+                const uint32_t cj = __shfl_sync(kFull, code, src);
+                const int b = (int)(cj & 3u), q = (int)((cj >> 2) & 31u);
+                const double ta = x.s_tab[3 * q], tb = x.s_tab[3 * q + 1], tc = x.s_tab[3 * q + 2];
+                const double term = (lane < 4) ? ((b == lane) ? ta : tb) : ((b == pa || b == pb) ? tc : tb);
+                acc += term;
+            }
+            if (inm != kFull) break;
+        }
+        finalize_warp(acc, cc, lane, pos, ref, d, prm, x.s_tab);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // the window kernel
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_pileup_windows(const TileDev d, const DevParams* __restrict__ gprm) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout lay = make_layout(d.T, d.pay_cap_words);
-    uint64_t* bar = (uint64_t*)(smem + lay.bar);
-    double* s_tab = (double*)(smem + lay.tab);
-    uint32_t* s_ref2 = (uint32_t*)(smem + lay.ref2);
-    uint32_t* s_refn = (uint32_t*)(smem + lay.refn);
-    uint32_t* s_refl = (uint32_t*)(smem + lay.refl);
-    uint32_t* s_cand = (uint32_t*)(smem + lay.cand);
-    uint32_t* s_cov = (uint32_t*)(smem + lay.cov);
-    uint16_t* s_list = (uint16_t*)(smem + lay.list);
-    int* s_misc = (int*)(smem + lay.misc);
-    ngsep_read_hdr* s_hdr = (ngsep_read_hdr*)(smem + lay.hdr);
-    uint32_t* s_pay = (uint32_t*)(smem + lay.pay);
+struct KArgs {
+    const TileDev* tiles;
+    const WinRange* win;
+    int n_windows;
+    const DevParams* prm;
+    LaunchCfg cfg;
+};
 
-    const int tid = threadIdx.x;
-    const int T = d.T;
-    const DevParams& prm = *gprm;
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const KArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const SmemLayout lay = make_layout(a.cfg.T_lay, a.cfg.pay_cap_words, a.cfg.n_stages);
+    uint64_t* s_bar = (uint64_t*)(smem + lay.bar);
+    double* s_tab = (double*)(smem + lay.tab);
+    int* s_kmin = (int*)(smem + lay.kmin);
+    int* s_misc = (int*)(smem + lay.misc);
+    uint32_t* s_bm = (uint32_t*)(smem + lay.bm);
+    uint16_t* s_list = (uint16_t*)(smem + lay.list);
+    int* s_wmax = (int*)(smem + lay.wmax);
+    int2* s_rare = (int2*)(smem + lay.rare);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DevParams& prm = *a.prm;
     for (int i = tid; i < NGSEP_N_TABLES; i += kThreads) s_tab[i] = prm.tables[i];
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
+    if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
+    for (int i = tid; i < a.cfg.T_lay / 32 + 1; i += kThreads) s_bm[i] = 0u;
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
-    uint32_t parity = 0;
+    uint32_t phase[2] = {0u, 0u};
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const int n_stages = a.cfg.n_stages;
 
-    for (int w = blockIdx.x; w < d.n_windows; w += gridDim.x) {
-        const int wbeg = (d.win0 + w) * T;                       // 0-based index of the window's first position
-        const int g_lo = max(wbeg, d.tile_first - 1);            // [g_lo, g_hi): indexes of this window inside the tile
+    auto fits = [&](const WinRange& wr) {
+        return (wr.hi - wr.lo) <= (int)lay.max_reads && (wr.off_hi - (wr.off_lo & ~3u)) <= a.cfg.pay_cap_words;
+    };
+    // thread 0: one mbarrier phase = the reference window + (windows that fit a stage) the whole record range
+    auto issue_window = [&](const WinRange& wr, int stage) {
+        const TileDev& d = a.tiles[wr.tile];
+        unsigned char* stg = smem + lay.stage0 + (unsigned)stage * lay.stage_stride;
+        uint64_t* bar = &s_bar[stage];
+        const int T = d.T;
+        const int64_t wbeg = (int64_t)wr.wabs * T;
+        const uint32_t b_ref2 = (uint32_t)(T + 2 * kRefLeft) / 4u, b_bits = (uint32_t)T / 8u;
+        const bool recs = fits(wr) && wr.hi > wr.lo;
+        const uint32_t o0 = wr.off_lo & ~3u;
+        const uint32_t hb = recs ? (uint32_t)(wr.hi - wr.lo + 1) * 16u : 0u;   // + the next record's header (sentinel)
+        const uint32_t pb = recs ? (((wr.off_hi - o0) * 4u + 15u) & ~15u) : 0u;
+        mbar_expect_tx(bar, b_ref2 + b_bits + (ignore_lower ? b_bits : 0u) + hb + pb);
+        bulk_g2s(stg + lay.o_ref2, (const unsigned char*)d.ref2 + (wbeg - kRefLeft) / 4, b_ref2, bar);
+        bulk_g2s(stg + lay.o_refn, (const unsigned char*)d.ref_n + wbeg / 8, b_bits, bar);
+        if (ignore_lower) bulk_g2s(stg + lay.o_refl, (const unsigned char*)d.ref_l + wbeg / 8, b_bits, bar);
+        if (hb) bulk_g2s(stg + lay.o_hdr, d.hdr + wr.lo, hb, bar);
+        if (pb) bulk_g2s(stg + lay.o_pay, d.payload + o0, pb, bar);
+    };
+
+    int w = blockIdx.x;
+    if (w >= a.n_windows) return;
+    WinRange wr = a.win[w];
+    bool prefetched = false;   // thread 0: the records of window w are already in flight
+    for (int it = 0; w < a.n_windows; it++) {
+        const int cur = (n_stages == 2) ? (it & 1) : 0;
+        const int wn = w + (int)gridDim.x;
+        WinRange nr = wr;
+        if (wn < a.n_windows) nr = a.win[wn];
+        if (tid == 0) {
+            if (!prefetched) issue_window(wr, cur);
+            prefetched = false;
+            if (n_stages == 2 && wn < a.n_windows) { issue_window(nr, cur ^ 1); prefetched = true; }   // other stage: free since the trailing barrier
+        }
+        const TileDev& d = a.tiles[wr.tile];
+        const int T = d.T;
+        const int wbeg = wr.wabs * T;
+        const int g_lo = max(wbeg, d.tile_first - 1);
         const int g_hi = (int)min((int64_t)min(wbeg + T, d.tile_last), d.ref_len);
-        const WinRange wr = d.win[w];
-        // stage the reference window + clear the bitmaps
-        for (int i = tid; i < T / 16 + 1; i += kThreads) {
-            int64_t gw = (int64_t)(wbeg >> 4) + i;
-            s_ref2[i] = (gw * 16 < d.ref_len) ? d.ref2[gw] : 0u;
-        }
-        for (int i = tid; i < T / 32; i += kThreads) {
-            int64_t gw = (int64_t)(wbeg >> 5) + i;
-            bool in = gw * 32 < d.ref_len;
-            s_refn[i] = in ? d.ref_n[gw] : 0xffffffffu;
-            s_refl[i] = in ? d.ref_l[gw] : 0u;
-            s_cand[i] = 0u;
-            s_cov[i] = 0u;
-        }
-        __syncthreads();
+        const int A = g_lo + 1, B = g_hi;   // 1-based inclusive positions of the window (empty when A > B)
+        const int n_rec = wr.hi - wr.lo;
+        const bool single = fits(wr);
+        unsigned char* stg = smem + lay.stage0 + (unsigned)cur * lay.stage_stride;
+        const ngsep_read_hdr* s_hdr = (const ngsep_read_hdr*)(stg + lay.o_hdr);
+        const uint32_t* s_pay = (const uint32_t*)(stg + lay.o_pay);
+        int* mset = s_misc + (it & 1) * kMiscSet;
+        WinCtx wc;
+        wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
+        wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
+        wc.s_bm = s_bm; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
 
-        const bool single_chunk = (wr.hi - wr.lo) <= (int)lay.max_reads && (wr.off_hi - (wr.off_lo & ~3u)) <= d.pay_cap_words;
-        int n_chunk = 0;         // records in the currently staged chunk
-        uint32_t pay_base = 0;   // payload word offset staged at s_pay[0]
-        int chunk_lo = 0;        // first record of the staged chunk
+        mbar_wait(&s_bar[cur], phase[cur]);
+        phase[cur] ^= 1u;
 
-        // ---- chunk loader (all threads call; thread 0 issues the bulk copies) ------------------------------------
-        auto load_chunk = [&](int r0) {
-            if (tid == 0) {
-                int r1;
-                if (single_chunk) r1 = wr.hi;
-                else {
-                    uint32_t base = d.hdr[r0].off & ~3u;
-                    int lo_r = r0 + 1, hi_r = min(wr.hi, r0 + (int)lay.max_reads);
-                    r1 = r0;  // largest r1 in (r0, hi_r] with off[r1] - base <= cap
-                    while (lo_r <= hi_r) {
-                        int mid = (lo_r + hi_r) >> 1;
-                        if (d.hdr[mid].off - base <= d.pay_cap_words) { r1 = mid; lo_r = mid + 1; } else hi_r = mid - 1;
-                    }
-                    if (r1 == r0) r1 = r0 + 1;  // cannot happen: tile_submit rejects records larger than a chunk
+        // ---- phase A: screen + coverage scan, one thread per record -------------------------------------------------
+        // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
+        // positions of (reach_i, s_{i+1}) are covered by nobody.  reach_i is at least the warp-local prefix maximum; only
+        // when that does not reach s_{i+1} - 1 is the record queued for the exact cross-warp evaluation (process_rare).
+        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, bool first_chunk) {
+            for (int base = 0; base < n_chunk; base += kThreads) {
+                const int i = base + tid;
+                const bool act = i < n_chunk;
+                int e = INT_MIN, nxt = INT_MIN, floor_i = INT_MAX;
+                if (act) {
+                    const ngsep_read_hdr h = s_hdr[i];
+                    const uint32_t* pay = s_pay + (h.off - pay_base);
+                    e = record_is_simple(h, pay) ? screen_simple(h, pay, wc) : screen_general(h, pay, wc);
+                    nxt = min(s_hdr[i + 1].first, B + 1);
+                    floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
+                    if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
                 }
-                uint32_t o0 = (single_chunk ? wr.off_lo : d.hdr[r0].off) & ~3u;
-                uint32_t o1 = single_chunk ? wr.off_hi : d.hdr[r1].off;
-                uint32_t hb = (uint32_t)(r1 - r0 + 1) * 16u;                 // headers incl. the next record's (sentinel) header
-                uint32_t pb = ((o1 - o0) * 4u + 15u) & ~15u;
-                s_misc[0] = r1;
-                s_misc[1] = (int)o0;
-                if (r1 > r0) {
-                    mbar_expect_tx(bar, hb + pb);
-                    bulk_g2s(s_hdr, d.hdr + r0, hb, bar);
-                    if (pb) bulk_g2s(s_pay, d.payload + o0, pb, bar);
-                }
+                int run = e;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, run, o); if (lane >= o) run = max(run, t); }
+                if (lane == 31) s_wmax[(base >> 5) + warp] = run;
+                if (act && nxt - 1 > max(run, floor_i)) s_rare[atomicAdd(&mset[M_NRARE], 1)] = make_int2(i, run);
             }
-            __syncthreads();
-            int r1 = s_misc[0];
-            if (r1 > r0) { mbar_wait(bar, parity); parity ^= 1u; }
-            n_chunk = r1 - r0;
-            pay_base = (uint32_t)s_misc[1];
-            chunk_lo = r0;
-            return r1;
+        };
+        auto process_rare = [&](int carry) {
+            const int n_rare = mset[M_NRARE];
+            for (int k = tid; k < n_rare; k += kThreads) {
+                const int2 rr = s_rare[k];
+                int reach = max(max(rr.y, A - 1), max(carry, s_hdr[rr.x].first - 1));
+                for (int c = 0; c < (rr.x >> 5); c++) reach = max(reach, s_wmax[c]);
+                const int gap = min(s_hdr[rr.x + 1].first, B + 1) - 1 - reach;
+                if (gap > 0) atomicAdd(&mset[M_UNC], gap);
+            }
         };
 
-        // ---- phase A: screen ---------------------------------------------------------------------------------
-        {
+        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += kThreads) s_list[i] = (uint16_t)(g_lo - wbeg + i);
+        if (single) {
+            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, true);
+            else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
+        } else {
+            // windows too deep for one stage: stream the record range chunk by chunk through the current stage
             int r0 = wr.lo;
+            bool first_chunk = true;
             while (r0 < wr.hi) {
-                int r1 = load_chunk(r0);
-                for (int i = tid; i < n_chunk; i += kThreads)
-                    screen_record(s_hdr[i], s_pay + (s_hdr[i].off - pay_base), g_lo, g_hi, wbeg, s_ref2, s_cand, s_cov);
-                __syncthreads();
-                r0 = r1;
-            }
-        }
-        // ---- candidate list (one warp) -----------------------------------------------------------------------
-        if (tid < 32) {
-            int total = 0, covered = 0;
-            for (int base_w = 0; base_w < T / 32; base_w += 32) {
-                int wi = base_w + tid;
-                uint32_t cw = 0, vw = 0;
-                if (wi < T / 32) {
-                    vw = s_cov[wi];
-                    cw = emit_all ? vw : (s_cand[wi] & vw & ~s_refn[wi]);
-                    if (ignore_lower) cw &= ~s_refl[wi];
-                }
-                int c = __popc(cw);
-                int incl = c;
-                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += t; }
-                int start = total + incl - c;
-                while (cw) { int b = __ffs(cw) - 1; cw &= cw - 1; s_list[start++] = (uint16_t)(wi * 32 + b); }
-                total += __shfl_sync(0xffffffffu, incl, 31);
-                int cv = __popc(vw);
-                for (int o = 16; o > 0; o >>= 1) cv += __shfl_xor_sync(0xffffffffu, cv, o);
-                covered += cv;
-            }
-            if (tid == 0) {
-                s_misc[2] = total;
-                if (covered) atomicAdd(&d.counters[0], (unsigned long long)covered);
-                if (total) atomicAdd(&d.counters[1], (unsigned long long)total);
-            }
-        }
-        __syncthreads();
-        const int n_cand = s_misc[2];
-
-        // ---- phase B: exact evaluation, kThreads candidates per round ----------------------------------------------
-        for (int base = 0; base < n_cand; base += kThreads) {
-            const bool active = base + tid < n_cand;
-            const int pos = active ? wbeg + (int)s_list[base + tid] + 1 : 0;  // 1-based
-            ColState st;
-            col_init(st);
-            int r0 = wr.lo;
-            while (r0 < wr.hi) {
-                int r1;
-                if (single_chunk) r1 = wr.hi;   // still resident from phase A
-                else r1 = load_chunk(r0);
-                if (active) {
-                    // records whose ordering start lies in [pos - max_span + 1, pos + max_back]
-                    int want = pos - d.max_span + 1;
-                    int lo_i = 0, hi_i = n_chunk;
-                    while (lo_i < hi_i) { int mid = (lo_i + hi_i) >> 1; if (s_hdr[mid].first < want) lo_i = mid + 1; else hi_i = mid; }
-                    const int last_first = pos + d.max_back;
-                    for (int i = lo_i; i < n_chunk; i++) {
-                        const ngsep_read_hdr h = s_hdr[i];
-                        if (h.first > last_first) break;
-                        RecView r = view_record(h, s_pay + (h.off - pay_base));
-                        int off = resolve_offset(r, h.ign_start, h.ign_end, pos);
-                        if (off >= 0) col_add(st, r, off, s_tab, prm.max_base_qs);
+                if (tid == 0) {
+                    const uint32_t base = d.hdr[r0].off & ~3u;
+                    int lo_r = r0 + 1, hi_r = min(wr.hi, r0 + (int)lay.max_reads), r1 = r0;
+                    while (lo_r <= hi_r) {
+                        const int mid = (lo_r + hi_r) >> 1;
+                        if (d.hdr[mid].off - base <= a.cfg.pay_cap_words) { r1 = mid; lo_r = mid + 1; } else hi_r = mid - 1;
                     }
+                    if (r1 == r0) r1 = r0 + 1;   // cannot happen: staging rejects records larger than a stage
+                    const uint32_t hb = (uint32_t)(r1 - r0 + 1) * 16u;
+                    const uint32_t pb = ((d.hdr[r1].off - base) * 4u + 15u) & ~15u;
+                    mset[M_R1] = r1;
+                    mset[M_PBASE] = (int)base;
+                    mbar_expect_tx(&s_bar[cur], hb + pb);
+                    bulk_g2s(stg + lay.o_hdr, d.hdr + r0, hb, &s_bar[cur]);
+                    if (pb) bulk_g2s(stg + lay.o_pay, d.payload + base, pb, &s_bar[cur]);
                 }
-                if (!single_chunk) __syncthreads();
+                __syncthreads();
+                const int r1 = mset[M_R1];
+                const uint32_t pay_base = (uint32_t)mset[M_PBASE];
+                const int carry = mset[M_CARRY];
+                mbar_wait(&s_bar[cur], phase[cur]);
+                phase[cur] ^= 1u;
+                screen_chunk(r1 - r0, pay_base, first_chunk);
+                __syncthreads();
+                process_rare(carry);
+                __syncthreads();
+                if (tid == 0) {
+                    int c = carry;
+                    for (int k = 0; k < ((r1 - r0 + 31) >> 5); k++) c = max(c, s_wmax[k]);
+                    mset[M_CARRY] = c;
+                    mset[M_NRARE] = 0;
+                }
+                first_chunk = false;
                 r0 = r1;
             }
-            if (active) {
-                const int li = pos - 1 - wbeg;
-                const bool ref_bad = (s_refn[li >> 5] >> (li & 31)) & 1u;
-                const int ref = (int)((s_ref2[li >> 4] >> ((li & 15) * 2)) & 3u);
-                if (emit_all && d.counts_dbg) {
-                    int32_t* o = d.counts_dbg + (int64_t)(pos - d.tile_first) * 5;
-                    o[0] = st.c0; o[1] = st.c1; o[2] = st.c2; o[3] = st.c3; o[4] = st.depth;
-                }
-                bool lower = ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u);
-                if (!ref_bad && !lower && st.depth > 0) {  // VD:101-107, SSVPL:198
-                    int nonref = st.c0 + st.c1 + st.c2 + st.c3 - ((ref == 0) ? st.c0 : (ref == 1) ? st.c1 : (ref == 2) ? st.c2 : st.c3);
-                    if (!(prm.fast_homref && nonref == 0)) col_finalize(st, pos, ref, d, prm, s_tab);
-                }
+        }
+        __syncthreads();   // ---- sync 1: candidates listed ---------------------------------------------------------------
+
+        if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
+        for (int i = tid; i < a.cfg.T_lay / 32 + 1; i += kThreads) s_bm[i] = 0u;
+        if (single && n_rec > 0) process_rare(INT_MIN);
+        const int n_cand = emit_all ? max(0, g_hi - g_lo) : mset[M_NCAND];
+
+        // ---- phase C: exact evaluation, one warp per candidate ------------------------------------------------------------
+        ExactCtx x;
+        x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = d.max_span; x.max_back = d.max_back;
+        x.s_list = s_list; x.s_ref2 = wc.s_ref2;
+        x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
+        x.s_tab = s_tab; x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
+        if (n_cand > 0 && n_rec > 0) {
+            if (single) {
+                Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
+                exact_phase<false>(R, x, d, prm, warp, lane);
+            } else {
+                Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
+                exact_phase<true>(R, x, d, prm, warp, lane);
             }
         }
-        __syncthreads();
+        __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
+
+        int uncovered = mset[M_UNC];
+        const int win_len = max(0, B - A + 1);
+        if (uncovered > 0 && mset[M_HASVER] && n_rec > 0) {
+            // rare: a gap in the cover of the unversioned records while realigner versions are present — count the cover
+            // of every record with a bitmap (s_bm is clear here and is cleared again below)
+            for (int i = tid; i < n_rec; i += kThreads) {
+                const ngsep_read_hdr h = d.hdr[wr.lo + i];
+                int s, e;
+                record_interval(h, d.payload + h.off, s, e);
+                s = max(s, A); e = min(e, B);
+                for (int p = s; p <= e; p++) { const int li = p - 1 - wbeg; atomicOr(&s_bm[li >> 5], 1u << (li & 31)); }
+            }
+            __syncthreads();
+            int cnt = 0;
+            for (int i = tid; i < T / 32; i += kThreads) cnt += __popc(s_bm[i]);
+            for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
+            if (lane == 0 && cnt) atomicAdd(&mset[M_FBCOV], cnt);
+            __syncthreads();
+            uncovered = win_len - mset[M_FBCOV];
+            for (int i = tid; i < T / 32; i += kThreads) s_bm[i] = 0u;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            const int covered = win_len - uncovered;
+            if (covered > 0) atomicAdd(&d.counters[0], (unsigned long long)covered);
+            if (n_cand > 0 && !emit_all) atomicAdd(&d.counters[1], (unsigned long long)n_cand);
+        }
+        w = wn;
+        wr = nr;
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // window index: record range + payload span of every window (two binary searches over the sorted starts)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_window_index(const TileDev d, WinRange* out) {
+__global__ void k_window_index(const TileDev d, WinRange* out, int tile_idx) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= d.n_windows) return;
     int64_t wbeg = (int64_t)(d.win0 + w) * d.T;
@@ -525,6 +756,7 @@ __global__ void k_window_index(const TileDev d, WinRange* out) {
     WinRange r;
     r.lo = a; r.hi = lo;
     r.off_lo = d.hdr[a].off; r.off_hi = d.hdr[lo].off;
+    r.tile = tile_idx; r.wabs = d.win0 + w;
     out[w] = r;
 }
 
@@ -553,18 +785,32 @@ __global__ void k_ref_pack(const char* __restrict__ ascii, int64_t len, uint32_t
     ref2[t * 2] = w0; ref2[t * 2 + 1] = w1; ref_n[t] = nb; ref_l[t] = lb;
 }
 
-void launch_window_index(const TileDev& d, cudaStream_t s) {
+void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s) {
     int n = d.n_windows;
-    k_window_index<<<(n + 127) / 128, 128, 0, s>>>(d, const_cast<WinRange*>(d.win));
+    if (n > 0) k_window_index<<<(n + 127) / 128, 128, 0, s>>>(d, out, tile_idx);
 }
 
-void launch_pileup(const TileDev& d, const DevParams* dprm, int grid, size_t smem, cudaStream_t s) {
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaFuncSetAttribute(k_pileup_windows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = smem;
-    }
-    k_pileup_windows<<<grid, kThreads, smem, s>>>(d, dprm);
+// The kernel is compiled for three register budgets (3, 4 or 5 resident CTAs per SM); the context picks one.
+typedef void (*PileupKernel)(const KArgs);
+static PileupKernel kernel_for(int min_blocks) {
+    if (min_blocks <= 3) return k_pileup_windows<3>;
+    if (min_blocks == 4) return k_pileup_windows<4>;
+    return k_pileup_windows<5>;
+}
+
+int pileup_max_ctas_per_sm(size_t smem, int min_blocks) {
+    PileupKernel k = kernel_for(min_blocks);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kThreads, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const LaunchCfg& cfg, int grid,
+                   size_t smem, cudaStream_t s) {
+    KArgs a;
+    a.tiles = d_tiles; a.win = d_win; a.n_windows = n_windows; a.prm = dprm; a.cfg = cfg;
+    kernel_for(cfg.min_blocks)<<<grid, kThreads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

@@ -1,19 +1,22 @@
 // Device side of libngsep_pileup.so: sm_100a kernels for the pileup walk + SNVQ genotype posterior.
 //
-// Design: reads are coordinate-sorted, so a window of T reference positions is covered by a
-// CONTIGUOUS range of read records.  One CTA owns one window at a time:
-//   load    one cp.async.bulk (TMA 1-D bulk copy, mbarrier completion) for the 16-byte headers and one for the
-//           packed payload (CIGAR | 2-bit bases | qualities) of the window's records -> shared memory;
-//   screen  thread-per-record, bit-parallel: XOR 16 packed read bases against 16 packed reference bases per
-//           instruction; only positions where some read disagrees with the reference can yield a non-hom-ref
-//           call (VD:100-222 starts from (ref,ref) and needs >0.01 more posterior to move), so only those become
-//           candidates (exact superset, no heuristics);
-//   exact   thread-per-candidate: walks the covering records IN PILEUP ORDER and restates
-//           PileupRecord.getAlleleCalls(1) / CountsHelper.updateCounts / getPosteriorProbabilities /
-//           VariantDiscoverySNVQAlgorithm.discoverSNV, summing the 10 distinct log-likelihoods in fp64 in the
-//           reference's own order (bit-identical logConditionalProbs given the same tables).
-// HBM traffic = each record once (plus the window halo, served by L2); no atomics on the data path except the
-// rare candidate-bit / call-slot claims.
+// Design.  Reads are coordinate-sorted, so a WINDOW of T reference positions is covered by a
+// CONTIGUOUS range of read records.  One persistent CTA owns one window at a time; ONE launch walks the windows of
+// every staged tile (all sequences of a genome):
+//   load    cp.async.bulk (TMA 1-D bulk copies, one mbarrier per stage): the window's 16-byte record headers, its
+//           packed payload (CIGAR | 2-bit bases | qualities) and the packed reference window -> shared memory;
+//   screen  thread-per-record, bit-parallel: 16 packed read bases XOR 16 packed reference bases per instruction.
+//           Only a position where some read base differs from the reference can give a non-hom-ref call
+//           (VD:100-222 starts from (ref,ref) and needs > 0.01 more posterior to move), so only those positions become
+//           candidates (an exact superset; no heuristic).  The same pass derives the covered-position count from a
+//           prefix-max scan over the sorted records (no atomics on the per-read path);
+//   exact   warp-per-candidate: the 32 lanes resolve the covering records IN PILEUP ORDER (restating
+//           PileupRecord.getAlleleCalls(1) / CountsHelper.updateCounts), ballots give the exact allele / strand counts,
+//           a proven bound drops columns whose posterior of (ref,ref) exceeds 1/2, and the survivors get the 10
+//           distinct log-likelihoods summed in fp64 in the reference's own order (bit-identical logConditionalProbs
+//           given the same tables) followed by CH.getPosteriorProbabilities / VD.discoverSNV, 16 events on 16 lanes.
+// HBM traffic = each record once (window halos are L2 hits); the only atomics on the data path are the rare
+// candidate-bit and call-slot claims.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -23,9 +26,12 @@
 namespace ngsep_b200 {
 
 constexpr int kThreads = 256;          // threads per CTA
-constexpr int kMaxChunkReads = 2048;   // records staged per chunk (headers: 32 KB + sentinel)
+constexpr int kWarps = kThreads / 32;
+constexpr int kRefLeft = 64;           // reference bases staged to the left of a window (read words straddle its start)
+constexpr int kMaxWindow = 8192;       // largest window length (positions); windows are multiples of 128
 
-struct WinRange { int lo, hi; uint32_t off_lo, off_hi; };  // record range [lo,hi) of a window and its payload span
+// Record range [lo,hi) of one window, its payload span (words) and where the window lives.
+struct WinRange { int lo, hi; uint32_t off_lo, off_hi; int tile; int wabs; };
 
 struct TileDev {
     const ngsep_read_hdr* hdr;   // [n_reads + 1], sentinel at n_reads carries off = n_words, first = INT_MAX
@@ -33,29 +39,38 @@ struct TileDev {
     const uint16_t* sample;
     int n_reads, max_span, max_back;
     int tile_first, tile_last, seq_idx;
-    const uint32_t* ref2;        // 2 bits/base, base idx i (0-based) at bits 2*(i%16) of word i/16
+    const uint32_t* ref2;        // 2 bits/base, base idx i (0-based) at bits 2*(i%16) of word i/16; 64 B of zero padding in front
     const uint32_t* ref_n;       // 1 bit/base: not ACGT (after upper-casing)
     const uint32_t* ref_l;       // 1 bit/base: lower case in the FASTA
     int64_t ref_len;
-    int T;                       // window length in positions (power of two, >= 64)
+    int T;                       // window length in positions (multiple of 128, <= the launch's layout window)
     int win0, n_windows;         // first absolute window index of the tile, number of windows
-    const WinRange* win;         // [n_windows]
     ngsep_snv_call* calls; unsigned int* n_calls; unsigned int cap_calls;
     int32_t* counts_dbg;         // [tile_len][5] or null
-    unsigned long long* counters;// [0] covered positions, [1] candidates, [2] aligned bases
-    unsigned int pay_cap_words;  // payload words that fit one staged chunk
+    unsigned long long* counters;// [0] covered positions, [1] candidates
 };
 
 struct DevParams {
     int max_base_qs, min_quality;
     unsigned int flags;
-    int fast_homref;             // 1: columns without a counted non-reference base are provably hom-ref
+    int fast_homref;             // 1: the proven hom-ref skips below are valid for these tables / priors
+    int k_min[16];               // k_min[m]: with m counted non-reference bases, k >= k_min[m] counted reference bases
+                                 // prove P(ref,ref) > 1/2; INT_MAX when no k suffices
     double tables[NGSEP_N_TABLES];
 };
 
-size_t pileup_smem_bytes(int T, unsigned int pay_cap_words);
-void launch_window_index(const TileDev& d, cudaStream_t s);
-void launch_pileup(const TileDev& d, const DevParams* dprm, int grid, size_t smem, cudaStream_t s);
+struct LaunchCfg {
+    int T_lay;                   // window length the shared-memory layout is sized for
+    unsigned int pay_cap_words;  // payload words one stage holds
+    int n_stages;                // 1 or 2 staged windows per CTA
+    int min_blocks;              // register budget: the kernel variant compiled for 3, 4 or 5 resident CTAs per SM
+};
+
+size_t pileup_smem_bytes(const LaunchCfg& cfg);
+void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
+int pileup_max_ctas_per_sm(size_t smem, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
+void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const LaunchCfg& cfg, int grid,
+                   size_t smem, cudaStream_t s);
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
 }  // namespace ngsep_b200

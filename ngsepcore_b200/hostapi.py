@@ -18,7 +18,7 @@ from .simulate import AlignmentBatch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
 EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
-           "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_host_pack", "ngsep_host_free"]
+           "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free"]
 
 
 class HostBatch(C.Structure):
@@ -64,6 +64,8 @@ def load_library() -> C.CDLL:
     lib.ngsep_ssvd_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
     lib.ngsep_host_pack.argtypes = [C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.ngsep_ssvd_pack.argtypes = [C.c_void_p, C.POINTER(HostBatch), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     lib.ngsep_host_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
@@ -139,6 +141,22 @@ class Detector:
         n = C.c_size_t()
         p = self.lib.ngsep_ssvd_vcf(self.h, C.byref(n))
         return C.string_at(p, n.value).decode()
+
+    def pack(self, batch: AlignmentBatch, seq_idx: int):
+        """The tile the detector submits for sequence seq_idx -> dict(hdr, payload, max_span, max_back, first, last, aligned_bases)."""
+        hb, keep = _host_batch(batch)
+        hdr_p, pay_p = C.c_void_p(), C.c_void_p()
+        n_reads, n_words, bases = C.c_int64(), C.c_uint64(), C.c_uint64()
+        span, back, tf, tl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = self.lib.ngsep_ssvd_pack(self.h, C.byref(hb), seq_idx, C.byref(hdr_p), C.byref(pay_p), C.byref(n_reads), C.byref(n_words),
+                                      C.byref(span), C.byref(back), C.byref(tf), C.byref(tl), C.byref(bases))
+        if rc != 0:
+            raise NgsepError(f"ngsep_ssvd_pack failed ({rc}): {self.lib.ngsep_ssvd_error(self.h).decode()}")
+        hdr = np.ctypeslib.as_array(C.cast(hdr_p, C.POINTER(C.c_uint8)), shape=(n_reads.value * 16,)).view(HDR_DTYPE).copy() if n_reads.value else np.zeros(0, HDR_DTYPE)
+        pay = np.ctypeslib.as_array(C.cast(pay_p, C.POINTER(C.c_uint32)), shape=(n_words.value,)).copy() if n_words.value else np.zeros(0, np.uint32)
+        self.lib.ngsep_host_free(hdr_p)
+        self.lib.ngsep_host_free(pay_p)
+        return dict(hdr=hdr, payload=pay, max_span=span.value, max_back=back.value, first=tf.value, last=tl.value, aligned_bases=bases.value)
 
     def stats(self) -> RunStats:
         s = RunStats()

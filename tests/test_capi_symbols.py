@@ -27,7 +27,7 @@ def test_struct_layouts_match_header():
     assert capi.HDR_DTYPE.itemsize == 16
     assert capi.CALL_DTYPE.itemsize == 224
     assert C.sizeof(capi.Params) == 32
-    assert C.sizeof(capi.Tile) == 56
+    assert C.sizeof(capi.Tile) == 56 and C.sizeof(capi.TileStats) == 48
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
