@@ -42,7 +42,7 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-constexpr size_t kMetaStride = 32;      // per slot: counters[2] (u64) | n_calls (u32) | pad
+constexpr size_t kMetaStride = 32;      // d_meta: [0] column-queue counters (2 x u32), then per slot: counters[2] (u64) | n_calls (u32) | pad
 constexpr size_t kMaxSlots = 65536;
 
 struct Slot {
@@ -54,7 +54,7 @@ struct Slot {
     TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches
     unsigned int* d_ncalls = nullptr;         // inside Ctx::d_meta
     unsigned long long* d_counters = nullptr; // inside Ctx::d_meta
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // before the pileup kernel / between the two kernels / after
     TileDev tile{};
     ngsep_read_hdr sentinel{};
     bool staged = false, launched = false, in_batch = false;
@@ -65,8 +65,9 @@ struct Slot {
         d_hdr.release(); d_pay.release(); d_win.release(); d_calls.release(); d_counts.release();
         if (d_tile) cudaFree(d_tile);
         if (e0) cudaEventDestroy(e0);
+        if (em) cudaEventDestroy(em);
         if (e1) cudaEventDestroy(e1);
-        d_tile = nullptr; e0 = e1 = nullptr;
+        d_tile = nullptr; e0 = em = e1 = nullptr;
     }
 };
 
@@ -74,7 +75,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // stopwatch
-    cudaEvent_t b0 = nullptr, b1 = nullptr;   // around the batched launch
+    cudaEvent_t b0 = nullptr, bm = nullptr, b1 = nullptr;   // around / between the kernels of the batched run
     ngsep_params params{};
     DevParams* d_prm = nullptr;
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
@@ -83,6 +84,10 @@ struct Ctx {
     // batched launch over every resident slot
     DevBuf<TileDev> d_btiles;
     DevBuf<WinRange> d_bwin;
+    // column queue shared by every launch of this context (launches are stream-ordered)
+    DevBuf<ColumnHdr> d_cols;
+    DevBuf<uint16_t> d_codes;
+    size_t q_min_cols = 0, q_min_codes = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
@@ -104,10 +109,11 @@ int new_slot(Ctx* c, Slot** out) {
     if (c->slots.size() >= kMaxSlots) return fail(c, NGSEP_ENOMEM, "too many resident tiles");
     Slot* s = new Slot();
     const size_t id = c->slots.size();
-    s->d_counters = (unsigned long long*)(c->d_meta + id * kMetaStride);
-    s->d_ncalls = (unsigned int*)(c->d_meta + id * kMetaStride + 16);
+    s->d_counters = (unsigned long long*)(c->d_meta + (1 + id) * kMetaStride);
+    s->d_ncalls = (unsigned int*)(c->d_meta + (1 + id) * kMetaStride + 16);
     cudaError_t e = cudaMalloc((void**)&s->d_tile, sizeof(TileDev));
     if (e == cudaSuccess) e = cudaEventCreate(&s->e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->em);
     if (e == cudaSuccess) e = cudaEventCreate(&s->e1);
     if (e != cudaSuccess) { s->release(); delete s; return cuda_fail(c, e, "slot setup"); }
     *out = s;
@@ -122,18 +128,58 @@ int clear_counts_dbg(Ctx* c, Slot* s) {
     return NGSEP_OK;
 }
 
-// one tile, one launch
+// Column-queue capacity a tile asks for: a small fraction of the positions reaches the genotype kernel (every position
+// with the EMIT_ALL test hook).  Overflow is detected after the run: the queue grows and the run is repeated.
+void queue_need(const Ctx* c, const Slot* s, size_t& cols, size_t& codes) {
+    const size_t len = (size_t)(s->tile.tile_last - s->tile.tile_first + 1);
+    if (c->params.flags & NGSEP_F_EMIT_ALL) { cols += len + 1024; codes += 2 * (size_t)s->aligned_bases + 8 * len + 65536; }
+    else { cols += len / 32 + 16384; codes += (len / 32 + 16384) * 48; }
+}
+
+int ensure_queue(Ctx* c, size_t cols, size_t codes) {
+    cols = std::max(cols, c->q_min_cols); codes = std::max(codes, c->q_min_codes);
+    if (codes > 0xfffffff0ull || cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "column queue too large (split the tile)");
+    CK(c->d_cols.reserve(cols), "column queue alloc");
+    CK(c->d_codes.reserve(codes), "column queue alloc");
+    return NGSEP_OK;
+}
+
+ColumnQueue queue_view(Ctx* c) {
+    ColumnQueue q;
+    q.cols = c->d_cols.p; q.codes = c->d_codes.p; q.ctr = (unsigned int*)c->d_meta;
+    q.cap_cols = (unsigned int)c->d_cols.cap; q.cap_codes = (unsigned int)std::min<size_t>(c->d_codes.cap, 0xfffffff0ull);
+    return q;
+}
+
+// After a run: did the column queue overflow?  (stream must be idle)  Returns 1 when it grew and the run must be repeated.
+int queue_overflowed(Ctx* c, int* grew) {
+    unsigned int ctr[2] = {0, 0};
+    CK(cudaMemcpy(ctr, c->d_meta, sizeof(ctr), cudaMemcpyDeviceToHost), "queue counters copy");
+    *grew = 0;
+    if (ctr[0] > c->d_cols.cap || ctr[1] > c->d_codes.cap) {
+        c->q_min_cols = std::max(c->q_min_cols, (size_t)ctr[0] + (size_t)ctr[0] / 4 + 1024);
+        c->q_min_codes = std::max(c->q_min_codes, (size_t)ctr[1] + (size_t)ctr[1] / 4 + 65536);
+        *grew = 1;
+    }
+    return NGSEP_OK;
+}
+
+// one tile: pileup kernel + genotype kernel
 int launch_slot(Ctx* c, Slot* s) {
     if (!s->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
+    size_t cols = 0, codes = 0;
+    queue_need(c, s, cols, codes);
+    int rc = ensure_queue(c, cols, codes);
+    if (rc != NGSEP_OK) return rc;
+    CK(cudaMemsetAsync(c->d_meta, 0, kMetaStride, c->stream), "memset queue counters");
     CK(cudaMemsetAsync(s->d_counters, 0, kMetaStride, c->stream), "memset counters");
     s->launches = 0;
-    int rc = clear_counts_dbg(c, s);
+    rc = clear_counts_dbg(c, s);
     if (rc != NGSEP_OK) return rc;
     CK(cudaEventRecord(s->e0, c->stream), "event record");
-    if (s->tile.n_windows > 0) {
-        launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, c->cfg, s->grid, c->smem, c->stream);
-        s->launches = 1;
-    }
+    if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
+    CK(cudaEventRecord(s->em, c->stream), "event record");
+    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->sm_count * 4, c->stream); s->launches = 2; }
     CK(cudaEventRecord(s->e1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     s->launched = true;
@@ -141,7 +187,8 @@ int launch_slot(Ctx* c, Slot* s) {
     return NGSEP_OK;
 }
 
-// every resident tile, ONE launch: the windows of all tiles form one list walked by persistent CTAs
+// every resident tile in ONE pileup launch (the windows of all tiles form one list walked by persistent CTAs) followed
+// by ONE genotype launch over the queued columns
 int launch_batch(Ctx* c) {
     const size_t n = c->slots.size();
     if (n <= 1) return fail(c, NGSEP_ESTATE, "no resident tiles");
@@ -164,13 +211,20 @@ int launch_batch(Ctx* c) {
         c->b_grid = (int)std::min<size_t>(n_win, (size_t)c->sm_count * (size_t)c->ctas_per_sm);
         c->batch_dirty = false;
     }
-    CK(cudaMemsetAsync(c->d_meta + kMetaStride, 0, (n - 1) * kMetaStride, c->stream), "memset counters");
-    for (size_t i = 1; i < n; i++) { int rc = clear_counts_dbg(c, c->slots[i]); if (rc != NGSEP_OK) return rc; }
+    size_t cols = 0, codes = 0;
+    for (size_t i = 1; i < n; i++) queue_need(c, c->slots[i], cols, codes);
+    int rc = ensure_queue(c, cols, codes);
+    if (rc != NGSEP_OK) return rc;
+    CK(cudaMemsetAsync(c->d_meta, 0, (1 + n) * kMetaStride, c->stream), "memset counters");   // queue + every slot: ONE memset
+    for (size_t i = 1; i < n; i++) { rc = clear_counts_dbg(c, c->slots[i]); if (rc != NGSEP_OK) return rc; }
     CK(cudaEventRecord(c->b0, c->stream), "event record");
-    if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, c->cfg, c->b_grid, c->smem, c->stream);
+    if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, queue_view(c), c->cfg, c->b_grid, c->smem, c->stream);
+    CK(cudaEventRecord(c->bm, c->stream), "event record");
+    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream);
     CK(cudaEventRecord(c->b1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
+    c->slots[0]->launched = false;   // the batch memset cleared slot 0's counters as well
     c->batch_ran = true;
     return NGSEP_OK;
 }
@@ -248,29 +302,39 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
     CK(cudaSetDevice(c->device), "set device");
     struct Meta { unsigned long long ctr[2]; unsigned int n_calls, pad[3]; } meta;
     static_assert(sizeof(Meta) == kMetaStride, "meta layout");
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 4; attempt++) {
         CK(cudaStreamSynchronize(c->stream), "tile kernels");
         CK(cudaMemcpy(&meta, s->d_counters, sizeof(meta), cudaMemcpyDeviceToHost), "counters copy");
-        if (meta.n_calls <= s->tile.cap_calls) break;
-        if (attempt == 1) return fail(c, NGSEP_EOVERFLOW, "call buffer overflow");
-        CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");   // grow and rerun the staged tile
-        s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
-        CK(cudaMemcpy(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice), "tile descriptor copy");
-        c->batch_dirty = true;
-        int rc = launch_slot(c, s);
+        int grew = 0;
+        int rc = queue_overflowed(c, &grew);
+        if (rc != NGSEP_OK) return rc;
+        if (meta.n_calls <= s->tile.cap_calls && !grew) break;
+        if (attempt == 3) return fail(c, NGSEP_EOVERFLOW, "call / column buffer overflow");
+        if (meta.n_calls > s->tile.cap_calls) {   // grow and rerun the staged tile
+            CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");
+            s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
+            CK(cudaMemcpy(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice), "tile descriptor copy");
+            c->batch_dirty = true;
+        }
+        rc = s->in_batch ? launch_batch(c) : launch_slot(c, s);
         if (rc != NGSEP_OK) return rc;
     }
     const unsigned int n = meta.n_calls;
     if (stats) {
-        float ms = 0.f;
-        if (s->in_batch) CK(cudaEventElapsedTime(&ms, c->b0, c->b1), "event elapsed");   // the whole batch: tiles share one launch
-        else CK(cudaEventElapsedTime(&ms, s->e0, s->e1), "event elapsed");
+        float ms = 0.f, pms = 0.f;
+        if (s->in_batch) {   // the whole batch: its tiles share the launches
+            CK(cudaEventElapsedTime(&ms, c->b0, c->b1), "event elapsed");
+            CK(cudaEventElapsedTime(&pms, c->b0, c->bm), "event elapsed");
+        } else {
+            CK(cudaEventElapsedTime(&ms, s->e0, s->e1), "event elapsed");
+            CK(cudaEventElapsedTime(&pms, s->e0, s->em), "event elapsed");
+        }
         stats->covered_positions = meta.ctr[0];
         stats->candidate_positions = meta.ctr[1];
         stats->calls = n;
         stats->aligned_bases = s->aligned_bases;
         stats->kernel_ms = ms;
-        stats->pileup_ms = ms;
+        stats->pileup_ms = pms;
         stats->kernel_launches = s->launches;
     }
     *n_out = n;
@@ -324,10 +388,11 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (e == cudaSuccess) e = cudaEventCreate(&c->t0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->t1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->b0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->bm);
     if (e == cudaSuccess) e = cudaEventCreate(&c->b1);
     if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_prm, sizeof(DevParams));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_meta, kMaxSlots * kMetaStride);
-    if (e == cudaSuccess) e = cudaMemset(c->d_meta, 0, kMaxSlots * kMetaStride);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->d_meta, (kMaxSlots + 1) * kMetaStride);
+    if (e == cudaSuccess) e = cudaMemset(c->d_meta, 0, (kMaxSlots + 1) * kMetaStride);
     if (e != cudaSuccess) { g_global_err = std::string("context setup: ") + cudaGetErrorString(e); delete c; return NGSEP_ECUDA; }
     c->smem = pileup_smem_bytes(c->cfg);
     if (c->smem > (size_t)prop.sharedMemPerBlockOptin) { g_global_err = "window / stage configuration exceeds the shared memory of one SM"; delete c; return NGSEP_EINVAL; }
@@ -382,12 +447,13 @@ int ngsep_ctx_destroy(void* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& r : c->refs) r.release();
     for (Slot* s : c->slots) { s->release(); delete s; }
-    c->d_btiles.release(); c->d_bwin.release();
+    c->d_btiles.release(); c->d_bwin.release(); c->d_cols.release(); c->d_codes.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->b0) cudaEventDestroy(c->b0);
+    if (c->bm) cudaEventDestroy(c->bm);
     if (c->b1) cudaEventDestroy(c->b1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -481,23 +547,34 @@ int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats) {
     if (!c || !stats) return NGSEP_EINVAL;
     if (!c->batch_ran) return fail(c, NGSEP_ESTATE, "no batched run to report");
     CK(cudaSetDevice(c->device), "set device");
-    CK(cudaStreamSynchronize(c->stream), "tile kernels");
     const size_t n = c->slots.size();
-    std::vector<unsigned char> meta(n * kMetaStride);
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaStreamSynchronize(c->stream), "tile kernels");
+        int grew = 0;
+        int rc = queue_overflowed(c, &grew);
+        if (rc != NGSEP_OK) return rc;
+        if (!grew) break;
+        if (attempt == 3) return fail(c, NGSEP_EOVERFLOW, "column buffer overflow");
+        rc = launch_batch(c);
+        if (rc != NGSEP_OK) return rc;
+    }
+    std::vector<unsigned char> meta((1 + n) * kMetaStride);
     CK(cudaMemcpy(meta.data(), c->d_meta, meta.size(), cudaMemcpyDeviceToHost), "counters copy");
     *stats = ngsep_tile_stats{};
     for (size_t i = 1; i < n; i++) {
-        const unsigned long long* ctr = (const unsigned long long*)(meta.data() + i * kMetaStride);
+        const unsigned char* m = meta.data() + (1 + i) * kMetaStride;
+        const unsigned long long* ctr = (const unsigned long long*)m;
         stats->covered_positions += ctr[0];
         stats->candidate_positions += ctr[1];
-        stats->calls += *(const unsigned int*)(meta.data() + i * kMetaStride + 16);
+        stats->calls += *(const unsigned int*)(m + 16);
         stats->aligned_bases += c->slots[i]->aligned_bases;
     }
-    float ms = 0.f;
+    float ms = 0.f, pms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->b0, c->b1), "event elapsed");
+    CK(cudaEventElapsedTime(&pms, c->b0, c->bm), "event elapsed");
     stats->kernel_ms = ms;
-    stats->pileup_ms = ms;
-    stats->kernel_launches = c->b_windows > 0 ? 1u : 0u;
+    stats->pileup_ms = pms;
+    stats->kernel_launches = c->b_windows > 0 ? 2u : 0u;
     return NGSEP_OK;
 }
 

@@ -12,7 +12,7 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, tab, kmin, misc, bm, list, wmax, rare;   // CTA-wide arrays
+    unsigned bar, kmin, misc, cnt, list, wmax, rare;       // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_hdr, o_pay, o_ref2, o_refn, o_refl;          // offsets inside a stage
     unsigned total, max_reads;
@@ -23,16 +23,15 @@ constexpr int kMiscSet = 16;
 constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
 
-__host__ __device__ inline SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
+static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     SmemLayout L;
     L.max_reads = pay_cap_words / 24;
     unsigned o = 0;
     L.bar = o; o += 16;
-    L.tab = o; o += 96 * 8;
     L.kmin = o; o += kSkipTable * 4;
     L.misc = o; o += 2 * kMiscSet * 4;
-    L.bm = o; o += (T / 32 + 1) * 4;
-    L.list = o; o += ((T * 2 + 3) & ~3u);
+    L.cnt = o; o += (T + 1) * 4;
+    L.list = o; o += T * 4;
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
     o = (o + 7u) & ~7u;
     L.rare = o; o += (L.max_reads + 1) * 8;
@@ -130,17 +129,20 @@ __device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h, const 
 struct WinCtx {
     int wbeg, g_lo, g_hi;        // 0-based index of the window start; [g_lo,g_hi) = the window inside tile and sequence
     const uint32_t* s_ref2;      // staged reference, base index wbeg - kRefLeft at bit 0 of word 0
-    uint32_t* s_bm;              // candidate bitmap of the window
-    uint16_t* s_list;            // candidate list
+    uint32_t* s_cnt;             // per position: flagged bases (an upper bound of the counted non-reference bases)
+    uint32_t* s_list;            // candidate list: position in the window | record that flagged it first << kListShift
     int* mset;                   // counters of this window
     bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
 };
+constexpr int kListShift = 13;                       // windows hold at most 8192 positions
+constexpr uint32_t kListPosMask = (1u << kListShift) - 1u;
+constexpr int kListMaxRec = (1 << (32 - kListShift)) - 1;
 
-__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx) {
+// rec = index of the flagging record inside the window's record range
+__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx, int rec) {
     const int li = idx - w.wbeg;
-    const uint32_t bit = 1u << (li & 31);
-    const uint32_t old = atomicOr(&w.s_bm[li >> 5], bit);
-    if (!(old & bit)) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint16_t)li;
+    if (atomicAdd(&w.s_cnt[li], 1u) == 0u)
+        w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li | ((uint32_t)min(rec, kListMaxRec) << kListShift);
 }
 
 // 16 read bases (one payload word) against the reference at 0-based index `idx0` of the word's first base
@@ -150,36 +152,59 @@ __device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
 }
 
 // Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
-__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
     const int L = (int)(h.meta & 0xffffu);
     const int mlen = (int)(pay[0] >> 3);
     const int ref0 = h.first - 1;                  // 0-based index of read offset 0
     const int a = max(ref0, w.g_lo), b = min(ref0 + mlen, w.g_hi);
     if (a < b && w.collect) {
         const uint32_t* b2 = pay + 1;
-        const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;
+        const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;       // payload words that intersect the window
         const int r0 = ref0 + 16 * j0 - w.wbeg + kRefLeft;
         const int sh = (r0 & 15) * 2;
         const uint32_t* rp = w.s_ref2 + (r0 >> 4);
-        uint32_t wlo = rp[0];
-        for (int j = j0; j <= j1; j++) {
-            const uint32_t whi = rp[j - j0 + 1];
-            const uint32_t x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
-            wlo = whi;
+        const int t_lo = a - ref0 - 16 * j0, t_hi = b - ref0 - 16 * j1;  // valid bases: [t_lo,16) of word j0, [0,t_hi) of word j1
+        const uint32_t head = 0xffffffffu << (2 * t_lo);
+        const uint32_t tail = (t_hi >= 16) ? 0xffffffffu : ((1u << (2 * t_hi)) - 1u);
+        // mismatch bits of payload word j (2 bits per base, low bit set when the base differs from the reference)
+        auto diff = [&](int j) {
+            const uint32_t x = b2[j] ^ __funnelshift_r(rp[j - j0], rp[j - j0 + 1], sh);
             uint32_t m = (x | (x >> 1)) & 0x55555555u;
-            if (m == 0) continue;
-            // rare: a mismatch (or the padding of the last word / a base outside the window)
-            const int o_lo = max(a - ref0, 16 * j) - 16 * j, o_hi = min(b - ref0, 16 * j + 16) - 16 * j;
-            m &= range_mask32(2 * o_lo, 2 * o_hi);
-            if (m == 0) continue;
+            if (j == j0) m &= head;
+            if (j == j1) m &= tail;
+            return m;
+        };
+        // rare: some base of word j differs — flag the ones CountsHelper would count (callable, RA:782-784; q > 3, CH:214)
+        auto flag_word = [&](int j, uint32_t m) {
             const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
-            const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);   // callable offsets (RA:782-784)
+            const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
             while (m) {
                 const int bit = __ffs(m) - 1;
                 m &= m - 1;
                 const int off = 16 * j + (bit >> 1);
-                if (off >= c_lo && off < c_hi && q[off] > 36) flag_candidate(w, ref0 + off);   // q = char - 33 > 3 (CH:214)
+                if (off >= c_lo && off < c_hi && q[off] > 36) flag_candidate(w, ref0 + off, rec);
             }
+        };
+        if (j1 - j0 < 32) {
+            // Branch-free pass over the words (a warp would otherwise take the mismatch path on almost every iteration,
+            // since SOME lane has a mismatch), then the few words that differ
+            uint32_t wm = 0u, wlo = rp[0];
+            for (int j = j0; j <= j1; j++) {
+                const uint32_t whi = rp[j - j0 + 1];
+                const uint32_t x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
+                wlo = whi;
+                uint32_t m = (x | (x >> 1)) & 0x55555555u;
+                m &= (j == j0) ? head : 0xffffffffu;
+                m &= (j == j1) ? tail : 0xffffffffu;
+                wm |= (m != 0u ? 1u : 0u) << (j - j0);
+            }
+            while (wm) {
+                const int j = j0 + __ffs(wm) - 1;
+                wm &= wm - 1;
+                flag_word(j, diff(j));
+            }
+        } else {
+            for (int j = j0; j <= j1; j++) { const uint32_t m = diff(j); if (m) flag_word(j, m); }
         }
     }
     return ref0 + mlen;
@@ -188,7 +213,7 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
 // General record (indels, clips, N mask, realigner versions): every aligned base that differs from the reference
 // is flagged (a superset of the counted ones).  Returns the last covered position, or INT_MIN for a version record
 // (its coverage goes through the bitmap fallback).
-__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
     const RecView r = view_record(h, pay);
     const int lo = max(w.g_lo, (r.vfrom == INT_MIN) ? INT_MIN : r.vfrom - 1);
     const int hi = min(w.g_hi, (r.vto == INT_MAX) ? INT_MAX : r.vto - 1);
@@ -210,7 +235,7 @@ __device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uin
                     while (m) {
                         const int bit = __ffs(m) - 1;
                         m &= m - 1;
-                        flag_candidate(w, o + (bit >> 1) - delta);
+                        flag_candidate(w, o + (bit >> 1) - delta, rec);
                     }
                 }
             }
@@ -309,48 +334,79 @@ __device__ __forceinline__ int dev_phred(double p) {  // math/PhredScoreHelper.j
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// index of the ordered event (i,j) in CH.getPosteriorProbabilities' enumeration (CH:416-430): per first allele i, the
-// homozygous event, then the heterozygous ones with j ascending
-__device__ __forceinline__ int ev_index(int i, int j) { return i * 4 + ((i == j) ? 0 : ((j < i) ? j + 1 : j)); }
+// ------------------------------------------------------------------------------------------------------------
+// SNVQ genotyping of one column (thread-serial; used by k_genotype_columns)
+// ------------------------------------------------------------------------------------------------------------
+struct ColState {
+    int c0, c1, c2, c3, depth;
+    int sn0, sn1, sn2, sn3;                      // negative-strand count per allele
+    double d0, d1, d2, d3, o01, o02, o03, o12, o13, o23;
+};
 
-struct ColCounts { int c[4], sn[4], depth; };
+// CH.updateCounts for one counted call (CH:223-249 with f == g == 250: L is symmetric, 10 distinct sums)
+__device__ __forceinline__ void col_add(ColState& s, int b, int q, bool neg, const double* s_tab) {
+    s.c0 += (b == 0); s.c1 += (b == 1); s.c2 += (b == 2); s.c3 += (b == 3);
+    s.sn0 += (neg && b == 0); s.sn1 += (neg && b == 1); s.sn2 += (neg && b == 2); s.sn3 += (neg && b == 3);
+    const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
+    s.d0 += (b == 0) ? ta : tb;
+    s.d1 += (b == 1) ? ta : tb;
+    s.d2 += (b == 2) ? ta : tb;
+    s.d3 += (b == 3) ? ta : tb;
+    s.o01 += (b == 0 || b == 1) ? tc : tb;
+    s.o02 += (b == 0 || b == 2) ? tc : tb;
+    s.o03 += (b == 0 || b == 3) ? tc : tb;
+    s.o12 += (b == 1 || b == 2) ? tc : tb;
+    s.o13 += (b == 1 || b == 3) ? tc : tb;
+    s.o23 += (b == 2 || b == 3) ? tc : tb;
+}
 
-// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223, one warp per column.
-// `acc` is lane-owned: lanes 0-3 hold L[i][i], lanes 4-9 hold L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3].
-__device__ __forceinline__ void finalize_warp(double acc, const ColCounts& cc, int lane, int pos, int ref, const TileDev& d, const DevParams& prm,
-                                              const double* s_tab) {
-    const int k = lane & 15;
-    const int i = k >> 2, r = k & 3;
-    const int j = (r == 0) ? i : ((r - 1 < i) ? r - 1 : r);
-    const int lo = min(i, j), hi = max(i, j);
-    const int owner = (i == j) ? i : ((lo == 0) ? 3 + hi : ((lo == 1) ? 5 + hi : 9));
-    const double Lij = __shfl_sync(kFull, acc, owner);
-    const double ev = Lij + ((i == j) ? s_tab[93] : s_tab[94]);
-    double mx = ev;   // CH:474-479: the quirk "starts at 1 and is replaced by the first event" reduces to the maximum
-    for (int o = 8; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
-    double e = ev - mx;
-    e = (e < -20.0) ? 0.0 : exp10(e);
-    double total = 0.0;
-    for (int t = 0; t < 16; t++) total += __shfl_sync(kFull, e, t);   // CH:480-486, same order
-    const double post = e / total;
-    // VD.getIndexesMaxGenotype (VD:223-243), every lane redundantly
-    const double p_ref = __shfl_sync(kFull, post, ev_index(ref, ref));
-    int ii = ref, jj = ref;
-    double pmax = p_ref;
-    for (int a = 0; a < 4; a++)
-        for (int b = a; b < 4; b++) {
-            double gp = __shfl_sync(kFull, post, ev_index(a, b));
-            if (a != b) gp += __shfl_sync(kFull, post, ev_index(b, a));
-            if (gp > pmax + 0.01) { pmax = gp; ii = a; jj = b; }
+// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223
+__device__ void col_finalize(const ColState& s, int pos, int ref, const TileDev& d, const DevParams& prm, const double* s_tab) {
+    double Lm[16];
+    Lm[0] = s.d0; Lm[5] = s.d1; Lm[10] = s.d2; Lm[15] = s.d3;
+    Lm[1] = Lm[4] = s.o01; Lm[2] = Lm[8] = s.o02; Lm[3] = Lm[12] = s.o03;
+    Lm[6] = Lm[9] = s.o12; Lm[7] = Lm[13] = s.o13; Lm[11] = Lm[14] = s.o23;
+    const double lp_hom = s_tab[93], lp_het = s_tab[94];
+    double ev[16];
+    {
+        int k = 0;
+        for (int i = 0; i < 4; i++) {
+            ev[k++] = Lm[i * 5] + lp_hom;
+            for (int j = 0; j < 4; j++) if (i != j) ev[k++] = Lm[i * 4 + j] + lp_het;
         }
-    double max_p = __shfl_sync(kFull, post, ev_index(ii, jj));
-    if (ii != jj) max_p += __shfl_sync(kFull, post, ev_index(jj, ii));
-    const double p_ii = __shfl_sync(kFull, post, ev_index(ii, ii));
-    const double p_jj = __shfl_sync(kFull, post, ev_index(jj, jj));
+    }
+    double log_max = 1.0;  // CH:474-479, quirk kept: starts at 1 and is replaced by the first event
+    for (int k = 0; k < 16; k++) if (log_max > 0.0 || log_max < ev[k]) log_max = ev[k];
+    double total = 0.0;
+    for (int k = 0; k < 16; k++) {
+        double e = ev[k] - log_max;
+        e = (e < -20.0) ? 0.0 : exp10(e);
+        ev[k] = e;
+        total += e;
+    }
+    double post[16];
+    {
+        int k = 0;
+        for (int i = 0; i < 4; i++) {
+            post[i * 5] = ev[k++] / total;
+            for (int j = 0; j < 4; j++) if (i != j) post[i * 4 + j] = ev[k++] / total;
+        }
+    }
+    // VD.getIndexesMaxGenotype (VD:223-243)
+    int ii = ref, jj = ref;
+    double pmax = post[ref * 5];
+    for (int i = 0; i < 4; i++) for (int j = i; j < 4; j++) {
+        double gp = post[i * 4 + j];
+        if (i != j) gp += post[j * 4 + i];
+        if (gp > pmax + 0.01) { pmax = gp; ii = i; jj = j; }
+    }
+    double max_p = post[ii * 4 + jj];
+    if (ii != jj) max_p += post[jj * 4 + ii];
+    int gq = dev_phred(1.0 - max_p);
     int kind, a0, a1;
     if (ii != jj && ii != ref && jj != ref) {  // VD:128-177
         kind = NGSEP_CALL_TRIALLELIC;
-        if (p_ii > p_jj + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
+        if (post[ii * 5] > post[jj * 5] + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
     } else if (ii != jj) {
         kind = NGSEP_CALL_HET; a0 = ref; a1 = (ref != ii) ? ii : jj;
     } else if (ii != ref) {
@@ -358,28 +414,22 @@ __device__ __forceinline__ void finalize_warp(double acc, const ColCounts& cc, i
     } else {
         return;  // homozygous reference: dropped by SSVPL:223
     }
-    const int gq = dev_phred(1.0 - max_p);
     if (prm.min_quality > gq) return;  // SSVPL:223
-    unsigned int slot = 0;
-    if (lane == 0) slot = atomicAdd(d.n_calls, 1u);
-    slot = __shfl_sync(kFull, slot, 0);
-    if (slot >= d.cap_calls) return;   // host sees n_calls > cap and reports NGSEP_EOVERFLOW (or grows and reruns)
+    unsigned int slot = atomicAdd(d.n_calls, 1u);
+    if (slot >= d.cap_calls) return;   // host sees n_calls > cap, grows the buffer and reruns
     ngsep_snv_call* o = &d.calls[slot];
-    if (lane < 16) o->logcond[i * 4 + j] = Lij;
-    if (lane == 16) {
-        o->seq_idx = d.seq_idx; o->pos = pos;
-        o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
-        o->depth = cc.depth;
-        for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
-    }
-    if (lane == 17) {
-        o->post_ref = p_ref;
-        o->post_max = max_p;
-        o->gq = (int16_t)gq;
-        o->qual = (int16_t)dev_phred(p_ref);
-        o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
-        o->sample = 0;
-    }
+    o->seq_idx = d.seq_idx; o->pos = pos;
+    o->count[0] = s.c0; o->count[1] = s.c1; o->count[2] = s.c2; o->count[3] = s.c3;
+    o->depth = s.depth;
+    o->strand[0] = s.sn0; o->strand[1] = s.c0 - s.sn0; o->strand[2] = s.sn1; o->strand[3] = s.c1 - s.sn1;
+    o->strand[4] = s.sn2; o->strand[5] = s.c2 - s.sn2; o->strand[6] = s.sn3; o->strand[7] = s.c3 - s.sn3;
+    for (int k = 0; k < 16; k++) o->logcond[k] = Lm[k];
+    o->post_ref = post[ref * 5];
+    o->post_max = max_p;
+    o->gq = (int16_t)gq;
+    o->qual = (int16_t)dev_phred(post[ref * 5]);
+    o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
+    o->sample = 0;
 }
 
 // Records of the window as the exact phase sees them: the staged copy in shared memory, or (windows too deep to stage
@@ -424,89 +474,114 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
 }
 
 struct ExactCtx {
-    int wbeg, n_cand, max_span, max_back;
-    const uint16_t* s_list;
+    int wbeg, n_cand, max_span, max_back, tile;
+    const uint32_t* s_list;
+    uint32_t* s_cnt;
     const uint32_t *s_ref2, *s_refn, *s_refl;
-    const double* s_tab;
     const int* s_kmin;
     bool emit_all, ignore_lower;
 };
 
+// Is record idx a simple record whose base at pos is a COUNTED reference base?  (offset = pos - first with one match
+// block, RA:842-871; callable, RA:782-784; q > 3, CH:214.)
 template <bool kGlobal>
-__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const TileDev& d, const DevParams& prm, int warp, int lane) {
-    const int max_qs = prm.max_base_qs;
-    for (int ci = warp; ci < x.n_cand; ci += kWarps) {
-        const int li = (int)x.s_list[ci];
-        const int pos = x.wbeg + li + 1;
-        if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) continue;   // SSVPL:198: no discovery at all
-        const bool ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
-        if (ref_bad && !x.emit_all) continue;                                       // VD:101-107
-        const int rr = li + kRefLeft;
-        const int ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
-        const int i_lo = warp_lower_bound(R, pos - x.max_span + 1, lane);
-        const int last_key = pos + x.max_back;
-        // ---- pass 1: exact integer counts ---------------------------------------------------------------------
-        ColCounts cc;
-        for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
-        cc.depth = 0;
-        for (int base = i_lo; base < R.n; base += 32) {
-            const int idx = base + lane;
-            uint32_t code = 0u;
-            bool in = false;
-            if (idx < R.n) {
-                const ngsep_read_hdr h = R.header(idx);
-                in = h.first <= last_key;
-                if (in) code = lane_eval(h, R.payload(h), pos, max_qs);
-            }
-            const unsigned inm = __ballot_sync(kFull, in);
-            cc.depth += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));
-            const unsigned ng = __ballot_sync(kFull, (code & kCodeNeg) != 0u);
-            const bool counted = (code & kCodeCounted) != 0u;
-            for (int b = 0; b < 4; b++) {
-                const unsigned mb = __ballot_sync(kFull, counted && (int)(code & 3u) == b);
-                cc.c[b] += __popc(mb);
-                cc.sn[b] += __popc(mb & ng);
-            }
-            if (inm != kFull) break;   // sorted by start: nothing further can cover pos
+__device__ __forceinline__ bool counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
+    if (idx < 0 || idx >= R.n) return false;
+    const ngsep_read_hdr h = R.header(idx);
+    if ((h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) != 0x00010000u) return false;
+    const uint32_t* pay = R.payload(h);
+    const uint32_t c0 = pay[0];
+    const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
+    if ((c0 & 7u) != 3u || off < 0 || off >= (int)(c0 >> 3) || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return false;
+    const uint32_t* b2 = pay + 1;
+    const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
+    return q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref;
+}
+
+// Column extraction (warp-cooperative): every covering record in pileup order, one record per lane and round, restating
+// PR.getAlleleCalls(1).  The calls (allele, quality, strand, counted) are appended to the column queue in that order;
+// k_genotype_columns turns them into counts, log-likelihoods and the genotype.
+template <bool kGlobal>
+__device__ __forceinline__ void extract_column(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, int max_qs, int li, int lane) {
+    const int pos = x.wbeg + li + 1;
+    const uint32_t ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
+    const int rr = li + kRefLeft;
+    const uint32_t ref = (x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
+    const int i_lo = warp_lower_bound(R, pos - x.max_span + 1, lane);
+    const int i_hi = warp_lower_bound(R, pos + x.max_back + 1, lane);   // first record that starts too far to the right
+    const int n_max = i_hi - i_lo;
+    if (n_max <= 0) return;
+    unsigned int col = 0, off = 0;
+    if (lane == 0) { col = atomicAdd(&cq.ctr[0], 1u); off = atomicAdd(&cq.ctr[1], (unsigned int)n_max); }
+    col = __shfl_sync(kFull, col, 0);
+    off = __shfl_sync(kFull, off, 0);
+    const bool room = col < cq.cap_cols && (uint64_t)off + (uint64_t)n_max <= (uint64_t)cq.cap_codes;   // else: host grows + reruns
+    unsigned int n = 0;
+    for (int base = i_lo; base < i_hi; base += 32) {
+        const int idx = base + lane;
+        uint32_t code = 0u;
+        if (idx < i_hi) {
+            const ngsep_read_hdr h = R.header(idx);
+            code = lane_eval(h, R.payload(h), pos, max_qs);
         }
-        if (x.emit_all && d.counts_dbg && lane == 0) {
-            int32_t* o = d.counts_dbg + (int64_t)(pos - d.tile_first) * 5;
-            o[0] = cc.c[0]; o[1] = cc.c[1]; o[2] = cc.c[2]; o[3] = cc.c[3]; o[4] = cc.depth;
-        }
-        if (ref_bad || cc.depth == 0) continue;   // VD:101-107
-        const int tot = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
-        const int k_ref = (ref == 0) ? cc.c[0] : ((ref == 1) ? cc.c[1] : ((ref == 2) ? cc.c[2] : cc.c[3]));
-        const int m_alt = tot - k_ref;
-        // Proven hom-ref: no counted non-reference base, or k >= k_min[m] counted reference bases:
-        // P(ref,ref) > 1/2, VD.discoverSNV returns the homozygous-reference call that SSVPL:223 drops.
-        if (prm.fast_homref && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= x.s_kmin[m_alt]))) continue;
-        // ---- pass 2: the 10 distinct log-likelihoods, one per lane, summed in pileup order (CH:231-249) --------------------
-        const int pa = (lane < 4) ? lane : ((lane < 7) ? 0 : ((lane < 9) ? 1 : 2));
-        const int pb = (lane < 4) ? lane : ((lane < 7) ? lane - 3 : ((lane < 9) ? lane - 5 : 3));
-        double acc = 0.0;
-        for (int base = i_lo; base < R.n; base += 32) {
-            const int idx = base + lane;
-            uint32_t code = 0u;
-            bool in = false;
-            if (idx < R.n) {
-                const ngsep_read_hdr h = R.header(idx);
-                in = h.first <= last_key;
-                if (in) code = lane_eval(h, R.payload(h), pos, max_qs);
+        const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
+        if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
+        n += __popc(cm);
+    }
+    if (lane == 0 && room) {
+        ColumnHdr ch;
+        ch.tile = x.tile; ch.pos = pos; ch.code_off = off; ch.n_codes = n | (ref << 28) | (ref_bad << 30);
+        cq.cols[col] = ch;
+    }
+}
+
+// Phase C.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
+// were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
+// of the records does).  k_lb >= k_min[m_up] closes the column.  What is left goes to the column queue.
+template <bool kGlobal>
+__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, const DevParams& prm, int warp, int lane) {
+    const int grp = lane >> 4, gl = lane & 15;
+    for (int base = 0; base < x.n_cand; base += 2 * kWarps) {
+        const int ci = base + 2 * warp + grp;
+        const bool act = ci < x.n_cand;
+        uint32_t ent = 0u, m_up = 0u;
+        int li = 0, pos = 0, ref = 0;
+        bool open = false, ok = false;
+        if (act) {
+            ent = x.s_list[ci];
+            li = (int)(ent & kListPosMask);
+            pos = x.wbeg + li + 1;
+            open = !(x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u));            // SSVPL:198: no discovery at all
+            if (!x.emit_all) {
+                m_up = x.s_cnt[li];
+                const bool ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
+                if (ref_bad) open = false;                                                  // VD:101-107
+                const int rr = li + kRefLeft;
+                ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
+                if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
             }
-            const unsigned inm = __ballot_sync(kFull, in);
-            unsigned cm = __ballot_sync(kFull, (code & kCodeCounted) != 0u);
-            while (cm) {
-                const int src = __ffs(cm) - 1;
-                cm &= cm - 1;
-                const uint32_t cj = __shfl_sync(kFull, code, src);
-                const int b = (int)(cj & 3u), q = (int)((cj >> 2) & 31u);
-                const double ta = x.s_tab[3 * q], tb = x.s_tab[3 * q + 1], tc = x.s_tab[3 * q + 2];
-                const double term = (lane < 4) ? ((b == lane) ? ta : tb) : ((b == pa || b == pb) ? tc : tb);
-                acc += term;
-            }
-            if (inm != kFull) break;
         }
-        finalize_warp(acc, cc, lane, pos, ref, d, prm, x.s_tab);
+        const unsigned okm = __ballot_sync(kFull, ok);
+        if (act && !x.emit_all) {
+            if (gl == 0) x.s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
+            if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
+        }
+        // the (few) columns still open: the warp handles them one by one
+        unsigned sm = __ballot_sync(kFull, open && gl == 0);
+        while (sm) {
+            const int src = __ffs(sm) - 1;
+            sm &= sm - 1;
+            const uint32_t e = __shfl_sync(kFull, ent, src);
+            const uint32_t mu = __shfl_sync(kFull, m_up, src);
+            const int e_li = (int)(e & kListPosMask);
+            if (!x.emit_all && prm.fast_homref && mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
+                // second chance with the whole warp: 32 records around the flagging one
+                const int e_ref = __shfl_sync(kFull, ref, src);
+                const bool ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, x.wbeg + e_li + 1, e_ref);
+                if (__popc(__ballot_sync(kFull, ok2)) >= x.s_kmin[mu]) continue;
+            }
+            extract_column(R, x, cq, prm.max_base_qs, e_li, lane);
+        }
     }
 }
 
@@ -518,28 +593,28 @@ struct KArgs {
     const WinRange* win;
     int n_windows;
     const DevParams* prm;
+    ColumnQueue cq;
     LaunchCfg cfg;
+    SmemLayout lay;
 };
 
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const KArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const SmemLayout lay = make_layout(a.cfg.T_lay, a.cfg.pay_cap_words, a.cfg.n_stages);
+    const SmemLayout& lay = a.lay;
     uint64_t* s_bar = (uint64_t*)(smem + lay.bar);
-    double* s_tab = (double*)(smem + lay.tab);
     int* s_kmin = (int*)(smem + lay.kmin);
     int* s_misc = (int*)(smem + lay.misc);
-    uint32_t* s_bm = (uint32_t*)(smem + lay.bm);
-    uint16_t* s_list = (uint16_t*)(smem + lay.list);
+    uint32_t* s_cnt = (uint32_t*)(smem + lay.cnt);
+    uint32_t* s_list = (uint32_t*)(smem + lay.list);
     int* s_wmax = (int*)(smem + lay.wmax);
     int2* s_rare = (int2*)(smem + lay.rare);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevParams& prm = *a.prm;
-    for (int i = tid; i < NGSEP_N_TABLES; i += kThreads) s_tab[i] = prm.tables[i];
     if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
     if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
-    for (int i = tid; i < a.cfg.T_lay / 32 + 1; i += kThreads) s_bm[i] = 0u;
+    for (int i = tid; i < a.cfg.T_lay + 1; i += kThreads) s_cnt[i] = 0u;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
     uint32_t phase[2] = {0u, 0u};
@@ -599,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         WinCtx wc;
         wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
         wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
-        wc.s_bm = s_bm; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
+        wc.s_cnt = s_cnt; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
 
         mbar_wait(&s_bar[cur], phase[cur]);
         phase[cur] ^= 1u;
@@ -608,7 +683,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
         // positions of (reach_i, s_{i+1}) are covered by nobody.  reach_i is at least the warp-local prefix maximum; only
         // when that does not reach s_{i+1} - 1 is the record queued for the exact cross-warp evaluation (process_rare).
-        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, bool first_chunk) {
+        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, int rec0, bool first_chunk) {
             for (int base = 0; base < n_chunk; base += kThreads) {
                 const int i = base + tid;
                 const bool act = i < n_chunk;
@@ -616,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
                 if (act) {
                     const ngsep_read_hdr h = s_hdr[i];
                     const uint32_t* pay = s_pay + (h.off - pay_base);
-                    e = record_is_simple(h, pay) ? screen_simple(h, pay, wc) : screen_general(h, pay, wc);
+                    e = record_is_simple(h, pay) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
                     nxt = min(s_hdr[i + 1].first, B + 1);
                     floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
                     if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
@@ -638,9 +713,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
             }
         };
 
-        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += kThreads) s_list[i] = (uint16_t)(g_lo - wbeg + i);
+        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += kThreads) s_list[i] = (uint32_t)(g_lo - wbeg + i);
         if (single) {
-            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, true);
+            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, 0, true);
             else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
         } else {
             // windows too deep for one stage: stream the record range chunk by chunk through the current stage
@@ -669,7 +744,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
                 const int carry = mset[M_CARRY];
                 mbar_wait(&s_bar[cur], phase[cur]);
                 phase[cur] ^= 1u;
-                screen_chunk(r1 - r0, pay_base, first_chunk);
+                screen_chunk(r1 - r0, pay_base, r0 - wr.lo, first_chunk);
                 __syncthreads();
                 process_rare(carry);
                 __syncthreads();
@@ -686,23 +761,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         __syncthreads();   // ---- sync 1: candidates listed ---------------------------------------------------------------
 
         if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
-        for (int i = tid; i < a.cfg.T_lay / 32 + 1; i += kThreads) s_bm[i] = 0u;
         if (single && n_rec > 0) process_rare(INT_MIN);
         const int n_cand = emit_all ? max(0, g_hi - g_lo) : mset[M_NCAND];
 
         // ---- phase C: exact evaluation, one warp per candidate ------------------------------------------------------------
         ExactCtx x;
-        x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = d.max_span; x.max_back = d.max_back;
-        x.s_list = s_list; x.s_ref2 = wc.s_ref2;
+        x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = d.max_span; x.max_back = d.max_back; x.tile = wr.tile;
+        x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
         x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
-        x.s_tab = s_tab; x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
+        x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
         if (n_cand > 0 && n_rec > 0) {
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                exact_phase<false>(R, x, d, prm, warp, lane);
+                exact_phase<false>(R, x, a.cq, prm, warp, lane);
             } else {
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                exact_phase<true>(R, x, d, prm, warp, lane);
+                exact_phase<true>(R, x, a.cq, prm, warp, lane);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
@@ -711,7 +785,9 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         const int win_len = max(0, B - A + 1);
         if (uncovered > 0 && mset[M_HASVER] && n_rec > 0) {
             // rare: a gap in the cover of the unversioned records while realigner versions are present — count the cover
-            // of every record with a bitmap (s_bm is clear here and is cleared again below)
+            // of every record with a bitmap (s_cnt is all zero here — every listed position reset its counter — and is
+            // cleared again below)
+            uint32_t* s_bm = s_cnt;
             for (int i = tid; i < n_rec; i += kThreads) {
                 const ngsep_read_hdr h = d.hdr[wr.lo + i];
                 int s, e;
@@ -736,6 +812,52 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         }
         w = wn;
         wr = nr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SNVQ genotyping of the queued columns: one thread per column
+// ------------------------------------------------------------------------------------------------------------
+// Restates CountsHelper.calculateCountsGTSNV / updateCounts (CH:86-95, 209-251) over the column's calls in pileup order,
+// then CH.getPosteriorProbabilities + VD.discoverSNV (col_finalize).  The 10 distinct log-likelihoods are summed in fp64
+// in the reference's own order from the host-supplied tables: logConditionalProbs are bit-identical to the Java doubles.
+__global__ void __launch_bounds__(128) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+    __shared__ double s_tab[96];
+    __shared__ int s_kmin[kSkipTable];
+    const DevParams& prm = *gprm;
+    for (int i = threadIdx.x; i < NGSEP_N_TABLES; i += blockDim.x) s_tab[i] = prm.tables[i];
+    if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
+    __syncthreads();
+    const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
+    const unsigned int n_cols = min(cq.ctr[0], cq.cap_cols);
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_cols; t += gridDim.x * blockDim.x) {
+        const ColumnHdr ch = cq.cols[t];
+        const unsigned int n = ch.n_codes & 0x0fffffffu;
+        const int ref = (int)((ch.n_codes >> 28) & 3u);
+        const bool ref_bad = (ch.n_codes >> 30) & 1u;
+        const TileDev& d = tiles[ch.tile];
+        const uint16_t* codes = cq.codes + ch.code_off;
+        ColState cs;
+        cs.c0 = cs.c1 = cs.c2 = cs.c3 = cs.depth = 0;
+        cs.sn0 = cs.sn1 = cs.sn2 = cs.sn3 = 0;
+        cs.d0 = cs.d1 = cs.d2 = cs.d3 = cs.o01 = cs.o02 = cs.o03 = cs.o12 = cs.o13 = cs.o23 = 0.0;
+        for (unsigned int i = 0; i < n; i++) {
+            const uint32_t code = codes[i];
+            cs.depth++;   // CH:210 totalCount counts every call returned by getAlleleCalls(1), whatever its quality or base
+            if (code & kCodeCounted) col_add(cs, (int)(code & 3u), (int)((code >> 2) & 31u), (code & kCodeNeg) != 0u, s_tab);
+        }
+        if (emit_all && d.counts_dbg) {
+            int32_t* o = d.counts_dbg + (int64_t)(ch.pos - d.tile_first) * 5;
+            o[0] = cs.c0; o[1] = cs.c1; o[2] = cs.c2; o[3] = cs.c3; o[4] = cs.depth;
+        }
+        if (ref_bad || cs.depth == 0) continue;   // VD:101-107
+        const int tot = cs.c0 + cs.c1 + cs.c2 + cs.c3;
+        const int k_ref = (ref == 0) ? cs.c0 : ((ref == 1) ? cs.c1 : ((ref == 2) ? cs.c2 : cs.c3));
+        const int m_alt = tot - k_ref;
+        // Proven hom-ref with the exact counts: VD.discoverSNV returns the homozygous-reference call that
+        // SSVPL:223 drops.
+        if (prm.fast_homref && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= s_kmin[m_alt]))) continue;
+        col_finalize(cs, ch.pos, ref, d, prm, s_tab);
     }
 }
 
@@ -806,11 +928,16 @@ int pileup_max_ctas_per_sm(size_t smem, int min_blocks) {
     return n;
 }
 
-void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const LaunchCfg& cfg, int grid,
-                   size_t smem, cudaStream_t s) {
+void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
+                   int grid, size_t smem, cudaStream_t s) {
     KArgs a;
-    a.tiles = d_tiles; a.win = d_win; a.n_windows = n_windows; a.prm = dprm; a.cfg = cfg;
+    a.tiles = d_tiles; a.win = d_win; a.n_windows = n_windows; a.prm = dprm; a.cq = cq; a.cfg = cfg;
+    a.lay = make_layout(cfg.T_lay, cfg.pay_cap_words, cfg.n_stages);
     kernel_for(cfg.min_blocks)<<<grid, kThreads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
+}
+
+void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+    k_genotype_columns<<<grid, 128, 0, s>>>(d_tiles, cq, dprm);
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

@@ -59,6 +59,16 @@ struct DevParams {
     double tables[NGSEP_N_TABLES];
 };
 
+// A column = one position that was not closed by the screen / hom-ref proof: its calls (PileupRecord.getAlleleCalls(1)) in
+// pileup order, 16 bits each: bits 0-1 allele, 2-6 quality after the caps of CH:91,217, 7 negative strand, 8 counted (CH:223),
+// 9 always set.
+struct ColumnHdr { int32_t tile; int32_t pos; uint32_t code_off; uint32_t n_codes; };   // n_codes: bits 0-27 count, 28-29 reference allele, 30 reference not ACGT
+struct ColumnQueue {
+    ColumnHdr* cols; uint16_t* codes;
+    unsigned int* ctr;                       // [0] columns claimed, [1] code slots claimed
+    unsigned int cap_cols, cap_codes;
+};
+
 struct LaunchCfg {
     int T_lay;                   // window length the shared-memory layout is sized for
     unsigned int pay_cap_words;  // payload words one stage holds
@@ -69,8 +79,9 @@ struct LaunchCfg {
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
 int pileup_max_ctas_per_sm(size_t smem, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
-void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const LaunchCfg& cfg, int grid,
-                   size_t smem, cudaStream_t s);
+void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
+                   int grid, size_t smem, cudaStream_t s);
+void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
 }  // namespace ngsep_b200
