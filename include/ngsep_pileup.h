@@ -70,7 +70,10 @@ typedef struct ngsep_read_hdr {
 #define NGSEP_M_WINDOW 0x04000000u /* payload starts with {valid_from, valid_to, first}: the record describes the
                                       read only for reference positions valid_from <= p < valid_to, with its own
                                       start `first` (versions written by the indel-realigner pre-pass)          */
-#define NGSEP_M_SAMPLE_SHIFT 27    /* unused in single-sample runs                                             */
+#define NGSEP_M_SIMPLE 0x10000000u /* packer's promise: ONE CIGAR word, a match block as long as the read (len*8+3), no
+                                      N mask, no valid window.  The device takes its fast path on it; a record without
+                                      the flag goes through the general path (always correct).  ngsep_tile_submit
+                                      verifies the promise against the payload.                                  */
 
 /* Payload of one record, 32-bit words, in this order:
  *   [valid_from, valid_to, first]      only with NGSEP_M_WINDOW

@@ -35,6 +35,7 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
     ngsep_read_hdr h;
     h.first = r.admit_first;
     h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
+    if (nc == 1 && !has_n && !windowed && st.cigar[0] == (((uint32_t)len << 3) | 3u)) h.meta |= NGSEP_M_SIMPLE;
     h.ign_start = (int16_t)st.ign_s;
     h.ign_end = (int16_t)st.ign_e;
     h.off = (uint32_t)out.payload.size();

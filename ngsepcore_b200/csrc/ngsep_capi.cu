@@ -91,7 +91,7 @@ struct Ctx {
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
-    LaunchCfg cfg{512, 7424u, 1, 4};
+    LaunchCfg cfg{512, 7424u, 1, 4, 256};
     size_t smem = 0;
     int ctas_per_sm = 1;
     std::string err;
@@ -247,6 +247,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     }
     s->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
     CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
+    launch_sanitize_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, c->stream);   // NGSEP_M_SIMPLE is trusted only when the payload backs it
     // validate ordering + stage fit (a record must fit one staged chunk)
     uint64_t bases = 0;
     const char* bad = nullptr;
@@ -396,8 +397,10 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (e != cudaSuccess) { g_global_err = std::string("context setup: ") + cudaGetErrorString(e); delete c; return NGSEP_ECUDA; }
     c->smem = pileup_smem_bytes(c->cfg);
     if (c->smem > (size_t)prop.sharedMemPerBlockOptin) { g_global_err = "window / stage configuration exceeds the shared memory of one SM"; delete c; return NGSEP_EINVAL; }
-    if (const char* s = std::getenv("NGSEP_MIN_BLOCKS")) { int v = std::atoi(s); if (v >= 3 && v <= 5) c->cfg.min_blocks = v; }
-    c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.min_blocks);
+    if (const char* s = std::getenv("NGSEP_THREADS")) { int v = std::atoi(s); if (v == 128 || v == 256) c->cfg.threads = v; }
+    if (c->cfg.threads == 128) c->cfg.min_blocks = 8;
+    if (const char* s = std::getenv("NGSEP_MIN_BLOCKS")) { int v = std::atoi(s); if (v >= 3 && v <= 12) c->cfg.min_blocks = v; }
+    c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.threads, c->cfg.min_blocks);
     if (c->ctas_per_sm < 1) { g_global_err = "the pileup kernel cannot be made resident with this configuration"; delete c; return NGSEP_ECUDA; }
     if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
     Slot* s0 = nullptr;

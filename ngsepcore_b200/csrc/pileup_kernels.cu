@@ -12,9 +12,9 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, kmin, misc, cnt, list, wmax, rare;       // CTA-wide arrays
+    unsigned bar, t0, kmin, misc, cnt, list, wmax, rare;   // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
-    unsigned o_hdr, o_pay, o_ref2, o_refn, o_refl;          // offsets inside a stage
+    unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
 };
 
@@ -23,11 +23,20 @@ constexpr int kMiscSet = 16;
 constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
 
+// State only thread 0 touches (kept in shared memory so that it costs no registers in the other 255 threads).
+struct Thread0State {
+    WinRange dq[2];              // descriptors of window w and of window w + stride, read ahead of their use
+    const unsigned char *ref2, *ref_n, *ref_l; const ngsep_read_hdr* hdr; const uint32_t* payload;   // fields of tile `tile`
+    unsigned long long acc_cov, acc_cand;   // statistics of tile acc_tile, flushed when the tile changes
+    int tile, T, acc_tile, prefetched;
+};
+
 static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     SmemLayout L;
     L.max_reads = pay_cap_words / 24;
     unsigned o = 0;
     L.bar = o; o += 16;
+    L.t0 = o; o += sizeof(Thread0State);
     L.kmin = o; o += kSkipTable * 4;
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
@@ -38,6 +47,7 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     o = (o + 127u) & ~127u;
     L.stage0 = o;
     unsigned s = 0;
+    L.o_win = s; s += sizeof(WinRange);
     L.o_hdr = s; s += (L.max_reads + 1) * 16;
     L.o_pay = s; s += (pay_cap_words + 8) * 4;
     s = (s + 15u) & ~15u;
@@ -70,10 +80,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(20000u)   // suspend-time hint: sleep in hardware instead of spinning
             : "memory");
     }
 }
@@ -118,9 +128,9 @@ __device__ __forceinline__ RecView view_record(const ngsep_read_hdr& h, const ui
     return r;
 }
 
-__device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h, const uint32_t* pay) {
-    // one CIGAR word that is a match block, no N mask, no valid window: the vast majority
-    return (h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && (pay[0] & 7u) == 3u;
+__device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h) {
+    // the packer's promise (verified at staging): one match block as long as the read, no N mask, no valid window
+    return (h.meta & NGSEP_M_SIMPLE) != 0u;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -153,10 +163,9 @@ __device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
 
 // Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
 __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
-    const int L = (int)(h.meta & 0xffffu);
-    const int mlen = (int)(pay[0] >> 3);
+    const int L = (int)(h.meta & 0xffffu);         // one match block of L bases
     const int ref0 = h.first - 1;                  // 0-based index of read offset 0
-    const int a = max(ref0, w.g_lo), b = min(ref0 + mlen, w.g_hi);
+    const int a = max(ref0, w.g_lo), b = min(ref0 + L, w.g_hi);
     if (a < b && w.collect) {
         const uint32_t* b2 = pay + 1;
         const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;       // payload words that intersect the window
@@ -187,16 +196,23 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
         };
         if (j1 - j0 < 32) {
             // Branch-free pass over the words (a warp would otherwise take the mismatch path on almost every iteration,
-            // since SOME lane has a mismatch), then the few words that differ
-            uint32_t wm = 0u, wlo = rp[0];
-            for (int j = j0; j <= j1; j++) {
-                const uint32_t whi = rp[j - j0 + 1];
-                const uint32_t x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
+            // since SOME lane has a mismatch), then the few words that differ.  First and last word carry the masks.
+            uint32_t wlo = rp[0], whi = rp[1];
+            uint32_t x = b2[j0] ^ __funnelshift_r(wlo, whi, sh);
+            uint32_t m = (x | (x >> 1)) & 0x55555555u & head;
+            if (j1 == j0) m &= tail;
+            uint32_t wm = (m != 0u) ? 1u : 0u;
+            for (int j = j0 + 1; j < j1; j++) {
                 wlo = whi;
-                uint32_t m = (x | (x >> 1)) & 0x55555555u;
-                m &= (j == j0) ? head : 0xffffffffu;
-                m &= (j == j1) ? tail : 0xffffffffu;
+                whi = rp[j - j0 + 1];
+                x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
+                m = (x | (x >> 1)) & 0x55555555u;
                 wm |= (m != 0u ? 1u : 0u) << (j - j0);
+            }
+            if (j1 > j0) {
+                x = b2[j1] ^ __funnelshift_r(whi, rp[j1 - j0 + 1], sh);
+                m = (x | (x >> 1)) & 0x55555555u & tail;
+                wm |= (m != 0u ? 1u : 0u) << (j1 - j0);
             }
             while (wm) {
                 const int j = j0 + __ffs(wm) - 1;
@@ -207,7 +223,7 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
             for (int j = j0; j <= j1; j++) { const uint32_t m = diff(j); if (m) flag_word(j, m); }
         }
     }
-    return ref0 + mlen;
+    return ref0 + L;
 }
 
 // General record (indels, clips, N mask, realigner versions): every aligned base that differs from the reference
@@ -485,17 +501,14 @@ struct ExactCtx {
 // Is record idx a simple record whose base at pos is a COUNTED reference base?  (offset = pos - first with one match
 // block, RA:842-871; callable, RA:782-784; q > 3, CH:214.)
 template <bool kGlobal>
-__device__ __forceinline__ bool counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
-    if (idx < 0 || idx >= R.n) return false;
+__device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
+    if (idx < 0 || idx >= R.n) return 0;
     const ngsep_read_hdr h = R.header(idx);
-    if ((h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) != 0x00010000u) return false;
-    const uint32_t* pay = R.payload(h);
-    const uint32_t c0 = pay[0];
     const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
-    if ((c0 & 7u) != 3u || off < 0 || off >= (int)(c0 >> 3) || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return false;
-    const uint32_t* b2 = pay + 1;
+    if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
+    const uint32_t* b2 = R.payload(h) + 1;
     const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
-    return q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref;
+    return (q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
 }
 
 // Column extraction (warp-cooperative): every covering record in pileup order, one record per lane and round, restating
@@ -503,6 +516,7 @@ __device__ __forceinline__ bool counted_ref_base(const Recs<kGlobal>& R, int idx
 // k_genotype_columns turns them into counts, log-likelihoods and the genotype.
 template <bool kGlobal>
 __device__ __forceinline__ void extract_column(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, int max_qs, int li, int lane) {
+    if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) return;           // SSVPL:198: no discovery at all
     const int pos = x.wbeg + li + 1;
     const uint32_t ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
     const int rr = li + kRefLeft;
@@ -539,29 +553,30 @@ __device__ __forceinline__ void extract_column(const Recs<kGlobal>& R, const Exa
 // were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
 // of the records does).  k_lb >= k_min[m_up] closes the column.  What is left goes to the column queue.
 template <bool kGlobal>
-__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, const DevParams& prm, int warp, int lane) {
+__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, const DevParams& prm, int warp, int lane, int nwarps) {
     const int grp = lane >> 4, gl = lane & 15;
-    for (int base = 0; base < x.n_cand; base += 2 * kWarps) {
+    for (int base = 0; base < x.n_cand; base += 2 * nwarps) {
         const int ci = base + 2 * warp + grp;
         const bool act = ci < x.n_cand;
         uint32_t ent = 0u, m_up = 0u;
         int li = 0, pos = 0, ref = 0;
-        bool open = false, ok = false;
+        bool open = false;
+        int ok = 0;
         if (act) {
             ent = x.s_list[ci];
             li = (int)(ent & kListPosMask);
             pos = x.wbeg + li + 1;
-            open = !(x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u));            // SSVPL:198: no discovery at all
+            open = true;
             if (!x.emit_all) {
                 m_up = x.s_cnt[li];
-                const bool ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
-                if (ref_bad) open = false;                                                  // VD:101-107
+                if ((x.s_refn[li >> 5] >> (li & 31)) & 1u) open = false;                                  // VD:101-107
+                if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;               // SSVPL:198
                 const int rr = li + kRefLeft;
                 ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
                 if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
             }
         }
-        const unsigned okm = __ballot_sync(kFull, ok);
+        const unsigned okm = __ballot_sync(kFull, ok != 0);
         if (act && !x.emit_all) {
             if (gl == 0) x.s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
             if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
@@ -577,8 +592,8 @@ __device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactC
             if (!x.emit_all && prm.fast_homref && mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
                 // second chance with the whole warp: 32 records around the flagging one
                 const int e_ref = __shfl_sync(kFull, ref, src);
-                const bool ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, x.wbeg + e_li + 1, e_ref);
-                if (__popc(__ballot_sync(kFull, ok2)) >= x.s_kmin[mu]) continue;
+                const int ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, x.wbeg + e_li + 1, e_ref);
+                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= x.s_kmin[mu]) continue;
             }
             extract_column(R, x, cq, prm.max_base_qs, e_li, lane);
         }
@@ -598,8 +613,9 @@ struct KArgs {
     SmemLayout lay;
 };
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const KArgs a) {
+template <int kThr, int kMinBlocks>
+__global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs a) {
+    constexpr int nthr = kThr, nwarps = kThr / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout& lay = a.lay;
     uint64_t* s_bar = (uint64_t*)(smem + lay.bar);
@@ -614,84 +630,104 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
     const DevParams& prm = *a.prm;
     if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
     if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
-    for (int i = tid; i < a.cfg.T_lay + 1; i += kThreads) s_cnt[i] = 0u;
+    for (int i = tid; i < a.cfg.T_lay + 1; i += nthr) s_cnt[i] = 0u;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
     uint32_t phase[2] = {0u, 0u};
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     const int n_stages = a.cfg.n_stages;
+    const int stride = (int)gridDim.x;
 
     auto fits = [&](const WinRange& wr) {
         return (wr.hi - wr.lo) <= (int)lay.max_reads && (wr.off_hi - (wr.off_lo & ~3u)) <= a.cfg.pay_cap_words;
     };
-    // thread 0: one mbarrier phase = the reference window + (windows that fit a stage) the whole record range
-    auto issue_window = [&](const WinRange& wr, int stage) {
-        const TileDev& d = a.tiles[wr.tile];
+
+    // ---- thread 0 only: window descriptors are read ahead of their use, tile fields are cached while the tile stays --------
+    Thread0State& t0 = *(Thread0State*)(smem + lay.t0);
+    // one mbarrier phase = the window descriptor + the reference window + (windows that fit a stage) the whole record range
+    auto issue_window = [&](const WinRange& wr, int w_idx, int stage) {
+        if (wr.tile != t0.tile) {
+            const TileDev& d = a.tiles[wr.tile];
+            t0.tile = wr.tile; t0.T = d.T;
+            t0.ref2 = (const unsigned char*)d.ref2; t0.ref_n = (const unsigned char*)d.ref_n; t0.ref_l = (const unsigned char*)d.ref_l;
+            t0.hdr = d.hdr; t0.payload = d.payload;
+        }
         unsigned char* stg = smem + lay.stage0 + (unsigned)stage * lay.stage_stride;
         uint64_t* bar = &s_bar[stage];
-        const int T = d.T;
-        const int64_t wbeg = (int64_t)wr.wabs * T;
-        const uint32_t b_ref2 = (uint32_t)(T + 2 * kRefLeft) / 4u, b_bits = (uint32_t)T / 8u;
+        const int64_t wbeg = wr.wbeg;
+        const uint32_t b_ref2 = (uint32_t)(t0.T + 2 * kRefLeft) / 4u, b_bits = (uint32_t)t0.T / 8u;
         const bool recs = fits(wr) && wr.hi > wr.lo;
         const uint32_t o0 = wr.off_lo & ~3u;
         const uint32_t hb = recs ? (uint32_t)(wr.hi - wr.lo + 1) * 16u : 0u;   // + the next record's header (sentinel)
         const uint32_t pb = recs ? (((wr.off_hi - o0) * 4u + 15u) & ~15u) : 0u;
-        mbar_expect_tx(bar, b_ref2 + b_bits + (ignore_lower ? b_bits : 0u) + hb + pb);
-        bulk_g2s(stg + lay.o_ref2, (const unsigned char*)d.ref2 + (wbeg - kRefLeft) / 4, b_ref2, bar);
-        bulk_g2s(stg + lay.o_refn, (const unsigned char*)d.ref_n + wbeg / 8, b_bits, bar);
-        if (ignore_lower) bulk_g2s(stg + lay.o_refl, (const unsigned char*)d.ref_l + wbeg / 8, b_bits, bar);
-        if (hb) bulk_g2s(stg + lay.o_hdr, d.hdr + wr.lo, hb, bar);
-        if (pb) bulk_g2s(stg + lay.o_pay, d.payload + o0, pb, bar);
+        mbar_expect_tx(bar, (uint32_t)sizeof(WinRange) + b_ref2 + b_bits + (ignore_lower ? b_bits : 0u) + hb + pb);
+        bulk_g2s(stg + lay.o_win, a.win + w_idx, (uint32_t)sizeof(WinRange), bar);
+        bulk_g2s(stg + lay.o_ref2, t0.ref2 + (wbeg - kRefLeft) / 4, b_ref2, bar);
+        bulk_g2s(stg + lay.o_refn, t0.ref_n + wbeg / 8, b_bits, bar);
+        if (ignore_lower) bulk_g2s(stg + lay.o_refl, t0.ref_l + wbeg / 8, b_bits, bar);
+        if (hb) bulk_g2s(stg + lay.o_hdr, t0.hdr + wr.lo, hb, bar);
+        if (pb) bulk_g2s(stg + lay.o_pay, t0.payload + o0, pb, bar);
+    };
+    auto flush_stats = [&]() {
+        if (t0.acc_tile >= 0) {
+            const TileDev& dp = a.tiles[t0.acc_tile];
+            if (t0.acc_cov) atomicAdd(&dp.counters[0], t0.acc_cov);
+            if (t0.acc_cand) atomicAdd(&dp.counters[1], t0.acc_cand);
+        }
     };
 
     int w = blockIdx.x;
     if (w >= a.n_windows) return;
-    WinRange wr = a.win[w];
-    bool prefetched = false;   // thread 0: the records of window w are already in flight
+    if (tid == 0) {
+        t0.tile = -1; t0.acc_tile = -1; t0.acc_cov = 0ull; t0.acc_cand = 0ull; t0.prefetched = 0;
+        t0.dq[0] = a.win[w];
+        t0.dq[1] = (w + stride < a.n_windows) ? a.win[w + stride] : t0.dq[0];
+    }
     for (int it = 0; w < a.n_windows; it++) {
         const int cur = (n_stages == 2) ? (it & 1) : 0;
-        const int wn = w + (int)gridDim.x;
-        WinRange nr = wr;
-        if (wn < a.n_windows) nr = a.win[wn];
+        const int wn = w + stride;
         if (tid == 0) {
-            if (!prefetched) issue_window(wr, cur);
-            prefetched = false;
-            if (n_stages == 2 && wn < a.n_windows) { issue_window(nr, cur ^ 1); prefetched = true; }   // other stage: free since the trailing barrier
+            WinRange dq2;   // window w + 2 stride: requested now, consumed at the end of this block (its latency overlaps the issue)
+            const bool have2 = wn + stride < a.n_windows;
+            if (have2) dq2 = a.win[wn + stride];
+            if (!t0.prefetched) issue_window(t0.dq[0], w, cur);
+            t0.prefetched = 0;
+            if (n_stages == 2 && wn < a.n_windows) { issue_window(t0.dq[1], wn, cur ^ 1); t0.prefetched = 1; }   // other stage: free since the trailing barrier
+            t0.dq[0] = t0.dq[1];
+            if (have2) t0.dq[1] = dq2;
         }
-        const TileDev& d = a.tiles[wr.tile];
-        const int T = d.T;
-        const int wbeg = wr.wabs * T;
-        const int g_lo = max(wbeg, d.tile_first - 1);
-        const int g_hi = (int)min((int64_t)min(wbeg + T, d.tile_last), d.ref_len);
-        const int A = g_lo + 1, B = g_hi;   // 1-based inclusive positions of the window (empty when A > B)
-        const int n_rec = wr.hi - wr.lo;
-        const bool single = fits(wr);
         unsigned char* stg = smem + lay.stage0 + (unsigned)cur * lay.stage_stride;
         const ngsep_read_hdr* s_hdr = (const ngsep_read_hdr*)(stg + lay.o_hdr);
         const uint32_t* s_pay = (const uint32_t*)(stg + lay.o_pay);
         int* mset = s_misc + (it & 1) * kMiscSet;
+
+        mbar_wait(&s_bar[cur], phase[cur]);
+        phase[cur] ^= 1u;
+
+        const WinRange wr = *(const WinRange*)(stg + lay.o_win);
+        const int wbeg = wr.wbeg, g_lo = wr.wbeg + (int)(wr.g_pack & 0xffffu), g_hi = wr.wbeg + (int)(wr.g_pack >> 16);
+        const int A = g_lo + 1, B = g_hi;   // 1-based inclusive positions of the window (empty when A > B)
+        const int n_rec = wr.hi - wr.lo;
+        const bool single = fits(wr);
         WinCtx wc;
         wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
         wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
         wc.s_cnt = s_cnt; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
-
-        mbar_wait(&s_bar[cur], phase[cur]);
-        phase[cur] ^= 1u;
 
         // ---- phase A: screen + coverage scan, one thread per record -------------------------------------------------
         // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
         // positions of (reach_i, s_{i+1}) are covered by nobody.  reach_i is at least the warp-local prefix maximum; only
         // when that does not reach s_{i+1} - 1 is the record queued for the exact cross-warp evaluation (process_rare).
         auto screen_chunk = [&](int n_chunk, uint32_t pay_base, int rec0, bool first_chunk) {
-            for (int base = 0; base < n_chunk; base += kThreads) {
+            for (int base = 0; base < n_chunk; base += nthr) {
                 const int i = base + tid;
                 const bool act = i < n_chunk;
                 int e = INT_MIN, nxt = INT_MIN, floor_i = INT_MAX;
                 if (act) {
                     const ngsep_read_hdr h = s_hdr[i];
                     const uint32_t* pay = s_pay + (h.off - pay_base);
-                    e = record_is_simple(h, pay) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
+                    e = record_is_simple(h) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
                     nxt = min(s_hdr[i + 1].first, B + 1);
                     floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
                     if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
@@ -704,7 +740,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
         };
         auto process_rare = [&](int carry) {
             const int n_rare = mset[M_NRARE];
-            for (int k = tid; k < n_rare; k += kThreads) {
+            for (int k = tid; k < n_rare; k += nthr) {
                 const int2 rr = s_rare[k];
                 int reach = max(max(rr.y, A - 1), max(carry, s_hdr[rr.x].first - 1));
                 for (int c = 0; c < (rr.x >> 5); c++) reach = max(reach, s_wmax[c]);
@@ -713,12 +749,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
             }
         };
 
-        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += kThreads) s_list[i] = (uint32_t)(g_lo - wbeg + i);
+        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += nthr) s_list[i] = (uint32_t)(g_lo - wbeg + i);
         if (single) {
             if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, 0, true);
             else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
         } else {
             // windows too deep for one stage: stream the record range chunk by chunk through the current stage
+            const TileDev& d = a.tiles[wr.tile];
             int r0 = wr.lo;
             bool first_chunk = true;
             while (r0 < wr.hi) {
@@ -762,21 +799,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
 
         if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
         if (single && n_rec > 0) process_rare(INT_MIN);
+        // ---- phase C: hom-ref proofs (half-warp per candidate) + column extraction of what stays open ---------------------
         const int n_cand = emit_all ? max(0, g_hi - g_lo) : mset[M_NCAND];
-
-        // ---- phase C: exact evaluation, one warp per candidate ------------------------------------------------------------
-        ExactCtx x;
-        x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = d.max_span; x.max_back = d.max_back; x.tile = wr.tile;
-        x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
-        x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
-        x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
         if (n_cand > 0 && n_rec > 0) {
+            ExactCtx x;
+            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile;
+            x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
+            x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
+            x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                exact_phase<false>(R, x, a.cq, prm, warp, lane);
+                exact_phase<false>(R, x, a.cq, prm, warp, lane, nwarps);
             } else {
+                const TileDev& d = a.tiles[wr.tile];
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                exact_phase<true>(R, x, a.cq, prm, warp, lane);
+                exact_phase<true>(R, x, a.cq, prm, warp, lane, nwarps);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
@@ -787,8 +824,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
             // rare: a gap in the cover of the unversioned records while realigner versions are present — count the cover
             // of every record with a bitmap (s_cnt is all zero here — every listed position reset its counter — and is
             // cleared again below)
+            const TileDev& d = a.tiles[wr.tile];
             uint32_t* s_bm = s_cnt;
-            for (int i = tid; i < n_rec; i += kThreads) {
+            const int n_words = (g_hi - wbeg + 31) >> 5;
+            for (int i = tid; i < n_rec; i += nthr) {
                 const ngsep_read_hdr h = d.hdr[wr.lo + i];
                 int s, e;
                 record_interval(h, d.payload + h.off, s, e);
@@ -797,22 +836,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) k_pileup_windows(const K
             }
             __syncthreads();
             int cnt = 0;
-            for (int i = tid; i < T / 32; i += kThreads) cnt += __popc(s_bm[i]);
+            for (int i = tid; i < n_words; i += nthr) cnt += __popc(s_bm[i]);
             for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(kFull, cnt, o);
             if (lane == 0 && cnt) atomicAdd(&mset[M_FBCOV], cnt);
             __syncthreads();
             uncovered = win_len - mset[M_FBCOV];
-            for (int i = tid; i < T / 32; i += kThreads) s_bm[i] = 0u;
+            for (int i = tid; i < n_words; i += nthr) s_bm[i] = 0u;
             __syncthreads();
         }
         if (tid == 0) {
-            const int covered = win_len - uncovered;
-            if (covered > 0) atomicAdd(&d.counters[0], (unsigned long long)covered);
-            if (n_cand > 0 && !emit_all) atomicAdd(&d.counters[1], (unsigned long long)n_cand);
+            if (wr.tile != t0.acc_tile) { flush_stats(); t0.acc_tile = wr.tile; t0.acc_cov = 0ull; t0.acc_cand = 0ull; }
+            t0.acc_cov += (unsigned long long)(win_len - uncovered);
+            if (!emit_all) t0.acc_cand += (unsigned long long)n_cand;
         }
         w = wn;
-        wr = nr;
     }
+    if (tid == 0) flush_stats();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -878,7 +917,11 @@ __global__ void k_window_index(const TileDev d, WinRange* out, int tile_idx) {
     WinRange r;
     r.lo = a; r.hi = lo;
     r.off_lo = d.hdr[a].off; r.off_hi = d.hdr[lo].off;
-    r.tile = tile_idx; r.wabs = d.win0 + w;
+    r.tile = tile_idx; r.wbeg = (int)wbeg;
+    // [g_lo, g_hi): 0-based indexes of the window inside the tile and the sequence, relative to wbeg
+    const int64_t g_lo = max(wbeg, (int64_t)d.tile_first - 1), g_hi = max(g_lo, min(min(wbeg + d.T, (int64_t)d.tile_last), d.ref_len));
+    r.g_pack = (uint32_t)(g_lo - wbeg) | ((uint32_t)(g_hi - wbeg) << 16);
+    r.span_pack = (uint32_t)min(d.max_span, 0xffff) | ((uint32_t)min(d.max_back, 0xffff) << 16);
     out[w] = r;
 }
 
@@ -912,19 +955,39 @@ void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStre
     if (n > 0) k_window_index<<<(n + 127) / 128, 128, 0, s>>>(d, out, tile_idx);
 }
 
-// The kernel is compiled for three register budgets (3, 4 or 5 resident CTAs per SM); the context picks one.
-typedef void (*PileupKernel)(const KArgs);
-static PileupKernel kernel_for(int min_blocks) {
-    if (min_blocks <= 3) return k_pileup_windows<3>;
-    if (min_blocks == 4) return k_pileup_windows<4>;
-    return k_pileup_windows<5>;
+// The packer's NGSEP_M_SIMPLE promise is checked once per staging, on the device copy of the headers: a record whose
+// flag is not backed by its payload loses the flag (and goes through the general path, which is always correct).
+__global__ void k_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t meta = hdr[i].meta;
+    if (!(meta & NGSEP_M_SIMPLE)) return;
+    const bool ok = (meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && payload[hdr[i].off] == (((meta & 0xffffu) << 3) | 3u);
+    if (!ok) hdr[i].meta = meta & ~NGSEP_M_SIMPLE;
 }
 
-int pileup_max_ctas_per_sm(size_t smem, int min_blocks) {
-    PileupKernel k = kernel_for(min_blocks);
+void launch_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, cudaStream_t s) {
+    if (n > 0) k_sanitize_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n);
+}
+
+// The kernel is compiled for two CTA sizes and three register budgets each; the context picks one.
+typedef void (*PileupKernel)(const KArgs);
+static PileupKernel kernel_for(int threads, int min_blocks) {
+    if (threads == 128) {
+        if (min_blocks <= 8) return k_pileup_windows<128, 8>;
+        if (min_blocks <= 10) return k_pileup_windows<128, 10>;
+        return k_pileup_windows<128, 12>;
+    }
+    if (min_blocks <= 3) return k_pileup_windows<256, 3>;
+    if (min_blocks == 4) return k_pileup_windows<256, 4>;
+    return k_pileup_windows<256, 5>;
+}
+
+int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks) {
+    PileupKernel k = kernel_for(threads, min_blocks);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, kThreads, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, threads, smem) != cudaSuccess) return 0;
     return n;
 }
 
@@ -933,7 +996,7 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
     KArgs a;
     a.tiles = d_tiles; a.win = d_win; a.n_windows = n_windows; a.prm = dprm; a.cq = cq; a.cfg = cfg;
     a.lay = make_layout(cfg.T_lay, cfg.pay_cap_words, cfg.n_stages);
-    kernel_for(cfg.min_blocks)<<<grid, kThreads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
+    kernel_for(cfg.threads, cfg.min_blocks)<<<grid, cfg.threads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
 }
 
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {

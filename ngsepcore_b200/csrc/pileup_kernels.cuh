@@ -25,13 +25,17 @@
 
 namespace ngsep_b200 {
 
-constexpr int kThreads = 256;          // threads per CTA
-constexpr int kWarps = kThreads / 32;
+constexpr int kThreads = 256;          // largest CTA (the window kernel is built for 128 and 256 threads)
 constexpr int kRefLeft = 64;           // reference bases staged to the left of a window (read words straddle its start)
 constexpr int kMaxWindow = 8192;       // largest window length (positions); windows are multiples of 128
 
-// Record range [lo,hi) of one window, its payload span (words) and where the window lives.
-struct WinRange { int lo, hi; uint32_t off_lo, off_hi; int tile; int wabs; };
+// Record range [lo,hi) of one window, its payload span (words) and where the window lives: 0-based index of its first
+// position and the index range [g_lo, g_hi) that lies inside the tile and the sequence.  32 bytes: bulk-copied with the window.
+struct WinRange {
+    int lo, hi; uint32_t off_lo, off_hi; int tile, wbeg;
+    uint32_t g_pack;     // (g_lo - wbeg) | (g_hi - wbeg) << 16
+    uint32_t span_pack;  // the tile's max_span | max_back << 16 (both capped at 65535)
+};
 
 struct TileDev {
     const ngsep_read_hdr* hdr;   // [n_reads + 1], sentinel at n_reads carries off = n_words, first = INT_MAX
@@ -73,12 +77,14 @@ struct LaunchCfg {
     int T_lay;                   // window length the shared-memory layout is sized for
     unsigned int pay_cap_words;  // payload words one stage holds
     int n_stages;                // 1 or 2 staged windows per CTA
-    int min_blocks;              // register budget: the kernel variant compiled for 3, 4 or 5 resident CTAs per SM
+    int min_blocks;              // register budget: resident CTAs per SM the kernel variant is compiled for (256 threads: 3, 4, 5; 128: 8, 10, 12)
+    int threads;                 // CTA size: 128 or 256
 };
 
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
-int pileup_max_ctas_per_sm(size_t smem, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
+int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
+void launch_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .capi import HDR_DTYPE, M_NEG, M_NMASK
+from .capi import HDR_DTYPE, M_NEG, M_NMASK, M_SIMPLE
 from .simulate import AlignmentBatch
 
 FLAG_UNMAPPED, FLAG_REVERSE, FLAG_SECONDARY, FLAG_MULTIPLE = 0x4, 0x10, 0x100, 0x1000
@@ -109,7 +109,10 @@ def pack_tile(batch: AlignmentBatch, idx: np.ndarray, ignore5: int = 0, ignore3:
     q_word = off[:-1][rep] + nc[rep] + w_b2[rep] + w_nm[rep] + within // 4
     np.add.at(payload, q_word, (quals.astype(np.uint32) << ((within % 4) * 8).astype(np.uint32)))
     hdr["first"] = batch.first[idx]
-    hdr["meta"] = (L | (nc << 16) | np.where(neg, M_NEG, 0) | np.where(has_n, M_NMASK, 0)).astype(np.uint32)
+    first_cig = np.zeros(n, np.int64)
+    first_cig[nc > 0] = batch.cigar[batch.cigar_off[idx][nc > 0]]
+    simple = (nc == 1) & ~has_n & (first_cig == ((L << 3) | 3))   # one match block as long as the read (NGSEP_M_SIMPLE)
+    hdr["meta"] = (L | (nc << 16) | np.where(neg, M_NEG, 0) | np.where(has_n, M_NMASK, 0) | np.where(simple, M_SIMPLE, 0)).astype(np.uint32)
     # 5' is the alignment start for + strand reads and the alignment end for - strand reads (RA:613-644)
     hdr["ign_start"] = np.where(neg, ignore3, ignore5)
     hdr["ign_end"] = np.where(neg, ignore5, ignore3)
