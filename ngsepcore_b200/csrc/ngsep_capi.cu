@@ -87,6 +87,7 @@ struct Ctx {
     // column queue shared by every launch of this context (launches are stream-ordered)
     DevBuf<ColumnHdr> d_cols;
     DevBuf<uint16_t> d_codes;
+    DevBuf<uint2> d_open;
     size_t q_min_cols = 0, q_min_codes = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
@@ -140,24 +141,27 @@ int ensure_queue(Ctx* c, size_t cols, size_t codes) {
     cols = std::max(cols, c->q_min_cols); codes = std::max(codes, c->q_min_codes);
     if (codes > 0xfffffff0ull || cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "column queue too large (split the tile)");
     CK(c->d_cols.reserve(cols), "column queue alloc");
+    CK(c->d_open.reserve(cols), "column queue alloc");
     CK(c->d_codes.reserve(codes), "column queue alloc");
     return NGSEP_OK;
 }
 
 ColumnQueue queue_view(Ctx* c) {
     ColumnQueue q;
-    q.cols = c->d_cols.p; q.codes = c->d_codes.p; q.ctr = (unsigned int*)c->d_meta;
+    q.cols = c->d_cols.p; q.codes = c->d_codes.p; q.open = c->d_open.p; q.ctr = (unsigned int*)c->d_meta;
+    q.cap_open = (unsigned int)c->d_open.cap;
     q.cap_cols = (unsigned int)c->d_cols.cap; q.cap_codes = (unsigned int)std::min<size_t>(c->d_codes.cap, 0xfffffff0ull);
     return q;
 }
 
 // After a run: did the column queue overflow?  (stream must be idle)  Returns 1 when it grew and the run must be repeated.
 int queue_overflowed(Ctx* c, int* grew) {
-    unsigned int ctr[2] = {0, 0};
+    unsigned int ctr[3] = {0, 0, 0};
     CK(cudaMemcpy(ctr, c->d_meta, sizeof(ctr), cudaMemcpyDeviceToHost), "queue counters copy");
     *grew = 0;
-    if (ctr[0] > c->d_cols.cap || ctr[1] > c->d_codes.cap) {
-        c->q_min_cols = std::max(c->q_min_cols, (size_t)ctr[0] + (size_t)ctr[0] / 4 + 1024);
+    if (ctr[0] > c->d_cols.cap || ctr[1] > c->d_codes.cap || ctr[2] > c->d_open.cap) {
+        const unsigned int nc = std::max(ctr[0], ctr[2]);
+        c->q_min_cols = std::max(c->q_min_cols, (size_t)nc + (size_t)nc / 4 + 1024);
         c->q_min_codes = std::max(c->q_min_codes, (size_t)ctr[1] + (size_t)ctr[1] / 4 + 65536);
         *grew = 1;
     }
@@ -179,7 +183,7 @@ int launch_slot(Ctx* c, Slot* s) {
     CK(cudaEventRecord(s->e0, c->stream), "event record");
     if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
-    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->sm_count * 4, c->stream); s->launches = 2; }
+    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, s->d_win.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream); s->launches = 3; }
     CK(cudaEventRecord(s->e1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     s->launched = true;
@@ -220,7 +224,7 @@ int launch_batch(Ctx* c) {
     CK(cudaEventRecord(c->b0, c->stream), "event record");
     if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, queue_view(c), c->cfg, c->b_grid, c->smem, c->stream);
     CK(cudaEventRecord(c->bm, c->stream), "event record");
-    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream);
+    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, c->d_bwin.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream);
     CK(cudaEventRecord(c->b1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
@@ -577,7 +581,7 @@ int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats) {
     CK(cudaEventElapsedTime(&pms, c->b0, c->bm), "event elapsed");
     stats->kernel_ms = ms;
     stats->pileup_ms = pms;
-    stats->kernel_launches = c->b_windows > 0 ? 2u : 0u;
+    stats->kernel_launches = c->b_windows > 0 ? 3u : 0u;
     return NGSEP_OK;
 }
 

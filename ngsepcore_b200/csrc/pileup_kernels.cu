@@ -12,7 +12,7 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, t0, kmin, misc, cnt, list, wmax, rare;   // CTA-wide arrays
+    unsigned bar, t0, kmin, misc, cnt, list, open, wmax, rare;   // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
@@ -20,7 +20,7 @@ struct SmemLayout {
 
 // s_misc holds two sets of kMiscSet ints (one per window parity)
 constexpr int kMiscSet = 16;
-constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7;
+constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
 
 // State only thread 0 touches (kept in shared memory so that it costs no registers in the other 255 threads).
@@ -41,6 +41,7 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
     L.list = o; o += T * 4;
+    L.open = o; o += 2 * ((T * 2 + 3) & ~3u);   // open columns of the window, one list per window parity
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
     o = (o + 7u) & ~7u;
     L.rare = o; o += (L.max_reads + 1) * 8;
@@ -514,15 +515,10 @@ __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx,
 // Column extraction (warp-cooperative): every covering record in pileup order, one record per lane and round, restating
 // PR.getAlleleCalls(1).  The calls (allele, quality, strand, counted) are appended to the column queue in that order;
 // k_genotype_columns turns them into counts, log-likelihoods and the genotype.
-template <bool kGlobal>
-__device__ __forceinline__ void extract_column(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, int max_qs, int li, int lane) {
-    if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) return;           // SSVPL:198: no discovery at all
-    const int pos = x.wbeg + li + 1;
-    const uint32_t ref_bad = (x.s_refn[li >> 5] >> (li & 31)) & 1u;
-    const int rr = li + kRefLeft;
-    const uint32_t ref = (x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
-    const int i_lo = warp_lower_bound(R, pos - x.max_span + 1, lane);
-    const int i_hi = warp_lower_bound(R, pos + x.max_back + 1, lane);   // first record that starts too far to the right
+__device__ __forceinline__ void extract_column(const Recs<true>& R, const ColumnQueue& cq, int tile, int pos, uint32_t ref, uint32_t ref_bad,
+                                               int max_span, int max_back, int max_qs, int lane) {
+    const int i_lo = warp_lower_bound(R, pos - max_span + 1, lane);
+    const int i_hi = warp_lower_bound(R, pos + max_back + 1, lane);   // first record that starts too far to the right
     const int n_max = i_hi - i_lo;
     if (n_max <= 0) return;
     unsigned int col = 0, off = 0;
@@ -544,16 +540,17 @@ __device__ __forceinline__ void extract_column(const Recs<kGlobal>& R, const Exa
     }
     if (lane == 0 && room) {
         ColumnHdr ch;
-        ch.tile = x.tile; ch.pos = pos; ch.code_off = off; ch.n_codes = n | (ref << 28) | (ref_bad << 30);
+        ch.tile = tile; ch.pos = pos; ch.code_off = off; ch.n_codes = n | (ref << 28) | (ref_bad << 30);
         cq.cols[col] = ch;
     }
 }
 
 // Phase C.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
 // were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
-// of the records does).  k_lb >= k_min[m_up] closes the column.  What is left goes to the column queue.
+// of the records does).  k_lb >= k_min[m_up] closes the column.  What stays open is listed for k_extract_columns.
 template <bool kGlobal>
-__device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, const DevParams& prm, int warp, int lane, int nwarps) {
+__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const DevParams& prm, uint16_t* s_open, int* n_open,
+                                            int warp, int lane, int nwarps) {
     const int grp = lane >> 4, gl = lane & 15;
     for (int base = 0; base < x.n_cand; base += 2 * nwarps) {
         const int ci = base + 2 * warp + grp;
@@ -566,22 +563,19 @@ __device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactC
             ent = x.s_list[ci];
             li = (int)(ent & kListPosMask);
             pos = x.wbeg + li + 1;
-            open = true;
-            if (!x.emit_all) {
-                m_up = x.s_cnt[li];
-                if ((x.s_refn[li >> 5] >> (li & 31)) & 1u) open = false;                                  // VD:101-107
-                if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;               // SSVPL:198
-                const int rr = li + kRefLeft;
-                ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
-                if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
-            }
+            m_up = x.s_cnt[li];
+            open = !((x.s_refn[li >> 5] >> (li & 31)) & 1u);                                           // VD:101-107
+            if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;               // SSVPL:198
+            const int rr = li + kRefLeft;
+            ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
+            if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
         }
         const unsigned okm = __ballot_sync(kFull, ok != 0);
-        if (act && !x.emit_all) {
+        if (act) {
             if (gl == 0) x.s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
             if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
         }
-        // the (few) columns still open: the warp handles them one by one
+        // second chance for the (few) columns still open: the whole warp looks at the 32 records around the flagging one
         unsigned sm = __ballot_sync(kFull, open && gl == 0);
         while (sm) {
             const int src = __ffs(sm) - 1;
@@ -589,13 +583,12 @@ __device__ __forceinline__ void exact_phase(const Recs<kGlobal>& R, const ExactC
             const uint32_t e = __shfl_sync(kFull, ent, src);
             const uint32_t mu = __shfl_sync(kFull, m_up, src);
             const int e_li = (int)(e & kListPosMask);
-            if (!x.emit_all && prm.fast_homref && mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
-                // second chance with the whole warp: 32 records around the flagging one
+            if (prm.fast_homref && mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
                 const int e_ref = __shfl_sync(kFull, ref, src);
                 const int ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, x.wbeg + e_li + 1, e_ref);
                 if (__popc(__ballot_sync(kFull, ok2 != 0)) >= x.s_kmin[mu]) continue;
             }
-            extract_column(R, x, cq, prm.max_base_qs, e_li, lane);
+            if (lane == 0) s_open[atomicAdd(n_open, 1)] = (uint16_t)e_li;
         }
     }
 }
@@ -749,7 +742,6 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             }
         };
 
-        if (emit_all) for (int i = tid; i < g_hi - g_lo; i += nthr) s_list[i] = (uint32_t)(g_lo - wbeg + i);
         if (single) {
             if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, 0, true);
             else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
@@ -799,24 +791,40 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 
         if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
         if (single && n_rec > 0) process_rare(INT_MIN);
-        // ---- phase C: hom-ref proofs (half-warp per candidate) + column extraction of what stays open ---------------------
-        const int n_cand = emit_all ? max(0, g_hi - g_lo) : mset[M_NCAND];
-        if (n_cand > 0 && n_rec > 0) {
+        // ---- phase C: hom-ref proofs (half-warp per candidate); what stays open is listed for k_extract_columns -----------
+        uint16_t* s_open = (uint16_t*)(smem + lay.open) + (it & 1) * a.cfg.T_lay;
+        const int n_cand = emit_all ? 0 : mset[M_NCAND];
+        if (emit_all) {   // test hook: every position of the window is an open column
+            for (int i = tid; i < g_hi - g_lo; i += nthr) s_open[i] = (uint16_t)(g_lo - wbeg + i);
+            if (tid == 0) mset[M_NOPEN] = (n_rec > 0) ? max(0, g_hi - g_lo) : 0;
+        } else if (n_cand > 0) {
             ExactCtx x;
-            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile;
+            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = 1; x.max_back = 0; x.tile = wr.tile;
             x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
             x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
             x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                exact_phase<false>(R, x, a.cq, prm, warp, lane, nwarps);
+                proof_phase<false>(R, x, prm, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             } else {
                 const TileDev& d = a.tiles[wr.tile];
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                exact_phase<true>(R, x, a.cq, prm, warp, lane, nwarps);
+                proof_phase<true>(R, x, prm, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
+
+        // warp 0 hands the open columns to the global list (the other warps move on; s_open and mset are per window parity)
+        if (warp == 0) {
+            const int n_open = mset[M_NOPEN];
+            if (n_open > 0) {
+                unsigned int gbase = 0u;
+                if (lane == 0) gbase = atomicAdd(&a.cq.ctr[2], (unsigned int)n_open);
+                gbase = __shfl_sync(kFull, gbase, 0);
+                for (int i = lane; i < n_open; i += 32)
+                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint2((unsigned int)w, (unsigned int)s_open[i]);
+            }
+        }
 
         int uncovered = mset[M_UNC];
         const int win_len = max(0, B - A + 1);
@@ -852,6 +860,29 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         w = wn;
     }
     if (tid == 0) flush_stats();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// extraction of the open columns: one warp per column, records read through L2
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_extract_columns(const TileDev* __restrict__ tiles, const WinRange* __restrict__ win, const ColumnQueue cq,
+                                                         const DevParams* __restrict__ gprm) {
+    const DevParams& prm = *gprm;
+    const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
+        const uint2 oc = cq.open[t];
+        const WinRange wr = win[oc.x];
+        const TileDev& d = tiles[wr.tile];
+        const int64_t gi = (int64_t)wr.wbeg + (int64_t)oc.y;   // 0-based index of the position
+        if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198: no discovery at all
+        const uint32_t ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
+        const uint32_t ref = (d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u;
+        Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = wr.hi - wr.lo;
+        extract_column(R, cq, wr.tile, (int)gi + 1, ref, ref_bad, d.max_span, d.max_back, prm.max_base_qs, lane);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -999,7 +1030,8 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
     kernel_for(cfg.threads, cfg.min_blocks)<<<grid, cfg.threads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
 }
 
-void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+void launch_genotype(const TileDev* d_tiles, const WinRange* d_win, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+    k_extract_columns<<<grid, 256, 0, s>>>(d_tiles, d_win, cq, dprm);
     k_genotype_columns<<<grid, 128, 0, s>>>(d_tiles, cq, dprm);
 }
 
