@@ -87,7 +87,7 @@ struct Ctx {
     // column queue shared by every launch of this context (launches are stream-ordered)
     DevBuf<ColumnHdr> d_cols;
     DevBuf<uint16_t> d_codes;
-    DevBuf<uint2> d_open;
+    DevBuf<uint4> d_open;
     size_t q_min_cols = 0, q_min_codes = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;

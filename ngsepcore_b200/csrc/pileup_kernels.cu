@@ -22,6 +22,8 @@ struct SmemLayout {
 constexpr int kMiscSet = 16;
 constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
+constexpr int kMaxOpen = 64;     // open columns listed in shared memory per window (more go straight to the global list)
+constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: k_extract_columns searches it
 
 // State only thread 0 touches (kept in shared memory so that it costs no registers in the other 255 threads).
 struct Thread0State {
@@ -41,7 +43,8 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
     L.list = o; o += T * 4;
-    L.open = o; o += 2 * ((T * 2 + 3) & ~3u);   // open columns of the window, one list per window parity
+    o = (o + 7u) & ~7u;
+    L.open = o; o += 2 * kMaxOpen * 8;   // open columns of the window, one list per window parity
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
     o = (o + 7u) & ~7u;
     L.rare = o; o += (L.max_reads + 1) * 8;
@@ -512,31 +515,65 @@ __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx,
     return (q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
 }
 
-// Column extraction (warp-cooperative): every covering record in pileup order, one record per lane and round, restating
-// PR.getAlleleCalls(1).  The calls (allele, quality, strand, counted) are appended to the column queue in that order;
-// k_genotype_columns turns them into counts, log-likelihoods and the genotype.
+// Column extraction (warp-cooperative): every record of [i_lo, i_hi) in pileup order, one record per lane and round,
+// restating PR.getAlleleCalls(1).  The calls (allele, quality, strand, counted) are appended to the column queue in that
+// order; k_genotype_columns turns them into counts, log-likelihoods and the genotype.  Columns of up to 128 records are
+// first counted (ballots) and dropped when the exact counts prove the homozygous-reference call.
+constexpr int kRegRounds = 4;
 __device__ __forceinline__ void extract_column(const Recs<true>& R, const ColumnQueue& cq, int tile, int pos, uint32_t ref, uint32_t ref_bad,
-                                               int max_span, int max_back, int max_qs, int lane) {
-    const int i_lo = warp_lower_bound(R, pos - max_span + 1, lane);
-    const int i_hi = warp_lower_bound(R, pos + max_back + 1, lane);   // first record that starts too far to the right
+                                               int i_lo, int i_hi, int max_qs, const int* s_kmin, bool may_skip, int lane) {
     const int n_max = i_hi - i_lo;
     if (n_max <= 0) return;
+    uint32_t codes[kRegRounds];
+    const bool in_regs = n_max <= 32 * kRegRounds;
+    unsigned int n_calls = 0;
+    if (in_regs) {
+        int c_ref = 0, c_all = 0;
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) {
+            const int idx = i_lo + 32 * r + lane;
+            uint32_t code = 0u;
+            if (idx < i_hi) {
+                const ngsep_read_hdr h = R.header(idx);
+                code = lane_eval(h, R.payload(h), pos, max_qs);
+            }
+            codes[r] = code;
+            const bool counted = (code & kCodeCounted) != 0u;
+            n_calls += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));
+            c_all += __popc(__ballot_sync(kFull, counted));
+            c_ref += __popc(__ballot_sync(kFull, counted && (code & 3u) == ref));
+        }
+        if (n_calls == 0 && may_skip) return;                           // empty column: nothing to call (VD:101)
+        const int m_alt = c_all - c_ref;
+        if (may_skip && !ref_bad && (m_alt == 0 || (m_alt < kSkipTable && c_ref >= s_kmin[m_alt]))) return;   // proven hom-ref
+    }
     unsigned int col = 0, off = 0;
-    if (lane == 0) { col = atomicAdd(&cq.ctr[0], 1u); off = atomicAdd(&cq.ctr[1], (unsigned int)n_max); }
+    const unsigned int n_alloc = in_regs ? n_calls : (unsigned int)n_max;
+    if (lane == 0) { col = atomicAdd(&cq.ctr[0], 1u); off = atomicAdd(&cq.ctr[1], n_alloc); }
     col = __shfl_sync(kFull, col, 0);
     off = __shfl_sync(kFull, off, 0);
-    const bool room = col < cq.cap_cols && (uint64_t)off + (uint64_t)n_max <= (uint64_t)cq.cap_codes;   // else: host grows + reruns
+    const bool room = col < cq.cap_cols && (uint64_t)off + (uint64_t)n_alloc <= (uint64_t)cq.cap_codes;   // else: host grows + reruns
     unsigned int n = 0;
-    for (int base = i_lo; base < i_hi; base += 32) {
-        const int idx = base + lane;
-        uint32_t code = 0u;
-        if (idx < i_hi) {
-            const ngsep_read_hdr h = R.header(idx);
-            code = lane_eval(h, R.payload(h), pos, max_qs);
+    if (in_regs) {
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) {
+            const uint32_t code = codes[r];
+            const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
+            if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
+            n += __popc(cm);
         }
-        const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
-        if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
-        n += __popc(cm);
+    } else {
+        for (int base = i_lo; base < i_hi; base += 32) {
+            const int idx = base + lane;
+            uint32_t code = 0u;
+            if (idx < i_hi) {
+                const ngsep_read_hdr h = R.header(idx);
+                code = lane_eval(h, R.payload(h), pos, max_qs);
+            }
+            const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
+            if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
+            n += __popc(cm);
+        }
     }
     if (lane == 0 && room) {
         ColumnHdr ch;
@@ -547,9 +584,10 @@ __device__ __forceinline__ void extract_column(const Recs<true>& R, const Column
 
 // Phase C.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
 // were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
-// of the records does).  k_lb >= k_min[m_up] closes the column.  What stays open is listed for k_extract_columns.
+// of the records does).  k_lb >= k_min[m_up] closes the column (k_min is INT_MAX when the bound does not apply).  What
+// stays open is listed, with its record range, for k_extract_columns.
 template <bool kGlobal>
-__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const DevParams& prm, uint16_t* s_open, int* n_open,
+__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, int w_idx, uint2* s_open, int* n_open,
                                             int warp, int lane, int nwarps) {
     const int grp = lane >> 4, gl = lane & 15;
     for (int base = 0; base < x.n_cand; base += 2 * nwarps) {
@@ -568,27 +606,38 @@ __device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactC
             if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;               // SSVPL:198
             const int rr = li + kRefLeft;
             ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
-            if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
+            if (open && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
         }
         const unsigned okm = __ballot_sync(kFull, ok != 0);
         if (act) {
             if (gl == 0) x.s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
-            if (open && prm.fast_homref && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
+            if (open && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
         }
-        // second chance for the (few) columns still open: the whole warp looks at the 32 records around the flagging one
+        // the (few) columns still open: second chance with the whole warp (the 32 records around the flagging one), then
+        // the record range of the column, then the list
         unsigned sm = __ballot_sync(kFull, open && gl == 0);
         while (sm) {
             const int src = __ffs(sm) - 1;
             sm &= sm - 1;
             const uint32_t e = __shfl_sync(kFull, ent, src);
             const uint32_t mu = __shfl_sync(kFull, m_up, src);
-            const int e_li = (int)(e & kListPosMask);
-            if (prm.fast_homref && mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
+            const int e_li = (int)(e & kListPosMask), e_pos = x.wbeg + e_li + 1;
+            if (mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
                 const int e_ref = __shfl_sync(kFull, ref, src);
-                const int ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, x.wbeg + e_li + 1, e_ref);
+                const int ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, e_pos, e_ref);
                 if (__popc(__ballot_sync(kFull, ok2 != 0)) >= x.s_kmin[mu]) continue;
             }
-            if (lane == 0) s_open[atomicAdd(n_open, 1)] = (uint16_t)e_li;
+            const int i_lo = warp_lower_bound(R, e_pos - x.max_span + 1, lane);
+            const int i_hi = warp_lower_bound(R, e_pos + x.max_back + 1, lane);   // first record that starts too far to the right
+            if (lane == 0 && i_hi > i_lo) {
+                const uint32_t n_range = (uint32_t)min(i_hi - i_lo, (int)kOpenSearch);
+                const int slot = atomicAdd(n_open, 1);
+                if (slot < kMaxOpen) s_open[slot] = make_uint2((uint32_t)e_li | (n_range << 16), (uint32_t)i_lo);
+                else {   // rare: the window's list is full
+                    const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
+                    if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)w_idx, (unsigned int)e_li, (unsigned int)i_lo, n_range);
+                }
+            }
         }
     }
 }
@@ -626,7 +675,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     for (int i = tid; i < a.cfg.T_lay + 1; i += nthr) s_cnt[i] = 0u;
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
-    uint32_t phase[2] = {0u, 0u};
+    uint32_t phase_bits = 0u;   // bit s = parity the next wait on stage s must see
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     const int n_stages = a.cfg.n_stages;
@@ -695,8 +744,8 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         const uint32_t* s_pay = (const uint32_t*)(stg + lay.o_pay);
         int* mset = s_misc + (it & 1) * kMiscSet;
 
-        mbar_wait(&s_bar[cur], phase[cur]);
-        phase[cur] ^= 1u;
+        mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);
+        phase_bits ^= 1u << cur;
 
         const WinRange wr = *(const WinRange*)(stg + lay.o_win);
         const int wbeg = wr.wbeg, g_lo = wr.wbeg + (int)(wr.g_pack & 0xffffu), g_hi = wr.wbeg + (int)(wr.g_pack >> 16);
@@ -771,8 +820,8 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 const int r1 = mset[M_R1];
                 const uint32_t pay_base = (uint32_t)mset[M_PBASE];
                 const int carry = mset[M_CARRY];
-                mbar_wait(&s_bar[cur], phase[cur]);
-                phase[cur] ^= 1u;
+                mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);
+                phase_bits ^= 1u << cur;
                 screen_chunk(r1 - r0, pay_base, r0 - wr.lo, first_chunk);
                 __syncthreads();
                 process_rare(carry);
@@ -792,37 +841,43 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
         if (single && n_rec > 0) process_rare(INT_MIN);
         // ---- phase C: hom-ref proofs (half-warp per candidate); what stays open is listed for k_extract_columns -----------
-        uint16_t* s_open = (uint16_t*)(smem + lay.open) + (it & 1) * a.cfg.T_lay;
+        uint2* s_open = (uint2*)(smem + lay.open) + (it & 1) * kMaxOpen;
         const int n_cand = emit_all ? 0 : mset[M_NCAND];
         if (emit_all) {   // test hook: every position of the window is an open column
-            for (int i = tid; i < g_hi - g_lo; i += nthr) s_open[i] = (uint16_t)(g_lo - wbeg + i);
-            if (tid == 0) mset[M_NOPEN] = (n_rec > 0) ? max(0, g_hi - g_lo) : 0;
+            const int n_all = (n_rec > 0) ? max(0, g_hi - g_lo) : 0;
+            if (tid == 0 && n_all > 0) mset[M_R1] = (int)atomicAdd(&a.cq.ctr[2], (unsigned int)n_all);
+            __syncthreads();
+            const unsigned int gbase = (unsigned int)mset[M_R1];
+            for (int i = tid; i < n_all; i += nthr)
+                if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)w, (unsigned int)(g_lo - wbeg + i), 0u, kOpenSearch);
         } else if (n_cand > 0) {
             ExactCtx x;
-            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = 1; x.max_back = 0; x.tile = wr.tile;
+            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile;
             x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
             x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
             x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                proof_phase<false>(R, x, prm, s_open, &mset[M_NOPEN], warp, lane, nwarps);
+                proof_phase<false>(R, x, a.cq, w, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             } else {
                 const TileDev& d = a.tiles[wr.tile];
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                proof_phase<true>(R, x, prm, s_open, &mset[M_NOPEN], warp, lane, nwarps);
+                proof_phase<true>(R, x, a.cq, w, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
 
         // warp 0 hands the open columns to the global list (the other warps move on; s_open and mset are per window parity)
         if (warp == 0) {
-            const int n_open = mset[M_NOPEN];
+            const int n_open = min(mset[M_NOPEN], kMaxOpen);
             if (n_open > 0) {
                 unsigned int gbase = 0u;
                 if (lane == 0) gbase = atomicAdd(&a.cq.ctr[2], (unsigned int)n_open);
                 gbase = __shfl_sync(kFull, gbase, 0);
-                for (int i = lane; i < n_open; i += 32)
-                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint2((unsigned int)w, (unsigned int)s_open[i]);
+                for (int i = lane; i < n_open; i += 32) {
+                    const uint2 oe = s_open[i];
+                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)w, oe.x & 0xffffu, oe.y, oe.x >> 16);
+                }
             }
         }
 
@@ -867,13 +922,18 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_extract_columns(const TileDev* __restrict__ tiles, const WinRange* __restrict__ win, const ColumnQueue cq,
                                                          const DevParams* __restrict__ gprm) {
+    __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
+    if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
+    __syncthreads();
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const bool may_skip = prm.fast_homref && !(prm.flags & NGSEP_F_EMIT_ALL);
+    const int max_qs = prm.max_base_qs;
     const int lane = threadIdx.x & 31;
     const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
-        const uint2 oc = cq.open[t];
+        const uint4 oc = cq.open[t];
         const WinRange wr = win[oc.x];
         const TileDev& d = tiles[wr.tile];
         const int64_t gi = (int64_t)wr.wbeg + (int64_t)oc.y;   // 0-based index of the position
@@ -881,7 +941,13 @@ __global__ void __launch_bounds__(256) k_extract_columns(const TileDev* __restri
         const uint32_t ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
         const uint32_t ref = (d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u;
         Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = wr.hi - wr.lo;
-        extract_column(R, cq, wr.tile, (int)gi + 1, ref, ref_bad, d.max_span, d.max_back, prm.max_base_qs, lane);
+        const int pos = (int)gi + 1;
+        int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
+        if (oc.w >= kOpenSearch) {   // no range from the window kernel (test hook, or a very deep column)
+            i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+            i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
+        }
+        extract_column(R, cq, wr.tile, pos, ref, ref_bad, i_lo, i_hi, max_qs, s_kmin, may_skip, lane);
     }
 }
 
@@ -891,7 +957,7 @@ __global__ void __launch_bounds__(256) k_extract_columns(const TileDev* __restri
 // Restates CountsHelper.calculateCountsGTSNV / updateCounts (CH:86-95, 209-251) over the column's calls in pileup order,
 // then CH.getPosteriorProbabilities + VD.discoverSNV (col_finalize).  The 10 distinct log-likelihoods are summed in fp64
 // in the reference's own order from the host-supplied tables: logConditionalProbs are bit-identical to the Java doubles.
-__global__ void __launch_bounds__(128) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+__global__ void __launch_bounds__(64) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
     __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
@@ -1031,8 +1097,8 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
 }
 
 void launch_genotype(const TileDev* d_tiles, const WinRange* d_win, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
-    k_extract_columns<<<grid, 256, 0, s>>>(d_tiles, d_win, cq, dprm);
-    k_genotype_columns<<<grid, 128, 0, s>>>(d_tiles, cq, dprm);
+    k_extract_columns<<<grid * 4, 256, 0, s>>>(d_tiles, d_win, cq, dprm);   // one warp per open column, grid-stride
+    k_genotype_columns<<<grid, 64, 0, s>>>(d_tiles, cq, dprm);
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

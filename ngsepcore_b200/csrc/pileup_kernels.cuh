@@ -69,7 +69,8 @@ struct DevParams {
 struct ColumnHdr { int32_t tile; int32_t pos; uint32_t code_off; uint32_t n_codes; };   // n_codes: bits 0-27 count, 28-29 reference allele, 30 reference not ACGT
 struct ColumnQueue {
     ColumnHdr* cols; uint16_t* codes;
-    uint2* open;                             // open columns handed from k_pileup_windows to k_extract_columns: (window, position in window)
+    uint4* open;                             // open columns handed from k_pileup_windows to k_extract_columns:
+                                             // (window, position in window, first record, number of records | 0xffff = search)
     unsigned int* ctr;                       // [0] columns claimed, [1] code slots claimed, [2] open columns listed
     unsigned int cap_cols, cap_codes, cap_open;
 };
