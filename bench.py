@@ -105,6 +105,19 @@ class _ClockSampler:
         return out
 
 
+def reduce_over_ranks(dist, device, sums, maxima):
+    """Whole-job aggregates: units are SUMMED over ranks, times take the MAX over ranks (contract: value = units of all ranks /
+    max-over-ranks time).  dist is None for a single process."""
+    if dist is None:
+        return [float(x) for x in sums], [float(x) for x in maxima]
+    import torch
+    w = torch.tensor([float(x) for x in sums], dtype=torch.float64, device=device)
+    dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    v = torch.tensor([float(x) for x in maxima], dtype=torch.float64, device=device)
+    dist.all_reduce(v, op=dist.ReduceOp.MAX)
+    return [float(x) for x in w.tolist()], [float(x) for x in v.tolist()]
+
+
 def _dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,16 +228,8 @@ def run_gpu(args):
                     "pack_s": st2.pack_s, "device_s": st2.device_s, "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
                     "note": "whole detector from decoded records on 1 host thread: admission + realigner pre-pass + packing + device + VCF text"}
 
-    if dist is not None:
-        import torch
-        v = torch.tensor([total_ms, e2e_s, pileup_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(v, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, pileup_ms = [float(x) for x in v.tolist()]
-        w = torch.tensor([covered, aligned_bases, h2d_bytes, calls, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        covered_all, bases_all, h2d_all, calls_all, launches_all = [float(x) for x in w.tolist()]
-    else:
-        covered_all, bases_all, h2d_all, calls_all, launches_all = covered, aligned_bases, h2d_bytes, calls, launches
+    (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
+        dist, "cuda", sums=[covered, aligned_bases, h2d_bytes, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -236,7 +241,7 @@ def run_gpu(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "depth": args.depth, "genome_bp": genome_len, "reads": int(batch.n), "tiles": len(slots),
-                       "genotyped_positions_per_gpu": int(covered), "candidate_positions": int(cand), "calls": int(calls),
+                       "genotyped_positions_per_gpu": int(covered), "candidate_positions": int(cand), "open_columns": int(st.open_columns), "calls": int(calls),
                        "l2": "inputs larger than L2 (%.0f MB of tile payload read per step)" % (h2d_bytes / 1e6),
                        "parallelism": f"region shards x{world}, no collective"},
             "aligned_bases_per_sec": bases_all / (ms_per_step / 1e3),

@@ -131,6 +131,7 @@ typedef struct ngsep_tile_stats {
                                     a batched run reports the whole batch's launch for every tile in it)  */
     float pileup_ms;             /* of which: the window kernel (k_pileup_windows)                        */
     uint32_t kernel_launches;    /* kernels launched for the tile                                        */
+    uint32_t open_columns;       /* positions the window kernel left to k_genotype_columns (whole launch) */
 } ngsep_tile_stats;
 
 /* Context = one GPU + one stream + device-resident reference.  Replaces the construction of

@@ -85,16 +85,15 @@ struct Ctx {
     DevBuf<TileDev> d_btiles;
     DevBuf<WinRange> d_bwin;
     // column queue shared by every launch of this context (launches are stream-ordered)
-    DevBuf<ColumnHdr> d_cols;
-    DevBuf<uint16_t> d_codes;
     DevBuf<uint4> d_open;
-    size_t q_min_cols = 0, q_min_codes = 0;   // learned from overflows
+    size_t q_min_cols = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
     LaunchCfg cfg{512, 7424u, 1, 4, 256};
     size_t smem = 0;
     int ctas_per_sm = 1;
+    int geno_grid = 0;                        // blocks of k_genotype_columns
     std::string err;
 };
 
@@ -129,40 +128,34 @@ int clear_counts_dbg(Ctx* c, Slot* s) {
     return NGSEP_OK;
 }
 
-// Column-queue capacity a tile asks for: a small fraction of the positions reaches the genotype kernel (every position
-// with the EMIT_ALL test hook).  Overflow is detected after the run: the queue grows and the run is repeated.
-void queue_need(const Ctx* c, const Slot* s, size_t& cols, size_t& codes) {
+// Open-column capacity a tile asks for: a small fraction of the positions stays open after the window kernel (every
+// position with the EMIT_ALL test hook).  Overflow is detected after the run: the list grows and the run is repeated.
+void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
     const size_t len = (size_t)(s->tile.tile_last - s->tile.tile_first + 1);
-    if (c->params.flags & NGSEP_F_EMIT_ALL) { cols += len + 1024; codes += 2 * (size_t)s->aligned_bases + 8 * len + 65536; }
-    else { cols += len / 32 + 16384; codes += (len / 32 + 16384) * 48; }
+    if (c->params.flags & NGSEP_F_EMIT_ALL) cols += len + 1024;
+    else cols += len / 32 + 16384;
 }
 
-int ensure_queue(Ctx* c, size_t cols, size_t codes) {
-    cols = std::max(cols, c->q_min_cols); codes = std::max(codes, c->q_min_codes);
-    if (codes > 0xfffffff0ull || cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "column queue too large (split the tile)");
-    CK(c->d_cols.reserve(cols), "column queue alloc");
-    CK(c->d_open.reserve(cols), "column queue alloc");
-    CK(c->d_codes.reserve(codes), "column queue alloc");
+int ensure_queue(Ctx* c, size_t cols) {
+    cols = std::max(cols, c->q_min_cols);
+    if (cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "open-column list too large (split the tile)");
+    CK(c->d_open.reserve(cols), "open-column list alloc");
     return NGSEP_OK;
 }
 
 ColumnQueue queue_view(Ctx* c) {
     ColumnQueue q;
-    q.cols = c->d_cols.p; q.codes = c->d_codes.p; q.open = c->d_open.p; q.ctr = (unsigned int*)c->d_meta;
-    q.cap_open = (unsigned int)c->d_open.cap;
-    q.cap_cols = (unsigned int)c->d_cols.cap; q.cap_codes = (unsigned int)std::min<size_t>(c->d_codes.cap, 0xfffffff0ull);
+    q.open = c->d_open.p; q.ctr = (unsigned int*)c->d_meta; q.cap_open = (unsigned int)c->d_open.cap;
     return q;
 }
 
-// After a run: did the column queue overflow?  (stream must be idle)  Returns 1 when it grew and the run must be repeated.
+// After a run: did the open-column list overflow?  (stream must be idle)  grew = 1: it was enlarged, repeat the run.
 int queue_overflowed(Ctx* c, int* grew) {
     unsigned int ctr[3] = {0, 0, 0};
     CK(cudaMemcpy(ctr, c->d_meta, sizeof(ctr), cudaMemcpyDeviceToHost), "queue counters copy");
     *grew = 0;
-    if (ctr[0] > c->d_cols.cap || ctr[1] > c->d_codes.cap || ctr[2] > c->d_open.cap) {
-        const unsigned int nc = std::max(ctr[0], ctr[2]);
-        c->q_min_cols = std::max(c->q_min_cols, (size_t)nc + (size_t)nc / 4 + 1024);
-        c->q_min_codes = std::max(c->q_min_codes, (size_t)ctr[1] + (size_t)ctr[1] / 4 + 65536);
+    if (ctr[2] > c->d_open.cap) {
+        c->q_min_cols = std::max(c->q_min_cols, (size_t)ctr[2] + (size_t)ctr[2] / 4 + 1024);
         *grew = 1;
     }
     return NGSEP_OK;
@@ -171,9 +164,9 @@ int queue_overflowed(Ctx* c, int* grew) {
 // one tile: pileup kernel + genotype kernel
 int launch_slot(Ctx* c, Slot* s) {
     if (!s->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
-    size_t cols = 0, codes = 0;
-    queue_need(c, s, cols, codes);
-    int rc = ensure_queue(c, cols, codes);
+    size_t cols = 0;
+    queue_need(c, s, cols);
+    int rc = ensure_queue(c, cols);
     if (rc != NGSEP_OK) return rc;
     CK(cudaMemsetAsync(c->d_meta, 0, kMetaStride, c->stream), "memset queue counters");
     CK(cudaMemsetAsync(s->d_counters, 0, kMetaStride, c->stream), "memset counters");
@@ -183,7 +176,7 @@ int launch_slot(Ctx* c, Slot* s) {
     CK(cudaEventRecord(s->e0, c->stream), "event record");
     if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
-    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, s->d_win.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream); s->launches = 3; }
+    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream); s->launches = 2; }
     CK(cudaEventRecord(s->e1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     s->launched = true;
@@ -215,16 +208,16 @@ int launch_batch(Ctx* c) {
         c->b_grid = (int)std::min<size_t>(n_win, (size_t)c->sm_count * (size_t)c->ctas_per_sm);
         c->batch_dirty = false;
     }
-    size_t cols = 0, codes = 0;
-    for (size_t i = 1; i < n; i++) queue_need(c, c->slots[i], cols, codes);
-    int rc = ensure_queue(c, cols, codes);
+    size_t cols = 0;
+    for (size_t i = 1; i < n; i++) queue_need(c, c->slots[i], cols);
+    int rc = ensure_queue(c, cols);
     if (rc != NGSEP_OK) return rc;
     CK(cudaMemsetAsync(c->d_meta, 0, (1 + n) * kMetaStride, c->stream), "memset counters");   // queue + every slot: ONE memset
     for (size_t i = 1; i < n; i++) { rc = clear_counts_dbg(c, c->slots[i]); if (rc != NGSEP_OK) return rc; }
     CK(cudaEventRecord(c->b0, c->stream), "event record");
     if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, queue_view(c), c->cfg, c->b_grid, c->smem, c->stream);
     CK(cudaEventRecord(c->bm, c->stream), "event record");
-    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, c->d_bwin.p, queue_view(c), c->d_prm, c->sm_count * 4, c->stream);
+    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
     CK(cudaEventRecord(c->b1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
@@ -341,6 +334,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         stats->kernel_ms = ms;
         stats->pileup_ms = pms;
         stats->kernel_launches = s->launches;
+        { unsigned int qc[3] = {0, 0, 0}; CK(cudaMemcpy(qc, c->d_meta, sizeof(qc), cudaMemcpyDeviceToHost), "queue counters copy"); stats->open_columns = qc[2]; }
     }
     *n_out = n;
     if (n > cap) return fail(c, NGSEP_EOVERFLOW, "caller's call buffer is too small; n_out holds the required capacity");
@@ -407,6 +401,8 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.threads, c->cfg.min_blocks);
     if (c->ctas_per_sm < 1) { g_global_err = "the pileup kernel cannot be made resident with this configuration"; delete c; return NGSEP_ECUDA; }
     if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
+    c->geno_grid = c->sm_count * 16;
+    if (const char* s = std::getenv("NGSEP_GENO_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 256) c->geno_grid = c->sm_count * v; }
     Slot* s0 = nullptr;
     if (new_slot(c, &s0) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }
     c->slots.push_back(s0);
@@ -454,7 +450,7 @@ int ngsep_ctx_destroy(void* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& r : c->refs) r.release();
     for (Slot* s : c->slots) { s->release(); delete s; }
-    c->d_btiles.release(); c->d_bwin.release(); c->d_cols.release(); c->d_codes.release();
+    c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -581,7 +577,8 @@ int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats) {
     CK(cudaEventElapsedTime(&pms, c->b0, c->bm), "event elapsed");
     stats->kernel_ms = ms;
     stats->pileup_ms = pms;
-    stats->kernel_launches = c->b_windows > 0 ? 3u : 0u;
+    stats->kernel_launches = c->b_windows > 0 ? 2u : 0u;
+    stats->open_columns = *(const unsigned int*)(meta.data() + 8);
     return NGSEP_OK;
 }
 

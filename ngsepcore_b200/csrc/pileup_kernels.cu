@@ -332,16 +332,30 @@ __device__ __forceinline__ int resolve_offset(const RecView& r, int ign_s, int i
 constexpr uint32_t kCodeNeg = 1u << 7, kCodeCounted = 1u << 8, kCodeCall = 1u << 9;
 
 __device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, int pos, int max_qs) {
-    const RecView r = view_record(h, pay);
-    const int off = resolve_offset(r, h.ign_start, h.ign_end, pos);
-    if (off < 0) return 0u;
-    int q = (int)r.q[off] - 33;
+    uint32_t qc, bw;
+    int off;
+    if (h.meta & NGSEP_M_SIMPLE) {
+        // one match block as long as the read: the offset needs no payload (RA:842-871), quality and bases load together
+        const int L = (int)(h.meta & 0xffffu);
+        off = pos - h.first;
+        if (off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0u;   // RA:782-784
+        const uint32_t* b2 = pay + 1;
+        qc = ((const uint8_t*)(b2 + ((L + 15) >> 4)))[off];
+        bw = b2[off >> 4];
+    } else {
+        const RecView r = view_record(h, pay);
+        off = resolve_offset(r, h.ign_start, h.ign_end, pos);
+        if (off < 0) return 0u;
+        qc = r.q[off];
+        bw = r.b2[off >> 4];
+        if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) qc = 0u;   // allele not in ACGT: a call that is not counted (CH:220-221)
+    }
+    int q = (int)qc - 33;
     q = min(30, q);                                   // CH:91
-    if (q <= 3) return kCodeCall;                     // CH:214-216
+    if (q <= 3) return kCodeCall;                     // CH:214-216 (and the N case above)
     if (q > max_qs) q = max_qs;                       // CH:217-219
-    if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) return kCodeCall;  // allele not in ACGT: CH:220-221
-    const uint32_t b = (r.b2[off >> 4] >> ((off & 15) * 2)) & 3u;
-    return kCodeCall | kCodeCounted | b | ((uint32_t)q << 2) | ((r.meta & NGSEP_M_NEG) ? kCodeNeg : 0u);
+    const uint32_t b = (bw >> ((off & 15) * 2)) & 3u;
+    return kCodeCall | kCodeCounted | b | ((uint32_t)q << 2) | ((h.meta & NGSEP_M_NEG) ? kCodeNeg : 0u);
 }
 
 __device__ __forceinline__ int dev_phred(double p) {  // math/PhredScoreHelper.java:31-40
@@ -355,78 +369,51 @@ __device__ __forceinline__ int dev_phred(double p) {  // math/PhredScoreHelper.j
 constexpr unsigned kFull = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------------------
-// SNVQ genotyping of one column (thread-serial; used by k_genotype_columns)
+// SNVQ genotyping of one column, one warp per column (used by k_genotype_columns)
 // ------------------------------------------------------------------------------------------------------------
-struct ColState {
-    int c0, c1, c2, c3, depth;
-    int sn0, sn1, sn2, sn3;                      // negative-strand count per allele
-    double d0, d1, d2, d3, o01, o02, o03, o12, o13, o23;
-};
+// index of the ordered event (i,j) in CH.getPosteriorProbabilities' enumeration (CH:416-430): per first allele i, the
+// homozygous event, then the heterozygous ones with j ascending
+__device__ __forceinline__ int ev_index(int i, int j) { return i * 4 + ((i == j) ? 0 : ((j < i) ? j + 1 : j)); }
 
-// CH.updateCounts for one counted call (CH:223-249 with f == g == 250: L is symmetric, 10 distinct sums)
-__device__ __forceinline__ void col_add(ColState& s, int b, int q, bool neg, const double* s_tab) {
-    s.c0 += (b == 0); s.c1 += (b == 1); s.c2 += (b == 2); s.c3 += (b == 3);
-    s.sn0 += (neg && b == 0); s.sn1 += (neg && b == 1); s.sn2 += (neg && b == 2); s.sn3 += (neg && b == 3);
-    const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
-    s.d0 += (b == 0) ? ta : tb;
-    s.d1 += (b == 1) ? ta : tb;
-    s.d2 += (b == 2) ? ta : tb;
-    s.d3 += (b == 3) ? ta : tb;
-    s.o01 += (b == 0 || b == 1) ? tc : tb;
-    s.o02 += (b == 0 || b == 2) ? tc : tb;
-    s.o03 += (b == 0 || b == 3) ? tc : tb;
-    s.o12 += (b == 1 || b == 2) ? tc : tb;
-    s.o13 += (b == 1 || b == 3) ? tc : tb;
-    s.o23 += (b == 2 || b == 3) ? tc : tb;
-}
+struct ColCounts { int c[4], sn[4], depth; };
 
-// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223
-__device__ void col_finalize(const ColState& s, int pos, int ref, const TileDev& d, const DevParams& prm, const double* s_tab) {
-    double Lm[16];
-    Lm[0] = s.d0; Lm[5] = s.d1; Lm[10] = s.d2; Lm[15] = s.d3;
-    Lm[1] = Lm[4] = s.o01; Lm[2] = Lm[8] = s.o02; Lm[3] = Lm[12] = s.o03;
-    Lm[6] = Lm[9] = s.o12; Lm[7] = Lm[13] = s.o13; Lm[11] = Lm[14] = s.o23;
-    const double lp_hom = s_tab[93], lp_het = s_tab[94];
-    double ev[16];
-    {
-        int k = 0;
-        for (int i = 0; i < 4; i++) {
-            ev[k++] = Lm[i * 5] + lp_hom;
-            for (int j = 0; j < 4; j++) if (i != j) ev[k++] = Lm[i * 4 + j] + lp_het;
-        }
-    }
-    double log_max = 1.0;  // CH:474-479, quirk kept: starts at 1 and is replaced by the first event
-    for (int k = 0; k < 16; k++) if (log_max > 0.0 || log_max < ev[k]) log_max = ev[k];
+// CH.getPosteriorProbabilities (CH:410-495) + VD.discoverSNV (VD:100-222) + the filter of SSVPL:223.
+// `acc` is lane-owned: lanes 0-3 hold L[i][i], lanes 4-9 hold L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3];
+// the 16 ordered events live on lanes 0-15 (lanes 16-31 mirror them).
+__device__ __forceinline__ void finalize_warp(double acc, const ColCounts& cc, int lane, int pos, int ref, const TileDev& d, int min_quality,
+                                              double lp_hom, double lp_het) {
+    const int k = lane & 15;
+    const int i = k >> 2, r = k & 3;
+    const int j = (r == 0) ? i : ((r - 1 < i) ? r - 1 : r);
+    const int lo = min(i, j), hi = max(i, j);
+    const int owner = (i == j) ? i : ((lo == 0) ? 3 + hi : ((lo == 1) ? 5 + hi : 9));
+    const double Lij = __shfl_sync(kFull, acc, owner);
+    const double ev = Lij + ((i == j) ? lp_hom : lp_het);
+    double mx = ev;   // CH:474-479: the quirk "starts at 1 and is replaced by the first event" reduces to the maximum
+    for (int o = 8; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(kFull, mx, o));
+    double e = ev - mx;
+    e = (e < -20.0) ? 0.0 : exp10(e);
     double total = 0.0;
-    for (int k = 0; k < 16; k++) {
-        double e = ev[k] - log_max;
-        e = (e < -20.0) ? 0.0 : exp10(e);
-        ev[k] = e;
-        total += e;
-    }
-    double post[16];
-    {
-        int k = 0;
-        for (int i = 0; i < 4; i++) {
-            post[i * 5] = ev[k++] / total;
-            for (int j = 0; j < 4; j++) if (i != j) post[i * 4 + j] = ev[k++] / total;
-        }
-    }
-    // VD.getIndexesMaxGenotype (VD:223-243)
+    for (int t = 0; t < 16; t++) total += __shfl_sync(kFull, e, t);   // CH:480-486, same order
+    const double post = e / total;
+    // VD.getIndexesMaxGenotype (VD:223-243), every lane redundantly
+    const double p_ref = __shfl_sync(kFull, post, ev_index(ref, ref));
     int ii = ref, jj = ref;
-    double pmax = post[ref * 5];
-    for (int i = 0; i < 4; i++) for (int j = i; j < 4; j++) {
-        double gp = post[i * 4 + j];
-        if (i != j) gp += post[j * 4 + i];
-        if (gp > pmax + 0.01) { pmax = gp; ii = i; jj = j; }
-    }
-    double max_p = post[ii * 4 + jj];
-    if (ii != jj) max_p += post[jj * 4 + ii];
-    int gq = dev_phred(1.0 - max_p);
+    double pmax = p_ref;
+    for (int a = 0; a < 4; a++)
+        for (int b = a; b < 4; b++) {
+            double gp = __shfl_sync(kFull, post, ev_index(a, b));
+            if (a != b) gp += __shfl_sync(kFull, post, ev_index(b, a));
+            if (gp > pmax + 0.01) { pmax = gp; ii = a; jj = b; }
+        }
+    double max_p = __shfl_sync(kFull, post, ev_index(ii, jj));
+    if (ii != jj) max_p += __shfl_sync(kFull, post, ev_index(jj, ii));
+    const double p_ii = __shfl_sync(kFull, post, ev_index(ii, ii));
+    const double p_jj = __shfl_sync(kFull, post, ev_index(jj, jj));
     int kind, a0, a1;
     if (ii != jj && ii != ref && jj != ref) {  // VD:128-177
         kind = NGSEP_CALL_TRIALLELIC;
-        if (post[ii * 5] > post[jj * 5] + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
+        if (p_ii > p_jj + 0.01) { a0 = ii; a1 = jj; } else { a0 = jj; a1 = ii; }
     } else if (ii != jj) {
         kind = NGSEP_CALL_HET; a0 = ref; a1 = (ref != ii) ? ii : jj;
     } else if (ii != ref) {
@@ -434,22 +421,28 @@ __device__ void col_finalize(const ColState& s, int pos, int ref, const TileDev&
     } else {
         return;  // homozygous reference: dropped by SSVPL:223
     }
-    if (prm.min_quality > gq) return;  // SSVPL:223
-    unsigned int slot = atomicAdd(d.n_calls, 1u);
+    const int gq = dev_phred(1.0 - max_p);
+    if (min_quality > gq) return;  // SSVPL:223
+    unsigned int slot = 0;
+    if (lane == 0) slot = atomicAdd(d.n_calls, 1u);
+    slot = __shfl_sync(kFull, slot, 0);
     if (slot >= d.cap_calls) return;   // host sees n_calls > cap, grows the buffer and reruns
     ngsep_snv_call* o = &d.calls[slot];
-    o->seq_idx = d.seq_idx; o->pos = pos;
-    o->count[0] = s.c0; o->count[1] = s.c1; o->count[2] = s.c2; o->count[3] = s.c3;
-    o->depth = s.depth;
-    o->strand[0] = s.sn0; o->strand[1] = s.c0 - s.sn0; o->strand[2] = s.sn1; o->strand[3] = s.c1 - s.sn1;
-    o->strand[4] = s.sn2; o->strand[5] = s.c2 - s.sn2; o->strand[6] = s.sn3; o->strand[7] = s.c3 - s.sn3;
-    for (int k = 0; k < 16; k++) o->logcond[k] = Lm[k];
-    o->post_ref = post[ref * 5];
-    o->post_max = max_p;
-    o->gq = (int16_t)gq;
-    o->qual = (int16_t)dev_phred(post[ref * 5]);
-    o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
-    o->sample = 0;
+    if (lane < 16) o->logcond[i * 4 + j] = Lij;
+    if (lane == 16) {
+        o->seq_idx = d.seq_idx; o->pos = pos;
+        o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
+        o->depth = cc.depth;
+        for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
+    }
+    if (lane == 17) {
+        o->post_ref = p_ref;
+        o->post_max = max_p;
+        o->gq = (int16_t)gq;
+        o->qual = (int16_t)dev_phred(p_ref);
+        o->a0 = (int8_t)a0; o->a1 = (int8_t)a1; o->ref = (int8_t)ref; o->kind = (int8_t)kind;
+        o->sample = 0;
+    }
 }
 
 // Records of the window as the exact phase sees them: the staged copy in shared memory, or (windows too deep to stage
@@ -494,7 +487,7 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
 }
 
 struct ExactCtx {
-    int wbeg, n_cand, max_span, max_back, tile;
+    int wbeg, n_cand, max_span, max_back, tile, rec0;   // rec0: index in the tile of the window's first record
     const uint32_t* s_list;
     uint32_t* s_cnt;
     const uint32_t *s_ref2, *s_refn, *s_refl;
@@ -515,71 +508,90 @@ __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx,
     return (q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
 }
 
-// Column extraction (warp-cooperative): every record of [i_lo, i_hi) in pileup order, one record per lane and round,
-// restating PR.getAlleleCalls(1).  The calls (allele, quality, strand, counted) are appended to the column queue in that
-// order; k_genotype_columns turns them into counts, log-likelihoods and the genotype.  Columns of up to 128 records are
-// first counted (ballots) and dropped when the exact counts prove the homozygous-reference call.
+// The exact column (warp-cooperative, records through L2): every record of [i_lo, i_hi) in pileup order, one record per
+// lane and round.  lane_eval restates PR.getAlleleCalls(1) + the quality rules of CH.updateCounts; ballots give the exact
+// counts[4], countsStrand[4][2] and totalCount; columns whose exact counts prove the homozygous-reference call are
+// dropped; the others get the 10 distinct log-likelihoods, one per lane, SUMMED IN PILEUP ORDER in fp64
+// (CH:231-249) from the host-supplied tables — bit-identical to the Java doubles — and finalize_warp.
 constexpr int kRegRounds = 4;
-__device__ __forceinline__ void extract_column(const Recs<true>& R, const ColumnQueue& cq, int tile, int pos, uint32_t ref, uint32_t ref_bad,
-                                               int i_lo, int i_hi, int max_qs, const int* s_kmin, bool may_skip, int lane) {
-    const int n_max = i_hi - i_lo;
-    if (n_max <= 0) return;
+struct GenoCtx { const double* s_tab; const int* s_kmin; int max_qs, min_quality; bool may_skip, emit_all; };
+
+__device__ __forceinline__ void count_round(uint32_t code, ColCounts& cc) {
+    cc.depth += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));   // CH:210 totalCount: every call, whatever its quality or base
+    const unsigned ng = __ballot_sync(kFull, (code & kCodeNeg) != 0u);
+    const bool counted = (code & kCodeCounted) != 0u;
+    for (int b = 0; b < 4; b++) {
+        const unsigned mb = __ballot_sync(kFull, counted && (int)(code & 3u) == b);
+        cc.c[b] += __popc(mb);
+        cc.sn[b] += __popc(mb & ng);
+    }
+}
+__device__ __forceinline__ void accumulate_round(uint32_t code, double& acc, int lane, int pa, int pb, const double* s_tab) {
+    unsigned cm = __ballot_sync(kFull, (code & kCodeCounted) != 0u);
+    while (cm) {
+        const int src = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const uint32_t cj = __shfl_sync(kFull, code, src);
+        const int b = (int)(cj & 3u), q = (int)((cj >> 2) & 31u);
+        const double tb = s_tab[3 * q + 1];
+        const double tx = (lane < 4) ? s_tab[3 * q] : s_tab[3 * q + 2];
+        acc += (b == pa || b == pb) ? tx : tb;
+    }
+}
+
+__device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev& d, const GenoCtx& g, int pos, int ref, bool ref_bad,
+                                             int i_lo, int i_hi, int lane) {
+    // lanes 0-3 own L[i][i]; lanes 4-9 own L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3]
+    const int pa = (lane < 4) ? lane : ((lane < 7) ? 0 : ((lane < 9) ? 1 : 2));
+    const int pb = (lane < 4) ? lane : ((lane < 7) ? lane - 3 : ((lane < 9) ? lane - 5 : 3));
+    double acc = 0.0;
+    ColCounts cc;
+    for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
+    cc.depth = 0;
+    const bool in_regs = (i_hi - i_lo) <= 32 * kRegRounds;
     uint32_t codes[kRegRounds];
-    const bool in_regs = n_max <= 32 * kRegRounds;
-    unsigned int n_calls = 0;
     if (in_regs) {
-        int c_ref = 0, c_all = 0;
+        // all the loads of the column are issued before the first ballot: headers, then quality + bases of every round
+        ngsep_read_hdr hs[kRegRounds];
 #pragma unroll
         for (int r = 0; r < kRegRounds; r++) {
             const int idx = i_lo + 32 * r + lane;
-            uint32_t code = 0u;
-            if (idx < i_hi) {
-                const ngsep_read_hdr h = R.header(idx);
-                code = lane_eval(h, R.payload(h), pos, max_qs);
-            }
-            codes[r] = code;
-            const bool counted = (code & kCodeCounted) != 0u;
-            n_calls += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));
-            c_all += __popc(__ballot_sync(kFull, counted));
-            c_ref += __popc(__ballot_sync(kFull, counted && (code & 3u) == ref));
+            hs[r].meta = 0u; hs[r].first = 0; hs[r].ign_start = hs[r].ign_end = 0; hs[r].off = 0u;
+            if (idx < i_hi) hs[r] = R.header(idx);
         }
-        if (n_calls == 0 && may_skip) return;                           // empty column: nothing to call (VD:101)
-        const int m_alt = c_all - c_ref;
-        if (may_skip && !ref_bad && (m_alt == 0 || (m_alt < kSkipTable && c_ref >= s_kmin[m_alt]))) return;   // proven hom-ref
-    }
-    unsigned int col = 0, off = 0;
-    const unsigned int n_alloc = in_regs ? n_calls : (unsigned int)n_max;
-    if (lane == 0) { col = atomicAdd(&cq.ctr[0], 1u); off = atomicAdd(&cq.ctr[1], n_alloc); }
-    col = __shfl_sync(kFull, col, 0);
-    off = __shfl_sync(kFull, off, 0);
-    const bool room = col < cq.cap_cols && (uint64_t)off + (uint64_t)n_alloc <= (uint64_t)cq.cap_codes;   // else: host grows + reruns
-    unsigned int n = 0;
-    if (in_regs) {
 #pragma unroll
-        for (int r = 0; r < kRegRounds; r++) {
-            const uint32_t code = codes[r];
-            const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
-            if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
-            n += __popc(cm);
-        }
+        for (int r = 0; r < kRegRounds; r++)
+            codes[r] = (i_lo + 32 * r + lane < i_hi) ? lane_eval(hs[r], R.payload(hs[r]), pos, g.max_qs) : 0u;
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) count_round(codes[r], cc);
     } else {
-        for (int base = i_lo; base < i_hi; base += 32) {
+        for (int base = i_lo; base < i_hi; base += 32) {   // deep column: count and sum on the fly
             const int idx = base + lane;
             uint32_t code = 0u;
             if (idx < i_hi) {
                 const ngsep_read_hdr h = R.header(idx);
-                code = lane_eval(h, R.payload(h), pos, max_qs);
+                code = lane_eval(h, R.payload(h), pos, g.max_qs);
             }
-            const unsigned cm = __ballot_sync(kFull, (code & kCodeCall) != 0u);
-            if ((code & kCodeCall) && room) cq.codes[off + n + __popc(cm & ((1u << lane) - 1u))] = (uint16_t)code;
-            n += __popc(cm);
+            count_round(code, cc);
+            accumulate_round(code, acc, lane, pa, pb, g.s_tab);
         }
     }
-    if (lane == 0 && room) {
-        ColumnHdr ch;
-        ch.tile = tile; ch.pos = pos; ch.code_off = off; ch.n_codes = n | (ref << 28) | (ref_bad << 30);
-        cq.cols[col] = ch;
+    if (g.emit_all && d.counts_dbg && lane == 0) {
+        int32_t* o = d.counts_dbg + (int64_t)(pos - d.tile_first) * 5;
+        o[0] = cc.c[0]; o[1] = cc.c[1]; o[2] = cc.c[2]; o[3] = cc.c[3]; o[4] = cc.depth;
     }
+    if (ref_bad || cc.depth == 0) return;   // VD:101-107
+    const int tot = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
+    const int k_ref = (ref == 0) ? cc.c[0] : ((ref == 1) ? cc.c[1] : ((ref == 2) ? cc.c[2] : cc.c[3]));
+    const int m_alt = tot - k_ref;
+    // Proven hom-ref with the exact counts: VD.discoverSNV returns the homozygous-reference call that
+    // SSVPL:223 drops.
+    if (g.may_skip && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= g.s_kmin[m_alt]))) return;
+    if (in_regs) {
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) accumulate_round(codes[r], acc, lane, pa, pb, g.s_tab);
+    }
+    finalize_warp(acc, cc, lane, pos, ref, d, g.min_quality, g.s_tab[93], g.s_tab[94]);
 }
 
 // Phase C.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
@@ -632,10 +644,10 @@ __device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactC
             if (lane == 0 && i_hi > i_lo) {
                 const uint32_t n_range = (uint32_t)min(i_hi - i_lo, (int)kOpenSearch);
                 const int slot = atomicAdd(n_open, 1);
-                if (slot < kMaxOpen) s_open[slot] = make_uint2((uint32_t)e_li | (n_range << 16), (uint32_t)i_lo);
+                if (slot < kMaxOpen) s_open[slot] = make_uint2((uint32_t)e_li | (n_range << 16), (uint32_t)(x.rec0 + i_lo));
                 else {   // rare: the window's list is full
                     const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
-                    if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)w_idx, (unsigned int)e_li, (unsigned int)i_lo, n_range);
+                    if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)x.tile, (unsigned int)e_pos, (unsigned int)(x.rec0 + i_lo), n_range);
                 }
             }
         }
@@ -744,8 +756,9 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         const uint32_t* s_pay = (const uint32_t*)(stg + lay.o_pay);
         int* mset = s_misc + (it & 1) * kMiscSet;
 
-        mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);
+        if (warp == 0) mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);   // one warp polls; the others park in the barrier
         phase_bits ^= 1u << cur;
+        __syncthreads();
 
         const WinRange wr = *(const WinRange*)(stg + lay.o_win);
         const int wbeg = wr.wbeg, g_lo = wr.wbeg + (int)(wr.g_pack & 0xffffu), g_hi = wr.wbeg + (int)(wr.g_pack >> 16);
@@ -849,10 +862,10 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             __syncthreads();
             const unsigned int gbase = (unsigned int)mset[M_R1];
             for (int i = tid; i < n_all; i += nthr)
-                if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)w, (unsigned int)(g_lo - wbeg + i), 0u, kOpenSearch);
+                if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)wr.tile, (unsigned int)(g_lo + i + 1), 0u, kOpenSearch);
         } else if (n_cand > 0) {
             ExactCtx x;
-            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile;
+            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile; x.rec0 = wr.lo;
             x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
             x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
             x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
@@ -876,7 +889,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 gbase = __shfl_sync(kFull, gbase, 0);
                 for (int i = lane; i < n_open; i += 32) {
                     const uint2 oe = s_open[i];
-                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)w, oe.x & 0xffffu, oe.y, oe.x >> 16);
+                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)wr.tile, (unsigned int)(wbeg + (int)(oe.x & 0xffffu) + 1), oe.y, oe.x >> 16);
                 }
             }
         }
@@ -918,82 +931,38 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// extraction of the open columns: one warp per column, records read through L2
+// SNVQ genotyping of the open columns: one warp per column, records read through L2
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_extract_columns(const TileDev* __restrict__ tiles, const WinRange* __restrict__ win, const ColumnQueue cq,
-                                                         const DevParams* __restrict__ gprm) {
-    __shared__ int s_kmin[kSkipTable];
-    const DevParams& prm = *gprm;
-    if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
-    __syncthreads();
-    const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
-    const bool may_skip = prm.fast_homref && !(prm.flags & NGSEP_F_EMIT_ALL);
-    const int max_qs = prm.max_base_qs;
-    const int lane = threadIdx.x & 31;
-    const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
-    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
-        const uint4 oc = cq.open[t];
-        const WinRange wr = win[oc.x];
-        const TileDev& d = tiles[wr.tile];
-        const int64_t gi = (int64_t)wr.wbeg + (int64_t)oc.y;   // 0-based index of the position
-        if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198: no discovery at all
-        const uint32_t ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
-        const uint32_t ref = (d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u;
-        Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = wr.hi - wr.lo;
-        const int pos = (int)gi + 1;
-        int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
-        if (oc.w >= kOpenSearch) {   // no range from the window kernel (test hook, or a very deep column)
-            i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
-            i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
-        }
-        extract_column(R, cq, wr.tile, pos, ref, ref_bad, i_lo, i_hi, max_qs, s_kmin, may_skip, lane);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// SNVQ genotyping of the queued columns: one thread per column
-// ------------------------------------------------------------------------------------------------------------
-// Restates CountsHelper.calculateCountsGTSNV / updateCounts (CH:86-95, 209-251) over the column's calls in pileup order,
-// then CH.getPosteriorProbabilities + VD.discoverSNV (col_finalize).  The 10 distinct log-likelihoods are summed in fp64
-// in the reference's own order from the host-supplied tables: logConditionalProbs are bit-identical to the Java doubles.
-__global__ void __launch_bounds__(64) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+__global__ void __launch_bounds__(256, 6) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
     __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
     for (int i = threadIdx.x; i < NGSEP_N_TABLES; i += blockDim.x) s_tab[i] = prm.tables[i];
     if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
     __syncthreads();
-    const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
-    const unsigned int n_cols = min(cq.ctr[0], cq.cap_cols);
-    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_cols; t += gridDim.x * blockDim.x) {
-        const ColumnHdr ch = cq.cols[t];
-        const unsigned int n = ch.n_codes & 0x0fffffffu;
-        const int ref = (int)((ch.n_codes >> 28) & 3u);
-        const bool ref_bad = (ch.n_codes >> 30) & 1u;
-        const TileDev& d = tiles[ch.tile];
-        const uint16_t* codes = cq.codes + ch.code_off;
-        ColState cs;
-        cs.c0 = cs.c1 = cs.c2 = cs.c3 = cs.depth = 0;
-        cs.sn0 = cs.sn1 = cs.sn2 = cs.sn3 = 0;
-        cs.d0 = cs.d1 = cs.d2 = cs.d3 = cs.o01 = cs.o02 = cs.o03 = cs.o12 = cs.o13 = cs.o23 = 0.0;
-        for (unsigned int i = 0; i < n; i++) {
-            const uint32_t code = codes[i];
-            cs.depth++;   // CH:210 totalCount counts every call returned by getAlleleCalls(1), whatever its quality or base
-            if (code & kCodeCounted) col_add(cs, (int)(code & 3u), (int)((code >> 2) & 31u), (code & kCodeNeg) != 0u, s_tab);
+    const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    GenoCtx g;
+    g.s_tab = s_tab; g.s_kmin = s_kmin; g.max_qs = prm.max_base_qs; g.min_quality = prm.min_quality;
+    g.emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
+    g.may_skip = prm.fast_homref != 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
+        const uint4 oc = cq.open[t];   // tile, position, first record, number of records
+        const TileDev& d = tiles[oc.x];
+        const int pos = (int)oc.y;
+        const int64_t gi = (int64_t)pos - 1;
+        if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198: no discovery at all
+        const bool ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
+        const int ref = (int)((d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u);
+        Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
+        if (oc.w >= kOpenSearch) {   // no range from the window kernel (test hook, or a very deep column)
+            i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+            i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);   // first record that starts too far to the right
         }
-        if (emit_all && d.counts_dbg) {
-            int32_t* o = d.counts_dbg + (int64_t)(ch.pos - d.tile_first) * 5;
-            o[0] = cs.c0; o[1] = cs.c1; o[2] = cs.c2; o[3] = cs.c3; o[4] = cs.depth;
-        }
-        if (ref_bad || cs.depth == 0) continue;   // VD:101-107
-        const int tot = cs.c0 + cs.c1 + cs.c2 + cs.c3;
-        const int k_ref = (ref == 0) ? cs.c0 : ((ref == 1) ? cs.c1 : ((ref == 2) ? cs.c2 : cs.c3));
-        const int m_alt = tot - k_ref;
-        // Proven hom-ref with the exact counts: VD.discoverSNV returns the homozygous-reference call that
-        // SSVPL:223 drops.
-        if (prm.fast_homref && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= s_kmin[m_alt]))) continue;
-        col_finalize(cs, ch.pos, ref, d, prm, s_tab);
+        exact_column(R, d, g, pos, ref, ref_bad, i_lo, i_hi, lane);
     }
 }
 
@@ -1096,9 +1065,8 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
     kernel_for(cfg.threads, cfg.min_blocks)<<<grid, cfg.threads, smem, s>>>(a);   // grid = min(windows, resident CTAs): persistent CTAs
 }
 
-void launch_genotype(const TileDev* d_tiles, const WinRange* d_win, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
-    k_extract_columns<<<grid * 4, 256, 0, s>>>(d_tiles, d_win, cq, dprm);   // one warp per open column, grid-stride
-    k_genotype_columns<<<grid, 64, 0, s>>>(d_tiles, cq, dprm);
+void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+    k_genotype_columns<<<grid, 256, 0, s>>>(d_tiles, cq, dprm);   // one warp per open column, grid-stride
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

@@ -63,16 +63,12 @@ struct DevParams {
     double tables[NGSEP_N_TABLES];
 };
 
-// A column = one position that was not closed by the screen / hom-ref proof: its calls (PileupRecord.getAlleleCalls(1)) in
-// pileup order, 16 bits each: bits 0-1 allele, 2-6 quality after the caps of CH:91,217, 7 negative strand, 8 counted (CH:223),
-// 9 always set.
-struct ColumnHdr { int32_t tile; int32_t pos; uint32_t code_off; uint32_t n_codes; };   // n_codes: bits 0-27 count, 28-29 reference allele, 30 reference not ACGT
+// Open columns = the positions the window kernel could not close (screen + hom-ref proof), handed to k_genotype_columns:
+// (tile, 1-based position, index in the tile of the first record that can cover it, number of such records | 0xffff = search).
 struct ColumnQueue {
-    ColumnHdr* cols; uint16_t* codes;
-    uint4* open;                             // open columns handed from k_pileup_windows to k_extract_columns:
-                                             // (window, position in window, first record, number of records | 0xffff = search)
-    unsigned int* ctr;                       // [0] columns claimed, [1] code slots claimed, [2] open columns listed
-    unsigned int cap_cols, cap_codes, cap_open;
+    uint4* open;
+    unsigned int* ctr;                       // [2] open columns listed ([0], [1] unused)
+    unsigned int cap_open;
 };
 
 struct LaunchCfg {
@@ -89,7 +85,7 @@ int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also 
 void launch_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
-void launch_genotype(const TileDev* d_tiles, const WinRange* d_win, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);   // k_extract_columns + k_genotype_columns
+void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
 }  // namespace ngsep_b200

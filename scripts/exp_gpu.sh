@@ -1,17 +1,17 @@
 cd "${GRAFT_REPO_ROOT:-.}"
-python __graft_entry__.py > gpurun_out/build_exp.log 2>&1
+python __graft_entry__.py > gpurun_out/build_exp.log 2>&1 || { tail gpurun_out/build_exp.log; exit 1; }
 run() { tag=$1; shift; env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-pipeline > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.err; python - $tag <<'PY'
 import json,sys
 tag=sys.argv[1]
 try:
     l=json.loads(open(f'gpurun_out/exp_{tag}.json').readline()); r=l['roofline']
-    print(tag, 'step_ms %.3f'%l['ms_per_step'], 'pileup_ms %.3f'%r['kernel_ms_per_step'], 'all_kernels_ms %.3f'%r['both_kernels_ms_per_step'], 'frac %.3f'%r['frac'])
+    print(tag, 'step_ms %.3f'%l['ms_per_step'], 'pileup_ms %.3f'%r['kernel_ms_per_step'], 'all_kernels_ms %.3f'%r['both_kernels_ms_per_step'], 'frac %.3f'%r['frac'], 'open', l['config'].get('open_columns'), 'e2e %.3e'%l['e2e']['value'])
 except Exception as e:
     print(tag,'FAILED',e); print(open(f'gpurun_out/exp_{tag}.err').read()[-800:])
 PY
 }
-run a NGSEP_WINDOW=256 NGSEP_PAY_CAP_WORDS=4608 NGSEP_STAGES=1 NGSEP_MIN_BLOCKS=4 NGSEP_THREADS=256 NGSEP_CTAS_PER_SM=4
-run b NGSEP_WINDOW=256 NGSEP_PAY_CAP_WORDS=4608 NGSEP_STAGES=2 NGSEP_MIN_BLOCKS=4 NGSEP_THREADS=256 NGSEP_CTAS_PER_SM=4
-run c NGSEP_WINDOW=512 NGSEP_PAY_CAP_WORDS=7424 NGSEP_STAGES=1 NGSEP_MIN_BLOCKS=3 NGSEP_THREADS=256 NGSEP_CTAS_PER_SM=3
-run d NGSEP_WINDOW=512 NGSEP_PAY_CAP_WORDS=7424 NGSEP_STAGES=2 NGSEP_MIN_BLOCKS=3 NGSEP_THREADS=256 NGSEP_CTAS_PER_SM=3
-run e NGSEP_WINDOW=512 NGSEP_PAY_CAP_WORDS=7424 NGSEP_STAGES=1 NGSEP_MIN_BLOCKS=4 NGSEP_THREADS=256 NGSEP_CTAS_PER_SM=2
+for cfg in "$@"; do
+  set -- $cfg
+  tag=$1; shift
+  run $tag "$@"
+done

@@ -16,3 +16,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 $CMD > gpurun_out/plain2_${TAG}.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_pileup_windows -s 3 -c 1 -f -o gpurun_out/prof_${TAG} $CMD > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
+# 3. the genotype kernel of the same batched run
+ncu --set full --clock-control none --import-source on -k regex:k_genotype_columns -s 3 -c 1 -f -o gpurun_out/prof_geno_${TAG} $CMD > gpurun_out/ncu_geno_${TAG}.log 2>&1
+ls -la gpurun_out | grep prof_

@@ -1,0 +1,39 @@
+"""Worker of tests/test_region_shards_gloo.py: one rank of a world_size-2 gloo job on CPU.
+
+Each rank runs the host pipeline (admission + event pre-pass + tiling; host_only: no device work) for ITS region shards,
+then the ranks exchange their records and counters exactly as bench.py / a multi-GPU detector run does: no data-path
+collective, only the final gather of per-shard records and the SUM / MAX reduction of the counters."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ngsepcore_b200 import hostapi, simulate  # noqa: E402
+import bench  # noqa: E402
+
+
+def main():
+    out_path = sys.argv[1]
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 150000), ("chrB", 60000)], depth=20, seeds=(7, 8, 9), indel_rate=1e-3)
+    det = hostapi.Detector(host_only=True, tile_len=25000, shard=rank, n_shards=world)
+    det.set_genome(genome)
+    lines = det.run(batch, with_header=False).splitlines()
+    st = det.stats()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, lines)
+    totals, maxima = bench.reduce_over_ranks(dist, torch.device("cpu"), sums=[float(len(lines)), float(st.admitted)], maxima=[float(rank + 1)])
+    if rank == 0:
+        json.dump({"lines": gathered, "totals": totals, "maxima": maxima, "world": world}, open(out_path, "w"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
