@@ -158,8 +158,8 @@ def run_gpu(args):
     t_pack = time.time() - t_pack
     for t in tiles:  # page-lock the host buffers, as a JVM host does for its direct ByteBuffers
         if t["hdr"].size:
-            capi.host_register(t["hdr"]); capi.host_register(t["payload"])
-    h2d_bytes = sum(t["hdr"].nbytes + t["payload"].nbytes for t in tiles)
+            capi.host_register(t["hdr"]); capi.host_register(t["payload"]); capi.host_register(t["qual"])
+    h2d_bytes = sum(t["hdr"].nbytes + t["payload"].nbytes + t["qual"].nbytes for t in tiles)
     aligned_bases = sum(t["aligned_bases"] for t in tiles)
     genome_len = sum(len(v) for v in genome.values())
 
@@ -169,7 +169,7 @@ def run_gpu(args):
     slots = []
     for ci, t in enumerate(tiles):
         if t["hdr"].size:
-            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["max_span"], t["max_back"]))
+            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"]))
 
     def barrier():
         if dist is not None:
@@ -201,7 +201,7 @@ def run_gpu(args):
         for ci, t in enumerate(tiles):
             if not t["hdr"].size:
                 continue
-            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["max_span"], t["max_back"])
+            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"])
             c, _, st = ctx.fetch(sort=False)
             n_calls += len(c)
         return n_calls

@@ -77,10 +77,11 @@ int ngsep_ssvd_stats(void* det, ngsep_run_stats* stats);
 
 /* Admission + packing of one sequence without the event pre-pass (device-resident benchmarking, packer tests). */
 int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_alns_per_start, int ignore5, int ignore3,
-                    ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads, uint64_t* n_words, int* max_span, uint64_t* aligned_bases);
+                    ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads, uint64_t* n_words, uint64_t* n_qual, int* max_span,
+                    uint64_t* aligned_bases);
 /* The tile the detector itself submits for a whole sequence: admission + event pre-pass (read versions) + packing. */
-int ngsep_ssvd_pack(void* det, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads,
-                    uint64_t* n_words, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases);
+int ngsep_ssvd_pack(void* det, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads,
+                    uint64_t* n_words, uint64_t* n_qual, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases);
 void ngsep_host_free(void* p);
 
 #ifdef __cplusplus

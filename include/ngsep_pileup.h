@@ -80,7 +80,11 @@ typedef struct ngsep_read_hdr {
  *   cigar[n_cigar]                     len*8+op, op codes H0 D1 I2 M3 P4 N5 S6 X7 (ReadAlignment.java:60-69,1180-1198)
  *   bases2[ceil(L/16)]                 2-bit A0 C1 G2 T3, base k in bits 2*(k%16) of word k/16
  *   nmask[ceil(L/32)]                  only with NGSEP_M_NMASK
- *   qual[ceil(L/4)]                    phred+33 bytes, little endian (ReadAlignment.qualityScores, RA:581-595)
+ *   lowq[ceil(L/32)]                   bit k set when quality char k - 33 <= 3: the base is never counted (CountsHelper.java:214)
+ *   qoff                               the read's qualities start at byte 4*qoff of ngsep_tile.qual
+ * The phred+33 quality bytes themselves (ReadAlignment.qualityScores, RA:581-595) live in the separate array
+ * ngsep_tile.qual, L bytes per read padded to a multiple of 4 (versions of one read share them): the window kernel never
+ * touches them — they are read only for the positions that reach the genotype kernel.
  */
 
 /* A region tile: every admitted read overlapping [tile_first, tile_last] on one sequence (halo included); calls
@@ -96,6 +100,8 @@ typedef struct ngsep_tile {
     const ngsep_read_hdr* hdr;     /* [n_reads]                                                                    */
     const uint32_t* payload;       /* [n_words]                                                                    */
     const uint16_t* sample;        /* [n_reads] sample index, NULL when n_samples == 1                             */
+    const uint8_t* qual;           /* [n_qual] phred+33 quality bytes, addressed through each record's qoff        */
+    uint64_t n_qual;               /* bytes in qual (a multiple of 4)                                              */
 } ngsep_tile;
 
 /* One SNV-path decision for one position.  Field semantics follow VariantDiscoverySNVQAlgorithm.discoverSNV
@@ -173,7 +179,7 @@ int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
-int ngsep_abi_version(void);
+int ngsep_abi_version(void);   /* 2000: quality bytes in their own array + low-quality mask in the payload */
 int ngsep_built_sm(void);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ class Params(C.Structure):
 class Tile(C.Structure):
     _fields_ = [("seq_idx", C.c_int32), ("tile_first", C.c_int32), ("tile_last", C.c_int32), ("n_reads", C.c_int32),
                 ("max_span", C.c_int32), ("max_back", C.c_int32), ("n_words", C.c_uint64), ("hdr", C.c_void_p),
-                ("payload", C.c_void_p), ("sample", C.c_void_p)]
+                ("payload", C.c_void_p), ("sample", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64)]
 
 
 class TileStats(C.Structure):
@@ -130,21 +130,23 @@ class Context:
         b = np.ascontiguousarray(bases, np.uint8)
         self._check(self.lib.ngsep_ref_upload(self.h, seq_idx, b.ctypes.data, b.size), "ngsep_ref_upload")
 
-    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back) -> Tile:
+    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back) -> Tile:
         hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
         payload = np.ascontiguousarray(payload, np.uint32)
-        self._keep = [hdr, payload]
+        qual = np.ascontiguousarray(qual, np.uint8)
+        self._keep = [hdr, payload, qual]
         return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
-                    hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None, None)
+                    hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None, None,
+                    qual.ctypes.data if qual.size else None, qual.size)
 
-    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> None:
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back)
+    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back)
         self._n_pos = tile_last - tile_first + 1
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
 
-    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back=0) -> int:
+    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0) -> int:
         """Stages a tile in HBM for repeated runs; returns its slot."""
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, max_span, max_back)
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back)
         slot = C.c_int(0)
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1

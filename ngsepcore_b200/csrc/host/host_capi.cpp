@@ -106,8 +106,9 @@ int ngsep_ssvd_stats(void* p, ngsep_run_stats* s) {
 // records of one sequence exactly as the detector would for an indel-free input.  Used by bench.py to build
 // device-resident tiles and by tests that compare the C++ packer with the numpy one.
 int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_alns_per_start, int ignore5, int ignore3,
-                    ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads, uint64_t* n_words, int* max_span, uint64_t* aligned_bases) {
-    if (!b || !hdr || !payload) return NGSEP_EINVAL;
+                    ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads, uint64_t* n_words, uint64_t* n_qual, int* max_span,
+                    uint64_t* aligned_bases) {
+    if (!b || !hdr || !payload || !qual) return NGSEP_EINVAL;
     BatchView v = view_of(b);
     int64_t lo = 0;
     while (lo < v.n && v.seq_idx[lo] != seq_idx) lo++;
@@ -124,17 +125,20 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
     if (aligned_bases) *aligned_bases = t.aligned_bases;
     *hdr = (ngsep_read_hdr*)std::malloc(t.hdr.size() * sizeof(ngsep_read_hdr) + 16);
     *payload = (uint32_t*)std::malloc(t.payload.size() * 4 + 64);
-    if (!*hdr || !*payload) return NGSEP_ENOMEM;
+    *qual = (uint8_t*)std::malloc(t.qual.size() + 64);
+    if (!*hdr || !*payload || !*qual) return NGSEP_ENOMEM;
+    *n_qual = t.qual.size();
     std::memcpy(*hdr, t.hdr.data(), t.hdr.size() * sizeof(ngsep_read_hdr));
     std::memcpy(*payload, t.payload.data(), t.payload.size() * 4);
+    std::memcpy(*qual, t.qual.data(), t.qual.size());
     return NGSEP_OK;
 }
 
 // The tile the detector itself would submit for a whole sequence (admission + event pre-pass versions + packing).
-int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, int64_t* n_reads,
-                    uint64_t* n_words, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases) {
+int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads,
+                    uint64_t* n_words, uint64_t* n_qual, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases) {
     Handle* h = (Handle*)p;
-    if (!h || !h->det || !b || !hdr || !payload) return NGSEP_EINVAL;
+    if (!h || !h->det || !b || !hdr || !payload || !qual) return NGSEP_EINVAL;
     PackedTile t;
     int rc = h->det->pack_sequence(view_of(b), seq_idx, t, *tile_first, *tile_last);
     if (rc != NGSEP_OK) { h->err = h->det->error(); return rc; }
@@ -145,9 +149,12 @@ int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_
     if (aligned_bases) *aligned_bases = t.aligned_bases;
     *hdr = (ngsep_read_hdr*)std::malloc(t.hdr.size() * sizeof(ngsep_read_hdr) + 16);
     *payload = (uint32_t*)std::malloc(t.payload.size() * 4 + 64);
-    if (!*hdr || !*payload) return NGSEP_ENOMEM;
+    *qual = (uint8_t*)std::malloc(t.qual.size() + 64);
+    if (!*hdr || !*payload || !*qual) return NGSEP_ENOMEM;
+    *n_qual = t.qual.size();
     std::memcpy(*hdr, t.hdr.data(), t.hdr.size() * sizeof(ngsep_read_hdr));
     std::memcpy(*payload, t.payload.data(), t.payload.size() * 4);
+    std::memcpy(*qual, t.qual.data(), t.qual.size());
     return NGSEP_OK;
 }
 

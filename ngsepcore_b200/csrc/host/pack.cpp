@@ -25,7 +25,7 @@ inline int ref_last_of(const ReadState& st) {
     return ref - 1;
 }
 
-void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from, int to, PackedTile& out) {
+void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from, int to, uint32_t qoff, PackedTile& out) {
     const CodeLut& L = lut();
     const int len = r.L;
     const int nc = (int)st.cigar.size();
@@ -51,9 +51,10 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
         p.resize(nm + (len + 31) / 32, 0u);
         for (int i = 0; i < len; i++) if (L.v[r.bases[i]] > 3) p[nm + (i >> 5)] |= 1u << (i & 31);
     }
-    size_t q = p.size();
-    p.resize(q + (len + 3) / 4, 0u);
-    std::memcpy(&p[q], r.quals, (size_t)len);
+    size_t lq = p.size();
+    p.resize(lq + (len + 31) / 32, 0u);
+    if (r.quals) for (int i = 0; i < len; i++) if ((int)r.quals[i] - 33 <= 3) p[lq + (i >> 5)] |= 1u << (i & 31);   // never counted (CH:214)
+    p.push_back(qoff);
     out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
     out.max_back = std::max(out.max_back, r.admit_first - st.first);
     out.aligned_bases += (uint64_t)len;
@@ -68,11 +69,17 @@ void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
     out.max_back = 0;
     out.aligned_bases = 0;
     out.hdr.reserve(hi - lo);
+    out.qual.clear();
     for (size_t i = lo; i < hi; i++) {
         const HostRead& r = reads[i];
-        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, false, 0, 0, out); continue; }
-        for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, out);
-        emit_record(r, r.st, true, r.cur_from, INT_MAX, out);
+        // the read's qualities go once into the quality array (every version of the read points at them)
+        const uint32_t qoff = (uint32_t)(out.qual.size() / 4);
+        if (r.quals) out.qual.insert(out.qual.end(), r.quals, r.quals + r.L);
+        else out.qual.insert(out.qual.end(), (size_t)r.L, (uint8_t)'+');   // absent QUAL reads as '+' (RA:1025)
+        out.qual.resize((out.qual.size() + 3) & ~(size_t)3, (uint8_t)'!');
+        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, false, 0, 0, qoff, out); continue; }
+        for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, qoff, out);
+        emit_record(r, r.st, true, r.cur_from, INT_MAX, qoff, out);
     }
 }
 
@@ -85,6 +92,8 @@ ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
     t.hdr = hdr.data();
     t.payload = payload.data();
     t.sample = nullptr;
+    t.qual = qual.data();
+    t.n_qual = qual.size();
     return t;
 }
 

@@ -51,6 +51,7 @@ double fisher_pvalue(int a, int b, int c, int d);   // math/FisherExactTest.java
 struct PackedTile {
     std::vector<ngsep_read_hdr> hdr;
     std::vector<uint32_t> payload;
+    std::vector<uint8_t> qual;   // phred+33 bytes, one run per read (padded to 4), addressed by the records' qoff
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
     ngsep_tile view(int seq_idx, int first, int last) const;

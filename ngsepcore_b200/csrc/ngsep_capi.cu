@@ -48,6 +48,7 @@ constexpr size_t kMaxSlots = 65536;
 struct Slot {
     DevBuf<ngsep_read_hdr> d_hdr;
     DevBuf<uint32_t> d_pay;
+    DevBuf<uint8_t> d_qual;
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
     DevBuf<int32_t> d_counts;
@@ -62,7 +63,7 @@ struct Slot {
     uint64_t aligned_bases = 0;
     unsigned int launches = 0;
     void release() {
-        d_hdr.release(); d_pay.release(); d_win.release(); d_calls.release(); d_counts.release();
+        d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
         if (d_tile) cudaFree(d_tile);
         if (e0) cudaEventDestroy(e0);
         if (em) cudaEventDestroy(em);
@@ -90,7 +91,7 @@ struct Ctx {
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
-    LaunchCfg cfg{512, 7424u, 1, 4, 256};
+    LaunchCfg cfg{640, 3840u, 2, 4, 256};
     size_t smem = 0;
     int ctas_per_sm = 1;
     int geno_grid = 0;                        // blocks of k_genotype_columns
@@ -230,7 +231,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     if (!t) return fail(c, NGSEP_EINVAL, "null argument");
     if (t->n_reads < 0 || t->tile_first < 1 || t->tile_last < t->tile_first) return fail(c, NGSEP_EINVAL, "bad tile extents");
     if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
-    if (t->n_reads > 0 && (!t->hdr || !t->payload)) return fail(c, NGSEP_EINVAL, "null tile buffers");
+    if (t->n_reads > 0 && (!t->hdr || !t->payload || !t->qual)) return fail(c, NGSEP_EINVAL, "null tile buffers");
+    if (t->n_qual > 0x3fffffff0ull) return fail(c, NGSEP_EINVAL, "tile qualities exceed 16 GiB");
     if (c->params.n_samples > 1) return fail(c, NGSEP_EINVAL, "multi-sample tiles are not supported by this build");
     if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
     CK(cudaSetDevice(c->device), "set device");
@@ -238,9 +240,11 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     // the copies start first; the host-side validation below runs while they are in flight
     CK(s->d_hdr.reserve((size_t)t->n_reads + 1), "hdr alloc");
     CK(s->d_pay.reserve((size_t)t->n_words + 16), "payload alloc");
+    CK(s->d_qual.reserve((size_t)t->n_qual + 16), "quality alloc");
     if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
+        CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->stream), "quality copy");
     }
     s->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
     CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
@@ -264,11 +268,11 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     double words_per_pos = (double)t->n_words / (double)tile_len;
     double recs_per_pos = (double)t->n_reads / (double)tile_len;
     const int span = t->max_span < 1 ? 1 : t->max_span;
-    while (T > 128 && (words_per_pos * (T + span) > 0.85 * c->cfg.pay_cap_words || recs_per_pos * (T + span) > 0.85 * (c->cfg.pay_cap_words / 24)))
+    while (T > 128 && (words_per_pos * (T + span) > 0.85 * c->cfg.pay_cap_words || recs_per_pos * (T + span) > 0.85 * (c->cfg.pay_cap_words / 12)))
         T = std::max(128, (T / 2) & ~127);
     TileDev& d = s->tile;
     d = TileDev{};
-    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.sample = nullptr;
+    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.sample = nullptr; d.qual = s->d_qual.p;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
     d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
     d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
@@ -353,7 +357,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
 
 extern "C" {
 
-int ngsep_abi_version(void) { return 1000; }
+int ngsep_abi_version(void) { return 2000; }
 int ngsep_built_sm(void) { return 100; }
 
 const char* ngsep_last_error(void* ctx) {

@@ -35,7 +35,7 @@ struct Thread0State {
 
 static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     SmemLayout L;
-    L.max_reads = pay_cap_words / 24;
+    L.max_reads = pay_cap_words / 12;   // a staged record has at least 12 payload words at the read lengths this is sized for
     unsigned o = 0;
     L.bar = o; o += 16;
     L.t0 = o; o += sizeof(Thread0State);
@@ -111,7 +111,8 @@ struct RecView {
     const uint32_t* cig;
     const uint32_t* b2;
     const uint32_t* nm;
-    const uint8_t* q;
+    const uint32_t* lowq;   // 1 bit/base: quality <= 3
+    uint32_t qoff;          // qualities at byte 4*qoff of the tile's quality array
 };
 __device__ __forceinline__ RecView view_record(const ngsep_read_hdr& h, const uint32_t* pay) {
     RecView r;
@@ -128,7 +129,8 @@ __device__ __forceinline__ RecView view_record(const ngsep_read_hdr& h, const ui
     const uint32_t* t = r.b2 + ((r.L + 15) >> 4);
     r.nm = t;
     if (h.meta & NGSEP_M_NMASK) t += (r.L + 31) >> 5;
-    r.q = (const uint8_t*)t;
+    r.lowq = t;
+    r.qoff = t[(r.L + 31) >> 5];
     return r;
 }
 
@@ -189,13 +191,13 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
         };
         // rare: some base of word j differs — flag the ones CountsHelper would count (callable, RA:782-784; q > 3, CH:214)
         auto flag_word = [&](int j, uint32_t m) {
-            const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
+            const uint32_t* lowq = b2 + ((L + 15) >> 4);   // simple record: the low-quality mask follows the bases
             const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
             while (m) {
                 const int bit = __ffs(m) - 1;
                 m &= m - 1;
                 const int off = 16 * j + (bit >> 1);
-                if (off >= c_lo && off < c_hi && q[off] > 36) flag_candidate(w, ref0 + off, rec);
+                if (off >= c_lo && off < c_hi && !((lowq[off >> 5] >> (off & 31)) & 1u)) flag_candidate(w, ref0 + off, rec);
             }
         };
         if (j1 - j0 < 32) {
@@ -331,7 +333,7 @@ __device__ __forceinline__ int resolve_offset(const RecView& r, int ign_s, int i
 // by getAlleleCalls(1) (counts for totalCount, CH:210).
 constexpr uint32_t kCodeNeg = 1u << 7, kCodeCounted = 1u << 8, kCodeCall = 1u << 9;
 
-__device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, int pos, int max_qs) {
+__device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, const uint8_t* __restrict__ qual, int pos, int max_qs) {
     uint32_t qc, bw;
     int off;
     if (h.meta & NGSEP_M_SIMPLE) {
@@ -340,13 +342,14 @@ __device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uin
         off = pos - h.first;
         if (off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0u;   // RA:782-784
         const uint32_t* b2 = pay + 1;
-        qc = ((const uint8_t*)(b2 + ((L + 15) >> 4)))[off];
+        const uint32_t qoff = b2[((L + 15) >> 4) + ((L + 31) >> 5)];   // after the bases and the low-quality mask
         bw = b2[off >> 4];
+        qc = qual[(size_t)qoff * 4u + (size_t)off];
     } else {
         const RecView r = view_record(h, pay);
         off = resolve_offset(r, h.ign_start, h.ign_end, pos);
         if (off < 0) return 0u;
-        qc = r.q[off];
+        qc = qual[(size_t)r.qoff * 4u + (size_t)off];
         bw = r.b2[off >> 4];
         if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) qc = 0u;   // allele not in ACGT: a call that is not counted (CH:220-221)
     }
@@ -504,8 +507,8 @@ __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx,
     const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
     if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
     const uint32_t* b2 = R.payload(h) + 1;
-    const uint8_t* q = (const uint8_t*)(b2 + ((L + 15) >> 4));
-    return (q[off] > 36 && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    const uint32_t* lowq = b2 + ((L + 15) >> 4);
+    return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
 }
 
 // The exact column (warp-cooperative, records through L2): every record of [i_lo, i_hi) in pileup order, one record per
@@ -561,7 +564,7 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
         }
 #pragma unroll
         for (int r = 0; r < kRegRounds; r++)
-            codes[r] = (i_lo + 32 * r + lane < i_hi) ? lane_eval(hs[r], R.payload(hs[r]), pos, g.max_qs) : 0u;
+            codes[r] = (i_lo + 32 * r + lane < i_hi) ? lane_eval(hs[r], R.payload(hs[r]), d.qual, pos, g.max_qs) : 0u;
 #pragma unroll
         for (int r = 0; r < kRegRounds; r++) count_round(codes[r], cc);
     } else {
@@ -570,7 +573,7 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
             uint32_t code = 0u;
             if (idx < i_hi) {
                 const ngsep_read_hdr h = R.header(idx);
-                code = lane_eval(h, R.payload(h), pos, g.max_qs);
+                code = lane_eval(h, R.payload(h), d.qual, pos, g.max_qs);
             }
             count_round(code, cc);
             accumulate_round(code, acc, lane, pa, pb, g.s_tab);

@@ -41,6 +41,7 @@ struct TileDev {
     const ngsep_read_hdr* hdr;   // [n_reads + 1], sentinel at n_reads carries off = n_words, first = INT_MAX
     const uint32_t* payload;
     const uint16_t* sample;
+    const uint8_t* qual;         // phred+33 bytes, addressed through the records' qoff (only k_genotype_columns reads them)
     int n_reads, max_span, max_back;
     int tile_first, tile_last, seq_idx;
     const uint32_t* ref2;        // 2 bits/base, base idx i (0-based) at bits 2*(i%16) of word i/16; 64 B of zero padding in front

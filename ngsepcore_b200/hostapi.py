@@ -63,9 +63,11 @@ def load_library() -> C.CDLL:
     lib.ngsep_ssvd_vcf.restype = C.c_void_p
     lib.ngsep_ssvd_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
     lib.ngsep_host_pack.argtypes = [C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
-                                    C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
-    lib.ngsep_ssvd_pack.argtypes = [C.c_void_p, C.POINTER(HostBatch), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
-                                    C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
+    lib.ngsep_ssvd_pack.argtypes = [C.c_void_p, C.POINTER(HostBatch), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     lib.ngsep_host_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
@@ -80,21 +82,29 @@ def _host_batch(b: AlignmentBatch):
     return hb, keep
 
 
+def _take(ptr, n, dtype, lib):
+    """Copies n items of a malloc'ed native buffer into a numpy array and frees the buffer."""
+    if n:
+        nbytes = n * np.dtype(dtype).itemsize
+        arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,)).view(dtype).copy()
+    else:
+        arr = np.zeros(0, dtype)
+    lib.ngsep_host_free(ptr)
+    return arr
+
+
 def pack_sequence(batch: AlignmentBatch, seq_idx: int, min_mq: int = 20, max_alns_per_start: int = 5, ignore5: int = 0, ignore3: int = 0):
-    """C++ admission + packing of one sequence (no event pre-pass) -> (hdr, payload, max_span, aligned_bases)."""
+    """C++ admission + packing of one sequence (no event pre-pass) -> (hdr, payload, qual, max_span, aligned_bases)."""
     lib = load_library()
     hb, keep = _host_batch(batch)
-    hdr_p, pay_p = C.c_void_p(), C.c_void_p()
-    n_reads, n_words, span, bases = C.c_int64(), C.c_uint64(), C.c_int(), C.c_uint64()
-    rc = lib.ngsep_host_pack(C.byref(hb), seq_idx, min_mq, max_alns_per_start, ignore5, ignore3, C.byref(hdr_p), C.byref(pay_p),
-                             C.byref(n_reads), C.byref(n_words), C.byref(span), C.byref(bases))
+    hdr_p, pay_p, q_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    n_reads, n_words, n_qual, span, bases = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_int(), C.c_uint64()
+    rc = lib.ngsep_host_pack(C.byref(hb), seq_idx, min_mq, max_alns_per_start, ignore5, ignore3, C.byref(hdr_p), C.byref(pay_p), C.byref(q_p),
+                             C.byref(n_reads), C.byref(n_words), C.byref(n_qual), C.byref(span), C.byref(bases))
     if rc != 0:
         raise NgsepError(f"ngsep_host_pack failed ({rc})")
-    hdr = np.ctypeslib.as_array(C.cast(hdr_p, C.POINTER(C.c_uint8)), shape=(n_reads.value * 16,)).view(HDR_DTYPE).copy() if n_reads.value else np.zeros(0, HDR_DTYPE)
-    pay = np.ctypeslib.as_array(C.cast(pay_p, C.POINTER(C.c_uint32)), shape=(n_words.value,)).copy() if n_words.value else np.zeros(0, np.uint32)
-    lib.ngsep_host_free(hdr_p)
-    lib.ngsep_host_free(pay_p)
-    return hdr, pay, span.value, bases.value
+    return (_take(hdr_p, n_reads.value, HDR_DTYPE, lib), _take(pay_p, n_words.value, np.uint32, lib), _take(q_p, n_qual.value, np.uint8, lib),
+            span.value, bases.value)
 
 
 class Detector:
@@ -143,20 +153,18 @@ class Detector:
         return C.string_at(p, n.value).decode()
 
     def pack(self, batch: AlignmentBatch, seq_idx: int):
-        """The tile the detector submits for sequence seq_idx -> dict(hdr, payload, max_span, max_back, first, last, aligned_bases)."""
+        """The tile the detector submits for sequence seq_idx -> dict(hdr, payload, qual, max_span, max_back, first, last, aligned_bases)."""
         hb, keep = _host_batch(batch)
-        hdr_p, pay_p = C.c_void_p(), C.c_void_p()
-        n_reads, n_words, bases = C.c_int64(), C.c_uint64(), C.c_uint64()
+        hdr_p, pay_p, q_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n_reads, n_words, n_qual, bases = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
         span, back, tf, tl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        rc = self.lib.ngsep_ssvd_pack(self.h, C.byref(hb), seq_idx, C.byref(hdr_p), C.byref(pay_p), C.byref(n_reads), C.byref(n_words),
-                                      C.byref(span), C.byref(back), C.byref(tf), C.byref(tl), C.byref(bases))
+        rc = self.lib.ngsep_ssvd_pack(self.h, C.byref(hb), seq_idx, C.byref(hdr_p), C.byref(pay_p), C.byref(q_p), C.byref(n_reads), C.byref(n_words),
+                                      C.byref(n_qual), C.byref(span), C.byref(back), C.byref(tf), C.byref(tl), C.byref(bases))
         if rc != 0:
             raise NgsepError(f"ngsep_ssvd_pack failed ({rc}): {self.lib.ngsep_ssvd_error(self.h).decode()}")
-        hdr = np.ctypeslib.as_array(C.cast(hdr_p, C.POINTER(C.c_uint8)), shape=(n_reads.value * 16,)).view(HDR_DTYPE).copy() if n_reads.value else np.zeros(0, HDR_DTYPE)
-        pay = np.ctypeslib.as_array(C.cast(pay_p, C.POINTER(C.c_uint32)), shape=(n_words.value,)).copy() if n_words.value else np.zeros(0, np.uint32)
-        self.lib.ngsep_host_free(hdr_p)
-        self.lib.ngsep_host_free(pay_p)
-        return dict(hdr=hdr, payload=pay, max_span=span.value, max_back=back.value, first=tf.value, last=tl.value, aligned_bases=bases.value)
+        return dict(hdr=_take(hdr_p, n_reads.value, HDR_DTYPE, self.lib), payload=_take(pay_p, n_words.value, np.uint32, self.lib),
+                    qual=_take(q_p, n_qual.value, np.uint8, self.lib), max_span=span.value, max_back=back.value, first=tf.value, last=tl.value,
+                    aligned_bases=bases.value)
 
     def stats(self) -> RunStats:
         s = RunStats()

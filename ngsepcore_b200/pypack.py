@@ -60,11 +60,11 @@ def admit(batch: AlignmentBatch, min_mq: int = 20, max_alns_per_start: int = 5, 
 
 
 def pack_tile(batch: AlignmentBatch, idx: np.ndarray, ignore5: int = 0, ignore3: int = 0):
-    """Packs the records idx (already in admission order, one sequence) -> (hdr, payload words, max_span)."""
+    """Packs the records idx (already in admission order, one sequence) -> (hdr, payload words, quality bytes, max_span)."""
     n = int(idx.size)
     hdr = np.zeros(n, HDR_DTYPE)
     if n == 0:
-        return hdr, np.zeros(0, np.uint32), 1
+        return hdr, np.zeros(0, np.uint32), np.zeros(0, np.uint8), 1
     L = (batch.base_off[idx + 1] - batch.base_off[idx]).astype(np.int64)
     nc = (batch.cigar_off[idx + 1] - batch.cigar_off[idx]).astype(np.int64)
     if (L > 0xffff).any() or (nc > 0xff).any():
@@ -83,8 +83,8 @@ def pack_tile(batch: AlignmentBatch, idx: np.ndarray, ignore5: int = 0, ignore3:
     np.logical_or.at(has_n, rep, is_n)
     w_b2 = (L + 15) // 16
     w_nm = np.where(has_n, (L + 31) // 32, 0)
-    w_q = (L + 3) // 4
-    words = nc + w_b2 + w_nm + w_q
+    w_lq = (L + 31) // 32          # low-quality mask
+    words = nc + w_b2 + w_nm + w_lq + 1   # + qoff
     off = np.zeros(n + 1, np.int64); np.cumsum(words, out=off[1:])
     payload = np.zeros(int(off[-1]), np.uint32)
     # cigar
@@ -105,9 +105,18 @@ def pack_tile(batch: AlignmentBatch, idx: np.ndarray, ignore5: int = 0, ignore3:
         sel = is_n
         nm_word = off[:-1][rep[sel]] + nc[rep[sel]] + w_b2[rep[sel]] + within[sel] // 32
         np.add.at(payload, nm_word, (np.uint32(1) << (within[sel] % 32).astype(np.uint32)))
-    # qualities
-    q_word = off[:-1][rep] + nc[rep] + w_b2[rep] + w_nm[rep] + within // 4
-    np.add.at(payload, q_word, (quals.astype(np.uint32) << ((within % 4) * 8).astype(np.uint32)))
+    # low-quality mask: quality char - 33 <= 3 is never counted (CountsHelper.java:214)
+    low = quals.astype(np.int64) - 33 <= 3
+    if low.any():
+        sel = low
+        lq_word = off[:-1][rep[sel]] + nc[rep[sel]] + w_b2[rep[sel]] + w_nm[rep[sel]] + within[sel] // 32
+        np.add.at(payload, lq_word, (np.uint32(1) << (within[sel] % 32).astype(np.uint32)))
+    # quality bytes: their own array, each read padded to a multiple of 4; qoff = start / 4
+    q_len = (L + 3) // 4 * 4
+    q_off = np.zeros(n + 1, np.int64); np.cumsum(q_len, out=q_off[1:])
+    qual = np.full(int(q_off[-1]), ord("!"), np.uint8)
+    qual[q_off[:-1][rep] + within] = quals
+    payload[off[:-1] + nc + w_b2 + w_nm + w_lq] = (q_off[:-1] // 4).astype(np.uint32)
     hdr["first"] = batch.first[idx]
     first_cig = np.zeros(n, np.int64)
     first_cig[nc > 0] = batch.cigar[batch.cigar_off[idx][nc > 0]]
@@ -117,4 +126,4 @@ def pack_tile(batch: AlignmentBatch, idx: np.ndarray, ignore5: int = 0, ignore3:
     hdr["ign_start"] = np.where(neg, ignore3, ignore5)
     hdr["ign_end"] = np.where(neg, ignore5, ignore3)
     hdr["off"] = off[:-1].astype(np.uint32)
-    return hdr, payload, int(max(1, span.max()))
+    return hdr, payload, qual, int(max(1, span.max()))

@@ -7,7 +7,7 @@ python __graft_entry__.py > gpurun_out/build_tune.log 2>&1 || { tail -20 gpurun_
 if [ "$1" == "--no-tests" ]; then shift; else
   timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_tune.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_tune.log
 fi
-[ $# -eq 0 ] && set -- "512 7424 1 4 256"
+[ $# -eq 0 ] && set -- "640 3840 2 4 256"
 for cfg in "$@"; do
   set -- $cfg
   tag="$1_$2_$3_$4_${5:-256}"

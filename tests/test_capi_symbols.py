@@ -20,14 +20,14 @@ def test_header_symbols_exported():
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ngsep_abi_version() == 1000 and lib.ngsep_built_sm() == 100
+    assert lib.ngsep_abi_version() == 2000 and lib.ngsep_built_sm() == 100
 
 
 def test_struct_layouts_match_header():
     assert capi.HDR_DTYPE.itemsize == 16
     assert capi.CALL_DTYPE.itemsize == 224
     assert C.sizeof(capi.Params) == 32
-    assert C.sizeof(capi.Tile) == 56 and C.sizeof(capi.TileStats) == 48
+    assert C.sizeof(capi.Tile) == 72 and C.sizeof(capi.TileStats) == 48
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
@@ -51,7 +51,7 @@ def test_pypack_layout():
     from ngsepcore_b200 import pypack, simulate
     g, b, _ = simulate.simulate(contigs=[("c", 5000)], depth=5, indel_rate=0.0, n_frac=0.0)
     idx = pypack.admit(b)
-    hdr, pay, span = pypack.pack_tile(b, idx)
+    hdr, pay, qual, span = pypack.pack_tile(b, idx)
     assert span == 100 and (np.diff(hdr["first"]) >= 0).all()
     i = 7
     L = int(hdr["meta"][i] & 0xFFFF)
@@ -60,5 +60,9 @@ def test_pypack_layout():
     codes = (pay[o + 1 + np.arange(L) // 16] >> ((np.arange(L) % 16) * 2).astype(np.uint32)) & 3
     src = b.bases[b.base_off[idx[i]]:b.base_off[idx[i] + 1]]
     assert bytes(np.frombuffer(b"ACGT", np.uint8)[codes]) == bytes(src)
-    q = (pay[o + 1 + 7 + np.arange(L) // 4] >> ((np.arange(L) % 4) * 8).astype(np.uint32)) & 0xFF
-    assert bytes(q.astype(np.uint8)) == bytes(b.quals[b.base_off[idx[i]]:b.base_off[idx[i] + 1]])
+    src_q = b.quals[b.base_off[idx[i]]:b.base_off[idx[i] + 1]]
+    lowq = (pay[o + 1 + 7 + np.arange(L) // 32] >> (np.arange(L) % 32).astype(np.uint32)) & 1     # low-quality mask after the bases
+    assert np.array_equal(lowq.astype(bool), src_q.astype(np.int64) - 33 <= 3)
+    qoff = int(pay[o + 1 + 7 + 4])                                                                  # then the quality offset
+    assert bytes(qual[4 * qoff:4 * qoff + L]) == bytes(src_q) and qual.size % 4 == 0
+    assert hdr["meta"][i] & capi.M_SIMPLE

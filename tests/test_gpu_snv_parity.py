@@ -32,8 +32,8 @@ def _run_case(oracle, tmp_path, contigs, depth, sim_kw=None, ctx_kw=None, oracle
         for ci, (name, length) in enumerate(contigs):
             ctx.ref_upload(ci, genome[name])
             idx = idx_all[batch.seq_idx[idx_all] == ci]
-            hdr, pay, span = pypack.pack_tile(batch, idx, **(pack_kw or {}))
-            ctx.submit(ci, 1, length, hdr, pay, span)
+            hdr, pay, qual, span = pypack.pack_tile(batch, idx, **(pack_kw or {}))
+            ctx.submit(ci, 1, length, hdr, pay, qual, span)
             calls, counts, stats = ctx.fetch(want_counts=True)
             n_cov += stats.covered_positions
             # counts parity: oracle dumps pos,A,C,G,T,DP for each position where discoverSNV ran, contig after contig

@@ -23,11 +23,12 @@ def test_cpp_packer_equals_numpy_packer():
     for ci in range(2):
         idx = pypack.admit(batch, max_alns_per_start=2)
         idx = idx[batch.seq_idx[idx] == ci]
-        h1, p1, s1 = pypack.pack_tile(batch, idx, ignore5=2, ignore3=4)
-        h2, p2, s2, nb = hostapi.pack_sequence(batch, ci, max_alns_per_start=2, ignore5=2, ignore3=4)
+        h1, p1, q1, s1 = pypack.pack_tile(batch, idx, ignore5=2, ignore3=4)
+        h2, p2, q2, s2, nb = hostapi.pack_sequence(batch, ci, max_alns_per_start=2, ignore5=2, ignore3=4)
         assert s1 == s2 and nb == int((h1["meta"] & 0xFFFF).sum())
         assert np.array_equal(h1, h2)
         assert np.array_equal(p1, p2)
+        assert np.array_equal(q1, q2)
 
 
 @pytest.mark.parametrize("seed,kw", [
