@@ -5,13 +5,18 @@
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host cores
 
 A "step" = one pass of the hot path over the whole workload: BASELINE configs[1], a yeast-like 12.16 Mb genome at
-30x (2x100 bp), simulated with planted SNVs/indels (ngsepcore_b200/simulate.py), one region tile per sequence.
-  value  = positions with >= 1 covering admitted read / device time, tiles resident in HBM (CUDA events on the context
-           stream; every tile's payload is read from HBM each step: 540 MB per step > 126 MB L2);
+30x (2x100 bp), simulated with planted SNVs/indels (ngsepcore_b200/simulate.py), one region tile per sequence, all
+tiles walked by ONE k_pileup_windows launch followed by ONE k_genotype_columns launch (ngsep_resident_run(-1)).
+  value  = positions with >= 1 covering admitted read / device time of the step, tiles resident in HBM (CUDA events on
+           the context stream; the step's input is 600 MB in HBM > 126 MB L2, so no step is served from cache);
   e2e    = the same metric through the C ABI with HOST buffers: ngsep_tile_submit (H2D from page-locked memory +
            kernels) + ngsep_tile_fetch (D2H of the calls) per tile, all inside the timed region;
-  roofline.achieved = algorithmic bytes (sum_reads(16 + 4 n_cigar + ceil(L/4) + L) + 1 B/reference
-           base + 64 B/call) / time spent in k_pileup_windows (CUDA events around every launch, summed).
+  roofline.achieved = ALGORITHMIC bytes (sum_reads(16 + 4 n_cigar + ceil(L/4) + L) + 1 B/reference base +
+           64 B/call) / device time of k_pileup_windows (CUDA events around the launch, same stream).  The kernel does
+           not need every one of those bytes: quality bytes are read only for the few positions that reach the genotype
+           kernel (the window kernel works from a 1-bit "quality <= 3" mask), so the measured DRAM traffic
+           (roofline.traffic, from the committed ncu capture) is BELOW the algorithmic bytes; roofline.frac_of_traffic
+           gives the fraction of peak the kernel's real traffic amounts to.
 N > 1 (torchrun): every rank owns one GPU and an independent, equally sized region shard (weak scaling, no data-path
 collective — SURVEY.md 8e); value = positions of all ranks / max-over-ranks time.
 """
@@ -43,6 +48,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic():
+    """DRAM bytes of one k_pileup_windows launch over this workload, from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_pileup_windows.json")
+    try:
+        d = json.load(open(p))
+        unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        return sum(float(d[k]["value"]) * unit[d[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def _workload(rank: int, depth: float, scale: float):
     from ngsepcore_b200 import simulate
     contigs = simulate.YEAST_CONTIGS
@@ -68,7 +84,7 @@ class _ClockSampler:
     def __init__(self, device: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(device)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -236,16 +252,20 @@ def run_gpu(args):
         alg_bytes = _algorithmic_bytes(batch, [t["hdr"] for t in tiles], genome_len, calls)
         ms_per_step = total_ms / args.steps
         achieved = alg_bytes * args.steps / (pileup_ms / 1e3) / 1e9
+        traffic = _ncu_traffic() if (args.scale == 1.0 and args.depth == 30.0) else None
         line = {
             "metric": METRIC, "value": covered_all / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "depth": args.depth, "genome_bp": genome_len, "reads": int(batch.n), "tiles": len(slots),
                        "genotyped_positions_per_gpu": int(covered), "candidate_positions": int(cand), "open_columns": int(st.open_columns), "calls": int(calls),
-                       "l2": "inputs larger than L2 (%.0f MB of tile payload read per step)" % (h2d_bytes / 1e6),
+                       "l2": "inputs larger than L2 (%.0f MB of packed tiles resident in HBM, walked every step)" % (h2d_bytes / 1e6),
                        "parallelism": f"region shards x{world}, no collective"},
             "aligned_bases_per_sec": bases_all / (ms_per_step / 1e3),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "frac_of_traffic": (traffic / (pileup_ms / args.steps / 1e3) / 1e9 / peak) if traffic else None,
+                         "traffic_note": "ncu dram__bytes_read+write of one launch on this workload (profiles/r01_ncu_pileup_windows.json); below the "
+                                         "algorithmic bytes because quality bytes are only read for the columns that reach k_genotype_columns",
                          "kernel": "k_pileup_windows", "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": pileup_ms / args.steps,
                          "launches_per_step": 1, "both_kernels_ms_per_step": kernels_ms / args.steps, "peak_source": peak_src},
             "e2e": {"value": covered_all * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),

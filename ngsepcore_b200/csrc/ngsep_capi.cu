@@ -91,7 +91,7 @@ struct Ctx {
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
-    LaunchCfg cfg{640, 3840u, 2, 4, 256};
+    LaunchCfg cfg{1280, 6400u, 1, 4, 256};
     size_t smem = 0;
     int ctas_per_sm = 1;
     int geno_grid = 0;                        // blocks of k_genotype_columns
