@@ -150,9 +150,14 @@ struct WinCtx {
     int* mset;                   // counters of this window
     bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
 };
-constexpr int kListShift = 13;                       // windows hold at most 8192 positions
+// candidate list entry as the screen writes it: bits 0-12 position in the window (windows hold at most 8192 positions),
+// 13-31 the flagging record.  The resolve pass (C1) rewrites it in place for the proofs: 0-12 position, 13-14 reference
+// allele, 15-20 `need` = k_min[m_up] (63 = no number of reference bases closes the column), 21-31 flagging record.
+constexpr int kListShift = 13;
 constexpr uint32_t kListPosMask = (1u << kListShift) - 1u;
 constexpr int kListMaxRec = (1 << (32 - kListShift)) - 1;
+constexpr int kProofRefShift = 13, kProofNeedShift = 15, kProofRecShift = 21;
+constexpr int kProofMaxRec = (1 << (32 - kProofRecShift)) - 1, kProofNoNeed = 63;
 
 // rec = index of the flagging record inside the window's record range
 __device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx, int rec) {
@@ -503,12 +508,23 @@ struct ExactCtx {
 template <bool kGlobal>
 __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
     if (idx < 0 || idx >= R.n) return 0;
-    const ngsep_read_hdr h = R.header(idx);
-    const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
-    if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
-    const uint32_t* b2 = R.payload(h) + 1;
-    const uint32_t* lowq = b2 + ((L + 15) >> 4);
-    return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    if (kGlobal) {
+        const ngsep_read_hdr h = R.header(idx);
+        const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
+        if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
+        const uint32_t* b2 = R.payload(h) + 1;
+        const uint32_t* lowq = b2 + ((L + 15) >> 4);
+        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    } else {
+        // staged window: the screen left the header in its proof form {first, first callable position, end of the callable
+        // positions (0, 0 for a record that is not simple), b2 word index | lowq word offset << 16}
+        const int4 dh = *(const int4*)(R.hdr + idx);
+        if (pos < dh.y || pos >= dh.z) return 0;
+        const int off = pos - dh.x;
+        const uint32_t* b2 = R.pay + (dh.w & 0xffff);
+        const uint32_t* lowq = b2 + ((uint32_t)dh.w >> 16);
+        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    }
 }
 
 // The exact column (warp-cooperative, records through L2): every record of [i_lo, i_hi) in pileup order, one record per
@@ -597,37 +613,28 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
     finalize_warp(acc, cc, lane, pos, ref, d, g.min_quality, g.s_tab[93], g.s_tab[94]);
 }
 
-// Phase C.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
+// Phase C2.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
 // were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
-// of the records does).  k_lb >= k_min[m_up] closes the column (k_min is INT_MAX when the bound does not apply).  What
-// stays open is listed, with its record range, for k_extract_columns.
+// of the records does).  k_lb >= need = k_min[m_up] closes the column.  What stays open is listed, with its record range,
+// for k_genotype_columns.  Entries come from the resolve pass (position | reference allele | need | flagging record).
 template <bool kGlobal>
-__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, int w_idx, uint2* s_open, int* n_open,
+__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, uint2* s_open, int* n_open,
                                             int warp, int lane, int nwarps) {
     const int grp = lane >> 4, gl = lane & 15;
     for (int base = 0; base < x.n_cand; base += 2 * nwarps) {
         const int ci = base + 2 * warp + grp;
-        const bool act = ci < x.n_cand;
-        uint32_t ent = 0u, m_up = 0u;
-        int li = 0, pos = 0, ref = 0;
+        uint32_t ent = 0u;
+        int ok = 0, need = 0;
         bool open = false;
-        int ok = 0;
-        if (act) {
+        if (ci < x.n_cand) {
             ent = x.s_list[ci];
-            li = (int)(ent & kListPosMask);
-            pos = x.wbeg + li + 1;
-            m_up = x.s_cnt[li];
-            open = !((x.s_refn[li >> 5] >> (li & 31)) & 1u);                                           // VD:101-107
-            if (x.ignore_lower && ((x.s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;               // SSVPL:198
-            const int rr = li + kRefLeft;
-            ref = (int)((x.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
-            if (open && m_up < (uint32_t)kSkipTable) ok = counted_ref_base(R, (int)(ent >> kListShift) - 8 + gl, pos, ref);
+            need = (int)((ent >> kProofNeedShift) & 63u);
+            open = need > 0;                               // need == 0: closed by the resolve pass
+            if (open && need <= 15)
+                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) - 8 + gl, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
         }
         const unsigned okm = __ballot_sync(kFull, ok != 0);
-        if (act) {
-            if (gl == 0) x.s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
-            if (open && m_up < (uint32_t)kSkipTable && __popc(okm & (0xffffu << (16 * grp))) >= x.s_kmin[m_up]) open = false;
-        }
+        if (open && __popc(okm & (0xffffu << (16 * grp))) >= need) open = false;
         // the (few) columns still open: second chance with the whole warp (the 32 records around the flagging one), then
         // the record range of the column, then the list
         unsigned sm = __ballot_sync(kFull, open && gl == 0);
@@ -635,12 +642,11 @@ __device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactC
             const int src = __ffs(sm) - 1;
             sm &= sm - 1;
             const uint32_t e = __shfl_sync(kFull, ent, src);
-            const uint32_t mu = __shfl_sync(kFull, m_up, src);
+            const int e_need = (int)((e >> kProofNeedShift) & 63u);
             const int e_li = (int)(e & kListPosMask), e_pos = x.wbeg + e_li + 1;
-            if (mu < (uint32_t)kSkipTable && x.s_kmin[mu] <= 30) {
-                const int e_ref = __shfl_sync(kFull, ref, src);
-                const int ok2 = counted_ref_base(R, (int)(e >> kListShift) - 16 + lane, e_pos, e_ref);
-                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= x.s_kmin[mu]) continue;
+            if (e_need <= 30) {
+                const int ok2 = counted_ref_base(R, (int)(e >> kProofRecShift) - 16 + lane, e_pos, (int)((e >> kProofRefShift) & 3u));
+                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= e_need) continue;
             }
             const int i_lo = warp_lower_bound(R, e_pos - x.max_span + 1, lane);
             const int i_hi = warp_lower_bound(R, e_pos + x.max_back + 1, lane);   // first record that starts too far to the right
@@ -786,6 +792,16 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                     const ngsep_read_hdr h = s_hdr[i];
                     const uint32_t* pay = s_pay + (h.off - pay_base);
                     e = record_is_simple(h) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
+                    {   // proof form of the staged header (counted_ref_base<false>); word 0 (the ordering start) stays
+                        int4 dh = make_int4(h.first, 0, 0, 0);
+                        if (record_is_simple(h)) {
+                            const int L = (int)(h.meta & 0xffffu);
+                            dh.y = h.first + max((int)h.ign_start, 0);
+                            dh.z = h.first + L - max((int)h.ign_end, 0);
+                            dh.w = (int)((uint32_t)(pay + 1 - s_pay) | ((uint32_t)((L + 15) >> 4) << 16));
+                        }
+                        *(int4*)(const_cast<ngsep_read_hdr*>(s_hdr) + i) = dh;
+                    }
                     nxt = min(s_hdr[i + 1].first, B + 1);
                     floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
                     if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
@@ -867,18 +883,36 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             for (int i = tid; i < n_all; i += nthr)
                 if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)wr.tile, (unsigned int)(g_lo + i + 1), 0u, kOpenSearch);
         } else if (n_cand > 0) {
+            const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
+            const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
+            // C1, resolve pass (thread per candidate): everything the proofs need goes into the list entry
+            for (int ci = tid; ci < n_cand; ci += nthr) {
+                const uint32_t ent = s_list[ci];
+                const int li = (int)(ent & kListPosMask);
+                const uint32_t m_up = s_cnt[li];
+                s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
+                bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // VD:101-107
+                if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
+                const int rr = li + kRefLeft;
+                const uint32_t ref = (wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
+                int need = (m_up < (uint32_t)kSkipTable) ? min(s_kmin[m_up], kProofNoNeed) : kProofNoNeed;
+                if (need <= 0) need = 1;
+                if (closed) need = 0;
+                s_list[ci] = (uint32_t)li | (ref << kProofRefShift) | ((uint32_t)need << kProofNeedShift) |
+                             ((uint32_t)min((int)(ent >> kListShift), kProofMaxRec) << kProofRecShift);
+            }
+            __syncthreads();   // ---- sync 3: entries resolved -----------------------------------------------------------------
             ExactCtx x;
             x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile; x.rec0 = wr.lo;
-            x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2;
-            x.s_refn = (const uint32_t*)(stg + lay.o_refn); x.s_refl = (const uint32_t*)(stg + lay.o_refl);
+            x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2; x.s_refn = s_refn; x.s_refl = s_refl;
             x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                proof_phase<false>(R, x, a.cq, w, s_open, &mset[M_NOPEN], warp, lane, nwarps);
+                proof_phase<false>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             } else {
                 const TileDev& d = a.tiles[wr.tile];
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                proof_phase<true>(R, x, a.cq, w, s_open, &mset[M_NOPEN], warp, lane, nwarps);
+                proof_phase<true>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
