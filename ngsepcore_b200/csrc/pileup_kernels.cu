@@ -208,26 +208,29 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
         if (j1 - j0 < 32) {
             // Branch-free pass over the words (a warp would otherwise take the mismatch path on almost every iteration,
             // since SOME lane has a mismatch), then the few words that differ.  First and last word carry the masks.
+            // wm collects one bit per word, most recent word in bit 0 (word j0 + t ends up in bit n - 1 - t)
             uint32_t wlo = rp[0], whi = rp[1];
             uint32_t x = b2[j0] ^ __funnelshift_r(wlo, whi, sh);
             uint32_t m = (x | (x >> 1)) & 0x55555555u & head;
             if (j1 == j0) m &= tail;
-            uint32_t wm = (m != 0u) ? 1u : 0u;
+            uint32_t wm = min(m, 1u);
+#pragma unroll 4
             for (int j = j0 + 1; j < j1; j++) {
                 wlo = whi;
                 whi = rp[j - j0 + 1];
                 x = b2[j] ^ __funnelshift_r(wlo, whi, sh);
                 m = (x | (x >> 1)) & 0x55555555u;
-                wm |= (m != 0u ? 1u : 0u) << (j - j0);
+                wm = (wm << 1) | min(m, 1u);
             }
             if (j1 > j0) {
                 x = b2[j1] ^ __funnelshift_r(whi, rp[j1 - j0 + 1], sh);
                 m = (x | (x >> 1)) & 0x55555555u & tail;
-                wm |= (m != 0u ? 1u : 0u) << (j1 - j0);
+                wm = (wm << 1) | min(m, 1u);
             }
             while (wm) {
-                const int j = j0 + __ffs(wm) - 1;
-                wm &= wm - 1;
+                const int bit = 31 - __clz(wm);
+                wm &= ~(1u << bit);
+                const int j = j1 - bit;
                 flag_word(j, diff(j));
             }
         } else {
