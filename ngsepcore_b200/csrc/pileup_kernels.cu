@@ -12,7 +12,7 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, t0, kmin, misc, cnt, list, open, wmax, rare;   // CTA-wide arrays
+    unsigned bar, t0, kmin, misc, cnt, list, ulist, open, wmax, rare;   // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
@@ -20,7 +20,7 @@ struct SmemLayout {
 
 // s_misc holds two sets of kMiscSet ints (one per window parity)
 constexpr int kMiscSet = 16;
-constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8;
+constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8, M_NUNRES = 9;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
 constexpr int kMaxOpen = 64;     // open columns listed in shared memory per window (more go straight to the global list)
 constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: k_extract_columns searches it
@@ -43,6 +43,7 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
     L.list = o; o += T * 4;
+    L.ulist = o; o += ((T * 2 + 3) & ~3u);      // candidates the quarter-warp proofs left open
     o = (o + 7u) & ~7u;
     L.open = o; o += 2 * kMaxOpen * 8;   // open columns of the window, one list per window parity
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
@@ -498,8 +499,9 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
 }
 
 struct ExactCtx {
-    int wbeg, n_cand, max_span, max_back, tile, rec0;   // rec0: index in the tile of the window's first record
+    int wbeg, n_cand, n_unres, max_span, max_back, tile, rec0;   // rec0: index in the tile of the window's first record
     const uint32_t* s_list;
+    const uint16_t* s_ulist;     // candidates the quarter-warp proofs left open (indexes into s_list)
     uint32_t* s_cnt;
     const uint32_t *s_ref2, *s_refn, *s_refl;
     const int* s_kmin;
@@ -616,7 +618,31 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
     finalize_warp(acc, cc, lane, pos, ref, d, g.min_quality, g.s_tab[93], g.s_tab[94]);
 }
 
-// Phase C2.  Fast proof of hom-ref by a HALF-WARP per candidate: at most m_up counted non-reference bases
+// Phase C2.  First proof attempt by a QUARTER-WARP per candidate: the 8 records next to the flagging one (4 on each side)
+// usually hold the k_min[1] = 7 counted reference bases that close a column with one flagged base.  What stays open is
+// listed for the half-warp pass.
+template <bool kGlobal>
+__device__ __forceinline__ void quarter_proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, uint16_t* s_ulist, int* n_unres, int warp, int lane, int nwarps) {
+    const int grp = lane >> 3, gl = lane & 7;
+    const int delta = (gl < 4) ? gl - 4 : gl - 3;   // -4..-1, +1..+4
+    for (int base = 0; base < x.n_cand; base += 4 * nwarps) {
+        const int ci = base + 4 * warp + grp;
+        int ok = 0, need = 0;
+        bool open = false;
+        if (ci < x.n_cand) {
+            const uint32_t ent = x.s_list[ci];
+            need = (int)((ent >> kProofNeedShift) & 63u);
+            open = need > 0;                               // need == 0: closed by the resolve pass
+            if (open && need <= 8)
+                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) + delta, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
+        }
+        const unsigned okm = __ballot_sync(kFull, ok != 0);
+        if (open && __popc(okm & (0xffu << (8 * grp))) >= need) open = false;
+        if (open && gl == 0) s_ulist[atomicAdd(n_unres, 1)] = (uint16_t)ci;
+    }
+}
+
+// Phase C3.  Fast proof of hom-ref by a HALF-WARP per candidate the quarter-warp pass left open: at most m_up counted non-reference bases
 // were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
 // of the records does).  k_lb >= need = k_min[m_up] closes the column.  What stays open is listed, with its record range,
 // for k_genotype_columns.  Entries come from the resolve pass (position | reference allele | need | flagging record).
@@ -624,16 +650,16 @@ template <bool kGlobal>
 __device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, uint2* s_open, int* n_open,
                                             int warp, int lane, int nwarps) {
     const int grp = lane >> 4, gl = lane & 15;
-    for (int base = 0; base < x.n_cand; base += 2 * nwarps) {
-        const int ci = base + 2 * warp + grp;
+    for (int base = 0; base < x.n_unres; base += 2 * nwarps) {
+        const int ui = base + 2 * warp + grp;
         uint32_t ent = 0u;
         int ok = 0, need = 0;
         bool open = false;
-        if (ci < x.n_cand) {
-            ent = x.s_list[ci];
+        if (ui < x.n_unres) {
+            ent = x.s_list[x.s_ulist[ui]];
             need = (int)((ent >> kProofNeedShift) & 63u);
-            open = need > 0;                               // need == 0: closed by the resolve pass
-            if (open && need <= 15)
+            open = true;
+            if (need <= 15)
                 ok = counted_ref_base(R, (int)(ent >> kProofRecShift) - 8 + gl, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
         }
         const unsigned okm = __ballot_sync(kFull, ok != 0);
@@ -689,6 +715,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     int* s_misc = (int*)(smem + lay.misc);
     uint32_t* s_cnt = (uint32_t*)(smem + lay.cnt);
     uint32_t* s_list = (uint32_t*)(smem + lay.list);
+    uint16_t* s_ulist = (uint16_t*)(smem + lay.ulist);
     int* s_wmax = (int*)(smem + lay.wmax);
     int2* s_rare = (int2*)(smem + lay.rare);
 
@@ -909,12 +936,19 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile; x.rec0 = wr.lo;
             x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2; x.s_refn = s_refn; x.s_refl = s_refl;
             x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
+            x.s_ulist = s_ulist; x.n_unres = 0;
             if (single) {
                 Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
+                quarter_proof_phase<false>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
+                __syncthreads();   // ---- sync 4: candidates left to the half-warp pass listed --------------------------------------
+                x.n_unres = mset[M_NUNRES];
                 proof_phase<false>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             } else {
                 const TileDev& d = a.tiles[wr.tile];
                 Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
+                quarter_proof_phase<true>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
+                __syncthreads();
+                x.n_unres = mset[M_NUNRES];
                 proof_phase<true>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
             }
         }
