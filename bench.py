@@ -212,16 +212,23 @@ def run_gpu(args):
     barrier()
     total_ms = float(sum(step_ms))
     # ---- end-to-end through the C ABI with host buffers ------------------------------------------------------------------
+    IN_FLIGHT = 3   # tiles between ngsep_tile_submit and ngsep_tile_fetch (the C ABI pipelines up to 4)
+
     def e2e_step():
-        n_calls = 0
+        n_calls, pending = 0, 0
         for ci, t in enumerate(tiles):
             if not t["hdr"].size:
                 continue
+            if pending == IN_FLIGHT:
+                c, _, st = ctx.fetch(sort=False)
+                n_calls += len(c); pending -= 1
             ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"])
+            pending += 1
+        while pending:
             c, _, st = ctx.fetch(sort=False)
-            n_calls += len(c)
+            n_calls += len(c); pending -= 1
         return n_calls
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()

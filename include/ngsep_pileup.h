@@ -151,11 +151,14 @@ const char* ngsep_last_error(void* ctx);
 int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t length);
 
 /* Asynchronous: copies the tile's host buffers to the device and launches the kernels on the context stream.
- * The host buffers must stay valid until ngsep_tile_fetch returns. */
+ * Up to 4 tiles may be in flight; they are fetched in submission order, so the host can pack / copy the next tile while
+ * the device works on the previous one (NGSEP_ESTATE when a fifth is submitted before a fetch).  A tile's host buffers
+ * must stay valid until the ngsep_tile_fetch that returns it. */
 int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
 
-/* Waits for the submitted tile and copies its calls (unordered) into out[0..cap).  counts_dbg, when not NULL and
- * NGSEP_F_EMIT_ALL is set, receives [tile_last-tile_first+1][5] = A,C,G,T,DP. */
+/* Waits for the OLDEST submitted tile and copies its calls (unordered) into out[0..cap).  counts_dbg, when not NULL and
+ * NGSEP_F_EMIT_ALL is set, receives [tile_last-tile_first+1][5] = A,C,G,T,DP.  NGSEP_EOVERFLOW with *n_out > cap: the
+ * tile stays at the head of the queue, call again with room for *n_out calls. */
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 
 /* Device-resident tiles: stage any number of tiles in HBM once (slots 1..n; slot 0 is the submit/fetch slot), then

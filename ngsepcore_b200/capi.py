@@ -134,7 +134,7 @@ class Context:
         hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
         payload = np.ascontiguousarray(payload, np.uint32)
         qual = np.ascontiguousarray(qual, np.uint8)
-        self._keep = [hdr, payload, qual]
+        self._keep = (getattr(self, "_keep", []) + [hdr, payload, qual])[-12:]   # buffers of the tiles still in flight
         return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
                     hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None, None,
                     qual.ctypes.data if qual.size else None, qual.size)

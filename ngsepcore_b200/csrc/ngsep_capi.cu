@@ -44,6 +44,7 @@ struct DevBuf {
 
 constexpr size_t kMetaStride = 32;      // d_meta: [0] column-queue counters (2 x u32), then per slot: counters[2] (u64) | n_calls (u32) | pad
 constexpr size_t kMaxSlots = 65536;
+constexpr size_t kRing = 4;             // tiles that may be in flight between ngsep_tile_submit and ngsep_tile_fetch
 
 struct Slot {
     DevBuf<ngsep_read_hdr> d_hdr;
@@ -52,19 +53,23 @@ struct Slot {
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
     DevBuf<int32_t> d_counts;
-    TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches
+    TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches, followed by the 16-byte staging report
+    bool report_read = false;                 // the staging report has been checked on the host
+    unsigned int* d_report() const { return (unsigned int*)(d_tile + 1); }
     unsigned int* d_ncalls = nullptr;         // inside Ctx::d_meta
     unsigned long long* d_counters = nullptr; // inside Ctx::d_meta
     cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // before the pileup kernel / between the two kernels / after
     TileDev tile{};
-    ngsep_read_hdr sentinel{};
-    bool staged = false, launched = false, in_batch = false;
+    struct Pinned { ngsep_read_hdr sentinel; TileDev tile; }* pin = nullptr;   // page-locked: small copies stay asynchronous
+    bool staged = false, launched = false, in_batch = false, pipelined = false;
     int grid = 0;
     uint64_t aligned_bases = 0;
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
         if (d_tile) cudaFree(d_tile);
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr;
         if (e0) cudaEventDestroy(e0);
         if (em) cudaEventDestroy(em);
         if (e1) cudaEventDestroy(e1);
@@ -81,7 +86,9 @@ struct Ctx {
     DevParams* d_prm = nullptr;
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
     std::vector<RefSeq> refs;
-    std::vector<Slot*> slots;                 // slot 0 = submit/fetch, 1.. = resident tiles
+    std::vector<Slot*> slots;                 // slot 0 = first submit/fetch slot, 1.. = resident tiles
+    std::vector<Slot*> ring;                  // submit/fetch pipeline: ring[0] == slots[0]; tiles are fetched in submission order
+    size_t ring_head = 0, ring_tail = 0, ring_count = 0;
     // batched launch over every resident slot
     DevBuf<TileDev> d_btiles;
     DevBuf<WinRange> d_bwin;
@@ -106,13 +113,13 @@ int cuda_fail(Ctx* c, cudaError_t e, const char* what) {
 
 std::string g_global_err;
 
-int new_slot(Ctx* c, Slot** out) {
-    if (c->slots.size() >= kMaxSlots) return fail(c, NGSEP_ENOMEM, "too many resident tiles");
+int new_slot(Ctx* c, Slot** out, size_t id) {   // id = index of the slot's 32-byte counter block in d_meta
+    if (c->slots.size() >= kMaxSlots - kRing) return fail(c, NGSEP_ENOMEM, "too many resident tiles");
     Slot* s = new Slot();
-    const size_t id = c->slots.size();
     s->d_counters = (unsigned long long*)(c->d_meta + (1 + id) * kMetaStride);
     s->d_ncalls = (unsigned int*)(c->d_meta + (1 + id) * kMetaStride + 16);
-    cudaError_t e = cudaMalloc((void**)&s->d_tile, sizeof(TileDev));
+    cudaError_t e = cudaMalloc((void**)&s->d_tile, sizeof(TileDev) + 16);   // + the staging report (k_check_headers)
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->pin, sizeof(Slot::Pinned), cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreate(&s->e0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->em);
     if (e == cudaSuccess) e = cudaEventCreate(&s->e1);
@@ -178,6 +185,8 @@ int launch_slot(Ctx* c, Slot* s) {
     if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
     if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream); s->launches = 2; }
+    // the open-column counter is shared by every launch of the context: keep this tile's value with the tile
+    CK(cudaMemcpyAsync((unsigned char*)s->d_counters + 20, c->d_meta + 8, 4, cudaMemcpyDeviceToDevice, c->stream), "open counter copy");
     CK(cudaEventRecord(s->e1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     s->launched = true;
@@ -222,8 +231,22 @@ int launch_batch(Ctx* c) {
     CK(cudaEventRecord(c->b1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
-    c->slots[0]->launched = false;   // the batch memset cleared slot 0's counters as well
+    c->slots[0]->launched = false;   // the batch memset cleared the first pipeline slot's counters as well
+    c->ring_head = c->ring_tail = c->ring_count = 0;
     c->batch_ran = true;
+    return NGSEP_OK;
+}
+
+// Reads the staging report of a tile whose staging work has completed on the device.
+int read_report(Ctx* c, Slot* s) {
+    if (s->report_read) return NGSEP_OK;
+    struct { unsigned int err, pad; unsigned long long bases; } rep;
+    CK(cudaMemcpy(&rep, s->d_report(), sizeof(rep), cudaMemcpyDeviceToHost), "report copy");
+    s->report_read = true;
+    s->aligned_bases = rep.bases;
+    if (rep.err & 1u) return fail(c, NGSEP_EINVAL, "records are not sorted by start");
+    if (rep.err & 2u) return fail(c, NGSEP_EINVAL, "payload offsets are not monotone");
+    if (rep.err & 4u) return fail(c, NGSEP_EINVAL, "record payload exceeds the device window (read too long)");
     return NGSEP_OK;
 }
 
@@ -238,30 +261,27 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     CK(cudaSetDevice(c->device), "set device");
     const RefSeq& ref = c->refs[t->seq_idx];
     // the copies start first; the host-side validation below runs while they are in flight
-    CK(s->d_hdr.reserve((size_t)t->n_reads + 1), "hdr alloc");
-    CK(s->d_pay.reserve((size_t)t->n_words + 16), "payload alloc");
-    CK(s->d_qual.reserve((size_t)t->n_qual + 16), "quality alloc");
+    {   // pipeline slots grow together: a slot takes the largest capacity any of them has needed so far, so that cycling
+        // tiles of different sizes through the ring stops reallocating after the first pass
+        size_t need_h = (size_t)t->n_reads + 1, need_p = (size_t)t->n_words + 16, need_q = (size_t)t->n_qual + 16;
+        if (s->pipelined) for (Slot* r : c->ring) { need_h = std::max(need_h, r->d_hdr.cap); need_p = std::max(need_p, r->d_pay.cap); need_q = std::max(need_q, r->d_qual.cap); }
+        if (need_h > s->d_hdr.cap) { s->d_hdr.release(); CK(cudaMalloc((void**)&s->d_hdr.p, need_h * sizeof(ngsep_read_hdr)), "hdr alloc"); s->d_hdr.cap = need_h; }
+        if (need_p > s->d_pay.cap) { s->d_pay.release(); CK(cudaMalloc((void**)&s->d_pay.p, need_p * sizeof(uint32_t)), "payload alloc"); s->d_pay.cap = need_p; }
+        if (need_q > s->d_qual.cap) { s->d_qual.release(); CK(cudaMalloc((void**)&s->d_qual.p, need_q), "quality alloc"); s->d_qual.cap = need_q; }
+    }
     if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
         CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->stream), "quality copy");
     }
-    s->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
-    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
-    launch_sanitize_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, c->stream);   // NGSEP_M_SIMPLE is trusted only when the payload backs it
-    // validate ordering + stage fit (a record must fit one staged chunk)
-    uint64_t bases = 0;
-    const char* bad = nullptr;
-    for (int i = 0; i < t->n_reads && !bad; i++) {
-        const ngsep_read_hdr& h = t->hdr[i];
-        if (i > 0 && h.first < t->hdr[i - 1].first) bad = "records are not sorted by start";
-        uint64_t next = (i + 1 < t->n_reads) ? t->hdr[i + 1].off : t->n_words;
-        if (next < h.off || next > t->n_words) bad = "payload offsets are not monotone";
-        else if (next - h.off + 4 > c->cfg.pay_cap_words) bad = "record payload exceeds the device window (read too long)";
-        bases += h.meta & 0xffffu;
-    }
-    if (bad) { cudaStreamSynchronize(c->stream); s->staged = false; return fail(c, NGSEP_EINVAL, bad); }   // the caller may free its buffers
-    s->aligned_bases = bases;
+    s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
+    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
+    // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
+    // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
+    CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
+    launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, c->cfg.pay_cap_words, s->d_report(), c->stream);
+    s->report_read = false;
+    s->aligned_bases = 0;
     // window length: a multiple of 128, shrunk while an average window would not fit one stage
     int T = c->cfg.T_lay;
     int64_t tile_len = (int64_t)t->tile_last - t->tile_first + 1;
@@ -289,8 +309,10 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
         d.counts_dbg = s->d_counts.p;
     }
     d.counters = s->d_counters;
+    d.report = s->d_report();
     s->grid = std::min(d.n_windows, c->sm_count * c->ctas_per_sm);   // persistent CTAs
-    CK(cudaMemcpyAsync(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice, c->stream), "tile descriptor copy");
+    s->pin->tile = s->tile;
+    CK(cudaMemcpyAsync(s->d_tile, &s->pin->tile, sizeof(TileDev), cudaMemcpyHostToDevice, c->stream), "tile descriptor copy");
     launch_window_index(d, s->d_win.p, 0, c->stream);   // depends on the staged records only: built once per staging
     CK(cudaGetLastError(), "window index launch");
     s->staged = true;
@@ -302,23 +324,32 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
     if (!n_out) return fail(c, NGSEP_EINVAL, "null argument");
     if (!s->launched) return fail(c, NGSEP_ESTATE, "no tile in flight");
     CK(cudaSetDevice(c->device), "set device");
-    struct Meta { unsigned long long ctr[2]; unsigned int n_calls, pad[3]; } meta;
+    struct Meta { unsigned long long ctr[2]; unsigned int n_calls, n_open, pad[2]; } meta;
     static_assert(sizeof(Meta) == kMetaStride, "meta layout");
     for (int attempt = 0; attempt < 4; attempt++) {
-        CK(cudaStreamSynchronize(c->stream), "tile kernels");
+        // a pipelined tile waits for ITS kernels only: later tiles may already be copying on the same stream
+        if (s->in_batch) CK(cudaStreamSynchronize(c->stream), "tile kernels");
+        else CK(cudaEventSynchronize(s->e1), "tile kernels");
         CK(cudaMemcpy(&meta, s->d_counters, sizeof(meta), cudaMemcpyDeviceToHost), "counters copy");
+        { int rrc = read_report(c, s); if (rrc != NGSEP_OK) return rrc; }
         int grew = 0;
-        int rc = queue_overflowed(c, &grew);
-        if (rc != NGSEP_OK) return rc;
+        if (s->in_batch) {
+            int rc = queue_overflowed(c, &grew);
+            if (rc != NGSEP_OK) return rc;
+        } else if (meta.n_open > c->d_open.cap) {
+            c->q_min_cols = std::max(c->q_min_cols, (size_t)meta.n_open + (size_t)meta.n_open / 4 + 1024);
+            grew = 1;
+        }
         if (meta.n_calls <= s->tile.cap_calls && !grew) break;
         if (attempt == 3) return fail(c, NGSEP_EOVERFLOW, "call / column buffer overflow");
+        if (grew && !s->in_batch) CK(cudaStreamSynchronize(c->stream), "drain before growing the open-column list");   // later tiles use the list too
         if (meta.n_calls > s->tile.cap_calls) {   // grow and rerun the staged tile
             CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");
             s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
             CK(cudaMemcpy(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice), "tile descriptor copy");
             c->batch_dirty = true;
         }
-        rc = s->in_batch ? launch_batch(c) : launch_slot(c, s);
+        int rc = s->in_batch ? launch_batch(c) : launch_slot(c, s);
         if (rc != NGSEP_OK) return rc;
     }
     const unsigned int n = meta.n_calls;
@@ -338,7 +369,8 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         stats->kernel_ms = ms;
         stats->pileup_ms = pms;
         stats->kernel_launches = s->launches;
-        { unsigned int qc[3] = {0, 0, 0}; CK(cudaMemcpy(qc, c->d_meta, sizeof(qc), cudaMemcpyDeviceToHost), "queue counters copy"); stats->open_columns = qc[2]; }
+        if (s->in_batch) { unsigned int qc[3] = {0, 0, 0}; CK(cudaMemcpy(qc, c->d_meta, sizeof(qc), cudaMemcpyDeviceToHost), "queue counters copy"); stats->open_columns = qc[2]; }
+        else stats->open_columns = meta.n_open;
     }
     *n_out = n;
     if (n > cap) return fail(c, NGSEP_EOVERFLOW, "caller's call buffer is too small; n_out holds the required capacity");
@@ -408,8 +440,16 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     c->geno_grid = c->sm_count * 16;
     if (const char* s = std::getenv("NGSEP_GENO_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 256) c->geno_grid = c->sm_count * v; }
     Slot* s0 = nullptr;
-    if (new_slot(c, &s0) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }
+    if (new_slot(c, &s0, 0) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }
     c->slots.push_back(s0);
+    s0->pipelined = true;
+    c->ring.push_back(s0);
+    for (size_t k = 1; k < kRing; k++) {   // counter blocks of the other ring slots sit at the end of d_meta
+        Slot* sk = nullptr;
+        if (new_slot(c, &sk, kMaxSlots - k) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }
+        sk->pipelined = true;
+        c->ring.push_back(sk);
+    }
     DevParams hp{};
     hp.max_base_qs = params->max_base_qs;
     hp.min_quality = params->min_quality;
@@ -454,6 +494,7 @@ int ngsep_ctx_destroy(void* ctx) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& r : c->refs) r.release();
     for (Slot* s : c->slots) { s->release(); delete s; }
+    for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
     c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
@@ -501,15 +542,27 @@ int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t leng
 int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
-    int rc = stage_slot(c, c->slots[0], t);
+    if (c->ring_count == c->ring.size()) return fail(c, NGSEP_ESTATE, "too many tiles in flight: call ngsep_tile_fetch first");
+    Slot* s = c->ring[c->ring_head];
+    int rc = stage_slot(c, s, t);
     if (rc != NGSEP_OK) return rc;
-    return launch_slot(c, c->slots[0]);
+    rc = launch_slot(c, s);
+    if (rc != NGSEP_OK) return rc;
+    c->ring_head = (c->ring_head + 1) % c->ring.size();
+    c->ring_count++;
+    return NGSEP_OK;
 }
 
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
-    return fetch_slot(c, c->slots[0], out, cap, n_out, counts_dbg, stats);
+    if (c->ring_count == 0) return fail(c, NGSEP_ESTATE, "no tile in flight");
+    Slot* s = c->ring[c->ring_tail];
+    int rc = fetch_slot(c, s, out, cap, n_out, counts_dbg, stats);
+    if (rc == NGSEP_EOVERFLOW && n_out && *n_out > cap) return rc;   // the caller retries with a larger buffer: the tile stays at the tail
+    c->ring_tail = (c->ring_tail + 1) % c->ring.size();
+    c->ring_count--;
+    return rc;
 }
 
 int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
@@ -517,7 +570,7 @@ int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
     if (!c || !slot) return NGSEP_EINVAL;
     CK(cudaSetDevice(c->device), "set device");
     Slot* s = nullptr;
-    int rc = new_slot(c, &s);
+    int rc = new_slot(c, &s, c->slots.size());
     if (rc != NGSEP_OK) return rc;
     rc = stage_slot(c, s, t);
     if (rc != NGSEP_OK) { s->release(); delete s; return rc; }
@@ -590,6 +643,7 @@ int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, s
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
     if (slot < 0 || (size_t)slot >= c->slots.size()) return fail(c, NGSEP_EINVAL, "bad slot");
+    if (slot == 0) return ngsep_tile_fetch(ctx, out, cap, n_out, counts_dbg, stats);   // slot 0 = the submit/fetch pipeline
     return fetch_slot(c, c->slots[slot], out, cap, n_out, counts_dbg, stats);
 }
 

@@ -1047,6 +1047,11 @@ __global__ void k_window_index(const TileDev d, WinRange* out, int tile_idx) {
     int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= d.n_windows) return;
     int64_t wbeg = (int64_t)(d.win0 + w) * d.T;
+    if (d.report && d.report[0]) {   // the tile failed its staging check: an empty window, nothing is walked
+        WinRange r; r.lo = r.hi = 0; r.off_lo = r.off_hi = 0u; r.tile = tile_idx; r.wbeg = (int)wbeg; r.g_pack = 0u; r.span_pack = 0u;
+        out[w] = r;
+        return;
+    }
     int64_t p_lo = wbeg + 1 - d.max_span + 1;     // smallest ordering start that can still reach the window
     int64_t p_hi = wbeg + d.T + d.max_back;       // largest ordering start that can begin inside it
     int lo = 0, hi = d.n_reads;
@@ -1095,19 +1100,38 @@ void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStre
     if (n > 0) k_window_index<<<(n + 127) / 128, 128, 0, s>>>(d, out, tile_idx);
 }
 
-// The packer's NGSEP_M_SIMPLE promise is checked once per staging, on the device copy of the headers: a record whose
-// flag is not backed by its payload loses the flag (and goes through the general path, which is always correct).
-__global__ void k_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n) {
+// Staging-time check of a tile, on the device copy of its headers (the host thread only enqueues copies):
+//   report[0] |= 1  records not sorted by start      |= 2  payload offsets not monotone / out of range
+//             |= 4  a record larger than one stage    report[2..3] += read lengths (aligned bases, 64 bit)
+// A tile with report[0] != 0 gets an EMPTY window index (k_window_index), so the kernels never walk it; the host reports
+// the error when it fetches the tile.  The packer's NGSEP_M_SIMPLE promise is verified here too: a record whose flag is
+// not backed by its payload loses the flag (and goes through the general path, which is always correct).
+__global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n, unsigned long long n_words, unsigned int pay_cap_words,
+                                unsigned int* report) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t meta = hdr[i].meta;
-    if (!(meta & NGSEP_M_SIMPLE)) return;
-    const bool ok = (meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && payload[hdr[i].off] == (((meta & 0xffffu) << 3) | 3u);
-    if (!ok) hdr[i].meta = meta & ~NGSEP_M_SIMPLE;
+    unsigned int err = 0u, L = 0u;
+    if (i < n) {
+        const ngsep_read_hdr h = hdr[i];
+        const unsigned long long next = hdr[i + 1].off;   // the sentinel carries n_words
+        if (i > 0 && h.first < hdr[i - 1].first) err |= 1u;
+        if (next < h.off || next > n_words) err |= 2u;
+        else if (next - h.off + 4ull > pay_cap_words) err |= 4u;
+        L = h.meta & 0xffffu;
+        if (!err && (h.meta & NGSEP_M_SIMPLE)) {
+            const bool ok = (h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && payload[h.off] == ((L << 3) | 3u);
+            if (!ok) hdr[i].meta = h.meta & ~NGSEP_M_SIMPLE;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { L += __shfl_xor_sync(0xffffffffu, L, o); err |= __shfl_xor_sync(0xffffffffu, err, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if (L) atomicAdd((unsigned long long*)(report + 2), (unsigned long long)L);
+        if (err) atomicOr(report, err);
+    }
 }
 
-void launch_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, cudaStream_t s) {
-    if (n > 0) k_sanitize_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned int pay_cap_words, unsigned int* report,
+                          cudaStream_t s) {
+    if (n > 0) k_check_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n, n_words, pay_cap_words, report);
 }
 
 // The kernel is compiled for two CTA sizes and three register budgets each; the context picks one.

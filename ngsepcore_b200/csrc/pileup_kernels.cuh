@@ -53,6 +53,7 @@ struct TileDev {
     ngsep_snv_call* calls; unsigned int* n_calls; unsigned int cap_calls;
     int32_t* counts_dbg;         // [tile_len][5] or null
     unsigned long long* counters;// [0] covered positions, [1] candidates
+    const unsigned int* report;  // staging check of the tile (k_check_headers): [0] error bits
 };
 
 struct DevParams {
@@ -83,7 +84,8 @@ struct LaunchCfg {
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
 int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
-void launch_sanitize_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, cudaStream_t s);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned int pay_cap_words, unsigned int* report,
+                          cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
