@@ -66,6 +66,12 @@ typedef struct ngsep_run_stats {
 
 void ngsep_detector_options_default(ngsep_detector_options* o);
 int ngsep_ssvd_create(const ngsep_detector_options* o, void** det);
+/* MultisampleVariantsDetector (src/ngsep/discovery/MultisampleVariantsDetector.java: run() :421-462): the detector handle is
+ * used with the same ngsep_ssvd_set_genome / _run / _vcf / _stats / _destroy calls.  rg_ids / rg_samples = the @RG table of the
+ * input(s) (ID and SM, SM NULL or "" when absent: the sample is then the read-group id, RAFR:188); ngsep_host_batch.rg indexes
+ * it.  Samples and their column order follow MSVD.loadSamplesFromAlignmentHeaders (MSVD:492-516). */
+int ngsep_msvd_create(const ngsep_detector_options* o, int n_read_groups, const char* const* rg_ids, const char* const* rg_samples,
+                      double min_allele_depth_frequency, void** det);
 int ngsep_ssvd_destroy(void* det);
 const char* ngsep_ssvd_error(void* det);
 /* setGenome (SSVD:161-163): sequence names, lengths and bases exactly as in the FASTA (case kept). */

@@ -99,7 +99,8 @@ typedef struct ngsep_tile {
     uint64_t n_words;              /* payload length in words                                                      */
     const ngsep_read_hdr* hdr;     /* [n_reads]                                                                    */
     const uint32_t* payload;       /* [n_words]                                                                    */
-    const uint16_t* sample;        /* [n_reads] sample index, NULL when n_samples == 1                             */
+    const uint16_t* group;         /* [n_reads] read-group id of each record (see ngsep_samples_set; 0xFFFF = no read group
+                                      that belongs to a sample); NULL when n_samples == 1                          */
     const uint8_t* qual;           /* [n_qual] phred+33 quality bytes, addressed through each record's qoff        */
     uint64_t n_qual;               /* bytes in qual (a multiple of 4)                                              */
 } ngsep_tile;
@@ -126,6 +127,36 @@ typedef struct ngsep_snv_call {
 #define NGSEP_CALL_HET 1      /* 0/1   CalledSNV heterozygous     VD:181-188 */
 #define NGSEP_CALL_HOMALT 2   /* 1/1   CalledSNV homozygous alt   VD:189-193 */
 #define NGSEP_CALL_TRIALLELIC 3 /* 1/2 MULTISNV                   VD:128-177; a0 = alt, a1 = third allele as ordered by VD:133-139 */
+
+/* ---- MultisampleVariantsDetector (ngsep_params.n_samples > 1) -------------------------------------------------------
+ * One emitted population SNV site: MultisampleVariantsDetector.onPileup for a span-1 position
+ * (discovery/MultisampleVariantsDetector.java:521-537): pooled allele discovery (discoverPopulationSNV, MSVD:585-597 +
+ * SingleSampleVariantPileupListener.createSNVVariantPool, SSVPL:297-332), per-sample VD.genotypeSNV (VD:21-97) through
+ * SSVPL.genotypeVariantSample (SSVPL:361-391, sample-level minQuality 40), QUAL = best GQ of the decided,
+ * non-homozygous-reference samples (MSVD:685-691), kept when QUAL != 0 and QUAL >= minQuality (MSVD:533). */
+typedef struct ngsep_pop_site {
+    int32_t seq_idx;
+    int32_t pos;
+    int32_t count[4];     /* pooled CountsHelper.counts over ALL reads of the column (any read group)   MSVD:586-587 */
+    int32_t depth;        /* pooled totalCount                                                                        */
+    int16_t qs;           /* variant quality                                                           MSVD:685-691 */
+    int8_t ref;           /* reference allele index (A0 C1 G2 T3)                                                     */
+    int8_t n_alleles;     /* alleles of the final variant, reference first                             MSVD:590-595 */
+    int8_t allele[4];     /* their base indexes; allele[0] == ref                                                     */
+    int8_t n_alleles0;    /* alleles createSNVVariantPool found before the refinement loop (a variant that was reduced
+                             to >2 alleles loses its MULTISNV type, SSVPL:346-359)                                    */
+    int8_t pad[7];
+} ngsep_pop_site;
+
+/* One sample's genotype at a population site; ngsep_tile_fetch_pop returns n_samples of them per site, in sample order. */
+typedef struct ngsep_sample_call {
+    int32_t count[4];     /* the sample's CountsHelper.counts                                          SSVPL:365-367 */
+    int32_t depth;        /* the sample's totalCount                                                                  */
+    int16_t gq;           /* genotype quality, 0 when undecided                                        SSVPL:388     */
+    int8_t g0, g1;        /* called alleles as indexes into ngsep_pop_site.allele (g0 == g1: homozygous); -1,-1 undecided */
+    double logcond[10];   /* logConditionalProbs of the sample, summed in ITS pileup order: [i][i] for i = 0..3, then
+                             [0][1] [0][2] [0][3] [1][2] [1][3] [2][3] (the matrix is symmetric, CH:231-249)         */
+} ngsep_sample_call;
 
 /* Counters of the last completed tile. */
 typedef struct ngsep_tile_stats {
@@ -161,6 +192,18 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
  * tile stays at the head of the queue, call again with room for *n_out calls. */
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 
+/* Multi-sample contexts (n_samples > 1).  ngsep_samples_set declares, once per context and before the first tile, which
+ * read groups form each sample and in which order PileupRecord.getAlleleCalls(span, Set<String>) (PR:104-111) visits them
+ * (the iteration order of Sample.readGroups): sample s owns sample_groups[sample_group_off[s] .. sample_group_off[s+1]).
+ * ngsep_tile.group carries each record's read-group id (0 <= id < n_groups, or 0xFFFF).  ngsep_tile_submit is unchanged;
+ * results come back through ngsep_tile_fetch_pop: sites[i] with its n_samples sample calls at calls[i * n_samples].
+ * min_allele_depth_freq = MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58, default 0). */
+int ngsep_samples_set(void* ctx, int32_t n_groups, const int32_t* sample_group_off, const uint16_t* sample_groups, double min_allele_depth_freq);
+int ngsep_tile_fetch_pop(void* ctx, ngsep_pop_site* sites, size_t cap_sites, size_t* n_sites, ngsep_sample_call* calls, int32_t* counts_dbg,
+                         ngsep_tile_stats* stats);
+int ngsep_resident_fetch_pop(void* ctx, int slot, ngsep_pop_site* sites, size_t cap_sites, size_t* n_sites, ngsep_sample_call* calls,
+                             int32_t* counts_dbg, ngsep_tile_stats* stats);
+
 /* Device-resident tiles: stage any number of tiles in HBM once (slots 1..n; slot 0 is the submit/fetch slot), then
  * run the kernels over them repeatedly without host<->device copies.  ngsep_resident_run(slot = -1) walks the windows
  * of EVERY resident tile in ONE kernel launch on the context stream (all sequences of a genome = one launch); results
@@ -182,7 +225,7 @@ int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
-int ngsep_abi_version(void);   /* 2000: quality bytes in their own array + low-quality mask in the payload */
+int ngsep_abi_version(void);   /* 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
 int ngsep_built_sm(void);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ class Params(C.Structure):
 class Tile(C.Structure):
     _fields_ = [("seq_idx", C.c_int32), ("tile_first", C.c_int32), ("tile_last", C.c_int32), ("n_reads", C.c_int32),
                 ("max_span", C.c_int32), ("max_back", C.c_int32), ("n_words", C.c_uint64), ("hdr", C.c_void_p),
-                ("payload", C.c_void_p), ("sample", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64)]
+                ("payload", C.c_void_p), ("group", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64)]
 
 
 class TileStats(C.Structure):
@@ -46,7 +46,13 @@ CALL_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)
 
 EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_ref_upload", "ngsep_tile_submit",
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
-           "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm"]
+           "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
+           "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop"]
+
+# multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
+SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
+                       ("allele", "i1", (4,)), ("n_alleles0", "i1"), ("pad", "i1", (7,))])
+SAMPLE_CALL_DTYPE = np.dtype([("count", "<i4", (4,)), ("depth", "<i4"), ("gq", "<i2"), ("g0", "i1"), ("g1", "i1"), ("logcond", "<f8", (10,))])
 
 _lib = None
 
@@ -75,6 +81,10 @@ def load_library() -> C.CDLL:
     lib.ngsep_host_register.argtypes = [C.c_void_p, C.c_size_t]
     lib.ngsep_host_unregister.argtypes = [C.c_void_p]
     lib.ngsep_tile_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(TileStats)]
+    lib.ngsep_samples_set.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double]
+    lib.ngsep_tile_fetch_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(TileStats)]
+    lib.ngsep_resident_fetch_pop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
+                                             C.POINTER(TileStats)]
     _lib = lib
     return lib
 
@@ -111,9 +121,10 @@ class Context:
     """One GPU context (ngsep_ctx_create .. ngsep_ctx_destroy)."""
 
     def __init__(self, device: int = 0, max_base_qs: int = 30, min_quality: int = 40, het_rate: float = 0.001, ploidy: int = 2,
-                 flags: int = 0, tables: np.ndarray | None = None):
+                 flags: int = 0, tables: np.ndarray | None = None, n_samples: int = 1):
         self.lib = load_library()
-        self.params = Params(max_base_qs, min_quality, het_rate, ploidy, flags, 1, 0)
+        self.n_samples = n_samples
+        self.params = Params(max_base_qs, min_quality, het_rate, ploidy, flags, n_samples, 0)
         tab = np.ascontiguousarray(host_tables(het_rate) if tables is None else tables, np.float64)
         self.h = C.c_void_p()
         rc = self.lib.ngsep_ctx_create(device, C.byref(self.params), tab.ctypes.data_as(C.POINTER(C.c_double)), tab.size, C.byref(self.h))
@@ -130,23 +141,54 @@ class Context:
         b = np.ascontiguousarray(bases, np.uint8)
         self._check(self.lib.ngsep_ref_upload(self.h, seq_idx, b.ctypes.data, b.size), "ngsep_ref_upload")
 
-    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back) -> Tile:
+    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group=None) -> Tile:
         hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
         payload = np.ascontiguousarray(payload, np.uint32)
         qual = np.ascontiguousarray(qual, np.uint8)
-        self._keep = (getattr(self, "_keep", []) + [hdr, payload, qual])[-12:]   # buffers of the tiles still in flight
+        group = None if group is None else np.ascontiguousarray(group, np.uint16)
+        self._keep = (getattr(self, "_keep", []) + [hdr, payload, qual, group])[-16:]   # buffers of the tiles still in flight
         return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
-                    hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None, None,
+                    hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None,
+                    group.ctypes.data if group is not None and group.size else None,
                     qual.ctypes.data if qual.size else None, qual.size)
 
-    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0) -> None:
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back)
+    def samples_set(self, sample_groups, n_groups: int, min_allele_depth_freq: float = 0.0) -> None:
+        """sample_groups: per sample, the read-group ids in the order PR.getAlleleCalls(span, Set) visits them."""
+        off = np.zeros(len(sample_groups) + 1, np.int32)
+        off[1:] = np.cumsum([len(g) for g in sample_groups])
+        flat = np.array([g for gs in sample_groups for g in gs] or [0], np.uint16)
+        self._check(self.lib.ngsep_samples_set(self.h, n_groups, off.ctypes.data, flat.ctypes.data, min_allele_depth_freq), "ngsep_samples_set")
+
+    def fetch_pop(self, cap: int = 4096, want_counts: bool = False, slot: int = 0):
+        """Multi-sample contexts: (sites sorted by pos, sample calls [n_sites, n_samples], pooled counts or None, TileStats)."""
+        stats = TileStats()
+        n_pos = self._n_pos if slot == 0 else self._slot_npos[slot]
+        counts = np.zeros((n_pos, 5), np.int32) if want_counts else None
+        while True:
+            sites = np.zeros(cap, SITE_DTYPE)
+            calls = np.zeros((cap, self.n_samples), SAMPLE_CALL_DTYPE)
+            n = C.c_size_t(0)
+            cp = counts.ctypes.data if want_counts else None
+            if slot == 0:
+                rc = self.lib.ngsep_tile_fetch_pop(self.h, sites.ctypes.data, cap, C.byref(n), calls.ctypes.data, cp, C.byref(stats))
+            else:
+                rc = self.lib.ngsep_resident_fetch_pop(self.h, slot, sites.ctypes.data, cap, C.byref(n), calls.ctypes.data, cp, C.byref(stats))
+            if rc == -6 and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            self._check(rc, "ngsep_tile_fetch_pop")
+            break
+        o = np.argsort(sites["pos"][: n.value], kind="stable")
+        return sites[: n.value][o], calls[: n.value][o], counts, stats
+
+    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group)
         self._n_pos = tile_last - tile_first + 1
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
 
-    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0) -> int:
+    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> int:
         """Stages a tile in HBM for repeated runs; returns its slot."""
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back)
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group)
         slot = C.c_int(0)
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1

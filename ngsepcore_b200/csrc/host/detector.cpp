@@ -53,7 +53,7 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
     int rc = opt_.host_only ? NGSEP_OK : ensure_ctx();
     if (rc != NGSEP_OK) return rc;
-    if (with_header) out += vcf_header(opt_.sample_id, opt_.ploidy, opt_.print_sample_ploidy);
+    if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
     bool query_found = false;
     int64_t i = 0;
@@ -82,9 +82,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     const int seq_len = (int)genome_->seqs[seq].size();
     double t0 = now_s();
     std::vector<HostRead>& reads = plan.reads;
-    std::vector<IndelRecord>& indels = plan.indels;
     std::set<int>& suppressed = plan.suppressed;
-    std::vector<std::pair<int, int>>& embedded = plan.embedded;
     // ---- 1. admission -------------------------------------------------------------------------------------------
     AdmissionOptions ao;
     ao.min_mq = opt_.min_mq; ao.max_alns_per_start = opt_.max_alns_per_start; ao.secondary = opt_.secondary;
@@ -105,8 +103,6 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     Realigner realigner;
     realigner.genome = genome_;
     realigner.seq = seq;
-    IndelCallerOptions io;
-    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
     int last_indel_end = 0;                           // SSVPL:143
     {
         std::priority_queue<int, std::vector<int>, std::greater<int>> heap;
@@ -155,14 +151,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             if (!genome_->get(seq, e, e + ev.span - 1, ref)) { suppressed.insert(e); continue; }   // SSVPL:195-196
             if (opt_.ignore_lower && ref[0] >= 'a' && ref[0] <= 'z') { suppressed.insert(e); continue; }
             if (emb || ev.span <= 1) continue;            // SNV path: the device decides
-            IndelRecord rec;
-            if (call_indel_at(e, upper(ref), ev.str, pileup, io, rec)) {
-                suppressed.insert(e);
-                last_indel_end = rec.last;                 // SSVPL:157-158
-                if (rec.last > e) embedded.push_back({e + 1, rec.last});
-                indels.push_back(std::move(rec));
-                stats_.indel_calls++;
-            }
+            on_span_event(e, upper(ref), ev, pileup, plan, last_indel_end);
         }
     }
     stats_.prepass_s += now_s() - t0;
@@ -176,6 +165,20 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         plan.max_back = std::max(plan.max_back, r.admit_first - firstp);
     }
     return NGSEP_OK;
+}
+
+void GpuSingleSampleVariantsDetector::on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan,
+                                                    int& last_indel_end) {
+    IndelCallerOptions io;
+    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
+    IndelRecord rec;
+    if (call_indel_at(e, ref_upper, ev.str, pileup, io, rec)) {
+        plan.suppressed.insert(e);
+        last_indel_end = rec.last;                 // SSVPL:157-158
+        if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
+        plan.indels.push_back(std::move(rec));
+        stats_.indel_calls++;
+    }
 }
 
 void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const {

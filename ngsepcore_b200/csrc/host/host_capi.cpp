@@ -17,6 +17,9 @@ struct Handle {
     DetectorOptions opt;
     Genome genome;
     GpuSingleSampleVariantsDetector* det = nullptr;
+    bool multi = false;
+    std::vector<SampleDef> samples;
+    int n_read_groups = 0;
     std::string vcf, err;
     ~Handle() { delete det; }
 };
@@ -60,6 +63,21 @@ int ngsep_ssvd_create(const ngsep_detector_options* o, void** out) {
     return NGSEP_OK;
 }
 
+int ngsep_msvd_create(const ngsep_detector_options* o, int n_read_groups, const char* const* rg_ids, const char* const* rg_samples,
+                      double min_allele_depth_frequency, void** out) {
+    if (!o || !out || n_read_groups < 1 || !rg_ids) return NGSEP_EINVAL;
+    Handle* h = new Handle();
+    h->opt = convert(o);
+    h->opt.min_allele_depth_freq = min_allele_depth_frequency;
+    h->multi = true;
+    h->n_read_groups = n_read_groups;
+    std::vector<std::string> ids, sms;
+    for (int i = 0; i < n_read_groups; i++) { ids.emplace_back(rg_ids[i]); sms.emplace_back((rg_samples && rg_samples[i]) ? rg_samples[i] : ""); }
+    h->samples = samples_from_read_groups(ids, sms, h->opt.ploidy);
+    *out = h;
+    return NGSEP_OK;
+}
+
 int ngsep_ssvd_destroy(void* p) { delete (Handle*)p; return NGSEP_OK; }
 
 const char* ngsep_ssvd_error(void* p) { return p ? ((Handle*)p)->err.c_str() : ""; }
@@ -70,7 +88,8 @@ int ngsep_ssvd_set_genome(void* p, int n, const char* const* names, const int64_
     h->genome.names.clear(); h->genome.seqs.clear();
     for (int i = 0; i < n; i++) { h->genome.names.emplace_back(names[i]); h->genome.seqs.emplace_back(bases[i], (size_t)lengths[i]); }
     delete h->det;
-    h->det = new GpuSingleSampleVariantsDetector(h->opt);
+    if (h->multi) h->det = new GpuMultisampleVariantsDetector(h->opt, h->samples, h->n_read_groups);
+    else h->det = new GpuSingleSampleVariantsDetector(h->opt);
     h->det->set_genome(&h->genome);
     return NGSEP_OK;
 }

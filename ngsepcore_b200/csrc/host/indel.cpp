@@ -294,5 +294,137 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
     return true;
 }
 
+// ---- sample axis --------------------------------------------------------------------------------------------------
+namespace {
+
+// CountsHelper.calculateCountsIndel over a call list (CH:96-105, 253-304): counts, total and the log-likelihood matrix.
+struct IndelCounts { std::vector<int> counts; std::vector<std::vector<double>> L; int total = 0; };
+
+IndelCounts indel_counts(const std::vector<std::string>& alleles, const std::vector<const SpanCall*>& calls, int max_base_qs) {
+    const QTables& t = qt();
+    const int n = (int)alleles.size();
+    IndelCounts h;
+    h.counts.assign(n, 0);
+    h.L.assign(n, std::vector<double>(n, 0.0));
+    for (const SpanCall* cp : calls) {
+        const SpanCall& c = *cp;
+        h.total++;
+        int index = -1;
+        for (int i = 0; i < n; i++) if (alleles[i] == c.allele) { index = i; break; }
+        std::vector<double> lc(n, t.log_err_indel);
+        int best = -1;
+        for (int i = 0; i < n; i++) {
+            if (alleles[i].size() != c.allele.size()) continue;
+            double v = 0;
+            for (size_t k = 0; k < alleles[i].size(); k++) {  // calculateLogCond, CH:384-396
+                int q = (int)(int8_t)std::min(max_base_qs, (int)(unsigned char)c.quals[k] - 33);
+                if (q < 3) continue;
+                v += (alleles[i][k] == c.allele[k]) ? t.match[q] : t.err4[q];
+            }
+            lc[i] = std::max(t.log_err_indel, v);
+            if (lc[i] > t.log_err_indel && (best == -1 || lc[best] < lc[i])) best = i;
+        }
+        if (index >= 0 && best >= 0 && best != index) index = std::min(index, best);
+        else if (index < 0 && best >= 0) index = best;
+        if (index >= 0) h.counts[index]++;
+        for (int i = 0; i < n; i++) {
+            h.L[i][i] += lc[i];
+            for (int j = 0; j < n; j++) {
+                if (i == j) continue;
+                if (j == index) h.L[i][j] += log_sum(t.lf251_0 + lc[index], t.lf251_1 + t.log_err_indel);
+                else if (i == index) h.L[i][j] += log_sum(t.lf251_1 + lc[index], t.lf251_0 + t.log_err_indel);
+                else h.L[i][j] += t.log_err_indel;
+            }
+        }
+    }
+    return h;
+}
+
+// SSVPL.genotypeVariantSample for a variant that is not an SNV (SSVPL:378-384, 386-388): VD.callIndel with the variant
+// given (VD:265-361) on the sample's calls, then the sample-level minQuality (40: the listener is a fresh one, MSVD:676-678).
+SampleIndelCall genotype_indel_sample(const std::vector<std::string>& alleles, const std::vector<const SpanCall*>& calls, int max_base_qs, double het_rate) {
+    SampleIndelCall sc;
+    IndelCounts h = indel_counts(alleles, calls, max_base_qs);
+    if (h.total == 0) return sc;                       // VD:273-276: undecided, no report
+    auto P = posteriors(h.L, het_rate);
+    const int n = (int)alleles.size();
+    int m0 = 0, m1 = 0;
+    double pmax = P[0][0];
+    for (int i = 0; i < n; i++) for (int j = i; j < n; j++) {
+        double gp = P[i][j];
+        if (i != j) gp += P[j][i];
+        if (gp > pmax + 0.01) { pmax = gp; m0 = i; m1 = j; }
+    }
+    if (m0 != m1) sc.called = {m0, m1}; else sc.called = {m0};
+    double max_p = P[m0][m1];
+    if (m0 != m1) max_p += P[m1][m0];
+    sc.gq = phred(1 - max_p);
+    sc.depth = h.total;
+    sc.has_report = true;
+    sc.counts = h.counts;
+    sc.logc = h.L;
+    if (40 > sc.gq) { sc.called.clear(); sc.gq = 0; }   // SSVPL:388 makeUndecided (the report stays)
+    return sc;
+}
+
+}  // namespace
+
+int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const std::vector<SampleDef>& samples,
+                             const IndelCallerOptions& opt, PopIndelRecord& rec) {
+    const int span = (int)ref_allele.size();
+    // PR.getAlleleCalls(span): every read of the column, pileup order (pooled discovery, MSVD:600)
+    std::vector<SpanCall> calls;
+    std::vector<int> call_rg;
+    for (HostRead* r : pileup) {
+        SpanCall c;
+        if (!r->span_call(pos, pos + span - 1, c.allele, c.quals)) continue;
+        c.allele = upper(c.allele);
+        c.neg = r->neg;
+        calls.push_back(std::move(c));
+        call_rg.push_back(r->rg);
+    }
+    std::vector<std::string> alleles = cluster_alleles(calls, ref_allele, opt.max_base_qs);   // MSVD:601-602
+    // createIndelVariantPool (SSVPL:333-338): the pooled helper is only asked for its allele list and total count
+    if (alleles.size() == 1 || calls.empty()) return 0;
+    // the sample's calls: PR.getAlleleCalls(span, sample.getReadGroups()) — read group by read group, pileup order inside (PR:104-111)
+    std::vector<std::vector<const SpanCall*>> per_sample(samples.size());
+    for (size_t s = 0; s < samples.size(); s++)
+        for (int rg : samples[s].rgs)
+            for (size_t k = 0; k < calls.size(); k++) if (call_rg[k] == rg) per_sample[s].push_back(&calls[k]);
+    auto genotype_all = [&](const std::vector<std::string>& al, std::vector<SampleIndelCall>& out) {   // MSVD:674-693
+        out.clear();
+        int qs = 0;
+        for (size_t s = 0; s < samples.size(); s++) {
+            out.push_back(genotype_indel_sample(al, per_sample[s], opt.max_base_qs, opt.het_rate));
+            const SampleIndelCall& c = out.back();
+            const bool hom_ref = c.called.size() == 1 && c.called[0] == 0;
+            if (!c.called.empty() && !hom_ref && c.gq > qs) qs = c.gq;
+        }
+        return qs;
+    };
+    std::vector<SampleIndelCall> gc;
+    while (alleles.size() > 2) {   // discoverPopulationIndel, MSVD:623-630
+        bool same_len = true;
+        for (auto& a : alleles) if (a.size() != alleles[0].size()) same_len = false;
+        if (same_len) return 0;                                   // (no input STRs in discovery mode)
+        int qs = genotype_all(alleles, gc);
+        if (qs < opt.min_quality) return 0;
+        std::set<std::string> called = {alleles[0]};              // makeNewVariant, MSVD:642-656 (TreeSet)
+        for (auto& c : gc) for (int k : c.called) called.insert(alleles[k]);
+        if (called.size() == alleles.size()) break;
+        std::vector<std::string> na = {alleles[0]};               // SSVPL:346-359: reference first, then set order
+        for (auto& a : called) if (a != alleles[0]) na.push_back(a);
+        alleles.swap(na);
+    }
+    rec = PopIndelRecord();
+    rec.pos = pos;
+    rec.last = pos + span - 1;
+    rec.alleles = alleles;
+    rec.str = is_str;
+    rec.qs = genotype_all(alleles, rec.calls);                    // MSVD:532
+    if (rec.qs == 0 || rec.qs < opt.min_quality) return 1;        // MSVD:533
+    return 2;
+}
+
 }  // namespace host
 }  // namespace ngsep_b200

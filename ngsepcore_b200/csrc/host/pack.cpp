@@ -62,7 +62,8 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
 
 }  // namespace
 
-void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out) {
+void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups) {
+    out.group.clear();
     out.hdr.clear();
     out.payload.clear();
     out.max_span = 1;
@@ -81,6 +82,17 @@ void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
         for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, qoff, out);
         emit_record(r, r.st, true, r.cur_from, INT_MAX, qoff, out);
     }
+    if (with_groups) {   // one id per record (every version of a read carries the read's group)
+        out.group.reserve(out.hdr.size());
+        size_t k = 0;
+        for (size_t i = lo; i < hi; i++) {
+            const HostRead& r = reads[i];
+            const size_t n_rec = (r.closed.empty() && r.st.first == r.admit_first) ? 1 : r.closed.size() + 1;
+            const uint16_t g = (r.rg >= 0 && r.rg < 0xffff) ? (uint16_t)r.rg : (uint16_t)0xffff;
+            for (size_t v = 0; v < n_rec && k < out.hdr.size(); v++, k++) out.group.push_back(g);
+        }
+        out.group.resize(out.hdr.size(), (uint16_t)0xffff);
+    }
 }
 
 ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
@@ -91,7 +103,7 @@ ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
     t.n_words = payload.size();
     t.hdr = hdr.data();
     t.payload = payload.data();
-    t.sample = nullptr;
+    t.group = group.size() == hdr.size() && !group.empty() ? group.data() : nullptr;
     t.qual = qual.data();
     t.n_qual = qual.size();
     return t;

@@ -48,16 +48,46 @@ long jround(double x);
 int phred(double p);
 double fisher_pvalue(int a, int b, int c, int d);   // math/FisherExactTest.java:65-136
 
+// ---- sample axis: MultisampleVariantsDetector ------------------------------------------------------------------------
+// One sample = the read groups whose @RG SM names it (MSVD:492-516); rgs holds batch read-group indexes in the order
+// PileupRecord.getAlleleCalls(span, Set<String>) visits them (PR:104-111: the iteration order of Sample.readGroups, a HashSet).
+struct SampleDef { std::string id; int ploidy = 2; std::vector<int> rgs; };
+// MSVD.loadSamplesFromAlignmentHeaders over the @RG table of the input (ids, SM values; SM "" = absent, RAFR:188).
+std::vector<SampleDef> samples_from_read_groups(const std::vector<std::string>& rg_ids, const std::vector<std::string>& rg_samples, int ploidy);
+
+// One sample's genotype of a population indel / STR (VD.callIndel with the variant given, VD:265-361, through
+// SSVPL.genotypeVariantSample, SSVPL:361-391).
+struct SampleIndelCall {
+    std::vector<int> called;               // allele indexes, empty = undecided
+    int gq = 0, depth = 0;
+    bool has_report = false;               // VariantCallReport present (totalDepth > 0, VD:350)
+    std::vector<int> counts;               // per variant allele
+    std::vector<std::vector<double>> logc; // per allele pair
+};
+struct PopIndelRecord {
+    int pos = 0, last = 0;
+    std::vector<std::string> alleles;      // reference first
+    bool str = false;
+    int qs = 0;
+    std::vector<SampleIndelCall> calls;    // one per sample
+};
+// MSVD.discoverPopulationVariantWithSpan (MSVD:599-634) + genotypeVariant (MSVD:674-693) + the filter of MSVD:533.
+// Returns 0: no indel variant — the SNV fall-back applies and the device's decision for the position stands;
+//         1: an indel variant that is not reported (nothing is reported at the position);  2: rec holds the record.
+int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const std::vector<SampleDef>& samples,
+                             const IndelCallerOptions& opt, PopIndelRecord& rec);
+
 struct PackedTile {
     std::vector<ngsep_read_hdr> hdr;
     std::vector<uint32_t> payload;
+    std::vector<uint16_t> group;   // read-group id per record (0xFFFF = none), filled when pack_reads is given with_groups
     std::vector<uint8_t> qual;   // phred+33 bytes, one run per read (padded to 4), addressed by the records' qoff
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
     ngsep_tile view(int seq_idx, int first, int last) const;
 };
 // Packs reads[lo,hi) (all their versions) in pileup order.
-void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out);
+void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false);
 
 struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 that affect this path
     std::string sample_id = "Sample";
@@ -73,6 +103,7 @@ struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 
     int max_base_qs = 30;
     int min_quality = 40;
     bool call_embedded = false, csb = false;
+    double min_allele_depth_freq = 0;   // MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58)
     // device plumbing (not reference options)
     int device = 0;
     int tile_len = 0;          // 0 = one tile per sequence; otherwise region tiles of this many positions
@@ -91,6 +122,7 @@ struct RunStats {
 struct SeqPlan {
     std::vector<HostRead> reads;                 // pileup order, with versions
     std::vector<IndelRecord> indels;             // host-made indel / STR calls
+    std::vector<PopIndelRecord> pop_indels;      // the same for a multi-sample run
     std::set<int> suppressed;                    // positions whose device SNV decision must not be reported
     std::vector<std::pair<int, int>> embedded;   // closed intervals of embedded positions (SSVPL:150-151)
     int win_first = 1, win_last = 0, max_reach = 1, max_back = 0;
@@ -100,27 +132,53 @@ struct SeqPlan {
 class GpuSingleSampleVariantsDetector {
 public:
     explicit GpuSingleSampleVariantsDetector(const DetectorOptions& o);
-    ~GpuSingleSampleVariantsDetector();
+    virtual ~GpuSingleSampleVariantsDetector();
     void set_genome(const Genome* g);                 // setGenome, SSVD:161-163
     // Processes a coordinate-sorted batch; appends VCF text (header included when with_header) to out.
     int run(const BatchView& batch, std::string& out, bool with_header = true);
     const RunStats& stats() const { return stats_; }
     const std::string& error() const { return err_; }
     static std::string vcf_header(const std::string& sample_id, int ploidy, bool psp);   // VCFFileHeader.java:45-71,219-246
-private:
+protected:
     DetectorOptions opt_;
     const Genome* genome_ = nullptr;
     void* ctx_ = nullptr;
     std::vector<bool> ref_uploaded_;
     RunStats stats_;
     std::string err_;
-    int ensure_ctx();
-    int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out);
+    virtual int ensure_ctx();
+    virtual std::string header_text() const { return vcf_header(opt_.sample_id, opt_.ploidy, opt_.print_sample_ploidy); }
+    virtual int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out);
+    // discoverVariantWithSpan at an event with a reference span > 1 that is not embedded (SSVPL:257-273)
+    virtual void on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan, int& last_indel_end);
     int plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan);
     void tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const;
 public:
     int pack_sequence(const BatchView& b, int seq, PackedTile& tile, int& tile_first, int& tile_last);
 };
+
+// Drop-in for MultisampleVariantsDetector.run (MSVD:421-462) over in-memory alignments of all samples (one coordinate-sorted
+// stream: the single-file input, or the k-way merge of APG:212-289 done by the caller).
+class GpuMultisampleVariantsDetector : public GpuSingleSampleVariantsDetector {
+public:
+    GpuMultisampleVariantsDetector(const DetectorOptions& o, std::vector<SampleDef> samples, int n_read_groups);
+    static std::string vcf_header(const std::vector<SampleDef>& samples, bool psp);
+    const std::vector<SampleDef>& samples() const { return samples_; }
+protected:
+    std::vector<SampleDef> samples_;
+    int n_read_groups_;
+    int ensure_ctx() override;
+    std::string header_text() const override { return vcf_header(samples_, opt_.print_sample_ploidy); }
+    int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) override;
+    void on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan, int& last_indel_end) override;
+};
+
+std::string pop_snv_vcf_line(const ngsep_pop_site& site, const ngsep_sample_call* calls, int n_samples, const std::string& chrom, int ploidy, bool embedded);
+std::string pop_indel_vcf_line(const PopIndelRecord& r, const std::string& chrom, int ploidy);
+std::string english_fmt(double v);   // main/io/ParseUtils.java:29, DecimalFormat("##0.0#")
+// CalledGenomicVariantImpl.updateAllelesCopyNumberFromCounts (CalledGenomicVariantImpl.java:228-286)
+std::vector<int> impl_copy_numbers(const std::vector<int>& called, const std::vector<int>& allele_counts, bool has_counts, int ploidy, size_t n_alleles);
+void append_gt(std::string& s, const std::vector<int>& called, int ploidy);   // VCFFileWriter.java:171-199
 
 std::string snv_vcf_line(const ngsep_snv_call& c, const std::string& chrom, int ploidy, bool csb, bool embedded);
 std::string indel_vcf_line(const IndelRecord& r, const std::string& chrom, int ploidy);

@@ -24,7 +24,7 @@ void host_tables(double het_rate, double* t) {
     t[94] = std::log10(het_rate / 12);
 }
 
-std::string GpuSingleSampleVariantsDetector::vcf_header(const std::string& sample_id, int ploidy, bool psp) {
+static std::string header_lines() {
     static const char* lines[][5] = {
         {"INFO", "CNV", "1", "Integer", "Number of samples with CNVs around this variant"},
         {"INFO", "TA", "1", "String", "Variant annotation based on a gene model"},
@@ -53,12 +53,30 @@ std::string GpuSingleSampleVariantsDetector::vcf_header(const std::string& sampl
     std::ostringstream o;
     o << "##fileformat=VCFv4.2\n";
     for (auto& l : lines) o << "##" << l[0] << "=<ID=" << l[1] << ",Number=" << l[2] << ",Type=" << l[3] << ",Description=\"" << l[4] << "\">\n";
+    return o.str();
+}
+
+std::string GpuSingleSampleVariantsDetector::vcf_header(const std::string& sample_id, int ploidy, bool psp) {
+    std::ostringstream o;
+    o << header_lines();
     if (psp) o << "##SAMPLE=<ID=" << sample_id << ",PL=" << ploidy << ">\n";
     o << "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" << sample_id << "\n";
     return o.str();
 }
 
-static void append_gt(std::string& s, const std::vector<int>& called, int ploidy) {  // VCFFileWriter.java:171-199
+// MSVD:453-455: every sample is added to the header (samplesWithHeaderLine is a TreeMap; the samples already come in id order)
+std::string GpuMultisampleVariantsDetector::vcf_header(const std::vector<SampleDef>& samples, bool psp) {
+    std::ostringstream o;
+    o << header_lines();
+    if (psp) for (auto& s : samples) o << "##SAMPLE=<ID=" << s.id << ",PL=" << s.ploidy << ">\n";
+    o << "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO";
+    if (!samples.empty()) o << "\tFORMAT";
+    for (auto& s : samples) o << "\t" << s.id;
+    o << "\n";
+    return o.str();
+}
+
+void append_gt(std::string& s, const std::vector<int>& called, int ploidy) {  // VCFFileWriter.java:171-199
     if (called.empty()) { s += "."; if (ploidy > 1) s += "/."; }
     else if (called.size() == 1) { s += std::to_string(called[0]); if (ploidy > 1) { s += "/"; s += std::to_string(called[0]); } }
     else for (size_t i = 0; i < called.size(); i++) { if (i) s += "/"; s += std::to_string(called[i]); }

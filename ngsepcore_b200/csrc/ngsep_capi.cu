@@ -52,6 +52,9 @@ struct Slot {
     DevBuf<uint8_t> d_qual;
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
+    DevBuf<uint16_t> d_group;                 // multi-sample contexts: read-group id per record
+    DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
+    DevBuf<ngsep_sample_call> d_scalls;       //                        ... x n_samples sample calls
     DevBuf<int32_t> d_counts;
     TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches, followed by the 16-byte staging report
     bool report_read = false;                 // the staging report has been checked on the host
@@ -67,6 +70,7 @@ struct Slot {
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
+        d_group.release(); d_sites.release(); d_scalls.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
@@ -84,6 +88,11 @@ struct Ctx {
     cudaEvent_t b0 = nullptr, bm = nullptr, b1 = nullptr;   // around / between the kernels of the batched run
     ngsep_params params{};
     DevParams* d_prm = nullptr;
+    DevParams hp{};                           // host copy of *d_prm
+    // sample axis (ngsep_samples_set)
+    bool samples_set = false;
+    DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch;
+    int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
     std::vector<RefSeq> refs;
     std::vector<Slot*> slots;                 // slot 0 = first submit/fetch slot, 1.. = resident tiles
@@ -140,7 +149,7 @@ int clear_counts_dbg(Ctx* c, Slot* s) {
 // position with the EMIT_ALL test hook).  Overflow is detected after the run: the list grows and the run is repeated.
 void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
     const size_t len = (size_t)(s->tile.tile_last - s->tile.tile_first + 1);
-    if (c->params.flags & NGSEP_F_EMIT_ALL) cols += len + 1024;
+    if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) cols += len + 1024;   // sample axis: every candidate stays open
     else cols += len / 32 + 16384;
 }
 
@@ -184,7 +193,11 @@ int launch_slot(Ctx* c, Slot* s) {
     CK(cudaEventRecord(s->e0, c->stream), "event record");
     if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
-    if (s->tile.n_windows > 0) { launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream); s->launches = 2; }
+    if (s->tile.n_windows > 0) {
+        if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(c), c->d_prm, c->multi_grid, c->stream);
+        else launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream);
+        s->launches = 2;
+    }
     // the open-column counter is shared by every launch of the context: keep this tile's value with the tile
     CK(cudaMemcpyAsync((unsigned char*)s->d_counters + 20, c->d_meta + 8, 4, cudaMemcpyDeviceToDevice, c->stream), "open counter copy");
     CK(cudaEventRecord(s->e1, c->stream), "event record");
@@ -227,7 +240,10 @@ int launch_batch(Ctx* c) {
     CK(cudaEventRecord(c->b0, c->stream), "event record");
     if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, queue_view(c), c->cfg, c->b_grid, c->smem, c->stream);
     CK(cudaEventRecord(c->bm, c->stream), "event record");
-    if (c->b_windows > 0) launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
+    if (c->b_windows > 0) {
+        if (c->params.n_samples > 1) launch_genotype_multi(c->d_btiles.p, queue_view(c), c->d_prm, c->multi_grid, c->stream);
+        else launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
+    }
     CK(cudaEventRecord(c->b1, c->stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     for (size_t i = 1; i < n; i++) { c->slots[i]->launched = true; c->slots[i]->in_batch = true; c->slots[i]->launches = 0; }
@@ -256,7 +272,9 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
     if (t->n_reads > 0 && (!t->hdr || !t->payload || !t->qual)) return fail(c, NGSEP_EINVAL, "null tile buffers");
     if (t->n_qual > 0x3fffffff0ull) return fail(c, NGSEP_EINVAL, "tile qualities exceed 16 GiB");
-    if (c->params.n_samples > 1) return fail(c, NGSEP_EINVAL, "multi-sample tiles are not supported by this build");
+    const bool multi = c->params.n_samples > 1;
+    if (multi && !c->samples_set) return fail(c, NGSEP_ESTATE, "multi-sample context: call ngsep_samples_set before the first tile");
+    if (multi && t->n_reads > 0 && !t->group) return fail(c, NGSEP_EINVAL, "multi-sample context: ngsep_tile.group is required");
     if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
     CK(cudaSetDevice(c->device), "set device");
     const RefSeq& ref = c->refs[t->seq_idx];
@@ -269,6 +287,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
         if (need_p > s->d_pay.cap) { s->d_pay.release(); CK(cudaMalloc((void**)&s->d_pay.p, need_p * sizeof(uint32_t)), "payload alloc"); s->d_pay.cap = need_p; }
         if (need_q > s->d_qual.cap) { s->d_qual.release(); CK(cudaMalloc((void**)&s->d_qual.p, need_q), "quality alloc"); s->d_qual.cap = need_q; }
     }
+    if (multi) CK(s->d_group.reserve((size_t)t->n_reads + 16), "read-group alloc");
+    if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream), "read-group copy");
     if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
@@ -292,7 +312,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
         T = std::max(128, (T / 2) & ~127);
     TileDev& d = s->tile;
     d = TileDev{};
-    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.sample = nullptr; d.qual = s->d_qual.p;
+    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = s->d_qual.p;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
     d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
     d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
@@ -300,9 +320,16 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     d.win0 = (t->tile_first - 1) / T;
     d.n_windows = (t->n_reads == 0) ? 0 : ((t->tile_last - 1) / T - d.win0 + 1);
     CK(s->d_win.reserve((size_t)d.n_windows + 1), "window alloc");
-    size_t cap_calls = (size_t)(tile_len / 16) + 65536;
-    if (s->d_calls.cap < cap_calls) CK(s->d_calls.reserve(cap_calls), "calls alloc");
-    d.calls = s->d_calls.p; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_calls.cap;
+    if (multi) {   // population sites + n_samples sample calls each; grown (and the tile rerun) when a tile needs more
+        size_t cap_sites = std::max<size_t>(s->d_sites.cap, (size_t)(tile_len / 64) + 4096);
+        if (s->d_sites.cap < cap_sites) CK(s->d_sites.reserve(cap_sites), "site alloc");
+        CK(s->d_scalls.reserve(s->d_sites.cap * (size_t)c->params.n_samples), "sample call alloc");
+        d.pop_sites = s->d_sites.p; d.pop_calls = s->d_scalls.p; d.calls = nullptr; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_sites.cap;
+    } else {
+        size_t cap_calls = (size_t)(tile_len / 16) + 65536;
+        if (s->d_calls.cap < cap_calls) CK(s->d_calls.reserve(cap_calls), "calls alloc");
+        d.calls = s->d_calls.p; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_calls.cap;
+    }
     d.counts_dbg = nullptr;
     if (c->params.flags & NGSEP_F_EMIT_ALL) {
         CK(s->d_counts.reserve((size_t)tile_len * 5), "counts alloc");
@@ -320,8 +347,14 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     return NGSEP_OK;
 }
 
-int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
+// Single-sample contexts return ngsep_snv_call records in `out`; multi-sample contexts return population sites in
+// `sites` and their n_samples sample calls each in `scalls`.
+int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats,
+               ngsep_pop_site* sites = nullptr, ngsep_sample_call* scalls = nullptr) {
     if (!n_out) return fail(c, NGSEP_EINVAL, "null argument");
+    const bool multi = c->params.n_samples > 1;
+    if (multi && out) return fail(c, NGSEP_ESTATE, "multi-sample context: use ngsep_tile_fetch_pop / ngsep_resident_fetch_pop");
+    if (!multi && (sites || scalls)) return fail(c, NGSEP_ESTATE, "single-sample context: use ngsep_tile_fetch / ngsep_resident_fetch");
     if (!s->launched) return fail(c, NGSEP_ESTATE, "no tile in flight");
     CK(cudaSetDevice(c->device), "set device");
     struct Meta { unsigned long long ctr[2]; unsigned int n_calls, n_open, pad[2]; } meta;
@@ -344,8 +377,15 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         if (attempt == 3) return fail(c, NGSEP_EOVERFLOW, "call / column buffer overflow");
         if (grew && !s->in_batch) CK(cudaStreamSynchronize(c->stream), "drain before growing the open-column list");   // later tiles use the list too
         if (meta.n_calls > s->tile.cap_calls) {   // grow and rerun the staged tile
-            CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");
-            s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
+            if (!s->in_batch) CK(cudaStreamSynchronize(c->stream), "drain before growing the call buffers");
+            if (multi) {
+                CK(s->d_sites.reserve((size_t)meta.n_calls + 1024), "site realloc");
+                CK(s->d_scalls.reserve(s->d_sites.cap * (size_t)c->params.n_samples), "sample call realloc");
+                s->tile.pop_sites = s->d_sites.p; s->tile.pop_calls = s->d_scalls.p; s->tile.cap_calls = (unsigned)s->d_sites.cap;
+            } else {
+                CK(s->d_calls.reserve((size_t)meta.n_calls + 1024), "calls realloc");
+                s->tile.calls = s->d_calls.p; s->tile.cap_calls = (unsigned)s->d_calls.cap;
+            }
             CK(cudaMemcpy(s->d_tile, &s->tile, sizeof(TileDev), cudaMemcpyHostToDevice), "tile descriptor copy");
             c->batch_dirty = true;
         }
@@ -374,7 +414,11 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
     }
     *n_out = n;
     if (n > cap) return fail(c, NGSEP_EOVERFLOW, "caller's call buffer is too small; n_out holds the required capacity");
-    if (n > 0) {
+    if (n > 0 && multi) {
+        if (!sites || !scalls) return fail(c, NGSEP_EINVAL, "null output buffer");
+        CK(cudaMemcpy(sites, s->d_sites.p, (size_t)n * sizeof(ngsep_pop_site), cudaMemcpyDeviceToHost), "site copy");
+        CK(cudaMemcpy(scalls, s->d_scalls.p, (size_t)n * (size_t)c->params.n_samples * sizeof(ngsep_sample_call), cudaMemcpyDeviceToHost), "sample call copy");
+    } else if (n > 0) {
         if (!out) return fail(c, NGSEP_EINVAL, "null output buffer");
         CK(cudaMemcpy(out, s->d_calls.p, (size_t)n * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost), "calls copy");
     }
@@ -389,7 +433,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
 
 extern "C" {
 
-int ngsep_abi_version(void) { return 2000; }
+int ngsep_abi_version(void) { return 2001; }
 int ngsep_built_sm(void) { return 100; }
 
 const char* ngsep_last_error(void* ctx) {
@@ -402,6 +446,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     *out = nullptr;
     if (n_tables != NGSEP_N_TABLES) { g_global_err = "tables must hold NGSEP_N_TABLES doubles"; return NGSEP_EINVAL; }
     if (params->ploidy >= 3) { g_global_err = "ploidy >= 3 (pool algorithm, SSVPL:240-254) is not on the device path"; return NGSEP_EINVAL; }
+    if (params->n_samples < 1 || params->n_samples > 65535) { g_global_err = "n_samples must be in 1..65535"; return NGSEP_EINVAL; }
     if (params->max_base_qs < 4 || params->max_base_qs > 30) { g_global_err = "max_base_qs must be in 4..30 (CountsHelper tables have 31 rows)"; return NGSEP_EINVAL; }
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -481,6 +526,11 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
             }
         }
     }
+    hp.n_samples = params->n_samples;
+    hp.sample_min_quality = 40;   // the per-sample listener of MSVD.genotypeVariant is a fresh one: SSVPL.DEF_MIN_QUALITY (MSVD:676-678, SSVPL:50)
+    c->hp = hp;
+    c->multi_grid = c->sm_count * 8;
+    if (const char* s = std::getenv("NGSEP_MULTI_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 16) c->multi_grid = c->sm_count * v; }
     e = cudaMemcpy(c->d_prm, &hp, sizeof(hp), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { g_global_err = std::string("params upload: ") + cudaGetErrorString(e); delete c; return NGSEP_ECUDA; }
     *out = c;
@@ -496,6 +546,7 @@ int ngsep_ctx_destroy(void* ctx) {
     for (Slot* s : c->slots) { s->release(); delete s; }
     for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
     c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
+    c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -563,6 +614,68 @@ int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, 
     c->ring_tail = (c->ring_tail + 1) % c->ring.size();
     c->ring_count--;
     return rc;
+}
+
+int ngsep_samples_set(void* ctx, int32_t n_groups, const int32_t* sample_group_off, const uint16_t* sample_groups, double min_allele_depth_freq) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    const int n_samples = c->params.n_samples;
+    if (n_samples < 2) return fail(c, NGSEP_ESTATE, "ngsep_samples_set needs a context created with n_samples > 1");
+    if (!sample_group_off || !sample_groups || n_groups < 1 || n_groups > 65535) return fail(c, NGSEP_EINVAL, "bad read-group table");
+    if (!(min_allele_depth_freq >= 0.0 && min_allele_depth_freq <= 1.0)) return fail(c, NGSEP_EINVAL, "min_allele_depth_freq must be in [0,1]");
+    if (c->ring_count != 0) return fail(c, NGSEP_ESTATE, "tiles in flight");
+    int max_g = 0;
+    if (sample_group_off[0] != 0) return fail(c, NGSEP_EINVAL, "sample_group_off[0] must be 0");
+    for (int s = 0; s < n_samples; s++) {
+        const int n = sample_group_off[s + 1] - sample_group_off[s];
+        if (n < 0) return fail(c, NGSEP_EINVAL, "sample_group_off must be non-decreasing");
+        max_g = std::max(max_g, n);
+    }
+    const int total = sample_group_off[n_samples];
+    std::vector<char> seen((size_t)n_groups, 0);
+    for (int k = 0; k < total; k++) {
+        if (sample_groups[k] >= n_groups) return fail(c, NGSEP_EINVAL, "read-group id out of range");
+        if (seen[sample_groups[k]]) return fail(c, NGSEP_EINVAL, "a read group belongs to two samples (MSVD:500-502)");
+        seen[sample_groups[k]] = 1;
+    }
+    CK(cudaSetDevice(c->device), "set device");
+    CK(cudaStreamSynchronize(c->stream), "drain");
+    CK(c->d_sgo.reserve((size_t)n_samples + 1), "sample table alloc");
+    CK(c->d_sgroups.reserve((size_t)std::max(total, 1)), "sample table alloc");
+    CK(c->d_scratch.reserve((size_t)c->multi_grid * (size_t)n_samples), "scratch alloc");
+    CK(cudaMemcpy(c->d_sgo.p, sample_group_off, ((size_t)n_samples + 1) * sizeof(int), cudaMemcpyHostToDevice), "sample table copy");
+    if (total > 0) CK(cudaMemcpy(c->d_sgroups.p, sample_groups, (size_t)total * sizeof(uint16_t), cudaMemcpyHostToDevice), "sample table copy");
+    c->hp.n_groups = n_groups;
+    c->hp.max_groups_per_sample = max_g;
+    c->hp.min_allele_depth_freq = min_allele_depth_freq;
+    c->hp.sample_group_off = c->d_sgo.p;
+    c->hp.sample_groups = c->d_sgroups.p;
+    c->hp.scratch = c->d_scratch.p;
+    CK(cudaMemcpy(c->d_prm, &c->hp, sizeof(DevParams), cudaMemcpyHostToDevice), "params copy");
+    c->samples_set = true;
+    return NGSEP_OK;
+}
+
+int ngsep_tile_fetch_pop(void* ctx, ngsep_pop_site* sites, size_t cap_sites, size_t* n_sites, ngsep_sample_call* calls, int32_t* counts_dbg,
+                         ngsep_tile_stats* stats) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (c->params.n_samples < 2) return fail(c, NGSEP_ESTATE, "single-sample context: use ngsep_tile_fetch");
+    if (c->ring_count == 0) return fail(c, NGSEP_ESTATE, "no tile in flight");
+    Slot* s = c->ring[c->ring_tail];
+    int rc = fetch_slot(c, s, nullptr, cap_sites, n_sites, counts_dbg, stats, sites, calls);
+    if (rc == NGSEP_EOVERFLOW && n_sites && *n_sites > cap_sites) return rc;   // the tile stays at the tail: retry with room for *n_sites
+    c->ring_tail = (c->ring_tail + 1) % c->ring.size();
+    c->ring_count--;
+    return rc;
+}
+
+int ngsep_resident_fetch_pop(void* ctx, int slot, ngsep_pop_site* sites, size_t cap_sites, size_t* n_sites, ngsep_sample_call* calls,
+                             int32_t* counts_dbg, ngsep_tile_stats* stats) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (slot < 1 || (size_t)slot >= c->slots.size()) return fail(c, NGSEP_EINVAL, "bad slot");
+    return fetch_slot(c, c->slots[slot], nullptr, cap_sites, n_sites, counts_dbg, stats, sites, calls);
 }
 
 int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {

@@ -729,6 +729,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     uint32_t phase_bits = 0u;   // bit s = parity the next wait on stage s must see
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const bool multi = prm.n_samples > 1;
     const int n_stages = a.cfg.n_stages;
     const int stride = (int)gridDim.x;
 
@@ -927,6 +928,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 const uint32_t ref = (wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
                 int need = (m_up < (uint32_t)kSkipTable) ? min(s_kmin[m_up], kProofNoNeed) : kProofNoNeed;
                 if (need <= 0) need = 1;
+                if (multi) need = kProofNoNeed;   // sample axis: every candidate goes to k_genotype_columns_multi (no proof is attempted)
                 if (closed) need = 0;
                 s_list[ci] = (uint32_t)li | (ref << kProofRefShift) | ((uint32_t)need << kProofNeedShift) |
                              ((uint32_t)min((int)(ent >> kListShift), kProofMaxRec) << kProofRecShift);
@@ -1038,6 +1040,266 @@ __global__ void __launch_bounds__(256, 6) k_genotype_columns(const TileDev* __re
         }
         exact_column(R, d, g, pos, ref, ref_bad, i_lo, i_hi, lane);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MultisampleVariantsDetector: the open columns of a multi-sample context, one CTA per column
+// ------------------------------------------------------------------------------------------------------------
+// MSVD.onPileup for a span-1 position (MSVD:521-537).  Phase A: the CTA resolves every covering record in pileup order
+// (lane_eval = PR.getAlleleCalls(1) + the quality rules of CH.updateCounts) into shared memory, chunk by chunk, and sums
+// the POOLED counts (all reads, any read group: discoverPopulationSNV, MSVD:586-587).  Phase B: one thread per sample
+// walks the chunk in order and adds the records of ITS read groups — in the order PR.getAlleleCalls(span, Set) visits
+// the groups (PR:104-111) — to its counts and its 10 distinct log-likelihoods, in fp64 (CH:231-249), so every sample's
+// logConditionalProbs are bit-identical to the Java doubles.  Phase C: createSNVVariantPool (SSVPL:297-332), the allele
+// refinement loop (MSVD:590-595, 642-656), per-sample VD.genotypeSNV (VD:21-97) with the sample-level minQuality of
+// SSVPL:388, QUAL = best GQ of the decided non-hom-ref samples (MSVD:685-691), the filter of MSVD:533.
+constexpr int kMultiChunk = 1024;
+
+struct SamplePost { double hom[4], het[6]; };   // posteriors: [i][i], and ONE ordered event of (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+
+__device__ __forceinline__ int pair_index(int lo, int hi) { return (lo == 0) ? hi - 1 : ((lo == 1) ? hi + 1 : 5); }   // into het[6]
+
+// CH.getPosteriorProbabilities (CH:410-443) + calculatePosteriorProbabilities (CH:472-495): 16 ordered events, the sum in
+// the reference's order.  L: [i][i] for i = 0..3, then the six pairs.
+__device__ __forceinline__ void sample_posteriors(const double* L, double lp_hom, double lp_het, SamplePost& P) {
+    double ev[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ev[4 * i] = L[i] + lp_hom;
+        int k = 4 * i + 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j != i) { ev[k++] = L[4 + pair_index(min(i, j), max(i, j))] + lp_het; }
+    }
+    double mx = ev[0];
+#pragma unroll
+    for (int k = 1; k < 16; k++) mx = fmax(mx, ev[k]);
+    double total = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) { const double e = ev[k] - mx; ev[k] = (e < -20.0) ? 0.0 : exp10(e); total += ev[k]; }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        P.hom[i] = ev[4 * i] / total;
+#pragma unroll
+        for (int j = i + 1; j < 4; j++) P.het[pair_index(i, j)] = ev[4 * i + j] / total;   // event (i,j), j > i, sits at 4i + j
+    }
+}
+
+// One sample's genotype for the allele list A (base indexes, reference first).  Returns g0 | g1 << 8 | gq << 16 with
+// g = 0xff for "undecided".
+__device__ __forceinline__ uint32_t sample_genotype(const SamplePost& P, int depth, const int* A, int nA, int sample_min_quality) {
+    if (depth == 0) return 0xffffu;                                    // VD:23-27: undecided, no quality
+    int g0, g1, gq;
+    if (nA == 2) {                                                     // variant instanceof SNV, VD:33-60
+        const int r = A[0], a = A[1];
+        double pmax = P.hom[r];
+        g0 = g1 = 0;
+        if (P.hom[a] > pmax + 0.01) { pmax = P.hom[a]; g0 = g1 = 1; }
+        const double ph = P.het[pair_index(min(r, a), max(r, a))];
+        const double phet = ph + ph;                                   // postProbs[r][a] + postProbs[a][r]: equal doubles
+        if (phet > pmax + 0.01) { pmax = phet; g0 = 0; g1 = 1; }
+        gq = dev_phred(1.0 - pmax);
+        if (gq == 0) return 0xffffu;                                   // VD:50
+    } else {                                                           // VD:61-95: arg-max over the sub-matrix, from (0,0)
+        g0 = g1 = 0;
+        double pmax = P.hom[A[0]];
+        for (int i = 0; i < nA; i++)
+            for (int j = i; j < nA; j++) {
+                double gp;
+                if (i == j) gp = P.hom[A[i]];
+                else { const double ph = P.het[pair_index(min(A[i], A[j]), max(A[i], A[j]))]; gp = ph + ph; }
+                if (gp > pmax + 0.01) { pmax = gp; g0 = i; g1 = j; }
+            }
+        double max_p;
+        if (g0 == g1) max_p = P.hom[A[g0]];
+        else { const double ph = P.het[pair_index(min(A[g0], A[g1]), max(A[g0], A[g1]))]; max_p = ph + ph; }
+        gq = dev_phred(1.0 - max_p);
+    }
+    if (sample_min_quality > gq) return 0xffffu;                       // SSVPL:388 makeUndecided
+    return (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)gq << 16);
+}
+
+__global__ void __launch_bounds__(kMultiThreads, 4) k_genotype_columns_multi(const TileDev* __restrict__ tiles, const ColumnQueue cq,
+                                                                             const DevParams* __restrict__ gprm) {
+    __shared__ double s_tab[96];
+    __shared__ uint32_t s_code[kMultiChunk];
+    __shared__ uint16_t s_grp[kMultiChunk];
+    __shared__ int s_pool[5];            // pooled A, C, G, T counts and totalCount
+    __shared__ int s_red[4];             // [0] called-allele mask, [1] best quality, [2] output slot
+    const DevParams& prm = *gprm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < NGSEP_N_TABLES; i += kMultiThreads) s_tab[i] = prm.tables[i];
+    const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
+    const int n_samples = prm.n_samples, max_qs = prm.max_base_qs;
+    const int n_batches = (n_samples + kMultiThreads - 1) / kMultiThreads;
+    ngsep_sample_call* scratch = prm.scratch + (size_t)blockIdx.x * (size_t)n_samples;
+    const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
+    __syncthreads();
+    for (unsigned int t = blockIdx.x; t < n_open; t += gridDim.x) {
+        __syncthreads();   // every `continue` below is uniform over the CTA; the previous column's shared state is free from here on
+        const uint4 oc = cq.open[t];   // tile, position, first record, number of records
+        const TileDev& d = tiles[oc.x];
+        const int pos = (int)oc.y;
+        const int64_t gi = (int64_t)pos - 1;
+        if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198
+        const bool ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
+        const int ref = (int)((d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u);
+        Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
+        if (oc.w >= kOpenSearch) {
+            i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+            i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
+        }
+        if (tid < 5) s_pool[tid] = 0;
+        if (tid < 4) s_red[tid] = 0;
+        // ---- phases A + B ------------------------------------------------------------------------------------------
+        for (int batch = 0; batch < n_batches; batch++) {
+            const int smp = batch * kMultiThreads + tid;
+            double L[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) L[k] = 0.0;
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, depth = 0;
+            const int g_lo = (smp < n_samples) ? prm.sample_group_off[smp] : 0;
+            const int g_n = (smp < n_samples) ? prm.sample_group_off[smp + 1] - g_lo : 0;
+            for (int pass = 0; pass < prm.max_groups_per_sample; pass++) {
+                const int my_group = (pass < g_n) ? (int)prm.sample_groups[g_lo + pass] : -1;
+                for (int base = i_lo; base < i_hi; base += kMultiChunk) {
+                    const int n_chunk = min(kMultiChunk, i_hi - base);
+                    __syncthreads();   // the previous chunk has been consumed
+                    int p0 = 0, p1 = 0, p2 = 0, p3 = 0, pd = 0;
+                    for (int k = tid; k < n_chunk; k += kMultiThreads) {
+                        const ngsep_read_hdr h = R.header(base + k);
+                        const uint32_t code = lane_eval(h, R.payload(h), d.qual, pos, max_qs);
+                        s_code[k] = code;
+                        s_grp[k] = d.group[base + k];
+                        if (code & kCodeCall) pd++;
+                        if (code & kCodeCounted) { const int b = (int)(code & 3u); p0 += (b == 0); p1 += (b == 1); p2 += (b == 2); p3 += (b == 3); }
+                    }
+                    if (batch == 0 && pass == 0) {
+                        for (int o = 16; o; o >>= 1) {
+                            p0 += __shfl_xor_sync(kFull, p0, o); p1 += __shfl_xor_sync(kFull, p1, o); p2 += __shfl_xor_sync(kFull, p2, o);
+                            p3 += __shfl_xor_sync(kFull, p3, o); pd += __shfl_xor_sync(kFull, pd, o);
+                        }
+                        if (lane == 0) { atomicAdd(&s_pool[0], p0); atomicAdd(&s_pool[1], p1); atomicAdd(&s_pool[2], p2); atomicAdd(&s_pool[3], p3); atomicAdd(&s_pool[4], pd); }
+                    }
+                    __syncthreads();
+                    if (my_group >= 0) {
+                        for (int k = 0; k < n_chunk; k++) {
+                            if ((int)s_grp[k] != my_group) continue;
+                            const uint32_t code = s_code[k];
+                            if (code & kCodeCall) depth++;                                   // CH:210
+                            if (!(code & kCodeCounted)) continue;
+                            const int b = (int)(code & 3u), q = (int)((code >> 2) & 31u);
+                            c0 += (b == 0); c1 += (b == 1); c2 += (b == 2); c3 += (b == 3);   // CH:223
+                            const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) L[i] += (b == i) ? ta : tb;           // CH:231-235
+                            L[4] += (b == 0 || b == 1) ? tc : tb;                             // CH:236-249 with f == g == 250
+                            L[5] += (b == 0 || b == 2) ? tc : tb;
+                            L[6] += (b == 0 || b == 3) ? tc : tb;
+                            L[7] += (b == 1 || b == 2) ? tc : tb;
+                            L[8] += (b == 1 || b == 3) ? tc : tb;
+                            L[9] += (b == 2 || b == 3) ? tc : tb;
+                        }
+                    }
+                }
+            }
+            if (smp < n_samples) {
+                ngsep_sample_call& o = scratch[smp];
+                o.count[0] = c0; o.count[1] = c1; o.count[2] = c2; o.count[3] = c3; o.depth = depth;
+                o.gq = 0; o.g0 = -1; o.g1 = -1;
+#pragma unroll
+                for (int k = 0; k < 10; k++) o.logcond[k] = L[k];
+            }
+        }
+        __syncthreads();
+        // ---- phase C ---------------------------------------------------------------------------------------------------
+        const int pc[4] = {s_pool[0], s_pool[1], s_pool[2], s_pool[3]};
+        const int pool_depth = s_pool[4];
+        if (emit_all && d.counts_dbg && tid == 0) {
+            int32_t* o = d.counts_dbg + (int64_t)(pos - d.tile_first) * 5;
+            o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = pc[3]; o[4] = pool_depth;
+        }
+        if (ref_bad || pool_depth == 0) continue;                                  // SSVPL:298-305 (uniform over the CTA)
+        // createSNVVariantPool (SSVPL:306-330): the reference allele, then every other base with count >= minCount
+        int A[4], nA = 1;
+        {
+            const int sum = pc[0] + pc[1] + pc[2] + pc[3];
+            const double min_count = fmax(1.0, prm.min_allele_depth_freq * (double)sum);
+            A[0] = ref; A[1] = A[2] = A[3] = 0;
+            for (int b = 0; b < 4; b++) if (b != ref && (double)pc[b] >= min_count) A[nA++] = b;
+        }
+        if (nA < 2) continue;
+        const int nA0 = nA;
+        const double lp_hom = s_tab[93], lp_het = s_tab[94];
+        int qs = 0;
+        bool final_pass = nA <= 2;   // the refinement loop runs only for more than two alleles (MSVD:590)
+        for (;;) {
+            // genotypeVariant (MSVD:674-693): every sample, with the current allele list
+            unsigned int mask = 0u;
+            int best = 0;
+            for (int smp = tid; smp < n_samples; smp += kMultiThreads) {
+                ngsep_sample_call& sc = scratch[smp];
+                double L[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++) L[k] = sc.logcond[k];
+                uint32_t g = 0xffffu;
+                if (sc.depth > 0) {
+                    SamplePost P;
+                    sample_posteriors(L, lp_hom, lp_het, P);
+                    g = sample_genotype(P, sc.depth, A, nA, prm.sample_min_quality);
+                }
+                const int g0 = (int)(g & 0xffu), g1 = (int)((g >> 8) & 0xffu), gq = (int)(g >> 16);
+                if (g0 != 0xff) {
+                    mask |= (1u << A[g0]) | (1u << A[g1]);                          // getCalledAlleles
+                    if (!(g0 == 0 && g1 == 0) && gq > best) best = gq;               // MSVD:685-687
+                }
+                if (final_pass) { sc.gq = (int16_t)gq; sc.g0 = (g0 == 0xff) ? (int8_t)-1 : (int8_t)g0; sc.g1 = (g1 == 0xff) ? (int8_t)-1 : (int8_t)g1; }
+            }
+            for (int o = 16; o; o >>= 1) { mask |= __shfl_xor_sync(kFull, mask, o); best = max(best, __shfl_xor_sync(kFull, best, o)); }
+            if (lane == 0) { atomicOr((unsigned int*)&s_red[0], mask); atomicMax(&s_red[1], best); }
+            __syncthreads();
+            const unsigned int called = (unsigned int)s_red[0] | (1u << ref);
+            qs = s_red[1];
+            __syncthreads();
+            if (tid == 0) { s_red[0] = 0; s_red[1] = 0; }
+            __syncthreads();
+            if (final_pass) break;
+            // makeNewVariant (MSVD:642-656): reference + called alleles (TreeSet order = base order); unchanged size ends the loop
+            if (__popc(called & 0xfu) != nA) {
+                int B[4] = {ref, 0, 0, 0}, nB = 1;
+                for (int b = 0; b < 4; b++) if (b != ref && ((called >> b) & 1u)) B[nB++] = b;
+                nA = nB;
+                for (int k = 0; k < 4; k++) A[k] = B[k];
+                if (nA <= 2) final_pass = true;
+            } else final_pass = true;
+            if (nA < 2) break;
+        }
+        // a variant reduced to its reference allele is not an SNV any more; every sample is then called homozygous
+        // reference or left undecided, so variantQS == 0 and MSVD:533 drops it
+        if (nA < 2) continue;
+        if (qs == 0 || qs < prm.min_quality) continue;                              // MSVD:533
+        if (tid == 0) s_red[2] = (int)atomicAdd(d.n_calls, 1u);
+        __syncthreads();
+        const unsigned int slot = (unsigned int)s_red[2];
+        if (slot < d.cap_calls) {   // else: the host sees n_calls > cap, grows the buffers and reruns the tile
+            if (tid == 0) {
+                ngsep_pop_site& o = d.pop_sites[slot];
+                o.seq_idx = d.seq_idx; o.pos = pos;
+                o.count[0] = pc[0]; o.count[1] = pc[1]; o.count[2] = pc[2]; o.count[3] = pc[3]; o.depth = pool_depth;
+                o.qs = (int16_t)qs; o.ref = (int8_t)ref; o.n_alleles = (int8_t)nA; o.n_alleles0 = (int8_t)nA0;
+                for (int k = 0; k < 4; k++) o.allele[k] = (int8_t)((k < nA) ? A[k] : -1);
+            }
+            const uint2* src = (const uint2*)scratch;
+            uint2* dst = (uint2*)(d.pop_calls + (size_t)slot * (size_t)n_samples);
+            const int n_words = n_samples * (int)(sizeof(ngsep_sample_call) / 8);
+            for (int k = tid; k < n_words; k += kMultiThreads) dst[k] = src[k];
+        }
+    }
+}
+
+void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+    k_genotype_columns_multi<<<grid, kMultiThreads, 0, s>>>(d_tiles, cq, dprm);
 }
 
 // ------------------------------------------------------------------------------------------------------------

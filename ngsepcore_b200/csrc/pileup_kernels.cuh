@@ -40,7 +40,7 @@ struct WinRange {
 struct TileDev {
     const ngsep_read_hdr* hdr;   // [n_reads + 1], sentinel at n_reads carries off = n_words, first = INT_MAX
     const uint32_t* payload;
-    const uint16_t* sample;
+    const uint16_t* group;       // [n_reads] read-group id per record (multi-sample contexts), else null
     const uint8_t* qual;         // phred+33 bytes, addressed through the records' qoff (only k_genotype_columns reads them)
     int n_reads, max_span, max_back;
     int tile_first, tile_last, seq_idx;
@@ -51,6 +51,7 @@ struct TileDev {
     int T;                       // window length in positions (multiple of 128, <= the launch's layout window)
     int win0, n_windows;         // first absolute window index of the tile, number of windows
     ngsep_snv_call* calls; unsigned int* n_calls; unsigned int cap_calls;
+    ngsep_pop_site* pop_sites; ngsep_sample_call* pop_calls;   // multi-sample contexts: cap_calls sites x n_samples sample calls
     int32_t* counts_dbg;         // [tile_len][5] or null
     unsigned long long* counters;// [0] covered positions, [1] candidates
     const unsigned int* report;  // staging check of the tile (k_check_headers): [0] error bits
@@ -63,6 +64,13 @@ struct DevParams {
     int k_min[16];               // k_min[m]: with m counted non-reference bases, k >= k_min[m] counted reference bases
                                  // prove P(ref,ref) > 1/2; INT_MAX when no k suffices
     double tables[NGSEP_N_TABLES];
+    // sample axis (MultisampleVariantsDetector); n_samples == 1: everything below is unused
+    int n_samples, n_groups, max_groups_per_sample;
+    int sample_min_quality;              // minQuality of the fresh per-sample listener: always 40 (MSVD:676-678, SSVPL:50)
+    double min_allele_depth_freq;        // MSVD:58
+    const int* sample_group_off;         // [n_samples + 1]
+    const uint16_t* sample_groups;       // read groups of each sample, in the order PR.getAlleleCalls(span, Set) visits them
+    ngsep_sample_call* scratch;          // [multi grid][n_samples] per-CTA work area of k_genotype_columns_multi
 };
 
 // Open columns = the positions the window kernel could not close (screen + hom-ref proof), handed to k_genotype_columns:
@@ -89,6 +97,8 @@ void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, u
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
+void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
+constexpr int kMultiThreads = 128;
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
 }  // namespace ngsep_b200

@@ -17,7 +17,7 @@ from .simulate import AlignmentBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
-EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
+EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_msvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
            "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free"]
 
 
@@ -54,6 +54,8 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     lib.ngsep_detector_options_default.argtypes = [C.POINTER(DetectorOptions)]
     lib.ngsep_ssvd_create.argtypes = [C.POINTER(DetectorOptions), C.POINTER(C.c_void_p)]
+    lib.ngsep_msvd_create.argtypes = [C.POINTER(DetectorOptions), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_double,
+                                      C.POINTER(C.c_void_p)]
     lib.ngsep_ssvd_destroy.argtypes = [C.c_void_p]
     lib.ngsep_ssvd_error.argtypes = [C.c_void_p]
     lib.ngsep_ssvd_error.restype = C.c_char_p
@@ -128,9 +130,12 @@ class Detector:
         o.max_base_qs, o.min_quality, o.call_embedded_snvs, o.calc_strand_bias = maxBaseQS, minQuality, int(embeddedSNVs), int(csb)
         o.device, o.tile_len, o.shard, o.n_shards, o.host_only = device, tile_len, shard, n_shards, int(host_only)
         self.h = C.c_void_p()
+        self._create(o)
+        self._keep = []
+
+    def _create(self, o: DetectorOptions) -> None:
         if self.lib.ngsep_ssvd_create(C.byref(o), C.byref(self.h)) != 0:
             raise NgsepError("ngsep_ssvd_create failed")
-        self._keep = []
 
     def set_genome(self, genome: dict) -> None:
         names = [n.encode() for n in genome]
@@ -181,3 +186,24 @@ class Detector:
             self.close()
         except Exception:
             pass
+
+
+class MultisampleDetector(Detector):
+    """GPU drop-in for MultisampleVariantsDetector (reference: src/ngsep/discovery/MultisampleVariantsDetector.java, run() :421-462;
+    option ids of main/CommandsDescriptor.xml:480-563).  ``read_groups`` is the @RG table of the input(s) as (ID, SM or None)
+    pairs; ``AlignmentBatch.rg`` indexes it.  Samples and their VCF column order follow MSVD.loadSamplesFromAlignmentHeaders."""
+
+    def __init__(self, read_groups, minAlleleDepthFrequency: float = 0.0, **options):
+        self._rg = [(i.encode(), (s or "").encode()) for i, s in read_groups]
+        self._madf = float(minAlleleDepthFrequency)
+        for k in ("sampleId", "csb"):
+            if k in options:
+                raise TypeError(f"MultisampleVariantsDetector has no option -{k}")
+        super().__init__(**options)
+
+    def _create(self, o: DetectorOptions) -> None:
+        n = len(self._rg)
+        ids = (C.c_char_p * n)(*[r[0] for r in self._rg])
+        sms = (C.c_char_p * n)(*[r[1] for r in self._rg])
+        if self.lib.ngsep_msvd_create(C.byref(o), n, ids, sms, self._madf, C.byref(self.h)) != 0:
+            raise NgsepError("ngsep_msvd_create failed")

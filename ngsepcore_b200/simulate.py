@@ -232,8 +232,13 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
              snv_rate: float = 1e-3, indel_rate: float = 1e-4, error_rate: float = 0.002, paired: bool = True,
              frag_mean: float = 350.0, frag_sd: float = 35.0, low_mapq_frac: float = 0.02, n_frac: float = 0.0,
              lower_frac: float = 0.0, indel_jitter: float = 0.3, ungapped_end_bp: int = 6, n_read_groups: int = 1,
-             genome=None, starts_per_pos_cap: int | None = None):
-    """Returns (genome dict name->uint8 ASCII, AlignmentBatch, truth dict name->[Variant])."""
+             genome=None, starts_per_pos_cap: int | None = None, variants_override: dict | None = None,
+             tag_sites: dict | None = None):
+    """Returns (genome dict name->uint8 ASCII, AlignmentBatch, truth dict name->[Variant]).
+
+    variants_override: name -> [Variant] (each with ``_hap`` set) used instead of planting (population runs).
+    tag_sites: name -> (ref_starts int64[], neg bool[]): GBS-style single-end reads, Poisson(depth) reads per tag, all
+    starting at the tag (README.txt:588-596 of the reference describes this data type)."""
     if contigs is None:
         contigs = YEAST_CONTIGS
     if genome is None:
@@ -246,9 +251,12 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
     per_contig = []
     for ci, (name, length) in enumerate(contigs):
         ref = genome[name]
-        variants = plant_variants(ref, rng_v, snv_rate, indel_rate)
-        for v in variants:
-            v._hap = int(rng_v.integers(0, 2))
+        if variants_override is not None:
+            variants = variants_override[name]
+        else:
+            variants = plant_variants(ref, rng_v, snv_rate, indel_rate)
+            for v in variants:
+                v._hap = int(rng_v.integers(0, 2))
         truth[name] = variants
         haps = [_build_haplotype(ref, variants, h, rng_v) for h in (0, 1)]
         n_reads = int(depth * length / read_len)
@@ -265,6 +273,20 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
             fl_fwd = np.where(swap, 0x1 | 0x2 | 0x20 | 0x40, 0x1 | 0x2 | 0x20 | 0x80)
             fl_rev = np.where(swap, 0x1 | 0x2 | 0x10 | 0x80, 0x1 | 0x2 | 0x10 | 0x40)
             flags = np.concatenate([fl_fwd, fl_rev]).astype(np.uint16)
+        elif tag_sites is not None:
+            t_start, t_neg = tag_sites[name]
+            per_tag = rng_r.poisson(depth, size=len(t_start))
+            tag_of = np.repeat(np.arange(len(t_start)), per_tag)
+            hap_of = rng_r.integers(0, 2, size=len(tag_of))
+            starts = np.zeros(len(tag_of), np.int64)
+            for h in (0, 1):
+                seq_h, mp_h = haps[h]
+                ff = np.maximum.accumulate(mp_h)          # inserted bases take the position before them
+                hs = np.searchsorted(ff, t_start, side="left")
+                hs = np.minimum(hs, len(seq_h) - read_len)
+                sel = hap_of == h
+                starts[sel] = hs[tag_of[sel]]
+            flags = np.where(t_neg[tag_of], 0x10, 0).astype(np.uint16)
         else:
             hap_of = rng_r.integers(0, 2, size=n_reads)
             hlen = np.array([len(haps[0][0]), len(haps[1][0])])[hap_of]
@@ -368,6 +390,68 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
     batch = AlignmentBatch(names, lens, seq_idx, first, flags, mapq, rg, np.full(tot, -1, np.int16), cigar_off, cigar,
                            base_off, bases, quals, rg_names, list(rg_names))
     return genome, batch, truth
+
+
+def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: str = "wgs", n_tags: int = 200,
+                        seeds=(1021, 2022, 3023), read_len: int = 100, rgs_per_sample: int = 1, no_rg_frac: float = 0.0,
+                        snv_rate: float = 1e-3, indel_rate: float = 1e-4, **kw):
+    """Population workload for MultisampleVariantsDetector (BASELINE configs[3]): shared planted sites, per-sample
+    genotypes drawn from a population allele frequency ~ Beta(0.2, 0.2); mode "wgs" = uniform single-end reads at `depth`
+    per sample, "gbs" = `n_tags` tag loci per contig with Poisson(depth) identical-start reads per sample and tag.
+    All samples' records are returned as ONE coordinate-sorted batch (one SAM/BAM with one @RG per sample and read group:
+    the single-file input of MSVD, APG:216-219); ties keep sample order.  Returns (genome, batch, truth)."""
+    genome = make_genome(contigs, gc=kw.pop("gc", 0.38), seed=seeds[0], n_frac=kw.pop("n_frac", 0.0), lower_frac=kw.pop("lower_frac", 0.0))
+    rng_v = np.random.default_rng(seeds[1])
+    shared, af, tags = {}, {}, {}
+    for name, length in contigs:
+        shared[name] = plant_variants(genome[name], rng_v, snv_rate, indel_rate)
+        af[name] = rng_v.beta(0.2, 0.2, size=len(shared[name]))
+        if mode == "gbs":
+            st = np.sort(rng_v.integers(1, max(2, length - read_len - 20), size=n_tags)).astype(np.int64)
+            tags[name] = (st, rng_v.random(n_tags) < 0.5)
+    batches = []
+    for smp in range(n_samples):
+        ov = {}
+        for name, _ in contigs:
+            vs = []
+            for v, f in zip(shared[name], af[name]):
+                a0, a1 = rng_v.random() < f, rng_v.random() < f
+                if not (a0 or a1):
+                    continue
+                w = Variant(v.pos, v.kind, v.length, v.alt, bool(a0 and a1))
+                w._hap = 0 if a0 else 1
+                vs.append(w)
+            ov[name] = vs
+        _, b, _ = simulate(contigs=contigs, depth=depth, read_len=read_len, seeds=(seeds[0], seeds[1], seeds[2] + smp), paired=False,
+                           genome=genome, variants_override=ov, tag_sites=tags if mode == "gbs" else None, n_read_groups=1, **kw)
+        rng_s = np.random.default_rng(seeds[2] + 7919 * (smp + 1))
+        rg = (smp * rgs_per_sample + rng_s.integers(0, rgs_per_sample, size=b.n)).astype(np.int16)
+        if no_rg_frac > 0:
+            rg[rng_s.random(b.n) < no_rg_frac] = -1
+        b.rg = rg
+        batches.append(b)
+    names = [c[0] for c in contigs]
+    lens = [c[1] for c in contigs]
+    seq_idx = np.concatenate([b.seq_idx for b in batches])
+    first = np.concatenate([b.first for b in batches])
+    order = np.lexsort((first, seq_idx))      # stable: ties keep sample, then in-sample order
+    cl = np.concatenate([np.diff(b.cigar_off) for b in batches])
+    bl = np.concatenate([np.diff(b.base_off) for b in batches])
+    c_start = np.concatenate([[0], np.cumsum(cl)])[:-1]
+    b_start = np.concatenate([[0], np.cumsum(bl)])[:-1]
+    cigar = np.concatenate([b.cigar for b in batches])
+    bases = np.concatenate([b.bases for b in batches])
+    quals = np.concatenate([b.quals for b in batches])
+    cl_o, bl_o = cl[order], bl[order]
+    co = np.zeros(len(order) + 1, np.int64); np.cumsum(cl_o, out=co[1:])
+    bo = np.zeros(len(order) + 1, np.int64); np.cumsum(bl_o, out=bo[1:])
+    rg_names = [f"RG{i}" for i in range(n_samples * rgs_per_sample)]
+    rg_samples = [f"S{i // rgs_per_sample:03d}" for i in range(n_samples * rgs_per_sample)]
+    batch = AlignmentBatch(names, lens, seq_idx[order], first[order], np.concatenate([b.flags for b in batches])[order],
+                           np.concatenate([b.mapq for b in batches])[order], np.concatenate([b.rg for b in batches])[order],
+                           np.full(len(order), -1, np.int16), co, _gather_ranges(cigar, c_start[order], cl_o), bo,
+                           _gather_ranges(bases, b_start[order], bl_o), _gather_ranges(quals, b_start[order], bl_o), rg_names, rg_samples)
+    return genome, batch, {"variants": shared, "af": af}
 
 
 _OPC = "HDIMPNSX"

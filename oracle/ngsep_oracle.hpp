@@ -309,6 +309,7 @@ struct DetectorOptions {
     bool ignore_lower = false; int max_alns_per_start = 5; bool non_unique_primary = false, secondary = false;
     int ignore5 = 0, ignore3 = 0; double het_rate = 0.001; bool het_modified = false; int max_base_qs = 30;
     short min_quality = 40; bool call_embedded = false, csb = false;
+    double min_allele_depth_freq = 0;   // MSVD:58 (setter only, no CLI option id; oracle switch --minAlleleDepthFrequency)
 };
 struct SingleSampleVariantsDetector : PileupListener {
     DetectorOptions opt;
@@ -326,6 +327,41 @@ struct SingleSampleVariantsDetector : PileupListener {
     void on_sequence_end(const std::string& seq) override;        // SSVD:933-968,1026-1032
 private:
     AlignmentReader reader; bool stopped = false;
+};
+
+// ---- discovery/MultisampleVariantsDetector.java (oracle/ngsep_oracle_multi.cpp) ----------------------------------
+std::vector<std::string> java_string_hashset_order(const std::vector<std::string>& keys_in_insertion_order);
+bool load_samples_from_headers(const std::vector<std::vector<std::string>>& header_lines_per_file, short ploidy, std::vector<Sample>& out, std::string& err);  // MSVD:492-516
+bool create_snv_variant_pool(const PileupRecord& p, const CountsHelper& h, char reference, double min_allele_depth_freq, GenomicVariant& out);  // SSVPL:297-332
+std::string english_fmt(double v);   // main/io/ParseUtils.java:29
+void print_genotype_field(std::ostream& out, CalledVariant& call, bool snv_format, short ploidy);  // VCFFileWriter.java:159-308
+void print_vcf_record_population(std::ostream& out, const GenomicVariant& v, std::vector<CalledVariant>& calls, const std::vector<Sample>& samples);  // VCFRecord.java:277-301
+
+struct MultisampleVariantsDetector : PileupListener {
+    DetectorOptions opt;                       // MSVD option set (XML:480-563); sample_id / csb unused
+    double min_allele_depth_freq = 0;          // MSVD:58 (no CLI option)
+    const ReferenceGenome* genome = nullptr;
+    std::ostream* out = nullptr;
+    std::vector<Sample> samples;               // MSVD:492-516 order
+    AlignmentsPileupGenerator gen;
+    IndelRealignerPileupListener realigner;
+    int last_indel_end = 0;
+    long n_records = 0, n_input_records = 0;
+    std::vector<std::array<int, 6>>* counts_dump = nullptr;   // test hook: pooled pos,A,C,G,T,DP wherever discoverPopulationSNV ran
+    void begin();                                          // MSVD:421-456
+    void add_alignment(const ReadPtr& a);                  // APG:243-262
+    void finish();
+    void process_files(std::vector<std::istream*>& sams);  // APG:212-289
+    void on_pileup(PileupRecord& p) override;              // MSVD:521-537
+    void on_sequence_start(const std::string&) override { last_indel_end = 0; }   // MSVD:561-565
+    void on_sequence_end(const std::string&) override {}
+    bool discover_population_snv(PileupRecord& p, char reference, GenomicVariant& out);                   // MSVD:585-597
+    bool discover_population_with_span(PileupRecord& p, const std::string& ref_allele, GenomicVariant& out);  // MSVD:599-618
+    bool discover_population_indel(PileupRecord& p, const CountsHelper& h, GenomicVariant& out);          // MSVD:620-634
+    std::vector<CalledVariant> genotype_variant(GenomicVariant& v, PileupRecord& p, double h);            // MSVD:674-693
+    bool make_new_variant(GenomicVariant& v, const std::vector<CalledVariant>& calls);                    // MSVD:642-656
+private:
+    bool stopped = false;
 };
 
 }  // namespace ngsep_oracle

@@ -572,7 +572,7 @@ static const char* type_name(int8_t t) {  // GenomicVariantImpl.java:59-71
     return nullptr;
 }
 
-static void print_genotype(std::ostream& out, CalledVariant& call, bool snv_format, short ploidy) {  // VCFFileWriter.java:159-308
+void print_genotype_field(std::ostream& out, CalledVariant& call, bool snv_format, short ploidy) {  // VCFFileWriter.java:159-308
     out << "\t";
     const auto& alleles = call.var.alleles;
     auto idx = call.called_indexes();
@@ -625,7 +625,7 @@ void print_vcf_record_single(std::ostream& out, CalledVariant& call, short ploid
     if (v.type != TYPE_UNDETERMINED && v.type != TYPE_BIALLELIC_SNV && tn) { if (printed) out << ";"; out << "TYPE=" << tn; printed = true; }
     if (!printed) out << ".";
     out << "\t" << (snv_format ? "GT:PL:GQ:DP:BSDP:ACN" : "GT:PL:GQ:DP:ADP:ACN");
-    print_genotype(out, call, snv_format, ploidy);
+    print_genotype_field(out, call, snv_format, ploidy);
     out << "\n";
 }
 

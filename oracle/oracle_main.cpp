@@ -11,6 +11,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
 #include <sstream>
 
 using namespace ngsep_oracle;
@@ -46,6 +47,40 @@ RunResult run_ssvd(const ReferenceGenome& genome, std::istream& sam, std::ostrea
     return r;
 }
 
+struct MsvdResult { long n_records = 0, n_pileups = 0, n_nonempty = 0, n_events = 0, n_vcf = 0; double seconds = 0; };
+
+// MultisampleVariantsDetector.run (MSVD:421-462) over SAM text files: samples from the @RG headers, k-way merged streams.
+bool run_msvd(const ReferenceGenome& genome, const std::vector<std::string>& sam_paths, std::ostream& vcf, const DetectorOptions& opt,
+              std::vector<std::array<int, 6>>* dump, MsvdResult& r, std::string& err) {
+    std::vector<std::vector<std::string>> headers;
+    for (auto& path : sam_paths) {
+        std::ifstream f(path);
+        if (!f) { err = "cannot open " + path; return false; }
+        std::vector<std::string> lines;
+        std::string line;
+        while (std::getline(f, line)) { if (line.empty() || line[0] != '@') break; if (line.back() == '\r') line.pop_back(); lines.push_back(line); }
+        headers.push_back(lines);
+    }
+    MultisampleVariantsDetector det;
+    det.opt = opt;
+    det.genome = &genome;
+    det.out = &vcf;
+    det.counts_dump = dump;
+    det.min_allele_depth_freq = opt.min_allele_depth_freq;
+    if (!load_samples_from_headers(headers, opt.ploidy, det.samples, err)) return false;
+    std::vector<std::unique_ptr<std::ifstream>> files;
+    std::vector<std::istream*> streams;
+    for (auto& path : sam_paths) { files.emplace_back(new std::ifstream(path)); streams.push_back(files.back().get()); }
+    auto t0 = std::chrono::steady_clock::now();
+    det.begin();
+    det.process_files(streams);
+    auto t1 = std::chrono::steady_clock::now();
+    r.seconds = std::chrono::duration<double>(t1 - t0).count();
+    r.n_records = det.n_input_records; r.n_pileups = det.gen.n_pileups; r.n_nonempty = det.gen.n_nonempty; r.n_events = det.realigner.n_events;
+    r.n_vcf = det.n_records;
+    return true;
+}
+
 int parse_options(int argc, char** argv, int start, DetectorOptions& opt, std::string& in, std::string& ref, std::string& out,
                   std::string& dump, std::string& stats) {
     for (int i = start; i < argc; i++) {
@@ -75,6 +110,7 @@ int parse_options(int argc, char** argv, int start, DetectorOptions& opt, std::s
         else if (a == "-minQuality") opt.min_quality = (short)std::atoi(need("-minQuality"));
         else if (a == "-embeddedSNVs") opt.call_embedded = true;
         else if (a == "-csb") opt.csb = true;
+        else if (a == "--minAlleleDepthFrequency") opt.min_allele_depth_freq = std::atof(need("--minAlleleDepthFrequency"));
         else if (a == "--dump-counts") dump = need("--dump-counts");
         else if (a == "--stats") stats = need("--stats");
         else { std::fprintf(stderr, "Unrecognized option %s\n", a.c_str()); return 1; }  // CommandsDescriptor.java:441-445
@@ -86,8 +122,36 @@ int parse_options(int argc, char** argv, int start, DetectorOptions& opt, std::s
 
 #ifndef NGSEP_ORACLE_NO_MAIN
 int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "MultisampleVariantsDetector") {   // MSVD.main, MSVD:412-419: options, then the input files
+        DetectorOptions opt;
+        std::string in, ref, out = "variants.vcf", dump, stats;
+        int i = 2;
+        std::vector<char*> oargs;
+        static const char* flags[] = {"-psp", "-ignoreLowerCaseRef", "-p", "-s", "-embeddedSNVs"};
+        while (i < argc && argv[i][0] == '-') {
+            bool is_flag = false;
+            for (auto f : flags) if (!std::strcmp(f, argv[i])) is_flag = true;
+            oargs.push_back(argv[i++]);
+            if (!is_flag && i < argc) oargs.push_back(argv[i++]);
+        }
+        if (parse_options((int)oargs.size(), oargs.data(), 0, opt, in, ref, out, dump, stats)) return 1;
+        std::vector<std::string> files;
+        for (; i < argc; i++) files.push_back(argv[i]);
+        if (ref.empty()) { std::fprintf(stderr, "The reference genome file is a required parameter\n"); return 2; }   // MSVD:423
+        ReferenceGenome genome = ReferenceGenome::load_fasta(ref);
+        std::ofstream vcf(out);   // MSVD:452
+        MsvdResult r; std::string err;
+        if (!run_msvd(genome, files, vcf, opt, nullptr, r, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
+        if (!stats.empty()) {
+            std::ofstream s(stats);
+            s << "{\"records\": " << r.n_records << ", \"pileups\": " << r.n_pileups << ", \"genotyped_positions\": " << r.n_nonempty
+              << ", \"indel_events\": " << r.n_events << ", \"vcf_records\": " << r.n_vcf << ", \"seconds\": " << r.seconds << "}\n";
+        }
+        return 0;
+    }
     if (argc < 2 || std::string(argv[1]) != "SingleSampleVariantsDetector") {
-        std::fprintf(stderr, "usage: ngsep_oracle SingleSampleVariantsDetector -i in.sam -r ref.fa -o prefix [options]\n");
+        std::fprintf(stderr, "usage: ngsep_oracle SingleSampleVariantsDetector -i in.sam -r ref.fa -o prefix [options]\n"
+                             "       ngsep_oracle MultisampleVariantsDetector -r ref.fa -o out.vcf [options] a.sam b.sam ...\n");
         return 1;
     }
     DetectorOptions opt;
@@ -182,6 +246,42 @@ char* oracle_run_ssvd(const char* fasta_path, const char* sam_path, int argc, ch
     char* res = (char*)std::malloc(s.size() + 1);
     std::memcpy(res, s.c_str(), s.size() + 1);
     return res;
+}
+
+// MultisampleVariantsDetector on SAM text files.  counts_out: pooled pos,A,C,G,T,DP wherever discoverPopulationSNV ran.
+char* oracle_run_msvd(const char* fasta_path, int n_files, char** sam_paths, int argc, char** argv, int** counts_out, long* n_counts,
+                      long* genotyped_positions, double* seconds) {
+    DetectorOptions opt;
+    std::string in, ref, out, dump, stats;
+    if (parse_options(argc, argv, 0, opt, in, ref, out, dump, stats)) return nullptr;
+    ReferenceGenome genome = ReferenceGenome::load_fasta(fasta_path);
+    std::vector<std::string> files;
+    for (int i = 0; i < n_files; i++) files.push_back(sam_paths[i]);
+    std::ostringstream vcf;
+    std::vector<std::array<int, 6>> counts;
+    MsvdResult r; std::string err;
+    if (!run_msvd(genome, files, vcf, opt, counts_out ? &counts : nullptr, r, err)) return nullptr;
+    if (counts_out) {
+        *counts_out = (int*)std::malloc(counts.size() * 6 * sizeof(int) + 8);
+        std::memcpy(*counts_out, counts.data(), counts.size() * 6 * sizeof(int));
+        *n_counts = (long)counts.size();
+    }
+    if (genotyped_positions) *genotyped_positions = r.n_nonempty;
+    if (seconds) *seconds = r.seconds;
+    std::string s = vcf.str();
+    char* res = (char*)std::malloc(s.size() + 1);
+    std::memcpy(res, s.c_str(), s.size() + 1);
+    return res;
+}
+
+// DiversityStatistics + ParseUtils.ENGLISHFMT known-answer hooks
+void oracle_english_fmt(double v, char* out16) { std::string s = english_fmt(v); std::strncpy(out16, s.c_str(), 15); out16[15] = 0; }
+int oracle_string_hashset_order(int n, char** keys, int* order_out) {
+    std::vector<std::string> k;
+    for (int i = 0; i < n; i++) k.push_back(keys[i]);
+    auto o = java_string_hashset_order(k);
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) if (o[i] == k[j]) order_out[i] = j;
+    return n;
 }
 
 void oracle_free(void* p) { std::free(p); }

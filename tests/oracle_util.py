@@ -33,6 +33,11 @@ def load_oracle():
     lib.oracle_run_ssvd.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_int)),
                                     C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_double)]
     lib.oracle_free.argtypes = [C.c_void_p]
+    lib.oracle_run_msvd.restype = C.c_void_p
+    lib.oracle_run_msvd.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_int)),
+                                    C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    lib.oracle_english_fmt.argtypes = [C.c_double, C.c_char_p]
+    lib.oracle_string_hashset_order.argtypes = [C.c_int, C.POINTER(C.c_char_p), ip]
     return lib
 
 
@@ -64,6 +69,31 @@ def run_ssvd(lib, fasta, sam, args=(), want_counts=False):
         counts = np.ctypeslib.as_array(cptr, shape=(n_counts.value, 6)).copy() if n_counts.value else np.zeros((0, 6), np.int32)
         lib.oracle_free(cptr)
     return text, counts, gp.value, sec.value
+
+
+def run_msvd(lib, fasta, sams, args=(), want_counts=False):
+    """Runs the oracle MultisampleVariantsDetector on SAM files; returns (vcf_text, pooled counts[n,6] or None, genotyped_positions, seconds)."""
+    argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
+    files = (C.c_char_p * len(sams))(*[s.encode() for s in sams])
+    cptr = C.POINTER(C.c_int)()
+    n_counts, gp, sec = C.c_long(0), C.c_long(0), C.c_double(0)
+    res = lib.oracle_run_msvd(fasta.encode(), len(sams), files, len(args), argv, C.byref(cptr) if want_counts else None,
+                              C.byref(n_counts), C.byref(gp), C.byref(sec))
+    if not res:
+        raise RuntimeError("oracle MSVD run failed")
+    text = C.string_at(res).decode()
+    lib.oracle_free(res)
+    counts = None
+    if want_counts:
+        counts = np.ctypeslib.as_array(cptr, shape=(n_counts.value, 6)).copy() if n_counts.value else np.zeros((0, 6), np.int32)
+        lib.oracle_free(cptr)
+    return text, counts, gp.value, sec.value
+
+
+def english_fmt(lib, v):
+    buf = C.create_string_buffer(16)
+    lib.oracle_english_fmt(v, buf)
+    return buf.value.decode()
 
 
 def parse_vcf(text):

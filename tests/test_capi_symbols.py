@@ -20,7 +20,7 @@ def test_header_symbols_exported():
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ngsep_abi_version() == 2000 and lib.ngsep_built_sm() == 100
+    assert lib.ngsep_abi_version() == 2001 and lib.ngsep_built_sm() == 100
 
 
 def test_struct_layouts_match_header():
@@ -28,6 +28,7 @@ def test_struct_layouts_match_header():
     assert capi.CALL_DTYPE.itemsize == 224
     assert C.sizeof(capi.Params) == 32
     assert C.sizeof(capi.Tile) == 72 and C.sizeof(capi.TileStats) == 48
+    assert capi.SITE_DTYPE.itemsize == 44 and capi.SAMPLE_CALL_DTYPE.itemsize == 104   # ngsep_pop_site, ngsep_sample_call
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")

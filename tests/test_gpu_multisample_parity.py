@@ -1,0 +1,102 @@
+"""GPU parity, MultisampleVariantsDetector: host pipeline + k_pileup_windows + k_genotype_columns_multi (C ABI) vs the
+oracle's restatement of discovery/MultisampleVariantsDetector.java, VCF text byte for byte (BASELINE configs[3]).
+
+Populations share planted SNV / indel sites with per-sample genotypes; samples may own several read groups and some
+reads carry no RG tag (pooled discovery only, SSVPL:365).  Every record checks, per sample, the integer counts (BSDP, DP,
+bit-exact), the genotype, GQ and the PL values (rounded -10 * fp64 log-likelihoods summed in the sample's pileup order)."""
+import numpy as np
+import pytest
+
+from ngsepcore_b200 import hostapi, simulate
+from tests import oracle_util as ou
+
+pytestmark = pytest.mark.gpu
+
+
+def _population(tmp_path, contigs, **kw):
+    genome, batch, _ = simulate.simulate_population(contigs, **kw)
+    fa, sam = str(tmp_path / "ref.fa"), str(tmp_path / "pop.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    return genome, batch, fa, sam
+
+
+def _body(text):
+    return [l for l in text.splitlines() if not l.startswith("#")]
+
+
+def _detector(batch, **kw):
+    return hostapi.MultisampleDetector(list(zip(batch.rg_names, batch.rg_samples)), **kw)
+
+
+def test_wgs_population_default_options(oracle, tmp_path):
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 150000), ("chrB", 60000)], n_samples=12, depth=8, mode="wgs",
+                                         rgs_per_sample=2, no_rg_frac=0.02, snv_rate=3e-3, indel_rate=5e-4, seeds=(21, 22, 23))
+    want, _, gp, _ = ou.run_msvd(oracle, fa, [sam])
+    det = _detector(batch)
+    det.set_genome(genome)
+    got = det.run(batch)
+    st = det.stats()
+    body = _body(want)
+    assert len(body) > 500 and sum(1 for l in body if "TYPE=INDEL" in l or "TYPE=STR" in l) > 30
+    assert any("," in l.split("\t")[4] and len(l.split("\t")[3]) == 1 for l in body)     # multi-allelic SNV sites are present
+    assert got == want
+    assert st.covered_positions == gp and st.kernel_launches > 0 and st.snv_calls > 400 and st.indel_calls > 30
+
+
+def test_gbs_population_deep_identical_starts(oracle, tmp_path):
+    """GBS-style tags: every sample's reads of a tag start at the same position (hundreds of records per start), run with
+    -maxAlnsPerStartPos 100 as the reference's documentation asks for this data type (README.txt:588-596)."""
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 120000)], n_samples=24, depth=10, mode="gbs", n_tags=400,
+                                         snv_rate=5e-3, indel_rate=4e-4, seeds=(31, 32, 33))
+    want, _, gp, _ = ou.run_msvd(oracle, fa, [sam], args=("-maxAlnsPerStartPos", "100"))
+    det = _detector(batch, maxAlnsPerStartPos=100)
+    det.set_genome(genome)
+    got = det.run(batch)
+    assert len(_body(want)) > 100
+    assert got == want
+    assert det.stats().covered_positions == gp
+
+
+@pytest.mark.parametrize("seed,det_kw,oargs", [
+    (4, dict(embeddedSNVs=True, minQuality=60, psp=True), ("-embeddedSNVs", "-minQuality", "60", "-psp")),
+    (5, dict(h=0.01, maxBaseQS=25, ignore5=3, ignore3=4, minAlleleDepthFrequency=0.05), ("-h", "0.01", "-maxBaseQS", "25", "-ignore5", "3", "-ignore3", "4",
+                                                                                        "--minAlleleDepthFrequency", "0.05")),
+    (6, dict(ignoreLowerCaseRef=True, maxAlnsPerStartPos=2, querySeq="chrA", first=20000, last=70000),
+     ("-ignoreLowerCaseRef", "-maxAlnsPerStartPos", "2", "-querySeq", "chrA", "-first", "20000", "-last", "70000")),
+])
+def test_option_matrix(oracle, tmp_path, seed, det_kw, oargs):
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 90000), ("chrB", 30000)], n_samples=9, depth=10, mode="wgs", snv_rate=4e-3,
+                                         indel_rate=1e-3, lower_frac=0.03, n_frac=0.01, seeds=(seed * 10, seed * 10 + 1, seed * 10 + 2))
+    want, _, _, _ = ou.run_msvd(oracle, fa, [sam], args=oargs)
+    det = _detector(batch, **det_kw)
+    det.set_genome(genome)
+    got = det.run(batch)
+    assert len(_body(want)) > 60
+    assert got == want
+
+
+def test_region_tiles_and_shards_are_invariant(oracle, tmp_path):
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 110000), ("chrB", 40000)], n_samples=6, depth=10, mode="wgs", snv_rate=3e-3,
+                                         indel_rate=5e-4, seeds=(81, 82, 83))
+    want, _, _, _ = ou.run_msvd(oracle, fa, [sam])
+    for n_shards in (1, 3):
+        lines = []
+        for shard in range(n_shards):
+            det = _detector(batch, tile_len=23000, shard=shard, n_shards=n_shards)
+            det.set_genome(genome)
+            lines += _body(det.run(batch, with_header=False))
+        order = {n: i for i, n in enumerate(genome)}
+        lines.sort(key=lambda l: (order[l.split("\t")[0]], int(l.split("\t")[1])))
+        assert lines == _body(want)
+
+
+def test_many_samples_more_than_one_cta_batch(oracle, tmp_path):
+    """More samples than threads in a CTA of k_genotype_columns_multi (128): the sample axis is walked in batches."""
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 20000)], n_samples=150, depth=3, mode="wgs", snv_rate=4e-3, indel_rate=0.0,
+                                         seeds=(51, 52, 53))
+    want, _, _, _ = ou.run_msvd(oracle, fa, [sam])
+    det = _detector(batch)
+    det.set_genome(genome)
+    assert det.run(batch) == want
+    assert len(_body(want)) > 40
