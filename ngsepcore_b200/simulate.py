@@ -394,7 +394,7 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
 
 def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: str = "wgs", n_tags: int = 200,
                         seeds=(1021, 2022, 3023), read_len: int = 100, rgs_per_sample: int = 1, no_rg_frac: float = 0.0,
-                        snv_rate: float = 1e-3, indel_rate: float = 1e-4, **kw):
+                        snv_rate: float = 1e-3, indel_rate: float = 1e-4, multi_allelic_frac: float = 0.1, **kw):
     """Population workload for MultisampleVariantsDetector (BASELINE configs[3]): shared planted sites, per-sample
     genotypes drawn from a population allele frequency ~ Beta(0.2, 0.2); mode "wgs" = uniform single-end reads at `depth`
     per sample, "gbs" = `n_tags` tag loci per contig with Poisson(depth) identical-start reads per sample and tag.
@@ -406,6 +406,12 @@ def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: 
     for name, length in contigs:
         shared[name] = plant_variants(genome[name], rng_v, snv_rate, indel_rate)
         af[name] = rng_v.beta(0.2, 0.2, size=len(shared[name]))
+        for v in shared[name]:        # a fraction of the SNV sites segregates a second alternative allele
+            v._alt2 = None
+            if v.kind == "snv" and rng_v.random() < multi_allelic_frac:
+                r = genome[name][v.pos - 1] & 0xDF
+                others = [int(x) for x in _ACGT if x != r and x != v.alt[0]]
+                v._alt2 = bytes([others[int(rng_v.integers(0, 2))]])
         if mode == "gbs":
             st = np.sort(rng_v.integers(1, max(2, length - read_len - 20), size=n_tags)).astype(np.int64)
             tags[name] = (st, rng_v.random(n_tags) < 0.5)
@@ -418,7 +424,18 @@ def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: 
                 a0, a1 = rng_v.random() < f, rng_v.random() < f
                 if not (a0 or a1):
                     continue
-                w = Variant(v.pos, v.kind, v.length, v.alt, bool(a0 and a1))
+                if v._alt2 is not None:
+                    x0 = v._alt2 if rng_v.random() < 0.4 else v.alt
+                    x1 = v._alt2 if rng_v.random() < 0.4 else v.alt
+                    if a0 and a1 and x0 != x1:      # the two haplotypes carry different alternative alleles
+                        for hp, x in ((0, x0), (1, x1)):
+                            w = Variant(v.pos, v.kind, v.length, x, False)
+                            w._hap = hp
+                            vs.append(w)
+                        continue
+                    w = Variant(v.pos, v.kind, v.length, x0 if a0 else x1, bool(a0 and a1))
+                else:
+                    w = Variant(v.pos, v.kind, v.length, v.alt, bool(a0 and a1))
                 w._hap = 0 if a0 else 1
                 vs.append(w)
             ov[name] = vs

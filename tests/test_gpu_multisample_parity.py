@@ -38,10 +38,10 @@ def test_wgs_population_default_options(oracle, tmp_path):
     got = det.run(batch)
     st = det.stats()
     body = _body(want)
-    assert len(body) > 500 and sum(1 for l in body if "TYPE=INDEL" in l or "TYPE=STR" in l) > 30
+    assert len(body) > 400 and sum(1 for l in body if "TYPE=INDEL" in l or "TYPE=STR" in l) > 30
     assert any("," in l.split("\t")[4] and len(l.split("\t")[3]) == 1 for l in body)     # multi-allelic SNV sites are present
     assert got == want
-    assert st.covered_positions == gp and st.kernel_launches > 0 and st.snv_calls > 400 and st.indel_calls > 30
+    assert st.covered_positions == gp and st.kernel_launches > 0 and st.snv_calls > 300 and st.indel_calls > 30
 
 
 def test_gbs_population_deep_identical_starts(oracle, tmp_path):
