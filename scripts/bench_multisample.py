@@ -1,0 +1,78 @@
+"""BASELINE configs[3] (MultisampleVariantsDetector, GBS-style samples) on one B200: whole-detector time and device time of
+the multi-sample path, with the oracle (CPU restatement) timed on a sample of the same input.  Not the driver's bench line
+(bench.py measures configs[1]); its output goes to profiles/ as evidence for the sample-axis kernels.
+
+    python scripts/bench_multisample.py [--samples 96] [--tags 1500] [--depth 10] [--mode gbs|wgs] [--steps 3]
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from ngsepcore_b200 import hostapi, simulate  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=96)
+    ap.add_argument("--tags", type=int, default=1500, help="tag loci per contig (gbs)")
+    ap.add_argument("--depth", type=float, default=10.0)
+    ap.add_argument("--mode", default="gbs")
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--contig-len", type=int, default=800000)
+    ap.add_argument("--contigs", type=int, default=3)
+    ap.add_argument("--oracle-bp", type=int, default=60000, help="prefix of the first contig the oracle is timed on (0 = skip)")
+    a = ap.parse_args()
+    contigs = [(f"chr{i + 1}", a.contig_len) for i in range(a.contigs)]
+    t0 = time.time()
+    genome, batch, _ = simulate.simulate_population(contigs, n_samples=a.samples, depth=a.depth, mode=a.mode, n_tags=a.tags, seeds=(1021, 2022, 3023))
+    sim_s = time.time() - t0
+    cap = 100 if a.mode == "gbs" else 5
+    det = hostapi.MultisampleDetector(list(zip(batch.rg_names, batch.rg_samples)), maxAlnsPerStartPos=cap)
+    det.set_genome(genome)
+    runs = []
+    for step in range(a.steps + 1):
+        s0 = det.stats()
+        k0, d0, p0, pk0, c0 = s0.kernel_ms, s0.device_s, s0.prepass_s, s0.pack_s, s0.covered_positions
+        t = time.time()
+        text = det.run(batch)
+        wall = time.time() - t
+        s1 = det.stats()
+        runs.append(dict(wall_s=wall, kernel_ms=s1.kernel_ms - k0, device_s=s1.device_s - d0, prepass_s=s1.prepass_s - p0, pack_s=s1.pack_s - pk0,
+                         covered=s1.covered_positions - c0))
+    best = min(runs[1:], key=lambda r: r["kernel_ms"])
+    n_rec = sum(1 for l in text.splitlines() if not l.startswith("#"))
+    line = {"metric": "genotyped_positions_per_sec", "workload": f"{a.samples} samples x {a.depth}x {a.mode}, {a.contigs} x {a.contig_len} bp"
+            + (f", {a.tags} tags per contig" if a.mode == "gbs" else "") + " (BASELINE configs[3], scaled)",
+            "reads": int(batch.n), "genotyped_positions": int(best["covered"]), "vcf_records": n_rec,
+            "kernels_ms": best["kernel_ms"], "value_kernels": best["covered"] / (best["kernel_ms"] / 1e3),
+            "sample_genotypes_per_sec_kernels": best["covered"] * a.samples / (best["kernel_ms"] / 1e3),
+            "detector_wall_s": best["wall_s"], "value_detector": best["covered"] / best["wall_s"],
+            "host": {"prepass_s": best["prepass_s"], "pack_s": best["pack_s"], "device_call_s": best["device_s"], "simulate_s": sim_s}}
+    if a.oracle_bp > 0:
+        from tests import oracle_util as ou
+        lib = ou.load_oracle()
+        with tempfile.TemporaryDirectory() as d:
+            fa, sam = os.path.join(d, "r.fa"), os.path.join(d, "r.sam")
+            simulate.write_fasta(fa, genome)
+            import numpy as np
+            idx = np.nonzero((batch.seq_idx == 0) & (batch.first <= a.oracle_bp))[0]
+            simulate.write_sam(sam, batch.select(idx))
+            args = ("-maxAlnsPerStartPos", str(cap), "-querySeq", contigs[0][0], "-first", "1", "-last", str(a.oracle_bp))
+            want, _, gp, sec = ou.run_msvd(lib, fa, [sam], args=args)
+            sub = hostapi.MultisampleDetector(list(zip(batch.rg_names, batch.rg_samples)), maxAlnsPerStartPos=cap, querySeq=contigs[0][0], first=1, last=a.oracle_bp)
+            sub.set_genome(genome)
+            got = sub.run(batch.select(idx))
+            line["cpu_baseline"] = {"value": gp / sec, "unit": "positions/s", "cores": 1, "kind": "port", "seconds": sec,
+                                    "sample": f"first {a.oracle_bp} bp of {contigs[0][0]} ({len(idx)} records, {gp} genotyped positions)",
+                                    "vcf_identical_on_sample": got == want}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -100,3 +100,30 @@ def test_many_samples_more_than_one_cta_batch(oracle, tmp_path):
     det.set_genome(genome)
     assert det.run(batch) == want
     assert len(_body(want)) > 40
+
+
+def test_cli_several_input_files(oracle, tmp_path):
+    """ngsep_b200 MultisampleVariantsDetector over one SAM per sample group: the k-way merge of APG:212-289 (order by
+    sequence, first, last; ties to the lowest file index) happens on the host before admission."""
+    import os
+    import subprocess
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 50000), ("chrB", 20000)], n_samples=6, depth=10, mode="wgs", snv_rate=4e-3,
+                                         indel_rate=1.5e-3, seeds=(71, 72, 73))
+    files = []
+    for k in range(3):   # three inputs with two samples each
+        idx = np.nonzero((batch.rg // 2) == k)[0]
+        path = str(tmp_path / f"part{k}.sam")
+        simulate.write_sam(path, batch.select(idx))
+        files.append(path)
+    want, _, _, _ = ou.run_msvd(oracle, fa, files, args=("-minQuality", "50"))
+    assert len(_body(want)) > 60
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "ngsepcore_b200", "ngsep_b200")
+    out = str(tmp_path / "multi.vcf")
+    subprocess.check_call([cli, "MultisampleVariantsDetector", "-r", fa, "-o", out, "-minQuality", "50"] + files)
+    assert open(out).read() == want
+    # one input with every read group: same samples, no merge
+    want1, _, _, _ = ou.run_msvd(oracle, fa, [sam])
+    subprocess.check_call([cli, "MultisampleVariantsDetector", "-r", fa, "-o", out, sam])
+    assert open(out).read() == want1
+    assert subprocess.call([cli, "MultisampleVariantsDetector", "-o", out, sam], stderr=subprocess.DEVNULL) == 2      # MSVD:423
