@@ -53,6 +53,7 @@ struct Slot {
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
     DevBuf<uint16_t> d_group;                 // multi-sample contexts: read-group id per record
+    DevBuf<uint32_t> d_gidx, d_goff, d_gblk;          //                        records indexed by read group (launch_group_index)
     DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
     DevBuf<ngsep_sample_call> d_scalls;       //                        ... x n_samples sample calls
     DevBuf<int32_t> d_counts;
@@ -70,7 +71,7 @@ struct Slot {
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
-        d_group.release(); d_sites.release(); d_scalls.release();
+        d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
@@ -92,6 +93,7 @@ struct Ctx {
     // sample axis (ngsep_samples_set)
     bool samples_set = false;
     DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch;
+    DevBuf<uint16_t> d_gkeys; DevBuf<uint32_t> d_gvals; DevBuf<unsigned char> d_cub;   // staging scratch of launch_group_index (stream-ordered reuse)
     int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
     std::vector<RefSeq> refs;
@@ -194,7 +196,7 @@ int launch_slot(Ctx* c, Slot* s) {
     if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
     if (s->tile.n_windows > 0) {
-        if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(c), c->d_prm, c->multi_grid, c->stream);
+        if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(c), c->d_prm, c->params.n_samples, c->multi_grid, c->stream);
         else launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream);
         s->launches = 2;
     }
@@ -241,7 +243,7 @@ int launch_batch(Ctx* c) {
     if (c->b_windows > 0) launch_pileup(c->d_btiles.p, c->d_bwin.p, c->b_windows, c->d_prm, queue_view(c), c->cfg, c->b_grid, c->smem, c->stream);
     CK(cudaEventRecord(c->bm, c->stream), "event record");
     if (c->b_windows > 0) {
-        if (c->params.n_samples > 1) launch_genotype_multi(c->d_btiles.p, queue_view(c), c->d_prm, c->multi_grid, c->stream);
+        if (c->params.n_samples > 1) launch_genotype_multi(c->d_btiles.p, queue_view(c), c->d_prm, c->params.n_samples, c->multi_grid, c->stream);
         else launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
     }
     CK(cudaEventRecord(c->b1, c->stream), "event record");
@@ -289,6 +291,21 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     }
     if (multi) CK(s->d_group.reserve((size_t)t->n_reads + 16), "read-group alloc");
     if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream), "read-group copy");
+    if (multi) {   // records indexed by read group; the scratch buffers are shared by the context (growing them waits for the stream)
+        const size_t n = (size_t)t->n_reads;
+        const size_t cub_bytes = group_index_temp_bytes(t->n_reads);
+        if (c->d_gkeys.cap < 2 * n + 16 || c->d_gvals.cap < n + 16 || c->d_cub.cap < cub_bytes + 256) {
+            CK(cudaStreamSynchronize(c->stream), "drain before growing the staging scratch");
+            CK(c->d_gkeys.reserve(2 * n + 16), "group key alloc");
+            CK(c->d_gvals.reserve(n + 16), "group value alloc");
+            CK(c->d_cub.reserve(cub_bytes + 256), "sort scratch alloc");
+        }
+        CK(s->d_gidx.reserve(n + 16), "group index alloc");
+        CK(s->d_goff.reserve((size_t)c->hp.n_groups + 4), "group offsets alloc");
+        CK(s->d_gblk.reserve(((size_t)c->hp.n_groups + 1) * ((size_t)group_blocks(t->n_reads) + 1) + 16), "group block table alloc");
+        CK(launch_group_index(s->d_group.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
+           "group index launch");
+    }
     if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
@@ -313,6 +330,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     TileDev& d = s->tile;
     d = TileDev{};
     d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = s->d_qual.p;
+    d.gidx = multi ? s->d_gidx.p : nullptr; d.goff = multi ? s->d_goff.p : nullptr;
+    d.gblk = multi ? s->d_gblk.p : nullptr; d.n_gblk = multi ? group_blocks(t->n_reads) : 0;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
     d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
     d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
@@ -546,7 +565,7 @@ int ngsep_ctx_destroy(void* ctx) {
     for (Slot* s : c->slots) { s->release(); delete s; }
     for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
     c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
-    c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release();
+    c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release(); c->d_gkeys.release(); c->d_gvals.release(); c->d_cub.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -640,6 +659,7 @@ int ngsep_samples_set(void* ctx, int32_t n_groups, const int32_t* sample_group_o
     }
     CK(cudaSetDevice(c->device), "set device");
     CK(cudaStreamSynchronize(c->stream), "drain");
+    if (!std::getenv("NGSEP_MULTI_BLOCKS_PER_SM")) c->multi_grid = c->sm_count * (n_samples + 1 <= 64 ? 16 : 8);   // narrower CTAs for a short sample axis
     CK(c->d_sgo.reserve((size_t)n_samples + 1), "sample table alloc");
     CK(c->d_sgroups.reserve((size_t)std::max(total, 1)), "sample table alloc");
     CK(c->d_scratch.reserve((size_t)c->multi_grid * (size_t)n_samples), "scratch alloc");

@@ -5,6 +5,7 @@
 #include "pileup_kernels.cuh"
 
 #include <climits>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace ngsep_b200 {
 
@@ -1045,16 +1046,17 @@ __global__ void __launch_bounds__(256, 6) k_genotype_columns(const TileDev* __re
 // ------------------------------------------------------------------------------------------------------------
 // MultisampleVariantsDetector: the open columns of a multi-sample context, one CTA per column
 // ------------------------------------------------------------------------------------------------------------
-// MSVD.onPileup for a span-1 position (MSVD:521-537).  Phase A: the CTA resolves every covering record in pileup order
-// (lane_eval = PR.getAlleleCalls(1) + the quality rules of CH.updateCounts) into shared memory, chunk by chunk, and sums
-// the POOLED counts (all reads, any read group: discoverPopulationSNV, MSVD:586-587).  Phase B: one thread per sample
-// walks the chunk in order and adds the records of ITS read groups — in the order PR.getAlleleCalls(span, Set) visits
-// the groups (PR:104-111) — to its counts and its 10 distinct log-likelihoods, in fp64 (CH:231-249), so every sample's
-// logConditionalProbs are bit-identical to the Java doubles.  Phase C: createSNVVariantPool (SSVPL:297-332), the allele
+// MSVD.onPileup for a span-1 position (MSVD:521-537).  At staging the records of a tile are indexed BY READ GROUP
+// (gidx / goff: a stable sort of the record indexes by group id, so every group's list is in pileup order).  For a
+// column covered by records [i_lo, i_hi) the records of one read group are then a contiguous piece of its list (two
+// binary searches), and ONE THREAD PER SAMPLE walks the pieces of its read groups — in the order
+// PR.getAlleleCalls(span, Set) visits the groups (PR:104-111) — evaluating each record once (lane_eval =
+// PR.getAlleleCalls(1) + the quality rules of CH.updateCounts) and adding it to the sample's counts and its 10 distinct
+// log-likelihoods in fp64 (CH:231-249): every sample's logConditionalProbs are bit-identical to the Java doubles.  The
+// records whose read group belongs to no sample (list n_groups) only enter the POOLED counts (discoverPopulationSNV,
+// MSVD:586-587), which are the sum over all lists.  Phase C: createSNVVariantPool (SSVPL:297-332), the allele
 // refinement loop (MSVD:590-595, 642-656), per-sample VD.genotypeSNV (VD:21-97) with the sample-level minQuality of
 // SSVPL:388, QUAL = best GQ of the decided non-hom-ref samples (MSVD:685-691), the filter of MSVD:533.
-constexpr int kMultiChunk = 1024;
-
 struct SamplePost { double hom[4], het[6]; };   // posteriors: [i][i], and ONE ordered event of (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
 
 __device__ __forceinline__ int pair_index(int lo, int hi) { return (lo == 0) ? hi - 1 : ((lo == 1) ? hi + 1 : 5); }   // into het[6]
@@ -1118,23 +1120,49 @@ __device__ __forceinline__ uint32_t sample_genotype(const SamplePost& P, int dep
     return (uint32_t)g0 | ((uint32_t)g1 << 8) | ((uint32_t)gq << 16);
 }
 
-__global__ void __launch_bounds__(kMultiThreads, 4) k_genotype_columns_multi(const TileDev* __restrict__ tiles, const ColumnQueue cq,
-                                                                             const DevParams* __restrict__ gprm) {
+
+// First entry of read-group list g that is >= want.  gblk[g][b] = the answer for want = b * kGroupBlock (built at
+// staging), so the search only looks at the few list entries that fall into one block of record indexes.
+constexpr int kGroupBlockShift = 8, kGroupBlock = 1 << kGroupBlockShift;
+__device__ __forceinline__ int list_lower_bound(const uint32_t* __restrict__ lst, const uint32_t* __restrict__ blk, int n_blk, uint32_t want) {
+    const int b = min((int)(want >> kGroupBlockShift), n_blk);
+    int lo = (int)__ldg(blk + b), hi = (int)__ldg(blk + min(b + 1, n_blk));
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(lst + mid) < want) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+struct SampleAcc { double L[10]; int c0, c1, c2, c3, depth; };
+
+__device__ __forceinline__ void sample_add(SampleAcc& a, uint32_t code, const double* s_tab) {
+    if (code & kCodeCall) a.depth++;                                   // CH:210
+    if (!(code & kCodeCounted)) return;
+    const int b = (int)(code & 3u), q = (int)((code >> 2) & 31u);
+    a.c0 += (b == 0); a.c1 += (b == 1); a.c2 += (b == 2); a.c3 += (b == 3);   // CH:223
+    const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a.L[i] += (b == i) ? ta : tb;          // CH:231-235
+    a.L[4] += (b == 0 || b == 1) ? tc : tb;                            // CH:236-249 with f == g == 250
+    a.L[5] += (b == 0 || b == 2) ? tc : tb;
+    a.L[6] += (b == 0 || b == 3) ? tc : tb;
+    a.L[7] += (b == 1 || b == 2) ? tc : tb;
+    a.L[8] += (b == 1 || b == 3) ? tc : tb;
+    a.L[9] += (b == 2 || b == 3) ? tc : tb;
+}
+
+template <int kThr>
+__global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
-    __shared__ uint32_t s_code[kMultiChunk];
-    __shared__ uint16_t s_grp[kMultiChunk];
     __shared__ int s_pool[5];            // pooled A, C, G, T counts and totalCount
     __shared__ int s_red[4];             // [0] called-allele mask, [1] best quality, [2] output slot
     const DevParams& prm = *gprm;
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int i = tid; i < NGSEP_N_TABLES; i += kMultiThreads) s_tab[i] = prm.tables[i];
+    for (int i = tid; i < NGSEP_N_TABLES; i += kThr) s_tab[i] = prm.tables[i];
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
-    const int n_samples = prm.n_samples, max_qs = prm.max_base_qs;
-    const int n_batches = (n_samples + kMultiThreads - 1) / kMultiThreads;
+    const int n_samples = prm.n_samples, n_groups = prm.n_groups, max_qs = prm.max_base_qs;
+    const int n_batches = (n_samples + 1 + kThr - 1) / kThr;   // + the list of the records that belong to no sample
     ngsep_sample_call* scratch = prm.scratch + (size_t)blockIdx.x * (size_t)n_samples;
     const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
-    __syncthreads();
     for (unsigned int t = blockIdx.x; t < n_open; t += gridDim.x) {
         __syncthreads();   // every `continue` below is uniform over the CTA; the previous column's shared state is free from here on
         const uint4 oc = cq.open[t];   // tile, position, first record, number of records
@@ -1152,64 +1180,50 @@ __global__ void __launch_bounds__(kMultiThreads, 4) k_genotype_columns_multi(con
         }
         if (tid < 5) s_pool[tid] = 0;
         if (tid < 4) s_red[tid] = 0;
-        // ---- phases A + B ------------------------------------------------------------------------------------------
+        __syncthreads();
+        // ---- phases A + B: one thread per sample ------------------------------------------------------------------------
         for (int batch = 0; batch < n_batches; batch++) {
-            const int smp = batch * kMultiThreads + tid;
-            double L[10];
+            const int smp = batch * kThr + tid;
+            SampleAcc a;
 #pragma unroll
-            for (int k = 0; k < 10; k++) L[k] = 0.0;
-            int c0 = 0, c1 = 0, c2 = 0, c3 = 0, depth = 0;
-            const int g_lo = (smp < n_samples) ? prm.sample_group_off[smp] : 0;
-            const int g_n = (smp < n_samples) ? prm.sample_group_off[smp + 1] - g_lo : 0;
-            for (int pass = 0; pass < prm.max_groups_per_sample; pass++) {
-                const int my_group = (pass < g_n) ? (int)prm.sample_groups[g_lo + pass] : -1;
-                for (int base = i_lo; base < i_hi; base += kMultiChunk) {
-                    const int n_chunk = min(kMultiChunk, i_hi - base);
-                    __syncthreads();   // the previous chunk has been consumed
-                    int p0 = 0, p1 = 0, p2 = 0, p3 = 0, pd = 0;
-                    for (int k = tid; k < n_chunk; k += kMultiThreads) {
-                        const ngsep_read_hdr h = R.header(base + k);
-                        const uint32_t code = lane_eval(h, R.payload(h), d.qual, pos, max_qs);
-                        s_code[k] = code;
-                        s_grp[k] = d.group[base + k];
-                        if (code & kCodeCall) pd++;
-                        if (code & kCodeCounted) { const int b = (int)(code & 3u); p0 += (b == 0); p1 += (b == 1); p2 += (b == 2); p3 += (b == 3); }
-                    }
-                    if (batch == 0 && pass == 0) {
-                        for (int o = 16; o; o >>= 1) {
-                            p0 += __shfl_xor_sync(kFull, p0, o); p1 += __shfl_xor_sync(kFull, p1, o); p2 += __shfl_xor_sync(kFull, p2, o);
-                            p3 += __shfl_xor_sync(kFull, p3, o); pd += __shfl_xor_sync(kFull, pd, o);
-                        }
-                        if (lane == 0) { atomicAdd(&s_pool[0], p0); atomicAdd(&s_pool[1], p1); atomicAdd(&s_pool[2], p2); atomicAdd(&s_pool[3], p3); atomicAdd(&s_pool[4], pd); }
-                    }
-                    __syncthreads();
-                    if (my_group >= 0) {
-                        for (int k = 0; k < n_chunk; k++) {
-                            if ((int)s_grp[k] != my_group) continue;
-                            const uint32_t code = s_code[k];
-                            if (code & kCodeCall) depth++;                                   // CH:210
-                            if (!(code & kCodeCounted)) continue;
-                            const int b = (int)(code & 3u), q = (int)((code >> 2) & 31u);
-                            c0 += (b == 0); c1 += (b == 1); c2 += (b == 2); c3 += (b == 3);   // CH:223
-                            const double ta = s_tab[3 * q], tb = s_tab[3 * q + 1], tc = s_tab[3 * q + 2];
+            for (int k = 0; k < 10; k++) a.L[k] = 0.0;
+            a.c0 = a.c1 = a.c2 = a.c3 = a.depth = 0;
+            int g_lo = 0, g_n = 0;
+            if (smp < n_samples) { g_lo = prm.sample_group_off[smp]; g_n = prm.sample_group_off[smp + 1] - g_lo; }
+            else if (smp == n_samples) g_n = 1;   // the records outside every sample
+            for (int gk = 0; gk < g_n; gk++) {
+                const int g = (smp < n_samples) ? (int)prm.sample_groups[g_lo + gk] : n_groups;
+                const uint32_t* lst = d.gidx + d.goff[g];
+                const uint32_t* blk = d.gblk + (size_t)g * (size_t)(d.n_gblk + 1);
+                int ka = list_lower_bound(lst, blk, d.n_gblk, (uint32_t)i_lo);
+                const int kb = list_lower_bound(lst, blk, d.n_gblk, (uint32_t)i_hi);
+                for (; ka < kb; ka += 4) {   // four records in flight: their loads are independent, the sums stay in list order
+                    uint32_t code[4];
 #pragma unroll
-                            for (int i = 0; i < 4; i++) L[i] += (b == i) ? ta : tb;           // CH:231-235
-                            L[4] += (b == 0 || b == 1) ? tc : tb;                             // CH:236-249 with f == g == 250
-                            L[5] += (b == 0 || b == 2) ? tc : tb;
-                            L[6] += (b == 0 || b == 3) ? tc : tb;
-                            L[7] += (b == 1 || b == 2) ? tc : tb;
-                            L[8] += (b == 1 || b == 3) ? tc : tb;
-                            L[9] += (b == 2 || b == 3) ? tc : tb;
+                    for (int u = 0; u < 4; u++) {
+                        code[u] = 0u;
+                        if (ka + u < kb) {
+                            const ngsep_read_hdr h = R.header((int)__ldg(lst + ka + u));
+                            code[u] = lane_eval(h, R.payload(h), d.qual, pos, max_qs);
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) sample_add(a, code[u], s_tab);
                 }
+            }
+            if (smp <= n_samples) {   // pooled counts: every record of the column is in exactly one list
+                if (a.c0) atomicAdd(&s_pool[0], a.c0);
+                if (a.c1) atomicAdd(&s_pool[1], a.c1);
+                if (a.c2) atomicAdd(&s_pool[2], a.c2);
+                if (a.c3) atomicAdd(&s_pool[3], a.c3);
+                if (a.depth) atomicAdd(&s_pool[4], a.depth);
             }
             if (smp < n_samples) {
                 ngsep_sample_call& o = scratch[smp];
-                o.count[0] = c0; o.count[1] = c1; o.count[2] = c2; o.count[3] = c3; o.depth = depth;
+                o.count[0] = a.c0; o.count[1] = a.c1; o.count[2] = a.c2; o.count[3] = a.c3; o.depth = a.depth;
                 o.gq = 0; o.g0 = -1; o.g1 = -1;
 #pragma unroll
-                for (int k = 0; k < 10; k++) o.logcond[k] = L[k];
+                for (int k = 0; k < 10; k++) o.logcond[k] = a.L[k];
             }
         }
         __syncthreads();
@@ -1238,7 +1252,7 @@ __global__ void __launch_bounds__(kMultiThreads, 4) k_genotype_columns_multi(con
             // genotypeVariant (MSVD:674-693): every sample, with the current allele list
             unsigned int mask = 0u;
             int best = 0;
-            for (int smp = tid; smp < n_samples; smp += kMultiThreads) {
+            for (int smp = tid; smp < n_samples; smp += kThr) {
                 ngsep_sample_call& sc = scratch[smp];
                 double L[10];
 #pragma unroll
@@ -1293,13 +1307,69 @@ __global__ void __launch_bounds__(kMultiThreads, 4) k_genotype_columns_multi(con
             const uint2* src = (const uint2*)scratch;
             uint2* dst = (uint2*)(d.pop_calls + (size_t)slot * (size_t)n_samples);
             const int n_words = n_samples * (int)(sizeof(ngsep_sample_call) / 8);
-            for (int k = tid; k < n_words; k += kMultiThreads) dst[k] = src[k];
+            for (int k = tid; k < n_words; k += kThr) dst[k] = src[k];
         }
     }
 }
 
-void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
-    k_genotype_columns_multi<<<grid, kMultiThreads, 0, s>>>(d_tiles, cq, dprm);
+void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s) {
+    // the CTA is as wide as the sample axis (+ the list of the records outside every sample), up to 128 threads
+    if (n_samples + 1 <= 32) k_genotype_columns_multi<32><<<grid, 32, 0, s>>>(d_tiles, cq, dprm);
+    else if (n_samples + 1 <= 64) k_genotype_columns_multi<64><<<grid, 64, 0, s>>>(d_tiles, cq, dprm);
+    else k_genotype_columns_multi<128><<<grid, 128, 0, s>>>(d_tiles, cq, dprm);
+}
+
+// ---- staging: records indexed by read group (stable) ---------------------------------------------------------------
+__global__ void k_group_keys(const uint16_t* __restrict__ group, int n, int n_groups, uint16_t* keys, uint32_t* vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int g = (int)group[i];
+    keys[i] = (uint16_t)min(g, n_groups);   // ids outside the table (0xFFFF: no read group of a sample) share the last list
+    vals[i] = (uint32_t)i;
+}
+__global__ void k_group_offsets(const uint16_t* __restrict__ keys_sorted, int n, int n_groups, uint32_t* goff) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups + 1) return;
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)keys_sorted[mid] < g) lo = mid + 1; else hi = mid; }
+    goff[g] = (uint32_t)lo;
+}
+
+// gblk[g][b], b = 0..n_blk: position in list g of its first record index >= b * kGroupBlock
+__global__ void k_group_blocks(const uint32_t* __restrict__ gidx, const uint32_t* __restrict__ goff, int n_groups, int n_blk, uint32_t* gblk) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)(n_groups + 1) * (n_blk + 1)) return;
+    const int g = (int)(t / (n_blk + 1)), b = (int)(t % (n_blk + 1));
+    const uint32_t* lst = gidx + goff[g];
+    int lo = 0, hi = (int)(goff[g + 1] - goff[g]);
+    const uint32_t want = (uint32_t)b << kGroupBlockShift;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (lst[mid] < want) lo = mid + 1; else hi = mid; }
+    gblk[t] = (uint32_t)lo;
+}
+
+int group_blocks(int n) { return (n + kGroupBlock - 1) >> kGroupBlockShift; }
+
+size_t group_index_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, n, 0, 16);
+    return bytes;
+}
+
+// gidx[n]: record indexes sorted by group (stable: each group's list keeps the pileup order); goff[n_groups + 2]: list g is
+// gidx[goff[g] .. goff[g+1]), list n_groups = the records outside every sample.  keys_tmp: 2 x n uint16, vals_tmp: n uint32.
+cudaError_t launch_group_index(const uint16_t* group, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
+                               uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s) {
+    if (n > 0) {
+        k_group_keys<<<(n + 255) / 256, 256, 0, s>>>(group, n, n_groups, keys_tmp, vals_tmp);
+        int bits = 1;
+        while ((1 << bits) <= n_groups) bits++;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint16_t*)keys_tmp, keys_tmp + n, (const uint32_t*)vals_tmp, gidx, n, 0, bits, s);
+        if (e != cudaSuccess) return e;
+    }
+    k_group_offsets<<<(n_groups + 2 + 127) / 128, 128, 0, s>>>(keys_tmp + n, n, n_groups, goff);
+    const long long cells = (long long)(n_groups + 1) * (group_blocks(n) + 1);
+    k_group_blocks<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(gidx, goff, n_groups, group_blocks(n), gblk);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------------------

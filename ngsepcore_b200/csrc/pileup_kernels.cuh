@@ -41,6 +41,10 @@ struct TileDev {
     const ngsep_read_hdr* hdr;   // [n_reads + 1], sentinel at n_reads carries off = n_words, first = INT_MAX
     const uint32_t* payload;
     const uint16_t* group;       // [n_reads] read-group id per record (multi-sample contexts), else null
+    const uint32_t* gidx;        // multi-sample contexts: record indexes sorted by read group (stable), see launch_group_index
+    const uint32_t* goff;        //                        [n_groups + 2] list offsets into gidx; list n_groups = records outside every sample
+    const uint32_t* gblk;        //                        [n_groups + 1][n_gblk + 1] list position of the first record index >= b * 256
+    int n_gblk;
     const uint8_t* qual;         // phred+33 bytes, addressed through the records' qoff (only k_genotype_columns reads them)
     int n_reads, max_span, max_back;
     int tile_first, tile_last, seq_idx;
@@ -97,8 +101,11 @@ void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, u
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
-void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
-constexpr int kMultiThreads = 128;
+void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s);
+size_t group_index_temp_bytes(int n);
+cudaError_t launch_group_index(const uint16_t* group, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
+                               uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s);
+int group_blocks(int n);   // blocks of record indexes in the per-group block table
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
 }  // namespace ngsep_b200
