@@ -659,7 +659,12 @@ int ngsep_samples_set(void* ctx, int32_t n_groups, const int32_t* sample_group_o
     }
     CK(cudaSetDevice(c->device), "set device");
     CK(cudaStreamSynchronize(c->stream), "drain");
-    if (!std::getenv("NGSEP_MULTI_BLOCKS_PER_SM")) c->multi_grid = c->sm_count * (n_samples + 1 <= 64 ? 16 : 8);   // narrower CTAs for a short sample axis
+    {   // one wave of persistent CTAs (the kernel's column loop is grid-strided)
+        int per_sm = genotype_multi_ctas_per_sm(n_samples);
+        if (per_sm < 1) return fail(c, NGSEP_ECUDA, "the multi-sample kernel cannot be made resident");
+        if (const char* e = std::getenv("NGSEP_MULTI_BLOCKS_PER_SM")) { int v = std::atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+        c->multi_grid = c->sm_count * per_sm;
+    }
     CK(c->d_sgo.reserve((size_t)n_samples + 1), "sample table alloc");
     CK(c->d_sgroups.reserve((size_t)std::max(total, 1)), "sample table alloc");
     CK(c->d_scratch.reserve((size_t)c->multi_grid * (size_t)n_samples), "scratch alloc");

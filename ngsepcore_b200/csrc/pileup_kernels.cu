@@ -1132,6 +1132,7 @@ __device__ __forceinline__ int list_lower_bound(const uint32_t* __restrict__ lst
 }
 
 struct SampleAcc { double L[10]; int c0, c1, c2, c3, depth; };
+constexpr int kInFlight = 6;
 
 __device__ __forceinline__ void sample_add(SampleAcc& a, uint32_t code, const double* s_tab) {
     if (code & kCodeCall) a.depth++;                                   // CH:210
@@ -1150,7 +1151,7 @@ __device__ __forceinline__ void sample_add(SampleAcc& a, uint32_t code, const do
 }
 
 template <int kThr>
-__global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+__global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
     __shared__ int s_pool[5];            // pooled A, C, G, T counts and totalCount
     __shared__ int s_red[4];             // [0] called-allele mask, [1] best quality, [2] output slot
@@ -1197,10 +1198,10 @@ __global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* 
                 const uint32_t* blk = d.gblk + (size_t)g * (size_t)(d.n_gblk + 1);
                 int ka = list_lower_bound(lst, blk, d.n_gblk, (uint32_t)i_lo);
                 const int kb = list_lower_bound(lst, blk, d.n_gblk, (uint32_t)i_hi);
-                for (; ka < kb; ka += 4) {   // four records in flight: their loads are independent, the sums stay in list order
-                    uint32_t code[4];
+                for (; ka < kb; ka += kInFlight) {   // several records in flight: their loads are independent, the sums stay in list order
+                    uint32_t code[kInFlight];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < kInFlight; u++) {
                         code[u] = 0u;
                         if (ka + u < kb) {
                             const ngsep_read_hdr h = R.header((int)__ldg(lst + ka + u));
@@ -1208,7 +1209,7 @@ __global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* 
                         }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) sample_add(a, code[u], s_tab);
+                    for (int u = 0; u < kInFlight; u++) sample_add(a, code[u], s_tab);
                 }
             }
             if (smp <= n_samples) {   // pooled counts: every record of the column is in exactly one list
@@ -1254,6 +1255,15 @@ __global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* 
             int best = 0;
             for (int smp = tid; smp < n_samples; smp += kThr) {
                 ngsep_sample_call& sc = scratch[smp];
+                // A sample without one counted base of any alternative allele of the list is called homozygous reference
+                // (or left undecided): every other genotype has at most the likelihood of (ref,ref) and a smaller or
+                // equal prior.  It cannot add an allele or raise the variant quality, so its posterior is
+                // only computed if the site turns out to be reported (g0 = -2: pending).
+                if (prm.fast_homref) {
+                    int alt = 0;
+                    for (int k = 1; k < nA; k++) alt += sc.count[A[k]];
+                    if (alt == 0) { if (final_pass) { sc.gq = 0; sc.g0 = -2; sc.g1 = -2; } continue; }
+                }
                 double L[10];
 #pragma unroll
                 for (int k = 0; k < 10; k++) L[k] = sc.logcond[k];
@@ -1293,6 +1303,21 @@ __global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* 
         // reference or left undecided, so variantQS == 0 and MSVD:533 drops it
         if (nA < 2) continue;
         if (qs == 0 || qs < prm.min_quality) continue;                              // MSVD:533
+        for (int smp = tid; smp < n_samples; smp += kThr) {   // the site is reported: the pending samples get their genotype now
+            ngsep_sample_call& sc = scratch[smp];
+            if (sc.g0 != -2) continue;
+            double L[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) L[k] = sc.logcond[k];
+            uint32_t g = 0xffffu;
+            if (sc.depth > 0) {
+                SamplePost P;
+                sample_posteriors(L, lp_hom, lp_het, P);
+                g = sample_genotype(P, sc.depth, A, nA, prm.sample_min_quality);
+            }
+            const int g0 = (int)(g & 0xffu), g1 = (int)((g >> 8) & 0xffu);
+            sc.gq = (int16_t)(g >> 16); sc.g0 = (g0 == 0xff) ? (int8_t)-1 : (int8_t)g0; sc.g1 = (g1 == 0xff) ? (int8_t)-1 : (int8_t)g1;
+        }
         if (tid == 0) s_red[2] = (int)atomicAdd(d.n_calls, 1u);
         __syncthreads();
         const unsigned int slot = (unsigned int)s_red[2];
@@ -1310,6 +1335,15 @@ __global__ void __launch_bounds__(kThr) k_genotype_columns_multi(const TileDev* 
             for (int k = tid; k < n_words; k += kThr) dst[k] = src[k];
         }
     }
+}
+
+// CTAs per SM that are resident at once: the column loop is grid-strided, so the grid must not exceed one wave
+int genotype_multi_ctas_per_sm(int n_samples) {
+    int n = 0;
+    if (n_samples + 1 <= 32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<32>, 32, 0);
+    else if (n_samples + 1 <= 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<64>, 64, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<128>, 128, 0);
+    return n;
 }
 
 void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s) {

@@ -102,6 +102,7 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s);
+int genotype_multi_ctas_per_sm(int n_samples);
 size_t group_index_temp_bytes(int n);
 cudaError_t launch_group_index(const uint16_t* group, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
                                uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s);

@@ -74,3 +74,12 @@ def test_options_quality_ignore(oracle, tmp_path):
               ctx_kw=dict(max_base_qs=20, min_quality=20, het_rate=0.01, flags=capi.F_IGNORE_LOWER_REF),
               oracle_args=("-maxBaseQS", "20", "-minQuality", "20", "-h", "0.01", "-ignoreLowerCaseRef", "-ignore5", "3", "-ignore3", "7"),
               pack_kw=dict(ignore5=3, ignore3=7))
+
+
+def test_panel_depth_1000x(oracle, tmp_path):
+    """BASELINE configs[4] depth stress: a 1000x targeted panel with the per-start cap lifted (-maxAlnsPerStartPos 0, as a
+    panel needs: APG:425); columns of ~1000 records stream through the stage chunk by chunk and the genotype kernel sums
+    a thousand terms per likelihood in pileup order."""
+    n = _run_case(oracle, tmp_path, [("panel", 3000)], 1000, sim_kw=dict(seeds=(41, 42, 43), snv_rate=4e-3), admit_kw=dict(max_alns_per_start=0),
+                  oracle_args=("-maxAlnsPerStartPos", "0"))
+    assert n >= 5
