@@ -215,25 +215,25 @@ def run_gpu(args):
     IN_FLIGHT = 3   # tiles between ngsep_tile_submit and ngsep_tile_fetch (the C ABI pipelines up to 4)
 
     def e2e_step():
-        n_calls, pending = 0, 0
+        n_calls, pending, copied, in_place = 0, 0, 0, 0
         for ci, t in enumerate(tiles):
             if not t["hdr"].size:
                 continue
             if pending == IN_FLIGHT:
                 c, _, st = ctx.fetch(sort=False)
-                n_calls += len(c); pending -= 1
+                n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
             ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"])
             pending += 1
         while pending:
             c, _, st = ctx.fetch(sort=False)
-            n_calls += len(c); pending -= 1
-        return n_calls
+            n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
+        return n_calls, copied, in_place
     for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n_calls_e2e = e2e_step()
+        n_calls_e2e, e2e_copied, e2e_in_place = e2e_step()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -252,7 +252,7 @@ def run_gpu(args):
                     "note": "whole detector from decoded records on 1 host thread: admission + realigner pre-pass + packing + device + VCF text"}
 
     (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
-        dist, "cuda", sums=[covered, aligned_bases, h2d_bytes, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
+        dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -276,7 +276,13 @@ def run_gpu(args):
                          "kernel": "k_pileup_windows", "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": pileup_ms / args.steps,
                          "launches_per_step": 1, "both_kernels_ms_per_step": kernels_ms / args.steps, "peak_source": peak_src},
             "e2e": {"value": covered_all * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
-                    "d2h_bytes_per_step": int(calls_all * 224 + 36 * len(slots) * world), "ms_per_step": e2e_s / args.steps * 1e3},
+                    "d2h_bytes_per_step": int(calls_all * 224 + 36 * len(slots) * world), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "host_input_bytes_per_step": int(h2d_bytes * world), "same_calls_as_resident_run": bool(n_calls_e2e == calls),
+                    "quality_in_place_tiles": int(e2e_in_place),
+                    "note": "h2d_bytes_per_step = bytes ngsep_tile_submit copies (record headers + payload); the phred bytes (%.0f MB) stay in the "
+                            "caller's page-locked buffers and k_genotype_columns reads the ~%d x depth bytes it needs in place over PCIe "
+                            "(NGSEP_LAZY_QUAL=0 copies them as well)" % ((h2d_bytes - e2e_copied) / 1e6, int(st.open_columns)) if e2e_in_place else
+                            "every host buffer of the step is copied host -> device"},
             "pipeline": pipeline,
             "gpu_launches": int(launches_all * args.steps),
             "clocks": clocks,

@@ -169,6 +169,9 @@ typedef struct ngsep_tile_stats {
     float pileup_ms;             /* of which: the window kernel (k_pileup_windows)                        */
     uint32_t kernel_launches;    /* kernels launched for the tile                                        */
     uint32_t open_columns;       /* positions the window kernel left to k_genotype_columns (whole launch) */
+    uint64_t h2d_bytes;          /* bytes of the tile copied host -> device at staging                     */
+    uint32_t quality_in_place;   /* 1: the quality bytes stayed in the caller's page-locked buffer and were read on demand */
+    uint32_t reserved;
 } ngsep_tile_stats;
 
 /* Context = one GPU + one stream + device-resident reference.  Replaces the construction of
@@ -220,7 +223,10 @@ int ngsep_timer_start(void* ctx);
 int ngsep_timer_stop(void* ctx, float* elapsed_ms);   /* synchronises the stream */
 
 /* Page-locks / releases a caller-owned host buffer (what a JVM host does for its direct ByteBuffers) so that
- * ngsep_tile_submit copies asynchronously at full PCIe rate. */
+ * ngsep_tile_submit copies asynchronously at full PCIe rate.  When ngsep_tile.qual is page-locked, a single-sample
+ * ngsep_tile_submit does not copy it at all: quality bytes are only needed at the few positions that reach the genotype
+ * kernel, which then reads them in place (ngsep_tile_stats.quality_in_place; NGSEP_LAZY_QUAL=0 in the environment
+ * restores the copy).  The buffers must stay valid and unchanged until the tile has been fetched — as before. */
 int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 

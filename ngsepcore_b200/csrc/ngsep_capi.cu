@@ -68,6 +68,8 @@ struct Slot {
     bool staged = false, launched = false, in_batch = false, pipelined = false;
     int grid = 0;
     uint64_t aligned_bases = 0;
+    uint64_t h2d_bytes = 0;                   // bytes of the tile copied to the device at staging
+    bool qual_on_host = false;                // quality bytes stay in the caller's page-locked buffer (read on demand by the genotype kernel)
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
@@ -95,6 +97,7 @@ struct Ctx {
     DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch;
     DevBuf<uint16_t> d_gkeys; DevBuf<uint32_t> d_gvals; DevBuf<unsigned char> d_cub;   // staging scratch of launch_group_index (stream-ordered reuse)
     int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
+    bool lazy_qual = true;                    // NGSEP_LAZY_QUAL=0 turns the in-place quality reads off
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
     std::vector<RefSeq> refs;
     std::vector<Slot*> slots;                 // slot 0 = first submit/fetch slot, 1.. = resident tiles
@@ -268,7 +271,18 @@ int read_report(Ctx* c, Slot* s) {
     return NGSEP_OK;
 }
 
-int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
+// Is [p, p + bytes) page-locked host memory the device can read in place?  (cudaHostRegister / cudaHostAlloc; the
+// device alias is returned.)
+const uint8_t* mapped_host_alias(const void* p, size_t bytes) {
+    if (!p || !bytes) return nullptr;
+    cudaPointerAttributes a0{}, a1{};
+    if (cudaPointerGetAttributes(&a0, p) != cudaSuccess || cudaPointerGetAttributes(&a1, (const char*)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+    if ((const char*)a1.devicePointer - (const char*)a0.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;   // one contiguous mapping
+    return (const uint8_t*)a0.devicePointer;
+}
+
+int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = false) {
     if (!t) return fail(c, NGSEP_EINVAL, "null argument");
     if (t->n_reads < 0 || t->tile_first < 1 || t->tile_last < t->tile_first) return fail(c, NGSEP_EINVAL, "bad tile extents");
     if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
@@ -280,10 +294,16 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
     CK(cudaSetDevice(c->device), "set device");
     const RefSeq& ref = c->refs[t->seq_idx];
-    // the copies start first; the host-side validation below runs while they are in flight
+    // Quality bytes are only read for the positions that reach k_genotype_columns (a fraction of a percent of a
+    // single-sample tile): when the caller's quality buffer is page-locked (ngsep_host_register) a pipelined tile leaves
+    // it where it is and the kernel reads the few bytes it needs in place, over PCIe.  Multi-sample contexts and the
+    // EMIT_ALL test hook evaluate every column: they always copy.
+    const uint8_t* host_qual = nullptr;
+    if (allow_host_qual && c->lazy_qual && !multi && !(c->params.flags & NGSEP_F_EMIT_ALL) && t->n_reads > 0) host_qual = mapped_host_alias(t->qual, (size_t)t->n_qual);
+    s->qual_on_host = host_qual != nullptr;
     {   // pipeline slots grow together: a slot takes the largest capacity any of them has needed so far, so that cycling
         // tiles of different sizes through the ring stops reallocating after the first pass
-        size_t need_h = (size_t)t->n_reads + 1, need_p = (size_t)t->n_words + 16, need_q = (size_t)t->n_qual + 16;
+        size_t need_h = (size_t)t->n_reads + 1, need_p = (size_t)t->n_words + 16, need_q = host_qual ? 0 : (size_t)t->n_qual + 16;
         if (s->pipelined) for (Slot* r : c->ring) { need_h = std::max(need_h, r->d_hdr.cap); need_p = std::max(need_p, r->d_pay.cap); need_q = std::max(need_q, r->d_qual.cap); }
         if (need_h > s->d_hdr.cap) { s->d_hdr.release(); CK(cudaMalloc((void**)&s->d_hdr.p, need_h * sizeof(ngsep_read_hdr)), "hdr alloc"); s->d_hdr.cap = need_h; }
         if (need_p > s->d_pay.cap) { s->d_pay.release(); CK(cudaMalloc((void**)&s->d_pay.p, need_p * sizeof(uint32_t)), "payload alloc"); s->d_pay.cap = need_p; }
@@ -309,8 +329,10 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
     if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
-        CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->stream), "quality copy");
+        if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->stream), "quality copy");
     }
+    s->h2d_bytes = (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
+                   (multi ? (uint64_t)t->n_reads * 2 : 0);
     s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
     CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
@@ -329,7 +351,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t) {
         T = std::max(128, (T / 2) & ~127);
     TileDev& d = s->tile;
     d = TileDev{};
-    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = s->d_qual.p;
+    d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = host_qual ? host_qual : s->d_qual.p;
     d.gidx = multi ? s->d_gidx.p : nullptr; d.goff = multi ? s->d_goff.p : nullptr;
     d.gblk = multi ? s->d_gblk.p : nullptr; d.n_gblk = multi ? group_blocks(t->n_reads) : 0;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
@@ -425,6 +447,8 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         stats->candidate_positions = meta.ctr[1];
         stats->calls = n;
         stats->aligned_bases = s->aligned_bases;
+        stats->h2d_bytes = s->h2d_bytes;
+        stats->quality_in_place = s->qual_on_host ? 1u : 0u;
         stats->kernel_ms = ms;
         stats->pileup_ms = pms;
         stats->kernel_launches = s->launches;
@@ -501,6 +525,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.threads, c->cfg.min_blocks);
     if (c->ctas_per_sm < 1) { g_global_err = "the pileup kernel cannot be made resident with this configuration"; delete c; return NGSEP_ECUDA; }
     if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
+    if (const char* s = std::getenv("NGSEP_LAZY_QUAL")) c->lazy_qual = std::atoi(s) != 0;
     c->geno_grid = c->sm_count * 16;
     if (const char* s = std::getenv("NGSEP_GENO_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 256) c->geno_grid = c->sm_count * v; }
     Slot* s0 = nullptr;
@@ -614,7 +639,7 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
     if (!c) return NGSEP_EINVAL;
     if (c->ring_count == c->ring.size()) return fail(c, NGSEP_ESTATE, "too many tiles in flight: call ngsep_tile_fetch first");
     Slot* s = c->ring[c->ring_head];
-    int rc = stage_slot(c, s, t);
+    int rc = stage_slot(c, s, t, true);
     if (rc != NGSEP_OK) return rc;
     rc = launch_slot(c, s);
     if (rc != NGSEP_OK) return rc;

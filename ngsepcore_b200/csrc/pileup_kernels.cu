@@ -957,6 +957,10 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
 
+        // one stage: the next window's copies start NOW (its descriptor has been in dq[0] since the top of this iteration), so
+        // that their latency overlaps the tail of this window instead of opening the next iteration
+        if (tid == 0 && n_stages == 1 && wn < a.n_windows) { issue_window(t0.dq[0], wn, 0); t0.prefetched = 1; }
+
         // warp 0 hands the open columns to the global list (the other warps move on; s_open and mset are per window parity)
         if (warp == 0) {
             const int n_open = min(mset[M_NOPEN], kMaxOpen);

@@ -27,7 +27,7 @@ def test_struct_layouts_match_header():
     assert capi.HDR_DTYPE.itemsize == 16
     assert capi.CALL_DTYPE.itemsize == 224
     assert C.sizeof(capi.Params) == 32
-    assert C.sizeof(capi.Tile) == 72 and C.sizeof(capi.TileStats) == 48
+    assert C.sizeof(capi.Tile) == 72 and C.sizeof(capi.TileStats) == 64
     assert capi.SITE_DTYPE.itemsize == 44 and capi.SAMPLE_CALL_DTYPE.itemsize == 104   # ngsep_pop_site, ngsep_sample_call
 
 

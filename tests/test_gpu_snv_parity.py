@@ -83,3 +83,27 @@ def test_panel_depth_1000x(oracle, tmp_path):
     n = _run_case(oracle, tmp_path, [("panel", 3000)], 1000, sim_kw=dict(seeds=(41, 42, 43), snv_rate=4e-3), admit_kw=dict(max_alns_per_start=0),
                   oracle_args=("-maxAlnsPerStartPos", "0"))
     assert n >= 5
+
+
+def test_quality_read_in_place_matches_copy(tmp_path):
+    """A single-sample tile whose quality buffer is page-locked is not copied: k_genotype_columns reads the bytes it needs
+    from the caller's buffer.  Same calls, bit for bit, as the copying path."""
+    genome, batch, _ = simulate.simulate(contigs=[("c1", 150000)], depth=30, indel_rate=0.0, seeds=(61, 62, 63))
+    idx = pypack.admit(batch)
+    hdr, pay, qual, span = pypack.pack_tile(batch, idx)
+    with capi.Context() as ctx:
+        ctx.ref_upload(0, genome["c1"])
+        ctx.submit(0, 1, 150000, hdr, pay, qual, span)
+        a, _, st_a = ctx.fetch()
+        assert st_a.quality_in_place == 0 and st_a.h2d_bytes == hdr.nbytes + pay.nbytes + qual.nbytes
+        capi.host_register(qual)
+        try:
+            ctx.submit(0, 1, 150000, hdr, pay, qual, span)
+            b, _, st_b = ctx.fetch()
+        finally:
+            capi.host_unregister(qual)
+        assert st_b.quality_in_place == 1 and st_b.h2d_bytes == hdr.nbytes + pay.nbytes
+        assert len(a) > 100 and len(a) == len(b)
+        for name in a.dtype.names:      # field by field: the struct's padding bytes are not written by the device
+            assert np.array_equal(a[name], b[name]), name
+        assert st_a.covered_positions == st_b.covered_positions   # (open_columns may differ: which record flags a position first is a race)
