@@ -52,6 +52,7 @@ struct Slot {
     DevBuf<uint8_t> d_qual;
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
+    DevBuf<uint4> d_open;                     // single-tile launches: the tile's own open-column list (its counter sits in d_counters)
     DevBuf<uint16_t> d_group;                 // multi-sample contexts: read-group id per record
     DevBuf<uint32_t> d_gidx, d_goff, d_gblk;          //                        records indexed by read group (launch_group_index)
     DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
@@ -63,6 +64,7 @@ struct Slot {
     unsigned int* d_ncalls = nullptr;         // inside Ctx::d_meta
     unsigned long long* d_counters = nullptr; // inside Ctx::d_meta
     cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // before the pileup kernel / between the two kernels / after
+    cudaEvent_t e_copy = nullptr;                           // the tile's host -> device copies (copy stream) are done
     TileDev tile{};
     struct Pinned { ngsep_read_hdr sentinel; TileDev tile; }* pin = nullptr;   // page-locked: small copies stay asynchronous
     bool staged = false, launched = false, in_batch = false, pipelined = false;
@@ -73,10 +75,11 @@ struct Slot {
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
-        d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release();
+        d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
+        if (e_copy) cudaEventDestroy(e_copy);
         if (e0) cudaEventDestroy(e0);
         if (em) cudaEventDestroy(em);
         if (e1) cudaEventDestroy(e1);
@@ -86,7 +89,9 @@ struct Slot {
 
 struct Ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;            // every kernel of the context
+    cudaStream_t copy_stream = nullptr;       // bulk host -> device copies of staged tiles
+    cudaStream_t geno_stream = nullptr;       // genotype kernels of single-tile launches
     cudaEvent_t t0 = nullptr, t1 = nullptr;   // stopwatch
     cudaEvent_t b0 = nullptr, bm = nullptr, b1 = nullptr;   // around / between the kernels of the batched run
     ngsep_params params{};
@@ -134,6 +139,7 @@ int new_slot(Ctx* c, Slot** out, size_t id) {   // id = index of the slot's 32-b
     s->d_ncalls = (unsigned int*)(c->d_meta + (1 + id) * kMetaStride + 16);
     cudaError_t e = cudaMalloc((void**)&s->d_tile, sizeof(TileDev) + 16);   // + the staging report (k_check_headers)
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->pin, sizeof(Slot::Pinned), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->e_copy, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&s->e0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->em);
     if (e == cudaSuccess) e = cudaEventCreate(&s->e1);
@@ -165,9 +171,16 @@ int ensure_queue(Ctx* c, size_t cols) {
     return NGSEP_OK;
 }
 
-ColumnQueue queue_view(Ctx* c) {
+ColumnQueue queue_view(Ctx* c) {   // the batched launch over the resident tiles
     ColumnQueue q;
     q.open = c->d_open.p; q.ctr = (unsigned int*)c->d_meta; q.cap_open = (unsigned int)c->d_open.cap;
+    return q;
+}
+// A single-tile launch has its own list: its kernels may overlap those of the next tile.  The kernels only touch ctr[2],
+// which is placed on the n_open word (byte 20) of the slot's counter block.
+ColumnQueue queue_view(Slot* s) {
+    ColumnQueue q;
+    q.open = s->d_open.p; q.ctr = (unsigned int*)((unsigned char*)s->d_counters + 12); q.cap_open = (unsigned int)s->d_open.cap;
     return q;
 }
 
@@ -188,24 +201,25 @@ int launch_slot(Ctx* c, Slot* s) {
     if (!s->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
     size_t cols = 0;
     queue_need(c, s, cols);
-    int rc = ensure_queue(c, cols);
-    if (rc != NGSEP_OK) return rc;
-    CK(cudaMemsetAsync(c->d_meta, 0, kMetaStride, c->stream), "memset queue counters");
+    cols = std::max(cols, c->q_min_cols);
+    if (cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "open-column list too large (split the tile)");
+    CK(s->d_open.reserve(cols), "open-column list alloc");   // the slot is idle here (its previous tile has been fetched)
     CK(cudaMemsetAsync(s->d_counters, 0, kMetaStride, c->stream), "memset counters");
     s->launches = 0;
-    rc = clear_counts_dbg(c, s);
+    int rc = clear_counts_dbg(c, s);
     if (rc != NGSEP_OK) return rc;
     CK(cudaEventRecord(s->e0, c->stream), "event record");
-    if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(c), c->cfg, s->grid, c->smem, c->stream);
+    if (s->tile.n_windows > 0) launch_pileup(s->d_tile, s->d_win.p, s->tile.n_windows, c->d_prm, queue_view(s), c->cfg, s->grid, c->smem, c->stream);
     CK(cudaEventRecord(s->em, c->stream), "event record");
+    // The genotype kernel runs on its own stream behind the tile's window kernel: the context stream goes on with the next
+    // tile (staging kernels, window kernel) meanwhile.  Genotype launches are ordered among themselves (shared scratch).
+    CK(cudaStreamWaitEvent(c->geno_stream, s->em, 0), "wait for the window kernel");
     if (s->tile.n_windows > 0) {
-        if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(c), c->d_prm, c->params.n_samples, c->multi_grid, c->stream);
-        else launch_genotype(s->d_tile, queue_view(c), c->d_prm, c->geno_grid, c->stream);
+        if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(s), c->d_prm, c->params.n_samples, c->multi_grid, c->geno_stream);
+        else launch_genotype(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         s->launches = 2;
     }
-    // the open-column counter is shared by every launch of the context: keep this tile's value with the tile
-    CK(cudaMemcpyAsync((unsigned char*)s->d_counters + 20, c->d_meta + 8, 4, cudaMemcpyDeviceToDevice, c->stream), "open counter copy");
-    CK(cudaEventRecord(s->e1, c->stream), "event record");
+    CK(cudaEventRecord(s->e1, c->geno_stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
     s->launched = true;
     s->in_batch = false;
@@ -310,7 +324,18 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         if (need_q > s->d_qual.cap) { s->d_qual.release(); CK(cudaMalloc((void**)&s->d_qual.p, need_q), "quality alloc"); s->d_qual.cap = need_q; }
     }
     if (multi) CK(s->d_group.reserve((size_t)t->n_reads + 16), "read-group alloc");
-    if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream), "read-group copy");
+    // The bulk copies run on the COPY stream, the kernels on the context stream: the copies of the next tile overlap the
+    // kernels of this one (a slot's buffers are only reused after its tile has been fetched).
+    if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream), "read-group copy");
+    if (t->n_reads > 0) {
+        CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->copy_stream), "hdr copy");
+        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->copy_stream), "payload copy");
+        if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->copy_stream), "quality copy");
+    }
+    s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
+    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->copy_stream), "sentinel copy");
+    CK(cudaEventRecord(s->e_copy, c->copy_stream), "copy event");
+    CK(cudaStreamWaitEvent(c->stream, s->e_copy, 0), "wait for the copies");
     if (multi) {   // records indexed by read group; the scratch buffers are shared by the context (growing them waits for the stream)
         const size_t n = (size_t)t->n_reads;
         const size_t cub_bytes = group_index_temp_bytes(t->n_reads);
@@ -326,15 +351,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         CK(launch_group_index(s->d_group.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
            "group index launch");
     }
-    if (t->n_reads > 0) {
-        CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "hdr copy");
-        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->stream), "payload copy");
-        if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->stream), "quality copy");
-    }
     s->h2d_bytes = (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
                    (multi ? (uint64_t)t->n_reads * 2 : 0);
-    s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
-    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->stream), "sentinel copy");
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
     // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
     CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
@@ -410,13 +428,12 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         if (s->in_batch) {
             int rc = queue_overflowed(c, &grew);
             if (rc != NGSEP_OK) return rc;
-        } else if (meta.n_open > c->d_open.cap) {
+        } else if (meta.n_open > s->d_open.cap) {
             c->q_min_cols = std::max(c->q_min_cols, (size_t)meta.n_open + (size_t)meta.n_open / 4 + 1024);
             grew = 1;
         }
         if (meta.n_calls <= s->tile.cap_calls && !grew) break;
         if (attempt == 3) return fail(c, NGSEP_EOVERFLOW, "call / column buffer overflow");
-        if (grew && !s->in_batch) CK(cudaStreamSynchronize(c->stream), "drain before growing the open-column list");   // later tiles use the list too
         if (meta.n_calls > s->tile.cap_calls) {   // grow and rerun the staged tile
             if (!s->in_batch) CK(cudaStreamSynchronize(c->stream), "drain before growing the call buffers");
             if (multi) {
@@ -508,6 +525,8 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (const char* s = std::getenv("NGSEP_STAGES")) { int v = std::atoi(s); if (v == 1 || v == 2) c->cfg.n_stages = v; }
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->geno_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->t0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->t1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->b0);
@@ -585,6 +604,8 @@ int ngsep_ctx_destroy(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
     cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->geno_stream) cudaStreamSynchronize(c->geno_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& r : c->refs) r.release();
     for (Slot* s : c->slots) { s->release(); delete s; }
@@ -598,6 +619,8 @@ int ngsep_ctx_destroy(void* ctx) {
     if (c->b0) cudaEventDestroy(c->b0);
     if (c->bm) cudaEventDestroy(c->bm);
     if (c->b1) cudaEventDestroy(c->b1);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->geno_stream) cudaStreamDestroy(c->geno_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NGSEP_OK;
