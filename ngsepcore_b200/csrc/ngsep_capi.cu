@@ -590,6 +590,10 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
         }
     }
     hp.n_samples = params->n_samples;
+    hp.column_run = 1;
+    if (const char* s = std::getenv("NGSEP_MULTI_RUN")) { int v = std::atoi(s); if (v >= 1 && v <= 256) hp.column_run = v; }
+    hp.multi_ordered = 1;
+    if (const char* s = std::getenv("NGSEP_MULTI_ORDERED")) hp.multi_ordered = std::atoi(s) != 0;
     hp.sample_min_quality = 40;   // the per-sample listener of MSVD.genotypeVariant is a fresh one: SSVPL.DEF_MIN_QUALITY (MSVD:676-678, SSVPL:50)
     c->hp = hp;
     c->multi_grid = c->sm_count * 8;

@@ -5,6 +5,7 @@
 #include "pileup_kernels.cuh"
 
 #include <climits>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace ngsep_b200 {
@@ -914,6 +915,55 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             const unsigned int gbase = (unsigned int)mset[M_R1];
             for (int i = tid; i < n_all; i += nthr)
                 if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)wr.tile, (unsigned int)(g_lo + i + 1), 0u, kOpenSearch);
+        } else if (multi && prm.multi_ordered && n_cand > 0) {
+            // Sample axis: no proof is attempted.  The window's candidates go to k_genotype_columns_multi IN POSITION ORDER
+            // and as one contiguous piece of the list: a CTA there walks a run of neighbouring columns, whose records are
+            // largely the same (L1 reuse).  Bitmap of the open positions -> ordered list -> record range per position.
+            const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
+            const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
+            uint32_t* s_bm = (uint32_t*)s_ulist;
+            const int nw = (a.cfg.T_lay + 31) >> 5;
+            for (int i = tid; i < nw; i += nthr) s_bm[i] = 0u;
+            __syncthreads();
+            for (int ci = tid; ci < n_cand; ci += nthr) {
+                const int li = (int)(s_list[ci] & kListPosMask);
+                s_cnt[li] = 0u;   // (nothing else clears s_cnt)
+                bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // SSVPL:298-305
+                if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
+                if (!closed) atomicOr(&s_bm[li >> 5], 1u << (li & 31));
+            }
+            __syncthreads();
+            for (int wi = tid; wi <= nw; wi += nthr) {
+                int o = 0;
+                for (int k = 0; k < wi; k++) o += __popc(s_bm[k]);
+                if (wi == nw) {   // the total: one reservation in the global list for the whole window
+                    mset[M_NUNRES] = o;
+                    mset[M_R1] = o ? (int)atomicAdd(&a.cq.ctr[2], (unsigned int)o) : 0;
+                } else {
+                    uint32_t bits = s_bm[wi];
+                    while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1u; s_list[o++] = (uint32_t)((wi << 5) | b); }
+                }
+            }
+            __syncthreads();
+            const int n_o = mset[M_NUNRES];
+            const unsigned int gbase = (unsigned int)mset[M_R1];
+            const int max_span = (int)(wr.span_pack & 0xffffu), max_back = (int)(wr.span_pack >> 16);
+            for (int k = warp; k < n_o; k += nwarps) {
+                const int e_pos = wbeg + (int)s_list[k] + 1;
+                int i_lo, i_hi;
+                if (single) {
+                    Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
+                    i_lo = warp_lower_bound<false>(R, e_pos - max_span + 1, lane);
+                    i_hi = warp_lower_bound<false>(R, e_pos + max_back + 1, lane);
+                } else {
+                    const TileDev& d = a.tiles[wr.tile];
+                    Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
+                    i_lo = warp_lower_bound<true>(R, e_pos - max_span + 1, lane);
+                    i_hi = warp_lower_bound<true>(R, e_pos + max_back + 1, lane);
+                }
+                if (lane == 0 && gbase + (unsigned int)k < a.cq.cap_open)
+                    a.cq.open[gbase + k] = make_uint4((unsigned int)wr.tile, (unsigned int)e_pos, (unsigned int)(wr.lo + i_lo), (uint32_t)min(max(i_hi - i_lo, 0), (int)kOpenSearch));
+            }
         } else if (n_cand > 0) {
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
@@ -1168,7 +1218,10 @@ __global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(co
     const int n_batches = (n_samples + 1 + kThr - 1) / kThr;   // + the list of the records that belong to no sample
     ngsep_sample_call* scratch = prm.scratch + (size_t)blockIdx.x * (size_t)n_samples;
     const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
-    for (unsigned int t = blockIdx.x; t < n_open; t += gridDim.x) {
+    // a CTA takes RUNS of kColumnRun neighbouring list entries: the window kernel lists a window's columns in position order,
+    // so the columns of a run share most of their records and a sample's thread finds them in L1 again
+    const unsigned int run = (unsigned int)max(1, prm.column_run);
+    for (unsigned int t = blockIdx.x * run; t < n_open; t = ((t + 1) % run) ? t + 1 : t + 1 + (gridDim.x - 1) * run) {
         __syncthreads();   // every `continue` below is uniform over the CTA; the previous column's shared state is free from here on
         const uint4 oc = cq.open[t];   // tile, position, first record, number of records
         const TileDev& d = tiles[oc.x];
@@ -1344,6 +1397,11 @@ __global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(co
 // CTAs per SM that are resident at once: the column loop is grid-strided, so the grid must not exceed one wave
 int genotype_multi_ctas_per_sm(int n_samples) {
     int n = 0;
+    if (const char* e = getenv("NGSEP_MULTI_MAX_L1")) if (atoi(e)) {   // experiment: the unified cache goes to L1
+        cudaFuncSetAttribute(k_genotype_columns_multi<32>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(k_genotype_columns_multi<64>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(k_genotype_columns_multi<128>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+    }
     if (n_samples + 1 <= 32) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<32>, 32, 0);
     else if (n_samples + 1 <= 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<64>, 64, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_genotype_columns_multi<128>, 128, 0);

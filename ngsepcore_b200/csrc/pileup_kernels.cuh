@@ -70,6 +70,8 @@ struct DevParams {
     double tables[NGSEP_N_TABLES];
     // sample axis (MultisampleVariantsDetector); n_samples == 1: everything below is unused
     int n_samples, n_groups, max_groups_per_sample;
+    int column_run;                      // k_genotype_columns_multi: neighbouring list entries one CTA takes in a row
+    int multi_ordered;                   // 1: the window kernel lists a window's candidates in position order (sample axis)
     int sample_min_quality;              // minQuality of the fresh per-sample listener: always 40 (MSVD:676-678, SSVPL:50)
     double min_allele_depth_freq;        // MSVD:58
     const int* sample_group_off;         // [n_samples + 1]
