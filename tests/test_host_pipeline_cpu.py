@@ -65,3 +65,27 @@ def test_header_text_matches_oracle(oracle, tmp_path):
     # fixed parts of the header are the reference's own (training/yeastDemo_...vcf.gz carries the same lines)
     assert hdr(got)[0] == "##fileformat=VCFv4.2"
     assert '##FORMAT=<ID=BSDP,Number=4,Type=Integer,Description="Number of base calls (depth) for the 4 nucleotides in called SNVs sorted as A,C,G,T">' in hdr(got)
+
+
+@pytest.mark.parametrize("seed,kw,det_kw,oargs", [
+    (1, dict(n_samples=8, depth=10, mode="wgs", indel_rate=1.5e-3, rgs_per_sample=2, no_rg_frac=0.03), {}, ()),
+    (2, dict(n_samples=12, depth=8, mode="gbs", n_tags=150, indel_rate=2e-3), dict(maxAlnsPerStartPos=100), ("-maxAlnsPerStartPos", "100")),
+    (3, dict(n_samples=5, depth=14, mode="wgs", indel_rate=2e-3, indel_jitter=0.6), dict(minQuality=60, h=0.01), ("-minQuality", "60", "-h", "0.01")),
+])
+def test_population_indel_records_match_oracle(oracle, tmp_path, seed, kw, det_kw, oargs):
+    """MultisampleVariantsDetector, host side only (no GPU): the population indel / STR records — pooled allele clustering,
+    the allele refinement loop, per-sample VD.callIndel(variant), DiversityStatistics INFO — against the oracle's."""
+    genome, batch, _ = simulate.simulate_population([("chrA", 60000), ("chrB", 30000)], seeds=(seed * 100, seed * 100 + 1, seed * 100 + 2), **kw)
+    fa, sam = str(tmp_path / "r.fa"), str(tmp_path / "r.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, _, _, _ = ou.run_msvd(oracle, fa, [sam], args=oargs)
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    det = hostapi.MultisampleDetector(list(zip(batch.rg_names, batch.rg_samples)), host_only=True, **det_kw)
+    det.set_genome(genome)
+    got = det.run(batch)
+    got_lines = [l for l in got.splitlines() if not l.startswith("#")]
+    assert len(want_lines) >= 8
+    assert got_lines == want_lines
+    hdr = lambda t: [l for l in t.splitlines() if l.startswith("#")]
+    assert hdr(got) == hdr(want)      # sample columns in TreeMap order, MSVD:494-515
