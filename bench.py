@@ -143,6 +143,8 @@ def _dist_setup(n_gpus):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout: this program prints ONE JSON line there
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     return rank, world, local, dist
@@ -179,7 +181,9 @@ def run_gpu(args):
     aligned_bases = sum(t["aligned_bases"] for t in tiles)
     genome_len = sum(len(v) for v in genome.values())
 
-    ctx = capi.Context(device=device)
+    # one GPU per host: the phred bytes stay in the page-locked host buffers and are read in place (NGSEP_F_QUALITY_IN_PLACE);
+    # several GPUs reading host memory at once are better served by the bulk copy (measured: profiles/README.md)
+    ctx = capi.Context(device=device, flags=capi.F_QUALITY_IN_PLACE if world == 1 else 0)
     for ci, n in enumerate(names):
         ctx.ref_upload(ci, genome[n])
     slots = []
@@ -281,7 +285,7 @@ def run_gpu(args):
                     "quality_in_place_tiles": int(e2e_in_place),
                     "note": "h2d_bytes_per_step = bytes ngsep_tile_submit copies (record headers + payload); the phred bytes (%.0f MB) stay in the "
                             "caller's page-locked buffers and k_genotype_columns reads the ~%d x depth bytes it needs in place over PCIe "
-                            "(NGSEP_LAZY_QUAL=0 copies them as well)" % ((h2d_bytes - e2e_copied) / 1e6, int(st.open_columns)) if e2e_in_place else
+                            "(NGSEP_F_QUALITY_IN_PLACE, set by this bench at N = 1 only)" % ((h2d_bytes - e2e_copied) / 1e6, int(st.open_columns)) if e2e_in_place else
                             "every host buffer of the step is copied host -> device"},
             "pipeline": pipeline,
             "gpu_launches": int(launches_all * args.steps),

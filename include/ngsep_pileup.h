@@ -32,6 +32,9 @@ extern "C" {
 /* ngsep_params.flags */
 #define NGSEP_F_STRAND_BIAS 0x1u      /* -csb            discovery/SingleSampleVariantsDetector.java:480 (calcStrandBias)   */
 #define NGSEP_F_IGNORE_LOWER_REF 0x2u /* -ignoreLowerCaseRef  discovery/SingleSampleVariantPileupListener.java:198          */
+#define NGSEP_F_QUALITY_IN_PLACE 0x10u /* single-sample tiles whose quality buffer is page-locked are not copied: the genotype kernel
+                                          reads the few quality bytes it needs in place over PCIe (see ngsep_host_register).  Pays on a
+                                          host that feeds ONE GPU; with several GPUs reading host memory at once the bulk copy is faster */
 #define NGSEP_F_EMIT_ALL 0x8u         /* test hook: also return A,C,G,T,DP for every tile position (counts_dbg)             */
 
 /* Options of main/CommandsDescriptor.xml:565-703 that change what the device computes. */
@@ -223,10 +226,11 @@ int ngsep_timer_start(void* ctx);
 int ngsep_timer_stop(void* ctx, float* elapsed_ms);   /* synchronises the stream */
 
 /* Page-locks / releases a caller-owned host buffer (what a JVM host does for its direct ByteBuffers) so that
- * ngsep_tile_submit copies asynchronously at full PCIe rate.  When ngsep_tile.qual is page-locked, a single-sample
- * ngsep_tile_submit does not copy it at all: quality bytes are only needed at the few positions that reach the genotype
- * kernel, which then reads them in place (ngsep_tile_stats.quality_in_place; NGSEP_LAZY_QUAL=0 in the environment
- * restores the copy).  The buffers must stay valid and unchanged until the tile has been fetched — as before. */
+ * ngsep_tile_submit copies asynchronously at full PCIe rate.  With NGSEP_F_QUALITY_IN_PLACE in ngsep_params.flags and a
+ * page-locked ngsep_tile.qual, a single-sample ngsep_tile_submit does not copy the qualities at all: they are only needed
+ * at the few positions that reach the genotype kernel, which then reads them in place (ngsep_tile_stats.quality_in_place;
+ * NGSEP_LAZY_QUAL=0/1 in the environment overrides the flag).  The buffers must stay valid and unchanged until the tile
+ * has been fetched — as before. */
 int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_pileup.so")
 
 N_TABLES = 95
-F_STRAND_BIAS, F_IGNORE_LOWER_REF, F_EMIT_ALL = 0x1, 0x2, 0x8
+F_STRAND_BIAS, F_IGNORE_LOWER_REF, F_EMIT_ALL, F_QUALITY_IN_PLACE = 0x1, 0x2, 0x8, 0x10
 M_NEG, M_NMASK, M_WINDOW, M_SIMPLE = 0x01000000, 0x02000000, 0x04000000, 0x10000000
 CALL_HET, CALL_HOMALT, CALL_TRIALLELIC = 1, 2, 3
 

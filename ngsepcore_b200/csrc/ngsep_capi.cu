@@ -102,7 +102,7 @@ struct Ctx {
     DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch;
     DevBuf<uint16_t> d_gkeys; DevBuf<uint32_t> d_gvals; DevBuf<unsigned char> d_cub;   // staging scratch of launch_group_index (stream-ordered reuse)
     int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
-    bool lazy_qual = true;                    // NGSEP_LAZY_QUAL=0 turns the in-place quality reads off
+    bool lazy_qual = false;                   // NGSEP_F_QUALITY_IN_PLACE (NGSEP_LAZY_QUAL=0/1 overrides)
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
     std::vector<RefSeq> refs;
     std::vector<Slot*> slots;                 // slot 0 = first submit/fetch slot, 1.. = resident tiles
@@ -544,6 +544,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     c->ctas_per_sm = pileup_max_ctas_per_sm(c->smem, c->cfg.threads, c->cfg.min_blocks);
     if (c->ctas_per_sm < 1) { g_global_err = "the pileup kernel cannot be made resident with this configuration"; delete c; return NGSEP_ECUDA; }
     if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
+    c->lazy_qual = (params->flags & NGSEP_F_QUALITY_IN_PLACE) != 0;
     if (const char* s = std::getenv("NGSEP_LAZY_QUAL")) c->lazy_qual = std::atoi(s) != 0;
     c->geno_grid = c->sm_count * 16;
     if (const char* s = std::getenv("NGSEP_GENO_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 256) c->geno_grid = c->sm_count * v; }

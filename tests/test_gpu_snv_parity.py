@@ -91,7 +91,7 @@ def test_quality_read_in_place_matches_copy(tmp_path):
     genome, batch, _ = simulate.simulate(contigs=[("c1", 150000)], depth=30, indel_rate=0.0, seeds=(61, 62, 63))
     idx = pypack.admit(batch)
     hdr, pay, qual, span = pypack.pack_tile(batch, idx)
-    with capi.Context() as ctx:
+    with capi.Context(flags=capi.F_QUALITY_IN_PLACE) as ctx:
         ctx.ref_upload(0, genome["c1"])
         ctx.submit(0, 1, 150000, hdr, pay, qual, span)
         a, _, st_a = ctx.fetch()
