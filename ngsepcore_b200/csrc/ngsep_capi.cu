@@ -117,7 +117,7 @@ struct Ctx {
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
     int sm_count = 0;
-    LaunchCfg cfg{1280, 6400u, 1, 4, 256};
+    LaunchCfg cfg{1280, 6400u, 1, 4, 256, 0};   // L2 prefetch of the window after next: measured 1 % slower, off (NGSEP_L2_PREFETCH=1)
     size_t smem = 0;
     int ctas_per_sm = 1;
     int geno_grid = 0;                        // blocks of k_genotype_columns
@@ -523,6 +523,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (const char* s = std::getenv("NGSEP_WINDOW")) { int v = std::atoi(s); if (v >= 128 && (v % 128) == 0 && v <= kMaxWindow) c->cfg.T_lay = v; }
     if (const char* s = std::getenv("NGSEP_PAY_CAP_WORDS")) { int v = std::atoi(s); if (v >= 1024 && v <= 50000) c->cfg.pay_cap_words = (unsigned)(v & ~3); }
     if (const char* s = std::getenv("NGSEP_STAGES")) { int v = std::atoi(s); if (v == 1 || v == 2) c->cfg.n_stages = v; }
+    if (const char* s = std::getenv("NGSEP_L2_PREFETCH")) c->cfg.l2_prefetch = std::atoi(s) != 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);

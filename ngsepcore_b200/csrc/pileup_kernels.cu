@@ -103,6 +103,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // ------------------------------------------------------------------------------------------------------------
 // record views
 // ------------------------------------------------------------------------------------------------------------
+// L2 prefetch hint for a span a later bulk copy will read (16-byte aligned, a multiple of 16 bytes)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ uint32_t range_mask32(int lo, int hi) {  // bits [lo,hi), 0 <= lo < hi <= 32
     uint32_t m = (hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u);
     return m & ~((1u << lo) - 1u);
@@ -1009,7 +1014,19 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 
         // one stage: the next window's copies start NOW (its descriptor has been in dq[0] since the top of this iteration), so
         // that their latency overlaps the tail of this window instead of opening the next iteration
-        if (tid == 0 && n_stages == 1 && wn < a.n_windows) { issue_window(t0.dq[0], wn, 0); t0.prefetched = 1; }
+        if (tid == 0 && n_stages == 1 && wn < a.n_windows) {
+            issue_window(t0.dq[0], wn, 0);
+            t0.prefetched = 1;
+            // ... and the records of the window after that one are asked into L2 (dq[1] has held its descriptor since the top)
+            if (wn + stride < a.n_windows && a.cfg.l2_prefetch) {
+                const WinRange& q = t0.dq[1];
+                if (q.tile == t0.tile && fits(q) && q.hi > q.lo) {
+                    const uint32_t o0 = q.off_lo & ~3u;
+                    bulk_prefetch_l2(t0.hdr + q.lo, (uint32_t)(q.hi - q.lo + 1) * 16u);
+                    bulk_prefetch_l2(t0.payload + o0, ((q.off_hi - o0) * 4u + 15u) & ~15u);
+                }
+            }
+        }
 
         // warp 0 hands the open columns to the global list (the other warps move on; s_open and mset are per window parity)
         if (warp == 0) {

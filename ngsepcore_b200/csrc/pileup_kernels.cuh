@@ -93,6 +93,7 @@ struct LaunchCfg {
     int n_stages;                // 1 or 2 staged windows per CTA
     int min_blocks;              // register budget: resident CTAs per SM the kernel variant is compiled for (256 threads: 3, 4, 5; 128: 8, 10, 12)
     int threads;                 // CTA size: 128 or 256
+    int l2_prefetch;             // 1: the window after the next one is prefetched into L2
 };
 
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
