@@ -92,7 +92,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;            // every kernel of the context
     cudaStream_t copy_stream = nullptr;       // bulk host -> device copies of staged tiles
     cudaStream_t geno_stream = nullptr;       // genotype kernels of single-tile launches
-    cudaEvent_t t0 = nullptr, t1 = nullptr;   // stopwatch
+    cudaEvent_t t0 = nullptr, t1 = nullptr, tg = nullptr;   // stopwatch (tg joins the genotype stream)
     cudaEvent_t b0 = nullptr, bm = nullptr, b1 = nullptr;   // around / between the kernels of the batched run
     ngsep_params params{};
     DevParams* d_prm = nullptr;
@@ -530,6 +530,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->geno_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->t0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->t1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->tg, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&c->b0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->bm);
     if (e == cudaSuccess) e = cudaEventCreate(&c->b1);
@@ -622,6 +623,7 @@ int ngsep_ctx_destroy(void* ctx) {
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    if (c->tg) cudaEventDestroy(c->tg);
     if (c->b0) cudaEventDestroy(c->b0);
     if (c->bm) cudaEventDestroy(c->bm);
     if (c->b1) cudaEventDestroy(c->b1);
@@ -851,6 +853,9 @@ int ngsep_timer_stop(void* ctx, float* ms) {
     Ctx* c = (Ctx*)ctx;
     if (!c || !ms) return NGSEP_EINVAL;
     CK(cudaSetDevice(c->device), "set device");
+    // single-tile launches run their genotype kernel on its own stream: the stopwatch covers it as well
+    CK(cudaEventRecord(c->tg, c->geno_stream), "timer join");
+    CK(cudaStreamWaitEvent(c->stream, c->tg, 0), "timer join");
     CK(cudaEventRecord(c->t1, c->stream), "timer stop");
     CK(cudaEventSynchronize(c->t1), "timer sync");
     CK(cudaEventElapsedTime(ms, c->t0, c->t1), "timer elapsed");
