@@ -99,7 +99,7 @@ struct Ctx {
     DevParams hp{};                           // host copy of *d_prm
     // sample axis (ngsep_samples_set)
     bool samples_set = false;
-    DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch;
+    DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch; DevBuf<uint8_t> d_gins;
     DevBuf<uint16_t> d_gkeys; DevBuf<uint32_t> d_gvals; DevBuf<unsigned char> d_cub;   // staging scratch of launch_group_index (stream-ordered reuse)
     int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
     bool lazy_qual = false;                   // NGSEP_F_QUALITY_IN_PLACE (NGSEP_LAZY_QUAL=0/1 overrides)
@@ -348,7 +348,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         CK(s->d_gidx.reserve(n + 16), "group index alloc");
         CK(s->d_goff.reserve((size_t)c->hp.n_groups + 4), "group offsets alloc");
         CK(s->d_gblk.reserve(((size_t)c->hp.n_groups + 1) * ((size_t)group_blocks(t->n_reads) + 1) + 16), "group block table alloc");
-        CK(launch_group_index(s->d_group.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
+        CK(launch_group_index(s->d_group.p, c->d_gins.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
            "group index launch");
     }
     s->h2d_bytes = (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
@@ -618,7 +618,7 @@ int ngsep_ctx_destroy(void* ctx) {
     for (Slot* s : c->slots) { s->release(); delete s; }
     for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
     c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
-    c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release(); c->d_gkeys.release(); c->d_gvals.release(); c->d_cub.release();
+    c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release(); c->d_gins.release(); c->d_gkeys.release(); c->d_gvals.release(); c->d_cub.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -726,6 +726,8 @@ int ngsep_samples_set(void* ctx, int32_t n_groups, const int32_t* sample_group_o
     CK(c->d_scratch.reserve((size_t)c->multi_grid * (size_t)n_samples), "scratch alloc");
     CK(cudaMemcpy(c->d_sgo.p, sample_group_off, ((size_t)n_samples + 1) * sizeof(int), cudaMemcpyHostToDevice), "sample table copy");
     if (total > 0) CK(cudaMemcpy(c->d_sgroups.p, sample_groups, (size_t)total * sizeof(uint16_t), cudaMemcpyHostToDevice), "sample table copy");
+    CK(c->d_gins.reserve((size_t)n_groups), "sample table alloc");   // which read groups belong to a sample at all
+    CK(cudaMemcpy(c->d_gins.p, seen.data(), (size_t)n_groups, cudaMemcpyHostToDevice), "sample table copy");
     c->hp.n_groups = n_groups;
     c->hp.max_groups_per_sample = max_g;
     c->hp.min_allele_depth_freq = min_allele_depth_freq;

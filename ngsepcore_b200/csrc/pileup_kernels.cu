@@ -1433,11 +1433,12 @@ void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const 
 }
 
 // ---- staging: records indexed by read group (stable) ---------------------------------------------------------------
-__global__ void k_group_keys(const uint16_t* __restrict__ group, int n, int n_groups, uint16_t* keys, uint32_t* vals) {
+__global__ void k_group_keys(const uint16_t* __restrict__ group, const uint8_t* __restrict__ in_sample, int n, int n_groups, uint16_t* keys, uint32_t* vals) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int g = (int)group[i];
-    keys[i] = (uint16_t)min(g, n_groups);   // ids outside the table (0xFFFF: no read group of a sample) share the last list
+    // ids outside the table (0xFFFF) and read groups that belong to no sample share the last list: pooled discovery only
+    keys[i] = (uint16_t)((g < n_groups && in_sample[g]) ? g : n_groups);
     vals[i] = (uint32_t)i;
 }
 __global__ void k_group_offsets(const uint16_t* __restrict__ keys_sorted, int n, int n_groups, uint32_t* goff) {
@@ -1470,10 +1471,10 @@ size_t group_index_temp_bytes(int n) {
 
 // gidx[n]: record indexes sorted by group (stable: each group's list keeps the pileup order); goff[n_groups + 2]: list g is
 // gidx[goff[g] .. goff[g+1]), list n_groups = the records outside every sample.  keys_tmp: 2 x n uint16, vals_tmp: n uint32.
-cudaError_t launch_group_index(const uint16_t* group, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
+cudaError_t launch_group_index(const uint16_t* group, const uint8_t* in_sample, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
                                uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s) {
     if (n > 0) {
-        k_group_keys<<<(n + 255) / 256, 256, 0, s>>>(group, n, n_groups, keys_tmp, vals_tmp);
+        k_group_keys<<<(n + 255) / 256, 256, 0, s>>>(group, in_sample, n, n_groups, keys_tmp, vals_tmp);
         int bits = 1;
         while ((1 << bits) <= n_groups) bits++;
         cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const uint16_t*)keys_tmp, keys_tmp + n, (const uint32_t*)vals_tmp, gidx, n, 0, bits, s);

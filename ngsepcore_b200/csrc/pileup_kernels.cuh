@@ -107,7 +107,7 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
 void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s);
 int genotype_multi_ctas_per_sm(int n_samples);
 size_t group_index_temp_bytes(int n);
-cudaError_t launch_group_index(const uint16_t* group, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
+cudaError_t launch_group_index(const uint16_t* group, const uint8_t* in_sample /* [n_groups]: the read group belongs to a sample */, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
                                uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s);
 int group_blocks(int n);   // blocks of record indexes in the per-group block table
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);

@@ -109,9 +109,15 @@ def test_cli_several_input_files(oracle, tmp_path):
     import subprocess
     genome, batch, fa, sam = _population(tmp_path, [("chrA", 50000), ("chrB", 20000)], n_samples=6, depth=10, mode="wgs", snv_rate=4e-3,
                                          indel_rate=1.5e-3, seeds=(71, 72, 73))
+    # some records carry a read group that no header declares: their own group for the per-start cap, no sample (pooled only)
+    batch.rg_names = batch.rg_names + ["ghost"]
+    ghost = np.random.default_rng(9).random(batch.n) < 0.04
+    keep_rg = batch.rg.copy()
+    batch.rg = np.where(ghost, len(batch.rg_names) - 1, batch.rg).astype(np.int16)
+    simulate.write_sam(sam, batch)      # header: the six declared groups (write_sam zips ids with SM values); records: seven
     files = []
     for k in range(3):   # three inputs with two samples each
-        idx = np.nonzero((batch.rg // 2) == k)[0]
+        idx = np.nonzero((keep_rg // 2) == k)[0]
         path = str(tmp_path / f"part{k}.sam")
         simulate.write_sam(path, batch.select(idx))
         files.append(path)
