@@ -1,6 +1,8 @@
 // C entry points of libngsep_host.so: the host pipeline (C++ mirror of the reference's Java detector) for callers
 // without a C++ toolchain — the Python harness (ctypes) and, in a JVM deployment, the JNI glue of INTEGRATION.md.
 // The device work goes through the C ABI of include/ngsep_pileup.h; nothing here computes the hot path on the CPU.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -135,9 +137,13 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
     while (hi < v.n && v.seq_idx[hi] == seq_idx) hi++;
     AdmissionOptions ao;
     ao.min_mq = min_mq; ao.max_alns_per_start = max_alns_per_start; ao.ignore5 = ignore5; ao.ignore3 = ignore3;
+    auto T0 = std::chrono::steady_clock::now();
     std::vector<HostRead> reads = admit_sequence(v, lo, hi, ao);
+    auto T1 = std::chrono::steady_clock::now();
     PackedTile t;
     pack_reads(reads, 0, reads.size(), t);
+    auto T2 = std::chrono::steady_clock::now();
+    if (std::getenv("NGSEP_HOST_TIMING")) std::fprintf(stderr, "admit %.3f s pack %.3f s\n", std::chrono::duration<double>(T1 - T0).count(), std::chrono::duration<double>(T2 - T1).count());
     *n_reads = (int64_t)t.hdr.size();
     *n_words = t.payload.size();
     *max_span = t.max_span;

@@ -30,8 +30,27 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
     const int len = r.L;
     const int nc = (int)st.cigar.size();
     if (len > 0xffff || nc > 0xff) return;  // rejected earlier by the detector; kept as a guard
-    bool has_n = false;
-    for (int i = 0; i < len; i++) if (L.v[r.bases[i]] > 3) { has_n = true; break; }
+    // one pass over the read: 2-bit bases, "not ACGT" bits and "quality <= 3" bits (never counted, CH:214)
+    const int nb = (len + 15) / 16, nm_words = (len + 31) / 32;
+    uint32_t small[3 * 64];
+    std::vector<uint32_t> big;
+    uint32_t* bw = small;
+    if (nb + 2 * nm_words > (int)(sizeof(small) / sizeof(small[0]))) { big.assign((size_t)nb + 2 * (size_t)nm_words, 0u); bw = big.data(); }
+    else std::memset(small, 0, sizeof(uint32_t) * (size_t)(nb + 2 * nm_words));
+    uint32_t* nmk = bw + nb;
+    uint32_t* lq = nmk + nm_words;
+    uint32_t any_n = 0u;
+    const uint8_t* bases = r.bases;
+    const uint8_t* quals = r.quals;
+    for (int i = 0; i < len; i++) {
+        const uint32_t c = L.v[bases[i]];
+        bw[i >> 4] |= (c & 3u) << ((i & 15) * 2);
+        const uint32_t isn = c >> 2;                  // 1 for anything outside ACGT
+        nmk[i >> 5] |= isn << (i & 31);
+        any_n |= isn;
+    }
+    if (quals) for (int i = 0; i < len; i++) lq[i >> 5] |= (uint32_t)((int)quals[i] - 33 <= 3) << (i & 31);
+    const bool has_n = any_n != 0u;
     ngsep_read_hdr h;
     h.first = r.admit_first;
     h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
@@ -42,18 +61,10 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
     out.hdr.push_back(h);
     auto& p = out.payload;
     if (windowed) { p.push_back((uint32_t)from); p.push_back((uint32_t)to); p.push_back((uint32_t)st.first); }
-    for (uint32_t c : st.cigar) p.push_back(c);
-    size_t b2 = p.size();
-    p.resize(b2 + (len + 15) / 16, 0u);
-    for (int i = 0; i < len; i++) p[b2 + (i >> 4)] |= (uint32_t)(L.v[r.bases[i]] & 3u) << ((i & 15) * 2);
-    if (has_n) {
-        size_t nm = p.size();
-        p.resize(nm + (len + 31) / 32, 0u);
-        for (int i = 0; i < len; i++) if (L.v[r.bases[i]] > 3) p[nm + (i >> 5)] |= 1u << (i & 31);
-    }
-    size_t lq = p.size();
-    p.resize(lq + (len + 31) / 32, 0u);
-    if (r.quals) for (int i = 0; i < len; i++) if ((int)r.quals[i] - 33 <= 3) p[lq + (i >> 5)] |= 1u << (i & 31);   // never counted (CH:214)
+    p.insert(p.end(), st.cigar.begin(), st.cigar.end());
+    p.insert(p.end(), bw, bw + nb);
+    if (has_n) p.insert(p.end(), nmk, nmk + nm_words);
+    p.insert(p.end(), lq, lq + nm_words);
     p.push_back(qoff);
     out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
     out.max_back = std::max(out.max_back, r.admit_first - st.first);
@@ -71,6 +82,12 @@ void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
     out.aligned_bases = 0;
     out.hdr.reserve(hi - lo);
     out.qual.clear();
+    {   // one reservation per array instead of geometric regrowth
+        size_t bases = 0;
+        for (size_t i = lo; i < hi; i++) bases += (size_t)reads[i].L;
+        out.payload.reserve((hi - lo) * 8 + bases / 16 + bases / 16 + 64);
+        out.qual.reserve(bases + 4 * (hi - lo) + 64);
+    }
     for (size_t i = lo; i < hi; i++) {
         const HostRead& r = reads[i];
         // the read's qualities go once into the quality array (every version of the read points at them)
