@@ -325,17 +325,22 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     }
     if (multi) CK(s->d_group.reserve((size_t)t->n_reads + 16), "read-group alloc");
     // The bulk copies run on the COPY stream, the kernels on the context stream: the copies of the next tile overlap the
-    // kernels of this one (a slot's buffers are only reused after its tile has been fetched).
-    if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, c->copy_stream), "read-group copy");
+    // kernels of this one (a slot's buffers are only reused after its tile has been fetched).  Pageable sources are staged by
+    // the driver synchronously with the host thread anyway: they stay on the context stream.
+    const bool pinned_src = t->n_reads > 0 && mapped_host_alias(t->payload, (size_t)t->n_words * 4) != nullptr;
+    cudaStream_t copy_stream = pinned_src ? c->copy_stream : c->stream;
+    if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream), "read-group copy");
     if (t->n_reads > 0) {
-        CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->copy_stream), "hdr copy");
-        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, c->copy_stream), "payload copy");
-        if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, c->copy_stream), "quality copy");
+        CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, copy_stream), "hdr copy");
+        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, copy_stream), "payload copy");
+        if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, copy_stream), "quality copy");
     }
     s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
-    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, c->copy_stream), "sentinel copy");
-    CK(cudaEventRecord(s->e_copy, c->copy_stream), "copy event");
-    CK(cudaStreamWaitEvent(c->stream, s->e_copy, 0), "wait for the copies");
+    CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, copy_stream), "sentinel copy");
+    if (pinned_src) {
+        CK(cudaEventRecord(s->e_copy, c->copy_stream), "copy event");
+        CK(cudaStreamWaitEvent(c->stream, s->e_copy, 0), "wait for the copies");
+    }
     if (multi) {   // records indexed by read group; the scratch buffers are shared by the context (growing them waits for the stream)
         const size_t n = (size_t)t->n_reads;
         const size_t cub_bytes = group_index_temp_bytes(t->n_reads);
