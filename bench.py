@@ -247,13 +247,17 @@ def run_gpu(args):
     if not args.no_pipeline:
         det2 = hostapi.Detector(device=device)
         det2.set_genome(genome)
+        det2.run(batch)                      # warm-up: context creation, device allocations, first-touch of the buffers
+        s0 = det2.stats()
+        w0 = (s0.covered_positions, s0.prepass_s, s0.pack_s, s0.device_s)
         t0 = time.perf_counter()
         vcf = det2.run(batch)
         pipeline_s = time.perf_counter() - t0
         st2 = det2.stats()
-        pipeline = {"value": st2.covered_positions / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s,
-                    "pack_s": st2.pack_s, "device_s": st2.device_s, "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
-                    "note": "whole detector from decoded records on 1 host thread: admission + realigner pre-pass + packing + device + VCF text"}
+        pipeline = {"value": (st2.covered_positions - w0[0]) / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s - w0[1],
+                    "pack_s": st2.pack_s - w0[2], "device_s": st2.device_s - w0[3], "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
+                    "note": "whole detector from decoded records on 1 host thread (second run of the detector object): admission + realigner "
+                            "pre-pass + packing + device + VCF text"}
 
     (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
         dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
