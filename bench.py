@@ -256,8 +256,8 @@ def run_gpu(args):
         st2 = det2.stats()
         pipeline = {"value": (st2.covered_positions - w0[0]) / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s - w0[1],
                     "pack_s": st2.pack_s - w0[2], "device_s": st2.device_s - w0[3], "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
-                    "note": "whole detector from decoded records on 1 host thread (second run of the detector object): admission + realigner "
-                            "pre-pass + packing + device + VCF text"}
+                    "note": "whole detector from decoded records (second run of the detector object): admission + realigner pre-pass on one "
+                            "host thread, tile packing on up to 8, device, VCF text"}
 
     (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
         dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])

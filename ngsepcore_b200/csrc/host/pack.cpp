@@ -1,7 +1,9 @@
 // Tile packer: host reads (with their realigner versions) -> the header / payload layout of include/ngsep_pileup.h.
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "pipeline.hpp"
 
@@ -73,15 +75,14 @@ void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from
 
 }  // namespace
 
-void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups) {
-    out.group.clear();
+static void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out) {
     out.hdr.clear();
     out.payload.clear();
+    out.qual.clear();
     out.max_span = 1;
     out.max_back = 0;
     out.aligned_bases = 0;
     out.hdr.reserve(hi - lo);
-    out.qual.clear();
     {   // one reservation per array instead of geometric regrowth
         size_t bases = 0;
         for (size_t i = lo; i < hi; i++) bases += (size_t)reads[i].L;
@@ -98,6 +99,54 @@ void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
         if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, false, 0, 0, qoff, out); continue; }
         for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, qoff, out);
         emit_record(r, r.st, true, r.cur_from, INT_MAX, qoff, out);
+    }
+}
+
+static int host_threads() {
+    if (const char* e = std::getenv("NGSEP_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) return v; }
+    unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(8u, hw ? hw : 1u));
+}
+
+void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups) {
+    out.group.clear();
+    const size_t n = hi > lo ? hi - lo : 0;
+    const int nt = (int)std::min<size_t>((size_t)host_threads(), n / 20000 + 1);   // small tiles are not worth a thread each
+    if (nt <= 1) pack_range(reads, lo, hi, out);
+    else {
+        // contiguous ranges of reads are packed independently, then concatenated: payload offsets move by the words in front
+        // of the range, quality offsets (the last payload word of every record) by the quality words in front of it
+        std::vector<PackedTile> part((size_t)nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t a = lo + n * (size_t)t / (size_t)nt, b = lo + n * (size_t)(t + 1) / (size_t)nt;
+            th.emplace_back([&reads, &part, a, b, t]() { pack_range(reads, a, b, part[(size_t)t]); });
+        }
+        for (auto& x : th) x.join();
+        size_t nh = 0, np = 0, nq = 0;
+        for (auto& p : part) { nh += p.hdr.size(); np += p.payload.size(); nq += p.qual.size(); }
+        out.hdr.resize(nh); out.payload.resize(np); out.qual.resize(nq);
+        out.max_span = 1; out.max_back = 0; out.aligned_bases = 0;
+        std::vector<size_t> bh((size_t)nt), bp((size_t)nt), bq((size_t)nt);
+        nh = np = nq = 0;
+        for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += part[t].hdr.size(); np += part[t].payload.size(); nq += part[t].qual.size(); }
+        th.clear();
+        for (int t = 0; t < nt; t++) {
+            th.emplace_back([&out, &part, &bh, &bp, &bq, t]() {
+                PackedTile& p = part[(size_t)t];
+                const uint32_t dp = (uint32_t)bp[t], dq = (uint32_t)(bq[t] / 4);
+                for (size_t i = 0; i < p.hdr.size(); i++) {
+                    const size_t end = (i + 1 < p.hdr.size()) ? p.hdr[i + 1].off : p.payload.size();
+                    p.payload[end - 1] += dq;          // qoff
+                    p.hdr[i].off += dp;
+                }
+                std::copy(p.hdr.begin(), p.hdr.end(), out.hdr.begin() + (ptrdiff_t)bh[t]);
+                std::copy(p.payload.begin(), p.payload.end(), out.payload.begin() + (ptrdiff_t)bp[t]);
+                std::copy(p.qual.begin(), p.qual.end(), out.qual.begin() + (ptrdiff_t)bq[t]);
+            });
+        }
+        for (auto& x : th) x.join();
+        for (auto& p : part) { out.max_span = std::max(out.max_span, p.max_span); out.max_back = std::max(out.max_back, p.max_back); out.aligned_bases += p.aligned_bases; }
     }
     if (with_groups) {   // one id per record (every version of a read carries the read's group)
         out.group.reserve(out.hdr.size());

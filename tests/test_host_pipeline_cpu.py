@@ -89,3 +89,22 @@ def test_population_indel_records_match_oracle(oracle, tmp_path, seed, kw, det_k
     assert got_lines == want_lines
     hdr = lambda t: [l for l in t.splitlines() if l.startswith("#")]
     assert hdr(got) == hdr(want)      # sample columns in TreeMap order, MSVD:494-515
+
+
+def test_threaded_packer_equals_single_thread(monkeypatch):
+    """Tiles above 20 k reads are packed by several host threads (contiguous read ranges, concatenated with payload / quality
+    offset fix-ups): byte-identical to the single-thread packing, read versions of the realigner pre-pass included."""
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 250000)], depth=30, seeds=(81, 82, 83), indel_rate=1e-3, n_frac=0.01)
+    out = {}
+    for threads in ("1", "5", "8"):
+        monkeypatch.setenv("NGSEP_HOST_THREADS", threads)
+        det = hostapi.Detector(host_only=True)
+        det.set_genome(genome)
+        out[threads] = det.pack(batch, 0)
+    ref = out["1"]
+    assert ref["hdr"].shape[0] > 70000 and (ref["hdr"]["meta"] & 0x04000000).any()      # realigner versions are present
+    for threads in ("5", "8"):
+        t = out[threads]
+        for k in ("hdr", "payload", "qual"):
+            assert np.array_equal(ref[k], t[k]), (threads, k)
+        assert (ref["max_span"], ref["max_back"], ref["aligned_bases"]) == (t["max_span"], t["max_back"], t["aligned_bases"])
