@@ -687,6 +687,7 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
 int ngsep_tile_fetch(void* ctx, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
+    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "multi-sample context: use ngsep_tile_fetch_pop");   // the tile stays in flight
     if (c->ring_count == 0) return fail(c, NGSEP_ESTATE, "no tile in flight");
     Slot* s = c->ring[c->ring_tail];
     int rc = fetch_slot(c, s, out, cap, n_out, counts_dbg, stats);

@@ -133,3 +133,65 @@ def test_cli_several_input_files(oracle, tmp_path):
     subprocess.check_call([cli, "MultisampleVariantsDetector", "-r", fa, "-o", out, sam])
     assert open(out).read() == want1
     assert subprocess.call([cli, "MultisampleVariantsDetector", "-o", out, sam], stderr=subprocess.DEVNULL) == 2      # MSVD:423
+
+
+def test_c_abi_sample_axis_directly(oracle, tmp_path):
+    """The sample axis through the C ABI itself (ctypes, numpy packer): pooled counts of EVERY position (EMIT_ALL hook)
+    against the oracle's, and the device-resident batched launch (ngsep_resident_run / ngsep_resident_fetch_pop) against the
+    submit / fetch_pop pipeline — same sites, same per-sample records."""
+    from ngsepcore_b200 import capi, pypack
+    contigs = [("chrA", 40000), ("chrB", 25000)]
+    genome, batch, _ = simulate.simulate_population(contigs, n_samples=5, depth=9, mode="wgs", snv_rate=4e-3, indel_rate=0.0, no_rg_frac=0.05,
+                                                    seeds=(91, 92, 93))
+    fa, sam = str(tmp_path / "ref.fa"), str(tmp_path / "pop.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, ocounts, gp, _ = ou.run_msvd(oracle, fa, [sam], want_counts=True)
+    idx_all = pypack.admit(batch)
+    groups = [[s] for s in range(5)]      # one read group per sample; records without RG carry -1 -> 0xFFFF
+    tiles = []
+    for ci, (name, length) in enumerate(contigs):
+        idx = idx_all[batch.seq_idx[idx_all] == ci]
+        hdr, pay, qual, span = pypack.pack_tile(batch, idx)
+        tiles.append((ci, length, hdr, pay, qual, span, batch.rg[idx].astype(np.uint16)))     # int16 -1 -> 0xFFFF
+    # (1) pooled counts of every position
+    with capi.Context(flags=capi.F_EMIT_ALL, n_samples=5) as ctx:
+        ctx.samples_set(groups, 5)
+        opos = 0
+        for ci, length, hdr, pay, qual, span, grp in tiles:
+            ctx.ref_upload(ci, genome[contigs[ci][0]])
+            ctx.submit(ci, 1, length, hdr, pay, qual, span, group=grp)
+            sites, calls, counts, st = ctx.fetch_pop(want_counts=True)
+            oc = ocounts[opos:]
+            nxt = np.nonzero(np.diff(oc[:, 0]) < 0)[0]
+            end = (nxt[0] + 1) if nxt.size else oc.shape[0]
+            oc = oc[:end]
+            opos += end
+            dense = np.zeros((length + 1, 5), np.int32)
+            dense[oc[:, 0]] = oc[:, 1:]
+            assert np.array_equal(counts, dense[1:]), f"pooled counts differ on {contigs[ci][0]}"
+    # (2) pipeline vs device-resident batch
+    with capi.Context(n_samples=5) as ctx:
+        ctx.samples_set(groups, 5)
+        piped, slots = [], []
+        for ci, length, hdr, pay, qual, span, grp in tiles:
+            ctx.ref_upload(ci, genome[contigs[ci][0]])
+            ctx.submit(ci, 1, length, hdr, pay, qual, span, group=grp)
+            piped.append(ctx.fetch_pop()[:2])
+        n_records = sum(len(s) for s, _ in piped)
+        assert n_records == len(_body(want)) and n_records > 60      # no indels planted: every record is a device SNV site
+        for ci, length, hdr, pay, qual, span, grp in tiles:
+            slots.append(ctx.resident_add(ci, 1, length, hdr, pay, qual, span, group=grp))
+        ctx.resident_run(-1)
+        for (s_p, c_p), slot in zip(piped, slots):
+            s_r, c_r, _, _ = ctx.fetch_pop(slot=slot)
+            for name in ("pos", "count", "depth", "qs", "ref", "n_alleles", "allele", "n_alleles0"):
+                assert np.array_equal(s_p[name], s_r[name]), name
+            for name in ("count", "depth", "gq", "g0", "g1", "logcond"):
+                assert np.array_equal(c_p[name], c_r[name]), name
+        # the single-sample entry point refuses, and leaves the tile in flight
+        ci, length, hdr, pay, qual, span, grp = tiles[0]
+        ctx.submit(ci, 1, length, hdr, pay, qual, span, group=grp)
+        with pytest.raises(capi.NgsepError):
+            ctx.fetch()
+        assert len(ctx.fetch_pop()[0]) == len(piped[0][0])
