@@ -21,8 +21,12 @@ def main():
     out_path = sys.argv[1]
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    genome, batch, _ = simulate.simulate(contigs=[("chrA", 150000), ("chrB", 60000)], depth=20, seeds=(7, 8, 9), indel_rate=1e-3)
-    det = hostapi.Detector(host_only=True, tile_len=25000, shard=rank, n_shards=world)
+    if len(sys.argv) > 2 and sys.argv[2] == "multisample":   # MultisampleVariantsDetector: the same region sharding, all samples of a tile on one rank
+        genome, batch, _ = simulate.simulate_population([("chrA", 90000), ("chrB", 40000)], n_samples=6, depth=9, mode="wgs", indel_rate=2e-3, seeds=(17, 18, 19))
+        det = hostapi.MultisampleDetector(list(zip(batch.rg_names, batch.rg_samples)), host_only=True, tile_len=15000, shard=rank, n_shards=world)
+    else:
+        genome, batch, _ = simulate.simulate(contigs=[("chrA", 150000), ("chrB", 60000)], depth=20, seeds=(7, 8, 9), indel_rate=1e-3)
+        det = hostapi.Detector(host_only=True, tile_len=25000, shard=rank, n_shards=world)
     det.set_genome(genome)
     lines = det.run(batch, with_header=False).splitlines()
     st = det.stats()
