@@ -93,3 +93,19 @@ def test_mutated_records(oracle, tmp_path, opts):
     got = open(out + ".vcf").read()
     assert len([l for l in want.splitlines() if not l.startswith("#")]) > 150
     assert got == want
+
+
+def test_mutated_records_multisample(oracle, tmp_path):
+    """The same record shapes through `ngsep_b200 MultisampleVariantsDetector` (population of 6 samples, one input file)."""
+    genome, batch, _ = simulate.simulate_population([("chrA", 50000), ("chrB", 20000)], n_samples=6, depth=10, mode="wgs", snv_rate=4e-3,
+                                                    indel_rate=1e-3, seeds=(141, 142, 143), lower_frac=0.02)
+    fa, sam0, sam = str(tmp_path / "r.fa"), str(tmp_path / "plain.sam"), str(tmp_path / "mutated.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam0, batch)
+    open(sam, "w").writelines(_mutate(open(sam0).readlines(), np.random.default_rng(11)))
+    for opts in ((), ("-s", "-p", "-minQuality", "30"), ("-minMQ", "0", "-maxAlnsPerStartPos", "2", "-ignore5", "2")):
+        want, _, _, _ = ou.run_msvd(oracle, fa, [sam], args=opts)
+        out = str(tmp_path / "out.vcf")
+        subprocess.check_call([CLI, "MultisampleVariantsDetector", "-r", fa, "-o", out] + list(opts) + [sam], stderr=subprocess.DEVNULL)
+        assert len([l for l in want.splitlines() if not l.startswith("#")]) > 80
+        assert open(out).read() == want
