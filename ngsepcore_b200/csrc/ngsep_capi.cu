@@ -371,7 +371,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     double recs_per_pos = (double)t->n_reads / (double)tile_len;
     const int span = t->max_span < 1 ? 1 : t->max_span;
     while (T > 128 && (words_per_pos * (T + span) > 0.85 * c->cfg.pay_cap_words || recs_per_pos * (T + span) > 0.85 * (c->cfg.pay_cap_words / 12)))
-        T = std::max(128, (T / 2) & ~127);
+        T -= 128;   // the largest multiple of 128 whose average window fits (60x: 512, not the 256 that halving gave)
     TileDev& d = s->tile;
     d = TileDev{};
     d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = host_qual ? host_qual : s->d_qual.p;
