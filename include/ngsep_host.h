@@ -81,6 +81,14 @@ int ngsep_ssvd_run(void* det, const ngsep_host_batch* batch, int with_header);
 const char* ngsep_ssvd_vcf(void* det, size_t* len);
 int ngsep_ssvd_stats(void* det, ngsep_run_stats* stats);
 
+/* AlignmentsPileupGenerator.processFiles (APG:212-289) for callers that hold one batch per input file: the order in which the
+ * records of the inputs are consumed — each input reduced to what its own reader hands over (record filter + duplicate-record
+ * rule), then a k-way merge by (sequence, first, last), ties to the lowest input.  *input_idx / *record_idx: n_out pairs,
+ * malloc'ed (ngsep_host_free).  Gather the records in that order into ONE batch (without name hashes: the duplicate rule has
+ * been applied) and hand it to the multi-sample detector. */
+int ngsep_host_merge_order(int n_inputs, const ngsep_host_batch* inputs, int min_mq, int process_non_unique_primary, int process_secondary,
+                           int32_t** input_idx, int64_t** record_idx, int64_t* n_out);
+
 /* Admission + packing of one sequence without the event pre-pass (device-resident benchmarking, packer tests). */
 int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_alns_per_start, int ignore5, int ignore3,
                     ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads, uint64_t* n_words, uint64_t* n_qual, int* max_span,

@@ -148,58 +148,13 @@ bool load_sam(const std::string& path, const Genome& g, OwnedBatch& b, std::stri
     return true;
 }
 
-// Which records of one input survive ReadAlignmentFileReader's iterator (RAFR:219-354 with the flag filter of APG:363-375):
-// the k-way merge of APG:212-289 only ever sees those.  Also the alignment end (GenomicRegionComparator orders by it).
-void reader_survivors(const OwnedBatch& b, const AdmissionOptions& opt, std::vector<size_t>& keep, std::vector<int>& last) {
-    int filter = 0x4;
-    if (!opt.secondary) { filter |= 0x100; if (!opt.non_unique_primary) filter |= 0x1000; }
-    long prev = -1;
-    for (size_t i = 0; i < b.first.size(); i++) {
-        int flags = b.flags[i];
-        if (prev >= 0) {   // duplicate record, RAFR:292-306
-            int pf = b.flags[prev];
-            bool same = b.first[prev] == b.first[i] && ((pf & 1) == (flags & 1)) && (!(pf & 1) || ((pf & 0x40) == (flags & 0x40))) && b.name_hash[prev] == b.name_hash[i];
-            if (same) continue;
-        }
-        prev = (long)i;
-        bool multiple;
-        int nh = b.nh[i];
-        if (flags & 0x100) multiple = true; else if (nh > 1) multiple = true; else if (nh == 1) multiple = false; else multiple = b.mapq[i] < opt.min_mq;
-        if (multiple) flags |= 0x1000;
-        if (flags & filter) continue;
-        if (b.cigar_off[i + 1] <= b.cigar_off[i]) continue;
-        int ref_len = 0;
-        for (int64_t k = b.cigar_off[i]; k < b.cigar_off[i + 1]; k++) if (cig_ref(b.cigar[k])) ref_len += cig_len(b.cigar[k]);
-        keep.push_back(i);
-        last.push_back(b.first[i] + ref_len - 1);
-    }
-}
-
-// AlignmentsPileupGenerator.processFiles / chooseNextAln (APG:212-289): the next alignment is the smallest head by
-// (sequence index, first, last) — genome/GenomicRegionComparator.java:51-67 — ties going to the lowest file index.
+// AlignmentsPileupGenerator.processFiles (APG:212-289): merge_order (model.cpp) gives the consumption order of the inputs' records.
 void merge_inputs(const std::vector<OwnedBatch>& files, const AdmissionOptions& opt, OwnedBatch& out) {
-    const size_t n = files.size();
-    std::vector<std::vector<size_t>> keep(n);
-    std::vector<std::vector<int>> last(n);
-    for (size_t f = 0; f < n; f++) reader_survivors(files[f], opt, keep[f], last[f]);
-    std::vector<size_t> head(n, 0);
-    while (true) {
-        int best = -1;
-        for (size_t f = 0; f < n; f++) {
-            if (head[f] >= keep[f].size()) continue;
-            if (best < 0) { best = (int)f; continue; }
-            const OwnedBatch& A = files[best]; const OwnedBatch& B = files[f];
-            const size_t ia = keep[best][head[best]], ib = keep[f][head[f]];
-            bool greater;   // cmp.compare(answer, current) > 0
-            if (A.seq_idx[ia] != B.seq_idx[ib]) greater = A.seq_idx[ia] > B.seq_idx[ib];
-            else if (A.first[ia] != B.first[ib]) greater = A.first[ia] > B.first[ib];
-            else greater = last[best][head[best]] > last[f][head[f]];
-            if (greater) best = (int)f;
-        }
-        if (best < 0) break;
-        out.append_from(files[best], keep[best][head[best]], files[best].rg[keep[best][head[best]]]);
-        head[best]++;
-    }
+    std::vector<BatchView> views;
+    for (auto& f : files) views.push_back(f.view());
+    std::vector<std::pair<int, int64_t>> order;
+    merge_order(views, opt, order);
+    for (auto& o : order) out.append_from(files[(size_t)o.first], (size_t)o.second, files[(size_t)o.first].rg[(size_t)o.second]);
 }
 
 void usage() {

@@ -183,6 +183,23 @@ int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_
     return NGSEP_OK;
 }
 
+int ngsep_host_merge_order(int n_inputs, const ngsep_host_batch* inputs, int min_mq, int process_non_unique_primary, int process_secondary,
+                           int32_t** input_idx, int64_t** record_idx, int64_t* n_out) {
+    if (n_inputs < 1 || !inputs || !input_idx || !record_idx || !n_out) return NGSEP_EINVAL;
+    std::vector<BatchView> views;
+    for (int i = 0; i < n_inputs; i++) views.push_back(view_of(&inputs[i]));
+    AdmissionOptions ao;
+    ao.min_mq = min_mq; ao.non_unique_primary = process_non_unique_primary != 0; ao.secondary = process_secondary != 0;
+    std::vector<std::pair<int, int64_t>> order;
+    merge_order(views, ao, order);
+    *n_out = (int64_t)order.size();
+    *input_idx = (int32_t*)std::malloc(order.size() * sizeof(int32_t) + 8);
+    *record_idx = (int64_t*)std::malloc(order.size() * sizeof(int64_t) + 8);
+    if (!*input_idx || !*record_idx) return NGSEP_ENOMEM;
+    for (size_t k = 0; k < order.size(); k++) { (*input_idx)[k] = order[k].first; (*record_idx)[k] = order[k].second; }
+    return NGSEP_OK;
+}
+
 void ngsep_host_free(void* p) { std::free(p); }
 
 }  // extern "C"

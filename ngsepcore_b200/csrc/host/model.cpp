@@ -314,5 +314,61 @@ std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi,
     return out;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// several inputs: APG.processFiles
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+void reader_survivors(const BatchView& b, const AdmissionOptions& opt, std::vector<int64_t>& keep, std::vector<int>& last) {
+    int filter = 0x4;
+    if (!opt.secondary) { filter |= 0x100; if (!opt.non_unique_primary) filter |= 0x1000; }
+    int64_t prev = -1;
+    for (int64_t i = 0; i < b.n; i++) {
+        int flags = b.flags[i];
+        if (prev >= 0 && b.name_hash) {   // duplicate record, RAFR:292-306
+            int pf = b.flags[prev];
+            bool same = b.first[prev] == b.first[i] && ((pf & 1) == (flags & 1)) && (!(pf & 1) || ((pf & 0x40) == (flags & 0x40))) && b.name_hash[prev] == b.name_hash[i];
+            if (same) continue;
+        }
+        prev = i;
+        bool multiple;
+        int nh = b.nh ? b.nh[i] : -1;
+        if (flags & 0x100) multiple = true; else if (nh > 1) multiple = true; else if (nh == 1) multiple = false; else multiple = b.mapq[i] < opt.min_mq;
+        if (multiple) flags |= 0x1000;
+        if (flags & filter) continue;
+        if (b.cigar_off[i + 1] <= b.cigar_off[i]) continue;
+        int ref_len = 0;
+        for (int64_t k = b.cigar_off[i]; k < b.cigar_off[i + 1]; k++) if (cig_ref(b.cigar[k])) ref_len += cig_len(b.cigar[k]);
+        keep.push_back(i);
+        last.push_back(b.first[i] + ref_len - 1);
+    }
+}
+}  // namespace
+
+void merge_order(const std::vector<BatchView>& inputs, const AdmissionOptions& opt, std::vector<std::pair<int, int64_t>>& out) {
+    const size_t n = inputs.size();
+    std::vector<std::vector<int64_t>> keep(n);
+    std::vector<std::vector<int>> last(n);
+    for (size_t f = 0; f < n; f++) reader_survivors(inputs[f], opt, keep[f], last[f]);
+    std::vector<size_t> head(n, 0);
+    out.clear();
+    while (true) {
+        int best = -1;
+        for (size_t f = 0; f < n; f++) {
+            if (head[f] >= keep[f].size()) continue;
+            if (best < 0) { best = (int)f; continue; }
+            const BatchView& A = inputs[best]; const BatchView& B = inputs[f];
+            const int64_t ia = keep[best][head[best]], ib = keep[f][head[f]];
+            bool greater;   // cmp.compare(answer, current) > 0
+            if (A.seq_idx[ia] != B.seq_idx[ib]) greater = A.seq_idx[ia] > B.seq_idx[ib];
+            else if (A.first[ia] != B.first[ib]) greater = A.first[ia] > B.first[ib];
+            else greater = last[best][head[best]] > last[f][head[f]];
+            if (greater) best = (int)f;
+        }
+        if (best < 0) break;
+        out.push_back({best, keep[best][head[best]]});
+        head[best]++;
+    }
+}
+
 }  // namespace host
 }  // namespace ngsep_b200

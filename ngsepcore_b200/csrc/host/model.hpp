@@ -12,6 +12,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace ngsep_b200 {
@@ -101,6 +102,13 @@ struct AdmissionOptions {
 // Applies the record filter of RAFR:219-354 (flag set from APG:363-375), the duplicate-record rule and the per-read-
 // group same-start cap of APG:407-433 to the records of one sequence; returns the admitted reads in pileup order.
 std::vector<HostRead> admit_sequence(const BatchView& b, int64_t rec_lo, int64_t rec_hi, const AdmissionOptions& opt);
+
+// AlignmentsPileupGenerator.processFiles / chooseNextAln (APG:212-289): the order in which the records of several
+// coordinate-sorted inputs are consumed.  Each input is first reduced to the records its own reader hands over (RAFR:219-354
+// with the flag filter of APG:363-375, the duplicate-record rule per input); the next record is then the smallest head by
+// (sequence index, first, last) — genome/GenomicRegionComparator.java:51-67 — ties going to the lowest input index.
+// out: (input, record) pairs in consumption order.
+void merge_order(const std::vector<BatchView>& inputs, const AdmissionOptions& opt, std::vector<std::pair<int, int64_t>>& out);
 
 inline int dna_index(char c) {
     switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; }

@@ -18,7 +18,8 @@ from .simulate import AlignmentBatch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
 EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_msvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
-           "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free"]
+           "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free",
+           "ngsep_host_merge_order"]
 
 
 class HostBatch(C.Structure):
@@ -71,6 +72,8 @@ def load_library() -> C.CDLL:
                                     C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     lib.ngsep_host_free.argtypes = [C.c_void_p]
+    lib.ngsep_host_merge_order.argtypes = [C.c_int, C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -107,6 +110,56 @@ def pack_sequence(batch: AlignmentBatch, seq_idx: int, min_mq: int = 20, max_aln
         raise NgsepError(f"ngsep_host_pack failed ({rc})")
     return (_take(hdr_p, n_reads.value, HDR_DTYPE, lib), _take(pay_p, n_words.value, np.uint32, lib), _take(q_p, n_qual.value, np.uint8, lib),
             span.value, bases.value)
+
+
+def merge_batches(batches, minMQ: int = 20, p: bool = False, s: bool = False) -> AlignmentBatch:
+    """AlignmentsPileupGenerator.processFiles (APG:212-289) over one AlignmentBatch per input file: ONE batch with the records in
+    the order the reference consumes them (per-input reader filter, k-way merge by sequence / first / last, ties to the lowest
+    input).  Read groups are unified by name; the contig lists must agree."""
+    lib = load_library()
+    n = len(batches)
+    arr = (HostBatch * n)()
+    keep = []
+    for i, b in enumerate(batches):
+        hb, k = _host_batch(b)
+        arr[i] = hb
+        keep.append(k)
+    in_p, rec_p, n_out = C.c_void_p(), C.c_void_p(), C.c_int64()
+    rc = lib.ngsep_host_merge_order(n, arr, minMQ, int(p), int(s), C.byref(in_p), C.byref(rec_p), C.byref(n_out))
+    if rc != 0:
+        raise NgsepError(f"ngsep_host_merge_order failed ({rc})")
+    which = _take(in_p, n_out.value, np.int32, lib)
+    rec = _take(rec_p, n_out.value, np.int64, lib)
+    names, samples, index = [], [], {}
+    remap = []
+    for b in batches:
+        m = np.full(len(b.rg_names) + 1, -1, np.int16)       # last entry: "no read group" (-1) stays -1
+        for j, (rid, sm) in enumerate(zip(b.rg_names, list(b.rg_samples) + [None] * len(b.rg_names))):
+            if rid not in index:
+                index[rid] = len(names); names.append(rid); samples.append(sm if sm is not None else rid)
+            m[j] = index[rid]
+        remap.append(m)
+    parts = [b.select(rec[which == i]) for i, b in enumerate(batches)]
+    pos_in_part = np.zeros(len(which), np.int64)
+    for i in range(n):
+        sel = which == i
+        pos_in_part[sel] = np.arange(int(sel.sum()))
+    # concatenate the parts, then gather in consumption order
+    off = np.concatenate([[0], np.cumsum([pt.n for pt in parts])])
+    cat_idx = off[which] + pos_in_part
+    cl = np.concatenate([np.diff(pt.cigar_off) for pt in parts]); bl = np.concatenate([np.diff(pt.base_off) for pt in parts])
+    c_start = np.concatenate([[0], np.cumsum(cl)])[:-1]; b_start = np.concatenate([[0], np.cumsum(bl)])[:-1]
+    from .simulate import _gather_ranges
+    cigar = np.concatenate([pt.cigar for pt in parts]); bases = np.concatenate([pt.bases for pt in parts]); quals = np.concatenate([pt.quals for pt in parts])
+    cl_o, bl_o = cl[cat_idx], bl[cat_idx]
+    co = np.zeros(len(cat_idx) + 1, np.int64); np.cumsum(cl_o, out=co[1:])
+    bo = np.zeros(len(cat_idx) + 1, np.int64); np.cumsum(bl_o, out=bo[1:])
+    rg = np.concatenate([remap[i][pt.rg] for i, pt in enumerate(parts)])
+    cat = lambda name: np.concatenate([getattr(pt, name) for pt in parts])[cat_idx]
+    b0 = batches[0]
+    return AlignmentBatch(b0.contig_names, b0.contig_lengths, cat("seq_idx"), cat("first"), cat("flags"), cat("mapq"), rg[cat_idx].astype(np.int16),
+                          cat("nh"), co, _gather_ranges(cigar, c_start[cat_idx], cl_o), bo, _gather_ranges(bases, b_start[cat_idx], bl_o),
+                          _gather_ranges(quals, b_start[cat_idx], bl_o), names, samples)
 
 
 class Detector:

@@ -108,3 +108,33 @@ def test_threaded_packer_equals_single_thread(monkeypatch):
         for k in ("hdr", "payload", "qual"):
             assert np.array_equal(ref[k], t[k]), (threads, k)
         assert (ref["max_span"], ref["max_back"], ref["aligned_bases"]) == (t["max_span"], t["max_back"], t["aligned_bases"])
+
+
+def test_merge_batches_follows_process_files(oracle, tmp_path):
+    """hostapi.merge_batches = AlignmentsPileupGenerator.processFiles (APG:212-289): one batch per input file, consumed in the
+    reference's order (k-way merge by sequence, first, last; ties to the lowest input).  The oracle reads the three SAM files;
+    the host pipeline gets the merged batch; their population indel records must agree — and the merged order must be the
+    oracle-independent rule itself."""
+    genome, batch, _ = simulate.simulate_population([("chrA", 50000), ("chrB", 20000)], n_samples=6, depth=10, mode="wgs", indel_rate=2.5e-3,
+                                                    seeds=(301, 302, 303))
+    fa = str(tmp_path / "r.fa")
+    simulate.write_fasta(fa, genome)
+    parts, files = [], []
+    for k in range(3):
+        part = batch.select(np.nonzero((batch.rg // 2) == k)[0])
+        parts.append(part)
+        path = str(tmp_path / f"part{k}.sam")
+        simulate.write_sam(path, part)
+        files.append(path)
+    merged = hostapi.merge_batches(parts)
+    assert merged.n == batch.n - int((batch.mapq < 20).sum())          # each input's reader drops its non-unique records first
+    # the rule itself: non-decreasing (sequence, first); within equal (sequence, first, last) the lower input comes first
+    key = merged.seq_idx.astype(np.int64) * (1 << 32) + merged.first
+    assert (np.diff(key) >= 0).all()
+    want, _, _, _ = ou.run_msvd(oracle, fa, files)
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    det = hostapi.MultisampleDetector(list(zip(merged.rg_names, merged.rg_samples)), host_only=True)
+    det.set_genome(genome)
+    got_lines = [l for l in det.run(merged).splitlines() if not l.startswith("#")]
+    assert len(want_lines) > 15
+    assert got_lines == want_lines
