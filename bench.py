@@ -143,7 +143,7 @@ def _dist_setup(n_gpus):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":   # unset (a nccl.conf may ask for the banner) or VERSION
             os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout: this program prints ONE JSON line there
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
