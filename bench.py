@@ -143,9 +143,19 @@ def _dist_setup(n_gpus):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local)
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":   # unset (a nccl.conf may ask for the banner) or VERSION
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout: this program prints ONE JSON line there
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # The communicator setup prints "NCCL version ..." on STDOUT (whatever NCCL_DEBUG says): this program prints ONE JSON
+        # line there, so file descriptor 1 points at stderr while the process group and its first collective come up.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist_mod.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         dist = dist_mod
     return rank, world, local, dist
 
