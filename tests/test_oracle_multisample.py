@@ -101,3 +101,82 @@ def test_population_invariants(oracle, tmp_path):
         assert int(r[1]) > last.get(r[0], 0)          # one record per position, ascending (indel suppression, MSVD:536-538)
         last[r[0]] = int(r[1]) if len(r[3]) == 1 else int(r[1]) + len(r[3]) - 1
     assert gp > 60000 and counts.shape[0] > 60000
+
+
+def _expected_impl_sample(oracle, counts, alleles, h=0.001):
+    """Independent numpy restatement of CH.updateCounts + CH.getPosteriorProbabilities + VD.genotypeSNV (multi-allelic branch)
+    for a sample whose bases all have quality 30: returns (GT, PL list, GQ)."""
+    import math
+    a30, b30, c30 = oracle.oracle_table_gt(250, 30, 0), oracle.oracle_table_error(30, 4), oracle.oracle_table_gt(250, 30, 4)
+    L = np.zeros((4, 4))
+    for b, n in enumerate(counts):                      # the order of summation does not matter here: equal terms per base
+        for _ in range(n):
+            for x in range(4):
+                L[x][x] += a30 if x == b else b30
+                for y in range(4):
+                    if x != y:
+                        L[x][y] += c30 if (x == b or y == b) else b30
+    ev = []
+    for i in range(4):
+        ev.append(L[i][i] + math.log10((1 - h) / 4))
+        for j in range(4):
+            if j != i:
+                ev.append(L[i][j] + math.log10(h / 12))
+    mx = max(ev)
+    e = [0.0 if v - mx < -20 else 10 ** (v - mx) for v in ev]
+    tot = sum(e)
+    P = np.zeros((4, 4))
+    k = 0
+    for i in range(4):
+        P[i][i] = e[k] / tot; k += 1
+        for j in range(4):
+            if j != i:
+                P[i][j] = e[k] / tot; k += 1
+    idx = ["ACGT".index(a) for a in alleles]
+    best, bi, bj = P[idx[0]][idx[0]], 0, 0
+    for i in range(len(idx)):
+        for j in range(i, len(idx)):
+            gp = P[idx[i]][idx[j]] + (P[idx[j]][idx[i]] if i != j else 0.0)
+            if gp > best + 0.01:
+                best, bi, bj = gp, i, j
+    maxp = P[idx[bi]][idx[bj]] + (P[idx[bj]][idx[bi]] if bi != bj else 0.0)
+    gq = 255 if (1 - maxp) <= 0 or -10 * math.log10(1 - maxp) > 255 else int(math.floor(-10 * math.log10(1 - maxp) + 0.5))
+    pl = [int(math.floor(-10 * L[idx[i]][idx[j]] + 0.5)) for j in range(len(idx)) for i in range(j + 1)]
+    return (bi, bj), pl, gq
+
+
+def test_handmade_multiallelic_site(oracle, tmp_path):
+    """Three samples, three alleles (A reference, C and G): the record is a MULTISNV with CalledGenomicVariantImpl genotypes
+    (VD:61-95): double-precision PL of the allele sub-matrix, BSDP from all counts, copy numbers from the counts, AFS over three
+    alleles and no MAF (not biallelic)."""
+    rng = np.random.default_rng(6)
+    ref = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 400)].copy()
+    ref[149] = ord("A")
+    fa, sam = str(tmp_path / "h.fa"), str(tmp_path / "h.sam")
+    simulate.write_fasta(fa, {"c": ref})
+    lines = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:c\tLN:400", "@RG\tID:g1\tSM:s1", "@RG\tID:g2\tSM:s2", "@RG\tID:g3\tSM:s3"]
+    k = 0
+    for start in range(91, 111):
+        for rg, base, every in (("g1", "C", 2), ("g2", "G", 2), ("g3", None, 1)):
+            if start % every:
+                continue
+            seq = ref[start - 1:start + 79].copy()
+            if base:
+                seq[150 - start] = ord(base)
+            lines.append(f"r{k}\t0\tc\t{start}\t60\t80M\t*\t0\t0\t{seq.tobytes().decode()}\t{'?' * 80}\tRG:Z:{rg}")
+            k += 1
+    open(sam, "w").write("\n".join(lines) + "\n")
+    text, _, _, _ = ou.run_msvd(oracle, fa, [sam])
+    rec = [l for l in text.splitlines() if not l.startswith("#")]
+    assert len(rec) == 1
+    f = rec[0].split("\t")
+    exp = [_expected_impl_sample(oracle, c, "ACG") for c in ([0, 10, 0, 0], [0, 0, 10, 0], [20, 0, 0, 0])]
+    assert [e[0] for e in exp] == [(1, 1), (2, 2), (0, 0)]
+    qual = max(exp[0][2], exp[1][2])
+    assert f[:7] == ["c", "150", ".", "A", "C,G", str(qual), "."]
+    assert f[7] == "NS=3;AN=3;AFS=2,2,2;OH=0.0;TYPE=MULTISNV"
+    assert f[8] == "GT:PL:GQ:DP:BSDP:ACN"
+    want = []
+    for (gt, pl, gq), cnt, acn in zip(exp, ([0, 10, 0, 0], [0, 0, 10, 0], [20, 0, 0, 0]), ("0,2,0", "0,0,2", "2,0,0")):
+        want.append(f"{gt[0]}/{gt[1]}:{','.join(map(str, pl))}:{gq}:{sum(cnt)}:{','.join(map(str, cnt))}:{acn}")
+    assert f[9:] == want
