@@ -385,7 +385,9 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     d.n_windows = (t->n_reads == 0) ? 0 : ((t->tile_last - 1) / T - d.win0 + 1);
     CK(s->d_win.reserve((size_t)d.n_windows + 1), "window alloc");
     if (multi) {   // population sites + n_samples sample calls each; grown (and the tile rerun) when a tile needs more
-        size_t cap_sites = std::max<size_t>(s->d_sites.cap, (size_t)(tile_len / 64) + 4096);
+        // (a site costs n_samples x 104 bytes: start at 0.2 % of the positions, not more — the fetch grows the buffers and
+        // reruns the tile in the rare case a tile reports more sites)
+        size_t cap_sites = std::max<size_t>(s->d_sites.cap, (size_t)(tile_len / 512) + 4096);
         if (s->d_sites.cap < cap_sites) CK(s->d_sites.reserve(cap_sites), "site alloc");
         CK(s->d_scalls.reserve(s->d_sites.cap * (size_t)c->params.n_samples), "sample call alloc");
         d.pop_sites = s->d_sites.p; d.pop_calls = s->d_scalls.p; d.calls = nullptr; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_sites.cap;
