@@ -1,0 +1,70 @@
+"""CPU fuzz of the host pipeline against the oracle (no GPU): random simulation parameters and option sets; compares the
+host-made indel / STR records (host_only mode) with the oracle's.  Round 1: 25 single-sample and 25 multi-sample seeds, no
+mismatch.   python scripts/fuzz_host_vs_oracle.py single|multi FIRST_SEED LAST_SEED"""
+import sys
+MODE = sys.argv.pop(1)
+import sys, os, tempfile, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ngsepcore_b200 import simulate, hostapi
+from tests import oracle_util as ou
+
+
+def single():
+    lib=ou.load_oracle()
+    d=tempfile.mkdtemp()
+    bad=0
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        rng=np.random.default_rng(seed)
+        kw=dict(depth=float(rng.choice([6,15,30,80])), indel_rate=float(rng.choice([5e-4,2e-3,5e-3])), snv_rate=3e-3, indel_jitter=float(rng.choice([0.0,0.3,0.8])),
+                ungapped_end_bp=int(rng.choice([3,6,12])), n_read_groups=int(rng.integers(1,4)), paired=bool(rng.integers(0,2)))
+        opts=[(),("-minQuality","10"),("-h","0.0001","-maxBaseQS","25"),("-ignore5","5","-ignore3","7"),("-maxAlnsPerStartPos","1"),("-embeddedSNVs",),("-ploidy","1")][int(rng.integers(0,7))]
+        detkw={(): {}, ("-minQuality","10"): dict(minQuality=10), ("-h","0.0001","-maxBaseQS","25"): dict(h=0.0001,maxBaseQS=25), ("-ignore5","5","-ignore3","7"): dict(ignore5=5,ignore3=7),
+               ("-maxAlnsPerStartPos","1"): dict(maxAlnsPerStartPos=1), ("-embeddedSNVs",): dict(embeddedSNVs=True), ("-ploidy","1"): dict(ploidy=1)}[opts]
+        genome,batch,_=simulate.simulate(contigs=[("chrA",60000),("chrB",20000)], seeds=(seed*5+1,seed*5+2,seed*5+3), **kw)
+        fa,sam=os.path.join(d,"r.fa"),os.path.join(d,"r.sam")
+        simulate.write_fasta(fa,genome); simulate.write_sam(sam,batch)
+        want,_,_,_=ou.run_ssvd(lib,fa,sam,args=opts)
+        wl=[l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+        det=hostapi.Detector(host_only=True, **detkw); det.set_genome(genome)
+        gl=det.run(batch, with_header=False).splitlines()
+        ok = gl==wl
+        if not ok:
+            bad+=1
+            for a,b in zip(gl,wl):
+                if a!=b: print("DIFF\n got ",a[:300],"\n want",b[:300]); break
+            print("len", len(gl), len(wl))
+        print(seed, kw["depth"], kw["indel_rate"], opts, len(wl), "OK" if ok else "MISMATCH", flush=True)
+    print("bad", bad)
+
+
+def multi():
+    lib=ou.load_oracle()
+    d=tempfile.mkdtemp()
+    bad=0
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        rng=np.random.default_rng(seed)
+        kw=dict(n_samples=int(rng.integers(2,14)), depth=float(rng.choice([4,8,12,20])), mode=str(rng.choice(["wgs","gbs"])), n_tags=120,
+                indel_rate=float(rng.choice([1e-3,3e-3])), snv_rate=3e-3, rgs_per_sample=int(rng.integers(1,3)), no_rg_frac=float(rng.choice([0,0.05])),
+                indel_jitter=float(rng.choice([0.3,0.7])))
+        opts=[(),("-minQuality","20"),("-h","0.01","-maxBaseQS","20"),("-ignore5","4","-ignore3","4")][int(rng.integers(0,4))]
+        detkw={(): {}, ("-minQuality","20"): dict(minQuality=20), ("-h","0.01","-maxBaseQS","20"): dict(h=0.01,maxBaseQS=20), ("-ignore5","4","-ignore3","4"): dict(ignore5=4,ignore3=4)}[opts]
+        cap = 100 if kw["mode"]=="gbs" else 5
+        genome,batch,_=simulate.simulate_population([("chrA",40000),("chrB",15000)], seeds=(seed*7+1,seed*7+2,seed*7+3), **kw)
+        fa,sam=os.path.join(d,"r.fa"),os.path.join(d,"r.sam")
+        simulate.write_fasta(fa,genome); simulate.write_sam(sam,batch)
+        want,_,_,_=ou.run_msvd(lib,fa,[sam],args=opts+("-maxAlnsPerStartPos",str(cap)))
+        wl=[l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+        det=hostapi.MultisampleDetector(list(zip(batch.rg_names,batch.rg_samples)), host_only=True, maxAlnsPerStartPos=cap, **detkw)
+        det.set_genome(genome)
+        gl=[l for l in det.run(batch).splitlines() if not l.startswith("#")]
+        ok = gl==wl
+        if not ok:
+            bad+=1
+            for a,b in zip(gl,wl):
+                if a!=b: print("DIFF\n got ",a[:300],"\n want",b[:300]); break
+            print("len", len(gl), len(wl))
+        print(seed, kw["mode"], kw["n_samples"], kw["depth"], opts, len(wl), "OK" if ok else "MISMATCH", flush=True)
+    print("bad", bad)
+
+
+(single if MODE == 'single' else multi)()
