@@ -9,7 +9,8 @@
 // Parity status: the SNV genotype arithmetic (CountsHelper / SNVQ / VCF fields)
 // is PINNED against the reference's own demo call set
 // training/yeastDemo_ann_q40_s_fi_I2_noREP_noCNV.vcf.gz (tests/golden/
-// yeast_demo_kat.tsv).  The pileup walk, indel realigner, allele clustering and
+// yeast_demo_kat.tsv), and so is the population INFO arithmetic (NS, AN, AFS,
+// MAF: tests/golden/yeast_demo_diversity.tsv).  The pileup walk, indel realigner, allele clustering and
 // multi-sample logic have NO golden vectors in the reference ("parity unpinned"
 // for those rows): fidelity rests on this line-by-line restatement.  No JVM
 // exists in this environment, so the reference jar itself cannot be run.
@@ -334,6 +335,7 @@ std::vector<std::string> java_string_hashset_order(const std::vector<std::string
 bool load_samples_from_headers(const std::vector<std::vector<std::string>>& header_lines_per_file, short ploidy, std::vector<Sample>& out, std::string& err);  // MSVD:492-516
 bool create_snv_variant_pool(const PileupRecord& p, const CountsHelper& h, char reference, double min_allele_depth_freq, GenomicVariant& out);  // SSVPL:297-332
 std::string english_fmt(double v);   // main/io/ParseUtils.java:29
+std::string diversity_info(size_t n_alleles, const std::vector<std::vector<int8_t>>& called_idx, const std::vector<std::vector<short>>& copy_numbers);  // VCFRecord.java:288-301
 void print_genotype_field(std::ostream& out, CalledVariant& call, bool snv_format, short ploidy);  // VCFFileWriter.java:159-308
 void print_vcf_record_population(std::ostream& out, const GenomicVariant& v, std::vector<CalledVariant>& calls, const std::vector<Sample>& samples);  // VCFRecord.java:277-301
 

@@ -269,6 +269,31 @@ std::string english_fmt(double v) {  // main/io/ParseUtils.java:29 "##0.0#", HAL
     return s;
 }
 
+// VCFRecord.updateDiversityStatistics (vcf/VCFRecord.java:288-301) over DiversityStatistics.calculateDiversityStatistics
+// (variants/DiversityStatistics.java:123-218, assumeAlwaysDiploid = false): "NS=..;AN=..;AFS=..;OH=..[;MAF=..]".
+// idx[k]: called allele indexes of sample k (empty = undecided); cn[k]: its allele copy numbers.
+std::string diversity_info(size_t na, const std::vector<std::vector<int8_t>>& idx, const std::vector<std::vector<short>>& cn) {
+    std::vector<int> counts(na, 0);
+    double sum = 0;
+    int genotyped = 0, n_het = 0;
+    for (size_t k = 0; k < idx.size(); k++) {
+        if (idx[k].empty()) continue;
+        genotyped++;
+        if (idx[k].size() > 1) n_het++;
+        for (int8_t j : idx[k]) if (j >= 0 && (size_t)j < na) { counts[j] += cn[k][j]; sum += cn[k][j]; }
+    }
+    int n_called = 0, min_ac = 0;
+    for (size_t i = 0; i < na; i++) if (counts[i] > 0) { n_called++; if (min_ac == 0 || min_ac > counts[i]) min_ac = counts[i]; }
+    double oh = genotyped > 0 ? (double)n_het / genotyped : 0.0;
+    double maf = n_called < 2 ? 0.0 : (double)min_ac / sum;
+    std::ostringstream out;
+    out << "NS=" << genotyped << ";AN=" << n_called << ";AFS=";
+    for (size_t i = 0; i < na; i++) { if (i) out << ","; out << counts[i]; }
+    out << ";OH=" << english_fmt(oh);
+    if (na == 2) out << ";MAF=" << english_fmt(maf);
+    return out.str();
+}
+
 void print_vcf_record_population(std::ostream& out, const GenomicVariant& v, std::vector<CalledVariant>& calls, const std::vector<Sample>& samples) {
     // vcf/VCFRecord.java:277-301 + vcf/VCFFileWriter.java:44-70
     const bool snv_format = v.is_snv();
@@ -278,27 +303,14 @@ void print_vcf_record_population(std::ostream& out, const GenomicVariant& v, std
     out << "\t" << v.qs << "\t.\t";
     // DiversityStatistics.calculateDiversityStatistics(calls, false), variants/DiversityStatistics.java:123-218
     const size_t na = v.alleles.size();
-    std::vector<int> counts(na, 0);
-    double sum = 0;
-    int genotyped = 0, n_het = 0;
+    std::vector<std::vector<int8_t>> idxs;
+    std::vector<std::vector<short>> cns;
     for (auto& c : calls) {
-        if (c.undecided()) continue;
-        genotyped++;
-        if (c.heterozygous()) n_het++;
-        auto idx = c.called_indexes();
-        std::vector<short> cn;
-        if (c.called_snv) cn = {c.ref_cn, (short)(c.total_cn - c.ref_cn)};   // CalledSNV.getAllelesCopyNumber :162-171
-        else cn = c.alleles_cn;
-        for (int8_t j : idx) if (j >= 0 && (size_t)j < na) { counts[j] += cn[j]; sum += cn[j]; }
+        idxs.push_back(c.called_indexes());
+        if (c.called_snv) cns.push_back({c.ref_cn, (short)(c.total_cn - c.ref_cn)});   // CalledSNV.getAllelesCopyNumber :162-171
+        else cns.push_back(c.alleles_cn);
     }
-    int n_called = 0, min_ac = 0;
-    for (size_t i = 0; i < na; i++) if (counts[i] > 0) { n_called++; if (min_ac == 0 || min_ac > counts[i]) min_ac = counts[i]; }
-    double oh = genotyped > 0 ? (double)n_het / genotyped : 0.0;
-    double maf = n_called < 2 ? 0.0 : (double)min_ac / sum;
-    out << "NS=" << genotyped << ";AN=" << n_called << ";AFS=";
-    for (size_t i = 0; i < na; i++) { if (i) out << ","; out << counts[i]; }
-    out << ";OH=" << english_fmt(oh);
-    if (na == 2) out << ";MAF=" << english_fmt(maf);
+    out << diversity_info(na, idxs, cns);
     static const char* names[] = {nullptr, "SNV", "MULTISNV", "EMBEDDED", "INDEL", "STR"};
     if (v.type != TYPE_UNDETERMINED && v.type != TYPE_BIALLELIC_SNV && v.type >= 0 && v.type <= TYPE_STR) out << ";TYPE=" << names[v.type];
     out << "\t" << (snv_format ? "GT:PL:GQ:DP:BSDP:ACN" : "GT:PL:GQ:DP:ADP:ACN");

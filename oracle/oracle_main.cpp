@@ -284,6 +284,23 @@ int oracle_string_hashset_order(int n, char** keys, int* order_out) {
     return n;
 }
 
+// DiversityStatistics known-answer hook: called[2k], called[2k+1] = allele indexes of sample k (-1 = none; equal = homozygous),
+// cn[k * n_alleles + j] = its copy number of allele j.  out: "NS=..;AN=..;AFS=..;OH=..[;MAF=..]".
+void oracle_diversity_info(int n_alleles, int n_calls, const int* called, const int* cn, char* out256) {
+    std::vector<std::vector<int8_t>> idx;
+    std::vector<std::vector<short>> cns;
+    for (int k = 0; k < n_calls; k++) {
+        std::vector<int8_t> i;
+        if (called[2 * k] >= 0) { i.push_back((int8_t)called[2 * k]); if (called[2 * k + 1] != called[2 * k]) i.push_back((int8_t)called[2 * k + 1]); }
+        idx.push_back(i);
+        std::vector<short> c;
+        for (int j = 0; j < n_alleles; j++) c.push_back((short)cn[k * n_alleles + j]);
+        cns.push_back(c);
+    }
+    std::string s = diversity_info((size_t)n_alleles, idx, cns);
+    std::strncpy(out256, s.c_str(), 255); out256[255] = 0;
+}
+
 void oracle_free(void* p) { std::free(p); }
 
 }  // extern "C"

@@ -38,6 +38,7 @@ def load_oracle():
                                     C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_double)]
     lib.oracle_english_fmt.argtypes = [C.c_double, C.c_char_p]
     lib.oracle_string_hashset_order.argtypes = [C.c_int, C.POINTER(C.c_char_p), ip]
+    lib.oracle_diversity_info.argtypes = [C.c_int, C.c_int, ip, ip, C.c_char_p]
     return lib
 
 
@@ -88,6 +89,16 @@ def run_msvd(lib, fasta, sams, args=(), want_counts=False):
         counts = np.ctypeslib.as_array(cptr, shape=(n_counts.value, 6)).copy() if n_counts.value else np.zeros((0, 6), np.int32)
         lib.oracle_free(cptr)
     return text, counts, gp.value, sec.value
+
+
+def diversity_info(lib, n_alleles, called, copy_numbers):
+    """called: per sample (g0, g1) or (-1, -1); copy_numbers: per sample a list of n_alleles ints -> 'NS=..;AN=..;AFS=..;OH=..[;MAF=..]'."""
+    n = len(called)
+    c = (C.c_int * (2 * n))(*[x for g in called for x in g])
+    cn = (C.c_int * (n * n_alleles))(*[x for row in copy_numbers for x in row])
+    buf = C.create_string_buffer(256)
+    lib.oracle_diversity_info(n_alleles, n, c, cn, buf)
+    return buf.value.decode()
 
 
 def english_fmt(lib, v):

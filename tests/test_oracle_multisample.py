@@ -180,3 +180,27 @@ def test_handmade_multiallelic_site(oracle, tmp_path):
     for (gt, pl, gq), cnt, acn in zip(exp, ([0, 10, 0, 0], [0, 0, 10, 0], [20, 0, 0, 0]), ("0,2,0", "0,0,2", "2,0,0")):
         want.append(f"{gt[0]}/{gt[1]}:{','.join(map(str, pl))}:{gq}:{sum(cnt)}:{','.join(map(str, cnt))}:{acn}")
     assert f[9:] == want
+
+
+def test_population_info_against_reference_demo_vcf(oracle):
+    """PINNED: the NS / AN / AFS / MAF values of the reference's own two-sample demo VCF (20 456 records, 7 distinct genotype
+    patterns; tests/golden/make_yeast_demo_diversity.py) are what the restated DiversityStatistics + DecimalFormat give for
+    the file's genotypes and allele copy numbers."""
+    import gzip
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden", "yeast_demo_diversity.tsv.gz")
+    n_rec = 0
+    with gzip.open(gold, "rt") as f:
+        for line in f:
+            if line.startswith("#"):
+                continue
+            n_alleles, samples, ns, an, afs, maf, mult = line.rstrip("\n").split("\t")
+            called, cns = [], []
+            for s in samples.split("|"):
+                gt, acn = s.split(":")
+                called.append((-1, -1) if gt == "./." else tuple(int(x) for x in gt.split("/")))
+                cns.append([int(x) for x in acn.split(",")])
+            info = dict(kv.split("=") for kv in ou.diversity_info(oracle, int(n_alleles), called, cns).split(";"))
+            assert (info["NS"], info["AN"], info["AFS"], info.get("MAF", ".")) == (ns, an, afs, maf), line
+            n_rec += int(mult)
+    assert n_rec == 20456
