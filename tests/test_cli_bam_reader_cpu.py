@@ -1,0 +1,64 @@
+"""The CLI's native BAM (BGZF) reader, on CPU: a SAM file and its BAM conversion must decode to the SAME record batch
+(`--dump-batch`, every array compared) and give the same host-made indel / STR records (`--host-only`: admission + realigner
+pre-pass + indel caller, no device).  Mutated records (clips, =/X/N/P, secondary / NH / missing QUAL / no read group /
+duplicates) are included; lower-case bases and short QUAL strings are left out of the mutation because BAM cannot hold them."""
+import os
+import subprocess
+
+import numpy as np
+
+from ngsepcore_b200 import simulate
+from tests import bam_util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "ngsepcore_b200", "ngsep_b200")
+
+
+def _read_dump(path):
+    raw = open(path, "rb").read()
+    out, p = [], 0
+    while p < len(raw):
+        n = int(np.frombuffer(raw, np.uint64, 1, p)[0])
+        out.append(raw[p + 8:p + 8 + n])
+        p += 8 + n
+    return out
+
+
+def test_bam_and_sam_decode_to_the_same_batch(tmp_path):
+    from tests.test_gpu_sam_torture import _mutate
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 60000), ("chrB", 25000)], depth=20, seeds=(151, 152, 153), indel_rate=2e-3, n_read_groups=2)
+    fa, sam0, sam, bam = (str(tmp_path / n) for n in ("r.fa", "plain.sam", "m.sam", "m.bam"))
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam0, batch)
+    lines = _mutate(open(sam0).readlines(), np.random.default_rng(3))
+    keep = []
+    for l in lines:                      # what BAM cannot represent: lower-case bases, QUAL shorter than SEQ
+        if not l.startswith("@"):
+            f = l.split("\t")
+            if f[9] != f[9].upper() or (f[10] != "*" and len(f[10]) != len(f[9])):
+                continue
+        keep.append(l)
+    open(sam, "w").writelines(keep)
+    n = bam_util.sam_to_bam(sam, bam)
+    assert n > 15000
+    outs = {}
+    for tag, path in (("sam", sam), ("bam", bam)):
+        prefix, dump = str(tmp_path / f"out_{tag}"), str(tmp_path / f"dump_{tag}.bin")
+        subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", prefix, "--host-only", "--dump-batch", dump],
+                              stderr=subprocess.DEVNULL)
+        outs[tag] = (_read_dump(dump), open(prefix + ".vcf").read())
+    names = ["seq_idx", "first", "flags", "mapq", "rg", "nh", "cigar_off", "cigar", "base_off", "bases", "quals", "name_hash"]
+    assert len(outs["sam"][0]) == len(names)
+    for name, a, b in zip(names, outs["sam"][0], outs["bam"][0]):
+        assert a == b, name
+    assert len(outs["sam"][0][1]) // 4 == n
+    body = [l for l in outs["sam"][1].splitlines() if not l.startswith("#")]
+    assert len(body) > 20 and outs["sam"][1] == outs["bam"][1]
+
+
+def test_bam_reader_rejects_garbage(tmp_path):
+    fa = str(tmp_path / "r.fa")
+    simulate.write_fasta(fa, {"c": np.frombuffer(b"ACGT" * 50, np.uint8)})
+    bad = str(tmp_path / "bad.bam")
+    open(bad, "wb").write(b"\x1f\x8b\x08\x04garbage-not-bgzf")
+    assert subprocess.call([CLI, "SingleSampleVariantsDetector", "-i", bad, "-r", fa, "-o", str(tmp_path / "o"), "--host-only"], stderr=subprocess.DEVNULL) == 2
