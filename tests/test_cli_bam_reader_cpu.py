@@ -62,3 +62,29 @@ def test_bam_reader_rejects_garbage(tmp_path):
     bad = str(tmp_path / "bad.bam")
     open(bad, "wb").write(b"\x1f\x8b\x08\x04garbage-not-bgzf")
     assert subprocess.call([CLI, "SingleSampleVariantsDetector", "-i", bad, "-r", fa, "-o", str(tmp_path / "o"), "--host-only"], stderr=subprocess.DEVNULL) == 2
+
+
+def test_multisample_cli_with_bam_inputs(oracle, tmp_path):
+    """`ngsep_b200 MultisampleVariantsDetector --host-only` over three BAM inputs (two samples each): header reading, the k-way
+    merge of APG:212-289 and the population indel caller — against the oracle reading the three SAM files."""
+    from tests import oracle_util as ou
+    genome, batch, _ = simulate.simulate_population([("chrA", 45000), ("chrB", 15000)], n_samples=6, depth=10, mode="wgs", indel_rate=2.5e-3,
+                                                    seeds=(311, 312, 313))
+    fa = str(tmp_path / "r.fa")
+    simulate.write_fasta(fa, genome)
+    sams, bams = [], []
+    for k in range(3):
+        part = batch.select(np.nonzero((batch.rg // 2) == k)[0])
+        sam, bam = str(tmp_path / f"p{k}.sam"), str(tmp_path / f"p{k}.bam")
+        simulate.write_sam(sam, part)
+        bam_util.sam_to_bam(sam, bam)
+        sams.append(sam)
+        bams.append(bam)
+    want, _, _, _ = ou.run_msvd(oracle, fa, sams, args=("-minQuality", "30"))
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    out = str(tmp_path / "ms.vcf")
+    subprocess.check_call([CLI, "MultisampleVariantsDetector", "-r", fa, "-o", out, "-minQuality", "30", "--host-only"] + bams, stderr=subprocess.DEVNULL)
+    got = open(out).read()
+    assert len(want_lines) > 15
+    assert [l for l in got.splitlines() if not l.startswith("#")] == want_lines
+    assert [l for l in got.splitlines() if l.startswith("#")] == [l for l in want.splitlines() if l.startswith("#")]
