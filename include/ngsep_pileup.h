@@ -177,7 +177,7 @@ typedef struct ngsep_tile_stats {
     uint32_t reserved;
 } ngsep_tile_stats;
 
-/* Context = one GPU + one stream + device-resident reference.  Replaces the construction of
+/* Context = one GPU + its streams (kernels, bulk copies, genotype kernels of pipelined tiles) + the device-resident reference.  Replaces the construction of
  * AlignmentsPileupGenerator + CountsHelper's static caches (APG:38-69, CH:135-187). */
 int ngsep_ctx_create(int device, const ngsep_params* params, const double* tables, size_t n_tables, void** ctx);
 int ngsep_ctx_destroy(void* ctx);
@@ -187,10 +187,10 @@ const char* ngsep_last_error(void* ctx);
  * Replaces ReferenceGenome.getReference for the path (genome/ReferenceGenome.java:222-245). */
 int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t length);
 
-/* Asynchronous: copies the tile's host buffers to the device and launches the kernels on the context stream.
- * Up to 4 tiles may be in flight; they are fetched in submission order, so the host can pack / copy the next tile while
- * the device works on the previous one (NGSEP_ESTATE when a fifth is submitted before a fetch).  A tile's host buffers
- * must stay valid until the ngsep_tile_fetch that returns it. */
+/* Asynchronous: copies the tile's host buffers to the device (page-locked buffers: on a copy stream that overlaps the kernels
+ * of the previous tile) and launches the kernels.  Up to 4 tiles may be in flight; they are fetched in submission order, so
+ * the host can pack / copy the next tile while the device works on the previous one (NGSEP_ESTATE when a fifth is submitted
+ * before a fetch).  A tile's host buffers must stay valid until the ngsep_tile_fetch that returns it. */
 int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
 
 /* Waits for the OLDEST submitted tile and copies its calls (unordered) into out[0..cap).  counts_dbg, when not NULL and
@@ -221,7 +221,7 @@ int ngsep_resident_run(void* ctx, int slot);
 int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
 
-/* CUDA-event stopwatch on the context stream (the stream every kernel of this context is launched on). */
+/* CUDA-event stopwatch on the context stream (ngsep_timer_stop also waits for the genotype kernels of pipelined tiles). */
 int ngsep_timer_start(void* ctx);
 int ngsep_timer_stop(void* ctx, float* elapsed_ms);   /* synchronises the stream */
 
