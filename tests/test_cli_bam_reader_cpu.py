@@ -88,3 +88,25 @@ def test_multisample_cli_with_bam_inputs(oracle, tmp_path):
     assert len(want_lines) > 15
     assert [l for l in got.splitlines() if not l.startswith("#")] == want_lines
     assert [l for l in got.splitlines() if l.startswith("#")] == [l for l in want.splitlines() if l.startswith("#")]
+
+
+def test_cli_host_only_records_match_oracle_on_mutated_sam(oracle, tmp_path):
+    """The SAM reader + admission + realigner pre-pass + indel caller of the CLI on the mutated-record SAM (clips, =/X/N/P,
+    secondary / NH / MAPQ / unmapped / duplicate records, missing or short QUAL, lower case, no read group), without a GPU:
+    its indel / STR records are the oracle's, under two option sets."""
+    from tests import oracle_util as ou
+    from tests.test_gpu_sam_torture import _mutate
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 70000), ("chrB", 30000)], depth=25, seeds=(161, 162, 163), indel_rate=2e-3, n_read_groups=2,
+                                         lower_frac=0.02)
+    fa, sam0, sam = (str(tmp_path / n) for n in ("r.fa", "plain.sam", "m.sam"))
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam0, batch)
+    open(sam, "w").writelines(_mutate(open(sam0).readlines(), np.random.default_rng(5)))
+    for opts in ((), ("-s", "-p", "-minMQ", "5", "-maxAlnsPerStartPos", "3", "-ignore5", "2")):
+        want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=opts)
+        want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+        prefix = str(tmp_path / "o")
+        subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", prefix, "--host-only"] + list(opts), stderr=subprocess.DEVNULL)
+        got_lines = [l for l in open(prefix + ".vcf").read().splitlines() if not l.startswith("#")]
+        assert len(want_lines) > 40
+        assert got_lines == want_lines
