@@ -17,3 +17,11 @@ def oracle():
     """ctypes handle on the CPU oracle (test infrastructure only)."""
     from tests import oracle_util
     return oracle_util.load_oracle()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_artifacts():
+    """The tests need the in-tree native libraries, the CLI and the oracle: build whatever is missing or stale (nvcc
+    cross-compiles without a GPU; a no-op when everything is up to date)."""
+    import __graft_entry__ as ge
+    ge.build()
