@@ -1,6 +1,6 @@
 """CPU fuzz of the host pipeline against the oracle (no GPU): random simulation parameters and option sets; compares the
-host-made indel / STR records (host_only mode) with the oracle's.  Round 1: 25 single-sample and 25 multi-sample seeds, no
-mismatch.   python scripts/fuzz_host_vs_oracle.py single|multi FIRST_SEED LAST_SEED"""
+host-made indel / STR records (host_only mode) with the oracle's.  Round 1: 85 single-sample, 85 multi-sample and 30 CLI seeds, no
+mismatch.   python scripts/fuzz_host_vs_oracle.py single|multi|cli FIRST_SEED LAST_SEED"""
 import sys
 MODE = sys.argv.pop(1)
 import sys, os, tempfile, numpy as np
@@ -67,4 +67,31 @@ def multi():
     print("bad", bad)
 
 
-(single if MODE == 'single' else multi)()
+def cli():
+    """Mutated-record SAMs (tests/test_gpu_sam_torture.py::_mutate) through the CLI's SAM reader in --host-only mode."""
+    import subprocess
+    from tests.test_gpu_sam_torture import _mutate
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "ngsepcore_b200", "ngsep_b200")
+    lib = ou.load_oracle()
+    d = tempfile.mkdtemp()
+    bad = 0
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        rng = np.random.default_rng(seed)
+        genome, batch, _ = simulate.simulate(contigs=[("chrA", 50000), ("chrB", 20000)], depth=float(rng.choice([10, 25, 50])), seeds=(seed * 3 + 1, seed * 3 + 2, seed * 3 + 3),
+                                             indel_rate=float(rng.choice([1e-3, 3e-3])), n_read_groups=int(rng.integers(1, 4)), lower_frac=0.02)
+        fa, sam0, sam = os.path.join(d, "r.fa"), os.path.join(d, "p.sam"), os.path.join(d, "m.sam")
+        simulate.write_fasta(fa, genome); simulate.write_sam(sam0, batch)
+        open(sam, "w").writelines(_mutate(open(sam0).readlines(), np.random.default_rng(seed + 1000)))
+        opts = [(), ("-s", "-p"), ("-minMQ", "0", "-maxAlnsPerStartPos", "2"), ("-p", "-ignore5", "3", "-ignore3", "3"), ("-s", "-minMQ", "30")][int(rng.integers(0, 5))]
+        want, _, _, _ = ou.run_ssvd(lib, fa, sam, args=opts)
+        wl = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+        subprocess.check_call([exe, "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", os.path.join(d, "o"), "--host-only"] + list(opts), stderr=subprocess.DEVNULL)
+        gl = [l for l in open(os.path.join(d, "o.vcf")).read().splitlines() if not l.startswith("#")]
+        ok = gl == wl
+        bad += not ok
+        print(seed, opts, len(wl), "OK" if ok else "MISMATCH", flush=True)
+    print("bad", bad)
+
+
+{"single": single, "multi": multi, "cli": cli}[MODE]()
