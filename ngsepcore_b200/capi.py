@@ -133,6 +133,7 @@ class Context:
             raise NgsepError(f"ngsep_ctx_create failed ({rc}): {self.lib.ngsep_last_error(None).decode()}")
         self._keep = []
         self._slot_npos = {}
+        self._inflight_npos = []      # positions of the pipelined tiles, oldest first (tiles are fetched in submission order)
 
     def _check(self, rc: int, what: str) -> None:
         if rc != 0:
@@ -163,7 +164,7 @@ class Context:
     def fetch_pop(self, cap: int = 4096, want_counts: bool = False, slot: int = 0):
         """Multi-sample contexts: (sites sorted by pos, sample calls [n_sites, n_samples], pooled counts or None, TileStats)."""
         stats = TileStats()
-        n_pos = self._n_pos if slot == 0 else self._slot_npos[slot]
+        n_pos = (self._inflight_npos[0] if self._inflight_npos else 0) if slot == 0 else self._slot_npos[slot]
         counts = np.zeros((n_pos, 5), np.int32) if want_counts else None
         while True:
             sites = np.zeros(cap, SITE_DTYPE)
@@ -177,6 +178,9 @@ class Context:
             if rc == -6 and n.value > cap:
                 cap = int(n.value) + 16
                 continue
+            if slot == 0:
+                if self._inflight_npos:
+                    self._inflight_npos.pop(0)      # the tile left the queue, whether the fetch succeeded or not
             self._check(rc, "ngsep_tile_fetch_pop")
             break
         o = np.argsort(sites["pos"][: n.value], kind="stable")
@@ -184,8 +188,8 @@ class Context:
 
     def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> None:
         t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group)
-        self._n_pos = tile_last - tile_first + 1
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
+        self._inflight_npos.append(tile_last - tile_first + 1)
 
     def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> int:
         """Stages a tile in HBM for repeated runs; returns its slot."""
@@ -219,7 +223,7 @@ class Context:
     def fetch(self, cap: int = 1 << 16, want_counts: bool = False, slot: int = 0, sort: bool = True):
         """Returns (calls structured array sorted by pos, counts [n_pos,5] or None, TileStats)."""
         stats = TileStats()
-        n_pos = self._n_pos if slot == 0 else self._slot_npos[slot]
+        n_pos = (self._inflight_npos[0] if self._inflight_npos else 0) if slot == 0 else self._slot_npos[slot]
         counts = np.zeros((n_pos, 5), np.int32) if want_counts else None
         while True:
             out = np.zeros(cap, CALL_DTYPE)
@@ -228,6 +232,9 @@ class Context:
             if rc == -6 and n.value > cap:
                 cap = int(n.value) + 16
                 continue
+            if slot == 0:
+                if self._inflight_npos:
+                    self._inflight_npos.pop(0)      # the tile left the queue, whether the fetch succeeded or not
             self._check(rc, "ngsep_tile_fetch")
             break
         calls = out[: n.value]

@@ -182,15 +182,18 @@ bool bgzf_inflate(const std::string& path, std::vector<unsigned char>& out, std:
     while (p + 18 <= raw.size()) {
         if (raw[p] != 0x1f || raw[p + 1] != 0x8b || raw[p + 2] != 8 || !(raw[p + 3] & 4)) { err = path + ": not a BGZF file"; return false; }
         const size_t xlen = raw[p + 10] | (raw[p + 11] << 8);
+        if (p + 12 + xlen > raw.size()) { err = path + ": truncated BGZF block"; return false; }
         size_t x = p + 12, bsize = 0;
         while (x + 4 <= p + 12 + xlen) {
             const size_t slen = raw[x + 2] | (raw[x + 3] << 8);
-            if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2) bsize = (size_t)(raw[x + 4] | (raw[x + 5] << 8)) + 1;
+            if (raw[x] == 'B' && raw[x + 1] == 'C' && slen == 2 && x + 6 <= p + 12 + xlen) bsize = (size_t)(raw[x + 4] | (raw[x + 5] << 8)) + 1;
             x += 4 + slen;
         }
-        if (!bsize || p + bsize > raw.size()) { err = path + ": truncated BGZF block"; return false; }
+        // header (12) + extra field + at least an empty deflate stream + CRC32 and ISIZE (8) must fit the block, the block the file
+        if (!bsize || bsize < xlen + 20 || p + bsize > raw.size()) { err = path + ": truncated BGZF block"; return false; }
         const size_t cdata = p + 12 + xlen, clen = bsize - xlen - 20;
         const size_t isize = raw[p + bsize - 4] | (raw[p + bsize - 3] << 8) | (raw[p + bsize - 2] << 16) | ((size_t)raw[p + bsize - 1] << 24);
+        if (isize > 65536) { err = path + ": corrupt BGZF block"; return false; }   // a BGZF block inflates to at most 64 KiB
         if (isize) {
             const size_t o = out.size();
             out.resize(o + isize);
@@ -215,6 +218,7 @@ bool load_bam(const std::string& path, Loader& ld) {
     if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4)) { ld.err = path + ": not a BAM file"; return false; }
     size_t p = 4;
     const size_t l_text = u32(p); p += 4;
+    if (l_text > d.size() - p || d.size() - p - l_text < 4) { ld.err = path + ": truncated BAM header"; return false; }
     {   // the SAM header text
         std::string text((const char*)d.data() + p, l_text);
         size_t s = 0;
@@ -229,9 +233,12 @@ bool load_bam(const std::string& path, Loader& ld) {
     }
     p += l_text;
     const size_t n_ref = u32(p); p += 4;
+    if (n_ref > (d.size() - p) / 8) { ld.err = path + ": truncated BAM header"; return false; }   // every reference takes at least 8 bytes
     std::vector<int> ref_to_seq(n_ref, -1);
     for (size_t r = 0; r < n_ref; r++) {
+        if (d.size() - p < 4) { ld.err = path + ": truncated BAM header"; return false; }
         const size_t l_name = u32(p); p += 4;
+        if (l_name > d.size() - p || d.size() - p - l_name < 4) { ld.err = path + ": truncated BAM header"; return false; }
         std::string name((const char*)d.data() + p, l_name ? l_name - 1 : 0); p += l_name;
         const long l_ref = (long)u32(p); p += 4;
         auto it = ld.seq_of.find(name);
@@ -251,6 +258,9 @@ bool load_bam(const std::string& path, Loader& ld) {
         const size_t n_cig = u16(q + 12);
         const int flag = (int)u16(q + 14);
         const size_t l_seq = u32(q + 16);
+        // every length of the fixed part against the record block (block <= the bytes left in the file, checked above)
+        if (l_seq > block || 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq > block) { ld.err = path + ": truncated BAM record"; return false; }
+        const size_t rec_end = q + block;
         size_t o = q + 32;
         std::string qname((const char*)d.data() + o, l_name ? l_name - 1 : 0); o += l_name;
         std::vector<uint32_t> cg;
@@ -264,10 +274,20 @@ bool load_bam(const std::string& path, Loader& ld) {
         const std::string* rg = nullptr;
         std::string rg_id;
         int nh = -1;
-        while (o + 3 <= q + block) {   // optional fields
+        bool aux_bad = false;
+        while (o + 3 <= rec_end) {   // optional fields; every value is checked against the end of the record before it is read
             const char t0 = (char)d[o], t1 = (char)d[o + 1], ty = (char)d[o + 2];
             o += 3;
             long ival = 0; bool is_int = true;
+            size_t need = 0;
+            switch (ty) {
+                case 'A': case 'c': case 'C': need = 1; break;
+                case 's': case 'S': need = 2; break;
+                case 'i': case 'I': case 'f': need = 4; break;
+                case 'B': need = 5; break;
+                default: break;
+            }
+            if (need > rec_end - o) { aux_bad = true; break; }
             switch (ty) {
                 case 'A': case 'c': ival = (int8_t)d[o]; o += 1; break;
                 case 'C': ival = d[o]; o += 1; break;
@@ -276,12 +296,27 @@ bool load_bam(const std::string& path, Loader& ld) {
                 case 'i': ival = (int32_t)u32(o); o += 4; break;
                 case 'I': ival = u32(o); o += 4; break;
                 case 'f': is_int = false; o += 4; break;
-                case 'Z': case 'H': { size_t e = o; while (e < q + block && d[e]) e++; if (t0 == 'R' && t1 == 'G' && ty == 'Z') { rg_id.assign((const char*)d.data() + o, e - o); rg = &rg_id; } o = e + 1; is_int = false; break; }
-                case 'B': { const char sub = (char)d[o]; const size_t cnt = u32(o + 1); const size_t w = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4); o += 5 + cnt * w; is_int = false; break; }
-                default: o = q + block; is_int = false; break;
+                case 'Z': case 'H': {
+                    size_t e = o;
+                    while (e < rec_end && d[e]) e++;
+                    if (e >= rec_end) { aux_bad = true; break; }   // no terminator inside the record
+                    if (t0 == 'R' && t1 == 'G' && ty == 'Z') { rg_id.assign((const char*)d.data() + o, e - o); rg = &rg_id; }
+                    o = e + 1; is_int = false; break;
+                }
+                case 'B': {
+                    const char sub = (char)d[o];
+                    const size_t cnt = u32(o + 1);
+                    const size_t w = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                    o += 5;
+                    if (cnt > (rec_end - o) / w) { aux_bad = true; break; }
+                    o += cnt * w; is_int = false; break;
+                }
+                default: o = rec_end; is_int = false; break;
             }
+            if (aux_bad) break;
             if (is_int && t0 == 'N' && t1 == 'H' && ty != 'A') nh = (int)std::min(32000L, std::max(-1L, ival));
         }
+        if (aux_bad) { ld.err = path + ": truncated BAM record (optional fields)"; return false; }
         p = q + block;
         if (bad || ref_id < 0 || (size_t)ref_id >= n_ref) continue;   // unplaced record / unknown operation: skipped like in the SAM reader
         ld.record(qname, flag, ref_to_seq[ref_id], pos, mapq, cg, l_seq ? seq : std::string(), qual, l_seq > 0, rg, nh);

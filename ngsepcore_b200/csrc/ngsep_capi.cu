@@ -53,6 +53,7 @@ struct Slot {
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
     DevBuf<uint4> d_open;                     // single-tile launches: the tile's own open-column list (its counter sits in d_counters)
+    DevBuf<uint2> d_ent;                      //                       ... and the resolved entries of its open columns
     DevBuf<uint16_t> d_group;                 // multi-sample contexts: read-group id per record
     DevBuf<uint32_t> d_gidx, d_goff, d_gblk;          //                        records indexed by read group (launch_group_index)
     DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
@@ -75,7 +76,7 @@ struct Slot {
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
-        d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release();
+        d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release(); d_ent.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
@@ -113,6 +114,7 @@ struct Ctx {
     DevBuf<WinRange> d_bwin;
     // column queue shared by every launch of this context (launches are stream-ordered)
     DevBuf<uint4> d_open;
+    DevBuf<uint2> d_ent;     // resolved entries of the open columns (a full list only costs speed: such columns go out as record ranges)
     size_t q_min_cols = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
     bool batch_dirty = true, batch_ran = false;
@@ -163,6 +165,12 @@ void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
     if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) cols += len + 1024;   // sample axis: every candidate stays open
     else cols += len / 32 + 16384;
 }
+// Entry-list capacity: open columns are a fraction of a percent of the positions and hold `depth` entries each, i.e. a few
+// tenths of an entry per record.  Only single-sample production runs use the list.
+size_t entries_need(const Ctx* c, const Slot* s) {
+    if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) return 0;
+    return std::min<size_t>((size_t)s->tile.n_reads / 2 + 65536, 0x7fffffffull);
+}
 
 int ensure_queue(Ctx* c, size_t cols) {
     cols = std::max(cols, c->q_min_cols);
@@ -174,13 +182,15 @@ int ensure_queue(Ctx* c, size_t cols) {
 ColumnQueue queue_view(Ctx* c) {   // the batched launch over the resident tiles
     ColumnQueue q;
     q.open = c->d_open.p; q.ctr = (unsigned int*)c->d_meta; q.cap_open = (unsigned int)c->d_open.cap;
+    q.ent = c->d_ent.p; q.cap_ent = (unsigned int)std::min<size_t>(c->d_ent.cap, 0x7fffffffull);
     return q;
 }
-// A single-tile launch has its own list: its kernels may overlap those of the next tile.  The kernels only touch ctr[2],
-// which is placed on the n_open word (byte 20) of the slot's counter block.
+// A single-tile launch has its own lists: its kernels may overlap those of the next tile.  The kernels only touch ctr[2]
+// and ctr[3], which are placed on the n_open and n_ent words (bytes 20, 24) of the slot's counter block.
 ColumnQueue queue_view(Slot* s) {
     ColumnQueue q;
     q.open = s->d_open.p; q.ctr = (unsigned int*)((unsigned char*)s->d_counters + 12); q.cap_open = (unsigned int)s->d_open.cap;
+    q.ent = s->d_ent.p; q.cap_ent = (unsigned int)std::min<size_t>(s->d_ent.cap, 0x7fffffffull);
     return q;
 }
 
@@ -204,6 +214,7 @@ int launch_slot(Ctx* c, Slot* s) {
     cols = std::max(cols, c->q_min_cols);
     if (cols > 0x7ffffff0ull) return fail(c, NGSEP_ENOMEM, "open-column list too large (split the tile)");
     CK(s->d_open.reserve(cols), "open-column list alloc");   // the slot is idle here (its previous tile has been fetched)
+    CK(s->d_ent.reserve(entries_need(c, s)), "column entry list alloc");
     CK(cudaMemsetAsync(s->d_counters, 0, kMetaStride, c->stream), "memset counters");
     s->launches = 0;
     int rc = clear_counts_dbg(c, s);
@@ -254,6 +265,11 @@ int launch_batch(Ctx* c) {
     for (size_t i = 1; i < n; i++) queue_need(c, c->slots[i], cols);
     int rc = ensure_queue(c, cols);
     if (rc != NGSEP_OK) return rc;
+    {
+        size_t ents = 0;
+        for (size_t i = 1; i < n; i++) ents += entries_need(c, c->slots[i]);
+        CK(c->d_ent.reserve(std::min<size_t>(ents, 0x7fffffffull)), "column entry list alloc");
+    }
     CK(cudaMemsetAsync(c->d_meta, 0, (1 + n) * kMetaStride, c->stream), "memset counters");   // queue + every slot: ONE memset
     for (size_t i = 1; i < n; i++) { rc = clear_counts_dbg(c, c->slots[i]); if (rc != NGSEP_OK) return rc; }
     CK(cudaEventRecord(c->b0, c->stream), "event record");
@@ -282,6 +298,7 @@ int read_report(Ctx* c, Slot* s) {
     if (rep.err & 1u) return fail(c, NGSEP_EINVAL, "records are not sorted by start");
     if (rep.err & 2u) return fail(c, NGSEP_EINVAL, "payload offsets are not monotone");
     if (rep.err & 4u) return fail(c, NGSEP_EINVAL, "record payload exceeds the device window (read too long)");
+    if (rep.err & 8u) return fail(c, NGSEP_EINVAL, "a record's body does not fit its payload span, or its qualities lie outside the quality array");
     return NGSEP_OK;
 }
 
@@ -361,7 +378,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
     // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
     CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
-    launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, c->cfg.pay_cap_words, s->d_report(), c->stream);
+    launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, (unsigned long long)t->n_qual, c->cfg.pay_cap_words, s->d_report(), c->stream);
     s->report_read = false;
     s->aligned_bases = 0;
     // window length: a multiple of 128, shrunk while an average window would not fit one stage
@@ -624,7 +641,7 @@ int ngsep_ctx_destroy(void* ctx) {
     for (auto& r : c->refs) r.release();
     for (Slot* s : c->slots) { s->release(); delete s; }
     for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
-    c->d_btiles.release(); c->d_bwin.release(); c->d_open.release();
+    c->d_btiles.release(); c->d_bwin.release(); c->d_open.release(); c->d_ent.release();
     c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release(); c->d_gins.release(); c->d_gkeys.release(); c->d_gvals.release(); c->d_cub.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);

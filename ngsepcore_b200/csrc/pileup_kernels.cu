@@ -14,7 +14,7 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, t0, kmin, misc, cnt, list, ulist, open, wmax, rare;   // CTA-wide arrays
+    unsigned bar, t0, kmin, misc, cnt, cov, list, wtot, wmax, rare;   // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
@@ -22,10 +22,15 @@ struct SmemLayout {
 
 // s_misc holds two sets of kMiscSet ints (one per window parity)
 constexpr int kMiscSet = 16;
-constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8, M_NUNRES = 9;
+constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NUNRES = 9;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
-constexpr int kMaxOpen = 64;     // open columns listed in shared memory per window (more go straight to the global list)
-constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: k_extract_columns searches it
+constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: the genotype kernel searches it
+// open-column entry, .w: either the number of records of the range that starts at record .z (0xffff = search), or — bit 31
+// set — the number of (record, offset) entries the window kernel resolved for the column (bits 0-23; they start at entry .z
+// of the entry list) with the reference allele in bits 24-25
+constexpr uint32_t kOpenEntries = 0x80000000u, kOpenCountMask = 0x00ffffffu;
+constexpr int kOpenRefShift = 24;
+constexpr uint32_t kEntNeg = 1u << 18, kEntNotAcgt = 1u << 19;   // ColumnEntry.y: bits 0-15 read offset, 16-17 base, 18 strand, 19 base outside ACGT
 
 // State only thread 0 touches (kept in shared memory so that it costs no registers in the other 255 threads).
 struct Thread0State {
@@ -44,10 +49,10 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.kmin = o; o += kSkipTable * 4;
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
+    L.cov = o; o += (T + 1) * 4;                // callable-cover deltas of the simple records, then their prefix sums
     L.list = o; o += T * 4;
-    L.ulist = o; o += ((T * 2 + 3) & ~3u);      // candidates the quarter-warp proofs left open
+    L.wtot = o; o += (kThreads / 32) * 4;       // per-warp totals of the prefix scan
     o = (o + 7u) & ~7u;
-    L.open = o; o += 2 * kMaxOpen * 8;   // open columns of the window, one list per window parity
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
     o = (o + 7u) & ~7u;
     L.rare = o; o += (L.max_reads + 1) * 8;
@@ -153,25 +158,17 @@ __device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h) {
 struct WinCtx {
     int wbeg, g_lo, g_hi;        // 0-based index of the window start; [g_lo,g_hi) = the window inside tile and sequence
     const uint32_t* s_ref2;      // staged reference, base index wbeg - kRefLeft at bit 0 of word 0
-    uint32_t* s_cnt;             // per position: flagged bases (an upper bound of the counted non-reference bases)
-    uint32_t* s_list;            // candidate list: position in the window | record that flagged it first << kListShift
+    uint32_t* s_cnt;             // per position: bits 0-15 flagged bases (an upper bound of the counted non-reference bases),
+                                 // bits 16-31 low-quality bases (q <= 3, never counted: CH:214) of simple records inside their callable range
+    int* s_cov;                  // per position: +1 / -1 where the callable range of a simple record starts / ends
+    uint32_t* s_list;            // candidate list: positions in the window
     int* mset;                   // counters of this window
     bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
+    bool proof;                  // collect the cover / low-quality counts the hom-ref proof needs (single-sample contexts)
 };
-// candidate list entry as the screen writes it: bits 0-12 position in the window (windows hold at most 8192 positions),
-// 13-31 the flagging record.  The resolve pass (C1) rewrites it in place for the proofs: 0-12 position, 13-14 reference
-// allele, 15-20 `need` = k_min[m_up] (63 = no number of reference bases closes the column), 21-31 flagging record.
-constexpr int kListShift = 13;
-constexpr uint32_t kListPosMask = (1u << kListShift) - 1u;
-constexpr int kListMaxRec = (1 << (32 - kListShift)) - 1;
-constexpr int kProofRefShift = 13, kProofNeedShift = 15, kProofRecShift = 21;
-constexpr int kProofMaxRec = (1 << (32 - kProofRecShift)) - 1, kProofNoNeed = 63;
-
-// rec = index of the flagging record inside the window's record range
-__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx, int rec) {
+__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx) {
     const int li = idx - w.wbeg;
-    if (atomicAdd(&w.s_cnt[li], 1u) == 0u)
-        w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li | ((uint32_t)min(rec, kListMaxRec) << kListShift);
+    if ((atomicAdd(&w.s_cnt[li], 1u) & 0xffffu) == 0u) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li;
 }
 
 // 16 read bases (one payload word) against the reference at 0-based index `idx0` of the word's first base
@@ -181,12 +178,36 @@ __device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
 }
 
 // Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
-__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
+// Besides the mismatch flags it leaves what the hom-ref proof of the window needs: the record's CALLABLE
+// range (RA:782-784) as +1 / -1 in s_cov, and its low-quality bases (never counted, CH:214) inside that range in the
+// upper half of s_cnt.  Per position p that gives, after a prefix sum, EXACTLY how many simple records hold a counted base
+// equal to the reference at p: cover(p) - lowq(p) - flagged(p).
+__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
     const int L = (int)(h.meta & 0xffffu);         // one match block of L bases
     const int ref0 = h.first - 1;                  // 0-based index of read offset 0
     const int a = max(ref0, w.g_lo), b = min(ref0 + L, w.g_hi);
     if (a < b && w.collect) {
         const uint32_t* b2 = pay + 1;
+        const uint32_t* lowq = b2 + ((L + 15) >> 4);   // simple record: the low-quality mask follows the bases
+        const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
+        if (w.proof) {
+            const int ca = max(ref0 + c_lo, w.g_lo), cb = min(ref0 + c_hi, w.g_hi);
+            if (ca < cb) {
+                atomicAdd(&w.s_cov[ca - w.wbeg], 1);
+                atomicAdd(&w.s_cov[cb - w.wbeg], -1);
+                const int o_lo = ca - ref0, o_hi = cb - ref0;   // read offsets [o_lo, o_hi) are callable and inside the window
+                for (int wi = o_lo >> 5; wi <= (o_hi - 1) >> 5; wi++) {
+                    uint32_t m = lowq[wi];
+                    if (m == 0u) continue;
+                    m &= range_mask32(max(o_lo - 32 * wi, 0), min(o_hi - 32 * wi, 32));
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        atomicAdd(&w.s_cnt[ref0 + 32 * wi + bit - w.wbeg], 0x10000u);
+                    }
+                }
+            }
+        }
         const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;       // payload words that intersect the window
         const int r0 = ref0 + 16 * j0 - w.wbeg + kRefLeft;
         const int sh = (r0 & 15) * 2;
@@ -204,13 +225,11 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
         };
         // rare: some base of word j differs — flag the ones CountsHelper would count (callable, RA:782-784; q > 3, CH:214)
         auto flag_word = [&](int j, uint32_t m) {
-            const uint32_t* lowq = b2 + ((L + 15) >> 4);   // simple record: the low-quality mask follows the bases
-            const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
             while (m) {
                 const int bit = __ffs(m) - 1;
                 m &= m - 1;
                 const int off = 16 * j + (bit >> 1);
-                if (off >= c_lo && off < c_hi && !((lowq[off >> 5] >> (off & 31)) & 1u)) flag_candidate(w, ref0 + off, rec);
+                if (off >= c_lo && off < c_hi && !((lowq[off >> 5] >> (off & 31)) & 1u)) flag_candidate(w, ref0 + off);
             }
         };
         if (j1 - j0 < 32) {
@@ -251,7 +270,7 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
 // General record (indels, clips, N mask, realigner versions): every aligned base that differs from the reference
 // is flagged (a superset of the counted ones).  Returns the last covered position, or INT_MIN for a version record
 // (its coverage goes through the bitmap fallback).
-__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
+__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
     const RecView r = view_record(h, pay);
     const int lo = max(w.g_lo, (r.vfrom == INT_MIN) ? INT_MIN : r.vfrom - 1);
     const int hi = min(w.g_hi, (r.vto == INT_MAX) ? INT_MAX : r.vto - 1);
@@ -273,7 +292,7 @@ __device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uin
                     while (m) {
                         const int bit = __ffs(m) - 1;
                         m &= m - 1;
-                        flag_candidate(w, o + (bit >> 1) - delta, rec);
+                        flag_candidate(w, o + (bit >> 1) - delta);
                     }
                 }
             }
@@ -505,40 +524,6 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
     return lo;
 }
 
-struct ExactCtx {
-    int wbeg, n_cand, n_unres, max_span, max_back, tile, rec0;   // rec0: index in the tile of the window's first record
-    const uint32_t* s_list;
-    const uint16_t* s_ulist;     // candidates the quarter-warp proofs left open (indexes into s_list)
-    uint32_t* s_cnt;
-    const uint32_t *s_ref2, *s_refn, *s_refl;
-    const int* s_kmin;
-    bool emit_all, ignore_lower;
-};
-
-// Is record idx a simple record whose base at pos is a COUNTED reference base?  (offset = pos - first with one match
-// block, RA:842-871; callable, RA:782-784; q > 3, CH:214.)
-template <bool kGlobal>
-__device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
-    if (idx < 0 || idx >= R.n) return 0;
-    if (kGlobal) {
-        const ngsep_read_hdr h = R.header(idx);
-        const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
-        if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
-        const uint32_t* b2 = R.payload(h) + 1;
-        const uint32_t* lowq = b2 + ((L + 15) >> 4);
-        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
-    } else {
-        // staged window: the screen left the header in its proof form {first, first callable position, end of the callable
-        // positions (0, 0 for a record that is not simple), b2 word index | lowq word offset << 16}
-        const int4 dh = *(const int4*)(R.hdr + idx);
-        if (pos < dh.y || pos >= dh.z) return 0;
-        const int off = pos - dh.x;
-        const uint32_t* b2 = R.pay + (dh.w & 0xffff);
-        const uint32_t* lowq = b2 + ((uint32_t)dh.w >> 16);
-        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
-    }
-}
-
 // The exact column (warp-cooperative, records through L2): every record of [i_lo, i_hi) in pileup order, one record per
 // lane and round.  lane_eval restates PR.getAlleleCalls(1) + the quality rules of CH.updateCounts; ballots give the exact
 // counts[4], countsStrand[4][2] and totalCount; columns whose exact counts prove the homozygous-reference call are
@@ -570,8 +555,9 @@ __device__ __forceinline__ void accumulate_round(uint32_t code, double& acc, int
     }
 }
 
-__device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev& d, const GenoCtx& g, int pos, int ref, bool ref_bad,
-                                             int i_lo, int i_hi, int lane) {
+// code_at(k) = the evidence code (lane_eval / entry_code) of the k-th record of the column, k in [0, n); 0 for k >= n
+template <class CodeAt>
+__device__ __forceinline__ void exact_column(CodeAt code_at, int n, const TileDev& d, const GenoCtx& g, int pos, int ref, bool ref_bad, int lane) {
     // lanes 0-3 own L[i][i]; lanes 4-9 own L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3]
     const int pa = (lane < 4) ? lane : ((lane < 7) ? 0 : ((lane < 9) ? 1 : 2));
     const int pb = (lane < 4) ? lane : ((lane < 7) ? lane - 3 : ((lane < 9) ? lane - 5 : 3));
@@ -579,30 +565,17 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
     ColCounts cc;
     for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
     cc.depth = 0;
-    const bool in_regs = (i_hi - i_lo) <= 32 * kRegRounds;
+    const bool in_regs = n <= 32 * kRegRounds;
     uint32_t codes[kRegRounds];
     if (in_regs) {
-        // all the loads of the column are issued before the first ballot: headers, then quality + bases of every round
-        ngsep_read_hdr hs[kRegRounds];
+        // every load of the column is issued before the first ballot
 #pragma unroll
-        for (int r = 0; r < kRegRounds; r++) {
-            const int idx = i_lo + 32 * r + lane;
-            hs[r].meta = 0u; hs[r].first = 0; hs[r].ign_start = hs[r].ign_end = 0; hs[r].off = 0u;
-            if (idx < i_hi) hs[r] = R.header(idx);
-        }
-#pragma unroll
-        for (int r = 0; r < kRegRounds; r++)
-            codes[r] = (i_lo + 32 * r + lane < i_hi) ? lane_eval(hs[r], R.payload(hs[r]), d.qual, pos, g.max_qs) : 0u;
+        for (int r = 0; r < kRegRounds; r++) codes[r] = code_at(32 * r + lane);
 #pragma unroll
         for (int r = 0; r < kRegRounds; r++) count_round(codes[r], cc);
     } else {
-        for (int base = i_lo; base < i_hi; base += 32) {   // deep column: count and sum on the fly
-            const int idx = base + lane;
-            uint32_t code = 0u;
-            if (idx < i_hi) {
-                const ngsep_read_hdr h = R.header(idx);
-                code = lane_eval(h, R.payload(h), d.qual, pos, g.max_qs);
-            }
+        for (int base = 0; base < n; base += 32) {   // deep column: count and sum on the fly
+            const uint32_t code = code_at(base + lane);
             count_round(code, cc);
             accumulate_round(code, acc, lane, pa, pb, g.s_tab);
         }
@@ -615,7 +588,7 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
     const int tot = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
     const int k_ref = (ref == 0) ? cc.c[0] : ((ref == 1) ? cc.c[1] : ((ref == 2) ? cc.c[2] : cc.c[3]));
     const int m_alt = tot - k_ref;
-    // Proven hom-ref with the exact counts (DESIGN.md 3.3): VD.discoverSNV returns the homozygous-reference call that
+    // Proven hom-ref with the exact counts (DESIGN.md 3.4): VD.discoverSNV returns the homozygous-reference call that
     // SSVPL:223 drops.
     if (g.may_skip && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= g.s_kmin[m_alt]))) return;
     if (in_regs) {
@@ -625,76 +598,87 @@ __device__ __forceinline__ void exact_column(const Recs<true>& R, const TileDev&
     finalize_warp(acc, cc, lane, pos, ref, d, g.min_quality, g.s_tab[93], g.s_tab[94]);
 }
 
-// Phase C2.  First proof attempt by a QUARTER-WARP per candidate: the 8 records next to the flagging one (4 on each side)
-// usually hold the k_min[1] = 7 counted reference bases that close a column with one flagged base.  What stays open is
-// listed for the half-warp pass.
-template <bool kGlobal>
-__device__ __forceinline__ void quarter_proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, uint16_t* s_ulist, int* n_unres, int warp, int lane, int nwarps) {
-    const int grp = lane >> 3, gl = lane & 7;
-    const int delta = (gl < 4) ? gl - 4 : gl - 3;   // -4..-1, +1..+4
-    for (int base = 0; base < x.n_cand; base += 4 * nwarps) {
-        const int ci = base + 4 * warp + grp;
-        int ok = 0, need = 0;
-        bool open = false;
-        if (ci < x.n_cand) {
-            const uint32_t ent = x.s_list[ci];
-            need = (int)((ent >> kProofNeedShift) & 63u);
-            open = need > 0;                               // need == 0: closed by the resolve pass
-            if (open && need <= 8)
-                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) + delta, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
-        }
-        const unsigned okm = __ballot_sync(kFull, ok != 0);
-        if (open && __popc(okm & (0xffu << (8 * grp))) >= need) open = false;
-        if (open && gl == 0) s_ulist[atomicAdd(n_unres, 1)] = (uint16_t)ci;
+// ------------------------------------------------------------------------------------------------------------
+// open columns: what the window kernel hands to k_genotype_columns
+// ------------------------------------------------------------------------------------------------------------
+// One record of an open column, resolved by the window kernel while the record sits in shared memory: everything
+// PR.getAlleleCalls(1) + CH.updateCounts need except the quality byte itself.  Returns false when the record gives no
+// call at pos (same rules as lane_eval).
+__device__ __forceinline__ bool resolve_entry(const ngsep_read_hdr& h, const uint32_t* pay, int pos, uint2& ent) {
+    uint32_t bw, qoff, extra = 0u;
+    int off;
+    if (h.meta & NGSEP_M_SIMPLE) {
+        const int L = (int)(h.meta & 0xffffu);
+        off = pos - h.first;
+        if (off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return false;   // RA:782-784
+        const uint32_t* b2 = pay + 1;
+        qoff = b2[((L + 15) >> 4) + ((L + 31) >> 5)];
+        bw = b2[off >> 4];
+    } else {
+        const RecView r = view_record(h, pay);
+        off = resolve_offset(r, h.ign_start, h.ign_end, pos);
+        if (off < 0) return false;
+        qoff = r.qoff;
+        bw = r.b2[off >> 4];
+        if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) extra = kEntNotAcgt;   // a call that is not counted (CH:220-221)
     }
+    ent.x = qoff;
+    ent.y = (uint32_t)off | (((bw >> ((off & 15) * 2)) & 3u) << 16) | ((h.meta & NGSEP_M_NEG) ? kEntNeg : 0u) | extra;
+    return true;
 }
 
-// Phase C3.  Fast proof of hom-ref by a HALF-WARP per candidate the quarter-warp pass left open: at most m_up counted non-reference bases
-// were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
-// of the records does).  k_lb >= need = k_min[m_up] closes the column.  What stays open is listed, with its record range,
-// for k_genotype_columns.  Entries come from the resolve pass (position | reference allele | need | flagging record).
+// The quality rules of CH.updateCounts on a resolved entry (the tail of lane_eval): the only global load is the quality byte.
+__device__ __forceinline__ uint32_t entry_code(const uint2 ent, const uint8_t* __restrict__ qual, int max_qs) {
+    uint32_t qc = qual[(size_t)ent.x * 4u + (size_t)(ent.y & 0xffffu)];
+    if (ent.y & kEntNotAcgt) qc = 0u;
+    int q = (int)qc - 33;
+    q = min(30, q);                                   // CH:91
+    if (q <= 3) return kCodeCall;                     // CH:214-216
+    if (q > max_qs) q = max_qs;                       // CH:217-219
+    return kCodeCall | kCodeCounted | ((ent.y >> 16) & 3u) | ((uint32_t)q << 2) | ((ent.y & kEntNeg) ? kCodeNeg : 0u);
+}
+
+// An open column of the window (warp-cooperative): its record range, then — windows staged in one piece — one entry per
+// record that gives a call, in pileup order, so that k_genotype_columns only has to fetch quality bytes.  Columns of
+// windows too deep for a stage, and columns that do not fit the entry list, are handed over as a record range.
 template <bool kGlobal>
-__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, uint2* s_open, int* n_open,
-                                            int warp, int lane, int nwarps) {
-    const int grp = lane >> 4, gl = lane & 15;
-    for (int base = 0; base < x.n_unres; base += 2 * nwarps) {
-        const int ui = base + 2 * warp + grp;
-        uint32_t ent = 0u;
-        int ok = 0, need = 0;
-        bool open = false;
-        if (ui < x.n_unres) {
-            ent = x.s_list[x.s_ulist[ui]];
-            need = (int)((ent >> kProofNeedShift) & 63u);
-            open = true;
-            if (need <= 15)
-                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) - 8 + gl, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
+__device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const ColumnQueue& cq, int tile, int rec0, int pos, int ref, int max_span, int max_back,
+                                                 bool span_capped, int lane) {
+    const int i_lo = warp_lower_bound(R, pos - max_span + 1, lane);
+    const int i_hi = warp_lower_bound(R, pos + max_back + 1, lane);   // first record that starts too far to the right
+    if (i_hi <= i_lo) return;
+    const uint32_t n_range = (uint32_t)(i_hi - i_lo);
+    bool as_range = kGlobal || span_capped || cq.cap_ent == 0u || n_range > kOpenCountMask;
+    unsigned int ebase = 0u;
+    if (!as_range) {
+        if (lane == 0) ebase = atomicAdd(&cq.ctr[3], n_range);
+        ebase = __shfl_sync(kFull, ebase, 0);
+        if (ebase > cq.cap_ent || n_range > cq.cap_ent - ebase) as_range = true;   // the list is full: the genotype kernel resolves the records itself
+    }
+    if (as_range) {
+        if (lane == 0) {
+            const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
+            if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)tile, (unsigned int)pos, (unsigned int)(rec0 + i_lo), span_capped ? kOpenSearch : min(n_range, kOpenSearch));
         }
-        const unsigned okm = __ballot_sync(kFull, ok != 0);
-        if (open && __popc(okm & (0xffffu << (16 * grp))) >= need) open = false;
-        // the (few) columns still open: second chance with the whole warp (the 32 records around the flagging one), then
-        // the record range of the column, then the list
-        unsigned sm = __ballot_sync(kFull, open && gl == 0);
-        while (sm) {
-            const int src = __ffs(sm) - 1;
-            sm &= sm - 1;
-            const uint32_t e = __shfl_sync(kFull, ent, src);
-            const int e_need = (int)((e >> kProofNeedShift) & 63u);
-            const int e_li = (int)(e & kListPosMask), e_pos = x.wbeg + e_li + 1;
-            if (e_need <= 30) {
-                const int ok2 = counted_ref_base(R, (int)(e >> kProofRecShift) - 16 + lane, e_pos, (int)((e >> kProofRefShift) & 3u));
-                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= e_need) continue;
+        return;
+    }
+    if (!kGlobal) {
+        unsigned int n_ent = 0u;
+        for (int base = i_lo; base < i_hi; base += 32) {
+            const int idx = base + lane;
+            uint2 ent = make_uint2(0u, 0u);
+            bool ok = false;
+            if (idx < i_hi) {
+                const ngsep_read_hdr h = R.header(idx);
+                ok = resolve_entry(h, R.payload(h), pos, ent);
             }
-            const int i_lo = warp_lower_bound(R, e_pos - x.max_span + 1, lane);
-            const int i_hi = warp_lower_bound(R, e_pos + x.max_back + 1, lane);   // first record that starts too far to the right
-            if (lane == 0 && i_hi > i_lo) {
-                const uint32_t n_range = (uint32_t)min(i_hi - i_lo, (int)kOpenSearch);
-                const int slot = atomicAdd(n_open, 1);
-                if (slot < kMaxOpen) s_open[slot] = make_uint2((uint32_t)e_li | (n_range << 16), (uint32_t)(x.rec0 + i_lo));
-                else {   // rare: the window's list is full
-                    const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
-                    if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)x.tile, (unsigned int)e_pos, (unsigned int)(x.rec0 + i_lo), n_range);
-                }
-            }
+            const unsigned int m = __ballot_sync(kFull, ok);
+            if (ok) cq.ent[ebase + n_ent + (unsigned int)__popc(m & ((1u << lane) - 1u))] = ent;
+            n_ent += (unsigned int)__popc(m);
+        }
+        if (lane == 0 && n_ent > 0u) {
+            const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
+            if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)tile, (unsigned int)pos, ebase, kOpenEntries | ((uint32_t)ref << kOpenRefShift) | n_ent);
         }
     }
 }
@@ -721,30 +705,38 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     int* s_kmin = (int*)(smem + lay.kmin);
     int* s_misc = (int*)(smem + lay.misc);
     uint32_t* s_cnt = (uint32_t*)(smem + lay.cnt);
+    int* s_cov = (int*)(smem + lay.cov);
     uint32_t* s_list = (uint32_t*)(smem + lay.list);
-    uint16_t* s_ulist = (uint16_t*)(smem + lay.ulist);
+    int* s_wtot = (int*)(smem + lay.wtot);
     int* s_wmax = (int*)(smem + lay.wmax);
     int2* s_rare = (int2*)(smem + lay.rare);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevParams& prm = *a.prm;
+    const int T_lay = a.cfg.T_lay;
+    const int P = (T_lay + nthr - 1) / nthr;   // positions per thread in the prefix scan and in the clearing pass
     if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
     if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
-    for (int i = tid; i < a.cfg.T_lay + 1; i += nthr) s_cnt[i] = 0u;
+    for (int i = tid; i < T_lay + 1; i += nthr) { s_cnt[i] = 0u; s_cov[i] = 0; }
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
     uint32_t phase_bits = 0u;   // bit s = parity the next wait on stage s must see
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     const bool multi = prm.n_samples > 1;
+    const bool proofs = !multi && !emit_all && prm.fast_homref != 0;
     const int n_stages = a.cfg.n_stages;
     const int stride = (int)gridDim.x;
+    // The thread that issues the bulk copies.  One stage: thread 0 (the copies of the next window start when the stage frees).
+    // Two stages: lane 0 of the LAST warp issues the next window's copies right after the top barrier, while the other warps
+    // are already screening the current window, so the copies overlap the whole window.
+    const int issuer = (n_stages == 2) ? nthr - 32 : 0;
 
     auto fits = [&](const WinRange& wr) {
         return (wr.hi - wr.lo) <= (int)lay.max_reads && (wr.off_hi - (wr.off_lo & ~3u)) <= a.cfg.pay_cap_words;
     };
 
-    // ---- thread 0 only: window descriptors are read ahead of their use, tile fields are cached while the tile stays --------
+    // ---- issuer only: window descriptors are read ahead of their use, tile fields are cached while the tile stays -----------
     Thread0State& t0 = *(Thread0State*)(smem + lay.t0);
     // one mbarrier phase = the window descriptor + the reference window + (windows that fit a stage) the whole record range
     auto issue_window = [&](const WinRange& wr, int w_idx, int stage) {
@@ -780,7 +772,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 
     int w = blockIdx.x;
     if (w >= a.n_windows) return;
-    if (tid == 0) {
+    if (tid == issuer) {
         t0.tile = -1; t0.acc_tile = -1; t0.acc_cov = 0ull; t0.acc_cand = 0ull; t0.prefetched = 0;
         t0.dq[0] = a.win[w];
         t0.dq[1] = (w + stride < a.n_windows) ? a.win[w + stride] : t0.dq[0];
@@ -788,15 +780,18 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     for (int it = 0; w < a.n_windows; it++) {
         const int cur = (n_stages == 2) ? (it & 1) : 0;
         const int wn = w + stride;
-        if (tid == 0) {
-            WinRange dq2;   // window w + 2 stride: requested now, consumed at the end of this block (its latency overlaps the issue)
-            const bool have2 = wn + stride < a.n_windows;
-            if (have2) dq2 = a.win[wn + stride];
-            if (!t0.prefetched) issue_window(t0.dq[0], w, cur);
-            t0.prefetched = 0;
-            if (n_stages == 2 && wn < a.n_windows) { issue_window(t0.dq[1], wn, cur ^ 1); t0.prefetched = 1; }   // other stage: free since the trailing barrier
-            t0.dq[0] = t0.dq[1];
-            if (have2) t0.dq[1] = dq2;
+        if (tid == issuer) {
+            if (n_stages == 2) {
+                if (!t0.prefetched) issue_window(t0.dq[0], w, cur);   // first window of the CTA only
+            } else {
+                WinRange dq2;   // window w + 2 stride: requested now, consumed at the end of this block (its latency overlaps the issue)
+                const bool have2 = wn + stride < a.n_windows;
+                if (have2) dq2 = a.win[wn + stride];
+                if (!t0.prefetched) issue_window(t0.dq[0], w, cur);
+                t0.prefetched = 0;
+                t0.dq[0] = t0.dq[1];
+                if (have2) t0.dq[1] = dq2;
+            }
         }
         unsigned char* stg = smem + lay.stage0 + (unsigned)cur * lay.stage_stride;
         const ngsep_read_hdr* s_hdr = (const ngsep_read_hdr*)(stg + lay.o_hdr);
@@ -807,21 +802,36 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         phase_bits ^= 1u << cur;
         __syncthreads();
 
+        if (n_stages == 2 && tid == issuer) {
+            // the other stage has been free since the trailing barrier of the previous window: the next window's copies run
+            // under this window's screen and proofs
+            const bool have2 = wn + stride < a.n_windows;
+            WinRange dq2;
+            if (have2) dq2 = a.win[wn + stride];
+            t0.prefetched = 0;
+            if (wn < a.n_windows) { issue_window(t0.dq[1], wn, cur ^ 1); t0.prefetched = 1; }
+            t0.dq[0] = t0.dq[1];
+            if (have2) t0.dq[1] = dq2;
+        }
+
         const WinRange wr = *(const WinRange*)(stg + lay.o_win);
         const int wbeg = wr.wbeg, g_lo = wr.wbeg + (int)(wr.g_pack & 0xffffu), g_hi = wr.wbeg + (int)(wr.g_pack >> 16);
         const int A = g_lo + 1, B = g_hi;   // 1-based inclusive positions of the window (empty when A > B)
         const int n_rec = wr.hi - wr.lo;
         const bool single = fits(wr);
+        const int max_span = (int)(wr.span_pack & 0xffffu), max_back = (int)(wr.span_pack >> 16);
+        const bool span_capped = max_span == 0xffff || max_back == 0xffff;   // the tile's real spans are larger: columns go out without a record range
         WinCtx wc;
         wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
         wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
-        wc.s_cnt = s_cnt; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
+        wc.s_cnt = s_cnt; wc.s_cov = s_cov; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
+        wc.proof = proofs && n_rec < 0xffff;   // (the 16-bit halves of s_cnt cannot overflow)
 
         // ---- phase A: screen + coverage scan, one thread per record -------------------------------------------------
         // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
         // positions of (reach_i, s_{i+1}) are covered by nobody.  reach_i is at least the warp-local prefix maximum; only
         // when that does not reach s_{i+1} - 1 is the record queued for the exact cross-warp evaluation (process_rare).
-        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, int rec0, bool first_chunk) {
+        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, bool first_chunk) {
             for (int base = 0; base < n_chunk; base += nthr) {
                 const int i = base + tid;
                 const bool act = i < n_chunk;
@@ -829,17 +839,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 if (act) {
                     const ngsep_read_hdr h = s_hdr[i];
                     const uint32_t* pay = s_pay + (h.off - pay_base);
-                    e = record_is_simple(h) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
-                    {   // proof form of the staged header (counted_ref_base<false>); word 0 (the ordering start) stays
-                        int4 dh = make_int4(h.first, 0, 0, 0);
-                        if (record_is_simple(h)) {
-                            const int L = (int)(h.meta & 0xffffu);
-                            dh.y = h.first + max((int)h.ign_start, 0);
-                            dh.z = h.first + L - max((int)h.ign_end, 0);
-                            dh.w = (int)((uint32_t)(pay + 1 - s_pay) | ((uint32_t)((L + 15) >> 4) << 16));
-                        }
-                        *(int4*)(const_cast<ngsep_read_hdr*>(s_hdr) + i) = dh;
-                    }
+                    e = record_is_simple(h) ? screen_simple(h, pay, wc) : screen_general(h, pay, wc);
                     nxt = min(s_hdr[i + 1].first, B + 1);
                     floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
                     if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         };
 
         if (single) {
-            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, 0, true);
+            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, true);
             else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
         } else {
             // windows too deep for one stage: stream the record range chunk by chunk through the current stage
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 const int carry = mset[M_CARRY];
                 mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);
                 phase_bits ^= 1u << cur;
-                screen_chunk(r1 - r0, pay_base, r0 - wr.lo, first_chunk);
+                screen_chunk(r1 - r0, pay_base, first_chunk);
                 __syncthreads();
                 process_rare(carry);
                 __syncthreads();
@@ -906,12 +906,10 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 r0 = r1;
             }
         }
-        __syncthreads();   // ---- sync 1: candidates listed ---------------------------------------------------------------
+        __syncthreads();   // ---- sync 1: candidates listed, cover deltas and low-quality counts complete ----------------------
 
         if (tid < kMiscSet) s_misc[((it & 1) ^ 1) * kMiscSet + tid] = (tid == M_CARRY) ? INT_MIN : 0;   // next window's counters
         if (single && n_rec > 0) process_rare(INT_MIN);
-        // ---- phase C: hom-ref proofs (half-warp per candidate); what stays open is listed for k_extract_columns -----------
-        uint2* s_open = (uint2*)(smem + lay.open) + (it & 1) * kMaxOpen;
         const int n_cand = emit_all ? 0 : mset[M_NCAND];
         if (emit_all) {   // test hook: every position of the window is an open column
             const int n_all = (n_rec > 0) ? max(0, g_hi - g_lo) : 0;
@@ -926,13 +924,12 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             // largely the same (L1 reuse).  Bitmap of the open positions -> ordered list -> record range per position.
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
-            uint32_t* s_bm = (uint32_t*)s_ulist;
-            const int nw = (a.cfg.T_lay + 31) >> 5;
+            uint32_t* s_bm = (uint32_t*)s_cov;   // (no cover deltas are collected on the sample axis)
+            const int nw = (T_lay + 31) >> 5;
             for (int i = tid; i < nw; i += nthr) s_bm[i] = 0u;
             __syncthreads();
             for (int ci = tid; ci < n_cand; ci += nthr) {
-                const int li = (int)(s_list[ci] & kListPosMask);
-                s_cnt[li] = 0u;   // (nothing else clears s_cnt)
+                const int li = (int)s_list[ci];
                 bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // SSVPL:298-305
                 if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
                 if (!closed) atomicOr(&s_bm[li >> 5], 1u << (li & 31));
@@ -952,7 +949,6 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             __syncthreads();
             const int n_o = mset[M_NUNRES];
             const unsigned int gbase = (unsigned int)mset[M_R1];
-            const int max_span = (int)(wr.span_pack & 0xffffu), max_back = (int)(wr.span_pack >> 16);
             for (int k = warp; k < n_o; k += nwarps) {
                 const int e_pos = wbeg + (int)s_list[k] + 1;
                 int i_lo, i_hi;
@@ -967,47 +963,63 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                     i_hi = warp_lower_bound<true>(R, e_pos + max_back + 1, lane);
                 }
                 if (lane == 0 && gbase + (unsigned int)k < a.cq.cap_open)
-                    a.cq.open[gbase + k] = make_uint4((unsigned int)wr.tile, (unsigned int)e_pos, (unsigned int)(wr.lo + i_lo), (uint32_t)min(max(i_hi - i_lo, 0), (int)kOpenSearch));
+                    a.cq.open[gbase + k] = make_uint4((unsigned int)wr.tile, (unsigned int)e_pos, (unsigned int)(wr.lo + i_lo),
+                                                      span_capped ? kOpenSearch : (uint32_t)min(max(i_hi - i_lo, 0), (int)kOpenSearch));
             }
         } else if (n_cand > 0) {
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
-            // C1, resolve pass (thread per candidate): everything the proofs need goes into the list entry
-            for (int ci = tid; ci < n_cand; ci += nthr) {
-                const uint32_t ent = s_list[ci];
-                const int li = (int)(ent & kListPosMask);
-                const uint32_t m_up = s_cnt[li];
-                s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
-                bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // VD:101-107
-                if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
-                const int rr = li + kRefLeft;
-                const uint32_t ref = (wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
-                int need = (m_up < (uint32_t)kSkipTable) ? min(s_kmin[m_up], kProofNoNeed) : kProofNoNeed;
-                if (need <= 0) need = 1;
-                if (multi) need = kProofNoNeed;   // sample axis: every candidate goes to k_genotype_columns_multi (no proof is attempted)
-                if (closed) need = 0;
-                s_list[ci] = (uint32_t)li | (ref << kProofRefShift) | ((uint32_t)need << kProofNeedShift) |
-                             ((uint32_t)min((int)(ent >> kListShift), kProofMaxRec) << kProofRecShift);
+            // ---- phase B: prefix sums of the cover deltas: s_cov[p] + the totals of the warps in front = simple records whose
+            // callable range holds position p
+            if (wc.proof) {
+                const int p0 = tid * P;
+                int tot = 0;
+                for (int i = 0; i < P; i++) if (p0 + i < T_lay) tot += s_cov[p0 + i];
+                int incl = tot;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+                int run = incl - tot;
+                for (int i = 0; i < P; i++) if (p0 + i < T_lay) { run += s_cov[p0 + i]; s_cov[p0 + i] = run; }
+                if (lane == 31) s_wtot[warp] = incl;
+                __syncthreads();   // ---- sync 3: prefix sums complete ------------------------------------------------------
             }
-            __syncthreads();   // ---- sync 3: entries resolved -----------------------------------------------------------------
-            ExactCtx x;
-            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = (int)(wr.span_pack & 0xffffu); x.max_back = (int)(wr.span_pack >> 16); x.tile = wr.tile; x.rec0 = wr.lo;
-            x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2; x.s_refn = s_refn; x.s_refl = s_refl;
-            x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
-            x.s_ulist = s_ulist; x.n_unres = 0;
-            if (single) {
-                Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                quarter_proof_phase<false>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
-                __syncthreads();   // ---- sync 4: candidates left to the half-warp pass listed --------------------------------------
-                x.n_unres = mset[M_NUNRES];
-                proof_phase<false>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
-            } else {
-                const TileDev& d = a.tiles[wr.tile];
-                Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                quarter_proof_phase<true>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
-                __syncthreads();
-                x.n_unres = mset[M_NUNRES];
-                proof_phase<true>(R, x, a.cq, s_open, &mset[M_NOPEN], warp, lane, nwarps);
+            // ---- phase C: the hom-ref proof, one thread per candidate.  With m = flagged bases (an upper
+            // bound of the counted non-reference bases: simple records exactly, every aligned mismatch of the others) and
+            // k = cover - low-quality - flagged (the counted reference bases of the simple records: a lower bound of all of
+            // them), k >= k_min[m] proves the column homozygous reference and closes it.  What stays open is handed to
+            // k_genotype_columns by the warp, column by column.
+            for (int base = 0; base < n_cand; base += nthr) {
+                const int ci = base + tid;
+                bool open = false;
+                int li = 0;
+                if (ci < n_cand) {
+                    li = (int)s_list[ci];
+                    open = ((s_refn[li >> 5] >> (li & 31)) & 1u) == 0u;                                           // VD:101-107
+                    if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;                      // SSVPL:198
+                    if (open && wc.proof) {
+                        const uint32_t c = s_cnt[li];
+                        const int m_up = (int)(c & 0xffffu), lowq = (int)(c >> 16);
+                        int cover = s_cov[li];
+                        const int ow = li / (32 * P);
+                        for (int k = 0; k < ow; k++) cover += s_wtot[k];
+                        if (m_up < kSkipTable && cover - lowq - m_up >= s_kmin[m_up]) open = false;
+                    }
+                }
+                unsigned om = __ballot_sync(kFull, open);
+                while (om) {
+                    const int src = __ffs(om) - 1;
+                    om &= om - 1;
+                    const int e_li = __shfl_sync(kFull, li, src);
+                    const int rr = e_li + kRefLeft;
+                    const int ref = (int)((wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
+                    if (single) {
+                        Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
+                        emit_open_column<false>(R, a.cq, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped || multi, lane);
+                    } else {
+                        const TileDev& d = a.tiles[wr.tile];
+                        Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
+                        emit_open_column<true>(R, a.cq, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped, lane);
+                    }
+                }
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
@@ -1027,27 +1039,19 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 }
             }
         }
-
-        // warp 0 hands the open columns to the global list (the other warps move on; s_open and mset are per window parity)
-        if (warp == 0) {
-            const int n_open = min(mset[M_NOPEN], kMaxOpen);
-            if (n_open > 0) {
-                unsigned int gbase = 0u;
-                if (lane == 0) gbase = atomicAdd(&a.cq.ctr[2], (unsigned int)n_open);
-                gbase = __shfl_sync(kFull, gbase, 0);
-                for (int i = lane; i < n_open; i += 32) {
-                    const uint2 oe = s_open[i];
-                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = make_uint4((unsigned int)wr.tile, (unsigned int)(wbeg + (int)(oe.x & 0xffffu) + 1), oe.y, oe.x >> 16);
-                }
-            }
+        // the per-position arrays go back to zero for the next window
+        if (!emit_all) {
+            const int p0 = tid * P;
+            for (int i = 0; i < P; i++) if (p0 + i < T_lay) { s_cnt[p0 + i] = 0u; s_cov[p0 + i] = 0; }
+            if (tid == 0) { s_cnt[T_lay] = 0u; s_cov[T_lay] = 0; }
         }
 
         int uncovered = mset[M_UNC];
         const int win_len = max(0, B - A + 1);
         if (uncovered > 0 && mset[M_HASVER] && n_rec > 0) {
             // rare: a gap in the cover of the unversioned records while realigner versions are present — count the cover
-            // of every record with a bitmap (s_cnt is all zero here — every listed position reset its counter — and is
-            // cleared again below)
+            // of every record with a bitmap (s_cnt has just been cleared and is cleared again below)
+            __syncthreads();
             const TileDev& d = a.tiles[wr.tile];
             uint32_t* s_bm = s_cnt;
             const int n_words = (g_hi - wbeg + 31) >> 5;
@@ -1068,20 +1072,21 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             for (int i = tid; i < n_words; i += nthr) s_bm[i] = 0u;
             __syncthreads();
         }
-        if (tid == 0) {
+        if (tid == issuer) {
             if (wr.tile != t0.acc_tile) { flush_stats(); t0.acc_tile = wr.tile; t0.acc_cov = 0ull; t0.acc_cand = 0ull; }
             t0.acc_cov += (unsigned long long)(win_len - uncovered);
             if (!emit_all) t0.acc_cand += (unsigned long long)n_cand;
         }
         w = wn;
     }
-    if (tid == 0) flush_stats();
+    if (tid == issuer) flush_stats();
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // SNVQ genotyping of the open columns: one warp per column, records read through L2
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 6) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
     __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
@@ -1097,20 +1102,36 @@ __global__ void __launch_bounds__(256, 6) k_genotype_columns(const TileDev* __re
     const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
     const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
-        const uint4 oc = cq.open[t];   // tile, position, first record, number of records
+        const uint4 oc = cq.open[t];   // tile, position, then a record range or a resolved entry list (kOpenEntries)
         const TileDev& d = tiles[oc.x];
         const int pos = (int)oc.y;
+        if (oc.w & kOpenEntries) {
+            // the window kernel resolved the column's records while they sat in shared memory (and found the reference base
+            // callable): one coalesced entry load and one quality byte per record
+            const int n = (int)(oc.w & kOpenCountMask);
+            const uint2* ent = cq.ent + oc.z;
+            const uint8_t* __restrict__ qual = d.qual;
+            const int max_qs = g.max_qs;
+            exact_column([&](int k) { return (k < n) ? entry_code(ent[k], qual, max_qs) : 0u; }, n, d, g, pos, (int)((oc.w >> kOpenRefShift) & 3u), false, lane);
+            continue;
+        }
         const int64_t gi = (int64_t)pos - 1;
         if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198: no discovery at all
         const bool ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
         const int ref = (int)((d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u);
         Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
         int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
-        if (oc.w >= kOpenSearch) {   // no range from the window kernel (test hook, or a very deep column)
+        if (oc.w >= kOpenSearch) {   // no range from the window kernel (test hook, a very deep column, spans beyond 65535)
             i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
             i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);   // first record that starts too far to the right
         }
-        exact_column(R, d, g, pos, ref, ref_bad, i_lo, i_hi, lane);
+        const uint8_t* __restrict__ qual = d.qual;
+        const int max_qs = g.max_qs;
+        exact_column([&](int k) {
+            if (i_lo + k >= i_hi) return 0u;
+            const ngsep_read_hdr h = R.header(i_lo + k);
+            return lane_eval(h, R.payload(h), qual, pos, max_qs);
+        }, i_hi - i_lo, d, g, pos, ref, ref_bad, lane);
     }
 }
 
@@ -1548,12 +1569,14 @@ void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStre
 
 // Staging-time check of a tile, on the device copy of its headers (the host thread only enqueues copies):
 //   report[0] |= 1  records not sorted by start      |= 2  payload offsets not monotone / out of range
-//             |= 4  a record larger than one stage    report[2..3] += read lengths (aligned bases, 64 bit)
+//             |= 4  a record larger than one stage    |= 8  a record's body (CIGAR, bases, masks, qoff) does not fit its payload
+//                                                          span, or its qualities reach beyond the quality array
+//   report[2..3] += read lengths (aligned bases, 64 bit)
 // A tile with report[0] != 0 gets an EMPTY window index (k_window_index), so the kernels never walk it; the host reports
 // the error when it fetches the tile.  The packer's NGSEP_M_SIMPLE promise is verified here too: a record whose flag is
 // not backed by its payload loses the flag (and goes through the general path, which is always correct).
-__global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n, unsigned long long n_words, unsigned int pay_cap_words,
-                                unsigned int* report) {
+__global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n, unsigned long long n_words, unsigned long long n_qual,
+                                unsigned int pay_cap_words, unsigned int* report) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int err = 0u, L = 0u;
     if (i < n) {
@@ -1563,6 +1586,15 @@ __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict_
         if (next < h.off || next > n_words) err |= 2u;
         else if (next - h.off + 4ull > pay_cap_words) err |= 4u;
         L = h.meta & 0xffffu;
+        if (!err) {
+            const unsigned int nc = (h.meta >> 16) & 0xffu, lw = (L + 31u) >> 5;
+            const unsigned long long body = ((h.meta & NGSEP_M_WINDOW) ? 3ull : 0ull) + nc + ((L + 15u) >> 4) + ((h.meta & NGSEP_M_NMASK) ? lw : 0u) + lw + 1ull;
+            if (body > next - h.off) err |= 8u;
+            else {
+                const unsigned long long qoff = payload[h.off + body - 1ull];
+                if (qoff * 4ull + L > n_qual) err |= 8u;
+            }
+        }
         if (!err && (h.meta & NGSEP_M_SIMPLE)) {
             const bool ok = (h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && payload[h.off] == ((L << 3) | 3u);
             if (!ok) hdr[i].meta = h.meta & ~NGSEP_M_SIMPLE;
@@ -1575,9 +1607,9 @@ __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict_
     }
 }
 
-void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned int pay_cap_words, unsigned int* report,
-                          cudaStream_t s) {
-    if (n > 0) k_check_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n, n_words, pay_cap_words, report);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int pay_cap_words,
+                          unsigned int* report, cudaStream_t s) {
+    if (n > 0) k_check_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n, n_words, n_qual, pay_cap_words, report);
 }
 
 // The kernel is compiled for two CTA sizes and three register budgets each; the context picks one.
@@ -1610,7 +1642,10 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
 }
 
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
-    k_genotype_columns<<<grid, 256, 0, s>>>(d_tiles, cq, dprm);   // one warp per open column, grid-stride
+    // one warp per open column, grid-stride; two register budgets (NGSEP_GENO_MIN_BLOCKS picks the other one for experiments)
+    static const int min_blocks = [] { const char* e = getenv("NGSEP_GENO_MIN_BLOCKS"); return e ? atoi(e) : 4; }();
+    if (min_blocks >= 6) k_genotype_columns<6><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
+    else k_genotype_columns<4><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

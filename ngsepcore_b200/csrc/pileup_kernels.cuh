@@ -34,7 +34,7 @@ constexpr int kMaxWindow = 8192;       // largest window length (positions); win
 struct WinRange {
     int lo, hi; uint32_t off_lo, off_hi; int tile, wbeg;
     uint32_t g_pack;     // (g_lo - wbeg) | (g_hi - wbeg) << 16
-    uint32_t span_pack;  // the tile's max_span | max_back << 16 (both capped at 65535)
+    uint32_t span_pack;  // the tile's max_span | max_back << 16 (65535 = larger than that: columns are handed over without a record range)
 };
 
 struct TileDev {
@@ -83,8 +83,10 @@ struct DevParams {
 // (tile, 1-based position, index in the tile of the first record that can cover it, number of such records | 0xffff = search).
 struct ColumnQueue {
     uint4* open;
-    unsigned int* ctr;                       // [2] open columns listed ([0], [1] unused)
+    unsigned int* ctr;                       // [2] open columns listed, [3] entries reserved in `ent` ([0], [1] unused)
     unsigned int cap_open;
+    uint2* ent;                              // per-record entries of the open columns the window kernel resolved (see emit_open_column)
+    unsigned int cap_ent;
 };
 
 struct LaunchCfg {
@@ -99,8 +101,8 @@ struct LaunchCfg {
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
 int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
-void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned int pay_cap_words, unsigned int* report,
-                          cudaStream_t s);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int pay_cap_words,
+                          unsigned int* report, cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);

@@ -392,9 +392,25 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
     return genome, batch, truth
 
 
+_POP = {}
+
+
+def _population_sample(smp: int):
+    """Reads of one sample of simulate_population (module state _POP: inherited by forked workers, not pickled)."""
+    P = _POP
+    _, b, _ = simulate(contigs=P["contigs"], depth=P["depth"], read_len=P["read_len"], seeds=(P["seeds"][0], P["seeds"][1], P["seeds"][2] + smp),
+                       paired=False, genome=P["genome"], variants_override=P["ovs"][smp], tag_sites=P["tags"], n_read_groups=1, **P["kw"])
+    rng_s = np.random.default_rng(P["seeds"][2] + 7919 * (smp + 1))
+    rg = (smp * P["rgs_per_sample"] + rng_s.integers(0, P["rgs_per_sample"], size=b.n)).astype(np.int16)
+    if P["no_rg_frac"] > 0:
+        rg[rng_s.random(b.n) < P["no_rg_frac"]] = -1
+    b.rg = rg
+    return b
+
+
 def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: str = "wgs", n_tags: int = 200,
                         seeds=(1021, 2022, 3023), read_len: int = 100, rgs_per_sample: int = 1, no_rg_frac: float = 0.0,
-                        snv_rate: float = 1e-3, indel_rate: float = 1e-4, multi_allelic_frac: float = 0.1, **kw):
+                        snv_rate: float = 1e-3, indel_rate: float = 1e-4, multi_allelic_frac: float = 0.1, workers: int = 1, n_tags_total: int | None = None, **kw):
     """Population workload for MultisampleVariantsDetector (BASELINE configs[3]): shared planted sites, per-sample
     genotypes drawn from a population allele frequency ~ Beta(0.2, 0.2); mode "wgs" = uniform single-end reads at `depth`
     per sample, "gbs" = `n_tags` tag loci per contig with Poisson(depth) identical-start reads per sample and tag.
@@ -413,9 +429,12 @@ def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: 
                 others = [int(x) for x in _ACGT if x != r and x != v.alt[0]]
                 v._alt2 = bytes([others[int(rng_v.integers(0, 2))]])
         if mode == "gbs":
-            st = np.sort(rng_v.integers(1, max(2, length - read_len - 20), size=n_tags)).astype(np.int64)
-            tags[name] = (st, rng_v.random(n_tags) < 0.5)
-    batches = []
+            nt = n_tags if n_tags_total is None else max(1, int(round(n_tags_total * length / sum(l for _, l in contigs))))   # tags in proportion to the sequence length
+            st = np.sort(rng_v.integers(1, max(2, length - read_len - 20), size=nt)).astype(np.int64)
+            tags[name] = (st, rng_v.random(nt) < 0.5)
+    # per-sample genotypes first (one sequential stream of draws), then the samples' reads — independent given their own
+    # seeds, so `workers` > 1 simulates them in forked processes with the same result
+    ovs = []
     for smp in range(n_samples):
         ov = {}
         for name, _ in contigs:
@@ -439,14 +458,16 @@ def simulate_population(contigs, n_samples: int = 8, depth: float = 10.0, mode: 
                 w._hap = 0 if a0 else 1
                 vs.append(w)
             ov[name] = vs
-        _, b, _ = simulate(contigs=contigs, depth=depth, read_len=read_len, seeds=(seeds[0], seeds[1], seeds[2] + smp), paired=False,
-                           genome=genome, variants_override=ov, tag_sites=tags if mode == "gbs" else None, n_read_groups=1, **kw)
-        rng_s = np.random.default_rng(seeds[2] + 7919 * (smp + 1))
-        rg = (smp * rgs_per_sample + rng_s.integers(0, rgs_per_sample, size=b.n)).astype(np.int16)
-        if no_rg_frac > 0:
-            rg[rng_s.random(b.n) < no_rg_frac] = -1
-        b.rg = rg
-        batches.append(b)
+        ovs.append(ov)
+    _POP.update(contigs=contigs, depth=depth, read_len=read_len, seeds=seeds, genome=genome, ovs=ovs, tags=tags if mode == "gbs" else None,
+                rgs_per_sample=rgs_per_sample, no_rg_frac=no_rg_frac, kw=kw)
+    if workers > 1 and n_samples > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, n_samples)) as pool:
+            batches = pool.map(_population_sample, range(n_samples), chunksize=1)
+    else:
+        batches = [_population_sample(smp) for smp in range(n_samples)]
+    _POP.clear()
     names = [c[0] for c in contigs]
     lens = [c[1] for c in contigs]
     seq_idx = np.concatenate([b.seq_idx for b in batches])

@@ -118,3 +118,51 @@ def parse_vcf(text):
         out.append(dict(chrom=t[0], pos=int(t[1]), ref=t[3], alt=t[4], qual=int(t[5]), info=t[7], fmt=t[8], gt=s[0], pl=s[1],
                         gq=int(s[2]), dp=int(s[3]), cnt=s[4], acn=s[5], line=line))
     return out
+
+
+# ---- the oracle over a whole workload, one process per sequence / region (the reference's only parallel mode: -querySeq) ----
+_PC = {}
+
+
+def _per_contig_job(job):
+    """Worker (forked: the batch is inherited, not pickled): SAM text of one region's records -> oracle -> (body lines, genotyped positions)."""
+    import tempfile
+
+    from ngsepcore_b200 import simulate
+    ci, first, last, multi, args = job
+    batch, fa, names = _PC["batch"], _PC["fa"], _PC["names"]
+    lo, hi = np.searchsorted(batch.seq_idx, ci, "left"), np.searchsorted(batch.seq_idx, ci, "right")
+    f = batch.first[lo:hi]
+    keep = lo + np.nonzero((f >= first - 2000) & (f <= last))[0]     # lead-in: every record that can reach `first`
+    with tempfile.TemporaryDirectory() as d:
+        sam = os.path.join(d, "r.sam")
+        simulate.write_sam(sam, batch.select(keep))
+        q = tuple(args) + ("-querySeq", names[ci], "-first", str(first), "-last", str(last))
+        lib = load_oracle()
+        if multi:
+            text, _, gp, sec = run_msvd(lib, fa, [sam], args=q)
+        else:
+            text, _, gp, sec = run_ssvd(lib, fa, sam, args=q)
+    return [l for l in text.splitlines() if not l.startswith("#")], gp, sec
+
+
+def run_regions(genome, batch, fa, regions=None, args=(), multi=False, workers=None, piece=400000):
+    """The oracle over `regions` [(contig index, first, last)] (default: every sequence of the batch, cut into pieces of
+    `piece` positions), one forked process per piece; returns (body lines in genome order, genotyped positions, cpu seconds).
+    A query window is exactly how the reference itself is run in parallel (APG:310-322): a piece sees every record that can reach it."""
+    import multiprocessing as mp
+    names = list(batch.contig_names)
+    if regions is None:
+        regions = []
+        for ci, length in enumerate(batch.contig_lengths):
+            for f in range(1, length + 1, piece):
+                regions.append((ci, f, min(length, f + piece - 1)))
+    _PC.update(batch=batch, fa=fa, names=names)
+    workers = workers or max(1, min(len(regions), os.cpu_count() or 1))
+    with mp.get_context("fork").Pool(workers) as pool:
+        res = pool.map(_per_contig_job, [(ci, f, l, multi, tuple(args)) for ci, f, l in regions], chunksize=1)
+    _PC.clear()
+    body, gp, sec = [], 0, 0.0
+    for lines, g, s in res:
+        body += lines; gp += g; sec += s
+    return body, gp, sec

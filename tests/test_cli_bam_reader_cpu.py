@@ -110,3 +110,69 @@ def test_cli_host_only_records_match_oracle_on_mutated_sam(oracle, tmp_path):
         got_lines = [l for l in open(prefix + ".vcf").read().splitlines() if not l.startswith("#")]
         assert len(want_lines) > 40
         assert got_lines == want_lines
+
+
+def test_bam_reader_survives_corrupted_lengths(tmp_path):
+    """every length field of a BAM record (block size, l_read_name, n_cigar_op, l_seq, B-array counts, unterminated Z
+    strings) and of a BGZF block (XLEN, BSIZE) is checked against the bytes that are really there.  Corrupted files must end with
+    the CLI's clean error (exit code 2) or decode — never crash (a negative return code = a signal) or allocate gigabytes."""
+    import struct
+    import zlib
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 8000)], depth=10, seeds=(171, 172, 173), indel_rate=2e-3, n_read_groups=2)
+    fa, sam, bam = (str(tmp_path / n) for n in ("r.fa", "p.sam", "p.bam"))
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    # a tag of every shape on the first records
+    lines = open(sam).readlines()
+    k = next(i for i, l in enumerate(lines) if not l.startswith("@"))
+    lines[k] = lines[k].rstrip("\n") + "\tNH:i:1\tXZ:Z:some text\n"
+    open(sam, "w").writelines(lines)
+    bam_util.sam_to_bam(sam, bam)
+    raw = open(bam, "rb").read()
+    # the decompressed stream
+    stream, p = bytearray(), 0
+    while p < len(raw):
+        bsize = struct.unpack_from("<H", raw, p + 16)[0] + 1
+        stream += zlib.decompress(raw[p + 18:p + bsize - 8], -15)
+        p += bsize
+    l_text = struct.unpack_from("<i", stream, 4)[0]
+    first_rec = 8 + l_text + 4 + 4 + len("chrA") + 1 + 4
+    rng = np.random.default_rng(9)
+
+    def run(data: bytes, name: str) -> int:
+        path = str(tmp_path / name)
+        with open(path, "wb") as o:
+            for i in range(0, len(data), 60000):
+                o.write(bam_util._bgzf_block(bytes(data[i:i + 60000])))
+            o.write(bam_util._bgzf_block(b""))
+        return subprocess.call([CLI, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", str(tmp_path / "o"), "--host-only"],
+                               stderr=subprocess.DEVNULL, timeout=60)
+
+    assert run(bytes(stream), "clean.bam") == 0
+    targeted = {"block_size": (first_rec, 4), "l_read_name": (first_rec + 4 + 8, 1), "n_cigar_op": (first_rec + 4 + 12, 2), "l_seq": (first_rec + 4 + 16, 4),
+                "l_text": (4, 4), "n_ref": (8 + l_text, 4), "l_name": (8 + l_text + 4, 4)}
+    for name, (off, width) in targeted.items():
+        for val in (0xFFFFFFFF, 0x7FFFFFFF, 0x00FFFFFF, 1, 0):
+            s = bytearray(stream)
+            s[off:off + width] = struct.pack("<I", val)[:width]
+            rc = run(bytes(s), f"{name}_{val:x}.bam")
+            assert rc in (0, 2), (name, hex(val), rc)
+    for it in range(40):       # random corruption of the first records (fixed part, CIGAR, tags) and truncation
+        s = bytearray(stream)
+        for _ in range(int(rng.integers(1, 6))):
+            s[int(rng.integers(first_rec, min(len(s), first_rec + 4000)))] = int(rng.integers(0, 256))
+        if it % 4 == 0:
+            s = s[:int(rng.integers(first_rec, len(s)))]
+        rc = run(bytes(s), f"rand_{it}.bam")
+        assert rc in (0, 2), (it, rc)
+    # BGZF level: XLEN / BSIZE that point outside the file, a block cut in the middle
+    for off, val in ((10, 0xFFFF), (16, 0xFFFF), (16, 3), (10, 0)):
+        b = bytearray(raw)
+        struct.pack_into("<H", b, off, val)
+        path = str(tmp_path / f"bgzf_{off}_{val}.bam")
+        open(path, "wb").write(bytes(b))
+        rc = subprocess.call([CLI, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", str(tmp_path / "o"), "--host-only"], stderr=subprocess.DEVNULL, timeout=60)
+        assert rc in (0, 2), (off, val, rc)
+    open(str(tmp_path / "cut.bam"), "wb").write(raw[:len(raw) // 2])
+    assert subprocess.call([CLI, "SingleSampleVariantsDetector", "-i", str(tmp_path / "cut.bam"), "-r", fa, "-o", str(tmp_path / "o"), "--host-only"],
+                           stderr=subprocess.DEVNULL, timeout=60) in (0, 2)

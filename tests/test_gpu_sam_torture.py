@@ -109,3 +109,39 @@ def test_mutated_records_multisample(oracle, tmp_path):
         subprocess.check_call([CLI, "MultisampleVariantsDetector", "-r", fa, "-o", out] + list(opts) + [sam], stderr=subprocess.DEVNULL)
         assert len([l for l in want.splitlines() if not l.startswith("#")]) > 80
         assert open(out).read() == want
+
+
+def test_reference_skip_longer_than_65535(oracle, tmp_path):
+    """A spliced record whose reference span exceeds 65 535 bp (60M70000N40M): the window index packs the tile's largest span
+    into 16 bits, so such a tile must hand its open columns over WITHOUT a record range and let the genotype kernel search
+    with the full span (a capped span silently dropped the record from the columns of its far part).  The far
+    40 bases of these records change DP / BSDP of the records called there, for one and for several samples."""
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 160000)], depth=15, seeds=(151, 152, 153), indel_rate=0.0, snv_rate=5e-3)
+    fa, sam0, sam = str(tmp_path / "r.fa"), str(tmp_path / "plain.sam"), str(tmp_path / "spliced.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam0, batch)
+    rng = np.random.default_rng(5)
+    ref = genome["chrA"].tobytes().decode()
+    out, n_spliced = [], 0
+    for line in open(sam0):
+        if not line.startswith("@"):
+            f = line.split("\t")
+            pos = int(f[3])
+            if f[5] == "100M" and pos < 80000 and rng.random() < 0.02:
+                far = pos + 60 + 70000 - 1                    # 0-based index of the first base after the skip
+                tail = list(ref[far:far + 40].upper())
+                for k in rng.integers(0, 40, size=2):          # two bases of the tail differ from the reference there
+                    tail[k] = "ACGT"[("ACGT".index(tail[k]) + 1) % 4] if tail[k] in "ACGT" else "A"
+                f[5] = "60M70000N40M"
+                f[9] = f[9][:60] + "".join(tail)
+                line = "\t".join(f)
+                n_spliced += 1
+        out.append(line)
+    open(sam, "w").writelines(out)
+    assert n_spliced > 100
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam)
+    res = str(tmp_path / "out")
+    subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", res], stderr=subprocess.DEVNULL)
+    body = [l for l in want.splitlines() if not l.startswith("#")]
+    assert sum(1 for l in body if 70000 < int(l.split("\t")[1]) < 150100) > 100
+    assert open(res + ".vcf").read() == want
