@@ -50,7 +50,9 @@ def _peaks():
 
 def _ncu_traffic():
     """DRAM bytes of one k_pileup_windows launch over this workload, from the committed ncu capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_pileup_windows.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_pileup_windows.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_ncu_pileup_windows.json")
     try:
         d = json.load(open(p))
         unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
@@ -191,15 +193,15 @@ def run_gpu(args):
     aligned_bases = sum(t["aligned_bases"] for t in tiles)
     genome_len = sum(len(v) for v in genome.values())
 
-    # one GPU per host: the phred bytes stay in the page-locked host buffers and are read in place (NGSEP_F_QUALITY_IN_PLACE);
-    # several GPUs reading host memory at once are better served by the bulk copy (measured: profiles/README.md)
-    ctx = capi.Context(device=device, flags=capi.F_QUALITY_IN_PLACE if world == 1 else 0)
+    # the same mode at every N: every host buffer of a tile is copied (qualities travel as 2-bit codes when the tile's
+    # qualities allow it, ngsep_tile.qual_bits); --quality-in-place leaves page-locked quality buffers on the host instead
+    ctx = capi.Context(device=device, flags=capi.F_QUALITY_IN_PLACE if args.quality_in_place else 0)
     for ci, n in enumerate(names):
         ctx.ref_upload(ci, genome[n])
     slots = []
     for ci, t in enumerate(tiles):
         if t["hdr"].size:
-            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"]))
+            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"]))
 
     def barrier():
         if dist is not None:
@@ -236,7 +238,7 @@ def run_gpu(args):
             if pending == IN_FLIGHT:
                 c, _, st = ctx.fetch(sort=False)
                 n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
-            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"])
+            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"])
             pending += 1
         while pending:
             c, _, st = ctx.fetch(sort=False)
@@ -266,8 +268,10 @@ def run_gpu(args):
         st2 = det2.stats()
         pipeline = {"value": (st2.covered_positions - w0[0]) / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s - w0[1],
                     "pack_s": st2.pack_s - w0[2], "device_s": st2.device_s - w0[3], "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
-                    "note": "whole detector from decoded records (second run of the detector object): admission + realigner pre-pass on one "
-                            "host thread, tile packing on up to 8, device, VCF text"}
+                    "host_threads": min(32, os.cpu_count() or 1),
+                    "note": "whole detector from decoded records (second run of the detector object): admission + realigner pre-pass of all "
+                            "sequences in parallel on the host threads (prepass_s = wall time of that stage), tiles packed into page-locked ring "
+                            "buffers with up to three tiles in flight (pack_s, device_s = host time spent packing / blocked in submit + fetch), VCF text"}
 
     (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
         dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
@@ -275,8 +279,15 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = _peaks()
         alg_bytes = _algorithmic_bytes(batch, [t["hdr"] for t in tiles], genome_len, calls)
+        quality_bytes_alg = sum(int((t["hdr"]["meta"] & 0xFFFF).astype(np.int64).sum()) for t in tiles)
         ms_per_step = total_ms / args.steps
-        achieved = alg_bytes * args.steps / (pileup_ms / 1e3) / 1e9
+        # achieved = algorithmic bytes of the path / device-resident time of the path = BOTH kernels of the step
+        step_kernels_s = kernels_ms / args.steps / 1e3
+        achieved = alg_bytes / step_kernels_s / 1e9
+        win_s = pileup_ms / args.steps / 1e3
+        # what each kernel reads of the canonical input: the window kernel headers + CIGAR + 2-bit bases + reference, the genotype
+        # kernel the quality bytes and the call records
+        own_win = alg_bytes - quality_bytes_alg - 64 * calls
         traffic = _ncu_traffic() if (args.scale == 1.0 and args.depth == 30.0) else None
         line = {
             "metric": METRIC, "value": covered_all / (ms_per_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -288,19 +299,26 @@ def run_gpu(args):
                        "parallelism": f"region shards x{world}, no collective"},
             "aligned_bases_per_sec": bases_all / (ms_per_step / 1e3),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "frac_of_traffic": (traffic / (pileup_ms / args.steps / 1e3) / 1e9 / peak) if traffic else None,
-                         "traffic_note": "ncu dram__bytes_read+write of one launch on this workload (profiles/r01_ncu_pileup_windows.json); below the "
-                                         "algorithmic bytes because quality bytes are only read for the columns that reach k_genotype_columns",
-                         "kernel": "k_pileup_windows", "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": pileup_ms / args.steps,
-                         "launches_per_step": 1, "both_kernels_ms_per_step": kernels_ms / args.steps, "peak_source": peak_src},
+                         "traffic": traffic,
+                         "kernel": "the device step: k_pileup_windows + k_genotype_columns (one launch each)", "algorithmic_bytes_per_step": alg_bytes,
+                         "kernels_ms_per_step": kernels_ms / args.steps, "launches_per_step": 2,
+                         "k_pileup_windows": {"ms_per_step": pileup_ms / args.steps, "share_of_step": pileup_ms / kernels_ms,
+                                              "own_algorithmic_bytes": own_win, "own_frac": own_win / win_s / 1e9 / peak,
+                                              "frac_of_traffic": (traffic / win_s / 1e9 / peak) if traffic else None},
+                         "k_genotype_columns": {"ms_per_step": (kernels_ms - pileup_ms) / args.steps, "share_of_step": 1.0 - pileup_ms / kernels_ms},
+                         "traffic_note": "ncu dram__bytes_read+write of one k_pileup_windows launch on this workload (committed capture under profiles/); "
+                                         "quality bytes are only read for the columns that reach k_genotype_columns",
+                         "peak_source": peak_src},
             "e2e": {"value": covered_all * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
                     "d2h_bytes_per_step": int(calls_all * 224 + 36 * len(slots) * world), "ms_per_step": e2e_s / args.steps * 1e3,
                     "host_input_bytes_per_step": int(h2d_bytes * world), "same_calls_as_resident_run": bool(n_calls_e2e == calls),
                     "quality_in_place_tiles": int(e2e_in_place),
-                    "note": "h2d_bytes_per_step = bytes ngsep_tile_submit copies (record headers + payload); the phred bytes (%.0f MB) stay in the "
-                            "caller's page-locked buffers and k_genotype_columns reads the ~%d x depth bytes it needs in place over PCIe "
-                            "(NGSEP_F_QUALITY_IN_PLACE, set by this bench at N = 1 only)" % ((h2d_bytes - e2e_copied) / 1e6, int(st.open_columns)) if e2e_in_place else
-                            "every host buffer of the step is copied host -> device"},
+                    "quality_bits": sorted({int(t["quality"][0]) for t in tiles}),
+                    "note": "h2d_bytes_per_step = bytes ngsep_tile_submit copies (record headers + payload); the quality array (%.0f MB) stays in the "
+                            "caller's page-locked buffers and k_genotype_columns reads what it needs in place over PCIe "
+                            "(--quality-in-place)" % ((h2d_bytes - e2e_copied) / 1e6) if e2e_in_place else
+                            "every host buffer of the step is copied host -> device, the same mode at every N; qualities travel as "
+                            "quality_bits-bit codes (ngsep_tile.qual_bits: the simulated qualities fall into 4 classes the path can tell apart)"},
             "pipeline": pipeline,
             "gpu_launches": int(launches_all * args.steps),
             "clocks": clocks,
@@ -410,6 +428,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="scale the sequence lengths (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the informational whole-detector run")
+    ap.add_argument("--quality-in-place", action="store_true", help="e2e: leave page-locked quality buffers on the host (NGSEP_F_QUALITY_IN_PLACE)")
     ap.add_argument("--reference-sample-bp", type=int, default=4_000_000)
     args = ap.parse_args()
     if args.impl == "reference":

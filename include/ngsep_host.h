@@ -53,9 +53,11 @@ typedef struct ngsep_detector_options {
     int32_t call_embedded_snvs;     /* -embeddedSNVs                */
     int32_t calc_strand_bias;       /* -csb                         */
     int32_t device;                 /* CUDA device index            */
-    int32_t tile_len;               /* 0 = one tile per sequence    */
+    int32_t tile_len;               /* region tiles of this many positions; 0 = automatic (2 Mb: shorter sequences are one tile) */
     int32_t shard, n_shards;        /* region sharding across ranks: tile t belongs to rank t % n_shards */
     int32_t host_only;              /* test hook: admission + event pre-pass only; output holds just the host-made indel/STR records */
+    int32_t synchronous;            /* test hook: one tile at a time from pageable buffers, host stages on the calling thread (default: sequences planned
+                                       in parallel, tiles pipelined through page-locked ring buffers) */
 } ngsep_detector_options;
 
 typedef struct ngsep_run_stats {
@@ -97,6 +99,9 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
 int ngsep_ssvd_pack(void* det, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads,
                     uint64_t* n_words, uint64_t* n_qual, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases);
 void ngsep_host_free(void* p);
+/* How the quality array of the tile the calling thread packed last (ngsep_host_pack / ngsep_ssvd_pack) is coded: the values for
+ * ngsep_tile.qual_bits and ngsep_tile.qual_dict. */
+int ngsep_host_pack_quality(uint32_t* qual_bits, uint8_t* qual_dict16);
 
 #ifdef __cplusplus
 }

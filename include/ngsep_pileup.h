@@ -106,6 +106,14 @@ typedef struct ngsep_tile {
                                       that belongs to a sample); NULL when n_samples == 1                          */
     const uint8_t* qual;           /* [n_qual] phred+33 quality bytes, addressed through each record's qoff        */
     uint64_t n_qual;               /* bytes in qual (a multiple of 4)                                              */
+    uint32_t qual_bits;            /* 0 or 8: qual holds the phred+33 bytes themselves.  2 or 4: qual holds CODES of that many
+                                      bits — code k of a read at bits [k*qual_bits, (k+1)*qual_bits) of the read's run (little
+                                      endian, runs padded to 4 bytes, qoff = start of the run in 4-byte units) — and qual_dict
+                                      maps a code to a phred+33 byte.  The path only distinguishes min(30, q) with every q <= 3
+                                      alike (CountsHelper.java:91,214-219), so a tile whose qualities fall into at most 4 / 16 such
+                                      classes (binned Illumina qualities do) travels at 2 / 4 bits per base with identical results */
+    uint8_t qual_dict[16];
+    uint32_t reserved;
 } ngsep_tile;
 
 /* One SNV-path decision for one position.  Field semantics follow VariantDiscoverySNVQAlgorithm.discoverSNV
@@ -235,7 +243,7 @@ int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
-int ngsep_abi_version(void);   /* 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
+int ngsep_abi_version(void);   /* 2002: + ngsep_tile.qual_bits / qual_dict; 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
 int ngsep_built_sm(void);
 
 #ifdef __cplusplus

@@ -31,7 +31,8 @@ class Params(C.Structure):
 class Tile(C.Structure):
     _fields_ = [("seq_idx", C.c_int32), ("tile_first", C.c_int32), ("tile_last", C.c_int32), ("n_reads", C.c_int32),
                 ("max_span", C.c_int32), ("max_back", C.c_int32), ("n_words", C.c_uint64), ("hdr", C.c_void_p),
-                ("payload", C.c_void_p), ("group", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64)]
+                ("payload", C.c_void_p), ("group", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64),
+                ("qual_bits", C.c_uint32), ("qual_dict", C.c_uint8 * 16), ("reserved", C.c_uint32)]
 
 
 class TileStats(C.Structure):
@@ -143,16 +144,18 @@ class Context:
         b = np.ascontiguousarray(bases, np.uint8)
         self._check(self.lib.ngsep_ref_upload(self.h, seq_idx, b.ctypes.data, b.size), "ngsep_ref_upload")
 
-    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group=None) -> Tile:
+    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group=None, quality=None) -> Tile:
+        """quality: None = `qual` holds phred+33 bytes; (bits, dict16) = 2- / 4-bit codes (ngsep_tile.qual_bits / qual_dict)."""
         hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
         payload = np.ascontiguousarray(payload, np.uint32)
         qual = np.ascontiguousarray(qual, np.uint8)
         group = None if group is None else np.ascontiguousarray(group, np.uint16)
         self._keep = (getattr(self, "_keep", []) + [hdr, payload, qual, group])[-16:]   # buffers of the tiles still in flight
+        bits, qdict = (0, bytes(16)) if quality is None else (int(quality[0]), bytes(quality[1]))
         return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
                     hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None,
                     group.ctypes.data if group is not None and group.size else None,
-                    qual.ctypes.data if qual.size else None, qual.size)
+                    qual.ctypes.data if qual.size else None, qual.size, bits, (C.c_uint8 * 16)(*qdict), 0)
 
     def samples_set(self, sample_groups, n_groups: int, min_allele_depth_freq: float = 0.0) -> None:
         """sample_groups: per sample, the read-group ids in the order PR.getAlleleCalls(span, Set) visits them."""
@@ -186,14 +189,14 @@ class Context:
         o = np.argsort(sites["pos"][: n.value], kind="stable")
         return sites[: n.value][o], calls[: n.value][o], counts, stats
 
-    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> None:
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group)
+    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality)
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
         self._inflight_npos.append(tile_last - tile_first + 1)
 
-    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None) -> int:
+    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None) -> int:
         """Stages a tile in HBM for repeated runs; returns its slot."""
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group)
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality)
         slot = C.c_int(0)
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1
@@ -226,7 +229,9 @@ class Context:
         n_pos = (self._inflight_npos[0] if self._inflight_npos else 0) if slot == 0 else self._slot_npos[slot]
         counts = np.zeros((n_pos, 5), np.int32) if want_counts else None
         while True:
-            out = np.zeros(cap, CALL_DTYPE)
+            if getattr(self, "_call_buf", None) is None or self._call_buf.shape[0] < cap:
+                self._call_buf = np.zeros(cap, CALL_DTYPE)      # reused from fetch to fetch: the caller gets a copy of the n records
+            out = self._call_buf
             n = C.c_size_t(0)
             rc = self.lib.ngsep_resident_fetch(self.h, slot, out.ctypes.data, cap, C.byref(n), counts.ctypes.data if want_counts else None, C.byref(stats))
             if rc == -6 and n.value > cap:
@@ -237,7 +242,7 @@ class Context:
                     self._inflight_npos.pop(0)      # the tile left the queue, whether the fetch succeeded or not
             self._check(rc, "ngsep_tile_fetch")
             break
-        calls = out[: n.value]
+        calls = out[: n.value].copy()
         if sort:
             calls = calls[np.argsort(calls["pos"], kind="stable")]
         return calls, counts, stats

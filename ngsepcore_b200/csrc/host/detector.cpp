@@ -4,11 +4,17 @@
 //   2. event pre-pass       indel realigner + span>1 calls at the sparse event positions  host, O(events x depth)
 //   3. pack + ngsep_tile_submit / ngsep_tile_fetch per region tile                        device: every position
 //   4. ordered merge        embedded / indel suppression (SSVPL:150-160), sort, VCF text  host, O(calls)
+// Sequences are independent (every listener is reset at onSequenceStart): stages 1-2 of all sequences run in parallel on
+// the host threads, stage 3 streams the tiles of all sequences through page-locked ring buffers with up to three tiles in
+// flight (the next tile is packed while the device works on the previous ones), stage 4 runs in parallel again.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <climits>
+#include <deque>
 #include <queue>
 #include <set>
+#include <thread>
 
 #include "pipeline.hpp"
 
@@ -48,6 +54,21 @@ int GpuSingleSampleVariantsDetector::ensure_ctx() {
     return rc;
 }
 
+namespace {
+// f(k) for k in [0, n) on up to `threads` host threads, longest jobs first (`weight`), each k exactly once
+template <typename F>
+void parallel_jobs(size_t n, int threads, const std::vector<size_t>& order, F&& f) {
+    if (threads <= 1 || n <= 1) { for (size_t k = 0; k < n; k++) f(order[k]); return; }
+    std::atomic<size_t> next{0};
+    auto work = [&]() { for (;;) { const size_t k = next.fetch_add(1); if (k >= n) return; f(order[k]); } };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>((size_t)threads, n);
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
 int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, bool with_header) {
     double t0 = now_s();
     if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
@@ -55,6 +76,8 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     if (rc != NGSEP_OK) return rc;
     if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
+    // ---- the sequences of the batch, in file order (APG:310-322 for a query sequence) ------------------------------------
+    std::vector<SeqJob> jobs;
     bool query_found = false;
     int64_t i = 0;
     while (i < b.n) {
@@ -62,19 +85,116 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         int64_t j = i;
         while (j < b.n && b.seq_idx[j] == seq) j++;
         bool take = true;
-        if (opt_.has_query) {  // APG:310-322
+        if (opt_.has_query) {
             bool is_q = seq >= 0 && seq < (int)genome_->names.size() && genome_->names[seq] == opt_.query_seq;
             if (is_q) query_found = true;
             else if (query_found) break;
             take = is_q;
         }
-        if (take && seq >= 0 && seq < (int)genome_->seqs.size()) {
-            rc = run_sequence(b, seq, i, j, out);
-            if (rc != NGSEP_OK) return rc;
-        }
+        if (take && seq >= 0 && seq < (int)genome_->seqs.size()) { jobs.emplace_back(); jobs.back().seq = seq; jobs.back().lo = i; jobs.back().hi = j; }
         i = j;
     }
+    const int threads = opt_.synchronous ? 1 : host_threads();
+    std::vector<size_t> order(jobs.size());
+    for (size_t k = 0; k < order.size(); k++) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].hi - jobs[x].lo > jobs[y].hi - jobs[y].lo; });
+    // ---- stages 1-2: admission + event pre-pass, every sequence on its own host thread ------------------------------------
+    double tp = now_s();
+    parallel_jobs(jobs.size(), threads, order, [&](size_t k) { jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan); });
+    stats_.prepass_s += now_s() - tp;
+    for (auto& job : jobs) {
+        if (job.rc != NGSEP_OK) { err_ = job.plan.err; return job.rc; }
+        stats_.add_host(job.plan.stats);
+    }
+    // ---- stage 3: the device -------------------------------------------------------------------------------------------
+    if (!opt_.host_only) {
+        rc = run_device(jobs);
+        if (rc != NGSEP_OK) return rc;
+    }
+    // ---- stage 4: ordered merge + text, per sequence ------------------------------------------------------------------------
+    parallel_jobs(jobs.size(), threads, order, [&](size_t k) { if (!jobs[k].plan.reads.empty()) emit_text(jobs[k]); });
+    size_t bytes = 0;
+    for (auto& job : jobs) bytes += job.text.size();
+    out.reserve(out.size() + bytes);
+    for (auto& job : jobs) { out += job.text; stats_.snv_calls += job.snv_records; }
+    {   // the plans hold millions of small allocations: release them on the host threads as well
+        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { SeqPlan().reads.swap(jobs[k].plan.reads); });
+    }
     stats_.total_s += now_s() - t0;
+    return NGSEP_OK;
+}
+
+// Stage 3.  Tiles of all sequences, in order, through the ring of page-locked host buffers: pack tile k (host threads) while
+// the device still works on tiles k-1, k-2, k-3 (ngsep_tile_submit only enqueues copies and kernels).
+int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
+    struct InFlight { SeqJob* job; };
+    std::deque<InFlight> q;
+    const int max_in_flight = opt_.synchronous ? 1 : kHostRing - 1;
+    int slot = 0;
+    auto fetch_oldest = [&]() -> int {
+        double td = now_s();
+        ngsep_tile_stats ts{};
+        int rc = fetch_tile(*q.front().job, ts);
+        q.pop_front();
+        if (rc != NGSEP_OK) return rc;
+        stats_.device_s += now_s() - td;
+        stats_.covered_positions += ts.covered_positions;
+        stats_.candidate_positions += ts.candidate_positions;
+        stats_.aligned_bases += ts.aligned_bases;
+        stats_.kernel_ms += ts.kernel_ms;
+        stats_.kernel_launches += ts.kernel_launches;
+        stats_.tiles++;
+        return NGSEP_OK;
+    };
+    auto drain = [&]() { while (!q.empty()) { ngsep_tile_stats ts{}; fetch_tile(*q.front().job, ts); q.pop_front(); } };   // after an error: nothing may stay in flight
+    for (auto& job : jobs) {
+        SeqPlan& plan = job.plan;
+        if (plan.reads.empty()) continue;
+        const int seq = job.seq;
+        if (!ref_uploaded_[seq]) {
+            int rc = ngsep_ref_upload(ctx_, seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
+            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); drain(); return rc; }
+            ref_uploaded_[seq] = true;
+        }
+        const int64_t tlen = tile_len();
+        int tile_no = 0;
+        for (int64_t tf = plan.win_first; tf <= plan.win_last; tf += tlen, tile_no++) {
+            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
+            const int tl = (int)std::min<int64_t>(plan.win_last, tf + tlen - 1);
+            size_t r_lo, r_hi;   // records whose ordering start can reach the tile
+            tile_records(plan, (int)tf, tl, r_lo, r_hi);
+            if (r_lo >= r_hi) continue;
+            while ((int)q.size() >= max_in_flight) { int rc = fetch_oldest(); if (rc != NGSEP_OK) { drain(); return rc; } }
+            PackedTile& tile = ring_[slot];
+            tile.set_pinned(!opt_.synchronous);
+            double tp = now_s();
+            if (!pack_reads(plan.reads, r_lo, r_hi, tile, with_groups(), &err_)) { drain(); return NGSEP_EINVAL; }
+            stats_.pack_s += now_s() - tp;
+            if (tile.hdr.empty()) continue;
+            double td = now_s();
+            ngsep_tile tv = tile.view(seq, (int)tf, tl);
+            int rc = ngsep_tile_submit(ctx_, &tv);
+            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); drain(); return rc; }
+            stats_.device_s += now_s() - td;
+            q.push_back({&job});
+            slot = (slot + 1) % kHostRing;
+        }
+    }
+    while (!q.empty()) { int rc = fetch_oldest(); if (rc != NGSEP_OK) { drain(); return rc; } }
+    return NGSEP_OK;
+}
+
+int GpuSingleSampleVariantsDetector::fetch_tile(SeqJob& job, ngsep_tile_stats& ts) {
+    // into a buffer that lives as long as the detector (no fresh pages per tile), then only the tile's calls move to the job
+    size_t n = 0;
+    if (call_buf_.size() < 65536) call_buf_.resize(65536);
+    int rc = ngsep_tile_fetch(ctx_, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
+    if (rc == NGSEP_EOVERFLOW && n > call_buf_.size()) {
+        call_buf_.resize(n + n / 4 + 16);
+        rc = ngsep_tile_fetch(ctx_, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
+    }
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+    job.snvs.insert(job.snvs.end(), call_buf_.begin(), call_buf_.begin() + (ptrdiff_t)n);
     return NGSEP_OK;
 }
 
@@ -93,8 +213,8 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     }
     if (opt_.has_query) ao.query_first = opt_.query_first;
     reads = admit_sequence(b, q_lo, q_hi, ao);
-    for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { err_ = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
-    stats_.admitted += reads.size();
+    for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { plan.err = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
+    plan.stats.admitted += reads.size();
     if (reads.empty()) { plan.win_first = 1; plan.win_last = seq_len; return NGSEP_OK; }
     const int win_first = plan.win_first = opt_.has_query ? std::max(1, opt_.query_first) : 1;
     const int win_last = plan.win_last = opt_.has_query ? std::min(seq_len, opt_.query_last) : seq_len;
@@ -133,7 +253,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             for (HostRead* r : pileup) before.push_back(r->st);
             EventOutcome ev = realigner.on_event(e, pileup);
             if (!ev.fired) continue;
-            stats_.events++;
+            plan.stats.events++;
             for (size_t k = 0; k < pileup.size(); k++) {
                 HostRead* r = pileup[k];
                 if (!r->derived) r->derive();
@@ -141,7 +261,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
                 if (r->cur_from == e) continue;  // cannot happen (one event per position); keeps windows well formed
                 r->closed.push_back(Version{r->cur_from, e, before[k]});
                 r->cur_from = e;
-                stats_.versions++;
+                plan.stats.versions++;
                 for (auto& a : r->anchors) if (a.pos > e) heap.push(a.pos);
             }
             // ---- SingleSampleVariantPileupListener.onPileup at the event (SSVPL:146-161) ----
@@ -154,7 +274,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             on_span_event(e, upper(ref), ev, pileup, plan, last_indel_end);
         }
     }
-    stats_.prepass_s += now_s() - t0;
+    plan.stats.prepass_s += now_s() - t0;
     // reach of every read over all of its versions, to pick the records of a tile (halo = read span)
     plan.max_reach = 1;
     plan.max_back = 0;
@@ -177,7 +297,7 @@ void GpuSingleSampleVariantsDetector::on_span_event(int e, const std::string& re
         last_indel_end = rec.last;                 // SSVPL:157-158
         if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
         plan.indels.push_back(std::move(rec));
-        stats_.indel_calls++;
+        plan.stats.indel_calls++;
     }
 }
 
@@ -187,65 +307,17 @@ void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, 
     r_hi = std::upper_bound(reads.begin(), reads.end(), tl + plan.max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
 }
 
-int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) {
-    const std::string& chrom = genome_->names[seq];
-    SeqPlan plan;
-    int prc = plan_sequence(b, seq, lo, hi, plan);
-    if (prc != NGSEP_OK) return prc;
-    if (plan.reads.empty()) return NGSEP_OK;
-    std::vector<HostRead>& reads = plan.reads;
-    std::vector<IndelRecord>& indels = plan.indels;
-    std::set<int>& suppressed = plan.suppressed;
-    std::vector<std::pair<int, int>>& embedded = plan.embedded;
-    const int win_first = plan.win_first, win_last = plan.win_last;
-
-    // ---- 3. device: region tiles ------------------------------------------------------------------------------------
-    if (!opt_.host_only && !ref_uploaded_[seq]) {
-        int rc = ngsep_ref_upload(ctx_, seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
-        if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-        ref_uploaded_[seq] = true;
-    }
-    std::vector<ngsep_snv_call> snvs;
-    if (!opt_.host_only) {
-        const int tile_len = opt_.tile_len > 0 ? opt_.tile_len : INT_MAX;
-        PackedTile tile;
-        std::vector<ngsep_snv_call> buf;
-        int tile_no = 0;
-        for (int64_t tf = win_first; tf <= win_last; tf += tile_len, tile_no++) {
-            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
-            int tl = (int)std::min<int64_t>(win_last, tf + (int64_t)tile_len - 1);
-            size_t r_lo, r_hi;   // records whose ordering start can reach the tile
-            tile_records(plan, (int)tf, tl, r_lo, r_hi);
-            if (r_lo >= r_hi) continue;
-            double tp = now_s();
-            pack_reads(reads, r_lo, r_hi, tile);
-            stats_.pack_s += now_s() - tp;
-            if (tile.hdr.empty()) continue;
-            double td = now_s();
-            ngsep_tile tv = tile.view(seq, (int)tf, tl);
-            int rc = ngsep_tile_submit(ctx_, &tv);
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-            size_t n = 0;
-            ngsep_tile_stats ts{};
-            buf.resize(std::max<size_t>(buf.size(), 65536));
-            rc = ngsep_tile_fetch(ctx_, buf.data(), buf.size(), &n, nullptr, &ts);
-            if (rc == NGSEP_EOVERFLOW && n > buf.size()) { buf.resize(n + 16); rc = ngsep_tile_fetch(ctx_, buf.data(), buf.size(), &n, nullptr, &ts); }
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-            stats_.device_s += now_s() - td;
-            stats_.covered_positions += ts.covered_positions;
-            stats_.candidate_positions += ts.candidate_positions;
-            stats_.aligned_bases += ts.aligned_bases;
-            stats_.kernel_ms += ts.kernel_ms;
-            stats_.kernel_launches += ts.kernel_launches;
-            stats_.tiles++;
-            snvs.insert(snvs.end(), buf.begin(), buf.begin() + n);
-        }
-    }
-
+void GpuSingleSampleVariantsDetector::emit_text(SeqJob& job) {
+    const std::string& chrom = genome_->names[job.seq];
+    SeqPlan& plan = job.plan;
+    std::vector<ngsep_snv_call>& snvs = job.snvs;
+    const std::set<int>& suppressed = plan.suppressed;
+    const std::vector<std::pair<int, int>>& embedded = plan.embedded;
     // ---- 4. ordered merge + text (SSVD:933-968) -------------------------------------------------------------------------
     std::sort(snvs.begin(), snvs.end(), [](const ngsep_snv_call& a, const ngsep_snv_call& c) { return a.pos < c.pos; });
     struct Line { int first, last, order; std::string text; };
     std::vector<Line> lines;
+    lines.reserve(snvs.size() + plan.indels.size());
     size_t ei = 0;
     for (auto& c : snvs) {
         if (suppressed.count(c.pos)) continue;
@@ -253,16 +325,18 @@ int GpuSingleSampleVariantsDetector::run_sequence(const BatchView& b, int seq, i
         bool emb = ei < embedded.size() && embedded[ei].first <= c.pos && c.pos <= embedded[ei].second;
         if (emb && !opt_.call_embedded) continue;
         lines.push_back({c.pos, c.pos, (int)lines.size(), snv_vcf_line(c, chrom, opt_.ploidy, opt_.csb, emb)});
-        stats_.snv_calls++;
+        job.snv_records++;
     }
-    for (auto& r : indels) {
-        bool mine = true;
-        if (opt_.n_shards > 1 && opt_.tile_len > 0) mine = (((r.pos - win_first) / opt_.tile_len) % opt_.n_shards) == opt_.shard;
+    for (auto& r : plan.indels) {
+        bool mine = true;   // host-made records go to the shard that owns the tile of their position
+        if (opt_.n_shards > 1) mine = (((r.pos - plan.win_first) / tile_len()) % opt_.n_shards) == opt_.shard;
         if (mine) lines.push_back({r.pos, r.last, (int)lines.size(), indel_vcf_line(r, chrom, opt_.ploidy)});
     }
     std::stable_sort(lines.begin(), lines.end(), [](const Line& a, const Line& c) { return a.first != c.first ? a.first < c.first : a.last < c.last; });
-    for (auto& l : lines) out += l.text;
-    return NGSEP_OK;
+    size_t bytes = 0;
+    for (auto& l : lines) bytes += l.text.size();
+    job.text.reserve(bytes);
+    for (auto& l : lines) job.text += l.text;
 }
 
 }  // namespace host
@@ -279,8 +353,8 @@ int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, 
     while (hi < b.n && b.seq_idx[hi] == seq) hi++;
     SeqPlan plan;
     int rc = plan_sequence(b, seq, lo, hi, plan);
-    if (rc != NGSEP_OK) return rc;
-    pack_reads(plan.reads, 0, plan.reads.size(), tile);
+    if (rc != NGSEP_OK) { err_ = plan.err; return rc; }
+    if (!pack_reads(plan.reads, 0, plan.reads.size(), tile, false, &err_)) return NGSEP_EINVAL;
     tile_first = plan.win_first;
     tile_last = plan.win_last;
     return NGSEP_OK;

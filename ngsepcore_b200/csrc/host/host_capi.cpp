@@ -15,6 +15,10 @@ using namespace ngsep_b200::host;
 
 namespace {
 
+thread_local uint32_t g_last_qual_bits = 8;
+thread_local uint8_t g_last_qual_dict[16] = {0};
+void remember_quality(const PackedTile& t) { g_last_qual_bits = t.qual_bits; std::memcpy(g_last_qual_dict, t.qual_dict, 16); }
+
 struct Handle {
     DetectorOptions opt;
     Genome genome;
@@ -44,6 +48,7 @@ DetectorOptions convert(const ngsep_detector_options* o) {
     d.ignore5 = o->ignore5; d.ignore3 = o->ignore3; d.het_rate = o->het_rate; d.het_modified = o->het_rate_set != 0;
     d.max_base_qs = o->max_base_qs; d.min_quality = o->min_quality; d.call_embedded = o->call_embedded_snvs != 0; d.csb = o->calc_strand_bias != 0;
     d.device = o->device; d.tile_len = o->tile_len; d.shard = o->shard; d.n_shards = o->n_shards < 1 ? 1 : o->n_shards; d.host_only = o->host_only != 0;
+    d.synchronous = o->synchronous != 0;
     return d;
 }
 
@@ -142,6 +147,7 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
     auto T1 = std::chrono::steady_clock::now();
     PackedTile t;
     pack_reads(reads, 0, reads.size(), t);
+    remember_quality(t);
     auto T2 = std::chrono::steady_clock::now();
     if (std::getenv("NGSEP_HOST_TIMING")) std::fprintf(stderr, "admit %.3f s pack %.3f s\n", std::chrono::duration<double>(T1 - T0).count(), std::chrono::duration<double>(T2 - T1).count());
     *n_reads = (int64_t)t.hdr.size();
@@ -167,6 +173,7 @@ int ngsep_ssvd_pack(void* p, const ngsep_host_batch* b, int seq_idx, ngsep_read_
     PackedTile t;
     int rc = h->det->pack_sequence(view_of(b), seq_idx, t, *tile_first, *tile_last);
     if (rc != NGSEP_OK) { h->err = h->det->error(); return rc; }
+    remember_quality(t);
     *n_reads = (int64_t)t.hdr.size();
     *n_words = t.payload.size();
     *max_span = t.max_span;
@@ -201,5 +208,12 @@ int ngsep_host_merge_order(int n_inputs, const ngsep_host_batch* inputs, int min
 }
 
 void ngsep_host_free(void* p) { std::free(p); }
+
+int ngsep_host_pack_quality(uint32_t* qual_bits, uint8_t* qual_dict16) {
+    if (!qual_bits || !qual_dict16) return NGSEP_EINVAL;
+    *qual_bits = g_last_qual_bits;
+    std::memcpy(qual_dict16, g_last_qual_dict, 16);
+    return NGSEP_OK;
+}
 
 }  // extern "C"

@@ -107,66 +107,32 @@ void GpuMultisampleVariantsDetector::on_span_event(int e, const std::string& ref
         last_indel_end = rec.last;      // MSVD:536-538
         if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
         plan.pop_indels.push_back(std::move(rec));
-        stats_.indel_calls++;
+        plan.stats.indel_calls++;
     }
 }
 
-int GpuMultisampleVariantsDetector::run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) {
-    const std::string& chrom = genome_->names[seq];
-    SeqPlan plan;
-    int prc = plan_sequence(b, seq, lo, hi, plan);
-    if (prc != NGSEP_OK) return prc;
-    if (plan.reads.empty()) return NGSEP_OK;
-    const int win_first = plan.win_first, win_last = plan.win_last;
-    const int n_samples = (int)samples_.size();
+int GpuMultisampleVariantsDetector::fetch_tile(SeqJob& job, ngsep_tile_stats& ts) {
+    const size_t n_samples = samples_.size();
+    size_t n = 0;
+    if (sbuf_.size() < 4096) { sbuf_.resize(4096); cbuf_.resize(4096 * n_samples); }
+    int rc = ngsep_tile_fetch_pop(ctx_, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
+    if (rc == NGSEP_EOVERFLOW && n > sbuf_.size()) {
+        sbuf_.resize(n + 16); cbuf_.resize((n + 16) * n_samples);
+        rc = ngsep_tile_fetch_pop(ctx_, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
+    }
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+    job.sites.insert(job.sites.end(), sbuf_.begin(), sbuf_.begin() + (ptrdiff_t)n);
+    job.scalls.insert(job.scalls.end(), cbuf_.begin(), cbuf_.begin() + (ptrdiff_t)(n * n_samples));
+    return NGSEP_OK;
+}
 
-    if (!opt_.host_only && !ref_uploaded_[seq]) {
-        int rc = ngsep_ref_upload(ctx_, seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
-        if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-        ref_uploaded_[seq] = true;
-    }
-    std::vector<ngsep_pop_site> sites;
-    std::vector<ngsep_sample_call> scalls;   // n_samples per site
-    if (!opt_.host_only) {
-        const int tile_len = opt_.tile_len > 0 ? opt_.tile_len : INT_MAX;
-        PackedTile tile;
-        std::vector<ngsep_pop_site> sbuf;
-        std::vector<ngsep_sample_call> cbuf;
-        int tile_no = 0;
-        for (int64_t tf = win_first; tf <= win_last; tf += tile_len, tile_no++) {
-            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
-            int tl = (int)std::min<int64_t>(win_last, tf + (int64_t)tile_len - 1);
-            size_t r_lo, r_hi;
-            tile_records(plan, (int)tf, tl, r_lo, r_hi);
-            if (r_lo >= r_hi) continue;
-            double tp = now_s();
-            pack_reads(plan.reads, r_lo, r_hi, tile, true);
-            stats_.pack_s += now_s() - tp;
-            if (tile.hdr.empty()) continue;
-            double td = now_s();
-            ngsep_tile tv = tile.view(seq, (int)tf, tl);
-            int rc = ngsep_tile_submit(ctx_, &tv);
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-            size_t n = 0;
-            ngsep_tile_stats ts{};
-            if (sbuf.size() < 4096) { sbuf.resize(4096); cbuf.resize(4096 * (size_t)n_samples); }
-            rc = ngsep_tile_fetch_pop(ctx_, sbuf.data(), sbuf.size(), &n, cbuf.data(), nullptr, &ts);
-            if (rc == NGSEP_EOVERFLOW && n > sbuf.size()) {
-                sbuf.resize(n + 16); cbuf.resize((n + 16) * (size_t)n_samples);
-                rc = ngsep_tile_fetch_pop(ctx_, sbuf.data(), sbuf.size(), &n, cbuf.data(), nullptr, &ts);
-            }
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
-            stats_.device_s += now_s() - td;
-            stats_.covered_positions += ts.covered_positions;
-            stats_.candidate_positions += ts.candidate_positions;
-            stats_.aligned_bases += ts.aligned_bases;
-            stats_.kernel_ms += ts.kernel_ms;
-            stats_.kernel_launches += ts.kernel_launches;
-            stats_.tiles++;
-            sites.insert(sites.end(), sbuf.begin(), sbuf.begin() + n);
-            scalls.insert(scalls.end(), cbuf.begin(), cbuf.begin() + n * (size_t)n_samples);
-        }
-    }
+void GpuMultisampleVariantsDetector::emit_text(SeqJob& job) {
+    const std::string& chrom = genome_->names[job.seq];
+    SeqPlan& plan = job.plan;
+    const int win_first = plan.win_first;
+    const int n_samples = (int)samples_.size();
+    std::vector<ngsep_pop_site>& sites = job.sites;
+    std::vector<ngsep_sample_call>& scalls = job.scalls;
 
     // ---- ordered merge + text: MSVD prints each record as its position is reached (MSVD:534-535) ----------------------
     std::vector<size_t> order(sites.size());
@@ -182,16 +148,15 @@ int GpuMultisampleVariantsDetector::run_sequence(const BatchView& b, int seq, in
         bool emb = ei < plan.embedded.size() && plan.embedded[ei].first <= c.pos && c.pos <= plan.embedded[ei].second;
         if (emb && !opt_.call_embedded) continue;
         lines.push_back({c.pos, c.pos, (int)lines.size(), pop_snv_vcf_line(c, scalls.data() + oi * (size_t)n_samples, n_samples, chrom, opt_.ploidy, emb)});
-        stats_.snv_calls++;
+        job.snv_records++;
     }
     for (auto& r : plan.pop_indels) {
         bool mine = true;
-        if (opt_.n_shards > 1 && opt_.tile_len > 0) mine = (((r.pos - win_first) / opt_.tile_len) % opt_.n_shards) == opt_.shard;
+        if (opt_.n_shards > 1) mine = (((r.pos - win_first) / tile_len()) % opt_.n_shards) == opt_.shard;
         if (mine) lines.push_back({r.pos, r.last, (int)lines.size(), pop_indel_vcf_line(r, chrom, opt_.ploidy)});
     }
     std::stable_sort(lines.begin(), lines.end(), [](const Line& a, const Line& c) { return a.first < c.first; });   // one record per position
-    for (auto& l : lines) out += l.text;
-    return NGSEP_OK;
+    for (auto& l : lines) job.text += l.text;
 }
 
 // ---- population VCF text ---------------------------------------------------------------------------------------------

@@ -1,5 +1,8 @@
 // Tile packer: host reads (with their realigner versions) -> the header / payload layout of include/ngsep_pileup.h.
+// Contiguous ranges of reads are packed by independent threads into per-thread parts (kept between calls: no allocation or
+// page faults after the first tile), then copied side by side into the tile's buffers with their offsets shifted.
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cstdlib>
 #include <cstring>
@@ -9,6 +12,41 @@
 
 namespace ngsep_b200 {
 namespace host {
+
+// ---- HostBuf ------------------------------------------------------------------------------------------------------------
+template <typename T>
+void HostBuf<T>::release() {
+    if (p) {
+        if (registered) ngsep_host_unregister(p);
+        std::free(p);
+    }
+    p = nullptr; n = cap = 0; registered = false;
+}
+template <typename T>
+void HostBuf<T>::reserve(size_t want) {
+    if (want <= cap && (registered || !pin || cap == 0)) return;
+    if (want <= cap && pin && !registered) {   // asked to pin after the allocation
+        registered = ngsep_host_register(p, cap * sizeof(T)) == NGSEP_OK;
+        return;
+    }
+    release();
+    size_t c = std::max<size_t>(want + want / 4, 1024);
+    size_t bytes = (c * sizeof(T) + 4095) & ~(size_t)4095;
+    p = (T*)std::aligned_alloc(4096, bytes);
+    if (!p) throw std::bad_alloc();
+    cap = bytes / sizeof(T);
+    if (pin) registered = ngsep_host_register(p, bytes) == NGSEP_OK;
+}
+template struct HostBuf<ngsep_read_hdr>;
+template struct HostBuf<uint32_t>;
+template struct HostBuf<uint16_t>;
+template struct HostBuf<uint8_t>;
+
+int host_threads() {
+    if (const char* e = std::getenv("NGSEP_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) return v; }
+    unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(32u, hw ? hw : 1u));
+}
 
 namespace {
 
@@ -27,138 +65,267 @@ inline int ref_last_of(const ReadState& st) {
     return ref - 1;
 }
 
-void emit_record(const HostRead& r, const ReadState& st, bool windowed, int from, int to, uint32_t qoff, PackedTile& out) {
+// ---- eight bases / qualities at a time ------------------------------------------------------------------------------------
+constexpr uint64_t k01 = 0x0101010101010101ull, k7f = 0x7f7f7f7f7f7f7f7full, k80 = 0x8080808080808080ull;
+inline uint64_t zero_bytes(uint64_t v) { return ~(((v & k7f) + k7f) | v | k7f); }            // 0x80 in every byte of v that is zero (exact)
+inline uint32_t gather_high_bits(uint64_t m) { return (uint32_t)((((m >> 7) & k01) * 0x0102040810204080ull) >> 56); }   // bit k = byte k
+
+// 2-bit codes (A0 C1 G2 T3, either case) of eight ASCII bases; *bad = one bit per byte that is not a base of ACGTacgt
+inline uint32_t encode8(uint64_t w, uint32_t* bad) {
+    const uint64_t u = w & 0xDFDFDFDFDFDFDFDFull;   // upper case
+    const uint64_t ok = zero_bytes(u ^ (0x41 * k01)) | zero_bytes(u ^ (0x43 * k01)) | zero_bytes(u ^ (0x47 * k01)) | zero_bytes(u ^ (0x54 * k01));
+    *bad = gather_high_bits(~ok & k80);
+    uint64_t x = (w >> 1) & (3 * k01);          // A 0, C 1, G 3, T 2
+    x ^= (x >> 1) & k01;                        // A 0, C 1, G 2, T 3
+    x = (x | (x >> 6)) & 0x000F000F000F000Full;
+    x = (x | (x >> 12)) & 0x000000FF000000FFull;
+    x = (x | (x >> 24)) & 0xFFFFull;
+    return (uint32_t)x;
+}
+// one bit per byte with quality char - 33 <= 3 (CountsHelper.java:214: such a base is never counted)
+inline uint32_t lowq8(uint64_t w) {
+    const uint64_t ge37 = (((w & k7f) + (0x7f - 36) * k01) | w) & k80;
+    return gather_high_bits(~ge37 & k80);
+}
+inline uint64_t load8(const uint8_t* p, int n, uint8_t fill) {   // n in 1..8 bytes, the rest = fill
+    uint64_t w;
+    if (n >= 8) { std::memcpy(&w, p, 8); return w; }
+    uint8_t t[8];
+    std::memset(t, fill, 8);
+    std::memcpy(t, p, (size_t)n);
+    std::memcpy(&w, t, 8);
+    return w;
+}
+
+// How the tile's qualities travel (ngsep_tile.qual_bits): the bytes themselves, or 2- / 4-bit codes when the tile's qualities
+// fall into at most 4 / 16 of the classes the path can tell apart — every q <= 3 alike (never counted, CH:214), min(30, q)
+// otherwise (CH:91) — with one representative byte per class in the dictionary.
+struct QualCoder {
+    int bits = 8;
+    uint8_t code_of[256];
+    uint8_t dict[16];
+};
+inline int qual_class(int c) { const int q = c - 33; return q <= 3 ? 0 : std::min(30, q); }
+QualCoder choose_coder(const bool* seen) {
+    QualCoder qc;
+    std::memset(qc.code_of, 0, sizeof qc.code_of);
+    std::memset(qc.dict, 0, sizeof qc.dict);
+    bool present[31] = {false};
+    for (int c = 0; c < 256; c++) if (seen[c]) present[qual_class(c)] = true;
+    int n = 0, code_of_class[31];
+    for (int k = 0; k < 31; k++) { code_of_class[k] = -1; if (present[k]) code_of_class[k] = n++; }
+    int bits = n <= 4 ? 2 : (n <= 16 ? 4 : 8);
+    if (const char* e = std::getenv("NGSEP_QUAL_BITS")) { const int v = std::atoi(e); if (v == 8 || (v == 4 && bits == 2)) bits = v; }   // experiments: wider than needed
+    qc.bits = bits;
+    if (bits == 8) return qc;
+    for (int k = 0; k < 31; k++) if (code_of_class[k] >= 0) qc.dict[code_of_class[k]] = (uint8_t)(k == 0 ? 35 : 33 + k);
+    for (int c = 0; c < 256; c++) { const int k = code_of_class[qual_class(c)]; qc.code_of[c] = (uint8_t)(k < 0 ? 0 : k); }
+    return qc;
+}
+inline size_t qual_run_bytes(int L, int bits) { return ((((size_t)L * (size_t)bits + 7) / 8) + 3) & ~(size_t)3; }
+
+// Per-thread output of a contiguous range of reads.
+struct Part {
+    std::vector<ngsep_read_hdr> hdr;
+    std::vector<uint32_t> payload;
+    std::vector<uint8_t> qual;
+    size_t n_hdr = 0, n_pay = 0, n_qual = 0;   // filled sizes (the vectors only grow)
+    int max_span = 1, max_back = 0;
+    uint64_t aligned_bases = 0;
+    bool bad = false;
+};
+
+// bases2 / N mask / low-quality mask of one read, computed once and shared by its versions
+struct ReadBits { uint32_t* b2; uint32_t* nm; uint32_t* lq; int nb, nw; bool has_n; };
+
+void encode_read(const HostRead& r, ReadBits& o) {
+    const int len = r.L;
+    o.nb = (len + 15) / 16; o.nw = (len + 31) / 32;
+    std::memset(o.b2, 0, sizeof(uint32_t) * (size_t)(o.nb + 2 * o.nw));
+    o.nm = o.b2 + o.nb; o.lq = o.nm + o.nw;
+    uint32_t any_bad = 0;
     const CodeLut& L = lut();
+    for (int i = 0; i < len; i += 8) {
+        const int n = std::min(8, len - i);
+        uint32_t bad;
+        uint32_t c = encode8(load8(r.bases + i, n, 'A'), &bad);
+        if (bad) {   // rare: a base outside ACGT — its code is 0 and its bit goes to the N mask
+            c = 0;
+            for (int k = 0; k < n; k++) c |= (uint32_t)(L.v[r.bases[i + k]] & 3u) << (2 * k);
+            any_bad |= bad;
+            o.nm[i >> 5] |= bad << (i & 31);
+        }
+        o.b2[i >> 4] |= c << ((i & 15) * 2);
+        o.lq[i >> 5] |= lowq8(load8(r.quals + i, n, 0xff)) << (i & 31);
+    }
+    o.has_n = any_bad != 0;
+}
+
+inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out) {
     const int len = r.L;
     const int nc = (int)st.cigar.size();
-    if (len > 0xffff || nc > 0xff) return;  // rejected earlier by the detector; kept as a guard
-    // one pass over the read: 2-bit bases, "not ACGT" bits and "quality <= 3" bits (never counted, CH:214)
-    const int nb = (len + 15) / 16, nm_words = (len + 31) / 32;
-    uint32_t small[3 * 64];
-    std::vector<uint32_t> big;
-    uint32_t* bw = small;
-    if (nb + 2 * nm_words > (int)(sizeof(small) / sizeof(small[0]))) { big.assign((size_t)nb + 2 * (size_t)nm_words, 0u); bw = big.data(); }
-    else std::memset(small, 0, sizeof(uint32_t) * (size_t)(nb + 2 * nm_words));
-    uint32_t* nmk = bw + nb;
-    uint32_t* lq = nmk + nm_words;
-    uint32_t any_n = 0u;
-    const uint8_t* bases = r.bases;
-    const uint8_t* quals = r.quals;
-    for (int i = 0; i < len; i++) {
-        const uint32_t c = L.v[bases[i]];
-        bw[i >> 4] |= (c & 3u) << ((i & 15) * 2);
-        const uint32_t isn = c >> 2;                  // 1 for anything outside ACGT
-        nmk[i >> 5] |= isn << (i & 31);
-        any_n |= isn;
-    }
-    if (quals) for (int i = 0; i < len; i++) lq[i >> 5] |= (uint32_t)((int)quals[i] - 33 <= 3) << (i & 31);
-    const bool has_n = any_n != 0u;
+    if (len > 0xffff || nc > 0xff) { out.bad = true; return false; }
     ngsep_read_hdr h;
     h.first = r.admit_first;
-    h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
-    if (nc == 1 && !has_n && !windowed && st.cigar[0] == (((uint32_t)len << 3) | 3u)) h.meta |= NGSEP_M_SIMPLE;
+    h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (rb.has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
+    if (nc == 1 && !rb.has_n && !windowed && st.cigar[0] == (((uint32_t)len << 3) | 3u)) h.meta |= NGSEP_M_SIMPLE;
     h.ign_start = (int16_t)st.ign_s;
     h.ign_end = (int16_t)st.ign_e;
-    h.off = (uint32_t)out.payload.size();
-    out.hdr.push_back(h);
-    auto& p = out.payload;
-    if (windowed) { p.push_back((uint32_t)from); p.push_back((uint32_t)to); p.push_back((uint32_t)st.first); }
-    p.insert(p.end(), st.cigar.begin(), st.cigar.end());
-    p.insert(p.end(), bw, bw + nb);
-    if (has_n) p.insert(p.end(), nmk, nmk + nm_words);
-    p.insert(p.end(), lq, lq + nm_words);
-    p.push_back(qoff);
+    h.off = (uint32_t)out.n_pay;
+    out.hdr[out.n_hdr++] = h;
+    uint32_t* p = out.payload.data() + out.n_pay;
+    if (windowed) { *p++ = (uint32_t)from; *p++ = (uint32_t)to; *p++ = (uint32_t)st.first; }
+    for (int k = 0; k < nc; k++) *p++ = st.cigar[(size_t)k];
+    std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
+    if (rb.has_n) { std::memcpy(p, rb.nm, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw; }
+    std::memcpy(p, rb.lq, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw;
+    *p++ = qoff;
+    out.n_pay = (size_t)(p - out.payload.data());
     out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
     out.max_back = std::max(out.max_back, r.admit_first - st.first);
     out.aligned_bases += (uint64_t)len;
+    return true;
+}
+
+void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const QualCoder& qc, Part& out) {
+    out.n_hdr = out.n_pay = out.n_qual = 0;
+    out.max_span = 1; out.max_back = 0; out.aligned_bases = 0; out.bad = false;
+    size_t n_rec = 0, n_words = 0, n_q = 0;
+    int max_len = 0;
+    for (size_t i = lo; i < hi; i++) {   // exact upper bounds: one reservation per array
+        const HostRead& r = reads[i];
+        const size_t per = 3 + (size_t)((r.L + 15) / 16) + 2 * (size_t)((r.L + 31) / 32) + 1;
+        const bool plain = r.closed.empty() && r.st.first == r.admit_first;
+        size_t rec = 1, cig = r.st.cigar.size();
+        if (!plain) { rec += r.closed.size(); for (const Version& v : r.closed) cig += v.st.cigar.size(); }
+        n_rec += rec; n_words += rec * per + cig; n_q += qual_run_bytes(r.L, qc.bits);
+        max_len = std::max(max_len, r.L);
+    }
+    if (out.hdr.size() < n_rec) out.hdr.resize(n_rec + n_rec / 8);
+    if (out.payload.size() < n_words) out.payload.resize(n_words + n_words / 8);
+    if (out.qual.size() < n_q) out.qual.resize(n_q + n_q / 8);
+    std::vector<uint32_t> scratch((size_t)((max_len + 15) / 16 + 2 * ((max_len + 31) / 32)) + 4);
+    ReadBits rb{};
+    rb.b2 = scratch.data();
+    for (size_t i = lo; i < hi; i++) {
+        const HostRead& r = reads[i];
+        // the read's qualities go once into the quality array (every version of the read points at them)
+        const uint32_t qoff = (uint32_t)(out.n_qual / 4);
+        uint8_t* q = out.qual.data() + out.n_qual;
+        const size_t padded = qual_run_bytes(r.L, qc.bits);
+        if (qc.bits == 8) {
+            std::memcpy(q, r.quals, (size_t)r.L);
+            for (size_t k = (size_t)r.L; k < padded; k++) q[k] = (uint8_t)'!';
+        } else if (qc.bits == 2) {
+            int i = 0;
+            size_t o = 0;
+            for (; i + 4 <= r.L; i += 4, o++)
+                q[o] = (uint8_t)(qc.code_of[r.quals[i]] | (qc.code_of[r.quals[i + 1]] << 2) | (qc.code_of[r.quals[i + 2]] << 4) | (qc.code_of[r.quals[i + 3]] << 6));
+            if (i < r.L) { uint8_t b = 0; for (int k = 0; i + k < r.L; k++) b |= (uint8_t)(qc.code_of[r.quals[i + k]] << (2 * k)); q[o++] = b; }
+            for (; o < padded; o++) q[o] = 0;
+        } else {
+            int i = 0;
+            size_t o = 0;
+            for (; i + 2 <= r.L; i += 2, o++) q[o] = (uint8_t)(qc.code_of[r.quals[i]] | (qc.code_of[r.quals[i + 1]] << 4));
+            if (i < r.L) q[o++] = qc.code_of[r.quals[i]];
+            for (; o < padded; o++) q[o] = 0;
+        }
+        out.n_qual += padded;
+        if (r.L > 0xffff) { out.bad = true; continue; }
+        encode_read(r, rb);
+        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, rb, false, 0, 0, qoff, out); continue; }
+        for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out);
+        emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out);
+    }
 }
 
 }  // namespace
 
-static void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out) {
-    out.hdr.clear();
-    out.payload.clear();
-    out.qual.clear();
-    out.max_span = 1;
-    out.max_back = 0;
-    out.aligned_bases = 0;
-    out.hdr.reserve(hi - lo);
-    {   // one reservation per array instead of geometric regrowth
-        size_t bases = 0;
-        for (size_t i = lo; i < hi; i++) bases += (size_t)reads[i].L;
-        out.payload.reserve((hi - lo) * 8 + bases / 16 + bases / 16 + 64);
-        out.qual.reserve(bases + 4 * (hi - lo) + 64);
-    }
-    for (size_t i = lo; i < hi; i++) {
-        const HostRead& r = reads[i];
-        // the read's qualities go once into the quality array (every version of the read points at them)
-        const uint32_t qoff = (uint32_t)(out.qual.size() / 4);
-        if (r.quals) out.qual.insert(out.qual.end(), r.quals, r.quals + r.L);
-        else out.qual.insert(out.qual.end(), (size_t)r.L, (uint8_t)'+');   // absent QUAL reads as '+' (RA:1025)
-        out.qual.resize((out.qual.size() + 3) & ~(size_t)3, (uint8_t)'!');
-        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, false, 0, 0, qoff, out); continue; }
-        for (const Version& v : r.closed) emit_record(r, v.st, true, v.from, v.to, qoff, out);
-        emit_record(r, r.st, true, r.cur_from, INT_MAX, qoff, out);
-    }
-}
-
-static int host_threads() {
-    if (const char* e = std::getenv("NGSEP_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) return v; }
-    unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(1u, std::min(8u, hw ? hw : 1u));
-}
-
-void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups) {
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err) {
     out.group.clear();
     const size_t n = hi > lo ? hi - lo : 0;
-    const int nt = (int)std::min<size_t>((size_t)host_threads(), n / 20000 + 1);   // small tiles are not worth a thread each
-    if (nt <= 1) pack_range(reads, lo, hi, out);
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 8192 + 1));   // small tiles are not worth a thread each
+    static thread_local std::vector<Part> tl_parts;   // per calling thread: reused from tile to tile
+    if ((int)tl_parts.size() < nt) tl_parts.resize((size_t)nt);
+    std::vector<Part>& parts = tl_parts;              // (worker threads must not name the thread_local themselves)
+    auto range_of = [&](int t, size_t& a, size_t& b) { a = lo + n * (size_t)t / (size_t)nt; b = lo + n * (size_t)(t + 1) / (size_t)nt; };
+    // which quality classes occur in the tile -> bytes, or 2- / 4-bit codes
+    std::vector<std::array<bool, 256>> seen((size_t)nt);
+    auto scan = [&](int t) {
+        size_t a, b;
+        range_of(t, a, b);
+        unsigned char hit[256];
+        std::memset(hit, 0, sizeof hit);
+        for (size_t i = a; i < b; i++) { const uint8_t* q = reads[i].quals; const int L = reads[i].L; for (int k = 0; k < L; k++) hit[q[k]] = 1; }
+        for (int c = 0; c < 256; c++) seen[(size_t)t][(size_t)c] = hit[c] != 0;
+    };
+    if (nt == 1) scan(0);
     else {
-        // contiguous ranges of reads are packed independently, then concatenated: payload offsets move by the words in front
-        // of the range, quality offsets (the last payload word of every record) by the quality words in front of it
-        std::vector<PackedTile> part((size_t)nt);
         std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) {
-            const size_t a = lo + n * (size_t)t / (size_t)nt, b = lo + n * (size_t)(t + 1) / (size_t)nt;
-            th.emplace_back([&reads, &part, a, b, t]() { pack_range(reads, a, b, part[(size_t)t]); });
-        }
+        for (int t = 1; t < nt; t++) th.emplace_back(scan, t);
+        scan(0);
         for (auto& x : th) x.join();
-        size_t nh = 0, np = 0, nq = 0;
-        for (auto& p : part) { nh += p.hdr.size(); np += p.payload.size(); nq += p.qual.size(); }
-        out.hdr.resize(nh); out.payload.resize(np); out.qual.resize(nq);
-        out.max_span = 1; out.max_back = 0; out.aligned_bases = 0;
-        std::vector<size_t> bh((size_t)nt), bp((size_t)nt), bq((size_t)nt);
-        nh = np = nq = 0;
-        for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += part[t].hdr.size(); np += part[t].payload.size(); nq += part[t].qual.size(); }
-        th.clear();
-        for (int t = 0; t < nt; t++) {
-            th.emplace_back([&out, &part, &bh, &bp, &bq, t]() {
-                PackedTile& p = part[(size_t)t];
-                const uint32_t dp = (uint32_t)bp[t], dq = (uint32_t)(bq[t] / 4);
-                for (size_t i = 0; i < p.hdr.size(); i++) {
-                    const size_t end = (i + 1 < p.hdr.size()) ? p.hdr[i + 1].off : p.payload.size();
-                    p.payload[end - 1] += dq;          // qoff
-                    p.hdr[i].off += dp;
-                }
-                std::copy(p.hdr.begin(), p.hdr.end(), out.hdr.begin() + (ptrdiff_t)bh[t]);
-                std::copy(p.payload.begin(), p.payload.end(), out.payload.begin() + (ptrdiff_t)bp[t]);
-                std::copy(p.qual.begin(), p.qual.end(), out.qual.begin() + (ptrdiff_t)bq[t]);
-            });
-        }
-        for (auto& x : th) x.join();
-        for (auto& p : part) { out.max_span = std::max(out.max_span, p.max_span); out.max_back = std::max(out.max_back, p.max_back); out.aligned_bases += p.aligned_bases; }
     }
+    bool any[256];
+    for (int c = 0; c < 256; c++) { any[c] = false; for (int t = 0; t < nt; t++) any[c] = any[c] || seen[(size_t)t][(size_t)c]; }
+    const QualCoder qc = choose_coder(any);
+    out.qual_bits = (uint32_t)qc.bits;
+    std::memcpy(out.qual_dict, qc.dict, 16);
+    if (nt == 1) pack_range(reads, lo, hi, qc, parts[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) { size_t a, b; range_of(t, a, b); Part* part = &parts[(size_t)t]; th.emplace_back([&reads, &qc, part, a, b]() { pack_range(reads, a, b, qc, *part); }); }
+        { size_t a, b; range_of(0, a, b); pack_range(reads, a, b, qc, parts[0]); }
+        for (auto& x : th) x.join();
+    }
+    // contiguous ranges were packed independently: payload offsets move by the words in front of the range, quality offsets
+    // (the last payload word of every record) by the quality words in front of it
+    size_t nh = 0, np = 0, nq = 0;
+    std::vector<size_t> bh((size_t)nt), bp((size_t)nt), bq((size_t)nt);
+    bool bad = false;
+    for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += parts[t].n_hdr; np += parts[t].n_pay; nq += parts[t].n_qual; bad = bad || parts[t].bad; }
+    if (bad) {
+        if (err) *err = "read longer than 65535 bases or with more than 255 CIGAR operations (after realignment): not supported by the device layout";
+        out.hdr.clear(); out.payload.clear(); out.qual.clear();
+        return false;
+    }
+    out.hdr.resize(nh); out.payload.resize(np); out.qual.resize(nq);
+    out.max_span = 1; out.max_back = 0; out.aligned_bases = 0;
+    auto place = [&](int t) {
+        Part& p = parts[(size_t)t];
+        const uint32_t dp = (uint32_t)bp[t], dq = (uint32_t)(bq[t] / 4);
+        ngsep_read_hdr* oh = out.hdr.data() + bh[t];
+        uint32_t* op = out.payload.data() + bp[t];
+        std::memcpy(op, p.payload.data(), p.n_pay * sizeof(uint32_t));
+        std::memcpy(out.qual.data() + bq[t], p.qual.data(), p.n_qual);
+        for (size_t i = 0; i < p.n_hdr; i++) {
+            ngsep_read_hdr h = p.hdr[i];
+            const size_t end = (i + 1 < p.n_hdr) ? p.hdr[i + 1].off : p.n_pay;
+            op[end - 1] += dq;          // qoff
+            h.off += dp;
+            oh[i] = h;
+        }
+    };
+    if (nt == 1) place(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(place, t);
+        place(0);
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < nt; t++) { out.max_span = std::max(out.max_span, parts[t].max_span); out.max_back = std::max(out.max_back, parts[t].max_back); out.aligned_bases += parts[t].aligned_bases; }
     if (with_groups) {   // one id per record (every version of a read carries the read's group)
-        out.group.reserve(out.hdr.size());
+        out.group.resize(out.hdr.size());
         size_t k = 0;
         for (size_t i = lo; i < hi; i++) {
             const HostRead& r = reads[i];
             const size_t n_rec = (r.closed.empty() && r.st.first == r.admit_first) ? 1 : r.closed.size() + 1;
             const uint16_t g = (r.rg >= 0 && r.rg < 0xffff) ? (uint16_t)r.rg : (uint16_t)0xffff;
-            for (size_t v = 0; v < n_rec && k < out.hdr.size(); v++, k++) out.group.push_back(g);
+            for (size_t v = 0; v < n_rec && k < out.hdr.size(); v++, k++) out.group[k] = g;
         }
-        out.group.resize(out.hdr.size(), (uint16_t)0xffff);
+        for (; k < out.hdr.size(); k++) out.group[k] = (uint16_t)0xffff;
     }
+    return true;
 }
 
 ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
@@ -172,6 +339,9 @@ ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
     t.group = group.size() == hdr.size() && !group.empty() ? group.data() : nullptr;
     t.qual = qual.data();
     t.n_qual = qual.size();
+    t.qual_bits = qual_bits;
+    std::memcpy(t.qual_dict, qual_dict, 16);
+    t.reserved = 0;
     return t;
 }
 

@@ -8,6 +8,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../../include/ngsep_pileup.h"
@@ -15,6 +16,13 @@
 
 namespace ngsep_b200 {
 namespace host {
+
+struct RunStats {
+    uint64_t records = 0, admitted = 0, versions = 0, events = 0, indel_calls = 0, snv_calls = 0;
+    uint64_t covered_positions = 0, candidate_positions = 0, aligned_bases = 0, tiles = 0, kernel_launches = 0;
+    double kernel_ms = 0, prepass_s = 0, pack_s = 0, device_s = 0, total_s = 0;   // prepass_s: wall time of the (parallel) host planning stage
+    void add_host(const RunStats& o) { admitted += o.admitted; versions += o.versions; events += o.events; indel_calls += o.indel_calls; }
+};
 
 struct EventOutcome { bool fired = false; int span = 1; bool str = false, new_str = false; };
 
@@ -77,17 +85,56 @@ struct PopIndelRecord {
 int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const std::vector<SampleDef>& samples,
                              const IndelCallerOptions& opt, PopIndelRecord& rec);
 
+// Grow-only host array for tile buffers.  With `pin` set the allocation is page-locked through ngsep_host_register (what a
+// JVM host does for its direct ByteBuffers), so ngsep_tile_submit copies it asynchronously; a registration that fails (no
+// device: host-only runs) leaves the memory pageable.  Contents are NOT kept across a growth.
+template <typename T>
+struct HostBuf {
+    T* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pin = false, registered = false;
+    HostBuf() = default;
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+    HostBuf(HostBuf&& o) noexcept { *this = std::move(o); }
+    HostBuf& operator=(HostBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; cap = o.cap; pin = o.pin; registered = o.registered; o.p = nullptr; o.n = o.cap = 0; o.registered = false; }
+        return *this;
+    }
+    ~HostBuf() { release(); }
+    void release();
+    void reserve(size_t want);                       // (discards the contents when it has to grow)
+    void resize(size_t k) { reserve(k); n = k; }
+    void clear() { n = 0; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* begin() { return p; }
+    T* end() { return p + n; }
+    const T* begin() const { return p; }
+    const T* end() const { return p + n; }
+};
+
 struct PackedTile {
-    std::vector<ngsep_read_hdr> hdr;
-    std::vector<uint32_t> payload;
-    std::vector<uint16_t> group;   // read-group id per record (0xFFFF = none), filled when pack_reads is given with_groups
-    std::vector<uint8_t> qual;   // phred+33 bytes, one run per read (padded to 4), addressed by the records' qoff
+    HostBuf<ngsep_read_hdr> hdr;
+    HostBuf<uint32_t> payload;
+    HostBuf<uint16_t> group;     // read-group id per record (0xFFFF = none), filled when pack_reads is given with_groups
+    HostBuf<uint8_t> qual;       // phred+33 bytes, one run per read (padded to 4), addressed by the records' qoff
+    uint32_t qual_bits = 8;      // how `qual` is coded: 8 = the bytes, 2 / 4 = codes into qual_dict (ngsep_tile.qual_bits)
+    uint8_t qual_dict[16] = {0};
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
+    void set_pinned(bool on) { hdr.pin = payload.pin = group.pin = qual.pin = on; }
     ngsep_tile view(int seq_idx, int first, int last) const;
 };
-// Packs reads[lo,hi) (all their versions) in pileup order.
-void pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false);
+// Packs reads[lo,hi) (all their versions) in pileup order, on up to host_threads() threads.  Returns false (and leaves `err`)
+// when a record cannot be represented in the device layout (more than 65535 bases or 255 CIGAR operations — also after the
+// realigner rewrote it).
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr);
+int host_threads();   // NGSEP_HOST_THREADS, else the hardware concurrency (at most 32)
 
 struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 that affect this path
     std::string sample_id = "Sample";
@@ -106,17 +153,15 @@ struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 
     double min_allele_depth_freq = 0;   // MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58)
     // device plumbing (not reference options)
     int device = 0;
-    int tile_len = 0;          // 0 = one tile per sequence; otherwise region tiles of this many positions
+    int tile_len = 0;          // region tiles of this many positions; 0 = automatic (kAutoTileLen: sequences up to that length are one tile)
+    bool synchronous = false;  // test hook: one tile at a time from pageable buffers, host stages on the calling thread (the pipelined run
+                               // must give the same bytes)
     int shard = 0, n_shards = 1;   // region sharding across ranks: this process handles tiles t % n_shards == shard
     bool host_only = false;    // test hook: run admission + event pre-pass only and report the host-made indel/STR records
                                // (no SNV calling happens anywhere in this mode; it is not a fallback)
 };
 
-struct RunStats {
-    uint64_t records = 0, admitted = 0, versions = 0, events = 0, indel_calls = 0, snv_calls = 0;
-    uint64_t covered_positions = 0, candidate_positions = 0, aligned_bases = 0, tiles = 0, kernel_launches = 0;
-    double kernel_ms = 0, prepass_s = 0, pack_s = 0, device_s = 0, total_s = 0;
-};
+constexpr int kAutoTileLen = 2000000;
 
 // Outcome of the host stages for one sequence (admission + event pre-pass).
 struct SeqPlan {
@@ -126,6 +171,21 @@ struct SeqPlan {
     std::set<int> suppressed;                    // positions whose device SNV decision must not be reported
     std::vector<std::pair<int, int>> embedded;   // closed intervals of embedded positions (SSVPL:150-151)
     int win_first = 1, win_last = 0, max_reach = 1, max_back = 0;
+    RunStats stats;                              // what the host stages of this sequence add to the run's statistics
+    std::string err;
+};
+
+// One sequence of a run: its plan (host stages), what came back from the device, and its VCF records.
+struct SeqJob {
+    int seq = 0;
+    int64_t lo = 0, hi = 0;                      // records of the batch
+    SeqPlan plan;
+    std::vector<ngsep_snv_call> snvs;            // single-sample device results
+    std::vector<ngsep_pop_site> sites;           // multi-sample device results ...
+    std::vector<ngsep_sample_call> scalls;       // ... n_samples per site
+    uint64_t snv_records = 0;
+    int rc = 0;
+    std::string text;
 };
 
 // Drop-in for SingleSampleVariantsDetector.findSNVs over in-memory alignments.
@@ -146,13 +206,23 @@ protected:
     std::vector<bool> ref_uploaded_;
     RunStats stats_;
     std::string err_;
+    static constexpr int kHostRing = 4;          // host tile buffers (page-locked, reused from run to run); up to 3 tiles in flight
+    PackedTile ring_[kHostRing];
+    std::vector<ngsep_snv_call> call_buf_;       // where ngsep_tile_fetch writes
     virtual int ensure_ctx();
     virtual std::string header_text() const { return vcf_header(opt_.sample_id, opt_.ploidy, opt_.print_sample_ploidy); }
-    virtual int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out);
-    // discoverVariantWithSpan at an event with a reference span > 1 that is not embedded (SSVPL:257-273)
+    virtual bool with_groups() const { return false; }
+    // waits for the oldest tile in flight and appends what it returned to the job it belongs to
+    virtual int fetch_tile(SeqJob& job, ngsep_tile_stats& ts);
+    // ordered merge (embedded / indel suppression, SSVPL:150-160) + VCF text of one sequence (SSVD:933-968) -> job.text
+    virtual void emit_text(SeqJob& job);
+    // discoverVariantWithSpan at an event with a reference span > 1 that is not embedded (SSVPL:257-273); may run on any
+    // host thread: everything it changes lives in `plan`
     virtual void on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan, int& last_indel_end);
     int plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan);
     void tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const;
+    int tile_len() const { return opt_.tile_len > 0 ? opt_.tile_len : kAutoTileLen; }
+    int run_device(std::vector<SeqJob>& jobs);
 public:
     int pack_sequence(const BatchView& b, int seq, PackedTile& tile, int& tile_first, int& tile_last);
 };
@@ -169,7 +239,11 @@ protected:
     int n_read_groups_;
     int ensure_ctx() override;
     std::string header_text() const override { return vcf_header(samples_, opt_.print_sample_ploidy); }
-    int run_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, std::string& out) override;
+    bool with_groups() const override { return true; }
+    int fetch_tile(SeqJob& job, ngsep_tile_stats& ts) override;
+    void emit_text(SeqJob& job) override;
+    std::vector<ngsep_pop_site> sbuf_;
+    std::vector<ngsep_sample_call> cbuf_;
     void on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan, int& last_indel_end) override;
 };
 

@@ -169,7 +169,8 @@ void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
 // tenths of an entry per record.  Only single-sample production runs use the list.
 size_t entries_need(const Ctx* c, const Slot* s) {
     if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) return 0;
-    return std::min<size_t>((size_t)s->tile.n_reads / 2 + 65536, 0x7fffffffull);
+    // + the pieces the resident warps of the window kernel reserve ahead (kEntChunk = 1024 entries each)
+    return std::min<size_t>((size_t)s->tile.n_reads / 2 + (size_t)c->sm_count * 64 * 1024, 0x7fffffffull);
 }
 
 int ensure_queue(Ctx* c, size_t cols) {
@@ -267,7 +268,8 @@ int launch_batch(Ctx* c) {
     if (rc != NGSEP_OK) return rc;
     {
         size_t ents = 0;
-        for (size_t i = 1; i < n; i++) ents += entries_need(c, c->slots[i]);
+        for (size_t i = 1; i < n; i++) ents += (c->params.n_samples > 1 || (c->params.flags & NGSEP_F_EMIT_ALL)) ? 0 : (size_t)c->slots[i]->tile.n_reads / 2;
+        if (ents) ents += (size_t)c->sm_count * 64 * 1024;
         CK(c->d_ent.reserve(std::min<size_t>(ents, 0x7fffffffull)), "column entry list alloc");
     }
     CK(cudaMemsetAsync(c->d_meta, 0, (1 + n) * kMetaStride, c->stream), "memset counters");   // queue + every slot: ONE memset
@@ -323,6 +325,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     if (multi && !c->samples_set) return fail(c, NGSEP_ESTATE, "multi-sample context: call ngsep_samples_set before the first tile");
     if (multi && t->n_reads > 0 && !t->group) return fail(c, NGSEP_EINVAL, "multi-sample context: ngsep_tile.group is required");
     if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
+    if (t->qual_bits != 0u && t->qual_bits != 2u && t->qual_bits != 4u && t->qual_bits != 8u) return fail(c, NGSEP_EINVAL, "ngsep_tile.qual_bits must be 0, 2, 4 or 8");
+    const unsigned int qual_bits = t->qual_bits ? t->qual_bits : 8u;
     CK(cudaSetDevice(c->device), "set device");
     const RefSeq& ref = c->refs[t->seq_idx];
     // Quality bytes are only read for the positions that reach k_genotype_columns (a fraction of a percent of a
@@ -378,7 +382,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
     // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
     CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
-    launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, (unsigned long long)t->n_qual, c->cfg.pay_cap_words, s->d_report(), c->stream);
+    launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, (unsigned long long)t->n_qual, qual_bits, c->cfg.pay_cap_words, s->d_report(), c->stream);
     s->report_read = false;
     s->aligned_bases = 0;
     // window length: a multiple of 128, shrunk while an average window would not fit one stage
@@ -392,6 +396,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     TileDev& d = s->tile;
     d = TileDev{};
     d.hdr = s->d_hdr.p; d.payload = s->d_pay.p; d.group = multi ? s->d_group.p : nullptr; d.qual = host_qual ? host_qual : s->d_qual.p;
+    d.qual_bits = qual_bits;
+    std::memcpy(d.qual_dict, t->qual_dict, 16);
     d.gidx = multi ? s->d_gidx.p : nullptr; d.goff = multi ? s->d_goff.p : nullptr;
     d.gblk = multi ? s->d_gblk.p : nullptr; d.n_gblk = multi ? group_blocks(t->n_reads) : 0;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
@@ -517,7 +523,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
 
 extern "C" {
 
-int ngsep_abi_version(void) { return 2001; }
+int ngsep_abi_version(void) { return 2002; }
 int ngsep_built_sm(void) { return 100; }
 
 const char* ngsep_last_error(void* ctx) {
@@ -572,7 +578,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (const char* s = std::getenv("NGSEP_CTAS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v < c->ctas_per_sm) c->ctas_per_sm = v; }
     c->lazy_qual = (params->flags & NGSEP_F_QUALITY_IN_PLACE) != 0;
     if (const char* s = std::getenv("NGSEP_LAZY_QUAL")) c->lazy_qual = std::atoi(s) != 0;
-    c->geno_grid = c->sm_count * 16;
+    c->geno_grid = c->sm_count * 8;
     if (const char* s = std::getenv("NGSEP_GENO_BLOCKS_PER_SM")) { int v = std::atoi(s); if (v >= 1 && v <= 256) c->geno_grid = c->sm_count * v; }
     Slot* s0 = nullptr;
     if (new_slot(c, &s0, 0) != NGSEP_OK) { g_global_err = c->err; delete c; return NGSEP_ECUDA; }

@@ -14,7 +14,8 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, t0, kmin, misc, cnt, cov, list, wtot, wmax, rare;   // CTA-wide arrays
+    unsigned bar, t0, kmin, misc, cnt, cov, list, openq, chunk, wtot, wmax, rare;   // CTA-wide arrays
+    unsigned cov_len;                                                                 // entries of the cover array (a multiple of the largest CTA)
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
@@ -22,8 +23,10 @@ struct SmemLayout {
 
 // s_misc holds two sets of kMiscSet ints (one per window parity)
 constexpr int kMiscSet = 16;
-constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NUNRES = 9;
+constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_R1 = 5, M_PBASE = 6, M_FBCOV = 7, M_NOPEN = 8, M_NUNRES = 9;
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
+constexpr int kMaxOpen = 32;     // open columns listed in shared memory per window (more go straight to the global list)
+constexpr unsigned int kEntChunk = 1024u;   // entries a warp reserves in the global entry list at a time
 constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: the genotype kernel searches it
 // open-column entry, .w: either the number of records of the range that starts at record .z (0xffff = search), or — bit 31
 // set — the number of (record, offset) entries the window kernel resolved for the column (bits 0-23; they start at entry .z
@@ -49,8 +52,12 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.kmin = o; o += kSkipTable * 4;
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
-    L.cov = o; o += (T + 1) * 4;                // callable-cover deltas of the simple records, then their prefix sums
+    L.cov_len = ((unsigned)(T + kThreads - 1) / kThreads) * kThreads;   // entries the prefix scan walks (a multiple of the largest CTA); entry T is only a sink
+    L.cov = o; o += (L.cov_len > (unsigned)T ? L.cov_len : (unsigned)T + 1u) * 4;   // clean-cover deltas of the simple records, then their prefix sums
     L.list = o; o += T * 4;
+    o = (o + 15u) & ~15u;
+    L.openq = o; o += 2 * kMaxOpen * 16;        // open columns of the window (finished list entries), one list per window parity
+    L.chunk = o; o += (kThreads / 32) * 8;      // per warp: the piece of the entry list it fills (next, end)
     L.wtot = o; o += (kThreads / 32) * 4;       // per-warp totals of the prefix scan
     o = (o + 7u) & ~7u;
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
@@ -158,17 +165,16 @@ __device__ __forceinline__ bool record_is_simple(const ngsep_read_hdr& h) {
 struct WinCtx {
     int wbeg, g_lo, g_hi;        // 0-based index of the window start; [g_lo,g_hi) = the window inside tile and sequence
     const uint32_t* s_ref2;      // staged reference, base index wbeg - kRefLeft at bit 0 of word 0
-    uint32_t* s_cnt;             // per position: bits 0-15 flagged bases (an upper bound of the counted non-reference bases),
-                                 // bits 16-31 low-quality bases (q <= 3, never counted: CH:214) of simple records inside their callable range
-    int* s_cov;                  // per position: +1 / -1 where the callable range of a simple record starts / ends
+    uint32_t* s_cnt;             // per position: flagged bases (an upper bound of the counted non-reference bases)
+    int* s_cov;                  // per position: +1 / -1 where a stretch of CLEAN callable bases of a simple record starts / ends
     uint32_t* s_list;            // candidate list: positions in the window
     int* mset;                   // counters of this window
     bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
-    bool proof;                  // collect the cover / low-quality counts the hom-ref proof needs (single-sample contexts)
+    bool proof;                  // collect the clean-cover counts the hom-ref proof needs (single-sample contexts)
 };
 __device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx) {
     const int li = idx - w.wbeg;
-    if ((atomicAdd(&w.s_cnt[li], 1u) & 0xffffu) == 0u) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li;
+    if (atomicAdd(&w.s_cnt[li], 1u) == 0u) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li;
 }
 
 // 16 read bases (one payload word) against the reference at 0-based index `idx0` of the word's first base
@@ -178,10 +184,11 @@ __device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
 }
 
 // Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
-// Besides the mismatch flags it leaves what the hom-ref proof of the window needs: the record's CALLABLE
-// range (RA:782-784) as +1 / -1 in s_cov, and its low-quality bases (never counted, CH:214) inside that range in the
-// upper half of s_cnt.  Per position p that gives, after a prefix sum, EXACTLY how many simple records hold a counted base
-// equal to the reference at p: cover(p) - lowq(p) - flagged(p).
+// Besides the mismatch flags it leaves what the hom-ref proof of the window needs: its CLEAN cover — the
+// callable range (RA:782-784) minus every 32-base stretch of the read that holds a low-quality base (q <= 3: never counted,
+// CH:214) — as +1 / -1 in s_cov.  After a prefix sum, clean_cover(p) - flagged(p) is a LOWER bound of the counted bases equal
+// to the reference at p: every record counted in clean_cover(p) holds a counted base there, and at most flagged(p) of those
+// bases differ from the reference.
 __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
     const int L = (int)(h.meta & 0xffffu);         // one match block of L bases
     const int ref0 = h.first - 1;                  // 0-based index of read offset 0
@@ -195,16 +202,11 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
             if (ca < cb) {
                 atomicAdd(&w.s_cov[ca - w.wbeg], 1);
                 atomicAdd(&w.s_cov[cb - w.wbeg], -1);
-                const int o_lo = ca - ref0, o_hi = cb - ref0;   // read offsets [o_lo, o_hi) are callable and inside the window
-                for (int wi = o_lo >> 5; wi <= (o_hi - 1) >> 5; wi++) {
-                    uint32_t m = lowq[wi];
-                    if (m == 0u) continue;
-                    m &= range_mask32(max(o_lo - 32 * wi, 0), min(o_hi - 32 * wi, 32));
-                    while (m) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        atomicAdd(&w.s_cnt[ref0 + 32 * wi + bit - w.wbeg], 0x10000u);
-                    }
+                for (int wi = (ca - ref0) >> 5; wi <= (cb - 1 - ref0) >> 5; wi++) {
+                    if (lowq[wi] == 0u) continue;
+                    // a stretch with a low-quality base somewhere: none of its bases supports the proof
+                    atomicAdd(&w.s_cov[max(ref0 + 32 * wi, ca) - w.wbeg], -1);
+                    atomicAdd(&w.s_cov[min(ref0 + 32 * wi + 32, cb) - w.wbeg], 1);
                 }
             }
         }
@@ -364,11 +366,26 @@ __device__ __forceinline__ int resolve_offset(const RecView& r, int ign_s, int i
     return -1;
 }
 
+// The tile's quality array: phred+33 bytes, or 2- / 4-bit codes into a small dictionary (ngsep_tile.qual_bits).
+struct QualView {
+    const uint8_t* __restrict__ p;
+    uint32_t bits, d0, d1, d2, d3;
+    __device__ __forceinline__ QualView(const TileDev& d) : p(d.qual), bits(d.qual_bits), d0(d.qual_dict[0]), d1(d.qual_dict[1]), d2(d.qual_dict[2]), d3(d.qual_dict[3]) {}
+    // phred+33 byte of base `off` of the read whose run starts at 4-byte unit qoff
+    __device__ __forceinline__ uint32_t at(uint32_t qoff, uint32_t off) const {
+        if (bits == 8u) return p[(size_t)qoff * 4u + (size_t)off];
+        const uint32_t bit = off * bits;
+        const uint32_t code = ((uint32_t)p[(size_t)qoff * 4u + (size_t)(bit >> 3)] >> (bit & 7u)) & ((1u << bits) - 1u);
+        const uint32_t w = (code < 4u) ? d0 : ((code < 8u) ? d1 : ((code < 12u) ? d2 : d3));
+        return (w >> ((code & 3u) * 8u)) & 0xffu;
+    }
+};
+
 // One lane = one record.  code: bits 0-1 allele, 2-6 quality, 7 negative strand, 8 counted (CH:223), 9 call returned
 // by getAlleleCalls(1) (counts for totalCount, CH:210).
 constexpr uint32_t kCodeNeg = 1u << 7, kCodeCounted = 1u << 8, kCodeCall = 1u << 9;
 
-__device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, const uint8_t* __restrict__ qual, int pos, int max_qs) {
+__device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uint32_t* pay, const QualView& qual, int pos, int max_qs) {
     uint32_t qc, bw;
     int off;
     if (h.meta & NGSEP_M_SIMPLE) {
@@ -379,12 +396,12 @@ __device__ __forceinline__ uint32_t lane_eval(const ngsep_read_hdr& h, const uin
         const uint32_t* b2 = pay + 1;
         const uint32_t qoff = b2[((L + 15) >> 4) + ((L + 31) >> 5)];   // after the bases and the low-quality mask
         bw = b2[off >> 4];
-        qc = qual[(size_t)qoff * 4u + (size_t)off];
+        qc = qual.at(qoff, (uint32_t)off);
     } else {
         const RecView r = view_record(h, pay);
         off = resolve_offset(r, h.ign_start, h.ign_end, pos);
         if (off < 0) return 0u;
-        qc = qual[(size_t)r.qoff * 4u + (size_t)off];
+        qc = qual.at(r.qoff, (uint32_t)off);
         bw = r.b2[off >> 4];
         if ((r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u)) qc = 0u;   // allele not in ACGT: a call that is not counted (CH:220-221)
     }
@@ -530,7 +547,10 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
 // dropped; the others get the 10 distinct log-likelihoods, one per lane, SUMMED IN PILEUP ORDER in fp64
 // (CH:231-249) from the host-supplied tables — bit-identical to the Java doubles — and finalize_warp.
 constexpr int kRegRounds = 4;
-struct GenoCtx { const double* s_tab; const int* s_kmin; int max_qs, min_quality; bool may_skip, emit_all; };
+struct GenoCtx { const double* s_tab; const double* s_tab2; const int* s_kmin; int max_qs, min_quality; bool may_skip, emit_all; };
+// s_tab2[(q * 4 + b) * kTabLanes + lane]: what a counted base b of quality q adds to the log-likelihood lane `lane` owns
+// (CH:231-249); row kTabZeroRow is all zeros (a call that is not counted adds nothing)
+constexpr int kTabLanes = 10, kTabZeroRow = 31 * 4, kTab2Size = (kTabZeroRow + 1) * kTabLanes;
 
 __device__ __forceinline__ void count_round(uint32_t code, ColCounts& cc) {
     cc.depth += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));   // CH:210 totalCount: every call, whatever its quality or base
@@ -542,25 +562,19 @@ __device__ __forceinline__ void count_round(uint32_t code, ColCounts& cc) {
         cc.sn[b] += __popc(mb & ng);
     }
 }
-__device__ __forceinline__ void accumulate_round(uint32_t code, double& acc, int lane, int pa, int pb, const double* s_tab) {
-    unsigned cm = __ballot_sync(kFull, (code & kCodeCounted) != 0u);
-    while (cm) {
-        const int src = __ffs(cm) - 1;
-        cm &= cm - 1;
-        const uint32_t cj = __shfl_sync(kFull, code, src);
-        const int b = (int)(cj & 3u), q = (int)((cj >> 2) & 31u);
-        const double tb = s_tab[3 * q + 1];
-        const double tx = (lane < 4) ? s_tab[3 * q] : s_tab[3 * q + 2];
-        acc += (b == pa || b == pb) ? tx : tb;
-    }
+// The records of one round (one per lane), in lane order = pileup order: every log-likelihood lane adds its table value.
+// The sums stay sequential per likelihood (bit-identical to the reference's loop, CH:231-249); what is parallel is the
+// table index, computed once by the lane that owns the record.
+__device__ __forceinline__ void accumulate_round(uint32_t code, int n_in_round, double& acc, int lane, const double* s_tab2) {
+    const int row = (code & kCodeCounted) ? (int)(((code >> 2) & 31u) * 4u + (code & 3u)) : kTabZeroRow;
+    const int col = min(lane, kTabLanes - 1);
+    for (int k = 0; k < n_in_round; k++) acc += s_tab2[__shfl_sync(kFull, row, k) * kTabLanes + col];
 }
 
 // code_at(k) = the evidence code (lane_eval / entry_code) of the k-th record of the column, k in [0, n); 0 for k >= n
 template <class CodeAt>
 __device__ __forceinline__ void exact_column(CodeAt code_at, int n, const TileDev& d, const GenoCtx& g, int pos, int ref, bool ref_bad, int lane) {
-    // lanes 0-3 own L[i][i]; lanes 4-9 own L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3]
-    const int pa = (lane < 4) ? lane : ((lane < 7) ? 0 : ((lane < 9) ? 1 : 2));
-    const int pb = (lane < 4) ? lane : ((lane < 7) ? lane - 3 : ((lane < 9) ? lane - 5 : 3));
+    // lanes 0-3 own L[i][i]; lanes 4-9 own L[0][1], L[0][2], L[0][3], L[1][2], L[1][3], L[2][3] (see the table in k_genotype_columns)
     double acc = 0.0;
     ColCounts cc;
     for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
@@ -577,7 +591,7 @@ __device__ __forceinline__ void exact_column(CodeAt code_at, int n, const TileDe
         for (int base = 0; base < n; base += 32) {   // deep column: count and sum on the fly
             const uint32_t code = code_at(base + lane);
             count_round(code, cc);
-            accumulate_round(code, acc, lane, pa, pb, g.s_tab);
+            accumulate_round(code, min(32, n - base), acc, lane, g.s_tab2);
         }
     }
     if (g.emit_all && d.counts_dbg && lane == 0) {
@@ -593,7 +607,7 @@ __device__ __forceinline__ void exact_column(CodeAt code_at, int n, const TileDe
     if (g.may_skip && (m_alt == 0 || (m_alt < kSkipTable && k_ref >= g.s_kmin[m_alt]))) return;
     if (in_regs) {
 #pragma unroll
-        for (int r = 0; r < kRegRounds; r++) accumulate_round(codes[r], acc, lane, pa, pb, g.s_tab);
+        for (int r = 0; r < kRegRounds; r++) accumulate_round(codes[r], min(32, max(0, n - 32 * r)), acc, lane, g.s_tab2);
     }
     finalize_warp(acc, cc, lane, pos, ref, d, g.min_quality, g.s_tab[93], g.s_tab[94]);
 }
@@ -628,8 +642,8 @@ __device__ __forceinline__ bool resolve_entry(const ngsep_read_hdr& h, const uin
 }
 
 // The quality rules of CH.updateCounts on a resolved entry (the tail of lane_eval): the only global load is the quality byte.
-__device__ __forceinline__ uint32_t entry_code(const uint2 ent, const uint8_t* __restrict__ qual, int max_qs) {
-    uint32_t qc = qual[(size_t)ent.x * 4u + (size_t)(ent.y & 0xffffu)];
+__device__ __forceinline__ uint32_t entry_code(const uint2 ent, const QualView& qual, int max_qs) {
+    uint32_t qc = qual.at(ent.x, ent.y & 0xffffu);
     if (ent.y & kEntNotAcgt) qc = 0u;
     int q = (int)qc - 33;
     q = min(30, q);                                   // CH:91
@@ -638,28 +652,53 @@ __device__ __forceinline__ uint32_t entry_code(const uint2 ent, const uint8_t* _
     return kCodeCall | kCodeCounted | ((ent.y >> 16) & 3u) | ((uint32_t)q << 2) | ((ent.y & kEntNeg) ? kCodeNeg : 0u);
 }
 
+// Where the open columns of a window go: a per-window list in shared memory (published to the global list after the
+// window, with ONE global atomic, off the critical path) and, for the resolved entries, the piece of the global entry list
+// the warp has reserved (kEntChunk entries at a time, so that a global atomic with its round trip is rare).
+struct OpenSink {
+    uint4* s_openq;          // [kMaxOpen] list entries of this window
+    int* n_open;             // shared counter
+    uint2* s_chunk;          // this warp's piece of the entry list: x = next free entry, y = end
+};
+
+__device__ __forceinline__ void push_open(const OpenSink& sink, const ColumnQueue& cq, uint4 e) {   // one lane
+    const int slot = atomicAdd(sink.n_open, 1);
+    if (slot < kMaxOpen) sink.s_openq[slot] = e;
+    else {   // rare: the window's list is full
+        const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
+        if (g < cq.cap_open) cq.open[g] = e;
+    }
+}
+
 // An open column of the window (warp-cooperative): its record range, then — windows staged in one piece — one entry per
 // record that gives a call, in pileup order, so that k_genotype_columns only has to fetch quality bytes.  Columns of
 // windows too deep for a stage, and columns that do not fit the entry list, are handed over as a record range.
 template <bool kGlobal>
-__device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const ColumnQueue& cq, int tile, int rec0, int pos, int ref, int max_span, int max_back,
-                                                 bool span_capped, int lane) {
+__device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const ColumnQueue& cq, const OpenSink& sink, int tile, int rec0, int pos, int ref,
+                                                 int max_span, int max_back, bool span_capped, int lane) {
     const int i_lo = warp_lower_bound(R, pos - max_span + 1, lane);
     const int i_hi = warp_lower_bound(R, pos + max_back + 1, lane);   // first record that starts too far to the right
     if (i_hi <= i_lo) return;
     const uint32_t n_range = (uint32_t)(i_hi - i_lo);
-    bool as_range = kGlobal || span_capped || cq.cap_ent == 0u || n_range > kOpenCountMask;
+    bool as_range = kGlobal || span_capped || cq.cap_ent == 0u || n_range > kEntChunk;
     unsigned int ebase = 0u;
     if (!as_range) {
-        if (lane == 0) ebase = atomicAdd(&cq.ctr[3], n_range);
+        if (lane == 0) {
+            uint2 ch = *sink.s_chunk;
+            if (ch.y - ch.x < n_range) {   // the warp's piece is used up: reserve the next one
+                ch.x = atomicAdd(&cq.ctr[3], kEntChunk);
+                ch.y = ch.x + kEntChunk;
+                if (ch.x > cq.cap_ent || kEntChunk > cq.cap_ent - ch.x) ch.x = ch.y = 0xffffffffu;   // the list is full
+            }
+            ebase = ch.x;
+            if (ch.x != 0xffffffffu) ch.x += n_range;
+            *sink.s_chunk = ch;
+        }
         ebase = __shfl_sync(kFull, ebase, 0);
-        if (ebase > cq.cap_ent || n_range > cq.cap_ent - ebase) as_range = true;   // the list is full: the genotype kernel resolves the records itself
+        if (ebase == 0xffffffffu) as_range = true;   // the genotype kernel resolves the records itself
     }
     if (as_range) {
-        if (lane == 0) {
-            const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
-            if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)tile, (unsigned int)pos, (unsigned int)(rec0 + i_lo), span_capped ? kOpenSearch : min(n_range, kOpenSearch));
-        }
+        if (lane == 0) push_open(sink, cq, make_uint4((unsigned int)tile, (unsigned int)pos, (unsigned int)(rec0 + i_lo), span_capped ? kOpenSearch : min(n_range, kOpenSearch)));
         return;
     }
     if (!kGlobal) {
@@ -676,10 +715,7 @@ __device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const C
             if (ok) cq.ent[ebase + n_ent + (unsigned int)__popc(m & ((1u << lane) - 1u))] = ent;
             n_ent += (unsigned int)__popc(m);
         }
-        if (lane == 0 && n_ent > 0u) {
-            const unsigned int g = atomicAdd(&cq.ctr[2], 1u);
-            if (g < cq.cap_open) cq.open[g] = make_uint4((unsigned int)tile, (unsigned int)pos, ebase, kOpenEntries | ((uint32_t)ref << kOpenRefShift) | n_ent);
-        }
+        if (lane == 0 && n_ent > 0u) push_open(sink, cq, make_uint4((unsigned int)tile, (unsigned int)pos, ebase, kOpenEntries | ((uint32_t)ref << kOpenRefShift) | n_ent));
     }
 }
 
@@ -707,6 +743,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     uint32_t* s_cnt = (uint32_t*)(smem + lay.cnt);
     int* s_cov = (int*)(smem + lay.cov);
     uint32_t* s_list = (uint32_t*)(smem + lay.list);
+    uint2* s_chunk = (uint2*)(smem + lay.chunk);
     int* s_wtot = (int*)(smem + lay.wtot);
     int* s_wmax = (int*)(smem + lay.wmax);
     int2* s_rare = (int2*)(smem + lay.rare);
@@ -714,10 +751,13 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevParams& prm = *a.prm;
     const int T_lay = a.cfg.T_lay;
-    const int P = (T_lay + nthr - 1) / nthr;   // positions per thread in the prefix scan and in the clearing pass
+    const int P = (int)lay.cov_len / nthr;     // positions per thread in the prefix scan and in the clearing pass (cov_len is a multiple of the CTA)
+    const unsigned int warp_magic = 0xffffffffu / (unsigned int)(32 * P) + 1u;   // li / (32 P) == umulhi(li, warp_magic) for li < 2^16
     if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
     if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
-    for (int i = tid; i < T_lay + 1; i += nthr) { s_cnt[i] = 0u; s_cov[i] = 0; }
+    for (int i = tid; i < T_lay + 1; i += nthr) s_cnt[i] = 0u;
+    for (int i = tid; i < max((int)lay.cov_len, T_lay + 1); i += nthr) s_cov[i] = 0;
+    if (tid < nwarps) s_chunk[tid] = make_uint2(0u, 0u);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
     uint32_t phase_bits = 0u;   // bit s = parity the next wait on stage s must see
@@ -825,7 +865,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
         wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
         wc.s_cnt = s_cnt; wc.s_cov = s_cov; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
-        wc.proof = proofs && n_rec < 0xffff;   // (the 16-bit halves of s_cnt cannot overflow)
+        wc.proof = proofs;
 
         // ---- phase A: screen + coverage scan, one thread per record -------------------------------------------------
         // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
@@ -930,6 +970,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             __syncthreads();
             for (int ci = tid; ci < n_cand; ci += nthr) {
                 const int li = (int)s_list[ci];
+                s_cnt[li] = 0u;   // (nothing else clears s_cnt)
                 bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // SSVPL:298-305
                 if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
                 if (!closed) atomicOr(&s_bm[li >> 5], 1u << (li & 31));
@@ -969,39 +1010,43 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         } else if (n_cand > 0) {
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
-            // ---- phase B: prefix sums of the cover deltas: s_cov[p] + the totals of the warps in front = simple records whose
-            // callable range holds position p
+            // ---- phase B: prefix sums of the clean-cover deltas: s_cov[p] + the totals of the warps in front = simple records
+            // that hold a clean callable base at position p
             if (wc.proof) {
                 const int p0 = tid * P;
                 int tot = 0;
-                for (int i = 0; i < P; i++) if (p0 + i < T_lay) tot += s_cov[p0 + i];
+                for (int i = 0; i < P; i++) tot += s_cov[p0 + i];
                 int incl = tot;
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
                 int run = incl - tot;
-                for (int i = 0; i < P; i++) if (p0 + i < T_lay) { run += s_cov[p0 + i]; s_cov[p0 + i] = run; }
+                for (int i = 0; i < P; i++) { run += s_cov[p0 + i]; s_cov[p0 + i] = run; }
                 if (lane == 31) s_wtot[warp] = incl;
                 __syncthreads();   // ---- sync 3: prefix sums complete ------------------------------------------------------
             }
             // ---- phase C: the hom-ref proof, one thread per candidate.  With m = flagged bases (an upper
             // bound of the counted non-reference bases: simple records exactly, every aligned mismatch of the others) and
-            // k = cover - low-quality - flagged (the counted reference bases of the simple records: a lower bound of all of
-            // them), k >= k_min[m] proves the column homozygous reference and closes it.  What stays open is handed to
-            // k_genotype_columns by the warp, column by column.
+            // k = clean cover - flagged (a lower bound of the counted reference bases), k >= k_min[m] proves the column
+            // homozygous reference and closes it.  What stays open is handed to k_genotype_columns by the warp, column by column.
+            OpenSink sink;
+            sink.s_openq = (uint4*)(smem + lay.openq) + (it & 1) * kMaxOpen;
+            sink.n_open = &mset[M_NOPEN];
+            sink.s_chunk = &s_chunk[warp];
             for (int base = 0; base < n_cand; base += nthr) {
-                const int ci = base + tid;
+                const int ci = base + lane * nwarps + warp;   // neighbouring candidates go to different warps: the open columns (a few
+                                                              // per window, each a warp-serial piece of work) spread over the CTA
                 bool open = false;
                 int li = 0;
                 if (ci < n_cand) {
                     li = (int)s_list[ci];
+                    const int m_up = (int)s_cnt[li];
+                    s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
                     open = ((s_refn[li >> 5] >> (li & 31)) & 1u) == 0u;                                           // VD:101-107
                     if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;                      // SSVPL:198
-                    if (open && wc.proof) {
-                        const uint32_t c = s_cnt[li];
-                        const int m_up = (int)(c & 0xffffu), lowq = (int)(c >> 16);
+                    if (open && wc.proof && m_up < kSkipTable) {
                         int cover = s_cov[li];
-                        const int ow = li / (32 * P);
+                        const int ow = (int)__umulhi((unsigned int)li, warp_magic);   // the warp that scanned position li
                         for (int k = 0; k < ow; k++) cover += s_wtot[k];
-                        if (m_up < kSkipTable && cover - lowq - m_up >= s_kmin[m_up]) open = false;
+                        if (cover - m_up >= s_kmin[m_up]) open = false;
                     }
                 }
                 unsigned om = __ballot_sync(kFull, open);
@@ -1013,11 +1058,11 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                     const int ref = (int)((wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
                     if (single) {
                         Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                        emit_open_column<false>(R, a.cq, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped || multi, lane);
+                        emit_open_column<false>(R, a.cq, sink, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped || multi, lane);
                     } else {
                         const TileDev& d = a.tiles[wr.tile];
                         Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                        emit_open_column<true>(R, a.cq, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped, lane);
+                        emit_open_column<true>(R, a.cq, sink, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped, lane);
                     }
                 }
             }
@@ -1039,11 +1084,26 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 }
             }
         }
-        // the per-position arrays go back to zero for the next window
-        if (!emit_all) {
+        // the cover array goes back to zero for the next window (s_cnt was cleared candidate by candidate)
+        if (proofs) {
             const int p0 = tid * P;
-            for (int i = 0; i < P; i++) if (p0 + i < T_lay) { s_cnt[p0 + i] = 0u; s_cov[p0 + i] = 0; }
-            if (tid == 0) { s_cnt[T_lay] = 0u; s_cov[T_lay] = 0; }
+            for (int i = 0; i < P; i++) s_cov[p0 + i] = 0;
+            if (tid == 0) s_cov[T_lay] = 0;   // the sink of the deltas at the window's end (inside the scanned range when T_lay is not a multiple of the CTA)
+        } else if (multi && !emit_all) {
+            for (int i = tid; i < ((T_lay + 31) >> 5); i += nthr) s_cov[i] = 0;   // (the sample axis keeps its candidate bitmap here)
+        }
+        // warp 1 hands the window's open columns to the global list: ONE global atomic per window, its round trip hidden behind
+        // the wait for the next window (the list and the counters are per window parity)
+        if (warp == 1 % nwarps) {
+            const int n_open = min(mset[M_NOPEN], kMaxOpen);
+            if (n_open > 0) {
+                const uint4* s_openq = (const uint4*)(smem + lay.openq) + (it & 1) * kMaxOpen;
+                unsigned int gbase = 0u;
+                if (lane == 0) gbase = atomicAdd(&a.cq.ctr[2], (unsigned int)n_open);
+                gbase = __shfl_sync(kFull, gbase, 0);
+                for (int i = lane; i < n_open; i += 32)
+                    if (gbase + i < a.cq.cap_open) a.cq.open[gbase + i] = s_openq[i];
+            }
         }
 
         int uncovered = mset[M_UNC];
@@ -1088,14 +1148,26 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
 template <int kMinBlocks>
 __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab[96];
+    __shared__ double s_tab2[kTab2Size];
     __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
     for (int i = threadIdx.x; i < NGSEP_N_TABLES; i += blockDim.x) s_tab[i] = prm.tables[i];
+    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) {
+        // lane l owns L[pa][pb]: lanes 0-3 the homozygous L[l][l], lanes 4-9 the pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3).
+        // A counted base b of quality q adds a_q to the homozygous likelihood of b, c_q to the pairs that hold b, b_q to the rest
+        // (CH:231-249 with f == g == 250: the matrix is symmetric).
+        const int l = i % kTabLanes, row = i / kTabLanes, q = row >> 2, b = row & 3;
+        const int pa = (l < 4) ? l : ((l < 7) ? 0 : ((l < 9) ? 1 : 2));
+        const int pb = (l < 4) ? l : ((l < 7) ? l - 3 : ((l < 9) ? l - 5 : 3));
+        double v = 0.0;
+        if (row < kTabZeroRow) v = (b == pa || b == pb) ? ((l < 4) ? prm.tables[3 * q] : prm.tables[3 * q + 2]) : prm.tables[3 * q + 1];
+        s_tab2[i] = v;
+    }
     if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
     __syncthreads();
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     GenoCtx g;
-    g.s_tab = s_tab; g.s_kmin = s_kmin; g.max_qs = prm.max_base_qs; g.min_quality = prm.min_quality;
+    g.s_tab = s_tab; g.s_tab2 = s_tab2; g.s_kmin = s_kmin; g.max_qs = prm.max_base_qs; g.min_quality = prm.min_quality;
     g.emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     g.may_skip = prm.fast_homref != 0;
     const int lane = threadIdx.x & 31;
@@ -1110,7 +1182,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
             // callable): one coalesced entry load and one quality byte per record
             const int n = (int)(oc.w & kOpenCountMask);
             const uint2* ent = cq.ent + oc.z;
-            const uint8_t* __restrict__ qual = d.qual;
+            const QualView qual(d);
             const int max_qs = g.max_qs;
             exact_column([&](int k) { return (k < n) ? entry_code(ent[k], qual, max_qs) : 0u; }, n, d, g, pos, (int)((oc.w >> kOpenRefShift) & 3u), false, lane);
             continue;
@@ -1125,7 +1197,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
             i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
             i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);   // first record that starts too far to the right
         }
-        const uint8_t* __restrict__ qual = d.qual;
+        const QualView qual(d);
         const int max_qs = g.max_qs;
         exact_column([&](int k) {
             if (i_lo + k >= i_hi) return 0u;
@@ -1269,6 +1341,7 @@ __global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(co
         const bool ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
         const int ref = (int)((d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u);
         Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        const QualView qv(d);
         int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
         if (oc.w >= kOpenSearch) {
             i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
@@ -1300,7 +1373,7 @@ __global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(co
                         code[u] = 0u;
                         if (ka + u < kb) {
                             const ngsep_read_hdr h = R.header((int)__ldg(lst + ka + u));
-                            code[u] = lane_eval(h, R.payload(h), d.qual, pos, max_qs);
+                            code[u] = lane_eval(h, R.payload(h), qv, pos, max_qs);
                         }
                     }
 #pragma unroll
@@ -1576,7 +1649,7 @@ void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStre
 // the error when it fetches the tile.  The packer's NGSEP_M_SIMPLE promise is verified here too: a record whose flag is
 // not backed by its payload loses the flag (and goes through the general path, which is always correct).
 __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict__ payload, int n, unsigned long long n_words, unsigned long long n_qual,
-                                unsigned int pay_cap_words, unsigned int* report) {
+                                unsigned int qual_bits, unsigned int pay_cap_words, unsigned int* report) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int err = 0u, L = 0u;
     if (i < n) {
@@ -1592,7 +1665,7 @@ __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict_
             if (body > next - h.off) err |= 8u;
             else {
                 const unsigned long long qoff = payload[h.off + body - 1ull];
-                if (qoff * 4ull + L > n_qual) err |= 8u;
+                if (qoff * 4ull + ((unsigned long long)L * qual_bits + 7ull) / 8ull > n_qual) err |= 8u;
             }
         }
         if (!err && (h.meta & NGSEP_M_SIMPLE)) {
@@ -1607,9 +1680,9 @@ __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict_
     }
 }
 
-void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int pay_cap_words,
-                          unsigned int* report, cudaStream_t s) {
-    if (n > 0) k_check_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n, n_words, n_qual, pay_cap_words, report);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int qual_bits,
+                          unsigned int pay_cap_words, unsigned int* report, cudaStream_t s) {
+    if (n > 0) k_check_headers<<<(n + 255) / 256, 256, 0, s>>>(hdr, payload, n, n_words, n_qual, qual_bits, pay_cap_words, report);
 }
 
 // The kernel is compiled for two CTA sizes and three register budgets each; the context picks one.

@@ -45,7 +45,9 @@ struct TileDev {
     const uint32_t* goff;        //                        [n_groups + 2] list offsets into gidx; list n_groups = records outside every sample
     const uint32_t* gblk;        //                        [n_groups + 1][n_gblk + 1] list position of the first record index >= b * 256
     int n_gblk;
-    const uint8_t* qual;         // phred+33 bytes, addressed through the records' qoff (only k_genotype_columns reads them)
+    const uint8_t* qual;         // phred+33 bytes (or qual_bits-bit codes into qual_dict), addressed through the records' qoff (only the genotype kernels read them)
+    uint32_t qual_bits;          // 8 = bytes, 2 / 4 = codes
+    uint32_t qual_dict[4];       // code -> phred+33 byte, four codes per word
     int n_reads, max_span, max_back;
     int tile_first, tile_last, seq_idx;
     const uint32_t* ref2;        // 2 bits/base, base idx i (0-based) at bits 2*(i%16) of word i/16; 64 B of zero padding in front
@@ -101,8 +103,8 @@ struct LaunchCfg {
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
 int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
-void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int pay_cap_words,
-                          unsigned int* report, cudaStream_t s);
+void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int qual_bits,
+                          unsigned int pay_cap_words, unsigned int* report, cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);

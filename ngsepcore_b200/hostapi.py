@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
 EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_msvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
            "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free",
-           "ngsep_host_merge_order"]
+           "ngsep_host_merge_order", "ngsep_host_pack_quality"]
 
 
 class HostBatch(C.Structure):
@@ -34,7 +34,8 @@ class DetectorOptions(C.Structure):
                 ("max_alns_per_start_pos", C.c_int32), ("process_non_unique_primary", C.c_int32), ("process_secondary", C.c_int32),
                 ("ignore5", C.c_int32), ("ignore3", C.c_int32), ("het_rate", C.c_double), ("het_rate_set", C.c_int32),
                 ("max_base_qs", C.c_int32), ("min_quality", C.c_int32), ("call_embedded_snvs", C.c_int32), ("calc_strand_bias", C.c_int32),
-                ("device", C.c_int32), ("tile_len", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("host_only", C.c_int32)]
+                ("device", C.c_int32), ("tile_len", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("host_only", C.c_int32),
+                ("synchronous", C.c_int32)]
 
 
 class RunStats(C.Structure):
@@ -72,6 +73,7 @@ def load_library() -> C.CDLL:
                                     C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                     C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
     lib.ngsep_host_free.argtypes = [C.c_void_p]
+    lib.ngsep_host_pack_quality.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
     lib.ngsep_host_merge_order.argtypes = [C.c_int, C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_int64)]
     _lib = lib
@@ -85,6 +87,38 @@ def _host_batch(b: AlignmentBatch):
             np.ascontiguousarray(b.bases, np.uint8), np.ascontiguousarray(b.quals, np.uint8)]
     hb = HostBatch(b.n, *[a.ctypes.data for a in keep], None)
     return hb, keep
+
+
+def last_pack_quality():
+    """(bits, dict16) of the quality array the last pack call of this thread produced (ngsep_tile.qual_bits / qual_dict)."""
+    bits = C.c_uint32(0)
+    d = (C.c_uint8 * 16)()
+    load_library().ngsep_host_pack_quality(C.byref(bits), d)
+    return int(bits.value), bytes(d)
+
+
+def decode_quality(qual: np.ndarray, hdr: np.ndarray, payload: np.ndarray, quality) -> np.ndarray:
+    """The phred+33 bytes a packed quality array stands for, in the layout of the 8-bit mode (L bytes per read padded to 4 with
+    '!'; reads in order of their first record) — for tests that compare packers."""
+    bits, qdict = quality
+    if bits == 8:
+        return qual
+    lut = np.frombuffer(qdict, np.uint8)
+    out = []
+    seen = set()
+    nxt = np.concatenate([hdr["off"][1:], [payload.size]]).astype(np.int64)
+    per = 8 // bits
+    for i in range(hdr.shape[0]):
+        qoff = int(payload[nxt[i] - 1])
+        if qoff in seen:
+            continue
+        seen.add(qoff)
+        L = int(hdr["meta"][i] & 0xFFFF)
+        raw = qual[qoff * 4: qoff * 4 + (L * bits + 7) // 8]
+        codes = np.stack([(raw >> (bits * k)) & ((1 << bits) - 1) for k in range(per)], axis=1).reshape(-1)[:L]
+        run = lut[codes]
+        out.append(np.concatenate([run, np.full((-L) % 4, ord("!"), np.uint8)]))
+    return np.concatenate(out) if out else np.zeros(0, np.uint8)
 
 
 def _take(ptr, n, dtype, lib):
@@ -108,6 +142,7 @@ def pack_sequence(batch: AlignmentBatch, seq_idx: int, min_mq: int = 20, max_aln
                              C.byref(n_reads), C.byref(n_words), C.byref(n_qual), C.byref(span), C.byref(bases))
     if rc != 0:
         raise NgsepError(f"ngsep_host_pack failed ({rc})")
+    pack_sequence.quality = last_pack_quality()      # how the returned quality array is coded (see decode_quality)
     return (_take(hdr_p, n_reads.value, HDR_DTYPE, lib), _take(pay_p, n_words.value, np.uint32, lib), _take(q_p, n_qual.value, np.uint8, lib),
             span.value, bases.value)
 
@@ -168,7 +203,8 @@ class Detector:
     def __init__(self, sampleId: str = "Sample", ploidy: int = 2, psp: bool = False, minMQ: int = 20, querySeq: str | None = None,
                  first: int = 0, last: int = 1000000000, ignoreLowerCaseRef: bool = False, maxAlnsPerStartPos: int = 5, p: bool = False,
                  s: bool = False, ignore5: int = 0, ignore3: int = 0, h: float | None = None, maxBaseQS: int = 30, minQuality: int = 40,
-                 embeddedSNVs: bool = False, csb: bool = False, device: int = 0, tile_len: int = 0, shard: int = 0, n_shards: int = 1, host_only: bool = False):
+                 embeddedSNVs: bool = False, csb: bool = False, device: int = 0, tile_len: int = 0, shard: int = 0, n_shards: int = 1, host_only: bool = False,
+                 synchronous: bool = False):
         self.lib = load_library()
         o = DetectorOptions()
         self.lib.ngsep_detector_options_default(C.byref(o))
@@ -182,6 +218,7 @@ class Detector:
             o.het_rate, o.het_rate_set = h, 1
         o.max_base_qs, o.min_quality, o.call_embedded_snvs, o.calc_strand_bias = maxBaseQS, minQuality, int(embeddedSNVs), int(csb)
         o.device, o.tile_len, o.shard, o.n_shards, o.host_only = device, tile_len, shard, n_shards, int(host_only)
+        o.synchronous = int(synchronous)
         self.h = C.c_void_p()
         self._create(o)
         self._keep = []
@@ -222,7 +259,7 @@ class Detector:
             raise NgsepError(f"ngsep_ssvd_pack failed ({rc}): {self.lib.ngsep_ssvd_error(self.h).decode()}")
         return dict(hdr=_take(hdr_p, n_reads.value, HDR_DTYPE, self.lib), payload=_take(pay_p, n_words.value, np.uint32, self.lib),
                     qual=_take(q_p, n_qual.value, np.uint8, self.lib), max_span=span.value, max_back=back.value, first=tf.value, last=tl.value,
-                    aligned_bases=bases.value)
+                    aligned_bases=bases.value, quality=last_pack_quality())
 
     def stats(self) -> RunStats:
         s = RunStats()

@@ -233,7 +233,7 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
              frag_mean: float = 350.0, frag_sd: float = 35.0, low_mapq_frac: float = 0.02, n_frac: float = 0.0,
              lower_frac: float = 0.0, indel_jitter: float = 0.3, ungapped_end_bp: int = 6, n_read_groups: int = 1,
              genome=None, starts_per_pos_cap: int | None = None, variants_override: dict | None = None,
-             tag_sites: dict | None = None):
+             tag_sites: dict | None = None, qual_vals=None):
     """Returns (genome dict name->uint8 ASCII, AlignmentBatch, truth dict name->[Variant]).
 
     variants_override: name -> [Variant] (each with ``_hap`` set) used instead of planting (population runs).
@@ -245,8 +245,14 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
         genome = make_genome(contigs, gc=gc, seed=seeds[0], n_frac=n_frac, lower_frac=lower_frac)
     rng_v = np.random.default_rng(seeds[1])
     rng_r = np.random.default_rng(seeds[2])
-    qual_vals = np.array([40, 30, 20, 10, 2], np.uint8) + 33
-    qual_p = np.array([0.70, 0.20, 0.07, 0.02, 0.01])
+    if qual_vals is None:
+        qual_vals = np.array([40, 30, 20, 10, 2], np.uint8) + 33
+        qual_p = np.array([0.70, 0.20, 0.07, 0.02, 0.01])
+    else:       # another quality alphabet (phred values): the higher the value the more frequent, 1 % at the lowest one
+        qv = np.sort(np.array(qual_vals, np.int64))
+        w = np.arange(1, len(qv) + 1, dtype=np.float64) ** 2
+        w[0] = 0.01 * w.sum()
+        qual_vals, qual_p = (qv + 33).astype(np.uint8), w / w.sum()
     truth = {}
     per_contig = []
     for ci, (name, length) in enumerate(contigs):
@@ -350,7 +356,7 @@ def simulate(contigs=None, depth: float = 30.0, read_len: int = 100, seeds=(1001
             new = cur.copy()
             new[okb] = _ACGT[(ci4[okb] + sub[okb]) % 4]
             bases[err] = new
-        quals = qual_vals[rng_r.choice(5, size=(n, read_len), p=qual_p)]
+        quals = qual_vals[rng_r.choice(len(qual_vals), size=(n, read_len), p=qual_p)]
         mapq = np.where(rng_r.random(n) < low_mapq_frac, 10, 60).astype(np.uint8)
         rg = (rng_r.integers(0, n_read_groups, size=n)).astype(np.int16) if n_read_groups > 0 else np.full(n, -1, np.int16)
         order = np.argsort(first, kind="stable")

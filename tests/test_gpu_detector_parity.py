@@ -90,3 +90,46 @@ def test_cli_sam_to_vcf(oracle, tmp_path):
     # error behaviour of the reference module: missing required parameter / unknown option
     assert subprocess.call([cli, "SingleSampleVariantsDetector", "-r", fa, "-o", out], stderr=subprocess.DEVNULL) == 2
     assert subprocess.call([cli, "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-bogus"], stderr=subprocess.DEVNULL) == 1
+
+
+def test_pipelined_run_equals_synchronous_run(oracle, tmp_path):
+    """The product path — sequences planned in parallel on the host threads, region tiles packed into page-locked ring buffers
+    with up to three tiles in flight — gives the bytes of the synchronous path (one tile at a time from pageable buffers, one host
+    thread) and of the oracle; a second run of the same detector object (buffers reused) as well."""
+    genome, batch, fa, sam = _inputs(tmp_path, [("chrA", 420000), ("chrB", 180000), ("chrC", 90000), ("chrD", 40000)], depth=30, seeds=(191, 192, 193),
+                                     indel_rate=5e-4)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam)
+    sync = hostapi.Detector(tile_len=50000, synchronous=True)
+    sync.set_genome(genome)
+    ref = sync.run(batch)
+    assert ref == want
+    for tile_len in (50000, 0):
+        det = hostapi.Detector(tile_len=tile_len)
+        det.set_genome(genome)
+        assert det.run(batch) == want
+        s1 = det.stats()
+        assert det.run(batch) == want
+        s2 = det.stats()
+        assert s1.covered_positions == gp and s2.covered_positions == 2 * gp
+        assert s1.tiles == (16 if tile_len else 4)
+
+
+@pytest.mark.parametrize("alphabet,bits", [((2, 11, 15, 22, 27, 33, 37, 40), 4), (tuple(range(2, 42)), 8), (None, 2)])
+def test_quality_code_modes_give_the_oracle_records(oracle, tmp_path, monkeypatch, alphabet, bits):
+    """Qualities travel host -> device as 2- / 4-bit codes when the tile's qualities fall into at most 4 / 16 classes the path can
+    tell apart (ngsep_tile.qual_bits), as bytes otherwise: the records are the oracle's in every mode, and forcing bytes
+    (NGSEP_QUAL_BITS=8) changes nothing."""
+    kw = {} if alphabet is None else dict(qual_vals=alphabet)
+    genome, batch, fa, sam = _inputs(tmp_path, [("chrA", 150000)], depth=25, seeds=(201, 202, 203), indel_rate=5e-4, **kw)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam, args=("-maxBaseQS", "27"))
+    monkeypatch.delenv("NGSEP_QUAL_BITS", raising=False)
+    det = hostapi.Detector(maxBaseQS=27)
+    det.set_genome(genome)
+    assert det.pack(batch, 0)["quality"][0] == bits
+    assert det.run(batch) == want
+    monkeypatch.setenv("NGSEP_QUAL_BITS", "8")
+    raw = hostapi.Detector(maxBaseQS=27)
+    raw.set_genome(genome)
+    assert raw.pack(batch, 0)["quality"][0] == 8
+    assert raw.run(batch) == want
+    assert len(_body(want)) > 100

@@ -18,17 +18,53 @@ def test_host_symbols():
         assert hasattr(lib, name)
 
 
-def test_cpp_packer_equals_numpy_packer():
+def test_cpp_packer_equals_numpy_packer(monkeypatch):
     genome, batch, _ = simulate.simulate(contigs=[("a", 30000), ("b", 20000)], depth=12, seeds=(3, 4, 5), n_frac=0.02, low_mapq_frac=0.1)
+    monkeypatch.setenv("NGSEP_QUAL_BITS", "8")       # quality bytes as they are: the layout of the numpy packer
     for ci in range(2):
         idx = pypack.admit(batch, max_alns_per_start=2)
         idx = idx[batch.seq_idx[idx] == ci]
         h1, p1, q1, s1 = pypack.pack_tile(batch, idx, ignore5=2, ignore3=4)
         h2, p2, q2, s2, nb = hostapi.pack_sequence(batch, ci, max_alns_per_start=2, ignore5=2, ignore3=4)
+        assert hostapi.pack_sequence.quality[0] == 8
         assert s1 == s2 and nb == int((h1["meta"] & 0xFFFF).sum())
         assert np.array_equal(h1, h2)
         assert np.array_equal(p1, p2)
         assert np.array_equal(q1, q2)
+
+
+def _quality_class(q):      # what the path can tell apart: every q <= 3 alike (CH:214), min(30, q) otherwise (CH:91)
+    v = q.astype(np.int32) - 33
+    return np.where(v <= 3, 0, np.minimum(v, 30))
+
+
+@pytest.mark.parametrize("alphabet,bits", [(None, 2), ((2, 11, 15, 22, 27, 33, 37, 40), 4), (tuple(range(2, 42)), 8)])
+def test_quality_dictionary_modes(monkeypatch, alphabet, bits):
+    """ngsep_tile.qual_bits: a tile whose qualities fall into at most 4 / 16 classes travels as 2- / 4-bit codes.  Decoding the
+    packed array through the dictionary gives, base by base, the class of the original quality; everything else of the tile
+    (headers, CIGARs, bases, masks) is what the 8-bit packing produces."""
+    monkeypatch.delenv("NGSEP_QUAL_BITS", raising=False)
+    kw = {} if alphabet is None else dict(qual_vals=alphabet)
+    genome, batch, _ = simulate.simulate(contigs=[("a", 40000)], depth=15, seeds=(13, 14, 15), n_frac=0.01, read_len=101, **kw)
+    h2, p2, q2, s2, nb = hostapi.pack_sequence(batch, 0)
+    quality = hostapi.pack_sequence.quality
+    assert quality[0] == bits
+    monkeypatch.setenv("NGSEP_QUAL_BITS", "8")
+    h8, p8, q8, s8, _ = hostapi.pack_sequence(batch, 0)
+    assert np.array_equal(h2, h8) and s2 == s8
+    nxt = np.concatenate([h2["off"][1:], [p2.size]]).astype(np.int64) - 1       # the qoff word of every record
+    mask = np.ones(p2.size, bool)
+    mask[nxt] = False
+    assert np.array_equal(p2[mask], p8[mask])
+    if bits == 8:
+        assert np.array_equal(q2, q8) and np.array_equal(p2, p8)
+        return
+    assert q2.size * 8 <= q8.size * bits + 4 * 8 * h2.shape[0]                   # the array really shrank (runs are padded to 4 bytes)
+    dec = hostapi.decode_quality(q2, h2, p2, quality)
+    assert dec.size == q8.size
+    L = 101
+    rows = dec.reshape(-1, 104)[:, :L], q8.reshape(-1, 104)[:, :L]
+    assert np.array_equal(_quality_class(rows[0]), _quality_class(rows[1]))
 
 
 @pytest.mark.parametrize("seed,kw", [
