@@ -360,6 +360,14 @@ def cpu_baseline(genome, batch, names, max_bp: int = 1_500_000):
             "sample": f"first {len(take)} sequences of the workload ({tot} bp, {sub.n} records), C++ restatement of NGSEP 4.3.2 (no JVM in the image)"}
 
 
+def _ref_write(job):
+    """Worker: SAM text of one region's records (untimed setup; forked, the batch is inherited)."""
+    from ngsepcore_b200 import simulate
+    sam, keep = job
+    simulate.write_sam(sam, _REF["batch"].select(keep))
+    return sam
+
+
 def _ref_worker(job):
     fa, sam, seq, first, last = job
     from tests import oracle_util as ou
@@ -368,36 +376,47 @@ def _ref_worker(job):
     return gp, sec
 
 
+_REF = {}
+
+
 def run_reference(args):
-    """The reference's CPU implementation of the path on all host cores.  The reference's only parallel mode is region
-    splitting (-querySeq/-first/-last): the sample is cut into one region per core."""
+    """The reference's CPU implementation of the path on all host cores, over the WHOLE workload of the CUDA arm (same
+    simulated genome and reads).  The reference's only parallel mode is region splitting (-querySeq/-first/-last, SURVEY.md
+    fact 0.3): the genome is cut into about two regions per core, one process each.  Timed: SAM text parsing, admission, the
+    per-position pileup walk with the realigner and both callers, VCF text — what `java -jar NGSEPcore.jar
+    SingleSampleVariantsDetector` does between reading its input and writing its output."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as ge
-    ge.build()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])      # the checker only: no CUDA library is loaded in this arm
     from ngsepcore_b200 import simulate
     genome, batch, _ = _workload(0, args.depth, args.scale)
     names = list(genome)
     cores = max(1, min(os.cpu_count() or 1, 64))
-    sub, take, tot = _sample_batch(batch, names, args.reference_sample_bp)
+    total = sum(batch.contig_lengths)
+    sample_bp = min(total, args.reference_sample_bp)
     d = tempfile.mkdtemp(prefix="ngsep_ref_")
     fa = os.path.join(d, "r.fa")
     simulate.write_fasta(fa, genome)
-    # one region per core, balanced by reference length; each worker reads only the records that can reach its region
-    per = max(20000, -(-tot // cores))
-    jobs = []
-    for ci in take:
-        L = batch.contig_lengths[ci]
-        sel = np.nonzero(sub.seq_idx == ci)[0]
-        first_arr = sub.first[sel]
+    # about two regions per core, balanced by reference length; each worker reads only the records that can reach its region
+    per = max(20000, -(-sample_bp // (2 * cores)))
+    jobs, writes, taken, n_records = [], [], 0, 0
+    for ci, L in enumerate(batch.contig_lengths):
+        if taken >= sample_bp:
+            break
+        lo, hi = np.searchsorted(batch.seq_idx, ci, "left"), np.searchsorted(batch.seq_idx, ci, "right")
+        first_arr = batch.first[lo:hi]
         for f in range(1, L + 1, per):
             l = min(L, f + per - 1)
-            keep = sel[(first_arr >= f - 1000) & (first_arr <= l)]
+            keep = lo + np.nonzero((first_arr >= f - 1000) & (first_arr <= l))[0]
             sam = os.path.join(d, f"{names[ci]}_{f}.sam")
-            simulate.write_sam(sam, sub.select(keep))
+            writes.append((sam, keep))
             jobs.append((fa, sam, names[ci], f, l))
+            n_records += len(keep)
+        taken += L
+    _REF["batch"] = batch
     pool = mp.get_context("fork").Pool(cores)
+    pool.map(_ref_write, writes, chunksize=1)
     times, positions = [], 0
     for it in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -407,12 +426,14 @@ def run_reference(args):
             times.append(dt)
             positions = sum(r[0] for r in res)
     pool.close()
-    total = sum(times)
-    value = positions * len(times) / total
-    sample = f"first {len(take)} sequences of the workload ({tot} bp, {sub.n} records) cut into {len(jobs)} regions, oracle port on {cores} processes"
+    total_s = sum(times)
+    value = positions * len(times) / total_s
+    whole = taken >= total
+    sample = (("the whole workload" if whole else f"the first {taken} bp of the workload") +
+              f" ({n_records} records incl. lead-ins) cut into {len(jobs)} regions, oracle port (C++ restatement of NGSEP 4.3.2; no JVM in the image) on {cores} processes")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "depth": args.depth, "sample": sample},
+            "ms_per_step": total_s / len(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "depth": args.depth, "genome_bp": int(total), "reads": int(batch.n), "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -429,7 +450,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the informational whole-detector run")
     ap.add_argument("--quality-in-place", action="store_true", help="e2e: leave page-locked quality buffers on the host (NGSEP_F_QUALITY_IN_PLACE)")
-    ap.add_argument("--reference-sample-bp", type=int, default=4_000_000)
+    ap.add_argument("--reference-sample-bp", type=int, default=1 << 40, help="reference arm: reference bases per step (default: the whole workload)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -58,6 +58,7 @@ typedef struct ngsep_detector_options {
     int32_t host_only;              /* test hook: admission + event pre-pass only; output holds just the host-made indel/STR records */
     int32_t synchronous;            /* test hook: one tile at a time from pageable buffers, host stages on the calling thread (default: sequences planned
                                        in parallel, tiles pipelined through page-locked ring buffers) */
+    int32_t n_devices;              /* GPUs device .. device + n_devices - 1: region tiles are dealt to them in turn (0 / 1 = one GPU) */
 } ngsep_detector_options;
 
 typedef struct ngsep_run_stats {

@@ -30,16 +30,33 @@ GpuSingleSampleVariantsDetector::GpuSingleSampleVariantsDetector(const DetectorO
 }
 
 GpuSingleSampleVariantsDetector::~GpuSingleSampleVariantsDetector() {
-    if (ctx_) ngsep_ctx_destroy(ctx_);
+    rings_.clear();   // page-locked buffers go first (they unregister themselves)
+    for (void* c : ctxs_) if (c) ngsep_ctx_destroy(c);
 }
 
 void GpuSingleSampleVariantsDetector::set_genome(const Genome* g) {
     genome_ = g;
-    ref_uploaded_.assign(g->seqs.size(), false);
+    ref_uploaded_.assign((size_t)std::max(1, opt_.n_devices), std::vector<bool>(g->seqs.size(), false));
 }
 
 int GpuSingleSampleVariantsDetector::ensure_ctx() {
-    if (ctx_) return NGSEP_OK;
+    if (!ctxs_.empty()) return NGSEP_OK;
+    const int n = std::max(1, opt_.n_devices);
+    for (int k = 0; k < n; k++) {
+        void* c = nullptr;
+        int rc = create_ctx(opt_.device + k, &c);
+        if (rc != NGSEP_OK) { for (void* x : ctxs_) ngsep_ctx_destroy(x); ctxs_.clear(); ctx_ = nullptr; return rc; }
+        ctxs_.push_back(c);
+    }
+    ctx_ = ctxs_[0];
+    rings_.resize((size_t)n);
+    for (auto& r : rings_) r.resize((size_t)kHostRing);
+    if (ref_uploaded_.size() != (size_t)n && genome_) ref_uploaded_.assign((size_t)n, std::vector<bool>(genome_->seqs.size(), false));
+    return NGSEP_OK;
+}
+
+int GpuSingleSampleVariantsDetector::create_ctx(int device, void** out) {
+    void* ctx_ = nullptr;   // (local: the members are set by ensure_ctx)
     ngsep_params p{};
     p.max_base_qs = opt_.max_base_qs;
     p.min_quality = opt_.min_quality;
@@ -49,8 +66,9 @@ int GpuSingleSampleVariantsDetector::ensure_ctx() {
     p.n_samples = 1;
     double tables[NGSEP_N_TABLES];
     host_tables(opt_.het_rate, tables);
-    int rc = ngsep_ctx_create(opt_.device, &p, tables, NGSEP_N_TABLES, &ctx_);
+    int rc = ngsep_ctx_create(device, &p, tables, NGSEP_N_TABLES, &ctx_);
     if (rc != NGSEP_OK) { err_ = ngsep_last_error(nullptr); ctx_ = nullptr; }
+    *out = ctx_;
     return rc;
 }
 
@@ -124,18 +142,20 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     return NGSEP_OK;
 }
 
-// Stage 3.  Tiles of all sequences, in order, through the ring of page-locked host buffers: pack tile k (host threads) while
-// the device still works on tiles k-1, k-2, k-3 (ngsep_tile_submit only enqueues copies and kernels).
+// Stage 3.  Tiles of all sequences, in order, through the rings of page-locked host buffers: pack tile k (host threads) while
+// the devices still work on the tiles before it (ngsep_tile_submit only enqueues copies and kernels).  With several devices
+// the tiles are dealt to them in turn; every device has its own context, ring and tiles in flight, and the calls of all of
+// them meet again in the per-sequence merge (no collective: SURVEY 8e).
 int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
-    struct InFlight { SeqJob* job; };
-    std::deque<InFlight> q;
-    const int max_in_flight = opt_.synchronous ? 1 : kHostRing - 1;
-    int slot = 0;
-    auto fetch_oldest = [&]() -> int {
+    const size_t n_dev = ctxs_.size();
+    std::vector<std::deque<SeqJob*>> q(n_dev);
+    std::vector<int> slot(n_dev, 0);
+    const size_t max_in_flight = opt_.synchronous ? 1 : (size_t)kHostRing - 1;
+    auto fetch_oldest = [&](size_t dev) -> int {
         double td = now_s();
         ngsep_tile_stats ts{};
-        int rc = fetch_tile(*q.front().job, ts);
-        q.pop_front();
+        int rc = fetch_tile(ctxs_[dev], *q[dev].front(), ts);
+        q[dev].pop_front();
         if (rc != NGSEP_OK) return rc;
         stats_.device_s += now_s() - td;
         stats_.covered_positions += ts.covered_positions;
@@ -146,16 +166,14 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         stats_.tiles++;
         return NGSEP_OK;
     };
-    auto drain = [&]() { while (!q.empty()) { ngsep_tile_stats ts{}; fetch_tile(*q.front().job, ts); q.pop_front(); } };   // after an error: nothing may stay in flight
+    auto drain = [&]() {   // after an error: nothing may stay in flight
+        for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { ngsep_tile_stats ts{}; fetch_tile(ctxs_[dev], *q[dev].front(), ts); q[dev].pop_front(); }
+    };
+    size_t dealt = 0;
     for (auto& job : jobs) {
         SeqPlan& plan = job.plan;
         if (plan.reads.empty()) continue;
         const int seq = job.seq;
-        if (!ref_uploaded_[seq]) {
-            int rc = ngsep_ref_upload(ctx_, seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); drain(); return rc; }
-            ref_uploaded_[seq] = true;
-        }
         const int64_t tlen = tile_len();
         int tile_no = 0;
         for (int64_t tf = plan.win_first; tf <= plan.win_last; tf += tlen, tile_no++) {
@@ -164,8 +182,14 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             size_t r_lo, r_hi;   // records whose ordering start can reach the tile
             tile_records(plan, (int)tf, tl, r_lo, r_hi);
             if (r_lo >= r_hi) continue;
-            while ((int)q.size() >= max_in_flight) { int rc = fetch_oldest(); if (rc != NGSEP_OK) { drain(); return rc; } }
-            PackedTile& tile = ring_[slot];
+            const size_t dev = dealt % n_dev;
+            if (!ref_uploaded_[dev][(size_t)seq]) {
+                int rc = ngsep_ref_upload(ctxs_[dev], seq, genome_->seqs[seq].data(), (int64_t)genome_->seqs[seq].size());
+                if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctxs_[dev]); drain(); return rc; }
+                ref_uploaded_[dev][(size_t)seq] = true;
+            }
+            while (q[dev].size() >= max_in_flight) { int rc = fetch_oldest(dev); if (rc != NGSEP_OK) { drain(); return rc; } }
+            PackedTile& tile = rings_[dev][(size_t)slot[dev]];
             tile.set_pinned(!opt_.synchronous);
             double tp = now_s();
             if (!pack_reads(plan.reads, r_lo, r_hi, tile, with_groups(), &err_)) { drain(); return NGSEP_EINVAL; }
@@ -173,27 +197,28 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             if (tile.hdr.empty()) continue;
             double td = now_s();
             ngsep_tile tv = tile.view(seq, (int)tf, tl);
-            int rc = ngsep_tile_submit(ctx_, &tv);
-            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); drain(); return rc; }
+            int rc = ngsep_tile_submit(ctxs_[dev], &tv);
+            if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctxs_[dev]); drain(); return rc; }
             stats_.device_s += now_s() - td;
-            q.push_back({&job});
-            slot = (slot + 1) % kHostRing;
+            q[dev].push_back(&job);
+            slot[dev] = (slot[dev] + 1) % kHostRing;
+            dealt++;
         }
     }
-    while (!q.empty()) { int rc = fetch_oldest(); if (rc != NGSEP_OK) { drain(); return rc; } }
+    for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { int rc = fetch_oldest(dev); if (rc != NGSEP_OK) { drain(); return rc; } }
     return NGSEP_OK;
 }
 
-int GpuSingleSampleVariantsDetector::fetch_tile(SeqJob& job, ngsep_tile_stats& ts) {
+int GpuSingleSampleVariantsDetector::fetch_tile(void* ctx, SeqJob& job, ngsep_tile_stats& ts) {
     // into a buffer that lives as long as the detector (no fresh pages per tile), then only the tile's calls move to the job
     size_t n = 0;
     if (call_buf_.size() < 65536) call_buf_.resize(65536);
-    int rc = ngsep_tile_fetch(ctx_, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
+    int rc = ngsep_tile_fetch(ctx, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
     if (rc == NGSEP_EOVERFLOW && n > call_buf_.size()) {
         call_buf_.resize(n + n / 4 + 16);
-        rc = ngsep_tile_fetch(ctx_, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
+        rc = ngsep_tile_fetch(ctx, call_buf_.data(), call_buf_.size(), &n, nullptr, &ts);
     }
-    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx); return rc; }
     job.snvs.insert(job.snvs.end(), call_buf_.begin(), call_buf_.begin() + (ptrdiff_t)n);
     return NGSEP_OK;
 }

@@ -49,6 +49,7 @@ DetectorOptions convert(const ngsep_detector_options* o) {
     d.max_base_qs = o->max_base_qs; d.min_quality = o->min_quality; d.call_embedded = o->call_embedded_snvs != 0; d.csb = o->calc_strand_bias != 0;
     d.device = o->device; d.tile_len = o->tile_len; d.shard = o->shard; d.n_shards = o->n_shards < 1 ? 1 : o->n_shards; d.host_only = o->host_only != 0;
     d.synchronous = o->synchronous != 0;
+    d.n_devices = o->n_devices < 1 ? 1 : o->n_devices;
     return d;
 }
 

@@ -69,8 +69,9 @@ static DetectorOptions multi_options(DetectorOptions o) {
 GpuMultisampleVariantsDetector::GpuMultisampleVariantsDetector(const DetectorOptions& o, std::vector<SampleDef> samples, int n_read_groups)
     : GpuSingleSampleVariantsDetector(multi_options(o)), samples_(std::move(samples)), n_read_groups_(n_read_groups) {}
 
-int GpuMultisampleVariantsDetector::ensure_ctx() {
-    if (ctx_) return NGSEP_OK;
+int GpuMultisampleVariantsDetector::create_ctx(int device, void** out) {
+    void* ctx_ = nullptr;   // (local: the members are set by ensure_ctx)
+    *out = nullptr;
     if (samples_.size() < 2) { err_ = "MultisampleVariantsDetector on the device needs at least two samples (use SingleSampleVariantsDetector for one)"; return NGSEP_EINVAL; }
     ngsep_params p{};
     p.max_base_qs = opt_.max_base_qs;
@@ -81,8 +82,8 @@ int GpuMultisampleVariantsDetector::ensure_ctx() {
     p.n_samples = (int32_t)samples_.size();
     double tables[NGSEP_N_TABLES];
     host_tables(opt_.het_rate, tables);
-    int rc = ngsep_ctx_create(opt_.device, &p, tables, NGSEP_N_TABLES, &ctx_);
-    if (rc != NGSEP_OK) { err_ = ngsep_last_error(nullptr); ctx_ = nullptr; return rc; }
+    int rc = ngsep_ctx_create(device, &p, tables, NGSEP_N_TABLES, &ctx_);
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(nullptr); return rc; }
     std::vector<int32_t> off = {0};
     std::vector<uint16_t> groups;
     for (auto& s : samples_) {
@@ -91,7 +92,8 @@ int GpuMultisampleVariantsDetector::ensure_ctx() {
     }
     if (groups.empty()) groups.push_back(0);
     rc = ngsep_samples_set(ctx_, std::max(1, n_read_groups_), off.data(), groups.data(), opt_.min_allele_depth_freq);
-    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); ngsep_ctx_destroy(ctx_); ctx_ = nullptr; }
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); ngsep_ctx_destroy(ctx_); return rc; }
+    *out = ctx_;
     return rc;
 }
 
@@ -111,16 +113,16 @@ void GpuMultisampleVariantsDetector::on_span_event(int e, const std::string& ref
     }
 }
 
-int GpuMultisampleVariantsDetector::fetch_tile(SeqJob& job, ngsep_tile_stats& ts) {
+int GpuMultisampleVariantsDetector::fetch_tile(void* ctx, SeqJob& job, ngsep_tile_stats& ts) {
     const size_t n_samples = samples_.size();
     size_t n = 0;
     if (sbuf_.size() < 4096) { sbuf_.resize(4096); cbuf_.resize(4096 * n_samples); }
-    int rc = ngsep_tile_fetch_pop(ctx_, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
+    int rc = ngsep_tile_fetch_pop(ctx, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
     if (rc == NGSEP_EOVERFLOW && n > sbuf_.size()) {
         sbuf_.resize(n + 16); cbuf_.resize((n + 16) * n_samples);
-        rc = ngsep_tile_fetch_pop(ctx_, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
+        rc = ngsep_tile_fetch_pop(ctx, sbuf_.data(), sbuf_.size(), &n, cbuf_.data(), nullptr, &ts);
     }
-    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx); return rc; }
     job.sites.insert(job.sites.end(), sbuf_.begin(), sbuf_.begin() + (ptrdiff_t)n);
     job.scalls.insert(job.scalls.end(), cbuf_.begin(), cbuf_.begin() + (ptrdiff_t)(n * n_samples));
     return NGSEP_OK;

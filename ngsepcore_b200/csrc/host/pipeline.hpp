@@ -153,6 +153,8 @@ struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 
     double min_allele_depth_freq = 0;   // MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58)
     // device plumbing (not reference options)
     int device = 0;
+    int n_devices = 1;         // GPUs device .. device + n_devices - 1 of this host: region tiles are dealt to them in turn, every GPU with its own
+                               // context, ring of page-locked tile buffers and tiles in flight (no collective, ordered merge on the host)
     int tile_len = 0;          // region tiles of this many positions; 0 = automatic (kAutoTileLen: sequences up to that length are one tile)
     bool synchronous = false;  // test hook: one tile at a time from pageable buffers, host stages on the calling thread (the pipelined run
                                // must give the same bytes)
@@ -202,18 +204,20 @@ public:
 protected:
     DetectorOptions opt_;
     const Genome* genome_ = nullptr;
-    void* ctx_ = nullptr;
-    std::vector<bool> ref_uploaded_;
+    void* ctx_ = nullptr;                        // context of the first device (ctxs_[0])
+    std::vector<void*> ctxs_;                    // one context per device
+    std::vector<std::vector<bool>> ref_uploaded_;   // per device, per sequence
     RunStats stats_;
     std::string err_;
     static constexpr int kHostRing = 4;          // host tile buffers (page-locked, reused from run to run); up to 3 tiles in flight
-    PackedTile ring_[kHostRing];
+    std::vector<std::vector<PackedTile>> rings_;   // per device: kHostRing tile buffers
     std::vector<ngsep_snv_call> call_buf_;       // where ngsep_tile_fetch writes
     virtual int ensure_ctx();
+    virtual int create_ctx(int device, void** ctx);   // one device context with this detector's options
     virtual std::string header_text() const { return vcf_header(opt_.sample_id, opt_.ploidy, opt_.print_sample_ploidy); }
     virtual bool with_groups() const { return false; }
     // waits for the oldest tile in flight and appends what it returned to the job it belongs to
-    virtual int fetch_tile(SeqJob& job, ngsep_tile_stats& ts);
+    virtual int fetch_tile(void* ctx, SeqJob& job, ngsep_tile_stats& ts);
     // ordered merge (embedded / indel suppression, SSVPL:150-160) + VCF text of one sequence (SSVD:933-968) -> job.text
     virtual void emit_text(SeqJob& job);
     // discoverVariantWithSpan at an event with a reference span > 1 that is not embedded (SSVPL:257-273); may run on any
@@ -237,10 +241,10 @@ public:
 protected:
     std::vector<SampleDef> samples_;
     int n_read_groups_;
-    int ensure_ctx() override;
+    int create_ctx(int device, void** ctx) override;
     std::string header_text() const override { return vcf_header(samples_, opt_.print_sample_ploidy); }
     bool with_groups() const override { return true; }
-    int fetch_tile(SeqJob& job, ngsep_tile_stats& ts) override;
+    int fetch_tile(void* ctx, SeqJob& job, ngsep_tile_stats& ts) override;
     void emit_text(SeqJob& job) override;
     std::vector<ngsep_pop_site> sbuf_;
     std::vector<ngsep_sample_call> cbuf_;

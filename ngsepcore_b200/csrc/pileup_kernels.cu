@@ -1695,7 +1695,8 @@ static PileupKernel kernel_for(int threads, int min_blocks) {
     }
     if (min_blocks <= 3) return k_pileup_windows<256, 3>;
     if (min_blocks == 4) return k_pileup_windows<256, 4>;
-    return k_pileup_windows<256, 5>;
+    if (min_blocks == 5) return k_pileup_windows<256, 5>;
+    return k_pileup_windows<256, 6>;
 }
 
 int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks) {
