@@ -168,6 +168,10 @@ void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
 // Entry-list capacity: open columns are a fraction of a percent of the positions and hold `depth` entries each, i.e. a few
 // tenths of an entry per record.  Only single-sample production runs use the list.
 size_t entries_need(const Ctx* c, const Slot* s) {
+    // Measured (profiles/README.md, round 2): resolving the entries in the window kernel costs it more (a warp-serial piece of
+    // work in front of a block barrier, ~0.045 ms per yeast pass) than the genotype kernel saves (~0.013 ms): off unless asked for.
+    static const bool on = [] { const char* e = std::getenv("NGSEP_ENTRIES"); return e && std::atoi(e) != 0; }();
+    if (!on) return 0;
     if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) return 0;
     // + the pieces the resident warps of the window kernel reserve ahead (kEntChunk = 1024 entries each)
     return std::min<size_t>((size_t)s->tile.n_reads / 2 + (size_t)c->sm_count * 64 * 1024, 0x7fffffffull);
@@ -268,7 +272,7 @@ int launch_batch(Ctx* c) {
     if (rc != NGSEP_OK) return rc;
     {
         size_t ents = 0;
-        for (size_t i = 1; i < n; i++) ents += (c->params.n_samples > 1 || (c->params.flags & NGSEP_F_EMIT_ALL)) ? 0 : (size_t)c->slots[i]->tile.n_reads / 2;
+        for (size_t i = 1; i < n; i++) ents += entries_need(c, c->slots[i]) ? (size_t)c->slots[i]->tile.n_reads / 2 : 0;
         if (ents) ents += (size_t)c->sm_count * 64 * 1024;
         CK(c->d_ent.reserve(std::min<size_t>(ents, 0x7fffffffull)), "column entry list alloc");
     }

@@ -14,8 +14,7 @@ namespace ngsep_b200 {
 // shared-memory layout
 // ------------------------------------------------------------------------------------------------------------
 struct SmemLayout {
-    unsigned bar, t0, kmin, misc, cnt, cov, list, openq, chunk, wtot, wmax, rare;   // CTA-wide arrays
-    unsigned cov_len;                                                                 // entries of the cover array (a multiple of the largest CTA)
+    unsigned bar, t0, kmin, misc, cnt, list, ulist, openq, chunk, wmax, rare;   // CTA-wide arrays
     unsigned stage0, stage_stride;                          // staged windows
     unsigned o_win, o_hdr, o_pay, o_ref2, o_refn, o_refl;   // offsets inside a stage
     unsigned total, max_reads;
@@ -27,6 +26,11 @@ constexpr int M_NCAND = 0, M_UNC = 1, M_NRARE = 2, M_HASVER = 3, M_CARRY = 4, M_
 constexpr int kSkipTable = 16;   // k_min[m] for m = 0..15 counted non-reference bases
 constexpr int kMaxOpen = 32;     // open columns listed in shared memory per window (more go straight to the global list)
 constexpr unsigned int kEntChunk = 1024u;   // entries a warp reserves in the global entry list at a time
+// Resolving the records of an open column into (record, offset) entries inside the window kernel was built and measured in
+// round 2 (profiles/README.md): the genotype kernel gains 0.013 ms per yeast pass, the window kernel loses 0.045 ms (a
+// warp-serial piece of work in front of a block barrier).  The code stays behind this switch; the shipped kernels hand the
+// open columns over as record ranges.
+constexpr bool kWithEntries = false;
 constexpr uint32_t kOpenSearch = 0xffffu;   // open-column entry without a record range: the genotype kernel searches it
 // open-column entry, .w: either the number of records of the range that starts at record .z (0xffff = search), or — bit 31
 // set — the number of (record, offset) entries the window kernel resolved for the column (bits 0-23; they start at entry .z
@@ -52,13 +56,11 @@ static SmemLayout make_layout(int T, unsigned pay_cap_words, int n_stages) {
     L.kmin = o; o += kSkipTable * 4;
     L.misc = o; o += 2 * kMiscSet * 4;
     L.cnt = o; o += (T + 1) * 4;
-    L.cov_len = ((unsigned)(T + kThreads - 1) / kThreads) * kThreads;   // entries the prefix scan walks (a multiple of the largest CTA); entry T is only a sink
-    L.cov = o; o += (L.cov_len > (unsigned)T ? L.cov_len : (unsigned)T + 1u) * 4;   // clean-cover deltas of the simple records, then their prefix sums
     L.list = o; o += T * 4;
+    L.ulist = o; o += ((T * 2 + 3) & ~3u);      // candidates the quarter-warp proofs left open (the sample axis keeps its candidate bitmap here)
     o = (o + 15u) & ~15u;
     L.openq = o; o += 2 * kMaxOpen * 16;        // open columns of the window (finished list entries), one list per window parity
     L.chunk = o; o += (kThreads / 32) * 8;      // per warp: the piece of the entry list it fills (next, end)
-    L.wtot = o; o += (kThreads / 32) * 4;       // per-warp totals of the prefix scan
     o = (o + 7u) & ~7u;
     L.wmax = o; o += ((L.max_reads + kThreads) / 32 + 2) * 4;
     o = (o + 7u) & ~7u;
@@ -166,15 +168,24 @@ struct WinCtx {
     int wbeg, g_lo, g_hi;        // 0-based index of the window start; [g_lo,g_hi) = the window inside tile and sequence
     const uint32_t* s_ref2;      // staged reference, base index wbeg - kRefLeft at bit 0 of word 0
     uint32_t* s_cnt;             // per position: flagged bases (an upper bound of the counted non-reference bases)
-    int* s_cov;                  // per position: +1 / -1 where a stretch of CLEAN callable bases of a simple record starts / ends
-    uint32_t* s_list;            // candidate list: positions in the window
+    uint32_t* s_list;            // candidate list: position in the window | record that flagged it first << kListShift
     int* mset;                   // counters of this window
     bool collect;                // false in EMIT_ALL mode (every position is a candidate already)
-    bool proof;                  // collect the clean-cover counts the hom-ref proof needs (single-sample contexts)
 };
-__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx) {
+// candidate list entry as the screen writes it: bits 0-12 position in the window (windows hold at most 8192 positions),
+// 13-31 the flagging record.  The resolve pass (C1) rewrites it in place for the proofs: 0-12 position, 13-14 reference
+// allele, 15-20 `need` = k_min[m_up] (63 = no number of reference bases closes the column), 21-31 flagging record.
+constexpr int kListShift = 13;
+constexpr uint32_t kListPosMask = (1u << kListShift) - 1u;
+constexpr int kListMaxRec = (1 << (32 - kListShift)) - 1;
+constexpr int kProofRefShift = 13, kProofNeedShift = 15, kProofRecShift = 21;
+constexpr int kProofMaxRec = (1 << (32 - kProofRecShift)) - 1, kProofNoNeed = 63;
+
+// rec = index of the flagging record inside the window's record range
+__device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx, int rec) {
     const int li = idx - w.wbeg;
-    if (atomicAdd(&w.s_cnt[li], 1u) == 0u) w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li;
+    if (atomicAdd(&w.s_cnt[li], 1u) == 0u)
+        w.s_list[atomicAdd(&w.mset[M_NCAND], 1)] = (uint32_t)li | ((uint32_t)min(rec, kListMaxRec) << kListShift);
 }
 
 // 16 read bases (one payload word) against the reference at 0-based index `idx0` of the word's first base
@@ -184,32 +195,12 @@ __device__ __forceinline__ uint32_t ref16(const WinCtx& w, int idx0) {
 }
 
 // Simple record.  Returns the last reference position (1-based) the record covers (PR.addAlignment, PR:154-156).
-// Besides the mismatch flags it leaves what the hom-ref proof of the window needs: its CLEAN cover — the
-// callable range (RA:782-784) minus every 32-base stretch of the read that holds a low-quality base (q <= 3: never counted,
-// CH:214) — as +1 / -1 in s_cov.  After a prefix sum, clean_cover(p) - flagged(p) is a LOWER bound of the counted bases equal
-// to the reference at p: every record counted in clean_cover(p) holds a counted base there, and at most flagged(p) of those
-// bases differ from the reference.
-__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+__device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
     const int L = (int)(h.meta & 0xffffu);         // one match block of L bases
     const int ref0 = h.first - 1;                  // 0-based index of read offset 0
     const int a = max(ref0, w.g_lo), b = min(ref0 + L, w.g_hi);
     if (a < b && w.collect) {
         const uint32_t* b2 = pay + 1;
-        const uint32_t* lowq = b2 + ((L + 15) >> 4);   // simple record: the low-quality mask follows the bases
-        const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
-        if (w.proof) {
-            const int ca = max(ref0 + c_lo, w.g_lo), cb = min(ref0 + c_hi, w.g_hi);
-            if (ca < cb) {
-                atomicAdd(&w.s_cov[ca - w.wbeg], 1);
-                atomicAdd(&w.s_cov[cb - w.wbeg], -1);
-                for (int wi = (ca - ref0) >> 5; wi <= (cb - 1 - ref0) >> 5; wi++) {
-                    if (lowq[wi] == 0u) continue;
-                    // a stretch with a low-quality base somewhere: none of its bases supports the proof
-                    atomicAdd(&w.s_cov[max(ref0 + 32 * wi, ca) - w.wbeg], -1);
-                    atomicAdd(&w.s_cov[min(ref0 + 32 * wi + 32, cb) - w.wbeg], 1);
-                }
-            }
-        }
         const int j0 = (a - ref0) >> 4, j1 = (b - 1 - ref0) >> 4;       // payload words that intersect the window
         const int r0 = ref0 + 16 * j0 - w.wbeg + kRefLeft;
         const int sh = (r0 & 15) * 2;
@@ -227,11 +218,13 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
         };
         // rare: some base of word j differs — flag the ones CountsHelper would count (callable, RA:782-784; q > 3, CH:214)
         auto flag_word = [&](int j, uint32_t m) {
+            const uint32_t* lowq = b2 + ((L + 15) >> 4);   // simple record: the low-quality mask follows the bases
+            const int c_lo = max((int)h.ign_start, 0), c_hi = L - max((int)h.ign_end, 0);
             while (m) {
                 const int bit = __ffs(m) - 1;
                 m &= m - 1;
                 const int off = 16 * j + (bit >> 1);
-                if (off >= c_lo && off < c_hi && !((lowq[off >> 5] >> (off & 31)) & 1u)) flag_candidate(w, ref0 + off);
+                if (off >= c_lo && off < c_hi && !((lowq[off >> 5] >> (off & 31)) & 1u)) flag_candidate(w, ref0 + off, rec);
             }
         };
         if (j1 - j0 < 32) {
@@ -272,7 +265,7 @@ __device__ __forceinline__ int screen_simple(const ngsep_read_hdr& h, const uint
 // General record (indels, clips, N mask, realigner versions): every aligned base that differs from the reference
 // is flagged (a superset of the counted ones).  Returns the last covered position, or INT_MIN for a version record
 // (its coverage goes through the bitmap fallback).
-__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w) {
+__device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uint32_t* pay, const WinCtx& w, int rec) {
     const RecView r = view_record(h, pay);
     const int lo = max(w.g_lo, (r.vfrom == INT_MIN) ? INT_MIN : r.vfrom - 1);
     const int hi = min(w.g_hi, (r.vto == INT_MAX) ? INT_MAX : r.vto - 1);
@@ -294,7 +287,7 @@ __device__ __forceinline__ int screen_general(const ngsep_read_hdr& h, const uin
                     while (m) {
                         const int bit = __ffs(m) - 1;
                         m &= m - 1;
-                        flag_candidate(w, o + (bit >> 1) - delta);
+                        flag_candidate(w, o + (bit >> 1) - delta, rec);
                     }
                 }
             }
@@ -541,6 +534,40 @@ __device__ __forceinline__ int warp_lower_bound(const Recs<kGlobal>& R, int want
     return lo;
 }
 
+struct ExactCtx {
+    int wbeg, n_cand, n_unres, max_span, max_back, tile, rec0;   // rec0: index in the tile of the window's first record
+    const uint32_t* s_list;
+    const uint16_t* s_ulist;     // candidates the quarter-warp proofs left open (indexes into s_list)
+    uint32_t* s_cnt;
+    const uint32_t *s_ref2, *s_refn, *s_refl;
+    const int* s_kmin;
+    bool emit_all, ignore_lower, span_capped;
+};
+
+// Is record idx a simple record whose base at pos is a COUNTED reference base?  (offset = pos - first with one match
+// block, RA:842-871; callable, RA:782-784; q > 3, CH:214.)
+template <bool kGlobal>
+__device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx, int pos, int ref) {
+    if (idx < 0 || idx >= R.n) return 0;
+    if (kGlobal) {
+        const ngsep_read_hdr h = R.header(idx);
+        const int L = (int)(h.meta & 0xffffu), off = pos - h.first;
+        if (!(h.meta & NGSEP_M_SIMPLE) || off < 0 || off >= L || off < (int)h.ign_start || (L - off) <= (int)h.ign_end) return 0;
+        const uint32_t* b2 = R.payload(h) + 1;
+        const uint32_t* lowq = b2 + ((L + 15) >> 4);
+        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    } else {
+        // staged window: the screen left the header in its proof form {first, first callable position, end of the callable
+        // positions (0, 0 for a record that is not simple), b2 word index | lowq word offset << 16}
+        const int4 dh = *(const int4*)(R.hdr + idx);
+        if (pos < dh.y || pos >= dh.z) return 0;
+        const int off = pos - dh.x;
+        const uint32_t* b2 = R.pay + (dh.w & 0xffff);
+        const uint32_t* lowq = b2 + ((uint32_t)dh.w >> 16);
+        return (!((lowq[off >> 5] >> (off & 31)) & 1u) && (int)((b2[off >> 4] >> ((off & 15) * 2)) & 3u) == ref) ? 1 : 0;
+    }
+}
+
 // The exact column (warp-cooperative, records through L2): every record of [i_lo, i_hi) in pileup order, one record per
 // lane and round.  lane_eval restates PR.getAlleleCalls(1) + the quality rules of CH.updateCounts; ballots give the exact
 // counts[4], countsStrand[4][2] and totalCount; columns whose exact counts prove the homozygous-reference call are
@@ -673,14 +700,16 @@ __device__ __forceinline__ void push_open(const OpenSink& sink, const ColumnQueu
 // An open column of the window (warp-cooperative): its record range, then — windows staged in one piece — one entry per
 // record that gives a call, in pileup order, so that k_genotype_columns only has to fetch quality bytes.  Columns of
 // windows too deep for a stage, and columns that do not fit the entry list, are handed over as a record range.
+// (The staged headers are in their proof form by now — only word 0, the ordering start, is intact — so the records' own
+// headers come from the tile's array, `ghdr` = the header of the window's first record: an L2 hit, a few dozen per open column.)
 template <bool kGlobal>
-__device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const ColumnQueue& cq, const OpenSink& sink, int tile, int rec0, int pos, int ref,
-                                                 int max_span, int max_back, bool span_capped, int lane) {
+__device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const ColumnQueue& cq, const OpenSink& sink, const ngsep_read_hdr* __restrict__ ghdr, int tile, int rec0,
+                                                 int pos, int ref, int max_span, int max_back, bool span_capped, int lane) {
     const int i_lo = warp_lower_bound(R, pos - max_span + 1, lane);
     const int i_hi = warp_lower_bound(R, pos + max_back + 1, lane);   // first record that starts too far to the right
     if (i_hi <= i_lo) return;
     const uint32_t n_range = (uint32_t)(i_hi - i_lo);
-    bool as_range = kGlobal || span_capped || cq.cap_ent == 0u || n_range > kEntChunk;
+    bool as_range = !kWithEntries || kGlobal || span_capped || cq.cap_ent == 0u || n_range > kEntChunk;
     unsigned int ebase = 0u;
     if (!as_range) {
         if (lane == 0) {
@@ -708,7 +737,9 @@ __device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const C
             uint2 ent = make_uint2(0u, 0u);
             bool ok = false;
             if (idx < i_hi) {
-                const ngsep_read_hdr h = R.header(idx);
+                const int4 v = __ldg((const int4*)(ghdr + idx));
+                ngsep_read_hdr h;
+                h.first = v.x; h.meta = (uint32_t)v.y; h.ign_start = (int16_t)(v.z & 0xffff); h.ign_end = (int16_t)((uint32_t)v.z >> 16); h.off = (uint32_t)v.w;
                 ok = resolve_entry(h, R.payload(h), pos, ent);
             }
             const unsigned int m = __ballot_sync(kFull, ok);
@@ -716,6 +747,70 @@ __device__ __forceinline__ void emit_open_column(const Recs<kGlobal>& R, const C
             n_ent += (unsigned int)__popc(m);
         }
         if (lane == 0 && n_ent > 0u) push_open(sink, cq, make_uint4((unsigned int)tile, (unsigned int)pos, ebase, kOpenEntries | ((uint32_t)ref << kOpenRefShift) | n_ent));
+    }
+}
+
+// Phase C2.  First proof attempt by a QUARTER-WARP per candidate: the 8 records next to the flagging one (4 on each side)
+// usually hold the k_min[1] = 7 counted reference bases that close a column with one flagged base.  What stays open is
+// listed for the half-warp pass.
+template <bool kGlobal>
+__device__ __forceinline__ void quarter_proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, uint16_t* s_ulist, int* n_unres, int warp, int lane, int nwarps) {
+    const int grp = lane >> 3, gl = lane & 7;
+    const int delta = (gl < 4) ? gl - 4 : gl - 3;   // -4..-1, +1..+4
+    for (int base = 0; base < x.n_cand; base += 4 * nwarps) {
+        const int ci = base + 4 * warp + grp;
+        int ok = 0, need = 0;
+        bool open = false;
+        if (ci < x.n_cand) {
+            const uint32_t ent = x.s_list[ci];
+            need = (int)((ent >> kProofNeedShift) & 63u);
+            open = need > 0;                               // need == 0: closed by the resolve pass
+            if (open && need <= 8)
+                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) + delta, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
+        }
+        const unsigned okm = __ballot_sync(kFull, ok != 0);
+        if (open && __popc(okm & (0xffu << (8 * grp))) >= need) open = false;
+        if (open && gl == 0) s_ulist[atomicAdd(n_unres, 1)] = (uint16_t)ci;
+    }
+}
+
+// Phase C3.  Fast proof of hom-ref by a HALF-WARP per candidate the quarter-warp pass left open: at most m_up counted non-reference bases
+// were flagged; the 16 records around the flagging one give a lower bound k_lb of the counted reference bases (any subset
+// of the records does).  k_lb >= need = k_min[m_up] closes the column.  What stays open is listed, with its record range,
+// for k_genotype_columns (emit_open_column).  Entries come from the resolve pass (position | reference allele | need | flagging record).
+template <bool kGlobal>
+__device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactCtx& x, const ColumnQueue& cq, const OpenSink& sink, const ngsep_read_hdr* __restrict__ ghdr,
+                                            int warp, int lane, int nwarps) {
+    const int grp = lane >> 4, gl = lane & 15;
+    for (int base = 0; base < x.n_unres; base += 2 * nwarps) {
+        const int ui = base + 2 * warp + grp;
+        uint32_t ent = 0u;
+        int ok = 0, need = 0;
+        bool open = false;
+        if (ui < x.n_unres) {
+            ent = x.s_list[x.s_ulist[ui]];
+            need = (int)((ent >> kProofNeedShift) & 63u);
+            open = true;
+            if (need <= 15)
+                ok = counted_ref_base(R, (int)(ent >> kProofRecShift) - 8 + gl, x.wbeg + (int)(ent & kListPosMask) + 1, (int)((ent >> kProofRefShift) & 3u));
+        }
+        const unsigned okm = __ballot_sync(kFull, ok != 0);
+        if (open && __popc(okm & (0xffffu << (16 * grp))) >= need) open = false;
+        // the (few) columns still open: second chance with the whole warp (the 32 records around the flagging one), then
+        // the record range of the column, then the list
+        unsigned sm = __ballot_sync(kFull, open && gl == 0);
+        while (sm) {
+            const int src = __ffs(sm) - 1;
+            sm &= sm - 1;
+            const uint32_t e = __shfl_sync(kFull, ent, src);
+            const int e_need = (int)((e >> kProofNeedShift) & 63u);
+            const int e_li = (int)(e & kListPosMask), e_pos = x.wbeg + e_li + 1;
+            if (e_need <= 30) {
+                const int ok2 = counted_ref_base(R, (int)(e >> kProofRecShift) - 16 + lane, e_pos, (int)((e >> kProofRefShift) & 3u));
+                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= e_need) continue;
+            }
+            emit_open_column<kGlobal>(R, cq, sink, ghdr, x.tile, x.rec0, e_pos, (int)((e >> kProofRefShift) & 3u), x.max_span, x.max_back, x.span_capped, lane);
+        }
     }
 }
 
@@ -741,22 +836,18 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     int* s_kmin = (int*)(smem + lay.kmin);
     int* s_misc = (int*)(smem + lay.misc);
     uint32_t* s_cnt = (uint32_t*)(smem + lay.cnt);
-    int* s_cov = (int*)(smem + lay.cov);
     uint32_t* s_list = (uint32_t*)(smem + lay.list);
+    uint16_t* s_ulist = (uint16_t*)(smem + lay.ulist);
     uint2* s_chunk = (uint2*)(smem + lay.chunk);
-    int* s_wtot = (int*)(smem + lay.wtot);
     int* s_wmax = (int*)(smem + lay.wmax);
     int2* s_rare = (int2*)(smem + lay.rare);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const DevParams& prm = *a.prm;
     const int T_lay = a.cfg.T_lay;
-    const int P = (int)lay.cov_len / nthr;     // positions per thread in the prefix scan and in the clearing pass (cov_len is a multiple of the CTA)
-    const unsigned int warp_magic = 0xffffffffu / (unsigned int)(32 * P) + 1u;   // li / (32 P) == umulhi(li, warp_magic) for li < 2^16
     if (tid < kSkipTable) s_kmin[tid] = prm.k_min[tid];
     if (tid < 2 * kMiscSet) s_misc[tid] = ((tid % kMiscSet) == M_CARRY) ? INT_MIN : 0;
     for (int i = tid; i < T_lay + 1; i += nthr) s_cnt[i] = 0u;
-    for (int i = tid; i < max((int)lay.cov_len, T_lay + 1); i += nthr) s_cov[i] = 0;
     if (tid < nwarps) s_chunk[tid] = make_uint2(0u, 0u);
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
@@ -764,7 +855,6 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
     const bool emit_all = (prm.flags & NGSEP_F_EMIT_ALL) != 0;
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
     const bool multi = prm.n_samples > 1;
-    const bool proofs = !multi && !emit_all && prm.fast_homref != 0;
     const int n_stages = a.cfg.n_stages;
     const int stride = (int)gridDim.x;
     // The thread that issues the bulk copies.  One stage: thread 0 (the copies of the next window start when the stage frees).
@@ -788,6 +878,9 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         }
         unsigned char* stg = smem + lay.stage0 + (unsigned)stage * lay.stage_stride;
         uint64_t* bar = &s_bar[stage];
+        // the stage was written with generic stores (proof-form headers) by the previous window: order them before the
+        // asynchronous-proxy writes of the bulk copies (the block barrier ordered the threads, this orders the proxies)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const int64_t wbeg = wr.wbeg;
         const uint32_t b_ref2 = (uint32_t)(t0.T + 2 * kRefLeft) / 4u, b_bits = (uint32_t)t0.T / 8u;
         const bool recs = fits(wr) && wr.hi > wr.lo;
@@ -864,14 +957,13 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         WinCtx wc;
         wc.wbeg = wbeg; wc.g_lo = g_lo; wc.g_hi = g_hi;
         wc.s_ref2 = (const uint32_t*)(stg + lay.o_ref2);
-        wc.s_cnt = s_cnt; wc.s_cov = s_cov; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
-        wc.proof = proofs;
+        wc.s_cnt = s_cnt; wc.s_list = s_list; wc.mset = mset; wc.collect = !emit_all;
 
         // ---- phase A: screen + coverage scan, one thread per record -------------------------------------------------
         // Coverage: with the records sorted by start s_i and reach_i = max(e_0..e_i) (e = last covered position), the
         // positions of (reach_i, s_{i+1}) are covered by nobody.  reach_i is at least the warp-local prefix maximum; only
         // when that does not reach s_{i+1} - 1 is the record queued for the exact cross-warp evaluation (process_rare).
-        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, bool first_chunk) {
+        auto screen_chunk = [&](int n_chunk, uint32_t pay_base, int rec0, bool first_chunk) {
             for (int base = 0; base < n_chunk; base += nthr) {
                 const int i = base + tid;
                 const bool act = i < n_chunk;
@@ -879,7 +971,17 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 if (act) {
                     const ngsep_read_hdr h = s_hdr[i];
                     const uint32_t* pay = s_pay + (h.off - pay_base);
-                    e = record_is_simple(h) ? screen_simple(h, pay, wc) : screen_general(h, pay, wc);
+                    e = record_is_simple(h) ? screen_simple(h, pay, wc, rec0 + i) : screen_general(h, pay, wc, rec0 + i);
+                    {   // proof form of the staged header (counted_ref_base<false>); word 0 (the ordering start) stays
+                        int4 dh = make_int4(h.first, 0, 0, 0);
+                        if (record_is_simple(h)) {
+                            const int L = (int)(h.meta & 0xffffu);
+                            dh.y = h.first + max((int)h.ign_start, 0);
+                            dh.z = h.first + L - max((int)h.ign_end, 0);
+                            dh.w = (int)((uint32_t)(pay + 1 - s_pay) | ((uint32_t)((L + 15) >> 4) << 16));
+                        }
+                        *(int4*)(const_cast<ngsep_read_hdr*>(s_hdr) + i) = dh;
+                    }
                     nxt = min(s_hdr[i + 1].first, B + 1);
                     floor_i = max(h.first - 1, A - 1);   // record i accounts for the positions of [s_i, s_{i+1}) only
                     if (first_chunk && i == 0) { const int lead = min(h.first, B + 1) - A; if (lead > 0) atomicAdd(&mset[M_UNC], lead); }
@@ -902,7 +1004,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         };
 
         if (single) {
-            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, true);
+            if (n_rec > 0) screen_chunk(n_rec, wr.off_lo & ~3u, 0, true);
             else if (tid == 0 && B >= A) mset[M_UNC] = B - A + 1;
         } else {
             // windows too deep for one stage: stream the record range chunk by chunk through the current stage
@@ -932,7 +1034,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 const int carry = mset[M_CARRY];
                 mbar_wait(&s_bar[cur], (phase_bits >> cur) & 1u);
                 phase_bits ^= 1u << cur;
-                screen_chunk(r1 - r0, pay_base, first_chunk);
+                screen_chunk(r1 - r0, pay_base, r0 - wr.lo, first_chunk);
                 __syncthreads();
                 process_rare(carry);
                 __syncthreads();
@@ -964,12 +1066,12 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
             // largely the same (L1 reuse).  Bitmap of the open positions -> ordered list -> record range per position.
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
-            uint32_t* s_bm = (uint32_t*)s_cov;   // (no cover deltas are collected on the sample axis)
+            uint32_t* s_bm = (uint32_t*)s_ulist;
             const int nw = (T_lay + 31) >> 5;
             for (int i = tid; i < nw; i += nthr) s_bm[i] = 0u;
             __syncthreads();
             for (int ci = tid; ci < n_cand; ci += nthr) {
-                const int li = (int)s_list[ci];
+                const int li = (int)(s_list[ci] & kListPosMask);
                 s_cnt[li] = 0u;   // (nothing else clears s_cnt)
                 bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // SSVPL:298-305
                 if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
@@ -1010,61 +1112,48 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         } else if (n_cand > 0) {
             const uint32_t* s_refn = (const uint32_t*)(stg + lay.o_refn);
             const uint32_t* s_refl = (const uint32_t*)(stg + lay.o_refl);
-            // ---- phase B: prefix sums of the clean-cover deltas: s_cov[p] + the totals of the warps in front = simple records
-            // that hold a clean callable base at position p
-            if (wc.proof) {
-                const int p0 = tid * P;
-                int tot = 0;
-                for (int i = 0; i < P; i++) tot += s_cov[p0 + i];
-                int incl = tot;
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-                int run = incl - tot;
-                for (int i = 0; i < P; i++) { run += s_cov[p0 + i]; s_cov[p0 + i] = run; }
-                if (lane == 31) s_wtot[warp] = incl;
-                __syncthreads();   // ---- sync 3: prefix sums complete ------------------------------------------------------
+            // C1, resolve pass (thread per candidate): everything the proofs need goes into the list entry
+            for (int ci = tid; ci < n_cand; ci += nthr) {
+                const uint32_t ent = s_list[ci];
+                const int li = (int)(ent & kListPosMask);
+                const uint32_t m_up = s_cnt[li];
+                s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
+                bool closed = ((s_refn[li >> 5] >> (li & 31)) & 1u) != 0u;                                       // VD:101-107
+                if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) closed = true;                        // SSVPL:198
+                const int rr = li + kRefLeft;
+                const uint32_t ref = (wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
+                int need = (m_up < (uint32_t)kSkipTable) ? min(s_kmin[m_up], kProofNoNeed) : kProofNoNeed;
+                if (need <= 0) need = 1;
+                if (multi) need = kProofNoNeed;   // sample axis: every candidate goes to k_genotype_columns_multi (no proof is attempted)
+                if (closed) need = 0;
+                s_list[ci] = (uint32_t)li | (ref << kProofRefShift) | ((uint32_t)need << kProofNeedShift) |
+                             ((uint32_t)min((int)(ent >> kListShift), kProofMaxRec) << kProofRecShift);
             }
-            // ---- phase C: the hom-ref proof, one thread per candidate.  With m = flagged bases (an upper
-            // bound of the counted non-reference bases: simple records exactly, every aligned mismatch of the others) and
-            // k = clean cover - flagged (a lower bound of the counted reference bases), k >= k_min[m] proves the column
-            // homozygous reference and closes it.  What stays open is handed to k_genotype_columns by the warp, column by column.
+            __syncthreads();   // ---- sync 3: entries resolved -----------------------------------------------------------------
+            ExactCtx x;
+            x.wbeg = wbeg; x.n_cand = n_cand; x.max_span = max_span; x.max_back = max_back; x.tile = wr.tile; x.rec0 = wr.lo;
+            x.s_list = s_list; x.s_cnt = s_cnt; x.s_ref2 = wc.s_ref2; x.s_refn = s_refn; x.s_refl = s_refl;
+            x.s_kmin = s_kmin; x.emit_all = emit_all; x.ignore_lower = ignore_lower;
+            x.s_ulist = s_ulist; x.n_unres = 0;
+            x.span_capped = span_capped || multi;   // the sample axis takes record ranges, not resolved entries
             OpenSink sink;
             sink.s_openq = (uint4*)(smem + lay.openq) + (it & 1) * kMaxOpen;
             sink.n_open = &mset[M_NOPEN];
             sink.s_chunk = &s_chunk[warp];
-            for (int base = 0; base < n_cand; base += nthr) {
-                const int ci = base + lane * nwarps + warp;   // neighbouring candidates go to different warps: the open columns (a few
-                                                              // per window, each a warp-serial piece of work) spread over the CTA
-                bool open = false;
-                int li = 0;
-                if (ci < n_cand) {
-                    li = (int)s_list[ci];
-                    const int m_up = (int)s_cnt[li];
-                    s_cnt[li] = 0u;   // the counter of a listed position goes back to zero here: nothing else clears s_cnt
-                    open = ((s_refn[li >> 5] >> (li & 31)) & 1u) == 0u;                                           // VD:101-107
-                    if (ignore_lower && ((s_refl[li >> 5] >> (li & 31)) & 1u)) open = false;                      // SSVPL:198
-                    if (open && wc.proof && m_up < kSkipTable) {
-                        int cover = s_cov[li];
-                        const int ow = (int)__umulhi((unsigned int)li, warp_magic);   // the warp that scanned position li
-                        for (int k = 0; k < ow; k++) cover += s_wtot[k];
-                        if (cover - m_up >= s_kmin[m_up]) open = false;
-                    }
-                }
-                unsigned om = __ballot_sync(kFull, open);
-                while (om) {
-                    const int src = __ffs(om) - 1;
-                    om &= om - 1;
-                    const int e_li = __shfl_sync(kFull, li, src);
-                    const int rr = e_li + kRefLeft;
-                    const int ref = (int)((wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u);
-                    if (single) {
-                        Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
-                        emit_open_column<false>(R, a.cq, sink, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped || multi, lane);
-                    } else {
-                        const TileDev& d = a.tiles[wr.tile];
-                        Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
-                        emit_open_column<true>(R, a.cq, sink, wr.tile, wr.lo, wbeg + e_li + 1, ref, max_span, max_back, span_capped, lane);
-                    }
-                }
+            const ngsep_read_hdr* ghdr = a.tiles[wr.tile].hdr + wr.lo;
+            if (single) {
+                Recs<false> R; R.hdr = s_hdr; R.pay = s_pay; R.pay_base = wr.off_lo & ~3u; R.n = n_rec;
+                quarter_proof_phase<false>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
+                __syncthreads();   // ---- sync 4: candidates left to the half-warp pass listed --------------------------------------
+                x.n_unres = mset[M_NUNRES];
+                proof_phase<false>(R, x, a.cq, sink, ghdr, warp, lane, nwarps);
+            } else {
+                const TileDev& d = a.tiles[wr.tile];
+                Recs<true> R; R.hdr = d.hdr + wr.lo; R.pay = d.payload; R.pay_base = 0u; R.n = n_rec;
+                quarter_proof_phase<true>(R, x, s_ulist, &mset[M_NUNRES], warp, lane, nwarps);
+                __syncthreads();
+                x.n_unres = mset[M_NUNRES];
+                proof_phase<true>(R, x, a.cq, sink, ghdr, warp, lane, nwarps);
             }
         }
         __syncthreads();   // ---- sync 2: the stage and the window arrays are free -------------------------------------------
@@ -1084,14 +1173,6 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 }
             }
         }
-        // the cover array goes back to zero for the next window (s_cnt was cleared candidate by candidate)
-        if (proofs) {
-            const int p0 = tid * P;
-            for (int i = 0; i < P; i++) s_cov[p0 + i] = 0;
-            if (tid == 0) s_cov[T_lay] = 0;   // the sink of the deltas at the window's end (inside the scanned range when T_lay is not a multiple of the CTA)
-        } else if (multi && !emit_all) {
-            for (int i = tid; i < ((T_lay + 31) >> 5); i += nthr) s_cov[i] = 0;   // (the sample axis keeps its candidate bitmap here)
-        }
         // warp 1 hands the window's open columns to the global list: ONE global atomic per window, its round trip hidden behind
         // the wait for the next window (the list and the counters are per window parity)
         if (warp == 1 % nwarps) {
@@ -1110,7 +1191,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
         const int win_len = max(0, B - A + 1);
         if (uncovered > 0 && mset[M_HASVER] && n_rec > 0) {
             // rare: a gap in the cover of the unversioned records while realigner versions are present — count the cover
-            // of every record with a bitmap (s_cnt has just been cleared and is cleared again below)
+            // of every record with a bitmap (s_cnt is all zero here — every listed position reset its counter — and is cleared again below)
             __syncthreads();
             const TileDev& d = a.tiles[wr.tile];
             uint32_t* s_bm = s_cnt;
@@ -1177,7 +1258,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
         const uint4 oc = cq.open[t];   // tile, position, then a record range or a resolved entry list (kOpenEntries)
         const TileDev& d = tiles[oc.x];
         const int pos = (int)oc.y;
-        if (oc.w & kOpenEntries) {
+        if (kWithEntries && (oc.w & kOpenEntries)) {
             // the window kernel resolved the column's records while they sat in shared memory (and found the reference base
             // callable): one coalesced entry load and one quality byte per record
             const int n = (int)(oc.w & kOpenCountMask);

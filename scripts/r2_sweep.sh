@@ -24,6 +24,8 @@ s2_768_3) run s2_768_3 NGSEP_STAGES=2 NGSEP_WINDOW=768 NGSEP_PAY_CAP_WORDS=3840 
 s1_1536) run s1_1536 NGSEP_WINDOW=1536 NGSEP_PAY_CAP_WORDS=7680 NGSEP_MIN_BLOCKS=3 ;;
 t128) run t128 NGSEP_THREADS=128 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 ;;
 geno6) run geno6 NGSEP_GENO_MIN_BLOCKS=6 ;;
+entries) run entries NGSEP_ENTRIES=1 ;;
+g16) run g16 NGSEP_GENO_BLOCKS_PER_SM=16 ;;
 s1_640) run s1_640 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 NGSEP_MIN_BLOCKS=5 ;;
 t128_640) run t128_640 NGSEP_THREADS=128 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 NGSEP_MIN_BLOCKS=10 ;;
 t128_1280) run t128_1280 NGSEP_THREADS=128 NGSEP_MIN_BLOCKS=8 ;;

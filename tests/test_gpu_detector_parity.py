@@ -133,3 +133,28 @@ def test_quality_code_modes_give_the_oracle_records(oracle, tmp_path, monkeypatc
     assert raw.pack(batch, 0)["quality"][0] == 8
     assert raw.run(batch) == want
     assert len(_body(want)) > 100
+
+
+def test_region_tiles_dealt_to_several_gpus_of_one_process(oracle, tmp_path):
+    """SURVEY 8e / VERDICT r01 item 5: ONE detector process, admission + event pre-pass once, region tiles dealt in turn to the
+    contexts of N GPUs (each with its own ring of page-locked buffers and tiles in flight), ordered merge on the host: the VCF
+    of the N-GPU run is the 1-GPU run's and the oracle's.  Needs at least two GPUs (gpurun --gpus 2); skipped on one."""
+    from ngsepcore_b200 import capi
+    try:
+        capi.Context(device=1).close()
+    except capi.NgsepError:
+        pytest.skip("one GPU only")
+    genome, batch, fa, sam = _inputs(tmp_path, [("chrA", 400000), ("chrB", 130000)], depth=30, seeds=(211, 212, 213), indel_rate=5e-4)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam)
+    one = hostapi.Detector(tile_len=40000)
+    one.set_genome(genome)
+    assert one.run(batch) == want
+    for n in (2, 4, 8):
+        try:
+            capi.Context(device=n - 1).close()
+        except capi.NgsepError:
+            break
+        det = hostapi.Detector(tile_len=40000, n_devices=n)
+        det.set_genome(genome)
+        assert det.run(batch) == want
+        assert det.stats().covered_positions == gp and det.stats().tiles == one.stats().tiles
