@@ -439,6 +439,85 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] and [4] with inputs generated on the device (ngsep_synth_*): no read crosses PCIe
+# ----------------------------------------------------------------------------------------------------------------------
+GRCH38_LIKE = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717, 133797422, 135086622, 133275309,
+               114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415]
+SYNTH_CONFIGS = {
+    "c3": dict(contigs=[64444167], depth=60.0, tile=2_000_000, gc=0.44, what="synthetic 64 Mb (chr20-sized) sequence x 60x (BASELINE configs[2])"),
+    "c5": dict(contigs=GRCH38_LIKE, depth=30.0, tile=4_000_000, gc=0.41, what="synthetic 3.1 Gb human-scale genome (24 sequences) x 30x (BASELINE configs[4])"),
+    "panel": dict(contigs=[2_000_000], depth=1000.0, tile=125_000, gc=0.41, what="2 Mb targeted panel x 1000x (BASELINE configs[4], depth stress)"),
+}
+
+
+def run_synth(args):
+    """Strong scaling: the tiles of ONE genome are dealt round-robin to the ranks (region sharding, no collective); every rank
+    generates its own tiles in HBM, walks them in one launch per step and keeps its calls; value = positions of all ranks / max time."""
+    rank, world, local, dist = _dist_setup(args.gpus)
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from ngsepcore_b200 import capi
+    cfg = SYNTH_CONFIGS[args.config]
+    device = local if world > 1 else 0
+    ctx = capi.Context(device=device)
+    tiles = [(ci, f, min(L, f + cfg["tile"] - 1)) for ci, L in enumerate(cfg["contigs"]) for f in range(1, L + 1, cfg["tile"])]
+    mine = tiles[rank::world]
+    t0 = time.time()
+    for ci in sorted({t[0] for t in mine}):
+        ctx.synth_reference(ci, cfg["contigs"][ci], seed=1031, gc=cfg["gc"])
+    slots = [ctx.synth_tile(ci, f, l, depth=cfg["depth"], seed=3033) for ci, f, l in mine]
+    gen_s = time.time() - t0
+    shapes = [ctx.resident_download(s, data=False) for s in slots]
+    n_reads = sum(t["n_reads"] for t in shapes)
+    in_bytes = sum(t["n_reads"] * 16 + t["n_words"] * 4 + t["n_qual"] for t in shapes)
+    for _ in range(max(3, args.warmup)):
+        ctx.resident_run(-1)
+    st = ctx.resident_stats()
+    sampler = _ClockSampler(device) if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+    step_ms, pileup_ms, kernels_ms = [], 0.0, 0.0
+    for _ in range(args.steps):
+        ctx.timer_start()
+        ctx.resident_run(-1)
+        step_ms.append(ctx.timer_stop())
+        rs = ctx.resident_stats()
+        pileup_ms += rs.pileup_ms
+        kernels_ms += rs.kernel_ms
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    L = 100
+    alg = n_reads * (16 + 4 + (L + 3) // 4 + L) + sum(l - f + 1 for _, f, l in mine) + 64 * st.calls      # SURVEY.md 8d
+    (covered, bases, calls, reads, alg_all, in_all), (total_ms, pileup_ms, kernels_ms, gen_s) = reduce_over_ranks(
+        dist, "cuda", sums=[st.covered_positions, st.aligned_bases, st.calls, n_reads, alg, in_bytes], maxima=[float(sum(step_ms)), pileup_ms, kernels_ms, gen_s])
+    if rank == 0:
+        peak, peak_src = _peaks()
+        ms = total_ms / args.steps
+        per_gpu_alg = alg_all / world
+        line = {"metric": METRIC, "value": covered / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (generated on the device)",
+                "config": {"workload": cfg["what"] + ", reads generated in HBM (ngsep_synth_tile), tiles of %d positions dealt round-robin to the GPUs" % cfg["tile"],
+                           "depth": cfg["depth"], "genome_bp": int(sum(cfg["contigs"])), "reads": int(reads), "tiles": len(tiles),
+                           "genotyped_positions": int(covered), "calls": int(calls), "resident_input_bytes": int(in_all),
+                           "l2": "inputs larger than L2 (%.1f GB of packed tiles per GPU resident in HBM, walked every step)" % (in_all / world / 1e9),
+                           "parallelism": f"region tiles x{world}, no collective"},
+                "aligned_bases_per_sec": bases / (ms / 1e3),
+                "roofline": {"bound": "hbm", "achieved": per_gpu_alg / (kernels_ms / args.steps / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": per_gpu_alg / (kernels_ms / args.steps / 1e3) / 1e9 / peak, "traffic": None,
+                             "kernel": "the device step: k_pileup_windows + k_genotype_columns (per GPU, slowest rank)", "algorithmic_bytes_per_step_per_gpu": per_gpu_alg,
+                             "kernels_ms_per_step": kernels_ms / args.steps, "k_pileup_windows_ms_per_step": pileup_ms / args.steps, "peak_source": peak_src},
+                "e2e": None, "gpu_launches": int(2 * args.steps * world), "clocks": clocks, "host": {"generate_s": gen_s}}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -451,9 +530,13 @@ def main():
     ap.add_argument("--no-pipeline", action="store_true", help="skip the informational whole-detector run")
     ap.add_argument("--quality-in-place", action="store_true", help="e2e: leave page-locked quality buffers on the host (NGSEP_F_QUALITY_IN_PLACE)")
     ap.add_argument("--reference-sample-bp", type=int, default=1 << 40, help="reference arm: reference bases per step (default: the whole workload)")
+    ap.add_argument("--config", default="c1", choices=["c1"] + sorted(SYNTH_CONFIGS),
+                    help="c1 (default): BASELINE configs[1], host-simulated yeast 30x; c3 / c5 / panel: configs[2] / [4] with device-generated inputs (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "c1":
+        run_synth(args)
     else:
         run_gpu(args)
 

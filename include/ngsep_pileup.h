@@ -229,6 +229,27 @@ int ngsep_resident_run(void* ctx, int slot);
 int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
 
+/* Synthetic inputs generated ON THE DEVICE — BASELINE configs[2] and [4] (64 Mb at 60x, 3.1 Gb at 30x, the 1000x panel): the
+ * reference sequence and the packed tile of any region are pure functions of (seed, sequence, position / read index), so no
+ * input crosses PCIe and every tile of a genome sees the same reads on whatever GPU.  Rates as the reference's simulator
+ * (simulation/SingleIndividualSimulator.java:57-58); reads are one match block each.  ngsep_synth_tile stages the tile as a
+ * resident slot (ngsep_resident_run / _fetch as usual); ngsep_resident_download / ngsep_ref_download bring a tile and its
+ * reference back so that a slice can be handed to the CPU oracle as SAM text. */
+typedef struct ngsep_synth_params {
+    uint64_t seed;
+    double depth;       /* read_len * reads / positions                          */
+    int32_t read_len;   /* 16..1000                                              */
+    int32_t reserved;
+    double snv_rate;    /* planted SNV sites per base, half of them heterozygous */
+    double error_rate;  /* substitution errors per read base                     */
+} ngsep_synth_params;
+int ngsep_synth_reference(void* ctx, int32_t seq_idx, int64_t length, uint64_t seed, double gc);
+int ngsep_synth_tile(void* ctx, int32_t seq_idx, int32_t tile_first, int32_t tile_last, const ngsep_synth_params* params, int* slot);
+/* shape: extents, counts and quality coding of the resident tile; hdr / payload / qual (each may be NULL) receive shape->n_reads
+ * headers, shape->n_words words, shape->n_qual bytes. */
+int ngsep_resident_download(void* ctx, int slot, ngsep_tile* shape, ngsep_read_hdr* hdr, uint32_t* payload, uint8_t* qual);
+int ngsep_ref_download(void* ctx, int32_t seq_idx, char* bases, int64_t length);
+
 /* CUDA-event stopwatch on the context stream (ngsep_timer_stop also waits for the genotype kernels of pipelined tiles). */
 int ngsep_timer_start(void* ctx);
 int ngsep_timer_stop(void* ctx, float* elapsed_ms);   /* synchronises the stream */

@@ -154,6 +154,42 @@ JNIEXPORT void JNICALL JNI_FN(residentStats)(JNIEnv* env, jclass cls, jlong ctx,
     if (rc != NGSEP_OK) { throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_resident_stats"); return; }
     fill_stats(env, stats, &st);
 }
+/* ngsep_synth_reference */
+JNIEXPORT void JNICALL JNI_FN(synthReference)(JNIEnv* env, jclass cls, jlong ctx, jint seqIdx, jlong length, jlong seed, jdouble gc) {
+    (void)cls;
+    int rc = ngsep_synth_reference((void*)(intptr_t)ctx, seqIdx, (int64_t)length, (uint64_t)seed, gc);
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_synth_reference");
+}
+/* ngsep_synth_tile */
+JNIEXPORT jint JNICALL JNI_FN(synthTile)(JNIEnv* env, jclass cls, jlong ctx, jint seqIdx, jint first, jint last, jlong seed, jdouble depth, jint readLen, jdouble snvRate,
+                                         jdouble errorRate) {
+    (void)cls;
+    ngsep_synth_params p;
+    memset(&p, 0, sizeof p);
+    p.seed = (uint64_t)seed; p.depth = depth; p.read_len = readLen; p.snv_rate = snvRate; p.error_rate = errorRate;
+    int slot = 0;
+    int rc = ngsep_synth_tile((void*)(intptr_t)ctx, seqIdx, first, last, &p, &slot);
+    if (rc != NGSEP_OK) { throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_synth_tile"); return -1; }
+    return slot;
+}
+/* ngsep_resident_download: shape = {n_reads, n_words, n_qual, qual_bits}; buffers may be null */
+JNIEXPORT void JNICALL JNI_FN(residentDownload)(JNIEnv* env, jclass cls, jlong ctx, jint slot, jlongArray shape, jobject hdr, jobject payload, jobject qual) {
+    (void)cls;
+    ngsep_tile t;
+    int rc = ngsep_resident_download((void*)(intptr_t)ctx, slot, &t, (ngsep_read_hdr*)direct(env, hdr), (uint32_t*)direct(env, payload), (uint8_t*)direct(env, qual));
+    if (rc != NGSEP_OK) { throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_resident_download"); return; }
+    jlong v[4] = {(jlong)t.n_reads, (jlong)t.n_words, (jlong)t.n_qual, (jlong)t.qual_bits};
+    if (shape) (*env)->SetLongArrayRegion(env, shape, 0, 4, v);
+}
+/* ngsep_ref_download */
+JNIEXPORT void JNICALL JNI_FN(refDownload)(JNIEnv* env, jclass cls, jlong ctx, jint seqIdx, jbyteArray bases) {
+    (void)cls;
+    jsize n = (*env)->GetArrayLength(env, bases);
+    jbyte* b = (*env)->GetByteArrayElements(env, bases, NULL);
+    int rc = ngsep_ref_download((void*)(intptr_t)ctx, seqIdx, (char*)b, (int64_t)n);
+    (*env)->ReleaseByteArrayElements(env, bases, b, 0);
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_ref_download");
+}
 /* ngsep_timer_start */
 JNIEXPORT void JNICALL JNI_FN(timerStart)(JNIEnv* env, jclass cls, jlong ctx) { (void)cls; int rc = ngsep_timer_start((void*)(intptr_t)ctx); if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_timer_start"); }
 /* ngsep_timer_stop */

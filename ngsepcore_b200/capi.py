@@ -35,6 +35,11 @@ class Tile(C.Structure):
                 ("qual_bits", C.c_uint32), ("qual_dict", C.c_uint8 * 16), ("reserved", C.c_uint32)]
 
 
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("depth", C.c_double), ("read_len", C.c_int32), ("reserved", C.c_int32), ("snv_rate", C.c_double),
+                ("error_rate", C.c_double)]
+
+
 class TileStats(C.Structure):
     _fields_ = [("covered_positions", C.c_uint64), ("candidate_positions", C.c_uint64), ("calls", C.c_uint64),
                 ("aligned_bases", C.c_uint64), ("kernel_ms", C.c_float), ("pileup_ms", C.c_float), ("kernel_launches", C.c_uint32), ("open_columns", C.c_uint32),
@@ -49,7 +54,8 @@ CALL_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)
 EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_ref_upload", "ngsep_tile_submit",
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
            "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
-           "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop"]
+           "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop",
+           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download"]
 
 # multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
 SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
@@ -87,6 +93,10 @@ def load_library() -> C.CDLL:
     lib.ngsep_tile_fetch_pop.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p, C.POINTER(TileStats)]
     lib.ngsep_resident_fetch_pop.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p, C.c_void_p,
                                              C.POINTER(TileStats)]
+    lib.ngsep_synth_reference.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double]
+    lib.ngsep_synth_tile.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(SynthParams), C.POINTER(C.c_int)]
+    lib.ngsep_resident_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(Tile), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ngsep_ref_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     _lib = lib
     return lib
 
@@ -201,6 +211,36 @@ class Context:
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1
         return slot.value
+
+    # ---- synthetic inputs generated on the device (BASELINE configs[2], [4]) ---------------------------------------------------
+    def synth_reference(self, seq_idx: int, length: int, seed: int = 1031, gc: float = 0.41) -> None:
+        self._check(self.lib.ngsep_synth_reference(self.h, seq_idx, length, seed, gc), "ngsep_synth_reference")
+
+    def synth_tile(self, seq_idx: int, tile_first: int, tile_last: int, depth: float = 30.0, read_len: int = 100, seed: int = 3033,
+                   snv_rate: float = 1e-3, error_rate: float = 2e-3) -> int:
+        """Generates the packed tile of a region in HBM and stages it as a resident slot; returns the slot."""
+        p = SynthParams(seed, depth, read_len, 0, snv_rate, error_rate)
+        slot = C.c_int(0)
+        self._check(self.lib.ngsep_synth_tile(self.h, seq_idx, tile_first, tile_last, C.byref(p), C.byref(slot)), "ngsep_synth_tile")
+        self._slot_npos[slot.value] = tile_last - tile_first + 1
+        return slot.value
+
+    def resident_download(self, slot: int, data: bool = True):
+        """dict(first, last, hdr, payload, qual, quality=(bits, dict16), max_span, max_back) of a resident tile (arrays only with data)."""
+        t = Tile()
+        self._check(self.lib.ngsep_resident_download(self.h, slot, C.byref(t), None, None, None), "ngsep_resident_download")
+        out = dict(seq_idx=t.seq_idx, first=t.tile_first, last=t.tile_last, n_reads=t.n_reads, n_words=t.n_words, n_qual=t.n_qual, max_span=t.max_span,
+                   max_back=t.max_back, quality=(t.qual_bits, bytes(t.qual_dict)))
+        if data:
+            hdr, pay, qual = np.zeros(t.n_reads, HDR_DTYPE), np.zeros(t.n_words, np.uint32), np.zeros(t.n_qual, np.uint8)
+            self._check(self.lib.ngsep_resident_download(self.h, slot, C.byref(t), hdr.ctypes.data, pay.ctypes.data, qual.ctypes.data), "ngsep_resident_download")
+            out.update(hdr=hdr, payload=pay, qual=qual)
+        return out
+
+    def ref_download(self, seq_idx: int, length: int) -> np.ndarray:
+        out = np.zeros(length, np.uint8)
+        self._check(self.lib.ngsep_ref_download(self.h, seq_idx, out.ctypes.data, length), "ngsep_ref_download")
+        return out
 
     def resident_run(self, slot: int = -1) -> None:
         self._check(self.lib.ngsep_resident_run(self.h, slot), "ngsep_resident_run")

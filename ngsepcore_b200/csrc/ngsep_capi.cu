@@ -72,6 +72,7 @@ struct Slot {
     int grid = 0;
     uint64_t aligned_bases = 0;
     uint64_t h2d_bytes = 0;                   // bytes of the tile copied to the device at staging
+    uint64_t n_words = 0, n_qual = 0;         // payload words / quality bytes of the staged tile
     bool qual_on_host = false;                // quality bytes stay in the caller's page-locked buffer (read on demand by the genotype kernel)
     unsigned int launches = 0;
     void release() {
@@ -319,11 +320,11 @@ const uint8_t* mapped_host_alias(const void* p, size_t bytes) {
     return (const uint8_t*)a0.devicePointer;
 }
 
-int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = false) {
+int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = false, const SynthSpec* synth = nullptr, int64_t synth_g_lo = 0) {
     if (!t) return fail(c, NGSEP_EINVAL, "null argument");
     if (t->n_reads < 0 || t->tile_first < 1 || t->tile_last < t->tile_first) return fail(c, NGSEP_EINVAL, "bad tile extents");
     if (t->seq_idx < 0 || (size_t)t->seq_idx >= c->refs.size() || !c->refs[t->seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
-    if (t->n_reads > 0 && (!t->hdr || !t->payload || !t->qual)) return fail(c, NGSEP_EINVAL, "null tile buffers");
+    if (!synth && t->n_reads > 0 && (!t->hdr || !t->payload || !t->qual)) return fail(c, NGSEP_EINVAL, "null tile buffers");
     if (t->n_qual > 0x3fffffff0ull) return fail(c, NGSEP_EINVAL, "tile qualities exceed 16 GiB");
     const bool multi = c->params.n_samples > 1;
     if (multi && !c->samples_set) return fail(c, NGSEP_ESTATE, "multi-sample context: call ngsep_samples_set before the first tile");
@@ -352,10 +353,11 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     // The bulk copies run on the COPY stream, the kernels on the context stream: the copies of the next tile overlap the
     // kernels of this one (a slot's buffers are only reused after its tile has been fetched).  Pageable sources are staged by
     // the driver synchronously with the host thread anyway: they stay on the context stream.
-    const bool pinned_src = t->n_reads > 0 && mapped_host_alias(t->payload, (size_t)t->n_words * 4) != nullptr;
+    const bool pinned_src = !synth && t->n_reads > 0 && mapped_host_alias(t->payload, (size_t)t->n_words * 4) != nullptr;
     cudaStream_t copy_stream = pinned_src ? c->copy_stream : c->stream;
     if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream), "read-group copy");
-    if (t->n_reads > 0) {
+    if (synth) launch_synth_tile(*synth, synth_g_lo, t->n_reads, ref.ref2, s->d_hdr.p, s->d_pay.p, s->d_qual.p, copy_stream);   // generated in place: nothing crosses PCIe
+    else if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, copy_stream), "hdr copy");
         CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, copy_stream), "payload copy");
         if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, copy_stream), "quality copy");
@@ -381,8 +383,9 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         CK(launch_group_index(s->d_group.p, c->d_gins.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
            "group index launch");
     }
-    s->h2d_bytes = (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
+    s->h2d_bytes = synth ? 0 : (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
                    (multi ? (uint64_t)t->n_reads * 2 : 0);
+    s->n_words = (uint64_t)t->n_words; s->n_qual = (uint64_t)t->n_qual;
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
     // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
     CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
@@ -419,7 +422,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         CK(s->d_scalls.reserve(s->d_sites.cap * (size_t)c->params.n_samples), "sample call alloc");
         d.pop_sites = s->d_sites.p; d.pop_calls = s->d_scalls.p; d.calls = nullptr; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_sites.cap;
     } else {
-        size_t cap_calls = (size_t)(tile_len / 16) + 65536;
+        size_t cap_calls = (size_t)(tile_len / 64) + 16384;   // ~20x the expected SNV density; a tile that needs more grows the buffer and reruns
         if (s->d_calls.cap < cap_calls) CK(s->d_calls.reserve(cap_calls), "calls alloc");
         d.calls = s->d_calls.p; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_calls.cap;
     }
@@ -808,6 +811,109 @@ int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
     c->slots.push_back(s);
     c->batch_dirty = true;
     *slot = (int)c->slots.size() - 1;
+    return NGSEP_OK;
+}
+
+// ---- synthetic inputs generated on the device (synth_kernels.cu) ------------------------------------------------------------
+int ngsep_synth_reference(void* ctx, int32_t seq_idx, int64_t length, uint64_t seed, double gc) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || seq_idx < 0 || length <= 0 || !(gc >= 0.0 && gc <= 1.0)) return fail(c, NGSEP_EINVAL, "bad reference arguments");
+    CK(cudaSetDevice(c->device), "set device");
+    if ((size_t)seq_idx >= c->refs.size()) c->refs.resize(seq_idx + 1);
+    RefSeq& r = c->refs[seq_idx];
+    r.release();
+    c->batch_dirty = true;
+    const int64_t n32 = (length + 31) / 32;
+    const size_t w2 = kRefFrontWords + (size_t)n32 * 2 + kRefTailWords2, w1 = kRefFrontWords + (size_t)n32 + kRefTailWords1;
+    char* d_ascii = nullptr;
+    CK(cudaMalloc((void**)&d_ascii, (size_t)length), "ref ascii alloc");
+    cudaError_t e = cudaMalloc((void**)&r.a_ref2, w2 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r.a_refn, w1 * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r.a_refl, w1 * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_ref2, 0, w2 * 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_refn, 0xff, w1 * 4, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(r.a_refl, 0, w1 * 4, c->stream);
+    if (e == cudaSuccess) {
+        r.ref2 = r.a_ref2 + kRefFrontWords; r.ref_n = r.a_refn + kRefFrontWords; r.ref_l = r.a_refl + kRefFrontWords;
+        launch_synth_ref(d_ascii, length, seed + (uint64_t)seq_idx * 0x100000001b3ull, gc, c->stream);
+        launch_ref_pack(d_ascii, length, r.ref2, r.ref_n, r.ref_l, c->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_ascii);
+    if (e != cudaSuccess) { r.release(); return cuda_fail(c, e, "reference generation"); }
+    r.len = length;
+    return NGSEP_OK;
+}
+
+int ngsep_ref_download(void* ctx, int32_t seq_idx, char* bases, int64_t length) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !bases || seq_idx < 0 || (size_t)seq_idx >= c->refs.size() || !c->refs[seq_idx].ref2 || length != c->refs[seq_idx].len) return fail(c, NGSEP_EINVAL, "bad reference arguments");
+    CK(cudaSetDevice(c->device), "set device");
+    const RefSeq& r = c->refs[seq_idx];
+    char* d_ascii = nullptr;
+    CK(cudaMalloc((void**)&d_ascii, (size_t)length), "ref ascii alloc");
+    launch_ref_unpack(r.ref2, r.ref_n, r.ref_l, length, d_ascii, c->stream);
+    cudaError_t e = cudaMemcpyAsync(bases, d_ascii, (size_t)length, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_ascii);
+    if (e != cudaSuccess) return cuda_fail(c, e, "reference download");
+    return NGSEP_OK;
+}
+
+int ngsep_synth_tile(void* ctx, int32_t seq_idx, int32_t tile_first, int32_t tile_last, const ngsep_synth_params* p, int* slot) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !p || !slot) return NGSEP_EINVAL;
+    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "synthetic tiles are single-sample");
+    if (seq_idx < 0 || (size_t)seq_idx >= c->refs.size() || !c->refs[seq_idx].ref2) return fail(c, NGSEP_ESTATE, "reference sequence not uploaded");
+    if (p->read_len < 16 || p->read_len > 1000 || !(p->depth > 0.0) || !(p->snv_rate >= 0.0 && p->snv_rate < 1.0) || !(p->error_rate >= 0.0 && p->error_rate < 1.0))
+        return fail(c, NGSEP_EINVAL, "bad synthetic-read parameters");
+    CK(cudaSetDevice(c->device), "set device");
+    SynthSpec sp;
+    sp.seed = p->seed + (uint64_t)seq_idx * 0x100000001b3ull;
+    sp.step = (double)p->read_len / p->depth;
+    sp.read_len = p->read_len;
+    sp.snv_thr = (uint32_t)(p->snv_rate * 4294967296.0);
+    sp.err_thr = (uint32_t)(p->error_rate * 4294967296.0);
+    int64_t g_lo = 0, n = 0;
+    synth_tile_shape(sp, c->refs[seq_idx].len, tile_first, tile_last, &g_lo, &n);
+    if (n > 0x7ffffff0ll) return fail(c, NGSEP_EINVAL, "tile holds too many reads (split it)");
+    const int L = p->read_len, W = 1 + ((L + 15) >> 4) + ((L + 31) >> 5) + 1, Q = (((L * 2 + 7) >> 3) + 3) >> 2;
+    ngsep_tile t;
+    std::memset(&t, 0, sizeof t);
+    t.seq_idx = seq_idx; t.tile_first = tile_first; t.tile_last = tile_last; t.n_reads = (int32_t)n;
+    t.max_span = L; t.max_back = 0;
+    t.n_words = (uint64_t)n * (uint64_t)W;
+    t.n_qual = (uint64_t)n * (uint64_t)Q * 4ull;
+    t.qual_bits = 2;
+    t.qual_dict[0] = 35; t.qual_dict[1] = 43; t.qual_dict[2] = 53; t.qual_dict[3] = 63;   // q <= 3 (never counted), 10, 20, >= 30
+    Slot* s = nullptr;
+    int rc = new_slot(c, &s, c->slots.size());
+    if (rc != NGSEP_OK) return rc;
+    rc = stage_slot(c, s, &t, false, &sp, g_lo);
+    if (rc != NGSEP_OK) { s->release(); delete s; return rc; }
+    c->slots.push_back(s);
+    c->batch_dirty = true;
+    *slot = (int)c->slots.size() - 1;
+    return NGSEP_OK;
+}
+
+int ngsep_resident_download(void* ctx, int slot, ngsep_tile* shape, ngsep_read_hdr* hdr, uint32_t* payload, uint8_t* qual) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c || !shape) return NGSEP_EINVAL;
+    if (slot < 1 || (size_t)slot >= c->slots.size()) return fail(c, NGSEP_EINVAL, "bad slot");
+    CK(cudaSetDevice(c->device), "set device");
+    Slot* s = c->slots[slot];
+    CK(cudaStreamSynchronize(c->copy_stream), "sync");
+    CK(cudaStreamSynchronize(c->stream), "sync");
+    std::memset(shape, 0, sizeof *shape);
+    shape->seq_idx = s->tile.seq_idx; shape->tile_first = s->tile.tile_first; shape->tile_last = s->tile.tile_last; shape->n_reads = s->tile.n_reads;
+    shape->max_span = s->tile.max_span; shape->max_back = s->tile.max_back; shape->n_words = s->n_words; shape->n_qual = s->n_qual;
+    shape->qual_bits = s->tile.qual_bits;
+    std::memcpy(shape->qual_dict, s->tile.qual_dict, 16);
+    if (hdr) CK(cudaMemcpy(hdr, s->d_hdr.p, (size_t)s->tile.n_reads * sizeof(ngsep_read_hdr), cudaMemcpyDeviceToHost), "hdr download");
+    if (payload) CK(cudaMemcpy(payload, s->d_pay.p, (size_t)s->n_words * 4, cudaMemcpyDeviceToHost), "payload download");
+    if (qual && !s->qual_on_host) CK(cudaMemcpy(qual, s->d_qual.p, (size_t)s->n_qual, cudaMemcpyDeviceToHost), "quality download");
     return NGSEP_OK;
 }
 

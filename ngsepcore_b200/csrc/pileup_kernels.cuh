@@ -116,4 +116,11 @@ cudaError_t launch_group_index(const uint16_t* group, const uint8_t* in_sample /
 int group_blocks(int n);   // blocks of record indexes in the per-group block table
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
+// synthetic inputs generated on the device (synth_kernels.cu)
+struct SynthSpec { uint64_t seed; double step; int read_len; uint32_t snv_thr, err_thr; };   // step = read_len / depth; thresholds = rate * 2^32
+void launch_synth_ref(char* ascii, int64_t len, uint64_t seed, double gc, cudaStream_t s);
+void launch_ref_unpack(const uint32_t* ref2, const uint32_t* ref_n, const uint32_t* ref_l, int64_t len, char* ascii, cudaStream_t s);
+void synth_tile_shape(const SynthSpec& sp, int64_t seq_len, int32_t tile_first, int32_t tile_last, int64_t* g_lo, int64_t* n_reads);
+void launch_synth_tile(const SynthSpec& sp, int64_t g_lo, int n_reads, const uint32_t* ref2, ngsep_read_hdr* hdr, uint32_t* payload, uint8_t* qual, cudaStream_t s);
+
 }  // namespace ngsep_b200
