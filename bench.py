@@ -447,6 +447,8 @@ GRCH38_LIKE = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979,
 SYNTH_CONFIGS = {
     "c3": dict(contigs=[64444167], depth=60.0, tile=2_000_000, gc=0.44, what="synthetic 64 Mb (chr20-sized) sequence x 60x (BASELINE configs[2])"),
     "c5": dict(contigs=GRCH38_LIKE, depth=30.0, tile=4_000_000, gc=0.41, what="synthetic 3.1 Gb human-scale genome (24 sequences) x 30x (BASELINE configs[4])"),
+    "c1s": dict(contigs=[230218, 813184, 316620, 1531933, 576874, 270161, 1090940, 562643, 439888, 745751, 666816, 1078177, 924431, 784333, 1091291, 948066, 85779],
+                depth=30.0, tile=2_000_000, gc=0.38, what="yeast-sized genome (17 sequences, 12.16 Mb) x 30x with device-generated reads (configs[1]'s shape without indels)"),
     "panel": dict(contigs=[2_000_000], depth=1000.0, tile=125_000, gc=0.41, what="2 Mb targeted panel x 1000x (BASELINE configs[4], depth stress)"),
 }
 

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libngsep_pileup.so")
+LIB_PATH = os.environ.get("NGSEP_PILEUP_LIB") or os.path.join(_HERE, "libngsep_pileup.so")   # (the override is for kernel experiments)
 
 N_TABLES = 95
 F_STRAND_BIAS, F_IGNORE_LOWER_REF, F_EMIT_ALL, F_QUALITY_IN_PLACE = 0x1, 0x2, 0x8, 0x10

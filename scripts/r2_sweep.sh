@@ -25,6 +25,8 @@ s1_1536) run s1_1536 NGSEP_WINDOW=1536 NGSEP_PAY_CAP_WORDS=7680 NGSEP_MIN_BLOCKS
 t128) run t128 NGSEP_THREADS=128 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 ;;
 geno6) run geno6 NGSEP_GENO_MIN_BLOCKS=6 ;;
 entries) run entries NGSEP_ENTRIES=1 ;;
+nofence) run nofence NGSEP_PILEUP_LIB=$PWD/ngsepcore_b200/_lib_nofence.so ;;
+warp0) run warp0 NGSEP_PILEUP_LIB=$PWD/ngsepcore_b200/_lib_warp0.so ;;
 g16) run g16 NGSEP_GENO_BLOCKS_PER_SM=16 ;;
 s1_640) run s1_640 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 NGSEP_MIN_BLOCKS=5 ;;
 t128_640) run t128_640 NGSEP_THREADS=128 NGSEP_WINDOW=640 NGSEP_PAY_CAP_WORDS=3200 NGSEP_MIN_BLOCKS=10 ;;
