@@ -180,6 +180,7 @@ constexpr uint32_t kListPosMask = (1u << kListShift) - 1u;
 constexpr int kListMaxRec = (1 << (32 - kListShift)) - 1;
 constexpr int kProofRefShift = 13, kProofNeedShift = 15, kProofRecShift = 21;
 constexpr int kProofMaxRec = (1 << (32 - kProofRecShift)) - 1, kProofNoNeed = 63;
+constexpr int kProofRings = 8;   // rings of 2 x 32 records the last proof stage may add around the flagging record (deep columns)
 
 // rec = index of the flagging record inside the window's record range
 __device__ __forceinline__ void flag_candidate(const WinCtx& w, int idx, int rec) {
@@ -805,9 +806,18 @@ __device__ __forceinline__ void proof_phase(const Recs<kGlobal>& R, const ExactC
             const uint32_t e = __shfl_sync(kFull, ent, src);
             const int e_need = (int)((e >> kProofNeedShift) & 63u);
             const int e_li = (int)(e & kListPosMask), e_pos = x.wbeg + e_li + 1;
-            if (e_need <= 30) {
-                const int ok2 = counted_ref_base(R, (int)(e >> kProofRecShift) - 16 + lane, e_pos, (int)((e >> kProofRefShift) & 3u));
-                if (__popc(__ballot_sync(kFull, ok2 != 0)) >= e_need) continue;
+            if (e_need < kProofNoNeed) {
+                // the 32 records around the flagging one, then — deep columns, whose k_min is beyond 32 — ring after ring of 32
+                // records on either side (any subset of the records gives a lower bound of the counted reference bases)
+                const int rc = (int)(e >> kProofRecShift), e_ref = (int)((e >> kProofRefShift) & 3u);
+                int got = __popc(__ballot_sync(kFull, counted_ref_base(R, rc - 16 + lane, e_pos, e_ref) != 0));
+                for (int ring = 1; got < e_need && ring < kProofRings && (rc - 16 - 32 * (ring - 1) > 0 || rc + 16 + 32 * (ring - 1) < R.n); ring++) {
+                    const int before = got;
+                    got += __popc(__ballot_sync(kFull, counted_ref_base(R, rc - 16 - 32 * ring + lane, e_pos, e_ref) != 0));
+                    got += __popc(__ballot_sync(kFull, counted_ref_base(R, rc + 16 + 32 * (ring - 1) + lane, e_pos, e_ref) != 0));
+                    if (got == before) break;   // the records this far from the flagging one no longer reach the position
+                }
+                if (got >= e_need) continue;
             }
             emit_open_column<kGlobal>(R, cq, sink, ghdr, x.tile, x.rec0, e_pos, (int)((e >> kProofRefShift) & 3u), x.max_span, x.max_back, x.span_capped, lane);
         }
