@@ -100,6 +100,10 @@ int ngsep_host_pack(const ngsep_host_batch* b, int seq_idx, int min_mq, int max_
 int ngsep_ssvd_pack(void* det, const ngsep_host_batch* b, int seq_idx, ngsep_read_hdr** hdr, uint32_t** payload, uint8_t** qual, int64_t* n_reads,
                     uint64_t* n_words, uint64_t* n_qual, int* max_span, int* max_back, int* tile_first, int* tile_last, uint64_t* aligned_bases);
 void ngsep_host_free(void* p);
+/* CoverageStats module (discovery/CoverageStatisticsCalculator.java:119-143, 250-256; option ids -i -o -minMQ of main/CommandsDescriptor.xml:458-478):
+ * admission with secondary alignments and 100 alignments per start position on the host, read-depth histograms per region tile on the
+ * device (ngsep_coverage_histogram), the printed table (depth, positions, positions counting unique alignments only; "More") as text. */
+int ngsep_coverage_stats(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_mq, int device, char** text);
 /* How the quality array of the tile the calling thread packed last (ngsep_host_pack / ngsep_ssvd_pack) is coded: the values for
  * ngsep_tile.qual_bits and ngsep_tile.qual_dict. */
 int ngsep_host_pack_quality(uint32_t* qual_bits, uint8_t* qual_dict16);

@@ -229,6 +229,14 @@ int ngsep_resident_run(void* ctx, int slot);
 int ngsep_resident_fetch(void* ctx, int slot, ngsep_snv_call* out, size_t cap, size_t* n_out, int32_t* counts_dbg, ngsep_tile_stats* stats);
 int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
 
+/* CoverageStatisticsCalculator (discovery/CoverageStatisticsCalculator.java:186-199, 250-256), a PileupListener that only needs
+ * PileupRecord.getNumAlignments / getNumUniqueAlns: the read-depth histograms of the region [tile_first, tile_last] given the
+ * admitted reads that overlap it (first / last = ReadAlignment.getFirst / getLast, unique = ReadAlignment.isUnique).
+ * hist_all[d] / hist_unique[d] = positions of the tile covered by exactly d (unique) alignments for d < max_coverage,
+ * [max_coverage] = positions with more.  Synchronous; the histograms of the tiles of a run are summed by the caller. */
+int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, int64_t n, const int32_t* first, const int32_t* last, const uint8_t* unique,
+                             int32_t max_coverage, uint64_t* hist_all, uint64_t* hist_unique);
+
 /* Synthetic inputs generated ON THE DEVICE — BASELINE configs[2] and [4] (64 Mb at 60x, 3.1 Gb at 30x, the 1000x panel): the
  * reference sequence and the packed tile of any region are pure functions of (seed, sequence, position / read index), so no
  * input crosses PCIe and every tile of a genome sees the same reads on whatever GPU.  Rates as the reference's simulator

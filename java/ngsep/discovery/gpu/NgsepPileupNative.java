@@ -42,6 +42,7 @@ public final class NgsepPileupNative implements AutoCloseable {
 	static native void residentRun(long ctx, int slot) throws IOException;
 	static native long residentFetch(long ctx, int slot, ByteBuffer calls, long[] stats) throws IOException;
 	static native void residentStats(long ctx, long[] stats) throws IOException;
+	static native void coverageHistogram(long ctx, int tileFirst, int tileLast, int[] first, int[] last, byte[] unique, int maxCoverage, long[] histAll, long[] histUnique) throws IOException;
 	static native void synthReference(long ctx, int seqIdx, long length, long seed, double gc) throws IOException;
 	static native int synthTile(long ctx, int seqIdx, int first, int last, long seed, double depth, int readLen, double snvRate, double errorRate) throws IOException;
 	static native void residentDownload(long ctx, int slot, long[] shape, ByteBuffer hdr, ByteBuffer payload, ByteBuffer qual) throws IOException;

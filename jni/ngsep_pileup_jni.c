@@ -154,6 +154,25 @@ JNIEXPORT void JNICALL JNI_FN(residentStats)(JNIEnv* env, jclass cls, jlong ctx,
     if (rc != NGSEP_OK) { throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_resident_stats"); return; }
     fill_stats(env, stats, &st);
 }
+/* ngsep_coverage_histogram: histAll / histUnique hold maxCoverage + 1 counts */
+JNIEXPORT void JNICALL JNI_FN(coverageHistogram)(JNIEnv* env, jclass cls, jlong ctx, jint tileFirst, jint tileLast, jintArray first, jintArray last, jbyteArray unique,
+                                                 jint maxCoverage, jlongArray histAll, jlongArray histUnique) {
+    (void)cls;
+    jsize n = (*env)->GetArrayLength(env, first);
+    jint* f = (*env)->GetIntArrayElements(env, first, NULL);
+    jint* l = (*env)->GetIntArrayElements(env, last, NULL);
+    jbyte* u = (*env)->GetByteArrayElements(env, unique, NULL);
+    jlong* ha = (*env)->GetLongArrayElements(env, histAll, NULL);
+    jlong* hu = (*env)->GetLongArrayElements(env, histUnique, NULL);
+    int rc = ngsep_coverage_histogram((void*)(intptr_t)ctx, tileFirst, tileLast, (int64_t)n, (const int32_t*)f, (const int32_t*)l, (const uint8_t*)u, maxCoverage,
+                                      (uint64_t*)ha, (uint64_t*)hu);
+    (*env)->ReleaseIntArrayElements(env, first, f, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, last, l, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, unique, u, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, histAll, ha, 0);
+    (*env)->ReleaseLongArrayElements(env, histUnique, hu, 0);
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_coverage_histogram");
+}
 /* ngsep_synth_reference */
 JNIEXPORT void JNICALL JNI_FN(synthReference)(JNIEnv* env, jclass cls, jlong ctx, jint seqIdx, jlong length, jlong seed, jdouble gc) {
     (void)cls;

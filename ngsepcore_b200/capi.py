@@ -55,7 +55,7 @@ EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_r
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
            "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
            "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop",
-           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download"]
+           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram"]
 
 # multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
 SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
@@ -97,6 +97,7 @@ def load_library() -> C.CDLL:
     lib.ngsep_synth_tile.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(SynthParams), C.POINTER(C.c_int)]
     lib.ngsep_resident_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(Tile), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ngsep_ref_download.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    lib.ngsep_coverage_histogram.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -211,6 +212,14 @@ class Context:
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1
         return slot.value
+
+    def coverage_histogram(self, tile_first: int, tile_last: int, first, last, unique, max_coverage: int = 300):
+        """Read-depth histograms (all / unique alignments) of a region: arrays of max_coverage + 1 counts, [max_coverage] = more."""
+        first = np.ascontiguousarray(first, np.int32); last = np.ascontiguousarray(last, np.int32); unique = np.ascontiguousarray(unique, np.uint8)
+        ha, hu = np.zeros(max_coverage + 1, np.uint64), np.zeros(max_coverage + 1, np.uint64)
+        self._check(self.lib.ngsep_coverage_histogram(self.h, tile_first, tile_last, first.size, first.ctypes.data, last.ctypes.data, unique.ctypes.data,
+                                                      max_coverage, ha.ctypes.data, hu.ctypes.data), "ngsep_coverage_histogram")
+        return ha, hu
 
     # ---- synthetic inputs generated on the device (BASELINE configs[2], [4]) ---------------------------------------------------
     def synth_reference(self, seq_idx: int, length: int, seed: int = 1031, gc: float = 0.41) -> None:

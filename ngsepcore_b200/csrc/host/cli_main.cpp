@@ -345,6 +345,7 @@ void merge_inputs(const std::vector<OwnedBatch>& files, const AdmissionOptions& 
 }
 
 void usage() {
+    std::fprintf(stderr, "usage: ngsep_b200 CoverageStats -i <alignments.sam|.bam> -r <genome.fa> [-o <out.txt>] [-minMQ N]\n");
     std::fprintf(stderr, "usage: ngsep_b200 MultisampleVariantsDetector -r <genome.fa> -o <out.vcf> [options] <alignments.sam|.bam>*\n"
                          "       ngsep_b200 SingleSampleVariantsDetector -i <alignments.sam|.bam> -r <genome.fa> -o <outputPrefix>\n"
                          "  [-sampleId S] [-ploidy N] [-psp] [-minMQ N] [-querySeq S -first N -last N] [-ignoreLowerCaseRef]\n"
@@ -355,6 +356,30 @@ void usage() {
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc >= 2 && !std::strcmp(argv[1], "CoverageStats")) {
+        // CoverageStatisticsCalculator (main/CommandsDescriptor.xml:458-478: -i, -o, -minMQ; -r is needed here to name the sequences)
+        std::string in, ref, out;
+        int min_mq = 20, device = 0;
+        for (int i = 2; i < argc; i++) {
+            std::string a = argv[i];
+            auto val = [&]() -> const char* { if (i + 1 >= argc) { usage(); std::exit(1); } return argv[++i]; };
+            if (a == "-i") in = val(); else if (a == "-r") ref = val(); else if (a == "-o") out = val(); else if (a == "-minMQ") min_mq = std::atoi(val());
+            else if (a == "--device") device = std::atoi(val());
+            else { std::fprintf(stderr, "Unrecognized option %s\n", a.c_str()); usage(); return 1; }
+        }
+        if (in.empty()) { std::fprintf(stderr, "The alignments input file is a required parameter\n"); return 2; }   // CoverageStatisticsCalculator.java:115
+        if (ref.empty()) { std::fprintf(stderr, "The reference genome file is a required parameter\n"); return 2; }
+        Genome g;
+        if (!load_fasta(ref, g)) { std::fprintf(stderr, "cannot read %s\n", ref.c_str()); return 2; }
+        OwnedBatch b;
+        std::string err, text;
+        if (!load_alignments(in, g, b, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
+        int rc = run_coverage_stats(g, b.view(), min_mq, device, text, err);
+        if (rc != 0) { std::fprintf(stderr, "ngsep_b200: %s (code %d)\n", err.c_str(), rc); return 3; }
+        if (out.empty()) std::fwrite(text.data(), 1, text.size(), stdout);   // "Writes to standard output unless the -o option is used"
+        else { std::ofstream os(out); os << text; }
+        return 0;
+    }
     if (argc < 2 || (std::strcmp(argv[1], "SingleSampleVariantsDetector") && std::strcmp(argv[1], "MultisampleVariantsDetector"))) { usage(); return 1; }
     const bool multi = !std::strcmp(argv[1], "MultisampleVariantsDetector");
     DetectorOptions o;

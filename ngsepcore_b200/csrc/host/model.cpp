@@ -291,6 +291,7 @@ std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi,
         r.rec = i;
         r.L = (int)(b.base_off[i + 1] - b.base_off[i]);
         r.neg = (flags & 0x10) != 0;
+        r.unique = !multiple;
         r.rg = b.rg ? b.rg[i] : -1;
         r.bases = b.bases + b.base_off[i];
         r.quals = b.quals + b.base_off[i];

@@ -67,6 +67,7 @@ struct HostRead {
     int admit_first = 0;           // start at admission: the ordering key of the pileup (APG:416-431)
     int L = 0;
     bool neg = false;
+    bool unique = true;            // ReadAlignment.isUnique(): not flagged MULTIPLE_ALN by the reader (RAFR:229-236, 284-291)
     int rg = -1;
     const uint8_t* bases = nullptr;
     const uint8_t* quals = nullptr;

@@ -258,6 +258,9 @@ std::string english_fmt(double v);   // main/io/ParseUtils.java:29, DecimalForma
 std::vector<int> impl_copy_numbers(const std::vector<int>& called, const std::vector<int>& allele_counts, bool has_counts, int ploidy, size_t n_alleles);
 void append_gt(std::string& s, const std::vector<int>& called, int ploidy);   // VCFFileWriter.java:171-199
 
+// CoverageStatisticsCalculator.processFile + printCoverageStats over a batch (coverage.cpp): the table text goes to `out`
+int run_coverage_stats(const Genome& genome, const BatchView& b, int min_mq, int device, std::string& out, std::string& err);
+
 std::string snv_vcf_line(const ngsep_snv_call& c, const std::string& chrom, int ploidy, bool csb, bool embedded);
 std::string indel_vcf_line(const IndelRecord& r, const std::string& chrom, int ploidy);
 void host_tables(double het_rate, double* t95);   // CountsHelper.updateProbabilitiesCache, CH:135-187,414-415

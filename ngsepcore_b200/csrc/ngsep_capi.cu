@@ -115,6 +115,8 @@ struct Ctx {
     DevBuf<WinRange> d_bwin;
     // column queue shared by every launch of this context (launches are stream-ordered)
     DevBuf<uint4> d_open;
+    DevBuf<int32_t> d_cov_first, d_cov_last; DevBuf<uint8_t> d_cov_unique; DevBuf<int2> d_cov_diff; DevBuf<unsigned char> d_cov_tmp;   // ngsep_coverage_histogram
+    DevBuf<unsigned long long> d_cov_hist;
     DevBuf<uint2> d_ent;     // resolved entries of the open columns (a full list only costs speed: such columns go out as record ranges)
     size_t q_min_cols = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
@@ -655,6 +657,7 @@ int ngsep_ctx_destroy(void* ctx) {
     for (Slot* s : c->slots) { s->release(); delete s; }
     for (size_t k = 1; k < c->ring.size(); k++) { c->ring[k]->release(); delete c->ring[k]; }
     c->d_btiles.release(); c->d_bwin.release(); c->d_open.release(); c->d_ent.release();
+    c->d_cov_first.release(); c->d_cov_last.release(); c->d_cov_unique.release(); c->d_cov_diff.release(); c->d_cov_tmp.release(); c->d_cov_hist.release();
     c->d_sgo.release(); c->d_sgroups.release(); c->d_scratch.release(); c->d_gins.release(); c->d_gkeys.release(); c->d_gvals.release(); c->d_cub.release();
     if (c->d_prm) cudaFree(c->d_prm);
     if (c->d_meta) cudaFree(c->d_meta);
@@ -811,6 +814,36 @@ int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
     c->slots.push_back(s);
     c->batch_dirty = true;
     *slot = (int)c->slots.size() - 1;
+    return NGSEP_OK;
+}
+
+// ---- CoverageStatisticsCalculator: read-depth histograms of one region tile (coverage_kernels.cu) ---------------------------------
+int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, int64_t n, const int32_t* first, const int32_t* last, const uint8_t* unique,
+                             int32_t max_coverage, uint64_t* hist_all, uint64_t* hist_unique) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (tile_first < 1 || tile_last < tile_first || n < 0 || max_coverage < 1 || max_coverage > 4095 || !hist_all || !hist_unique || (n > 0 && (!first || !last || !unique)))
+        return fail(c, NGSEP_EINVAL, "bad coverage arguments");
+    CK(cudaSetDevice(c->device), "set device");
+    const int64_t n_pos = (int64_t)tile_last - tile_first + 1;
+    const size_t bins = (size_t)max_coverage + 1;
+    CK(c->d_cov_first.reserve((size_t)n + 1), "coverage alloc"); CK(c->d_cov_last.reserve((size_t)n + 1), "coverage alloc"); CK(c->d_cov_unique.reserve((size_t)n + 1), "coverage alloc");
+    CK(c->d_cov_diff.reserve((size_t)n_pos + 2), "coverage alloc");
+    const size_t tmp = coverage_scan_temp_bytes(n_pos);
+    CK(c->d_cov_tmp.reserve(tmp + 256), "coverage alloc");
+    CK(c->d_cov_hist.reserve(2 * bins), "coverage alloc");
+    if (n > 0) {
+        CK(cudaMemcpyAsync(c->d_cov_first.p, first, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream), "coverage copy");
+        CK(cudaMemcpyAsync(c->d_cov_last.p, last, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream), "coverage copy");
+        CK(cudaMemcpyAsync(c->d_cov_unique.p, unique, (size_t)n, cudaMemcpyHostToDevice, c->stream), "coverage copy");
+    }
+    CK(cudaMemsetAsync(c->d_cov_hist.p, 0, 2 * bins * sizeof(unsigned long long), c->stream), "coverage memset");
+    CK(launch_coverage(c->d_cov_first.p, c->d_cov_last.p, c->d_cov_unique.p, n, tile_first, tile_last, max_coverage, c->d_cov_diff.p, c->d_cov_tmp.p, c->d_cov_tmp.cap,
+                       c->d_cov_hist.p, c->d_cov_hist.p + bins, c->sm_count, c->stream), "coverage kernels");
+    std::vector<unsigned long long> h(2 * bins);
+    CK(cudaMemcpyAsync(h.data(), c->d_cov_hist.p, 2 * bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), "coverage copy");
+    CK(cudaStreamSynchronize(c->stream), "coverage sync");
+    for (size_t k = 0; k < bins; k++) { hist_all[k] = h[k]; hist_unique[k] = h[bins + k]; }
     return NGSEP_OK;
 }
 

@@ -116,6 +116,11 @@ cudaError_t launch_group_index(const uint16_t* group, const uint8_t* in_sample /
 int group_blocks(int n);   // blocks of record indexes in the per-group block table
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
+// read-depth histograms of a tile (coverage_kernels.cu)
+size_t coverage_scan_temp_bytes(int64_t n_pos);
+cudaError_t launch_coverage(const int32_t* first, const int32_t* last, const uint8_t* unique, int64_t n, int32_t tile_first, int32_t tile_last, int max_cov, int2* diff,
+                            void* tmp, size_t tmp_bytes, unsigned long long* hist_all, unsigned long long* hist_unique, int sm_count, cudaStream_t s);
+
 // synthetic inputs generated on the device (synth_kernels.cu)
 struct SynthSpec { uint64_t seed; double step; int read_len; uint32_t snv_thr, err_thr; };   // step = read_len / depth; thresholds = rate * 2^32
 void launch_synth_ref(char* ascii, int64_t len, uint64_t seed, double gc, cudaStream_t s);

@@ -248,6 +248,60 @@ char* oracle_run_ssvd(const char* fasta_path, const char* sam_path, int argc, ch
     return res;
 }
 
+
+// ---- discovery/CoverageStatisticsCalculator.java -------------------------------------------------------------------------------
+// The listener (processPileup :186-199, printCoverageStats :250-256) on the generator processFile configures for it (:130-138):
+// secondary alignments processed (so only unmapped records are filtered, APG:367-371), 100 alignments per start position.
+struct CoverageStatisticsCalculator : PileupListener {
+    int max_coverage = 300;
+    std::vector<long> counts, counts_unique;
+    long high = 0, high_unique = 0;
+    CoverageStatisticsCalculator() : counts(300, 0), counts_unique(300, 0) {}
+    void on_pileup(PileupRecord& p) override {
+        if (p.n_alns < (int)counts.size()) counts[p.n_alns]++; else high++;
+        if (p.n_unique < (int)counts_unique.size()) counts_unique[p.n_unique]++; else high_unique++;
+    }
+    void on_sequence_start(const std::string&) override {}
+    void on_sequence_end(const std::string&) override {}
+    void print(std::ostream& out) const {
+        for (size_t i = 1; i < counts.size(); i++) out << i << "\t" << counts[i] << "\t" << counts_unique[i] << "\n";
+        out << "More\t" << high << "\t" << high_unique << "\n";
+    }
+};
+
+char* oracle_run_coverage_stats(const char* fasta_path, const char* sam_path, int min_mq, double* seconds) {
+    ReferenceGenome genome = ReferenceGenome::load_fasta(fasta_path);
+    std::ifstream sam(sam_path);
+    if (!sam) return nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    CoverageStatisticsCalculator calc;
+    AlignmentsPileupGenerator gen;
+    gen.secondary = true;              // setProcessSecondaryAlignments(true)
+    gen.max_alns_per_start = 100;      // setMaxAlnsPerStartPos(100)
+    gen.min_mq = min_mq;
+    gen.listeners = {&calc};
+    AlignmentReader reader;
+    reader.filter_flags = gen.filter_flags();
+    reader.min_mq = gen.min_mq;
+    reader.genome = &genome;
+    std::string line;
+    SamRecord rec;
+    while (std::getline(sam, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!parse_sam_line(line, rec)) continue;
+        ReadPtr a = reader.load(rec);
+        if (a) gen.process_alignment(a);
+    }
+    gen.notify_end();
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::ostringstream out;
+    calc.print(out);
+    std::string s = out.str();
+    char* res = (char*)std::malloc(s.size() + 1);
+    std::memcpy(res, s.c_str(), s.size() + 1);
+    return res;
+}
+
 // MultisampleVariantsDetector on SAM text files.  counts_out: pooled pos,A,C,G,T,DP wherever discoverPopulationSNV ran.
 char* oracle_run_msvd(const char* fasta_path, int n_files, char** sam_paths, int argc, char** argv, int** counts_out, long* n_counts,
                       long* genotyped_positions, double* seconds) {

@@ -36,6 +36,8 @@ def load_oracle():
     lib.oracle_run_msvd.restype = C.c_void_p
     lib.oracle_run_msvd.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.POINTER(C.c_int)),
                                     C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_double)]
+    lib.oracle_run_coverage_stats.restype = C.c_void_p
+    lib.oracle_run_coverage_stats.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
     lib.oracle_english_fmt.argtypes = [C.c_double, C.c_char_p]
     lib.oracle_string_hashset_order.argtypes = [C.c_int, C.POINTER(C.c_char_p), ip]
     lib.oracle_diversity_info.argtypes = [C.c_int, C.c_int, ip, ip, C.c_char_p]
@@ -89,6 +91,17 @@ def run_msvd(lib, fasta, sams, args=(), want_counts=False):
         counts = np.ctypeslib.as_array(cptr, shape=(n_counts.value, 6)).copy() if n_counts.value else np.zeros((0, 6), np.int32)
         lib.oracle_free(cptr)
     return text, counts, gp.value, sec.value
+
+
+def run_coverage_stats(lib, fasta, sam, min_mq=20):
+    """The oracle's CoverageStatisticsCalculator on a SAM file -> (table text, seconds)."""
+    sec = C.c_double(0)
+    res = lib.oracle_run_coverage_stats(fasta.encode(), sam.encode(), min_mq, C.byref(sec))
+    if not res:
+        raise RuntimeError("oracle CoverageStats run failed")
+    text = C.string_at(res).decode()
+    lib.oracle_free(res)
+    return text, sec.value
 
 
 def diversity_info(lib, n_alleles, called, copy_numbers):
