@@ -59,6 +59,8 @@ typedef struct ngsep_detector_options {
     int32_t synchronous;            /* test hook: one tile at a time from pageable buffers, host stages on the calling thread (default: sequences planned
                                        in parallel, tiles pipelined through page-locked ring buffers) */
     int32_t n_devices;              /* GPUs device .. device + n_devices - 1: region tiles are dealt to them in turn (0 / 1 = one GPU) */
+    const char* known_strs;         /* -knownSTRs: file with tandem-repeat loci (sequence, first, last in its first three columns), NULL = none;
+                                       SingleSampleVariantsDetector only (SSVD:906-913) */
 } ngsep_detector_options;
 
 typedef struct ngsep_run_stats {

@@ -92,6 +92,10 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
     int rc = opt_.host_only ? NGSEP_OK : ensure_ctx();
     if (rc != NGSEP_OK) return rc;
+    if (!opt_.known_strs.empty() && !strs_loaded_) {   // SSVD:906-913
+        if (!load_known_strs(opt_.known_strs, *genome_, strs_, err_)) return NGSEP_EINVAL;
+        strs_loaded_ = true;
+    }
     if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
     // ---- the sequences of the batch, in file order (APG:310-322 for a query sequence) ------------------------------------
@@ -254,6 +258,20 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         std::vector<HostRead*> active, pileup;
         std::vector<ReadState> before;
         size_t next = 0;
+        // -knownSTRs: every input locus is an event at its first position, whether a read anchors an indel there or not, and the
+        // positions behind it are embedded (IRPL:89-99); indels inside a locus are not events of their own
+        static const std::vector<StrLocus> no_loci;
+        const std::vector<StrLocus>& loci = (strs_loaded_ && (size_t)seq < strs_.size()) ? strs_[(size_t)seq] : no_loci;
+        for (const StrLocus& l : loci) {
+            heap.push(l.first);
+            if (l.last > l.first) plan.embedded.push_back({l.first + 1, l.last});
+        }
+        auto locus_at = [&](int pos) -> const StrLocus* {
+            auto it = std::upper_bound(loci.begin(), loci.end(), pos, [](int v, const StrLocus& l) { return v < l.first; });
+            if (it == loci.begin()) return nullptr;
+            --it;
+            return pos <= it->last ? &*it : nullptr;
+        };
         while (next < reads.size() || !heap.empty()) {
             int s = next < reads.size() ? reads[next].admit_first : INT_MAX;
             int e = heap.empty() ? INT_MAX : heap.top();
@@ -271,12 +289,17 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             active.resize(w);
             pileup.clear();
             for (HostRead* r : active) if (r->st.first <= e && e <= r->st.last) pileup.push_back(r);       // PR:154-156
-            bool any = false;
-            for (HostRead* r : pileup) if (r->anchor_at(e)) { any = true; break; }
-            if (!any) continue;
+            const StrLocus* locus = locus_at(e);
+            if (locus && locus->first != e) continue;    // inside an input locus: embedded, the realigner does nothing (IRPL:96-98)
+            if (locus) { if (pileup.empty()) continue; }
+            else {
+                bool any = false;
+                for (HostRead* r : pileup) if (r->anchor_at(e)) { any = true; break; }
+                if (!any) continue;
+            }
             before.clear();
             for (HostRead* r : pileup) before.push_back(r->st);
-            EventOutcome ev = realigner.on_event(e, pileup);
+            EventOutcome ev = realigner.on_event(e, pileup, locus);
             if (!ev.fired) continue;
             plan.stats.events++;
             for (size_t k = 0; k < pileup.size(); k++) {
@@ -291,6 +314,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             }
             // ---- SingleSampleVariantPileupListener.onPileup at the event (SSVPL:146-161) ----
             bool emb = e <= last_indel_end;
+            if (ev.str && !ev.new_str && e >= last_indel_end) { last_indel_end = e + ev.span - 1; emb = false; }   // an input STR (SSVPL:150)
             if (emb && !opt_.call_embedded) continue;     // SSVPL:193 — nothing is called here (interval already recorded)
             std::string ref;
             if (!genome_->get(seq, e, e + ev.span - 1, ref)) { suppressed.insert(e); continue; }   // SSVPL:195-196
@@ -317,7 +341,9 @@ void GpuSingleSampleVariantsDetector::on_span_event(int e, const std::string& re
     IndelCallerOptions io;
     io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
     IndelRecord rec;
-    if (call_indel_at(e, ref_upper, ev.str, pileup, io, rec)) {
+    const bool input_str = ev.str && !ev.new_str;
+    if (input_str) plan.suppressed.insert(e);      // no SNV is tried at an input locus when the indel alleles give no call (SSVPL:264)
+    if (call_indel_at(e, ref_upper, ev.str, pileup, io, rec, input_str)) {
         plan.suppressed.insert(e);
         last_indel_end = rec.last;                 // SSVPL:157-158
         if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
@@ -337,7 +363,17 @@ void GpuSingleSampleVariantsDetector::emit_text(SeqJob& job) {
     SeqPlan& plan = job.plan;
     std::vector<ngsep_snv_call>& snvs = job.snvs;
     const std::set<int>& suppressed = plan.suppressed;
-    const std::vector<std::pair<int, int>>& embedded = plan.embedded;
+    // embedded positions: inside called indels / STRs and inside input loci — as one sorted list of disjoint intervals
+    std::vector<std::pair<int, int>> embedded = plan.embedded;
+    std::sort(embedded.begin(), embedded.end());
+    {
+        size_t w = 0;
+        for (size_t k = 0; k < embedded.size(); k++) {
+            if (w > 0 && embedded[k].first <= embedded[w - 1].second + 1) embedded[w - 1].second = std::max(embedded[w - 1].second, embedded[k].second);
+            else embedded[w++] = embedded[k];
+        }
+        embedded.resize(w);
+    }
     // ---- 4. ordered merge + text (SSVD:933-968) -------------------------------------------------------------------------
     std::sort(snvs.begin(), snvs.end(), [](const ngsep_snv_call& a, const ngsep_snv_call& c) { return a.pos < c.pos; });
     struct Line { int first, last, order; std::string text; };

@@ -50,6 +50,7 @@ DetectorOptions convert(const ngsep_detector_options* o) {
     d.device = o->device; d.tile_len = o->tile_len; d.shard = o->shard; d.n_shards = o->n_shards < 1 ? 1 : o->n_shards; d.host_only = o->host_only != 0;
     d.synchronous = o->synchronous != 0;
     d.n_devices = o->n_devices < 1 ? 1 : o->n_devices;
+    if (o->known_strs && o->known_strs[0]) d.known_strs = o->known_strs;
     return d;
 }
 

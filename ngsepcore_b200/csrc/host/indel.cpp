@@ -196,7 +196,7 @@ std::vector<std::string> cluster_alleles(const std::vector<SpanCall>& calls, con
 
 }  // namespace
 
-bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out) {
+bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str) {
     const QTables& t = qt();
     const int span = (int)ref_allele.size();
     std::vector<SpanCall> calls;
@@ -262,7 +262,7 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
         if (alleles[m1].size() != alleles[0].size()) length_change = true;
         if (va.size() == 3 && alleles[m1].size() != va[1].size()) length_change = true;
     }
-    if (!length_change) return false;  // (no input STRs in this mode)
+    if (!length_change && !input_str) return false;   // VD:307
     out = IndelRecord();
     out.pos = pos;
     out.last = pos + span - 1;

@@ -26,10 +26,17 @@ struct RunStats {
 
 struct EventOutcome { bool fired = false; int span = 1; bool str = false, new_str = false; };
 
+// An input tandem-repeat locus of the realigner (-knownSTRs): first .. last after merging and padding (SSVD:843-894)
+struct StrLocus { int first = 0, last = 0; };
+// per sequence of the genome, sorted by position (strs.cpp)
+bool load_known_strs(const std::string& path, const Genome& genome, std::vector<std::vector<StrLocus>>& out, std::string& err);
+
 struct Realigner {
     const Genome* genome = nullptr;
     int seq = 0;
-    EventOutcome on_event(int pos, std::vector<HostRead*>& pileup);            // IRPL:84-216
+    // IRPL:84-216.  locus: the input STR that starts at pos (the event is then fixed to the locus: every indel inside it moves to its
+    // start, IRPL:90-95, 169, 205-206), or null (an event is found from the reads' own indels)
+    EventOutcome on_event(int pos, std::vector<HostRead*>& pileup, const StrLocus* locus = nullptr);
     void process_ends(std::vector<HostRead*>& pileup, int ev_first, int ev_last);  // IRPL:400-526
 };
 
@@ -49,7 +56,8 @@ struct IndelCallerOptions { int max_base_qs = 30; double het_rate = 0.001; int m
 
 // SingleSampleVariantPileupListener.discoverVariantWithSpan (SSVPL:257-273) up to the SNV fall-back:
 // AlleleCallClustersBuilder + CountsHelper.calculateCountsIndel + VariantDiscoverySNVQAlgorithm.callIndel.
-bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out);
+// input_str: the span is an input tandem-repeat locus (PileupRecord.isInputSTR): a call without a length change is kept (VD:307)
+bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str = false);
 
 // Phred / rounding helpers shared by the host writer (math/PhredScoreHelper.java:31-40)
 long jround(double x);
@@ -151,6 +159,7 @@ struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 
     int min_quality = 40;
     bool call_embedded = false, csb = false;
     double min_allele_depth_freq = 0;   // MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58)
+    std::string known_strs;             // -knownSTRs: file with tandem-repeat loci (sequence, first, last); SingleSampleVariantsDetector only
     // device plumbing (not reference options)
     int device = 0;
     int n_devices = 1;         // GPUs device .. device + n_devices - 1 of this host: region tiles are dealt to them in turn, every GPU with its own
@@ -206,6 +215,8 @@ protected:
     const Genome* genome_ = nullptr;
     void* ctx_ = nullptr;                        // context of the first device (ctxs_[0])
     std::vector<void*> ctxs_;                    // one context per device
+    std::vector<std::vector<StrLocus>> strs_;    // -knownSTRs: loci per sequence (loaded with the genome)
+    bool strs_loaded_ = false;
     std::vector<std::vector<bool>> ref_uploaded_;   // per device, per sequence
     RunStats stats_;
     std::string err_;

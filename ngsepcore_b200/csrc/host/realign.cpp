@@ -61,18 +61,28 @@ int mononucleotide_run(const std::string& s) {  // IRPL:365-391
 
 }  // namespace
 
-EventOutcome Realigner::on_event(int pos, std::vector<HostRead*>& pileup) {
+EventOutcome Realigner::on_event(int pos, std::vector<HostRead*>& pileup, const StrLocus* locus) {
     EventOutcome out;
-    int max_len = 0, max_span = 0;
-    for (HostRead* r : pileup) {
-        const Anchor* a = r->anchor_at(pos);
-        if (!a) continue;
-        max_len = std::max(max_len, a->len);
-        max_span = std::max(max_span, a->last - a->pos + 1);
+    int event_end;
+    if (locus) {   // IRPL:90-95: the pileup is an input STR, the event is its locus
+        out.fired = true;
+        out.str = true;
+        out.span = locus->last - locus->first + 1;
+        event_end = locus->last;
+        if (event_end <= pos) return out;   // IRPL:118: nothing to conciliate
+    } else {
+        int max_len = 0, max_span = 0;
+        for (HostRead* r : pileup) {
+            const Anchor* a = r->anchor_at(pos);
+            if (!a) continue;
+            max_len = std::max(max_len, a->len);
+            max_span = std::max(max_span, a->last - a->pos + 1);
+        }
+        if (max_len == 0) return out;  // not an event after all (stale queue entry)
+        out.fired = true;
+        event_end = pos + std::max(max_len, max_span) + 1;  // IRPL:116
     }
-    if (max_len == 0) return out;  // not an event after all (stale queue entry)
-    out.fired = true;
-    int event_end = pos + std::max(max_len, max_span) + 1;  // IRPL:116
+    const int locus_span = out.span;
 
     // ---- conciliateIndels, IRPL:165-216 -------------------------------------------------------------------
     std::set<int> lengths;
@@ -95,8 +105,9 @@ EventOutcome Realigner::on_event(int pos, std::vector<HostRead*>& pileup) {
     int best_vote = 0;
     for (int i = 1; i < (int)votes.size(); i++) if (votes[best_vote] < votes[i]) best_vote = i;  // first strict maximum
     int answer = 0;
-    bool fixed = false;
-    if (lengths.size() > 1) {  // lookForNewSTR, IRPL:315-349
+    bool fixed = locus != nullptr;
+    if (fixed) best_vote = 0;   // IRPL:183-184: no vote, no search for a new tandem repeat
+    if (!fixed && lengths.size() > 1) {  // lookForNewSTR, IRPL:315-349
         int new_span = 0;
         std::string ref;
         int run = 0;
@@ -139,13 +150,13 @@ EventOutcome Realigner::on_event(int pos, std::vector<HostRead*>& pileup) {
         for (const Anchor& a : r->anchors) if (a.pos >= pos && a.pos <= ref_last + longest) ref_last = a.last;
         new_end = std::max(new_end, ref_last);
     }
-    if (best_vote > 0) { out.span = answer > 0 ? answer : 1; return out; }
+    if (best_vote > 0) { out.span = answer > 0 ? answer : locus_span; return out; }
     if (!fixed && new_end != event_end) {
         event_end = new_end;
         answer = event_end - pos + 1;
     }
     process_ends(pileup, pos, event_end);
-    out.span = answer > 0 ? answer : 1;
+    out.span = answer > 0 ? answer : locus_span;
     return out;
 }
 

@@ -239,16 +239,31 @@ struct PileupListener {
 };
 
 // ---- discovery/IndelRealignerPileupListener.java ------------------------------
+// An input variant of the realigner (IRPL:52-53, 62-66): with -knownSTRs the merged, padded tandem-repeat loci of
+// SingleSampleVariantsDetector.makeNonRedundantSTRs (SSVD:843-894), GenomicVariantImpl of TYPE_STR with the reference allele only
+struct InputVariant { int first = 0, last = 0; bool str = false; };
+struct GenomicRegionRow { std::string seq; int first = 0, last = 0; };
+std::vector<GenomicRegionRow> load_regions(const std::string& path);   // genome/io/SimpleGenomicRegionFileHandler.java:57-80
+std::map<std::string, std::vector<InputVariant>> make_non_redundant_strs(const ReferenceGenome& genome, const std::vector<GenomicRegionRow>& strs);  // SSVD:843-894
+
 struct IndelRealignerPileupListener : PileupListener {
     const ReferenceGenome* genome = nullptr;
+    std::map<std::string, std::vector<InputVariant>> input_variants;   // per sequence, sorted (IRPL:129-134)
     int min_bp_good_ref_aln = 5, max_bp_realign_end = 50;   // IRPL:46-47
     double min_prop_alns_realign = 0;                       // IRPL:48
     long n_events = 0;
     void on_pileup(PileupRecord& p) override;               // IRPL:84-126
-    void on_sequence_start(const std::string&) override {}
+    void on_sequence_start(const std::string& seq) override {   // IRPL:129-134
+        auto it = input_variants.find(seq);
+        seq_variants = it == input_variants.end() ? nullptr : &it->second;
+        idx_next_variant = 0;
+    }
     void on_sequence_end(const std::string&) override {}
 private:
-    int conciliate(PileupRecord& p, std::vector<ReadAlignment*>& alns, int event_end);       // IRPL:165-216
+    const std::vector<InputVariant>* seq_variants = nullptr;
+    size_t idx_next_variant = 0;
+    const InputVariant* intersect_with_variants(int pos);   // IRPL:141-157
+    int conciliate(PileupRecord& p, std::vector<ReadAlignment*>& alns, int event_end, bool fixed_event);       // IRPL:165-216
     int analyze(std::vector<ReadAlignment*>& alns, int ev_start, int ev_end, std::set<int>& lengths, std::vector<ReadAlignment*>& indel_alns, std::vector<int>& votes);  // IRPL:229-265
     int move_starts(std::vector<ReadAlignment*>& alns, int first, int last, int max_len, int offset);  // IRPL:274-313
     int look_for_new_str(PileupRecord& p, std::vector<ReadAlignment*>& alns, int max_len);  // IRPL:315-349
@@ -310,6 +325,7 @@ struct DetectorOptions {
     bool ignore_lower = false; int max_alns_per_start = 5; bool non_unique_primary = false, secondary = false;
     int ignore5 = 0, ignore3 = 0; double het_rate = 0.001; bool het_modified = false; int max_base_qs = 30;
     short min_quality = 40; bool call_embedded = false, csb = false;
+    std::string known_strs;             // -knownSTRs (SSVD:906-913)
     double min_allele_depth_freq = 0;   // MSVD:58 (setter only, no CLI option id; oracle switch --minAlleleDepthFrequency)
 };
 struct SingleSampleVariantsDetector : PileupListener {

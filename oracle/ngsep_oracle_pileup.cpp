@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 
@@ -28,25 +29,48 @@ static double hamming(const std::string& a, const std::string& b) {  // HammingS
 // ---------------------------------------------------------------------------------------------
 // IndelRealignerPileupListener (no input variants: -knownVariants / -knownSTRs are "next" rows)
 // ---------------------------------------------------------------------------------------------
+const InputVariant* IndelRealignerPileupListener::intersect_with_variants(int pos) {  // IRPL:141-157
+    if (!seq_variants) return nullptr;
+    while (idx_next_variant < seq_variants->size()) {
+        const InputVariant& v = (*seq_variants)[idx_next_variant];
+        if (pos < v.first) break;
+        if (v.first <= pos && pos <= v.last) return &v;
+        idx_next_variant++;
+    }
+    return nullptr;
+}
+
 void IndelRealignerPileupListener::on_pileup(PileupRecord& p) {  // IRPL:84-126
     int cur = p.pos;
     int span = 1;
     int predicted_end = cur;
-    std::vector<ReadAlignment*>& alns = p.alns;
-    int max_len = 0, max_span = 0;
-    for (ReadAlignment* a : alns) {
-        const IndelCall* indel = a->get_indel_call(cur);
-        if (indel) {
-            int isp = indel->last - indel->first + 1;
-            int il = indel->length;
-            if (il > max_len) max_len = il;
-            if (isp > max_span) max_span = isp;
+    const InputVariant* var = intersect_with_variants(cur);
+    if (var) {
+        if (var->first == cur) {
+            if (var->str) p.str = true;
+            span = var->last - var->first + 1;
+            predicted_end = var->last;
+        } else {
+            p.embedded = true;
         }
     }
-    if (max_len > 0) predicted_end = cur + std::max(max_len, max_span) + 1;
+    std::vector<ReadAlignment*>& alns = p.alns;
+    if (!var) {
+        int max_len = 0, max_span = 0;
+        for (ReadAlignment* a : alns) {
+            const IndelCall* indel = a->get_indel_call(cur);
+            if (indel) {
+                int isp = indel->last - indel->first + 1;
+                int il = indel->length;
+                if (il > max_len) max_len = il;
+                if (isp > max_span) max_span = isp;
+            }
+        }
+        if (max_len > 0) predicted_end = cur + std::max(max_len, max_span) + 1;
+    }
     if (predicted_end > cur) {
         n_events++;
-        int cs = conciliate(p, alns, predicted_end);
+        int cs = conciliate(p, alns, predicted_end, var != nullptr);
         if (cs > 0) span = cs;
     }
     p.span = span;
@@ -157,10 +181,10 @@ int IndelRealignerPileupListener::look_for_new_str(PileupRecord& p, std::vector<
     return new_span;
 }
 
-int IndelRealignerPileupListener::conciliate(PileupRecord& p, std::vector<ReadAlignment*>& alns, int event_end) {  // IRPL:165-216
+int IndelRealignerPileupListener::conciliate(PileupRecord& p, std::vector<ReadAlignment*>& alns, int event_end, bool fixed_event) {  // IRPL:165-216
     int answer = 0;
     int cur = p.pos;
-    bool fixed = false;
+    bool fixed = fixed_event;
     std::set<int> lengths;
     std::vector<ReadAlignment*> indel_alns;
     std::vector<int> votes(event_end - cur + 1, 0);
@@ -168,7 +192,7 @@ int IndelRealignerPileupListener::conciliate(PileupRecord& p, std::vector<ReadAl
     if (lengths.empty()) return answer;
     if (min_prop_alns_realign > 0 && indel_alns.size() < min_prop_alns_realign * alns.size()) return answer;
     int max_i = 0;
-    {
+    if (!fixed) {
         // NumberArrays.getIndexMaximum, math/NumberArrays.java:87-95: first strict maximum
         int idx = -1;
         for (int i = 0; i < (int)votes.size(); i++) if (idx == -1 || votes[idx] < votes[i]) idx = i;
@@ -638,6 +662,7 @@ void SingleSampleVariantsDetector::begin() {
     gen.max_alns_per_start = opt.max_alns_per_start; gen.non_unique_primary = opt.non_unique_primary; gen.secondary = opt.secondary;
     gen.ignore5 = (int8_t)opt.ignore5; gen.ignore3 = (int8_t)opt.ignore3; gen.min_mq = opt.min_mq;
     realigner.genome = genome;
+    if (!opt.known_strs.empty()) realigner.input_variants = make_non_redundant_strs(*genome, load_regions(opt.known_strs));   // SSVD:906-913
     var_listener.genome = genome; var_listener.het_rate = opt.het_rate; var_listener.csb = opt.csb;
     var_listener.max_base_qs = (int8_t)opt.max_base_qs; var_listener.ignore_lower = opt.ignore_lower;
     var_listener.call_embedded = opt.call_embedded; var_listener.min_quality = opt.min_quality;
@@ -675,4 +700,77 @@ void SingleSampleVariantsDetector::on_sequence_end(const std::string&) {  // SSV
     calls.clear();
 }
 
+}  // namespace ngsep_oracle
+
+
+// ---- -knownSTRs: genome/io/SimpleGenomicRegionFileHandler.java:57-80 and SingleSampleVariantsDetector.makeNonRedundantSTRs (SSVD:843-894) ----
+namespace ngsep_oracle {
+std::vector<GenomicRegionRow> load_regions(const std::string& path) {
+    std::vector<GenomicRegionRow> out;
+    std::ifstream in(path);
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::vector<std::string> items;   // line.split(" |\t")
+        size_t s = 0;
+        while (true) {
+            size_t e = line.find_first_of(" \t", s);
+            items.push_back(line.substr(s, e == std::string::npos ? std::string::npos : e - s));
+            if (e == std::string::npos) break;
+            s = e + 1;
+        }
+        if (items.size() < 3) continue;
+        char* end = nullptr;
+        long f = std::strtol(items[1].c_str(), &end, 10);
+        if (items[1].empty() || *end) continue;     // NumberFormatException: the line is skipped
+        long l = std::strtol(items[2].c_str(), &end, 10);
+        if (items[2].empty() || *end) continue;
+        out.push_back({items[0], (int)f, (int)l});
+    }
+    return out;
+}
+
+static int overlap_length(const std::string& s1, const std::string& s2) {   // sequences/AbstractLimitedSequence.java:376-390
+    for (size_t i = 0; i < s1.size(); i++) {
+        size_t a = i, b = 0;
+        bool ok = true;
+        for (; a < s1.size() && b < s2.size(); a++, b++) if (s1[a] != s2[b]) { ok = false; break; }
+        if (ok && a == s1.size()) return (int)(s1.size() - i);
+    }
+    return 0;
+}
+static std::string upper_copy(std::string s) { for (auto& c : s) if (c >= 'a' && c <= 'z') c = (char)(c - 32); return s; }
+
+std::map<std::string, std::vector<InputVariant>> make_non_redundant_strs(const ReferenceGenome& genome, const std::vector<GenomicRegionRow>& strs) {
+    std::map<std::string, std::vector<InputVariant>> answer;
+    for (size_t si = 0; si < genome.names.size(); si++) {
+        const std::string& name = genome.names[si];
+        const int seq_len = (int)genome.seqs[si].size();
+        std::vector<GenomicRegionRow> rs;
+        for (auto& r : strs) if (r.seq == name) rs.push_back(r);
+        std::stable_sort(rs.begin(), rs.end(), [](const GenomicRegionRow& a, const GenomicRegionRow& b) { return a.first != b.first ? a.first < b.first : a.last < b.last; });
+        auto merge = [&](int first, int last, const GenomicRegionRow& r) {   // mergeSTRs, SSVD:872-879
+            if (r.first - last > 5) return false;
+            if (r.first - last <= 2) return true;
+            std::string ref1, ref2;
+            if (!genome.get(name, std::max(first, last - 10), last, ref1) || !genome.get(name, r.first, r.last, ref2)) return false;
+            return overlap_length(upper_copy(ref1), upper_copy(ref2)) > 5;
+        };
+        auto emit = [&](int first, int last) {   // makeSTRVariant, SSVD:882-894: the variant spans its reference allele
+            std::string ref;
+            if (!genome.get(name, first, last, ref)) return;
+            answer[name].push_back({first, first + (int)ref.size() - 1, true});
+        };
+        int first = 0, last = 0;
+        for (auto& r : rs) {
+            if (last == 0 || !merge(first, last, r)) {
+                if (last > 0) emit(std::max(1, first - 1), std::min(last + 1, seq_len));
+                first = r.first;
+            }
+            last = r.last;
+        }
+        if (last > 0) emit(std::max(1, first - 1), std::min(last + 1, seq_len));
+    }
+    return answer;
+}
 }  // namespace ngsep_oracle

@@ -5,6 +5,7 @@ fires, reads get versioned, indel records come from the host caller and SNV reco
 import os
 import subprocess
 
+import numpy as np
 import pytest
 
 from ngsepcore_b200 import hostapi, simulate
@@ -158,3 +159,36 @@ def test_region_tiles_dealt_to_several_gpus_of_one_process(oracle, tmp_path):
         det.set_genome(genome)
         assert det.run(batch) == want
         assert det.stats().covered_positions == gp and det.stats().tiles == one.stats().tiles
+
+
+@pytest.mark.parametrize("opts,det_kw", [((), {}), (("-embeddedSNVs", "-minQuality", "30"), dict(embeddedSNVs=True, minQuality=30))])
+def test_known_strs_mode(oracle, tmp_path, opts, det_kw):
+    """-knownSTRs (SSVD:906-913): the loci of the reference's yeast tutorial (first 400 rows of training/Saccharomyces_cerevisiae_STRs.txt,
+    tests/golden/yeast_strs_head.txt) plus loci laid over planted indels, on a chrI-sized sequence.  Input loci are fixed realigner
+    events (IRPL:89-99), their calls span the locus as TYPE=STR, no SNV is tried at a locus start, SNVs inside a locus are embedded
+    (dropped, or TYPE=EMBEDDED with -embeddedSNVs).  Whole detector and the CLI against the oracle, byte for byte."""
+    import subprocess
+    from tests.test_host_pipeline_cpu import _write_str_loci
+    contigs = [("chrI", 230218)]
+    genome, batch, truth = simulate.simulate(contigs=contigs, depth=30, seeds=(241, 242, 243), indel_rate=1e-3, snv_rate=3e-3)
+    fa, sam, strs = str(tmp_path / "ref.fa"), str(tmp_path / "reads.sam"), str(tmp_path / "strs.txt")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    _write_str_loci(strs, truth, contigs, np.random.default_rng(17), per_contig_random=0)
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "yeast_strs_head.txt")
+    rows = sorted([l.split()[:3] for l in open(strs) if l.split()[0] == "chrI"] + [l.split()[:3] for l in open(golden)], key=lambda r: (int(r[1]), int(r[2])))
+    open(strs, "w").writelines(f"{r[0]}\t{r[1]}\t{r[2]}\n" for r in rows)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownSTRs", strs) + opts)
+    plain, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=opts)
+    body = _body(want)
+    assert sum("TYPE=STR" in l for l in body) > 40 and len(body) != len(_body(plain))
+    if "-embeddedSNVs" in opts:
+        assert sum("TYPE=EMBEDDED" in l for l in body) > 20
+    det = hostapi.Detector(knownSTRs=strs, **det_kw)
+    det.set_genome(genome)
+    assert det.run(batch) == want
+    assert det.stats().covered_positions == gp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "out")
+    subprocess.check_call([os.path.join(root, "ngsepcore_b200", "ngsep_b200"), "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-knownSTRs", strs] + list(opts))
+    assert open(out + ".vcf").read() == want

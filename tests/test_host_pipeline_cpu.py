@@ -174,3 +174,54 @@ def test_merge_batches_follows_process_files(oracle, tmp_path):
     got_lines = [l for l in det.run(merged).splitlines() if not l.startswith("#")]
     assert len(want_lines) > 15
     assert got_lines == want_lines
+
+
+def _write_str_loci(path, truth, contigs, rng, per_contig_random=40):
+    """A -knownSTRs file (sequence, first, last + extra columns as in the tutorial's TRF table): loci around about half of the planted
+    indels, loci without any indel, neighbouring loci that makeNonRedundantSTRs merges (gap <= 2) or keeps apart (gap > 5)."""
+    rows = []
+    for name, length in contigs:
+        for v in truth[name]:
+            if v.kind != "snv" and rng.random() < 0.5:
+                f = max(2, v.pos - int(rng.integers(1, 6)))
+                l = min(length - 2, v.pos + v.length + int(rng.integers(2, 14)))
+                rows.append((name, f, l))
+                if rng.random() < 0.3:
+                    rows.append((name, l + int(rng.integers(0, 3)), min(length - 2, l + 12)))     # merged with the previous one
+                elif rng.random() < 0.3:
+                    rows.append((name, l + 7, min(length - 2, l + 20)))                              # a separate locus right behind
+        for _ in range(per_contig_random):
+            f = int(rng.integers(50, length - 100))
+            rows.append((name, f, f + int(rng.integers(8, 40))))
+    order = {n: i for i, (n, _) in enumerate(contigs)}
+    rows.sort(key=lambda r: (order[r[0]], r[1], r[2]))
+    with open(path, "w") as fh:
+        for k, (n, f, l) in enumerate(rows):
+            fh.write(f"{n} {f} {l} 2 {l - f + 1}.0 2 90 5 40 25 25 25 25 1.9 AC ACACAC\n" if k % 2 else f"{n}\t{f}\t{l}\n")
+        fh.write("chrUnknown 5 20\nchrA x y\n")     # an unknown sequence and a malformed line are skipped
+    return len(rows)
+
+
+@pytest.mark.parametrize("seed,kw,opts", [
+    (4, dict(indel_rate=2e-3, depth=30), ()),
+    (5, dict(indel_rate=3e-3, depth=18, indel_jitter=0.6), ("-minQuality", "20")),
+])
+def test_known_strs_indel_records_match_oracle(oracle, tmp_path, seed, kw, opts):
+    """-knownSTRs (SSVD:906-913, IRPL:89-99): input loci are fixed events — every indel inside moves to the locus start, the call
+    spans the locus, TYPE=STR, a locus without a length change is still a candidate (VD:307) — and positions inside are embedded.
+    Host stages only (no GPU): the indel / STR records of the C++ host pipeline against the oracle."""
+    contigs = [("chrA", 90000), ("chrB", 40000)]
+    genome, batch, truth = simulate.simulate(contigs=contigs, seeds=(seed * 10, seed * 10 + 1, seed * 10 + 2), **kw)
+    fa, sam, strs = str(tmp_path / "r.fa"), str(tmp_path / "r.sam"), str(tmp_path / "strs.txt")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    assert _write_str_loci(strs, truth, contigs, np.random.default_rng(seed)) > 100
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownSTRs", strs) + opts)
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    plain, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=opts)
+    assert want != plain and sum("TYPE=STR" in l for l in want_lines) > 10
+    det_kw = {"minQuality": int(opts[1])} if opts else {}
+    det = hostapi.Detector(host_only=True, knownSTRs=strs, **det_kw)
+    det.set_genome(genome)
+    got_lines = [l for l in det.run(batch).splitlines() if not l.startswith("#")]
+    assert got_lines == want_lines
