@@ -195,3 +195,21 @@ def test_c_abi_sample_axis_directly(oracle, tmp_path):
         with pytest.raises(capi.NgsepError):
             ctx.fetch()
         assert len(ctx.fetch_pop()[0]) == len(piped[0][0])
+
+
+def test_population_tiles_dealt_to_several_gpus(oracle, tmp_path):
+    """MultisampleVariantsDetector with region tiles dealt to the contexts of several GPUs of one process (every context gets the
+    sample table, ngsep_samples_set): the VCF is the one-GPU run's and the oracle's.  Needs two GPUs; skipped on one."""
+    from ngsepcore_b200 import capi
+    try:
+        capi.Context(device=1).close()
+    except capi.NgsepError:
+        pytest.skip("one GPU only")
+    genome, batch, fa, sam = _population(tmp_path, [("chrA", 160000), ("chrB", 50000)], n_samples=8, depth=8, mode="wgs", snv_rate=3e-3, indel_rate=5e-4,
+                                         seeds=(51, 52, 53))
+    want, _, gp, _ = ou.run_msvd(oracle, fa, [sam])
+    for n in (1, 2):
+        det = _detector(batch, tile_len=30000, n_devices=n)
+        det.set_genome(genome)
+        assert det.run(batch) == want
+        assert det.stats().covered_positions == gp
