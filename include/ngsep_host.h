@@ -61,6 +61,8 @@ typedef struct ngsep_detector_options {
     int32_t n_devices;              /* GPUs device .. device + n_devices - 1: region tiles are dealt to them in turn (0 / 1 = one GPU) */
     const char* known_strs;         /* -knownSTRs: file with tandem-repeat loci (sequence, first, last in its first three columns), NULL = none;
                                        SingleSampleVariantsDetector only (SSVD:906-913) */
+    const char* known_variants;     /* -knownVariants: VCF with the variants to genotype instead of discovering variants (SSVD:897-905), NULL = none;
+                                       SingleSampleVariantsDetector only.  Wins over known_strs, as in the reference */
 } ngsep_detector_options;
 
 typedef struct ngsep_run_stats {

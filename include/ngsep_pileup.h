@@ -138,6 +138,10 @@ typedef struct ngsep_snv_call {
 #define NGSEP_CALL_HET 1      /* 0/1   CalledSNV heterozygous     VD:181-188 */
 #define NGSEP_CALL_HOMALT 2   /* 1/1   CalledSNV homozygous alt   VD:189-193 */
 #define NGSEP_CALL_TRIALLELIC 3 /* 1/2 MULTISNV                   VD:128-177; a0 = alt, a1 = third allele as ordered by VD:133-139 */
+#define NGSEP_CALL_SITE 4      /* a known site (ngsep_tile_sites): VD.genotypeSNV, VD:21-97.  a0 <= a1 are indexes into the SITE's allele list
+                                  (a0 == a1: homozygous, 0/0 included), -1,-1 = undecided (gq 0: no call, gq == 0, or gq < minQuality, SSVPL:388);
+                                  count / depth / logcond as always; sample = index of the site in the list given to ngsep_tile_sites;
+                                  qual, post_max unused */
 
 /* ---- MultisampleVariantsDetector (ngsep_params.n_samples > 1) -------------------------------------------------------
  * One emitted population SNV site: MultisampleVariantsDetector.onPileup for a span-1 position
@@ -200,6 +204,16 @@ int ngsep_ref_upload(void* ctx, int32_t seq_idx, const char* bases, int64_t leng
  * the host can pack / copy the next tile while the device works on the previous one (NGSEP_ESTATE when a fifth is submitted
  * before a fetch).  A tile's host buffers must stay valid until the ngsep_tile_fetch that returns it. */
 int ngsep_tile_submit(void* ctx, const ngsep_tile* tile);
+
+/* -knownVariants (discovery/SingleSampleVariantsDetector.java:897-905): declares the known SNV sites of the NEXT ngsep_tile_submit on
+ * this context.  That tile is then GENOTYPED at these positions instead of being searched for variants — what
+ * SingleSampleVariantPileupListener.onPileup does with input variants (SSVPL:162-176): genotypeVariantSample (SSVPL:361-391) with
+ * VD.genotypeSNV (VD:21-97) at every listed site, homozygous-reference and undecided results included.  pos[i]: 1-based position inside
+ * the tile; alleles[i]: the site's alleles as base indexes (A0 C1 G2 T3), reference first, 2 bits each from bit 0, and their number
+ * (2..4) in bits 8-10 — two alleles = a variants/SNV (CalledSNV rules, VD:33-60), more = the sub-matrix arg-max of VD:61-95.
+ * ngsep_tile_fetch returns exactly n_sites records of kind NGSEP_CALL_SITE, record i for site i (a site no read gives a call at has
+ * depth 0).  The arrays are copied before the call returns.  Single-sample contexts, submit / fetch tiles only. */
+int ngsep_tile_sites(void* ctx, int32_t n_sites, const int32_t* pos, const uint16_t* alleles);
 
 /* Waits for the OLDEST submitted tile and copies its calls (unordered) into out[0..cap).  counts_dbg, when not NULL and
  * NGSEP_F_EMIT_ALL is set, receives [tile_last-tile_first+1][5] = A,C,G,T,DP.  NGSEP_EOVERFLOW with *n_out > cap: the
@@ -272,7 +286,7 @@ int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
-int ngsep_abi_version(void);   /* 2002: + ngsep_tile.qual_bits / qual_dict; 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
+int ngsep_abi_version(void);   /* 2003: + ngsep_tile_sites (known sites); 2002: + ngsep_tile.qual_bits / qual_dict; 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
 int ngsep_built_sm(void);
 
 #ifdef __cplusplus

@@ -32,6 +32,7 @@ public final class NgsepPileupNative implements AutoCloseable {
 	static native void refUpload(long ctx, int seqIdx, byte[] bases) throws IOException;
 	static native void tileSubmit(long ctx, int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords,
 			ByteBuffer qual, long nQual, ByteBuffer group) throws IOException;
+	static native void tileSites(long ctx, int nSites, int[] pos, short[] alleles) throws IOException;
 	static native long tileFetch(long ctx, ByteBuffer calls, long[] stats) throws IOException;
 	static native void samplesSet(long ctx, int nGroups, int[] sampleGroupOff, short[] sampleGroups, double minAlleleDepthFrequency) throws IOException;
 	static native long tileFetchPop(long ctx, ByteBuffer sites, ByteBuffer calls, long[] stats) throws IOException;
@@ -88,6 +89,9 @@ public final class NgsepPileupNative implements AutoCloseable {
 			long nQual, ByteBuffer group) throws IOException {
 		tileSubmit(ctx, seqIdx, first, last, nReads, maxSpan, maxBack, hdr, payload, nWords, qual, nQual, group);
 	}
+	/** -knownVariants: the SNV sites of the NEXT tileSubmit (position; allele base indexes 2 bits each, reference first, their number in bits 8-10):
+	 *  that tile is genotyped at these sites (SingleSampleVariantPileupListener.genotypeVariantSample) instead of being searched for variants. */
+	public void tileSites(int nSites, int[] pos, short[] alleles) throws IOException { tileSites(ctx, nSites, pos, alleles); }
 	/** Number of ngsep_snv_call records written to calls; a value above calls.capacity()/224 means: call again with room for that many. */
 	public long tileFetch(ByteBuffer calls, long[] stats) throws IOException { return tileFetch(ctx, calls, stats); }
 	public long tileFetchPop(ByteBuffer sites, ByteBuffer calls, long[] stats) throws IOException { return tileFetchPop(ctx, sites, calls, stats); }

@@ -81,6 +81,16 @@ JNIEXPORT void JNICALL JNI_FN(tileSubmit)(JNIEnv* env, jclass cls, jlong ctx, ji
     int rc = ngsep_tile_submit((void*)(intptr_t)ctx, &t);
     if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_tile_submit");
 }
+/* ngsep_tile_sites: the known SNV sites (-knownVariants) of the next submitted tile */
+JNIEXPORT void JNICALL JNI_FN(tileSites)(JNIEnv* env, jclass cls, jlong ctx, jint nSites, jintArray pos, jshortArray alleles) {
+    (void)cls;
+    jint* p = (*env)->GetIntArrayElements(env, pos, NULL);
+    jshort* a = (*env)->GetShortArrayElements(env, alleles, NULL);
+    int rc = ngsep_tile_sites((void*)(intptr_t)ctx, nSites, (const int32_t*)p, (const uint16_t*)a);
+    (*env)->ReleaseIntArrayElements(env, pos, p, JNI_ABORT);
+    (*env)->ReleaseShortArrayElements(env, alleles, a, JNI_ABORT);
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_tile_sites");
+}
 /* ngsep_tile_fetch: returns the number of calls; a value above the buffer's capacity means "call again with a larger buffer" */
 JNIEXPORT jlong JNICALL JNI_FN(tileFetch)(JNIEnv* env, jclass cls, jlong ctx, jobject calls, jlongArray stats) {
     (void)cls;

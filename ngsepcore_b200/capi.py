@@ -55,7 +55,7 @@ EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_r
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
            "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
            "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop",
-           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram"]
+           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram", "ngsep_tile_sites"]
 
 # multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
 SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
     lib.ngsep_last_error.restype = C.c_char_p
     lib.ngsep_ref_upload.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.ngsep_tile_submit.argtypes = [C.c_void_p, C.POINTER(Tile)]
+    lib.ngsep_tile_sites.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.ngsep_resident_add.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(C.c_int)]
     lib.ngsep_resident_clear.argtypes = [C.c_void_p]
     lib.ngsep_resident_run.argtypes = [C.c_void_p, C.c_int]
@@ -199,6 +200,12 @@ class Context:
             break
         o = np.argsort(sites["pos"][: n.value], kind="stable")
         return sites[: n.value][o], calls[: n.value][o], counts, stats
+
+    def tile_sites(self, pos, alleles) -> None:
+        """-knownVariants: the SNV sites of the NEXT submitted tile.  alleles: per site the base indexes (A0 C1 G2 T3), reference first."""
+        pos = np.ascontiguousarray(pos, np.int32)
+        codes = np.ascontiguousarray([sum(b << (2 * k) for k, b in enumerate(a)) | (len(a) << 8) for a in alleles], np.uint16)
+        self._check(self.lib.ngsep_tile_sites(self.h, len(pos), pos.ctypes.data, codes.ctypes.data), "ngsep_tile_sites")
 
     def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None) -> None:
         t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality)

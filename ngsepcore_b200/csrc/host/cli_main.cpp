@@ -350,7 +350,7 @@ void usage() {
                          "       ngsep_b200 SingleSampleVariantsDetector -i <alignments.sam|.bam> -r <genome.fa> -o <outputPrefix>\n"
                          "  [-sampleId S] [-ploidy N] [-psp] [-minMQ N] [-querySeq S -first N -last N] [-ignoreLowerCaseRef]\n"
                          "  [-maxAlnsPerStartPos N] [-p] [-s] [-ignore5 N] [-ignore3 N] [-h X] [-maxBaseQS N] [-minQuality N]\n"
-                         "  [-embeddedSNVs] [-csb] [-knownSTRs file] [--device N] [--gpus N] [--tile-len N]\n");
+                         "  [-embeddedSNVs] [-csb] [-knownSTRs file] [-knownVariants file.vcf] [--device N] [--gpus N] [--tile-len N]\n");
 }
 
 }  // namespace
@@ -402,6 +402,7 @@ int main(int argc, char** argv) {
         else if (a == "-maxBaseQS") o.max_base_qs = std::atoi(val()); else if (a == "-minQuality") o.min_quality = std::atoi(val());
         else if (a == "-embeddedSNVs") o.call_embedded = true; else if (a == "-csb") o.csb = true;
         else if (a == "-knownSTRs" && !multi) o.known_strs = val();
+        else if (a == "-knownVariants" && !multi) o.known_variants = val();
         else if (a == "--device") o.device = std::atoi(val()); else if (a == "--tile-len") o.tile_len = std::atoi(val());
         else if (a == "--gpus") o.n_devices = std::max(1, std::atoi(val()));   // region tiles dealt to this many GPUs (device .. device + n - 1)
         else if (a == "--host-only") o.host_only = true;   // test hook: admission + event pre-pass only, indel / STR records only (no device)

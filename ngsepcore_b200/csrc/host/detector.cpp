@@ -92,9 +92,15 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
     int rc = opt_.host_only ? NGSEP_OK : ensure_ctx();
     if (rc != NGSEP_OK) return rc;
-    if (!opt_.known_strs.empty() && !strs_loaded_) {   // SSVD:906-913
+    if (!opt_.known_strs.empty() && opt_.known_variants.empty() && !strs_loaded_) {   // SSVD:906-913 (the else branch of -knownVariants)
         if (!load_known_strs(opt_.known_strs, *genome_, strs_, err_)) return NGSEP_EINVAL;
         strs_loaded_ = true;
+    }
+    if (!opt_.known_variants.empty() && !known_loaded_) {   // SSVD:897-905
+        if (!load_known_variants(opt_.known_variants, *genome_, known_, err_)) return NGSEP_EINVAL;
+        known_loaded_ = true;
+        n_known_ = 0;
+        for (auto& vs : known_) n_known_ += vs.size();
     }
     if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
@@ -152,15 +158,31 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
 // them meet again in the per-sequence merge (no collective: SURVEY 8e).
 int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
     const size_t n_dev = ctxs_.size();
-    std::vector<std::deque<SeqJob*>> q(n_dev);
+    struct InFlight { SeqJob* job; size_t site_base, n_sites; };   // (-knownVariants: the tile's piece of plan.sites)
+    std::vector<std::deque<InFlight>> q(n_dev);
+    const bool known = known_mode();
+    std::vector<int32_t> site_pos;
+    std::vector<uint16_t> site_codes;
     std::vector<int> slot(n_dev, 0);
     const size_t max_in_flight = opt_.synchronous ? 1 : (size_t)kHostRing - 1;
     auto fetch_oldest = [&](size_t dev) -> int {
         double td = now_s();
         ngsep_tile_stats ts{};
-        int rc = fetch_tile(ctxs_[dev], *q[dev].front(), ts);
+        const InFlight f = q[dev].front();
+        const size_t before = f.job->snvs.size();
+        int rc = fetch_tile(ctxs_[dev], *f.job, ts);
         q[dev].pop_front();
         if (rc != NGSEP_OK) return rc;
+        if (known) {   // record k of a site tile belongs to site k of the list it was submitted with
+            std::vector<ngsep_snv_call>& snvs = f.job->snvs;
+            for (size_t k = before; k < snvs.size(); k++) {
+                const ngsep_snv_call& c = snvs[k];
+                if (c.kind != NGSEP_CALL_SITE || c.sample < 0 || (size_t)c.sample >= f.n_sites) { err_ = "unexpected record from a tile of known sites"; return NGSEP_ESTATE; }
+                f.job->site_calls[f.site_base + (size_t)c.sample] = c;
+                f.job->site_have[f.site_base + (size_t)c.sample] = 1;
+            }
+            snvs.resize(before);
+        }
         stats_.device_s += now_s() - td;
         stats_.covered_positions += ts.covered_positions;
         stats_.candidate_positions += ts.candidate_positions;
@@ -171,7 +193,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         return NGSEP_OK;
     };
     auto drain = [&]() {   // after an error: nothing may stay in flight
-        for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { ngsep_tile_stats ts{}; fetch_tile(ctxs_[dev], *q[dev].front(), ts); q[dev].pop_front(); }
+        for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { ngsep_tile_stats ts{}; fetch_tile(ctxs_[dev], *q[dev].front().job, ts); q[dev].pop_front(); }
     };
     size_t dealt = 0;
     for (auto& job : jobs) {
@@ -180,9 +202,20 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         const int seq = job.seq;
         const int64_t tlen = tile_len();
         int tile_no = 0;
+        const std::vector<KnownVariant>* kvars = (known && (size_t)seq < known_.size()) ? &known_[(size_t)seq] : nullptr;
+        if (known) { job.site_calls.assign(plan.sites.size(), ngsep_snv_call{}); job.site_have.assign(plan.sites.size(), 0); }
+        size_t site_next = 0;
         for (int64_t tf = plan.win_first; tf <= plan.win_last; tf += tlen, tile_no++) {
-            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
             const int tl = (int)std::min<int64_t>(plan.win_last, tf + tlen - 1);
+            size_t site_base = 0, n_sites = 0;
+            if (known) {   // the known SNV sites of the tile; a tile without one has nothing to report
+                while (site_next < plan.sites.size() && (*kvars)[(size_t)plan.sites[site_next]].first < tf) site_next++;
+                site_base = site_next;
+                while (site_next < plan.sites.size() && (*kvars)[(size_t)plan.sites[site_next]].first <= tl) site_next++;
+                n_sites = site_next - site_base;
+                if (n_sites == 0) continue;
+            }
+            if (opt_.n_shards > 1 && (tile_no % opt_.n_shards) != opt_.shard) continue;
             size_t r_lo, r_hi;   // records whose ordering start can reach the tile
             tile_records(plan, (int)tf, tl, r_lo, r_hi);
             if (r_lo >= r_hi) continue;
@@ -201,10 +234,19 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             if (tile.hdr.empty()) continue;
             double td = now_s();
             ngsep_tile tv = tile.view(seq, (int)tf, tl);
-            int rc = ngsep_tile_submit(ctxs_[dev], &tv);
+            int rc = NGSEP_OK;
+            if (known) {
+                site_pos.clear(); site_codes.clear();
+                for (size_t k = 0; k < n_sites; k++) {
+                    const KnownVariant& v = (*kvars)[(size_t)plan.sites[site_base + k]];
+                    site_pos.push_back(v.first); site_codes.push_back(v.site_code);
+                }
+                rc = ngsep_tile_sites(ctxs_[dev], (int32_t)n_sites, site_pos.data(), site_codes.data());
+            }
+            if (rc == NGSEP_OK) rc = ngsep_tile_submit(ctxs_[dev], &tv);
             if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctxs_[dev]); drain(); return rc; }
             stats_.device_s += now_s() - td;
-            q[dev].push_back(&job);
+            q[dev].push_back(InFlight{&job, site_base, n_sites});
             slot[dev] = (slot[dev] + 1) % kHostRing;
             dealt++;
         }
@@ -261,11 +303,20 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         // -knownSTRs: every input locus is an event at its first position, whether a read anchors an indel there or not, and the
         // positions behind it are embedded (IRPL:89-99); indels inside a locus are not events of their own
         static const std::vector<StrLocus> no_loci;
-        const std::vector<StrLocus>& loci = (strs_loaded_ && (size_t)seq < strs_.size()) ? strs_[(size_t)seq] : no_loci;
+        static const std::vector<KnownVariant> no_known;
+        // -knownVariants: the input variants are the realigner's loci as well (IRPL:141-157), and every variant is genotyped at its
+        // first position (SSVPL:162-176): each of them is an event
+        const bool known = known_mode();
+        const std::vector<KnownVariant>& kvars = (known && (size_t)seq < known_.size()) ? known_[(size_t)seq] : no_known;
+        const std::vector<StrLocus> kloci = known ? known_variant_loci(kvars) : std::vector<StrLocus>();
+        const std::vector<StrLocus>& loci = known ? kloci : ((strs_loaded_ && (size_t)seq < strs_.size()) ? strs_[(size_t)seq] : no_loci);
         for (const StrLocus& l : loci) {
-            heap.push(l.first);
-            if (l.last > l.first) plan.embedded.push_back({l.first + 1, l.last});
+            if (l.starter) heap.push(l.first);
+            if (!known && l.last > l.first) plan.embedded.push_back({l.first + 1, l.last});
         }
+        for (const KnownVariant& v : kvars) heap.push(v.first);
+        IndelCallerOptions kio;
+        kio.max_base_qs = opt_.max_base_qs; kio.het_rate = opt_.het_rate; kio.min_quality = opt_.min_quality; kio.csb = false;
         auto locus_at = [&](int pos) -> const StrLocus* {
             auto it = std::upper_bound(loci.begin(), loci.end(), pos, [](int v, const StrLocus& l) { return v < l.first; });
             if (it == loci.begin()) return nullptr;
@@ -284,34 +335,55 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             }
             while (!heap.empty() && heap.top() == e) heap.pop();
             if (e < win_first || e > win_last) continue;  // no pileup outside the query window (APG:481-484)
+            bool prev_covered = false;   // (known variants) was e - 1 under a read?  Then a pileup — an empty one — is still handed out at e
+            if (known && e - 1 >= win_first) for (HostRead* r : active) if (r->st.first <= e - 1 && e - 1 <= r->st.last) { prev_covered = true; break; }
             size_t w = 0;
             for (size_t k = 0; k < active.size(); k++) if (active[k]->st.last >= e) active[w++] = active[k];  // APG:464-471
             active.resize(w);
             pileup.clear();
             for (HostRead* r : active) if (r->st.first <= e && e <= r->st.last) pileup.push_back(r);       // PR:154-156
             const StrLocus* locus = locus_at(e);
-            if (locus && locus->first != e) continue;    // inside an input locus: embedded, the realigner does nothing (IRPL:96-98)
-            if (locus) { if (pileup.empty()) continue; }
-            else {
+            // inside an input locus: embedded, the realigner does nothing (IRPL:96-98)
+            bool realign = !(locus && !(locus->starter && locus->first == e));
+            if (realign && locus) { if (pileup.empty()) realign = false; }
+            else if (realign) {
                 bool any = false;
                 for (HostRead* r : pileup) if (r->anchor_at(e)) { any = true; break; }
-                if (!any) continue;
+                if (!any) realign = false;
             }
-            before.clear();
-            for (HostRead* r : pileup) before.push_back(r->st);
-            EventOutcome ev = realigner.on_event(e, pileup, locus);
+            EventOutcome ev;
+            if (realign) {
+                before.clear();
+                for (HostRead* r : pileup) before.push_back(r->st);
+                ev = realigner.on_event(e, pileup, locus);
+            }
+            if (ev.fired) {
+                plan.stats.events++;
+                for (size_t k = 0; k < pileup.size(); k++) {
+                    HostRead* r = pileup[k];
+                    if (!r->derived) r->derive();
+                    if (r->st == before[k]) continue;
+                    if (r->cur_from == e) continue;  // cannot happen (one event per position); keeps windows well formed
+                    r->closed.push_back(Version{r->cur_from, e, before[k]});
+                    r->cur_from = e;
+                    plan.stats.versions++;
+                    for (auto& a : r->anchors) if (a.pos > e) heap.push(a.pos);
+                }
+            }
+            if (known) {
+                // ---- SingleSampleVariantPileupListener.onPileup with input variants (SSVPL:162-176): the variants that start at e, in
+                // list order, given that the generator hands out a pileup here: a position under a read, or the first position behind
+                // the last read of a covered stretch (APG:475-498: the reads that ended are only dropped after that empty pileup)
+                if (pileup.empty() && !prev_covered) continue;
+                auto it = std::lower_bound(kvars.begin(), kvars.end(), e, [](const KnownVariant& v, int p) { return v.first < p; });
+                for (; it != kvars.end() && it->first == e; ++it) {
+                    const int vi = (int)(it - kvars.begin());
+                    if (it->is_snv) plan.sites.push_back(vi);
+                    else plan.known_indels.push_back({vi, genotype_known_indel_at(e, it->alleles, pileup, kio)});
+                }
+                continue;
+            }
             if (!ev.fired) continue;
-            plan.stats.events++;
-            for (size_t k = 0; k < pileup.size(); k++) {
-                HostRead* r = pileup[k];
-                if (!r->derived) r->derive();
-                if (r->st == before[k]) continue;
-                if (r->cur_from == e) continue;  // cannot happen (one event per position); keeps windows well formed
-                r->closed.push_back(Version{r->cur_from, e, before[k]});
-                r->cur_from = e;
-                plan.stats.versions++;
-                for (auto& a : r->anchors) if (a.pos > e) heap.push(a.pos);
-            }
             // ---- SingleSampleVariantPileupListener.onPileup at the event (SSVPL:146-161) ----
             bool emb = e <= last_indel_end;
             if (ev.str && !ev.new_str && e >= last_indel_end) { last_indel_end = e + ev.span - 1; emb = false; }   // an input STR (SSVPL:150)
@@ -358,7 +430,33 @@ void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, 
     r_hi = std::upper_bound(reads.begin(), reads.end(), tl + plan.max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
 }
 
+// -knownVariants: one record per input variant that met a pileup, in the order of the input list (the listener appends them in that
+// order and SSVD:937 sorts by first, last — the order of the list — with a stable sort)
+void GpuSingleSampleVariantsDetector::emit_known_text(SeqJob& job) {
+    const std::string& chrom = genome_->names[job.seq];
+    const std::vector<KnownVariant>& kvars = known_[(size_t)job.seq];
+    SeqPlan& plan = job.plan;
+    size_t si = 0, ii = 0;
+    while (si < plan.sites.size() || ii < plan.known_indels.size()) {
+        const bool take_site = ii >= plan.known_indels.size() || (si < plan.sites.size() && plan.sites[si] < plan.known_indels[ii].first);
+        const int vi = take_site ? plan.sites[si] : plan.known_indels[ii].first;
+        const KnownVariant& v = kvars[(size_t)vi];
+        bool mine = true;   // records go to the shard that owns the tile of their position
+        if (opt_.n_shards > 1) mine = (((v.first - plan.win_first) / tile_len()) % opt_.n_shards) == opt_.shard;
+        if (mine) {
+            if (take_site) {
+                const bool have = si < job.site_have.size() && job.site_have[si];
+                if (have || opt_.host_only) {   // (host-only test runs report the host-made records only)
+                    if (!opt_.host_only) { job.text += known_snv_vcf_line(v, &job.site_calls[si], chrom, opt_.ploidy); job.snv_records++; }
+                } else job.text += known_snv_vcf_line(v, nullptr, chrom, opt_.ploidy), job.snv_records++;   // no record of the tile reaches the site
+            } else job.text += known_indel_vcf_line(v, plan.known_indels[ii].second, chrom, opt_.ploidy);
+        }
+        if (take_site) si++; else ii++;
+    }
+}
+
 void GpuSingleSampleVariantsDetector::emit_text(SeqJob& job) {
+    if (known_mode()) { emit_known_text(job); return; }
     const std::string& chrom = genome_->names[job.seq];
     SeqPlan& plan = job.plan;
     std::vector<ngsep_snv_call>& snvs = job.snvs;

@@ -51,6 +51,7 @@ DetectorOptions convert(const ngsep_detector_options* o) {
     d.synchronous = o->synchronous != 0;
     d.n_devices = o->n_devices < 1 ? 1 : o->n_devices;
     if (o->known_strs && o->known_strs[0]) d.known_strs = o->known_strs;
+    if (o->known_variants && o->known_variants[0]) d.known_variants = o->known_variants;
     return d;
 }
 

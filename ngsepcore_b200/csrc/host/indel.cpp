@@ -342,7 +342,8 @@ IndelCounts indel_counts(const std::vector<std::string>& alleles, const std::vec
 
 // SSVPL.genotypeVariantSample for a variant that is not an SNV (SSVPL:378-384, 386-388): VD.callIndel with the variant
 // given (VD:265-361) on the sample's calls, then the sample-level minQuality (40: the listener is a fresh one, MSVD:676-678).
-SampleIndelCall genotype_indel_sample(const std::vector<std::string>& alleles, const std::vector<const SpanCall*>& calls, int max_base_qs, double het_rate) {
+SampleIndelCall genotype_indel_sample(const std::vector<std::string>& alleles, const std::vector<const SpanCall*>& calls, int max_base_qs, double het_rate,
+                                      int sample_min_quality = 40) {
     SampleIndelCall sc;
     IndelCounts h = indel_counts(alleles, calls, max_base_qs);
     if (h.total == 0) return sc;                       // VD:273-276: undecided, no report
@@ -363,11 +364,26 @@ SampleIndelCall genotype_indel_sample(const std::vector<std::string>& alleles, c
     sc.has_report = true;
     sc.counts = h.counts;
     sc.logc = h.L;
-    if (40 > sc.gq) { sc.called.clear(); sc.gq = 0; }   // SSVPL:388 makeUndecided (the report stays)
+    if (sample_min_quality > sc.gq) { sc.called.clear(); sc.gq = 0; }   // SSVPL:388 makeUndecided (the report stays)
     return sc;
 }
 
 }  // namespace
+
+SampleIndelCall genotype_known_indel_at(int pos, const std::vector<std::string>& alleles, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt) {
+    const int span = (int)alleles[0].size();
+    std::vector<SpanCall> calls;
+    for (HostRead* r : pileup) {
+        SpanCall c;
+        if (!r->span_call(pos, pos + span - 1, c.allele, c.quals)) continue;
+        c.allele = upper(c.allele);
+        c.neg = r->neg;
+        calls.push_back(std::move(c));
+    }
+    std::vector<const SpanCall*> ptrs;
+    for (auto& c : calls) ptrs.push_back(&c);
+    return genotype_indel_sample(alleles, ptrs, opt.max_base_qs, opt.het_rate, opt.min_quality);
+}
 
 int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const std::vector<SampleDef>& samples,
                              const IndelCallerOptions& opt, PopIndelRecord& rec) {

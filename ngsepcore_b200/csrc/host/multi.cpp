@@ -63,6 +63,7 @@ std::vector<SampleDef> samples_from_read_groups(const std::vector<std::string>& 
 
 static DetectorOptions multi_options(DetectorOptions o) {
     o.het_modified = true;   // MSVD has no haploid default for the heterozygosity rate (MSVD:80)
+    o.known_strs.clear(); o.known_variants.clear();   // SingleSampleVariantsDetector options
     return o;
 }
 

@@ -27,9 +27,31 @@ struct RunStats {
 struct EventOutcome { bool fired = false; int span = 1; bool str = false, new_str = false; };
 
 // An input tandem-repeat locus of the realigner (-knownSTRs): first .. last after merging and padding (SSVD:843-894)
-struct StrLocus { int first = 0, last = 0; };
+struct StrLocus {
+    int first = 0, last = 0;
+    bool str = true;       // the input variant is a tandem repeat (PileupRecord.setSTR, IRPL:91)
+    bool starter = true;   // the realigner sees the variant START at `first` (IRPL:90); false: only the tail of an input variant that an
+                           // earlier, overlapping one hides (IRPL:141-157 returns the earlier variant while it lasts): every position embedded
+};
 // per sequence of the genome, sorted by position (strs.cpp)
 bool load_known_strs(const std::string& path, const Genome& genome, std::vector<std::vector<StrLocus>>& out, std::string& err);
+
+// -knownVariants (SSVD:897-905): one variant of the input VCF as vcf/VCFFileReader.loadVariants keeps it (VCFFileReader.java:192-255,
+// 261-306, 585-600): a variants/SNV (two alleles, both one base of ACGT) or a GenomicVariantImpl
+struct KnownVariant {
+    int first = 0, last = 0;
+    std::vector<std::string> alleles;      // reference first, as written in the file
+    int type = 0;                          // GenomicVariant.TYPE_* (0 undetermined, 1 SNV, 2 MULTISNV, 3 EMBEDDED, 4 INDEL, 5 STR)
+    int qs = 0;                            // QUAL column, rounded
+    std::string id;                        // ID column, "" = none
+    bool snv_class = false;                // instance of variants/SNV
+    bool is_snv = false;                   // GenomicVariant.isSNV(): genotyped on the device as a known site
+    uint16_t site_code = 0;                // the site's alleles as ngsep_tile_sites takes them
+};
+// per sequence of the genome, in the order of GenomicRegionSortedCollection.getSequenceRegions(name).asList(): first, then last, stable
+bool load_known_variants(const std::string& path, const Genome& genome, std::vector<std::vector<KnownVariant>>& out, std::string& err);
+// what IndelRealignerPileupListener.intersectWithVariants (IRPL:141-157) returns along a sequence, as disjoint loci sorted by position
+std::vector<StrLocus> known_variant_loci(const std::vector<KnownVariant>& vars);
 
 struct Realigner {
     const Genome* genome = nullptr;
@@ -92,6 +114,13 @@ struct PopIndelRecord {
 //         1: an indel variant that is not reported (nothing is reported at the position);  2: rec holds the record.
 int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const std::vector<SampleDef>& samples,
                              const IndelCallerOptions& opt, PopIndelRecord& rec);
+
+// SSVPL.genotypeVariantSample for a known variant that is not an SNV (SSVPL:378-388): PR.getAlleleCalls(reference allele length) +
+// CountsHelper.calculateCountsIndel over the variant's alleles + VD.callIndel with the variant given, then minQuality => undecided.
+SampleIndelCall genotype_known_indel_at(int pos, const std::vector<std::string>& alleles, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt);
+// VCF records of a -knownVariants run (SSVD:933-968): c == nullptr: no record gave a call (an undecided call without data, VD:23-27)
+std::string known_snv_vcf_line(const KnownVariant& v, const ngsep_snv_call* c, const std::string& chrom, int ploidy);
+std::string known_indel_vcf_line(const KnownVariant& v, const SampleIndelCall& c, const std::string& chrom, int ploidy);
 
 // Grow-only host array for tile buffers.  With `pin` set the allocation is page-locked through ngsep_host_register (what a
 // JVM host does for its direct ByteBuffers), so ngsep_tile_submit copies it asynchronously; a registration that fails (no
@@ -160,6 +189,7 @@ struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 
     bool call_embedded = false, csb = false;
     double min_allele_depth_freq = 0;   // MultisampleVariantsDetector.minAlleleDepthFrequency (MSVD:58)
     std::string known_strs;             // -knownSTRs: file with tandem-repeat loci (sequence, first, last); SingleSampleVariantsDetector only
+    std::string known_variants;         // -knownVariants: VCF with the variants to genotype (SSVD:897-905); SingleSampleVariantsDetector only
     // device plumbing (not reference options)
     int device = 0;
     int n_devices = 1;         // GPUs device .. device + n_devices - 1 of this host: region tiles are dealt to them in turn, every GPU with its own
@@ -181,6 +211,9 @@ struct SeqPlan {
     std::vector<PopIndelRecord> pop_indels;      // the same for a multi-sample run
     std::set<int> suppressed;                    // positions whose device SNV decision must not be reported
     std::vector<std::pair<int, int>> embedded;   // closed intervals of embedded positions (SSVPL:150-151)
+    // -knownVariants: the input variants that got a pileup (SSVPL:162-176), as indexes into the sequence's variant list
+    std::vector<int> sites;                                      // SNVs: genotyped on the device (ngsep_tile_sites), ascending position
+    std::vector<std::pair<int, SampleIndelCall>> known_indels;   // the others: genotyped by the host at their event
     int win_first = 1, win_last = 0, max_reach = 1, max_back = 0;
     RunStats stats;                              // what the host stages of this sequence add to the run's statistics
     std::string err;
@@ -192,6 +225,8 @@ struct SeqJob {
     int64_t lo = 0, hi = 0;                      // records of the batch
     SeqPlan plan;
     std::vector<ngsep_snv_call> snvs;            // single-sample device results
+    std::vector<ngsep_snv_call> site_calls;      // -knownVariants: the device's record of plan.sites[k] (site_have[k] != 0)
+    std::vector<char> site_have;
     std::vector<ngsep_pop_site> sites;           // multi-sample device results ...
     std::vector<ngsep_sample_call> scalls;       // ... n_samples per site
     uint64_t snv_records = 0;
@@ -217,6 +252,11 @@ protected:
     std::vector<void*> ctxs_;                    // one context per device
     std::vector<std::vector<StrLocus>> strs_;    // -knownSTRs: loci per sequence (loaded with the genome)
     bool strs_loaded_ = false;
+    std::vector<std::vector<KnownVariant>> known_;   // -knownVariants: per sequence
+    bool known_loaded_ = false;
+    bool known_mode() const { return known_loaded_ && n_known_ > 0; }   // SSVPL:147: an empty input list means discovery
+    size_t n_known_ = 0;
+    void emit_known_text(SeqJob& job);
     std::vector<std::vector<bool>> ref_uploaded_;   // per device, per sequence
     RunStats stats_;
     std::string err_;

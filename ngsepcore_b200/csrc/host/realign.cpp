@@ -1,5 +1,5 @@
 // Indel-realigner logic applied at ONE event position (a position where some covering read anchors an indel).
-// Restates IndelRealignerPileupListener.onPileup for runs without -knownVariants / -knownSTRs
+// Restates IndelRealignerPileupListener.onPileup; the input variants of -knownVariants / -knownSTRs reach it as loci
 // (IRPL = /root/reference/src/ngsep/discovery/IndelRealignerPileupListener.java).  At every other position the
 // listener only sets referenceSpan = 1 (IRPL:87-124), which is why the host can skip them.
 #include <algorithm>
@@ -66,7 +66,7 @@ EventOutcome Realigner::on_event(int pos, std::vector<HostRead*>& pileup, const 
     int event_end;
     if (locus) {   // IRPL:90-95: the pileup is an input STR, the event is its locus
         out.fired = true;
-        out.str = true;
+        out.str = locus->str;
         out.span = locus->last - locus->first + 1;
         event_end = locus->last;
         if (event_end <= pos) return out;   // IRPL:118: nothing to conciliate

@@ -59,6 +59,8 @@ struct Slot {
     DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
     DevBuf<ngsep_sample_call> d_scalls;       //                        ... x n_samples sample calls
     DevBuf<int32_t> d_counts;
+    DevBuf<int32_t> d_site_pos; DevBuf<uint16_t> d_site_alleles;   // -knownVariants: the sites of the staged tile (ngsep_tile_sites)
+    std::vector<int32_t> h_site_pos; std::vector<uint16_t> h_site_alleles;
     TileDev* d_tile = nullptr;                // device copy of `tile` for single-tile launches, followed by the 16-byte staging report
     bool report_read = false;                 // the staging report has been checked on the host
     unsigned int* d_report() const { return (unsigned int*)(d_tile + 1); }
@@ -77,6 +79,7 @@ struct Slot {
     unsigned int launches = 0;
     void release() {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
+        d_site_pos.release(); d_site_alleles.release();
         d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release(); d_ent.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
@@ -103,6 +106,8 @@ struct Ctx {
     bool samples_set = false;
     DevBuf<int> d_sgo; DevBuf<uint16_t> d_sgroups; DevBuf<ngsep_sample_call> d_scratch; DevBuf<uint8_t> d_gins;
     DevBuf<uint16_t> d_gkeys; DevBuf<uint32_t> d_gvals; DevBuf<unsigned char> d_cub;   // staging scratch of launch_group_index (stream-ordered reuse)
+    std::vector<int32_t> next_site_pos; std::vector<uint16_t> next_site_alleles;   // ngsep_tile_sites: sites of the next submitted tile
+    bool next_has_sites = false;
     int multi_grid = 0;                       // CTAs of k_genotype_columns_multi
     bool lazy_qual = false;                   // NGSEP_F_QUALITY_IN_PLACE (NGSEP_LAZY_QUAL=0/1 overrides)
     unsigned char* d_meta = nullptr;          // kMaxSlots x kMetaStride: per-slot counters, cleared with ONE memset per batch
@@ -233,7 +238,10 @@ int launch_slot(Ctx* c, Slot* s) {
     // The genotype kernel runs on its own stream behind the tile's window kernel: the context stream goes on with the next
     // tile (staging kernels, window kernel) meanwhile.  Genotype launches are ordered among themselves (shared scratch).
     CK(cudaStreamWaitEvent(c->geno_stream, s->em, 0), "wait for the window kernel");
-    if (s->tile.n_windows > 0) {
+    if (s->tile.site_pos) {   // known sites: genotyped, nothing is discovered (the window kernel has only counted the covered positions)
+        launch_genotype_sites(s->d_tile, c->d_prm, s->tile.n_sites, c->geno_grid, c->geno_stream);
+        s->launches = s->tile.n_windows > 0 ? 2 : 1;
+    } else if (s->tile.n_windows > 0) {
         if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(s), c->d_prm, c->params.n_samples, c->multi_grid, c->geno_stream);
         else launch_genotype(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         s->launches = 2;
@@ -428,6 +436,23 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         if (s->d_calls.cap < cap_calls) CK(s->d_calls.reserve(cap_calls), "calls alloc");
         d.calls = s->d_calls.p; d.n_calls = s->d_ncalls; d.cap_calls = (unsigned)s->d_calls.cap;
     }
+    d.site_pos = nullptr; d.site_alleles = nullptr; d.n_sites = 0;
+    if (s->pipelined && c->next_has_sites) {   // ngsep_tile_sites: this tile is genotyped at the listed sites
+        s->h_site_pos.swap(c->next_site_pos); s->h_site_alleles.swap(c->next_site_alleles);
+        c->next_site_pos.clear(); c->next_site_alleles.clear(); c->next_has_sites = false;
+        const size_t ns = s->h_site_pos.size();
+        for (size_t k = 0; k < ns; k++)
+            if (s->h_site_pos[k] < t->tile_first || s->h_site_pos[k] > t->tile_last) return fail(c, NGSEP_EINVAL, "ngsep_tile_sites: a site lies outside the tile");
+        CK(s->d_site_pos.reserve(ns + 1), "site alloc");
+        CK(s->d_site_alleles.reserve(ns + 1), "site alloc");
+        if (ns) {
+            CK(cudaMemcpyAsync(s->d_site_pos.p, s->h_site_pos.data(), ns * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream), "site copy");
+            CK(cudaMemcpyAsync(s->d_site_alleles.p, s->h_site_alleles.data(), ns * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream), "site copy");
+        }
+        if (s->d_calls.cap < ns + 16) { CK(s->d_calls.reserve(ns + 16), "calls alloc"); d.calls = s->d_calls.p; d.cap_calls = (unsigned)s->d_calls.cap; }
+        d.site_pos = s->d_site_pos.p; d.site_alleles = s->d_site_alleles.p; d.n_sites = (int)ns;
+        s->h2d_bytes += (uint64_t)ns * 6;
+    }
     d.counts_dbg = nullptr;
     if (c->params.flags & NGSEP_F_EMIT_ALL) {
         CK(s->d_counts.reserve((size_t)tile_len * 5), "counts alloc");
@@ -532,7 +557,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
 
 extern "C" {
 
-int ngsep_abi_version(void) { return 2002; }
+int ngsep_abi_version(void) { return 2003; }
 int ngsep_built_sm(void) { return 100; }
 
 const char* ngsep_last_error(void* ctx) {
@@ -716,6 +741,21 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
     if (rc != NGSEP_OK) return rc;
     c->ring_head = (c->ring_head + 1) % c->ring.size();
     c->ring_count++;
+    return NGSEP_OK;
+}
+
+int ngsep_tile_sites(void* ctx, int32_t n_sites, const int32_t* pos, const uint16_t* alleles) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites: single-sample contexts only");
+    if (n_sites < 0 || (n_sites > 0 && (!pos || !alleles))) return fail(c, NGSEP_EINVAL, "ngsep_tile_sites: bad arguments");
+    for (int32_t k = 0; k < n_sites; k++) {
+        const unsigned n_al = (alleles[k] >> 8) & 7u;
+        if (n_al < 2 || n_al > 4 || (alleles[k] >> 11)) return fail(c, NGSEP_EINVAL, "ngsep_tile_sites: a site needs 2 to 4 alleles");
+    }
+    c->next_site_pos.assign(pos, pos + n_sites);
+    c->next_site_alleles.assign(alleles, alleles + n_sites);
+    c->next_has_sites = true;
     return NGSEP_OK;
 }
 

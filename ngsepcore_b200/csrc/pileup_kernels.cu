@@ -1376,6 +1376,92 @@ __device__ __forceinline__ uint32_t sample_genotype(const SamplePost& P, int dep
 }
 
 
+// ------------------------------------------------------------------------------------------------------------
+// -knownVariants: the SNV sites of a tile (ngsep_tile_sites), one warp per site
+// ------------------------------------------------------------------------------------------------------------
+// SingleSampleVariantPileupListener.onPileup with input variants (SSVPL:162-176) for a variant that is an SNV:
+// genotypeVariantSample (SSVPL:361-391) = PR.getAlleleCalls(1) + CH.calculateCountsSNV over EVERY covering record in
+// pileup order (no screen, no hom-ref proof: a known site is reported whatever its genotype) + VD.genotypeSNV (VD:21-97)
+// for the site's own allele list + the minQuality rule of SSVPL:388.  Record t of the tile's call array belongs to site t.
+__global__ void __launch_bounds__(256) k_genotype_sites(const TileDev* __restrict__ tiles, const DevParams* __restrict__ gprm) {
+    __shared__ double s_tab2[kTab2Size];
+    const DevParams& prm = *gprm;
+    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) {   // the table of k_genotype_columns: what a counted base adds to the likelihood a lane owns
+        const int l = i % kTabLanes, row = i / kTabLanes, q = row >> 2, b = row & 3;
+        const int pa = (l < 4) ? l : ((l < 7) ? 0 : ((l < 9) ? 1 : 2));
+        const int pb = (l < 4) ? l : ((l < 7) ? l - 3 : ((l < 9) ? l - 5 : 3));
+        double v = 0.0;
+        if (row < kTabZeroRow) v = (b == pa || b == pb) ? ((l < 4) ? prm.tables[3 * q] : prm.tables[3 * q + 2]) : prm.tables[3 * q + 1];
+        s_tab2[i] = v;
+    }
+    __syncthreads();
+    const TileDev& d = tiles[0];
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    const int max_qs = prm.max_base_qs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *d.n_calls = (unsigned int)d.n_sites;
+    for (int t = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < d.n_sites; t += n_warps) {
+        const int pos = d.site_pos[t];
+        const uint32_t al = d.site_alleles[t];   // bits 0-7: up to four base indexes, reference first; bits 8-10: how many
+        Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        const int i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+        const int i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
+        const QualView qual(d);
+        double acc = 0.0;
+        ColCounts cc;
+        for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
+        cc.depth = 0;
+        for (int base = i_lo; base < i_hi; base += 32) {
+            uint32_t code = 0u;
+            if (base + lane < i_hi) {
+                const ngsep_read_hdr h = R.header(base + lane);
+                code = lane_eval(h, R.payload(h), qual, pos, max_qs);
+            }
+            count_round(code, cc);
+            accumulate_round(code, min(32, i_hi - base), acc, lane, s_tab2);
+        }
+        // logConditionalProbs[i][j] on lane 4 i + j (the matrix is symmetric: CH:231-249 with f == g == 250)
+        const int i = (lane & 15) >> 2, j = lane & 3;
+        const int lo = min(i, j), hi = max(i, j);
+        const int owner = (i == j) ? i : ((lo == 0) ? 3 + hi : ((lo == 1) ? 5 + hi : 9));
+        const double Lij = __shfl_sync(kFull, acc, owner);
+        double L[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) L[k] = __shfl_sync(kFull, acc, k);
+        if ((unsigned int)t >= d.cap_calls) continue;
+        ngsep_snv_call* o = &d.calls[t];
+        if (lane < 16) o->logcond[lane] = Lij;
+        if (lane == 16) {
+            o->seq_idx = d.seq_idx; o->pos = pos;
+            o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
+            o->depth = cc.depth;
+            for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
+        }
+        if (lane == 0) {
+            const int nA = (int)((al >> 8) & 7u);
+            int A[4];
+            for (int k = 0; k < 4; k++) A[k] = (int)((al >> (2 * k)) & 3u);
+            uint32_t gt = 0xffffu;
+            SamplePost P;
+            P.hom[A[0]] = 0.0;
+            if (cc.depth > 0) {
+                sample_posteriors(L, prm.tables[93], prm.tables[94], P);
+                gt = sample_genotype(P, cc.depth, A, nA, prm.min_quality);
+            }
+            const bool undecided = (gt & 0xffu) == 0xffu;
+            o->post_ref = (cc.depth > 0) ? P.hom[A[0]] : 0.0;
+            o->post_max = 0.0;
+            o->gq = (int16_t)(undecided ? 0 : (int)(gt >> 16));
+            o->qual = 0;
+            o->a0 = (int8_t)(undecided ? -1 : (int)(gt & 0xffu));
+            o->a1 = (int8_t)(undecided ? -1 : (int)((gt >> 8) & 0xffu));
+            o->ref = (int8_t)A[0];
+            o->kind = (int8_t)NGSEP_CALL_SITE;
+            o->sample = t;
+        }
+    }
+}
+
 // First entry of read-group list g that is >= want.  gblk[g][b] = the answer for want = b * kGroupBlock (built at
 // staging), so the search only looks at the few list entries that fall into one block of record indexes.
 constexpr int kGroupBlockShift = 8, kGroupBlock = 1 << kGroupBlockShift;
@@ -1811,6 +1897,11 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
     static const int min_blocks = [] { const char* e = getenv("NGSEP_GENO_MIN_BLOCKS"); return e ? atoi(e) : 4; }();
     if (min_blocks >= 6) k_genotype_columns<6><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
     else k_genotype_columns<4><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
+}
+
+void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s) {
+    const int grid = max(1, min(max_grid, (n_sites + 7) / 8));   // one warp per site
+    k_genotype_sites<<<grid, 256, 0, s>>>(d_tile, dprm);
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

@@ -61,6 +61,8 @@ struct TileDev {
     int32_t* counts_dbg;         // [tile_len][5] or null
     unsigned long long* counters;// [0] covered positions, [1] candidates
     const unsigned int* report;  // staging check of the tile (k_check_headers): [0] error bits
+    // -knownVariants (ngsep_tile_sites): the SNV sites genotyped on this tile instead of the discovery
+    const int32_t* site_pos; const uint16_t* site_alleles; int n_sites;
 };
 
 struct DevParams {
@@ -108,6 +110,7 @@ void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, u
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
+void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s);
 void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s);
 int genotype_multi_ctas_per_sm(int n_samples);
 size_t group_index_temp_bytes(int n);

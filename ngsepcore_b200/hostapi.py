@@ -35,7 +35,7 @@ class DetectorOptions(C.Structure):
                 ("ignore5", C.c_int32), ("ignore3", C.c_int32), ("het_rate", C.c_double), ("het_rate_set", C.c_int32),
                 ("max_base_qs", C.c_int32), ("min_quality", C.c_int32), ("call_embedded_snvs", C.c_int32), ("calc_strand_bias", C.c_int32),
                 ("device", C.c_int32), ("tile_len", C.c_int32), ("shard", C.c_int32), ("n_shards", C.c_int32), ("host_only", C.c_int32),
-                ("synchronous", C.c_int32), ("n_devices", C.c_int32), ("known_strs", C.c_char_p)]
+                ("synchronous", C.c_int32), ("n_devices", C.c_int32), ("known_strs", C.c_char_p), ("known_variants", C.c_char_p)]
 
 
 class RunStats(C.Structure):
@@ -222,7 +222,7 @@ class Detector:
                  first: int = 0, last: int = 1000000000, ignoreLowerCaseRef: bool = False, maxAlnsPerStartPos: int = 5, p: bool = False,
                  s: bool = False, ignore5: int = 0, ignore3: int = 0, h: float | None = None, maxBaseQS: int = 30, minQuality: int = 40,
                  embeddedSNVs: bool = False, csb: bool = False, device: int = 0, tile_len: int = 0, shard: int = 0, n_shards: int = 1, host_only: bool = False,
-                 synchronous: bool = False, n_devices: int = 1, knownSTRs: str | None = None):
+                 synchronous: bool = False, n_devices: int = 1, knownSTRs: str | None = None, knownVariants: str | None = None):
         self.lib = load_library()
         o = DetectorOptions()
         self.lib.ngsep_detector_options_default(C.byref(o))
@@ -240,6 +240,8 @@ class Detector:
         o.n_devices = int(n_devices)
         self._strs = knownSTRs.encode() if knownSTRs else None
         o.known_strs = self._strs
+        self._known = knownVariants.encode() if knownVariants else None
+        o.known_variants = self._known
         self.h = C.c_void_p()
         self._create(o)
         self._keep = []

@@ -78,6 +78,7 @@ struct GenomicVariant {
     std::vector<std::string> alleles;
     int8_t type = TYPE_UNDETERMINED;
     short qs = 0;
+    std::string id;          // VCF ID column ("" = none, GenomicVariantImpl.java:139-144)
     bool snv_class = false;  // instance of variants/SNV.java
     bool is_snv() const;     // GenomicVariantImpl.java:251-258 / SNV.java:193
     bool is_biallelic() const { return alleles.size() == 2; }
@@ -242,6 +243,11 @@ struct PileupListener {
 // An input variant of the realigner (IRPL:52-53, 62-66): with -knownSTRs the merged, padded tandem-repeat loci of
 // SingleSampleVariantsDetector.makeNonRedundantSTRs (SSVD:843-894), GenomicVariantImpl of TYPE_STR with the reference allele only
 struct InputVariant { int first = 0, last = 0; bool str = false; };
+// -knownVariants: vcf/VCFFileReader.loadVariants(file, true, true) (VCFFileReader.java:585-600 over :152-306, load mode MINIMAL)
+std::vector<GenomicVariant> load_variants(const std::string& path);
+// the per-sequence, position-sorted view GenomicRegionSortedCollection.getSequenceRegions(name).asList() gives of them
+// (genome/GenomicRegionSortedCollection.java:224-232, GenomicRegionPositionComparator.java:34-37: first, then last, stable)
+std::map<std::string, std::vector<GenomicVariant>> sort_variants_by_sequence(const std::vector<GenomicVariant>& vars);
 struct GenomicRegionRow { std::string seq; int first = 0, last = 0; };
 std::vector<GenomicRegionRow> load_regions(const std::string& path);   // genome/io/SimpleGenomicRegionFileHandler.java:57-80
 std::map<std::string, std::vector<InputVariant>> make_non_redundant_strs(const ReferenceGenome& genome, const std::vector<GenomicRegionRow>& strs);  // SSVD:843-894
@@ -281,11 +287,23 @@ struct SingleSampleVariantPileupListener : PileupListener {
     Sample sample{"Sample", 2, {}};
     std::vector<CalledVariant> called;
     int last_indel_end = 0;
+    // -knownVariants (SSVPL:77, 135-137): non-empty = genotype these variants instead of discovering
+    std::map<std::string, std::vector<GenomicVariant>> input_variants;
+    size_t n_input_variants = 0;
     // optional per-position count dump (test hook; not in the reference): pos -> A,C,G,T,DP
     std::vector<std::array<int, 6>>* counts_dump = nullptr;
     void on_pileup(PileupRecord& p) override;                    // SSVPL:146-177
-    void on_sequence_start(const std::string&) override { last_indel_end = 0; }
+    void on_sequence_start(const std::string& seq) override {    // SSVPL:183-187
+        auto it = input_variants.find(seq);
+        seq_input_variants = it == input_variants.end() ? nullptr : &it->second;
+        next_siv_index = 0;
+        last_indel_end = 0;
+    }
     void on_sequence_end(const std::string&) override {}
+private:
+    const std::vector<GenomicVariant>* seq_input_variants = nullptr;
+    size_t next_siv_index = 0;
+public:
     static bool reference_allele_discovery(PileupRecord& p, const ReferenceGenome& g, bool call_embedded, bool ignore_lower, std::string& out);  // SSVPL:191-206
     bool discover_variant(PileupRecord& p, const std::string& ref_allele, CalledVariant& out);   // SSVPL:213-232
     bool discover_snv_at(PileupRecord& p, char ref, CalledVariant& out);                         // SSVPL:234-255
@@ -326,6 +344,7 @@ struct DetectorOptions {
     int ignore5 = 0, ignore3 = 0; double het_rate = 0.001; bool het_modified = false; int max_base_qs = 30;
     short min_quality = 40; bool call_embedded = false, csb = false;
     std::string known_strs;             // -knownSTRs (SSVD:906-913)
+    std::string known_variants;         // -knownVariants (SSVD:897-905)
     double min_allele_depth_freq = 0;   // MSVD:58 (setter only, no CLI option id; oracle switch --minAlleleDepthFrequency)
 };
 struct SingleSampleVariantsDetector : PileupListener {

@@ -369,7 +369,18 @@ bool SingleSampleVariantPileupListener::reference_allele_discovery(PileupRecord&
     return true;
 }
 
-void SingleSampleVariantPileupListener::on_pileup(PileupRecord& p) {  // SSVPL:146-161 (inputVariants empty)
+void SingleSampleVariantPileupListener::on_pileup(PileupRecord& p) {  // SSVPL:146-177
+    if (n_input_variants > 0) {   // -knownVariants: the variants that start here are genotyped, nothing is discovered (SSVPL:162-176)
+        if (!seq_input_variants || next_siv_index >= seq_input_variants->size()) return;
+        const GenomicVariant* iv = &(*seq_input_variants)[next_siv_index];
+        while (iv->first <= p.pos) {
+            if (iv->first == p.pos) called.push_back(genotype_variant_sample(*iv, p, nullptr, het_rate));
+            next_siv_index++;
+            if (next_siv_index >= seq_input_variants->size()) return;
+            iv = &(*seq_input_variants)[next_siv_index];
+        }
+        return;
+    }
     if (p.input_str() && p.pos >= last_indel_end) last_indel_end = p.pos + p.span - 1;
     else if (p.pos <= last_indel_end) p.embedded = true;
     std::string ref;
@@ -639,7 +650,7 @@ void print_genotype_field(std::ostream& out, CalledVariant& call, bool snv_forma
 void print_vcf_record_single(std::ostream& out, CalledVariant& call, short ploidy) {  // SSVD:944-963 + VCFFileWriter.java:44-104
     bool snv_format = call.called_snv || call.has_all_counts;
     const GenomicVariant& v = call.var;
-    out << v.seq << "\t" << v.first << "\t.\t" << v.alleles[0] << "\t";
+    out << v.seq << "\t" << v.first << "\t" << (v.id.empty() ? "." : v.id) << "\t" << v.alleles[0] << "\t";
     if (v.alleles.size() == 1) out << ".";
     else for (size_t i = 1; i < v.alleles.size(); i++) { if (i > 1) out << ","; out << v.alleles[i]; }
     out << "\t" << v.qs << "\t.\t";
@@ -662,7 +673,14 @@ void SingleSampleVariantsDetector::begin() {
     gen.max_alns_per_start = opt.max_alns_per_start; gen.non_unique_primary = opt.non_unique_primary; gen.secondary = opt.secondary;
     gen.ignore5 = (int8_t)opt.ignore5; gen.ignore3 = (int8_t)opt.ignore3; gen.min_mq = opt.min_mq;
     realigner.genome = genome;
-    if (!opt.known_strs.empty()) realigner.input_variants = make_non_redundant_strs(*genome, load_regions(opt.known_strs));   // SSVD:906-913
+    if (!opt.known_variants.empty()) {   // SSVD:897-905: the same collection goes to the realigner and to the variant listener
+        auto by_seq = sort_variants_by_sequence(load_variants(opt.known_variants));
+        for (auto& kv : by_seq) {
+            var_listener.n_input_variants += kv.second.size();
+            for (auto& v : kv.second) realigner.input_variants[kv.first].push_back({v.first, v.last, v.type == TYPE_STR});
+        }
+        var_listener.input_variants = std::move(by_seq);
+    } else if (!opt.known_strs.empty()) realigner.input_variants = make_non_redundant_strs(*genome, load_regions(opt.known_strs));   // SSVD:906-913
     var_listener.genome = genome; var_listener.het_rate = opt.het_rate; var_listener.csb = opt.csb;
     var_listener.max_base_qs = (int8_t)opt.max_base_qs; var_listener.ignore_lower = opt.ignore_lower;
     var_listener.call_embedded = opt.call_embedded; var_listener.min_quality = opt.min_quality;
@@ -772,5 +790,113 @@ std::map<std::string, std::vector<InputVariant>> make_non_redundant_strs(const R
         if (last > 0) emit(std::max(1, first - 1), std::min(last + 1, seq_len));
     }
     return answer;
+}
+}  // namespace ngsep_oracle
+
+
+// ---- -knownVariants: vcf/VCFFileReader.loadVariants (VCFFileReader.java:585-600) over loadVCFRecord / loadGenomicVariant /
+//      loadInfoField (:152-306), load mode MINIMAL: only the variant of each record matters on this path ----
+namespace ngsep_oracle {
+static std::vector<std::string> parse_string(const std::string& s, char delim) {   // main/io/ParseUtils.java:38-53
+    std::vector<std::string> out;
+    std::string cur;
+    for (char c : s) { if (c == delim) { out.push_back(cur); cur.clear(); } else cur.push_back(c); }
+    out.push_back(cur);
+    return out;
+}
+static bool java_parse_int(const std::string& s, long& v) {   // Integer.parseInt
+    if (s.empty()) return false;
+    size_t i = (s[0] == '-' || s[0] == '+') ? 1 : 0;
+    if (i == s.size()) return false;
+    for (size_t k = i; k < s.size(); k++) if (!std::isdigit((unsigned char)s[k])) return false;
+    errno = 0;
+    v = std::strtol(s.c_str(), nullptr, 10);
+    return errno == 0 && v >= INT32_MIN && v <= INT32_MAX;
+}
+static int8_t variant_type_id(const std::string& name) {   // GenomicVariantImpl.java:44-58, 90-96
+    static const std::map<std::string, int8_t> ids = {
+        {"SNV", TYPE_BIALLELIC_SNV}, {"MULTISNV", TYPE_MULTIALLELIC_SNV}, {"EMBEDDED", TYPE_EMBEDDED_SNV}, {"INDEL", TYPE_INDEL}, {"STR", TYPE_STR},
+        {"CNV", 10}, {"REPEAT", 11}, {"DEL", 12}, {"INS", 13}, {"INV", 14}, {"DUP", 15}, {"Deletion", 12}, {"Insertion", 13}, {"Inversion", 14}, {"Duplication", 15}};
+    auto it = ids.find(name);
+    return it == ids.end() ? TYPE_UNDETERMINED : it->second;
+}
+
+std::vector<GenomicVariant> load_variants(const std::string& path) {
+    std::vector<GenomicVariant> answer;
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    std::string line;
+    size_t n_samples = 0;
+    bool have_samples_line = false;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!have_samples_line) {   // loadHeader (:142-149): "##" lines, then the line with the sample ids (VCFFileHeader.java:155-167)
+            if (line.rfind("##", 0) == 0) continue;
+            if (line.empty() || line[0] != '#') throw std::runtime_error("VCF file does not have line with sample ids");
+            auto items = parse_string(line, '\t');
+            n_samples = items.size() > 9 ? items.size() - 9 : 0;
+            have_samples_line = true;
+            continue;
+        }
+        auto items = parse_string(line, '\t');
+        if (items.size() < 8) continue;                                    // :154-157
+        // loadGenomicVariant, :192-255
+        long position;
+        if (!java_parse_int(items[1], position) || position <= 0) continue;
+        if (items[3].empty() || items[4].empty()) continue;
+        std::vector<std::string> alleles = {items[3]};
+        if (items[4][0] != '.') for (auto& a : parse_string(items[4], ',')) alleles.push_back(a);
+        if ((int)alleles.size() > MAX_NUM_ALLELES) continue;
+        short qs = 0;
+        if (!items[5].empty() && items[5][0] != '.') {
+            char* end = nullptr;
+            double d = std::strtod(items[5].c_str(), &end);
+            if (!end || *end) continue;
+            if (d > 32767) d = 255;
+            qs = (short)java_round(d);
+            if (qs < 0) continue;
+        }
+        GenomicVariant v;
+        v.seq = items[0]; v.first = (int)position; v.qs = qs;
+        if (items[2] != ".") v.id = items[2];
+        auto in_alphabet = [](char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; };
+        if (alleles.size() == 2 && items[3].size() == 1 && items[4].size() == 1 && in_alphabet(items[3][0]) && in_alphabet(items[4][0])) {
+            v.snv_class = true; v.type = TYPE_BIALLELIC_SNV; v.last = v.first; v.len = 1;
+        } else {
+            v.len = (int)alleles[0].size(); v.last = v.first + v.len - 1;      // GenomicVariantImpl.java:99-106
+        }
+        v.alleles = alleles;
+        // loadInfoField, :261-306 (what changes the variant itself)
+        if (items[7] != ".") {
+            bool sv_len_present = false;
+            std::vector<std::string> info;   // parseStringWithText(';', '"')
+            { std::string cur; bool text = false; for (char c : items[7]) { if (c == '"') text = !text; if (c == ';' && !text) { info.push_back(cur); cur.clear(); } else cur.push_back(c); } info.push_back(cur); }
+            for (auto& it : info) {
+                size_t eq = it.find('=');
+                if (eq == std::string::npos) continue;
+                std::string attr = it.substr(0, eq), value = it.substr(eq + 1);
+                if (attr == "TYPE") { int8_t t = variant_type_id(value); if (t > 0 && t <= 14) v.type = t; }
+                if (attr == "END" && !v.snv_class) { long l; if (!java_parse_int(value, l)) throw std::runtime_error("NumberFormatException: " + value); v.last = (int)l; if (!sv_len_present) v.len = v.last - v.first + 1; }
+                if (attr == "SVLEN" && !v.snv_class) { long l; if (!java_parse_int(value, l)) throw std::runtime_error("NumberFormatException: " + value); v.len = (int)l; sv_len_present = true; }
+                if (attr == "SVTYPE") { int8_t t = variant_type_id(value); if (t >= 10) v.type = t; }
+            }
+        }
+        // :166-181: the genotype columns must agree with the header
+        if (items.size() == 8) { if (n_samples > 0) continue; }
+        else if (items.size() - 9 != n_samples) continue;
+        if (v.alleles.size() < 2) continue;     // filterReferenceSitesGVCF, :593
+        if (v.type >= 10) continue;             // filterSVs, :594
+        answer.push_back(std::move(v));
+    }
+    if (!have_samples_line) throw std::runtime_error("VCF file does not have line with sample ids");
+    return answer;
+}
+
+std::map<std::string, std::vector<GenomicVariant>> sort_variants_by_sequence(const std::vector<GenomicVariant>& vars) {
+    std::map<std::string, std::vector<GenomicVariant>> out;
+    for (auto& v : vars) out[v.seq].push_back(v);
+    for (auto& kv : out)
+        std::stable_sort(kv.second.begin(), kv.second.end(), [](const GenomicVariant& a, const GenomicVariant& b) { return a.first != b.first ? a.first < b.first : a.last < b.last; });
+    return out;
 }
 }  // namespace ngsep_oracle

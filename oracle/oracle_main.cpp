@@ -111,6 +111,7 @@ int parse_options(int argc, char** argv, int start, DetectorOptions& opt, std::s
         else if (a == "-embeddedSNVs") opt.call_embedded = true;
         else if (a == "-csb") opt.csb = true;
         else if (a == "-knownSTRs") opt.known_strs = need("-knownSTRs");
+        else if (a == "-knownVariants") opt.known_variants = need("-knownVariants");
         else if (a == "--minAlleleDepthFrequency") opt.min_allele_depth_freq = std::atof(need("--minAlleleDepthFrequency"));
         else if (a == "--dump-counts") dump = need("--dump-counts");
         else if (a == "--stats") stats = need("--stats");

@@ -20,7 +20,7 @@ def test_header_symbols_exported():
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ngsep_abi_version() == 2002 and lib.ngsep_built_sm() == 100
+    assert lib.ngsep_abi_version() == 2003 and lib.ngsep_built_sm() == 100
 
 
 def test_struct_layouts_match_header():

@@ -192,3 +192,48 @@ def test_known_strs_mode(oracle, tmp_path, opts, det_kw):
     out = str(tmp_path / "out")
     subprocess.check_call([os.path.join(root, "ngsepcore_b200", "ngsep_b200"), "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-knownSTRs", strs] + list(opts))
     assert open(out + ".vcf").read() == want
+
+
+@pytest.mark.parametrize("depth,opts,det_kw", [
+    (25, (), {}),
+    (3, ("-minQuality", "10", "-maxBaseQS", "25"), dict(minQuality=10, maxBaseQS=25)),     # gaps in the cover, shallow columns, undecided calls
+])
+def test_known_variants_mode(oracle, tmp_path, depth, opts, det_kw):
+    """-knownVariants (SSVD:897-905; the genotyping half of the reference's per-sample pipeline, training/runGenotyping): the detector
+    genotypes the variants of an input VCF — SNV sites on the device (ngsep_tile_sites: every covering record counted, VD.genotypeSNV
+    for the site's alleles, no screen and no hom-ref proof), the other variants by the host at their realigner event — and reports
+    every one that meets a pileup, 0/0 and ./. included.  Input = the records of a discovery run plus hom-ref sites, multi-allelic
+    SNVs, SNVs inside indel spans, variants sharing a position, input STRs, uncovered positions and records the reader drops.
+    Whole detector (one tile, many tiles, synchronous) and the CLI against the oracle, byte for byte."""
+    from tests.known_util import make_known_vcf
+    contigs = [("chrA", 200000), ("chrB", 90000)]
+    genome, batch, truth = simulate.simulate(contigs=contigs, depth=depth, seeds=(341, 342, 343), indel_rate=1e-3, snv_rate=2e-3)
+    fa, sam, kv = str(tmp_path / "ref.fa"), str(tmp_path / "reads.sam"), str(tmp_path / "known.vcf")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    discovered, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-minQuality", "0"))
+    assert make_known_vcf(kv, discovered, genome, contigs, np.random.default_rng(depth), extra_per_contig=400) > 1000
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownVariants", kv) + opts)
+    body = _body(want)
+    gts = [l.split("\t")[9].split(":")[0] for l in body]
+    assert len(body) > 1000 and gts.count("0/0") > 50 and gts.count("./.") > 20 and sum("," in l.split("\t")[4] for l in body) > 50
+    det = hostapi.Detector(knownVariants=kv, **det_kw)
+    det.set_genome(genome)
+    assert det.run(batch) == want
+    tiled = hostapi.Detector(knownVariants=kv, tile_len=30000, **det_kw)
+    tiled.set_genome(genome)
+    assert tiled.run(batch) == want
+    sync = hostapi.Detector(knownVariants=kv, tile_len=70000, synchronous=True, **det_kw)
+    sync.set_genome(genome)
+    assert sync.run(batch) == want
+    parts = []
+    for shard in range(2):
+        d = hostapi.Detector(knownVariants=kv, tile_len=25000, shard=shard, n_shards=2, **det_kw)
+        d.set_genome(genome)
+        parts += _body(d.run(batch))
+    key = {n: i for i, (n, _) in enumerate(contigs)}
+    assert sorted(parts, key=lambda l: (key[l.split("\t")[0]], int(l.split("\t")[1]))) == sorted(body, key=lambda l: (key[l.split("\t")[0]], int(l.split("\t")[1])))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "out")
+    subprocess.check_call([os.path.join(root, "ngsepcore_b200", "ngsep_b200"), "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-knownVariants", kv] + list(opts))
+    assert open(out + ".vcf").read() == want

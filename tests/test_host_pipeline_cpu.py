@@ -225,3 +225,58 @@ def test_known_strs_indel_records_match_oracle(oracle, tmp_path, seed, kw, opts)
     det.set_genome(genome)
     got_lines = [l for l in det.run(batch).splitlines() if not l.startswith("#")]
     assert got_lines == want_lines
+
+
+def _is_snv_record(line):
+    t = line.split("\t")
+    return all(len(a) == 1 and a in "ACGT" for a in [t[3]] + t[4].split(","))
+
+
+@pytest.mark.parametrize("seed,kw,opts,det_kw", [
+    (4, dict(indel_rate=1e-3, depth=12), (), {}),
+    (5, dict(indel_rate=3e-3, depth=2), ("-minQuality", "20"), dict(minQuality=20)),                 # coverage gaps: variants without a pileup, empty pileups
+    (6, dict(indel_rate=2e-3, depth=20, indel_jitter=0.6), ("-querySeq", "chrA", "-first", "5000", "-last", "41000"), dict(querySeq="chrA", first=5000, last=41000)),
+])
+def test_known_variants_host_records_match_oracle(oracle, tmp_path, seed, kw, opts, det_kw):
+    """-knownVariants (SSVD:897-905): the input variants are the realigner's fixed events (IRPL:89-99, 141-157) and every one of them
+    that meets a pileup is genotyped (SSVPL:162-176) — homozygous-reference and undecided results are records too, with the ID and
+    QUAL of the input.  Host stages only (no GPU): the records of the variants that are NOT SNVs (VD.callIndel with the variant given)
+    against the oracle; the SNV sites are device work (tests/test_gpu_detector_parity.py::test_known_variants_mode)."""
+    from tests.known_util import make_known_vcf
+    contigs = [("chrA", 60000), ("chrB", 30000)]
+    genome, batch, truth = simulate.simulate(contigs=contigs, seeds=(seed * 10, seed * 10 + 1, seed * 10 + 2), **kw)
+    fa, sam, kv = str(tmp_path / "r.fa"), str(tmp_path / "r.sam"), str(tmp_path / "known.vcf")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    discovered, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-minQuality", "0"))
+    assert make_known_vcf(kv, discovered, genome, contigs, np.random.default_rng(seed)) > 200
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownVariants", kv) + opts)
+    want_lines = [l for l in want.splitlines() if not l.startswith("#") and not _is_snv_record(l)]
+    gts = {l.split("\t")[9].split(":")[0] for l in want_lines}
+    assert len(want_lines) > 40 and {"0/0", "./."} <= gts and len(gts) >= 3
+    det = hostapi.Detector(host_only=True, knownVariants=kv, **det_kw)
+    det.set_genome(genome)
+    got_lines = [l for l in det.run(batch).splitlines() if not l.startswith("#")]
+    assert got_lines == want_lines
+
+
+def test_known_variants_loader_and_empty_list(oracle, tmp_path):
+    """An input VCF without a usable record means discovery (SSVPL:147: inputVariants.size() == 0); a file without the #CHROM line is
+    an error (VCFFileHeader.java:165-167)."""
+    contigs = [("chrA", 30000)]
+    genome, batch, _ = simulate.simulate(contigs=contigs, seeds=(71, 72, 73), depth=15, indel_rate=2e-3)
+    fa, sam, kv = str(tmp_path / "r.fa"), str(tmp_path / "r.sam"), str(tmp_path / "known.vcf")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    open(kv, "w").write("##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\nchrA\t100\t.\tA\t<DEL>\t.\t.\tSVTYPE=DEL\nchrA\t200\t.\tA\t.\t.\t.\t.\n")
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownVariants", kv))
+    plain, _, _, _ = ou.run_ssvd(oracle, fa, sam)
+    assert want == plain
+    det = hostapi.Detector(host_only=True, knownVariants=kv)
+    det.set_genome(genome)
+    assert [l for l in det.run(batch).splitlines() if not l.startswith("#")] == [l for l in plain.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    open(kv, "w").write("chrA\t100\t.\tA\tC\t.\t.\t.\n")
+    bad = hostapi.Detector(host_only=True, knownVariants=kv)
+    bad.set_genome(genome)
+    with pytest.raises(Exception):
+        bad.run(batch)
