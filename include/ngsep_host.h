@@ -108,6 +108,11 @@ void ngsep_host_free(void* p);
  * admission with secondary alignments and 100 alignments per start position on the host, read-depth histograms per region tile on the
  * device (ngsep_coverage_histogram), the printed table (depth, positions, positions counting unique alignments only; "More") as text. */
 int ngsep_coverage_stats(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_mq, int device, char** text);
+/* RelativeAlleleCountsCalculator module (discovery/RelativeAlleleCountsCalculator.java:209-243, 246-290; option ids -i -o -m -M -q -s of
+ * main/CommandsDescriptor.xml:805-847; -frs / -srs are not built): admission with maxRD alignments per start position on the host, the
+ * allele counts of every position per region tile on the device (ngsep_tile_allele_counts), the three distributions of the report as text. */
+int ngsep_relative_allele_counts(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_rd, int max_rd,
+                                 int min_base_qs, int secondary, int device, char** text);
 /* How the quality array of the tile the calling thread packed last (ngsep_host_pack / ngsep_ssvd_pack) is coded: the values for
  * ngsep_tile.qual_bits and ngsep_tile.qual_dict. */
 int ngsep_host_pack_quality(uint32_t* qual_bits, uint8_t* qual_dict16);

@@ -251,6 +251,13 @@ int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
 int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, int64_t n, const int32_t* first, const int32_t* last, const uint8_t* unique,
                              int32_t max_coverage, uint64_t* hist_all, uint64_t* hist_unique);
 
+/* RelativeAlleleCountsCalculator (discovery/RelativeAlleleCountsCalculator.java:246-290), a PileupListener over PileupRecord.getAlleleCalls(1):
+ * for every position of the tile, out[2 i] = (largest allele count) | (number of alleles seen) << 28 and out[2 i + 1] = the second largest
+ * count, counting the calls whose base quality is >= min_base_qs; both words are 0 at a position with fewer than min_rd calls or without a
+ * counted call (the listener records nothing there).  Alleles are A, C, G, T and "any other base".  Synchronous; no tile may be in flight.
+ * With coded qualities (ngsep_tile.qual_bits 2 / 4) min_base_qs must lie in 4..30 — the codes keep min(30, q) and every q <= 3 alike. */
+int ngsep_tile_allele_counts(void* ctx, const ngsep_tile* tile, int32_t min_rd, int32_t min_base_qs, uint32_t* out);
+
 /* Synthetic inputs generated ON THE DEVICE — BASELINE configs[2] and [4] (64 Mb at 60x, 3.1 Gb at 30x, the 1000x panel): the
  * reference sequence and the packed tile of any region are pure functions of (seed, sequence, position / read index), so no
  * input crosses PCIe and every tile of a genome sees the same reads on whatever GPU.  Rates as the reference's simulator

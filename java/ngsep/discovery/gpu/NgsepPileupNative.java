@@ -33,6 +33,8 @@ public final class NgsepPileupNative implements AutoCloseable {
 	static native void tileSubmit(long ctx, int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords,
 			ByteBuffer qual, long nQual, ByteBuffer group) throws IOException;
 	static native void tileSites(long ctx, int nSites, int[] pos, short[] alleles) throws IOException;
+	static native void tileAlleleCounts(long ctx, int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords,
+			ByteBuffer qual, long nQual, int minRD, int minBaseQS, ByteBuffer out) throws IOException;
 	static native long tileFetch(long ctx, ByteBuffer calls, long[] stats) throws IOException;
 	static native void samplesSet(long ctx, int nGroups, int[] sampleGroupOff, short[] sampleGroups, double minAlleleDepthFrequency) throws IOException;
 	static native long tileFetchPop(long ctx, ByteBuffer sites, ByteBuffer calls, long[] stats) throws IOException;
@@ -92,6 +94,11 @@ public final class NgsepPileupNative implements AutoCloseable {
 	/** -knownVariants: the SNV sites of the NEXT tileSubmit (position; allele base indexes 2 bits each, reference first, their number in bits 8-10):
 	 *  that tile is genotyped at these sites (SingleSampleVariantPileupListener.genotypeVariantSample) instead of being searched for variants. */
 	public void tileSites(int nSites, int[] pos, short[] alleles) throws IOException { tileSites(ctx, nSites, pos, alleles); }
+	/** RelativeAlleleCountsCalculator.onPileup over a tile: per position (largest allele count | alleles << 28, second largest count), 8 bytes each, into out. */
+	public void tileAlleleCounts(int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords, ByteBuffer qual,
+			long nQual, int minRD, int minBaseQS, ByteBuffer out) throws IOException {
+		tileAlleleCounts(ctx, seqIdx, first, last, nReads, maxSpan, maxBack, hdr, payload, nWords, qual, nQual, minRD, minBaseQS, out);
+	}
 	/** Number of ngsep_snv_call records written to calls; a value above calls.capacity()/224 means: call again with room for that many. */
 	public long tileFetch(ByteBuffer calls, long[] stats) throws IOException { return tileFetch(ctx, calls, stats); }
 	public long tileFetchPop(ByteBuffer sites, ByteBuffer calls, long[] stats) throws IOException { return tileFetchPop(ctx, sites, calls, stats); }

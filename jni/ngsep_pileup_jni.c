@@ -91,6 +91,15 @@ JNIEXPORT void JNICALL JNI_FN(tileSites)(JNIEnv* env, jclass cls, jlong ctx, jin
     (*env)->ReleaseShortArrayElements(env, alleles, a, JNI_ABORT);
     if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_tile_sites");
 }
+/* ngsep_tile_allele_counts: out = direct IntBuffer-backed ByteBuffer of 8 bytes per tile position */
+JNIEXPORT void JNICALL JNI_FN(tileAlleleCounts)(JNIEnv* env, jclass cls, jlong ctx, jint seq, jint first, jint last, jint nReads, jint maxSpan, jint maxBack,
+                                                jobject hdr, jobject payload, jlong nWords, jobject qual, jlong nQual, jint minRD, jint minBaseQS, jobject out) {
+    (void)cls;
+    ngsep_tile t;
+    fill_tile(env, &t, seq, first, last, nReads, maxSpan, maxBack, hdr, payload, nWords, qual, nQual, NULL);
+    int rc = ngsep_tile_allele_counts((void*)(intptr_t)ctx, &t, minRD, minBaseQS, (uint32_t*)direct(env, out));
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_tile_allele_counts");
+}
 /* ngsep_tile_fetch: returns the number of calls; a value above the buffer's capacity means "call again with a larger buffer" */
 JNIEXPORT jlong JNICALL JNI_FN(tileFetch)(JNIEnv* env, jclass cls, jlong ctx, jobject calls, jlongArray stats) {
     (void)cls;

@@ -55,7 +55,7 @@ EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_r
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
            "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
            "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop",
-           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram", "ngsep_tile_sites"]
+           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram", "ngsep_tile_sites", "ngsep_tile_allele_counts"]
 
 # multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
 SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
@@ -80,6 +80,7 @@ def load_library() -> C.CDLL:
     lib.ngsep_ref_upload.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.ngsep_tile_submit.argtypes = [C.c_void_p, C.POINTER(Tile)]
     lib.ngsep_tile_sites.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ngsep_tile_allele_counts.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_int32, C.c_int32, C.c_void_p]
     lib.ngsep_resident_add.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(C.c_int)]
     lib.ngsep_resident_clear.argtypes = [C.c_void_p]
     lib.ngsep_resident_run.argtypes = [C.c_void_p, C.c_int]
@@ -219,6 +220,13 @@ class Context:
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1
         return slot.value
+
+    def tile_allele_counts(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, min_rd=10, min_base_qs=20, quality=None):
+        """RelativeAlleleCountsCalculator.onPileup over a tile: uint32 [n_pos, 2] = (largest allele count | alleles seen << 28, second largest count)."""
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, None, quality)
+        out = np.zeros((tile_last - tile_first + 1, 2), np.uint32)
+        self._check(self.lib.ngsep_tile_allele_counts(self.h, C.byref(t), min_rd, min_base_qs, out.ctypes.data), "ngsep_tile_allele_counts")
+        return out
 
     def coverage_histogram(self, tile_first: int, tile_last: int, first, last, unique, max_coverage: int = 300):
         """Read-depth histograms (all / unique alignments) of a region: arrays of max_coverage + 1 counts, [max_coverage] = more."""

@@ -106,7 +106,7 @@ struct QualCoder {
     uint8_t dict[16];
 };
 inline int qual_class(int c) { const int q = c - 33; return q <= 3 ? 0 : std::min(30, q); }
-QualCoder choose_coder(const bool* seen) {
+QualCoder choose_coder(const bool* seen, int min_bits = 0) {
     QualCoder qc;
     std::memset(qc.code_of, 0, sizeof qc.code_of);
     std::memset(qc.dict, 0, sizeof qc.dict);
@@ -116,6 +116,7 @@ QualCoder choose_coder(const bool* seen) {
     for (int k = 0; k < 31; k++) { code_of_class[k] = -1; if (present[k]) code_of_class[k] = n++; }
     int bits = n <= 4 ? 2 : (n <= 16 ? 4 : 8);
     if (const char* e = std::getenv("NGSEP_QUAL_BITS")) { const int v = std::atoi(e); if (v == 8 || (v == 4 && bits == 2)) bits = v; }   // experiments: wider than needed
+    if (bits < min_bits) bits = min_bits;   // a caller that needs the quality bytes themselves
     qc.bits = bits;
     if (bits == 8) return qc;
     for (int k = 0; k < 31; k++) if (code_of_class[k] >= 0) qc.dict[code_of_class[k]] = (uint8_t)(k == 0 ? 35 : 33 + k);
@@ -241,7 +242,7 @@ void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const 
 
 }  // namespace
 
-bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err) {
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits) {
     out.group.clear();
     const size_t n = hi > lo ? hi - lo : 0;
     const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 8192 + 1));   // small tiles are not worth a thread each
@@ -268,7 +269,7 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
     }
     bool any[256];
     for (int c = 0; c < 256; c++) { any[c] = false; for (int t = 0; t < nt; t++) any[c] = any[c] || seen[(size_t)t][(size_t)c]; }
-    const QualCoder qc = choose_coder(any);
+    const QualCoder qc = choose_coder(any, min_qual_bits);
     out.qual_bits = (uint32_t)qc.bits;
     std::memcpy(out.qual_dict, qc.dict, 16);
     if (nt == 1) pack_range(reads, lo, hi, qc, parts[0]);

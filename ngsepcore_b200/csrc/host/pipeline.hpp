@@ -170,7 +170,7 @@ struct PackedTile {
 // Packs reads[lo,hi) (all their versions) in pileup order, on up to host_threads() threads.  Returns false (and leaves `err`)
 // when a record cannot be represented in the device layout (more than 65535 bases or 255 CIGAR operations — also after the
 // realigner rewrote it).
-bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr);
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0);
 int host_threads();   // NGSEP_HOST_THREADS, else the hardware concurrency (at most 32)
 
 struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 that affect this path
@@ -309,6 +309,9 @@ std::string english_fmt(double v);   // main/io/ParseUtils.java:29, DecimalForma
 std::vector<int> impl_copy_numbers(const std::vector<int>& called, const std::vector<int>& allele_counts, bool has_counts, int ploidy, size_t n_alleles);
 void append_gt(std::string& s, const std::vector<int>& called, int ploidy);   // VCFFileWriter.java:171-199
 
+// RelativeAlleleCountsCalculator.runProcess + printResults over a batch (allele_counts.cpp): the report text goes to `out`
+int run_relative_allele_counts(const Genome& genome, const BatchView& b, int min_rd, int max_rd, int min_base_qs, bool secondary, int device, std::string& out,
+                               std::string& err);
 // CoverageStatisticsCalculator.processFile + printCoverageStats over a batch (coverage.cpp): the table text goes to `out`
 int run_coverage_stats(const Genome& genome, const BatchView& b, int min_mq, int device, std::string& out, std::string& err);
 

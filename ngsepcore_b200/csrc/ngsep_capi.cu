@@ -122,6 +122,7 @@ struct Ctx {
     DevBuf<uint4> d_open;
     DevBuf<int32_t> d_cov_first, d_cov_last; DevBuf<uint8_t> d_cov_unique; DevBuf<int2> d_cov_diff; DevBuf<unsigned char> d_cov_tmp;   // ngsep_coverage_histogram
     DevBuf<unsigned long long> d_cov_hist;
+    DevBuf<uint2> d_allele_out;   // ngsep_tile_allele_counts
     DevBuf<uint2> d_ent;     // resolved entries of the open columns (a full list only costs speed: such columns go out as record ranges)
     size_t q_min_cols = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
@@ -884,6 +885,34 @@ int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, i
     CK(cudaMemcpyAsync(h.data(), c->d_cov_hist.p, 2 * bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), "coverage copy");
     CK(cudaStreamSynchronize(c->stream), "coverage sync");
     for (size_t k = 0; k < bins; k++) { hist_all[k] = h[k]; hist_unique[k] = h[bins + k]; }
+    return NGSEP_OK;
+}
+
+// ---- RelativeAlleleCountsCalculator: the allele counts of every position of one region tile (k_allele_counts) --------------------
+int ngsep_tile_allele_counts(void* ctx, const ngsep_tile* t, int32_t min_rd, int32_t min_base_qs, uint32_t* out) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (!t || !out) return fail(c, NGSEP_EINVAL, "null argument");
+    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "ngsep_tile_allele_counts: single-sample contexts only");
+    if (c->ring_count != 0) return fail(c, NGSEP_ESTATE, "ngsep_tile_allele_counts: fetch the tiles in flight first");
+    // coded qualities keep min(30, q) with every q <= 3 alike (ngsep_tile.qual_bits): enough to compare with a threshold of 4..30 only
+    if (t->qual_bits != 0u && t->qual_bits != 8u && (min_base_qs < 4 || min_base_qs > 30))
+        return fail(c, NGSEP_EINVAL, "ngsep_tile_allele_counts: this base-quality threshold needs the quality bytes themselves (qual_bits 8)");
+    CK(cudaSetDevice(c->device), "set device");
+    Slot* s = c->ring[0];
+    c->next_has_sites = false;
+    int rc = stage_slot(c, s, t);
+    if (rc != NGSEP_OK) return rc;
+    const size_t n_pos = (size_t)(t->tile_last - t->tile_first + 1);
+    CK(c->d_allele_out.reserve(n_pos), "allele count alloc");
+    CK(cudaStreamSynchronize(c->stream), "staging");
+    rc = read_report(c, s);
+    if (rc != NGSEP_OK) return rc;
+    launch_allele_counts(s->d_tile, (int)n_pos, min_rd, min_base_qs, c->d_allele_out.p, c->sm_count * 8, c->stream);
+    CK(cudaGetLastError(), "allele count launch");
+    CK(cudaMemcpyAsync(out, c->d_allele_out.p, n_pos * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream), "allele count copy");
+    CK(cudaStreamSynchronize(c->stream), "allele counts");
+    s->staged = false;
     return NGSEP_OK;
 }
 

@@ -1462,6 +1462,84 @@ __global__ void __launch_bounds__(256) k_genotype_sites(const TileDev* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// RelativeAlleleCountsCalculator: allele counts of EVERY position of a tile (a PileupListener reducer)
+// ------------------------------------------------------------------------------------------------------------
+// discovery/RelativeAlleleCountsCalculator.java:246-290 per position: calls = PR.getAlleleCalls(1); fewer than minRD calls: nothing;
+// the calls whose base quality is at least minBaseQualityScore are counted per allele; out = the largest count, the second largest
+// and the number of alleles seen.  Read-centric: one CTA owns a window of positions and its count tile in shared memory
+// (position x {A, C, G, T, other, calls}); every record that can reach the window scatters its callable bases into the tile
+// (shared-memory atomics), then one thread per position reduces its row.  The callable-base rules are the detector's own
+// (resolve_offset / the simple-record test of lane_eval = RA.getAlleleCall, RA:747-871).
+constexpr int kAlleleT = 1024;
+__global__ void __launch_bounds__(256) k_allele_counts(const TileDev* __restrict__ tiles, int min_rd, int min_bq, uint2* __restrict__ out) {
+    __shared__ unsigned int s_cnt[kAlleleT * 6];
+    __shared__ int s_range[2];
+    const TileDev& d = tiles[0];
+    const QualView qual(d);
+    const int n_pos = d.tile_last - d.tile_first + 1;
+    const int n_win = (n_pos + kAlleleT - 1) / kAlleleT;
+    const int tid = threadIdx.x, lane = tid & 31;
+    Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+    for (int w = blockIdx.x; w < n_win; w += gridDim.x) {
+        const int A = d.tile_first + w * kAlleleT, B = min(d.tile_last, A + kAlleleT - 1);
+        for (int i = tid; i < kAlleleT * 6; i += blockDim.x) s_cnt[i] = 0u;
+        if (tid < 32) {
+            const int lo = warp_lower_bound(R, A - d.max_span + 1, lane);
+            const int hi = warp_lower_bound(R, B + d.max_back + 1, lane);
+            if (lane == 0) { s_range[0] = lo; s_range[1] = hi; }
+        }
+        __syncthreads();
+        const int i_lo = s_range[0], i_hi = s_range[1];
+        for (int i = i_lo + tid; i < i_hi; i += blockDim.x) {
+            const ngsep_read_hdr h = R.header(i);
+            const uint32_t* pay = R.payload(h);
+            if (h.meta & NGSEP_M_SIMPLE) {
+                const int L = (int)(h.meta & 0xffffu);
+                const uint32_t* b2 = pay + 1;
+                const uint32_t qoff = b2[((L + 15) >> 4) + ((L + 31) >> 5)];
+                const int o_lo = max(max((int)h.ign_start, 0), A - h.first);                 // RA:782-784
+                const int o_hi = min(L - max((int)h.ign_end, 0), B - h.first + 1);
+                for (int off = o_lo; off < o_hi; off++) {
+                    unsigned int* row = s_cnt + (h.first + off - A) * 6;
+                    atomicAdd(row + 5, 1u);
+                    if ((int)qual.at(qoff, (uint32_t)off) - 33 >= min_bq) atomicAdd(row + ((b2[off >> 4] >> ((off & 15) * 2)) & 3u), 1u);
+                }
+            } else {
+                const RecView r = view_record(h, pay);
+                int s, e;
+                record_interval(h, pay, s, e);
+                s = max(s, A); e = min(e, B);
+                for (int pos = s; pos <= e; pos++) {
+                    const int off = resolve_offset(r, h.ign_start, h.ign_end, pos);
+                    if (off < 0) continue;
+                    unsigned int* row = s_cnt + (pos - A) * 6;
+                    atomicAdd(row + 5, 1u);
+                    if ((int)qual.at(r.qoff, (uint32_t)off) - 33 < min_bq) continue;
+                    const bool other = (r.meta & NGSEP_M_NMASK) && ((r.nm[off >> 5] >> (off & 31)) & 1u);   // a base outside ACGT is an allele of its own
+                    atomicAdd(row + (other ? 4u : ((r.b2[off >> 4] >> ((off & 15) * 2)) & 3u)), 1u);
+                }
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p <= B - A; p += blockDim.x) {
+            const unsigned int* row = s_cnt + p * 6;
+            uint2 o = make_uint2(0u, 0u);
+            if ((int)row[5] >= min_rd) {
+                unsigned int mx = 0u, second = 0u, n_al = 0u;
+                for (int k = 0; k < 5; k++) {
+                    const unsigned int c = row[k];
+                    if (c) n_al++;
+                    if (c > mx) { second = mx; mx = c; } else if (c > second) second = c;
+                }
+                o = make_uint2(mx | (n_al << 28), second);
+            }
+            out[(size_t)(A - d.tile_first) + (size_t)p] = o;
+        }
+        __syncthreads();
+    }
+}
+
 // First entry of read-group list g that is >= want.  gblk[g][b] = the answer for want = b * kGroupBlock (built at
 // staging), so the search only looks at the few list entries that fall into one block of record indexes.
 constexpr int kGroupBlockShift = 8, kGroupBlock = 1 << kGroupBlockShift;
@@ -1902,6 +1980,11 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s) {
     const int grid = max(1, min(max_grid, (n_sites + 7) / 8));   // one warp per site
     k_genotype_sites<<<grid, 256, 0, s>>>(d_tile, dprm);
+}
+
+void launch_allele_counts(const TileDev* d_tile, int n_pos, int min_rd, int min_bq, uint2* out, int max_grid, cudaStream_t s) {
+    const int n_win = (n_pos + kAlleleT - 1) / kAlleleT;
+    k_allele_counts<<<max(1, min(max_grid, n_win)), 256, 0, s>>>(d_tile, min_rd, min_bq, out);
 }
 
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s) {

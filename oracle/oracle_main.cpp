@@ -6,6 +6,8 @@
 #include "ngsep_oracle.hpp"
 
 #include <chrono>
+#include <cmath>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -281,6 +283,134 @@ char* oracle_run_coverage_stats(const char* fasta_path, const char* sam_path, in
     gen.secondary = true;              // setProcessSecondaryAlignments(true)
     gen.max_alns_per_start = 100;      // setMaxAlnsPerStartPos(100)
     gen.min_mq = min_mq;
+    gen.listeners = {&calc};
+    AlignmentReader reader;
+    reader.filter_flags = gen.filter_flags();
+    reader.min_mq = gen.min_mq;
+    reader.genome = &genome;
+    std::string line;
+    SamRecord rec;
+    while (std::getline(sam, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (!parse_sam_line(line, rec)) continue;
+        ReadPtr a = reader.load(rec);
+        if (a) gen.process_alignment(a);
+    }
+    gen.notify_end();
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::ostringstream out;
+    calc.print(out);
+    std::string s = out.str();
+    char* res = (char*)std::malloc(s.size() + 1);
+    std::memcpy(res, s.c_str(), s.size() + 1);
+    return res;
+}
+
+// ---- math/Distribution.java (what RelativeAlleleCountsCalculator uses of it) ----------------------------------------------------
+struct Distribution {
+    double sum = 0, sum_sq = 0, count = 0, min_v, max_v, bin;
+    std::vector<double> dist;
+    long less = 0, more = 0;
+    Distribution(double mn, double mx, double b) : min_v(mn), max_v(mx), bin(b), dist((size_t)((int)((mx - mn) / b) + 1), 0.0) {}   // :46-55
+    void process(double value) {                                        // processDatapoint(1, value), :59-78
+        sum += value; sum_sq += value * value; count += 1;
+        if (value >= min_v && value <= max_v) dist[(size_t)(int)((value - min_v) / bin)] += 1;
+        else if (value < min_v) less++;
+        else if (value > max_v) more++;
+    }
+    void print(std::ostream& out, bool integer_counts) const {          // printDistribution(out, integerCounts, maxValueDistribution), :302-345
+        if (less > 0) { out << "Less\t"; if (integer_counts) out << less << "\n"; else out << english_fmt((double)less) << "\n"; }
+        const int max_idx = (int)((max_v - min_v) / bin);   // getBinIndex(double maxValue), :268-270
+        for (int i = 0; i < (int)dist.size() && i <= max_idx; i++) {
+            if (integer_counts) out << (int)(min_v + i * bin) << "\t" << (int)java_round(dist[(size_t)i]) << "\n";
+            else out << english_fmt(min_v + i * bin) << "\t" << english_fmt(dist[(size_t)i]) << "\n";
+        }
+        double more_count = (double)more;
+        for (int i = max_idx + 1; i < (int)dist.size(); i++) more_count += dist[(size_t)i];
+        if (more_count > 0) { out << "More\t"; if (integer_counts) out << (int)java_round(more_count) << "\n"; else out << english_fmt(more_count) << "\n"; }
+        if (count > 2147483647.0) out << "Count\t" << java_round(count) << "\n"; else out << "Count\t" << (int)java_round(count) << "\n";
+        if (integer_counts) { if (sum > 2147483647.0) out << "Sum\t" << java_round(sum) << "\n"; else out << "Sum\t" << (int)java_round(sum) << "\n"; }
+        else out << "Sum\t" << english_fmt(sum) << "\n";
+        if (count > 0) out << "Average\t" << english_fmt(sum / count) << "\n";
+        if (count > 1) {
+            double variance = (sum_sq - sum * sum / count) / (count - 1);
+            out << "Variance\t" << english_fmt(variance) << "\n";
+            out << "STDev\t" << english_fmt(std::sqrt(variance)) << "\n";
+        }
+    }
+};
+
+// ---- discovery/RelativeAlleleCountsCalculator.java -----------------------------------------------------------------------------
+// The listener (onPileup :246-290, onSequenceStart :309-320, printResults :221-243) on the generator runProcess configures for it
+// (:209-219): secondary alignments on request, maxRD alignments per start position.  (Regions to filter / select: not restated.)
+struct RelativeAlleleCountsCalculator : PileupListener {
+    int min_rd = 10, min_bq = 20;
+    const ReferenceGenome* genome = nullptr;
+    Distribution dist_prop{0, 0.5, 0.01}, dist_num{1, 10, 1};
+    std::vector<std::string> seq_names;
+    std::vector<Distribution> per_seq;
+    bool cur = false;
+    void on_pileup(PileupRecord& p) override {
+        auto calls = p.allele_calls(1, (const std::string*)nullptr);
+        if ((int)calls.size() < min_rd) return;
+        std::map<std::string, int> counts;   // TreeMap
+        for (auto& c : calls) {
+            int qs = (int)(int8_t)c.quals[0] - 33;
+            // (htsjdk hands the bases over in upper case — SAMRecord.setReadString normalises them — so the listener never sees a
+            // lower-case allele; this oracle's SAM reader keeps the file's case, hence the upper-casing here)
+            if (qs >= min_bq) counts[c.allele()]++;
+        }
+        if (counts.empty()) return;
+        dist_num.process((double)counts.size());
+        auto maximum = [&](const std::string* ignore) -> const std::string* {   // getMaximum, :292-305
+            const std::string* mx = nullptr; int mc = -1;
+            for (auto& kv : counts) { if (ignore && kv.first == *ignore) continue; if (!mx || mc < kv.second) { mx = &kv.first; mc = kv.second; } }
+            return mx;
+        };
+        const std::string* a1 = maximum(nullptr);
+        int c1 = 0, c2 = 0;
+        if (a1) { c1 = counts[*a1]; const std::string* a2 = maximum(a1); if (a2) c2 = counts[*a2]; }
+        if (c1 > 0) {
+            double prop = (double)c2 / (c1 + c2);
+            dist_prop.process(prop);
+            if (cur) per_seq.back().process(prop);
+        }
+    }
+    void on_sequence_start(const std::string& seq) override {
+        int i = genome->find(seq);
+        if (i >= 0 && genome->seqs[(size_t)i].size() > 100000) { seq_names.push_back(seq); per_seq.emplace_back(0, 0.5, 0.01); cur = true; }
+        else cur = false;
+    }
+    void on_sequence_end(const std::string&) override {}
+    void print(std::ostream& out) const {
+        out << "Distribution of allele proportions\n";
+        dist_prop.print(out, false);
+        out << "Distribution of number of alleles\n";
+        dist_num.print(out, true);
+        if (seq_names.empty()) return;
+        out << "Distribution of allele proportions per sequence\nProportion";
+        for (auto& n : seq_names) out << "\t" << n;
+        out << "\n";
+        double mn = 0;
+        for (size_t i = 0; i < dist_prop.dist.size(); i++) {
+            out << english_fmt(mn);
+            for (auto& d : per_seq) out << "\t" << english_fmt(d.dist[i]);
+            out << "\n";
+            mn += 0.01;
+        }
+    }
+};
+
+char* oracle_run_relative_allele_counts(const char* fasta_path, const char* sam_path, int min_rd, int max_rd, int min_bq, int secondary, double* seconds) {
+    ReferenceGenome genome = ReferenceGenome::load_fasta(fasta_path);
+    std::ifstream sam(sam_path);
+    if (!sam) return nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    RelativeAlleleCountsCalculator calc;
+    calc.min_rd = min_rd; calc.min_bq = min_bq; calc.genome = &genome;
+    AlignmentsPileupGenerator gen;
+    gen.secondary = secondary != 0;      // setProcessSecondaryAlignments(secondaryAlns)
+    gen.max_alns_per_start = max_rd;     // setMaxAlnsPerStartPos(maxRD)
     gen.listeners = {&calc};
     AlignmentReader reader;
     reader.filter_flags = gen.filter_flags();
