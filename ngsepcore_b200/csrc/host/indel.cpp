@@ -53,8 +53,6 @@ double fisher_pvalue(int a, int b, int c, int d) {
 
 namespace {
 
-struct SpanCall { std::string allele, quals; bool neg; };
-
 struct QTables {   // the slices of CountsHelper's caches this caller needs
     double match[31], err4[31], lf251_0, lf251_1, log_err_indel;
     double a250[31], c250[31];
@@ -196,56 +194,63 @@ std::vector<std::string> cluster_alleles(const std::vector<SpanCall>& calls, con
 
 }  // namespace
 
-bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str) {
-    const QTables& t = qt();
+void gather_span_event(int pos, const std::string& ref_allele, bool is_str, bool input_str, std::vector<HostRead*>& pileup, int max_base_qs, SpanEventInput& out) {
     const int span = (int)ref_allele.size();
-    std::vector<SpanCall> calls;
+    out.pos = pos; out.ref_allele = ref_allele; out.is_str = is_str; out.input_str = input_str;
+    out.calls.clear();
     for (HostRead* r : pileup) {
         SpanCall c;
         if (!r->span_call(pos, pos + span - 1, c.allele, c.quals)) continue;
         c.allele = upper(c.allele);
         c.neg = r->neg;
-        calls.push_back(std::move(c));
+        out.calls.push_back(std::move(c));
     }
-    std::vector<std::string> alleles = cluster_alleles(calls, ref_allele, opt.max_base_qs);
+    out.alleles = cluster_alleles(out.calls, ref_allele, max_base_qs);
+}
+
+// CountsHelper.calculateCountsIndel (CH:96-105, 253-304) + getPosteriorProbabilities (CH:410-495) + VD.getIndexesMaxGenotype (VD:223-243) on the
+// host: what k_indel_tallies computes on the device for the product's single-sample runs; this copy serves the sample axis, whose
+// per-sample genotypes stay on the host, and the host-only test hook.
+void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& opt, IndelTally& t) {
+    const QTables& q = qt();
+    const std::vector<std::string>& alleles = in.alleles;
     const int n = (int)alleles.size();
-    std::vector<int> counts(n, 0);
-    std::vector<std::array<int, 2>> strand(n, {0, 0});
-    std::vector<std::vector<double>> L(n, std::vector<double>(n, 0.0));
-    int total = 0;
-    for (auto& c : calls) {  // updateCountsIndel, CH:253-304
-        total++;
+    t = IndelTally();
+    t.counts.assign(n, 0);
+    t.strand.assign(n, {0, 0});
+    t.L.assign(n, std::vector<double>(n, 0.0));
+    for (auto& c : in.calls) {  // updateCountsIndel, CH:253-304
+        t.total++;
         int index = -1;
         for (int i = 0; i < n; i++) if (alleles[i] == c.allele) { index = i; break; }
-        std::vector<double> lc(n, t.log_err_indel);
+        std::vector<double> lc(n, q.log_err_indel);
         int best = -1;
         for (int i = 0; i < n; i++) {
             if (alleles[i].size() != c.allele.size()) continue;
             double v = 0;
             for (size_t k = 0; k < alleles[i].size(); k++) {  // calculateLogCond, CH:384-396
-                int q = (int)(int8_t)std::min(opt.max_base_qs, (int)(unsigned char)c.quals[k] - 33);
-                if (q < 3) continue;
-                v += (alleles[i][k] == c.allele[k]) ? t.match[q] : t.err4[q];
+                int qs = (int)(int8_t)std::min(opt.max_base_qs, (int)(unsigned char)c.quals[k] - 33);
+                if (qs < 3) continue;
+                v += (alleles[i][k] == c.allele[k]) ? q.match[qs] : q.err4[qs];
             }
-            lc[i] = std::max(t.log_err_indel, v);
-            if (lc[i] > t.log_err_indel && (best == -1 || lc[best] < lc[i])) best = i;
+            lc[i] = std::max(q.log_err_indel, v);
+            if (lc[i] > q.log_err_indel && (best == -1 || lc[best] < lc[i])) best = i;
         }
         if (index >= 0 && best >= 0 && best != index) index = std::min(index, best);
         else if (index < 0 && best >= 0) index = best;
-        if (index >= 0) { counts[index]++; strand[index][c.neg ? 0 : 1]++; }
+        if (index >= 0) { t.counts[index]++; t.strand[index][c.neg ? 0 : 1]++; }
         for (int i = 0; i < n; i++) {
-            L[i][i] += lc[i];
+            t.L[i][i] += lc[i];
             for (int j = 0; j < n; j++) {
                 if (i == j) continue;
-                if (j == index) L[i][j] += log_sum(t.lf251_0 + lc[index], t.lf251_1 + t.log_err_indel);
-                else if (i == index) L[i][j] += log_sum(t.lf251_1 + lc[index], t.lf251_0 + t.log_err_indel);
-                else L[i][j] += t.log_err_indel;
+                if (j == index) t.L[i][j] += log_sum(q.lf251_0 + lc[index], q.lf251_1 + q.log_err_indel);
+                else if (i == index) t.L[i][j] += log_sum(q.lf251_1 + lc[index], q.lf251_0 + q.log_err_indel);
+                else t.L[i][j] += q.log_err_indel;
             }
         }
     }
-    // callIndel, VD:265-361 (variant == null)
-    auto P = posteriors(L, opt.het_rate);
-    if (total == 0) return false;
+    auto P = posteriors(t.L, opt.het_rate);
+    t.p00 = P[0][0];
     int m0 = 0, m1 = 0;
     double pmax = P[0][0];
     for (int i = 0; i < n; i++) for (int j = i; j < n; j++) {
@@ -253,6 +258,16 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
         if (i != j) gp += P[j][i];
         if (gp > pmax + 0.01) { pmax = gp; m0 = i; m1 = j; }
     }
+    t.m0 = m0; t.m1 = m1;
+    t.max_p = P[m0][m1];
+    if (m0 != m1) t.max_p += P[m1][m0];
+}
+
+// callIndel, VD:265-361 (variant == null) from the tallies, then the filter of SSVPL:263
+bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const IndelCallerOptions& opt, IndelRecord& out) {
+    const std::vector<std::string>& alleles = in.alleles;
+    if (t.total == 0) return false;
+    const int m0 = t.m0, m1 = t.m1;
     std::vector<int> idx = {0};
     std::vector<std::string> va = {alleles[0]};
     bool length_change = false;
@@ -262,27 +277,25 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
         if (alleles[m1].size() != alleles[0].size()) length_change = true;
         if (va.size() == 3 && alleles[m1].size() != va[1].size()) length_change = true;
     }
-    if (!length_change && !input_str) return false;   // VD:307
+    if (!length_change && !in.input_str) return false;   // VD:307
     out = IndelRecord();
-    out.pos = pos;
-    out.last = pos + span - 1;
+    out.pos = in.pos;
+    out.last = in.pos + (int)in.ref_allele.size() - 1;
     out.alleles = va;
-    out.str = is_str;
-    out.qual = phred(P[0][0]);
-    for (int i : idx) out.counts.push_back(counts[i]);
+    out.str = in.is_str;
+    out.qual = phred(t.p00);
+    for (int i : idx) out.counts.push_back(t.counts[i]);
     out.logc.assign(idx.size(), std::vector<double>(idx.size(), 0.0));
-    for (size_t i = 0; i < idx.size(); i++) for (size_t j = 0; j < idx.size(); j++) out.logc[i][j] = L[idx[i]][idx[j]];
+    for (size_t i = 0; i < idx.size(); i++) for (size_t j = 0; j < idx.size(); j++) out.logc[i][j] = t.L[idx[i]][idx[j]];
     if (m1 != m0) out.called = (va.size() == 3) ? std::vector<int>{1, 2} : std::vector<int>{0, 1};
     else out.called = {m0 == 0 ? 0 : 1};
-    double max_p = P[m0][m1];
-    if (m0 != m1) max_p += P[m1][m0];
-    out.gq = phred(1 - max_p);
-    out.depth = total;
+    out.gq = phred(1 - t.max_p);
+    out.depth = t.total;
     if (opt.csb) {
         // CountsHelper.getScoreStrandBiasFisher is indexed with the positions in calledAlleles (VD:356-357), i.e. into the
         // helper's allele list, not the reduced list — restated as is.
         auto score = [&](int i1, int i2) {
-            double p = fisher_pvalue(strand[i1][0], strand[i2][0], strand[i1][1], strand[i2][1]);
+            double p = fisher_pvalue(t.strand[i1][0], t.strand[i2][0], t.strand[i1][1], t.strand[i2][1]);
             return std::min(100, phred(p));
         };
         if (out.called.size() == 1 && out.called[0] != 0) out.strand_bias = score(0, out.called[0]);
@@ -292,6 +305,14 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
     bool hom_ref = out.called.size() == 1 && out.called[0] == 0;
     if (hom_ref || opt.min_quality > out.gq) return false;
     return true;
+}
+
+bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str) {
+    SpanEventInput in;
+    gather_span_event(pos, ref_allele, is_str, input_str, pileup, opt.max_base_qs, in);
+    IndelTally t;
+    tally_span_event_host(in, opt, t);
+    return finish_indel_call(in, t, opt, out);
 }
 
 // ---- sample axis --------------------------------------------------------------------------------------------------

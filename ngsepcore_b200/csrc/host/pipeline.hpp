@@ -3,6 +3,7 @@
 // (src/ngsep/discovery/SingleSampleVariantsDetector.java: setters of :141-560, run() :589-656) and of
 // AlignmentsPileupGenerator (APG:71-193) for this path only.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -74,12 +75,26 @@ struct IndelRecord {
     int strand_bias = -1;
 };
 
+// One event with a reference span > 1 as the variant listener sees it (SSVPL:257-273): the calls of PR.getAlleleCalls(span) in pileup
+// order and the alleles AlleleCallClustersBuilder proposes for them (reference first)
+struct SpanCall { std::string allele, quals; bool neg = false; };
+struct SpanEventInput { int pos = 0; std::string ref_allele; bool is_str = false, input_str = false; std::vector<SpanCall> calls; std::vector<std::string> alleles; };
+// CountsHelper.calculateCountsIndel + posteriors + the arg-max genotype of one event: counts, strand counts, logConditionalProbs,
+// P(ref, ref), the genotype (m0 <= m1) and its probability
+struct IndelTally { int total = 0; std::vector<int> counts; std::vector<std::array<int, 2>> strand; std::vector<std::vector<double>> L; double p00 = 0, max_p = 0; int m0 = 0, m1 = 0; };
+
 struct IndelCallerOptions { int max_base_qs = 30; double het_rate = 0.001; int min_quality = 40; bool csb = false; };
 
 // SingleSampleVariantPileupListener.discoverVariantWithSpan (SSVPL:257-273) up to the SNV fall-back:
 // AlleleCallClustersBuilder + CountsHelper.calculateCountsIndel + VariantDiscoverySNVQAlgorithm.callIndel.
 // input_str: the span is an input tandem-repeat locus (PileupRecord.isInputSTR): a call without a length change is kept (VD:307)
 bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str = false);
+
+// The three steps of call_indel_at: gather (PR.getAlleleCalls(span) + AlleleCallClustersBuilder), tally (the device's k_indel_tallies in
+// single-sample runs; tally_span_event_host for the sample axis and the host-only test hook), finish (VD.callIndel's record + SSVPL:263)
+void gather_span_event(int pos, const std::string& ref_allele, bool is_str, bool input_str, std::vector<HostRead*>& pileup, int max_base_qs, SpanEventInput& out);
+void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& opt, IndelTally& t);
+bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const IndelCallerOptions& opt, IndelRecord& out);
 
 // Phred / rounding helpers shared by the host writer (math/PhredScoreHelper.java:31-40)
 long jround(double x);
