@@ -251,6 +251,33 @@ int ngsep_resident_stats(void* ctx, ngsep_tile_stats* stats);
 int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, int64_t n, const int32_t* first, const int32_t* last, const uint8_t* unique,
                              int32_t max_coverage, uint64_t* hist_all, uint64_t* hist_unique);
 
+/* Indel / STR allele tallies of the events with a reference span > 1: the per-call part of
+ * CountsHelper.updateCountsIndel (discovery/CountsHelper.java:253-304) over the calls of PileupRecord.getAlleleCalls(span) — calculateLogCond
+ * (CH:384-396) of every call against every allele of its length, the allele the call counts for (an exact match, else the best fit,
+ * CH:262-283), counts and strand counts per allele (CH:284-287), the diagonal of logConditionalProbs (CH:289) — one event per device thread,
+ * calls in pileup order, every sum a sum of host-supplied table values in the reference's order (bit-identical).  The host keeps what decides
+ * WHICH alleles and calls an event has (the realigner, IRPL:84-526; AlleleCallClustersBuilder, ACCB:72-141) and what hangs on libm: the
+ * heterozygous mixture terms log10(f 10^x + (1-f) 10^err) of the off-diagonal entries (CH:290-300), the posteriors (CH:410-495), the record
+ * (VD:265-361) — from call_index / call_fit, one addition per call and entry.
+ * Event k owns alleles allele_first[k] .. allele_first[k+1]) — the reference allele first — and calls call_first[k] .. call_first[k+1]) in
+ * pileup order; allele a = allele_chars[allele_off[a] .. allele_off[a+1]), call c = call_chars / call_quals (phred+33) [call_off[c] ..
+ * call_off[c+1]).  log_err = log10(0.0001) (CH:52).  Out: total[k] calls of event k (CH:254); counts / strand (negative, positive) / diag per
+ * allele; call_index[c] = the allele call c counts for (-1: none), call_fit[c] = its log-likelihood under that allele.  Synchronous. */
+typedef struct ngsep_indel_events {
+    int32_t n_events, n_alleles, n_calls, reserved;
+    const int32_t* allele_first;   /* [n_events + 1] */
+    const int32_t* call_first;     /* [n_events + 1] */
+    const int32_t* allele_off;     /* [n_alleles + 1] */
+    const int32_t* call_off;       /* [n_calls + 1]   */
+    const char* allele_chars;
+    const char* call_chars;
+    const uint8_t* call_quals;
+    const uint8_t* call_neg;       /* [n_calls] 1 = negative strand */
+    double log_err;
+} ngsep_indel_events;
+int ngsep_indel_tallies(void* ctx, const ngsep_indel_events* events, int32_t* total, int32_t* counts, int32_t* strand, double* diag, int32_t* call_index,
+                        double* call_fit);
+
 /* RelativeAlleleCountsCalculator (discovery/RelativeAlleleCountsCalculator.java:246-290), a PileupListener over PileupRecord.getAlleleCalls(1):
  * for every position of the tile, out[2 i] = (largest allele count) | (number of alleles seen) << 28 and out[2 i + 1] = the second largest
  * count, counting the calls whose base quality is >= min_base_qs; both words are 0 at a position with fewer than min_rd calls or without a

@@ -35,6 +35,8 @@ public final class NgsepPileupNative implements AutoCloseable {
 	static native void tileSites(long ctx, int nSites, int[] pos, short[] alleles) throws IOException;
 	static native void tileAlleleCounts(long ctx, int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords,
 			ByteBuffer qual, long nQual, int minRD, int minBaseQS, ByteBuffer out) throws IOException;
+	static native void indelTallies(long ctx, int[] alleleFirst, int[] callFirst, int[] alleleOff, int[] callOff, byte[] alleleChars, byte[] callChars, byte[] callQuals,
+			byte[] callNeg, double logErr, int[] total, int[] counts, int[] strand, double[] diag, int[] callIndex, double[] callFit) throws IOException;
 	static native long tileFetch(long ctx, ByteBuffer calls, long[] stats) throws IOException;
 	static native void samplesSet(long ctx, int nGroups, int[] sampleGroupOff, short[] sampleGroups, double minAlleleDepthFrequency) throws IOException;
 	static native long tileFetchPop(long ctx, ByteBuffer sites, ByteBuffer calls, long[] stats) throws IOException;
@@ -98,6 +100,13 @@ public final class NgsepPileupNative implements AutoCloseable {
 	public void tileAlleleCounts(int seqIdx, int first, int last, int nReads, int maxSpan, int maxBack, ByteBuffer hdr, ByteBuffer payload, long nWords, ByteBuffer qual,
 			long nQual, int minRD, int minBaseQS, ByteBuffer out) throws IOException {
 		tileAlleleCounts(ctx, seqIdx, first, last, nReads, maxSpan, maxBack, hdr, payload, nWords, qual, nQual, minRD, minBaseQS, out);
+	}
+	/** The per-call part of CountsHelper.updateCountsIndel for a batch of span > 1 events (include/ngsep_pileup.h: ngsep_indel_events): per allele counts,
+	 *  strand counts and the diagonal of logConditionalProbs, per call the allele it counts for and its fit; the caller adds the mixture terms
+	 *  (CountsHelper.java:290-300) with its own Math.log10 / Math.pow and goes on with getPosteriorProbabilities. */
+	public void indelTallies(int[] alleleFirst, int[] callFirst, int[] alleleOff, int[] callOff, byte[] alleleChars, byte[] callChars, byte[] callQuals, byte[] callNeg,
+			double logErr, int[] total, int[] counts, int[] strand, double[] diag, int[] callIndex, double[] callFit) throws IOException {
+		indelTallies(ctx, alleleFirst, callFirst, alleleOff, callOff, alleleChars, callChars, callQuals, callNeg, logErr, total, counts, strand, diag, callIndex, callFit);
 	}
 	/** Number of ngsep_snv_call records written to calls; a value above calls.capacity()/224 means: call again with room for that many. */
 	public long tileFetch(ByteBuffer calls, long[] stats) throws IOException { return tileFetch(ctx, calls, stats); }

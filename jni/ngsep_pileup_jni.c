@@ -100,6 +100,35 @@ JNIEXPORT void JNICALL JNI_FN(tileAlleleCounts)(JNIEnv* env, jclass cls, jlong c
     int rc = ngsep_tile_allele_counts((void*)(intptr_t)ctx, &t, minRD, minBaseQS, (uint32_t*)direct(env, out));
     if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_tile_allele_counts");
 }
+/* ngsep_indel_tallies: the events arrive as arrays (offsets int[], strings byte[]) */
+JNIEXPORT void JNICALL JNI_FN(indelTallies)(JNIEnv* env, jclass cls, jlong ctx, jintArray alleleFirst, jintArray callFirst, jintArray alleleOff, jintArray callOff,
+                                            jbyteArray alleleChars, jbyteArray callChars, jbyteArray callQuals, jbyteArray callNeg, jdouble logErr,
+                                            jintArray total, jintArray counts, jintArray strand, jdoubleArray diag, jintArray callIndex, jdoubleArray callFit) {
+    (void)cls;
+    ngsep_indel_events e;
+    memset(&e, 0, sizeof e);
+    e.n_events = (int32_t)(*env)->GetArrayLength(env, alleleFirst) - 1;
+    e.n_alleles = (int32_t)(*env)->GetArrayLength(env, alleleOff) - 1;
+    e.n_calls = (int32_t)(*env)->GetArrayLength(env, callOff) - 1;
+    jint* af = (*env)->GetIntArrayElements(env, alleleFirst, NULL); jint* cf = (*env)->GetIntArrayElements(env, callFirst, NULL);
+    jint* ao = (*env)->GetIntArrayElements(env, alleleOff, NULL); jint* co = (*env)->GetIntArrayElements(env, callOff, NULL);
+    jbyte* ac = (*env)->GetByteArrayElements(env, alleleChars, NULL); jbyte* cc = (*env)->GetByteArrayElements(env, callChars, NULL);
+    jbyte* cq = (*env)->GetByteArrayElements(env, callQuals, NULL); jbyte* cn = (*env)->GetByteArrayElements(env, callNeg, NULL);
+    jint* ot = (*env)->GetIntArrayElements(env, total, NULL); jint* oc = (*env)->GetIntArrayElements(env, counts, NULL); jint* os = (*env)->GetIntArrayElements(env, strand, NULL);
+    jdouble* od = (*env)->GetDoubleArrayElements(env, diag, NULL); jint* oi = (*env)->GetIntArrayElements(env, callIndex, NULL);
+    jdouble* of = (*env)->GetDoubleArrayElements(env, callFit, NULL);
+    e.allele_first = (const int32_t*)af; e.call_first = (const int32_t*)cf; e.allele_off = (const int32_t*)ao; e.call_off = (const int32_t*)co;
+    e.allele_chars = (const char*)ac; e.call_chars = (const char*)cc; e.call_quals = (const uint8_t*)cq; e.call_neg = (const uint8_t*)cn;
+    e.log_err = logErr;
+    int rc = ngsep_indel_tallies((void*)(intptr_t)ctx, &e, (int32_t*)ot, (int32_t*)oc, (int32_t*)os, od, (int32_t*)oi, of);
+    (*env)->ReleaseIntArrayElements(env, alleleFirst, af, JNI_ABORT); (*env)->ReleaseIntArrayElements(env, callFirst, cf, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, alleleOff, ao, JNI_ABORT); (*env)->ReleaseIntArrayElements(env, callOff, co, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, alleleChars, ac, JNI_ABORT); (*env)->ReleaseByteArrayElements(env, callChars, cc, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, callQuals, cq, JNI_ABORT); (*env)->ReleaseByteArrayElements(env, callNeg, cn, JNI_ABORT);
+    (*env)->ReleaseIntArrayElements(env, total, ot, 0); (*env)->ReleaseIntArrayElements(env, counts, oc, 0); (*env)->ReleaseIntArrayElements(env, strand, os, 0);
+    (*env)->ReleaseDoubleArrayElements(env, diag, od, 0); (*env)->ReleaseIntArrayElements(env, callIndex, oi, 0); (*env)->ReleaseDoubleArrayElements(env, callFit, of, 0);
+    if (rc != NGSEP_OK) throw_io(env, (void*)(intptr_t)ctx, rc, "ngsep_indel_tallies");
+}
 /* ngsep_tile_fetch: returns the number of calls; a value above the buffer's capacity means "call again with a larger buffer" */
 JNIEXPORT jlong JNICALL JNI_FN(tileFetch)(JNIEnv* env, jclass cls, jlong ctx, jobject calls, jlongArray stats) {
     (void)cls;

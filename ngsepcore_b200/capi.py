@@ -51,11 +51,17 @@ CALL_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)
                        ("logcond", "<f8", (16,)), ("post_ref", "<f8"), ("post_max", "<f8"), ("gq", "<i2"), ("qual", "<i2"),
                        ("a0", "i1"), ("a1", "i1"), ("ref", "i1"), ("kind", "i1"), ("sample", "<i4")], align=True)
 
+class IndelEvents(C.Structure):      # ngsep_indel_events
+    _fields_ = [("n_events", C.c_int32), ("n_alleles", C.c_int32), ("n_calls", C.c_int32), ("reserved", C.c_int32), ("allele_first", C.c_void_p),
+                ("call_first", C.c_void_p), ("allele_off", C.c_void_p), ("call_off", C.c_void_p), ("allele_chars", C.c_void_p), ("call_chars", C.c_void_p),
+                ("call_quals", C.c_void_p), ("call_neg", C.c_void_p), ("log_err", C.c_double)]
+
+
 EXPORTS = ["ngsep_ctx_create", "ngsep_ctx_destroy", "ngsep_last_error", "ngsep_ref_upload", "ngsep_tile_submit",
            "ngsep_tile_fetch", "ngsep_resident_add", "ngsep_resident_clear", "ngsep_resident_run", "ngsep_resident_fetch", "ngsep_resident_stats",
            "ngsep_timer_start", "ngsep_timer_stop", "ngsep_host_register", "ngsep_host_unregister", "ngsep_abi_version", "ngsep_built_sm",
            "ngsep_samples_set", "ngsep_tile_fetch_pop", "ngsep_resident_fetch_pop",
-           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram", "ngsep_tile_sites", "ngsep_tile_allele_counts"]
+           "ngsep_synth_reference", "ngsep_synth_tile", "ngsep_resident_download", "ngsep_ref_download", "ngsep_coverage_histogram", "ngsep_tile_sites", "ngsep_tile_allele_counts", "ngsep_indel_tallies"]
 
 # multi-sample results (include/ngsep_pileup.h: ngsep_pop_site, ngsep_sample_call)
 SITE_DTYPE = np.dtype([("seq_idx", "<i4"), ("pos", "<i4"), ("count", "<i4", (4,)), ("depth", "<i4"), ("qs", "<i2"), ("ref", "i1"), ("n_alleles", "i1"),
@@ -80,6 +86,7 @@ def load_library() -> C.CDLL:
     lib.ngsep_ref_upload.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
     lib.ngsep_tile_submit.argtypes = [C.c_void_p, C.POINTER(Tile)]
     lib.ngsep_tile_sites.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.ngsep_indel_tallies.argtypes = [C.c_void_p, C.POINTER(IndelEvents), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ngsep_tile_allele_counts.argtypes = [C.c_void_p, C.POINTER(Tile), C.c_int32, C.c_int32, C.c_void_p]
     lib.ngsep_resident_add.argtypes = [C.c_void_p, C.POINTER(Tile), C.POINTER(C.c_int)]
     lib.ngsep_resident_clear.argtypes = [C.c_void_p]
@@ -220,6 +227,31 @@ class Context:
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1
         return slot.value
+
+    def indel_tallies(self, events, log_err: float):
+        """events: list of (alleles [str, reference first], calls [(allele str, quality str phred+33, negative strand bool)]) -> per event
+        dict(total, counts, strand [n,2], diag, call_index, call_fit): the per-call part of CountsHelper.updateCountsIndel (ngsep_indel_tallies)."""
+        af, cf, ao, co = [0], [0], [0], [0]
+        ac, cc, cq, cn = bytearray(), bytearray(), bytearray(), bytearray()
+        for alleles, calls in events:
+            for a in alleles:
+                ac += a.encode(); ao.append(len(ac))
+            for a, q, neg in calls:
+                assert len(a) == len(q)
+                cc += a.encode(); cq += q.encode(); co.append(len(cc)); cn.append(1 if neg else 0)
+            af.append(len(ao) - 1); cf.append(len(co) - 1)
+        arr = lambda v, t: np.ascontiguousarray(v, t)
+        af, cf, ao, co = arr(af, np.int32), arr(cf, np.int32), arr(ao, np.int32), arr(co, np.int32)
+        ac, cc, cq, cn = (arr(np.frombuffer(bytes(b) + b"\0", np.uint8), np.uint8) for b in (ac, cc, cq, cn))
+        n_ev, n_al, n_ca = len(events), len(ao) - 1, len(co) - 1
+        e = IndelEvents(n_ev, n_al, n_ca, 0, af.ctypes.data, cf.ctypes.data, ao.ctypes.data, co.ctypes.data, ac.ctypes.data, cc.ctypes.data, cq.ctypes.data,
+                        cn.ctypes.data, log_err)
+        total, counts, strand = np.zeros(n_ev, np.int32), np.zeros(n_al, np.int32), np.zeros((n_al, 2), np.int32)
+        diag, idx, fit = np.zeros(n_al, np.float64), np.zeros(n_ca + 1, np.int32), np.zeros(n_ca + 1, np.float64)
+        self._check(self.lib.ngsep_indel_tallies(self.h, C.byref(e), total.ctypes.data, counts.ctypes.data, strand.ctypes.data, diag.ctypes.data, idx.ctypes.data,
+                                                 fit.ctypes.data), "ngsep_indel_tallies")
+        return [dict(total=int(total[k]), counts=counts[af[k]:af[k + 1]].copy(), strand=strand[af[k]:af[k + 1]].copy(), diag=diag[af[k]:af[k + 1]].copy(),
+                     call_index=idx[cf[k]:cf[k + 1]].copy(), call_fit=fit[cf[k]:cf[k + 1]].copy()) for k in range(n_ev)]
 
     def tile_allele_counts(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, min_rd=10, min_base_qs=20, quality=None):
         """RelativeAlleleCountsCalculator.onPileup over a tile: uint32 [n_pos, 2] = (largest allele count | alleles seen << 28, second largest count)."""

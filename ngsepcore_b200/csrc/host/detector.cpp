@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cmath>
 #include <deque>
 #include <queue>
 #include <set>
@@ -133,6 +134,12 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     for (auto& job : jobs) {
         if (job.rc != NGSEP_OK) { err_ = job.plan.err; return job.rc; }
         stats_.add_host(job.plan.stats);
+    }
+    if (deferred_tallies() && !known_mode()) {
+        rc = tally_span_events(jobs);
+        if (rc != NGSEP_OK) return rc;
+        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { resolve_fired_events(jobs[k].plan); });
+        for (auto& job : jobs) stats_.indel_calls += job.plan.stats.indel_calls_late;
     }
     // ---- stage 3: the device -------------------------------------------------------------------------------------------
     if (!opt_.host_only) {
@@ -384,6 +391,20 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
                 continue;
             }
             if (!ev.fired) continue;
+            if (deferred_tallies()) {   // the listener's part follows the device's tallies (resolve_fired_events)
+                SeqPlan::FiredEvent fe;
+                fe.e = e; fe.ev = ev;
+                std::string ref;
+                fe.ref_ok = genome_->get(seq, e, e + ev.span - 1, ref);
+                fe.ref_lower = fe.ref_ok && ref[0] >= 'a' && ref[0] <= 'z';
+                if (fe.ref_ok && ev.span > 1 && !(opt_.ignore_lower && fe.ref_lower)) {
+                    fe.input = (int)plan.span_inputs.size();
+                    plan.span_inputs.emplace_back();
+                    gather_span_event(e, upper(ref), ev.str, ev.str && !ev.new_str, pileup, opt_.max_base_qs, plan.span_inputs.back());
+                }
+                plan.fired.push_back(fe);
+                continue;
+            }
             // ---- SingleSampleVariantPileupListener.onPileup at the event (SSVPL:146-161) ----
             bool emb = e <= last_indel_end;
             if (ev.str && !ev.new_str && e >= last_indel_end) { last_indel_end = e + ev.span - 1; emb = false; }   // an input STR (SSVPL:150)
@@ -422,6 +443,86 @@ void GpuSingleSampleVariantsDetector::on_span_event(int e, const std::string& re
         plan.indels.push_back(std::move(rec));
         plan.stats.indel_calls++;
     }
+}
+
+// The allele tallies (per-call fits, counts, strand counts, diagonal of logConditionalProbs) of every span > 1 event of the run in ONE
+// device call (k_indel_tallies); the mixture terms and the posteriors are finished here (finish_tally)
+int GpuSingleSampleVariantsDetector::tally_span_events(std::vector<SeqJob>& jobs) {
+    size_t n_ev = 0;
+    for (auto& job : jobs) n_ev += job.plan.span_inputs.size();
+    if (n_ev == 0) return NGSEP_OK;
+    std::vector<int32_t> allele_first{0}, call_first{0}, allele_off{0}, call_off{0};
+    std::string allele_chars, call_chars;
+    std::vector<uint8_t> call_quals, call_neg;
+    for (auto& job : jobs)
+        for (const SpanEventInput& in : job.plan.span_inputs) {
+            for (auto& a : in.alleles) { allele_chars += a; allele_off.push_back((int32_t)allele_chars.size()); }
+            for (auto& c : in.calls) {
+                call_chars += c.allele;
+                call_quals.insert(call_quals.end(), c.quals.begin(), c.quals.begin() + (ptrdiff_t)c.allele.size());
+                call_off.push_back((int32_t)call_chars.size());
+                call_neg.push_back(c.neg ? 1 : 0);
+            }
+            allele_first.push_back((int32_t)allele_off.size() - 1);
+            call_first.push_back((int32_t)call_off.size() - 1);
+        }
+    if (allele_chars.size() > 0x7ffffff0ull || call_chars.size() > 0x7ffffff0ull) { err_ = "too many span events for one tally call"; return NGSEP_EINVAL; }
+    ngsep_indel_events ev{};
+    ev.n_events = (int32_t)n_ev; ev.n_alleles = (int32_t)allele_off.size() - 1; ev.n_calls = (int32_t)call_off.size() - 1;
+    ev.allele_first = allele_first.data(); ev.call_first = call_first.data(); ev.allele_off = allele_off.data(); ev.call_off = call_off.data();
+    ev.allele_chars = allele_chars.data(); ev.call_chars = call_chars.data(); ev.call_quals = call_quals.data(); ev.call_neg = call_neg.data();
+    ev.log_err = indel_log_error();
+    std::vector<int32_t> total(n_ev), counts((size_t)ev.n_alleles), strand(2 * (size_t)ev.n_alleles), call_index((size_t)ev.n_calls + 1);
+    std::vector<double> diag((size_t)ev.n_alleles), call_fit((size_t)ev.n_calls + 1);
+    int rc = ngsep_indel_tallies(ctx_, &ev, total.data(), counts.data(), strand.data(), diag.data(), call_index.data(), call_fit.data());
+    if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctx_); return rc; }
+    size_t k = 0;
+    for (auto& job : jobs) {
+        job.plan.span_tallies.resize(job.plan.span_inputs.size());
+        for (size_t i = 0; i < job.plan.span_inputs.size(); i++, k++) {
+            const int a0 = allele_first[k], n = allele_first[k + 1] - a0, c0 = call_first[k], c1 = call_first[k + 1];
+            CallTallies ct;
+            ct.total = total[k];
+            ct.counts.assign(counts.begin() + a0, counts.begin() + a0 + n);
+            ct.strand.resize((size_t)n);
+            for (int x = 0; x < n; x++) ct.strand[(size_t)x] = {strand[2 * (size_t)(a0 + x)], strand[2 * (size_t)(a0 + x) + 1]};
+            ct.diag.assign(diag.begin() + a0, diag.begin() + a0 + n);
+            ct.call_index.assign(call_index.begin() + c0, call_index.begin() + c1);
+            ct.call_fit.assign(call_fit.begin() + c0, call_fit.begin() + c1);
+            finish_tally(ct, (size_t)n, opt_.het_rate, job.plan.span_tallies[i]);   // the part that hangs on libm stays with the host's
+        }
+    }
+    return NGSEP_OK;
+}
+
+// SingleSampleVariantPileupListener.onPileup (SSVPL:146-161) + discoverVariantWithSpan (SSVPL:257-273) over the fired events of one
+// sequence, in order, with the device's tallies
+void GpuSingleSampleVariantsDetector::resolve_fired_events(SeqPlan& plan) {
+    IndelCallerOptions io;
+    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
+    int last_indel_end = 0;   // SSVPL:143
+    for (const SeqPlan::FiredEvent& fe : plan.fired) {
+        const int e = fe.e;
+        const EventOutcome& ev = fe.ev;
+        const bool input_str = ev.str && !ev.new_str;
+        bool emb = e <= last_indel_end;
+        if (input_str && e >= last_indel_end) { last_indel_end = e + ev.span - 1; emb = false; }   // SSVPL:150
+        if (emb && !opt_.call_embedded) continue;            // SSVPL:193
+        if (!fe.ref_ok) { plan.suppressed.insert(e); continue; }                                   // SSVPL:195-196
+        if (opt_.ignore_lower && fe.ref_lower) { plan.suppressed.insert(e); continue; }
+        if (emb || ev.span <= 1) continue;                   // SNV path: the device decides
+        if (input_str) plan.suppressed.insert(e);            // no SNV is tried at an input locus when the indel alleles give no call (SSVPL:264)
+        IndelRecord rec;
+        if (fe.input >= 0 && finish_indel_call(plan.span_inputs[(size_t)fe.input], plan.span_tallies[(size_t)fe.input], io, rec)) {
+            plan.suppressed.insert(e);
+            last_indel_end = rec.last;                       // SSVPL:157-158
+            if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
+            plan.indels.push_back(std::move(rec));
+            plan.stats.indel_calls_late++;
+        }
+    }
+    std::vector<SpanEventInput>().swap(plan.span_inputs);
+    std::vector<IndelTally>().swap(plan.span_tallies);
 }
 
 void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const {

@@ -208,19 +208,19 @@ void gather_span_event(int pos, const std::string& ref_allele, bool is_str, bool
     out.alleles = cluster_alleles(out.calls, ref_allele, max_base_qs);
 }
 
-// CountsHelper.calculateCountsIndel (CH:96-105, 253-304) + getPosteriorProbabilities (CH:410-495) + VD.getIndexesMaxGenotype (VD:223-243) on the
-// host: what k_indel_tallies computes on the device for the product's single-sample runs; this copy serves the sample axis, whose
-// per-sample genotypes stay on the host, and the host-only test hook.
-void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& opt, IndelTally& t) {
+// The per-call part of CountsHelper.updateCountsIndel (CH:253-289) on the host: what k_indel_tallies computes on the device for the
+// product's single-sample runs; this copy serves the sample axis, whose per-sample genotypes stay on the host, and the host-only
+// test hook.
+void tally_calls_host(const SpanEventInput& in, const IndelCallerOptions& opt, CallTallies& ct) {
     const QTables& q = qt();
     const std::vector<std::string>& alleles = in.alleles;
     const int n = (int)alleles.size();
-    t = IndelTally();
-    t.counts.assign(n, 0);
-    t.strand.assign(n, {0, 0});
-    t.L.assign(n, std::vector<double>(n, 0.0));
-    for (auto& c : in.calls) {  // updateCountsIndel, CH:253-304
-        t.total++;
+    ct = CallTallies();
+    ct.counts.assign(n, 0);
+    ct.strand.assign(n, {0, 0});
+    ct.diag.assign(n, 0.0);
+    for (auto& c : in.calls) {
+        ct.total++;
         int index = -1;
         for (int i = 0; i < n; i++) if (alleles[i] == c.allele) { index = i; break; }
         std::vector<double> lc(n, q.log_err_indel);
@@ -238,18 +238,40 @@ void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& o
         }
         if (index >= 0 && best >= 0 && best != index) index = std::min(index, best);
         else if (index < 0 && best >= 0) index = best;
-        if (index >= 0) { t.counts[index]++; t.strand[index][c.neg ? 0 : 1]++; }
-        for (int i = 0; i < n; i++) {
-            t.L[i][i] += lc[i];
+        if (index >= 0) { ct.counts[index]++; ct.strand[index][c.neg ? 0 : 1]++; }
+        for (int i = 0; i < n; i++) ct.diag[i] += lc[i];
+        ct.call_index.push_back(index);
+        ct.call_fit.push_back(index >= 0 ? lc[index] : q.log_err_indel);
+    }
+}
+
+// The rest of updateCountsIndel (the heterozygous mixture terms of the off-diagonal entries, CH:290-300: one log-sum per call and
+// direction), getPosteriorProbabilities (CH:410-495) and VD.getIndexesMaxGenotype (VD:223-243) — the part that hangs on libm.
+void finish_tally(const CallTallies& ct, size_t n_alleles, double het_rate, IndelTally& t) {
+    const QTables& q = qt();
+    const int n = (int)n_alleles;
+    t = IndelTally();
+    t.total = ct.total;
+    t.counts = ct.counts;
+    t.strand = ct.strand;
+    t.L.assign(n, std::vector<double>(n, 0.0));
+    for (int i = 0; i < n; i++) t.L[i][i] = ct.diag[i];
+    for (size_t c = 0; c < ct.call_index.size(); c++) {
+        const int index = ct.call_index[c];
+        double t_to = 0, t_from = 0;
+        if (index >= 0) {
+            t_to = log_sum(q.lf251_0 + ct.call_fit[c], q.lf251_1 + q.log_err_indel);
+            t_from = log_sum(q.lf251_1 + ct.call_fit[c], q.lf251_0 + q.log_err_indel);
+        }
+        for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 if (i == j) continue;
-                if (j == index) t.L[i][j] += log_sum(q.lf251_0 + lc[index], q.lf251_1 + q.log_err_indel);
-                else if (i == index) t.L[i][j] += log_sum(q.lf251_1 + lc[index], q.lf251_0 + q.log_err_indel);
+                if (j == index) t.L[i][j] += t_to;
+                else if (i == index) t.L[i][j] += t_from;
                 else t.L[i][j] += q.log_err_indel;
             }
-        }
     }
-    auto P = posteriors(t.L, opt.het_rate);
+    auto P = posteriors(t.L, het_rate);
     t.p00 = P[0][0];
     int m0 = 0, m1 = 0;
     double pmax = P[0][0];
@@ -262,6 +284,14 @@ void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& o
     t.max_p = P[m0][m1];
     if (m0 != m1) t.max_p += P[m1][m0];
 }
+
+void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& opt, IndelTally& t) {
+    CallTallies ct;
+    tally_calls_host(in, opt, ct);
+    finish_tally(ct, in.alleles.size(), opt.het_rate, t);
+}
+
+double indel_log_error() { return qt().log_err_indel; }
 
 // callIndel, VD:265-361 (variant == null) from the tallies, then the filter of SSVPL:263
 bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const IndelCallerOptions& opt, IndelRecord& out) {

@@ -20,6 +20,7 @@ namespace host {
 
 struct RunStats {
     uint64_t records = 0, admitted = 0, versions = 0, events = 0, indel_calls = 0, snv_calls = 0;
+    uint64_t indel_calls_late = 0;   // (per sequence) indel records made after the device's tallies
     uint64_t covered_positions = 0, candidate_positions = 0, aligned_bases = 0, tiles = 0, kernel_launches = 0;
     double kernel_ms = 0, prepass_s = 0, pack_s = 0, device_s = 0, total_s = 0;   // prepass_s: wall time of the (parallel) host planning stage
     void add_host(const RunStats& o) { admitted += o.admitted; versions += o.versions; events += o.events; indel_calls += o.indel_calls; }
@@ -83,6 +84,10 @@ struct SpanEventInput { int pos = 0; std::string ref_allele; bool is_str = false
 // P(ref, ref), the genotype (m0 <= m1) and its probability
 struct IndelTally { int total = 0; std::vector<int> counts; std::vector<std::array<int, 2>> strand; std::vector<std::vector<double>> L; double p00 = 0, max_p = 0; int m0 = 0, m1 = 0; };
 
+// The per-call part of CountsHelper.updateCountsIndel of one event (the device's k_indel_tallies): per allele counts, strand counts and the
+// diagonal of logConditionalProbs; per call the allele it counts for (-1: none) and its log-likelihood under that allele
+struct CallTallies { int total = 0; std::vector<int> counts; std::vector<std::array<int, 2>> strand; std::vector<double> diag; std::vector<int> call_index; std::vector<double> call_fit; };
+
 struct IndelCallerOptions { int max_base_qs = 30; double het_rate = 0.001; int min_quality = 40; bool csb = false; };
 
 // SingleSampleVariantPileupListener.discoverVariantWithSpan (SSVPL:257-273) up to the SNV fall-back:
@@ -94,6 +99,9 @@ bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vec
 // single-sample runs; tally_span_event_host for the sample axis and the host-only test hook), finish (VD.callIndel's record + SSVPL:263)
 void gather_span_event(int pos, const std::string& ref_allele, bool is_str, bool input_str, std::vector<HostRead*>& pileup, int max_base_qs, SpanEventInput& out);
 void tally_span_event_host(const SpanEventInput& in, const IndelCallerOptions& opt, IndelTally& t);
+void tally_calls_host(const SpanEventInput& in, const IndelCallerOptions& opt, CallTallies& ct);
+void finish_tally(const CallTallies& ct, size_t n_alleles, double het_rate, IndelTally& t);   // mixture terms, posteriors, arg-max genotype
+double indel_log_error();   // log10(0.0001), CH:52
 bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const IndelCallerOptions& opt, IndelRecord& out);
 
 // Phred / rounding helpers shared by the host writer (math/PhredScoreHelper.java:31-40)
@@ -226,6 +234,12 @@ struct SeqPlan {
     std::vector<PopIndelRecord> pop_indels;      // the same for a multi-sample run
     std::set<int> suppressed;                    // positions whose device SNV decision must not be reported
     std::vector<std::pair<int, int>> embedded;   // closed intervals of embedded positions (SSVPL:150-151)
+    // single-sample runs: the tallies of the span > 1 events are made on the device (ngsep_indel_tallies), so the listener's sequential part
+    // (SSVPL:146-161: what is embedded, which calls stand) runs after the sweep, over the events it fired, in order
+    struct FiredEvent { int e = 0; EventOutcome ev; bool ref_ok = false, ref_lower = false; int input = -1; };
+    std::vector<FiredEvent> fired;
+    std::vector<SpanEventInput> span_inputs;     // FiredEvent.input indexes these (events with a reference span > 1 and a reference allele)
+    std::vector<IndelTally> span_tallies;
     // -knownVariants: the input variants that got a pileup (SSVPL:162-176), as indexes into the sequence's variant list
     std::vector<int> sites;                                      // SNVs: genotyped on the device (ngsep_tile_sites), ascending position
     std::vector<std::pair<int, SampleIndelCall>> known_indels;   // the others: genotyped by the host at their event
@@ -272,6 +286,10 @@ protected:
     bool known_mode() const { return known_loaded_ && n_known_ > 0; }   // SSVPL:147: an empty input list means discovery
     size_t n_known_ = 0;
     void emit_known_text(SeqJob& job);
+    // the tallies of every sequence's span > 1 events in ONE device call, then the listener's sequential part per sequence
+    int tally_span_events(std::vector<SeqJob>& jobs);
+    void resolve_fired_events(SeqPlan& plan);
+    bool deferred_tallies() const { return !opt_.host_only && !with_groups(); }
     std::vector<std::vector<bool>> ref_uploaded_;   // per device, per sequence
     RunStats stats_;
     std::string err_;

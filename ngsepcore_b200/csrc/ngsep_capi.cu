@@ -123,6 +123,7 @@ struct Ctx {
     DevBuf<int32_t> d_cov_first, d_cov_last; DevBuf<uint8_t> d_cov_unique; DevBuf<int2> d_cov_diff; DevBuf<unsigned char> d_cov_tmp;   // ngsep_coverage_histogram
     DevBuf<unsigned long long> d_cov_hist;
     DevBuf<uint2> d_allele_out;   // ngsep_tile_allele_counts
+    DevBuf<unsigned char> d_ev_in; DevBuf<unsigned char> d_ev_out;   // ngsep_indel_tallies: inputs / outputs + scratch, each one allocation
     DevBuf<uint2> d_ent;     // resolved entries of the open columns (a full list only costs speed: such columns go out as record ranges)
     size_t q_min_cols = 0;   // learned from overflows
     int b_windows = 0, b_grid = 0;
@@ -885,6 +886,76 @@ int ngsep_coverage_histogram(void* ctx, int32_t tile_first, int32_t tile_last, i
     CK(cudaMemcpyAsync(h.data(), c->d_cov_hist.p, 2 * bins * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), "coverage copy");
     CK(cudaStreamSynchronize(c->stream), "coverage sync");
     for (size_t k = 0; k < bins; k++) { hist_all[k] = h[k]; hist_unique[k] = h[bins + k]; }
+    return NGSEP_OK;
+}
+
+// ---- indel / STR allele tallies of the span > 1 events (k_indel_tallies) ------------------------------------------------------------
+int ngsep_indel_tallies(void* ctx, const ngsep_indel_events* e, int32_t* total, int32_t* counts, int32_t* strand, double* diag, int32_t* call_index, double* call_fit) {
+    Ctx* c = (Ctx*)ctx;
+    if (!c) return NGSEP_EINVAL;
+    if (!e || e->n_events < 0 || e->n_alleles < 0 || e->n_calls < 0) return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: bad arguments");
+    if (e->n_events == 0) return NGSEP_OK;
+    if (!total || !counts || !strand || !diag || !e->allele_first || !e->call_first || !e->allele_off || !e->call_off || !e->allele_chars ||
+        (e->n_calls > 0 && (!e->call_chars || !e->call_quals || !e->call_neg || !call_index || !call_fit)))
+        return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: null argument");
+    // the layout is checked on the host: monotone offsets that cover the arrays, at least the reference allele per event
+    if (e->allele_first[0] != 0 || e->call_first[0] != 0 || e->allele_first[e->n_events] != e->n_alleles || e->call_first[e->n_events] != e->n_calls)
+        return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: event offsets do not cover the alleles / calls");
+    for (int k = 0; k < e->n_events; k++)
+        if (e->allele_first[k + 1] <= e->allele_first[k] || e->call_first[k + 1] < e->call_first[k]) return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: bad event");
+    if (e->allele_off[0] != 0 || e->call_off[0] != 0) return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: offsets must start at 0");
+    for (int a = 0; a < e->n_alleles; a++) if (e->allele_off[a + 1] < e->allele_off[a]) return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: allele offsets are not monotone");
+    for (int k = 0; k < e->n_calls; k++) if (e->call_off[k + 1] < e->call_off[k]) return fail(c, NGSEP_EINVAL, "ngsep_indel_tallies: call offsets are not monotone");
+    CK(cudaSetDevice(c->device), "set device");
+    const size_t n_ev = (size_t)e->n_events, n_al = (size_t)e->n_alleles, n_ca = (size_t)e->n_calls;
+    const size_t n_achars = (size_t)e->allele_off[n_al], n_cchars = (size_t)e->call_off[n_ca];
+    auto up = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    size_t o = 0;   // one input allocation: offsets and strings
+    const size_t o_af = o; o += up((n_ev + 1) * 4);
+    const size_t o_cf = o; o += up((n_ev + 1) * 4);
+    const size_t o_ao = o; o += up((n_al + 1) * 4);
+    const size_t o_co = o; o += up((n_ca + 1) * 4);
+    const size_t o_ac = o; o += up(n_achars + 1);
+    const size_t o_cc = o; o += up(n_cchars + 1);
+    const size_t o_cq = o; o += up(n_cchars + 1);
+    const size_t o_cn = o; o += up(n_ca + 1);
+    CK(c->d_ev_in.reserve(o), "indel event alloc");
+    std::vector<unsigned char> h(o, 0);
+    std::memcpy(h.data() + o_af, e->allele_first, (n_ev + 1) * 4);
+    std::memcpy(h.data() + o_cf, e->call_first, (n_ev + 1) * 4);
+    std::memcpy(h.data() + o_ao, e->allele_off, (n_al + 1) * 4);
+    std::memcpy(h.data() + o_co, e->call_off, (n_ca + 1) * 4);
+    std::memcpy(h.data() + o_ac, e->allele_chars, n_achars);
+    if (n_cchars) { std::memcpy(h.data() + o_cc, e->call_chars, n_cchars); std::memcpy(h.data() + o_cq, e->call_quals, n_cchars); }
+    if (n_ca) std::memcpy(h.data() + o_cn, e->call_neg, n_ca);
+    CK(cudaMemcpyAsync(c->d_ev_in.p, h.data(), o, cudaMemcpyHostToDevice, c->stream), "indel event copy");
+    size_t q = 0;   // one output allocation: totals, counts, strand counts, diagonals, per-call results + the kernel's scratch
+    const size_t q_t = q; q += up(n_ev * 4);
+    const size_t q_c = q; q += up(n_al * 4);
+    const size_t q_s = q; q += up(2 * n_al * 4);
+    const size_t q_d = q; q += up(n_al * 8);
+    const size_t q_i = q; q += up(n_ca * 4);
+    const size_t q_f = q; q += up(n_ca * 8);
+    const size_t q_out = q;
+    const size_t q_lc = q; q += up(n_al * 8);
+    CK(c->d_ev_out.reserve(q), "indel tally alloc");
+    IndelEventsDev d;
+    unsigned char* base = c->d_ev_in.p;
+    d.n_events = e->n_events; d.max_qs = c->params.max_base_qs;
+    d.allele_first = (const int*)(base + o_af); d.call_first = (const int*)(base + o_cf); d.allele_off = (const int*)(base + o_ao); d.call_off = (const int*)(base + o_co);
+    d.allele_chars = (const char*)(base + o_ac); d.call_chars = (const char*)(base + o_cc); d.call_quals = base + o_cq; d.call_neg = base + o_cn;
+    d.log_err = e->log_err;
+    unsigned char* ob = c->d_ev_out.p;
+    launch_indel_tallies(d, c->d_prm, (int*)(ob + q_t), (int*)(ob + q_c), (int*)(ob + q_s), (double*)(ob + q_d), (int*)(ob + q_i), (double*)(ob + q_f), (double*)(ob + q_lc), c->stream);
+    CK(cudaGetLastError(), "indel tally launch");
+    std::vector<unsigned char> r(q_out);
+    CK(cudaMemcpyAsync(r.data(), ob, q_out, cudaMemcpyDeviceToHost, c->stream), "indel tally copy");
+    CK(cudaStreamSynchronize(c->stream), "indel tallies");
+    std::memcpy(total, r.data() + q_t, n_ev * 4);
+    std::memcpy(counts, r.data() + q_c, n_al * 4);
+    std::memcpy(strand, r.data() + q_s, 2 * n_al * 4);
+    std::memcpy(diag, r.data() + q_d, n_al * 8);
+    if (n_ca) { std::memcpy(call_index, r.data() + q_i, n_ca * 4); std::memcpy(call_fit, r.data() + q_f, n_ca * 8); }
     return NGSEP_OK;
 }
 

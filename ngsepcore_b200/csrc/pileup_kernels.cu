@@ -1540,6 +1540,62 @@ __global__ void __launch_bounds__(256) k_allele_counts(const TileDev* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Indel / STR allele tallies of the span > 1 events: one event per thread
+// ------------------------------------------------------------------------------------------------------------
+// The per-call part of CountsHelper.updateCountsIndel (CH:253-304), call by call in pileup order: calculateLogCond (CH:384-396) of
+// the call against every allele of its length, the allele the call counts for (an exact match, else the best-fitting one), the
+// allele and strand counts, the diagonal of logConditionalProbs.  Every value is a sum of host-supplied table entries in the
+// reference's order, so the outputs are bit-identical to the Java doubles; what depends on libm (the mixture terms of the
+// off-diagonal entries, the posteriors) is finished by the host from call_index / call_fit.  Events are a few per ten thousand
+// positions and a few dozen calls each: the point is that these tallies are made where the SNV tallies are made, not speed.
+__global__ void __launch_bounds__(128) k_indel_tallies(const IndelEventsDev ev, const DevParams* __restrict__ gprm, int* __restrict__ total, int* __restrict__ counts,
+                                                       int* __restrict__ strand, double* __restrict__ diag, int* __restrict__ call_index, double* __restrict__ call_fit,
+                                                       double* __restrict__ lc_scratch) {
+    const int k = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k >= ev.n_events) return;
+    const double* tab = gprm->tables;   // tables[3 q] = log10(1 - e_q) (a match), tables[3 q + 1] = log10(e_q / 3) (a mismatch)
+    const int a0 = ev.allele_first[k], n = ev.allele_first[k + 1] - a0;
+    const int c0 = ev.call_first[k], c1 = ev.call_first[k + 1];
+    double* lc = lc_scratch + a0;
+    double* dg = diag + a0;
+    int* cnt = counts + a0;
+    int* snd = strand + 2 * a0;
+    const double lerr = ev.log_err;
+    for (int i = 0; i < n; i++) { cnt[i] = 0; snd[2 * i] = 0; snd[2 * i + 1] = 0; dg[i] = 0.0; }
+    for (int c = c0; c < c1; c++) {
+        const int co = ev.call_off[c], clen = ev.call_off[c + 1] - co;
+        const char* cs = ev.call_chars + co;
+        const unsigned char* cq = ev.call_quals + co;
+        int index = -1, best = -1;
+        for (int i = 0; i < n; i++) {
+            const int ao = ev.allele_off[a0 + i], alen = ev.allele_off[a0 + i + 1] - ao;
+            const char* as = ev.allele_chars + ao;
+            lc[i] = lerr;
+            if (alen != clen) continue;
+            bool same = true;
+            double v = 0.0;
+            for (int b = 0; b < alen; b++) {
+                const bool eq = as[b] == cs[b];
+                same = same && eq;
+                const int q = (int)(signed char)min(ev.max_qs, (int)cq[b] - 33);
+                if (q < 3) continue;
+                v += eq ? tab[3 * q] : tab[3 * q + 1];
+            }
+            if (same && index < 0) index = i;
+            lc[i] = fmax(lerr, v);
+            if (lc[i] > lerr && (best == -1 || lc[best] < lc[i])) best = i;
+        }
+        if (index >= 0 && best >= 0 && best != index) index = min(index, best);
+        else if (index < 0 && best >= 0) index = best;
+        if (index >= 0) { cnt[index]++; snd[2 * index + (ev.call_neg[c] ? 0 : 1)]++; }
+        for (int i = 0; i < n; i++) dg[i] += lc[i];
+        call_index[c] = index;
+        call_fit[c] = (index >= 0) ? lc[index] : lerr;
+    }
+    total[k] = c1 - c0;
+}
+
 // First entry of read-group list g that is >= want.  gblk[g][b] = the answer for want = b * kGroupBlock (built at
 // staging), so the search only looks at the few list entries that fall into one block of record indexes.
 constexpr int kGroupBlockShift = 8, kGroupBlock = 1 << kGroupBlockShift;
@@ -1980,6 +2036,12 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s) {
     const int grid = max(1, min(max_grid, (n_sites + 7) / 8));   // one warp per site
     k_genotype_sites<<<grid, 256, 0, s>>>(d_tile, dprm);
+}
+
+void launch_indel_tallies(const IndelEventsDev& ev, const DevParams* dprm, int* total, int* counts, int* strand, double* diag, int* call_index, double* call_fit,
+                          double* lc_scratch, cudaStream_t s) {
+    if (ev.n_events <= 0) return;
+    k_indel_tallies<<<(ev.n_events + 127) / 128, 128, 0, s>>>(ev, dprm, total, counts, strand, diag, call_index, call_fit, lc_scratch);
 }
 
 void launch_allele_counts(const TileDev* d_tile, int n_pos, int min_rd, int min_bq, uint2* out, int max_grid, cudaStream_t s) {

@@ -111,6 +111,15 @@ void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s);
+// indel / STR allele tallies (k_indel_tallies): device view of ngsep_indel_events
+struct IndelEventsDev {
+    int n_events, max_qs;
+    const int* allele_first; const int* call_first; const int* allele_off; const int* call_off;
+    const char* allele_chars; const char* call_chars; const unsigned char* call_quals; const unsigned char* call_neg;
+    double log_err;
+};
+void launch_indel_tallies(const IndelEventsDev& ev, const DevParams* dprm, int* total, int* counts, int* strand, double* diag, int* call_index, double* call_fit,
+                          double* lc_scratch, cudaStream_t s);
 void launch_allele_counts(const TileDev* d_tile, int n_pos, int min_rd, int min_bq, uint2* out, int max_grid, cudaStream_t s);
 void launch_genotype_multi(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int n_samples, int grid, cudaStream_t s);
 int genotype_multi_ctas_per_sm(int n_samples);
