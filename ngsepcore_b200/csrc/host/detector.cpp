@@ -127,7 +127,9 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     std::vector<size_t> order(jobs.size());
     for (size_t k = 0; k < order.size(); k++) order[k] = k;
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].hi - jobs[x].lo > jobs[y].hi - jobs[y].lo; });
-    // ---- stages 1-2: admission + event pre-pass, every sequence on its own host thread ------------------------------------
+    // ---- stages 1-2: admission + event pre-pass, every sequence on its own host thread (a run with fewer sequences than threads
+    // also splits the work inside a sequence) -----------------------------------------------------------------------------------
+    inner_threads_ = (jobs.empty() || (int)jobs.size() >= threads) ? 1 : std::max(1, threads / (int)jobs.size());
     double tp = now_s();
     parallel_jobs(jobs.size(), threads, order, [&](size_t k) { jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan); });
     stats_.prepass_s += now_s() - tp;
@@ -290,7 +292,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         while (q_hi > q_lo && b.first[q_hi - 1] > opt_.query_last) q_hi--;
     }
     if (opt_.has_query) ao.query_first = opt_.query_first;
-    reads = admit_sequence(b, q_lo, q_hi, ao);
+    reads = admit_sequence(b, q_lo, q_hi, ao, inner_threads_);
     for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { plan.err = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
     plan.stats.admitted += reads.size();
     if (reads.empty()) { plan.win_first = 1; plan.win_last = seq_len; return NGSEP_OK; }

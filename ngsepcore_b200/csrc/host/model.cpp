@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <thread>
 #include <unordered_map>
 
 namespace ngsep_b200 {
@@ -242,7 +243,43 @@ void HostRead::realign_end(int ref_before, int read_before, int final_ref_start,
 // ------------------------------------------------------------------------------------------------------------
 // admission
 // ------------------------------------------------------------------------------------------------------------
-std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt) {
+namespace {
+std::vector<HostRead> admit_range(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt);
+}
+
+// Everything admission does is local to the records of one start position — the duplicate-record rule compares equal starts
+// (RAFR:292-306), the cap counts the alignments of one start (APG:407-433) — so a sequence cut where the start changes is
+// admitted piece by piece, on `threads` host threads, with the pieces' reads concatenated in order.
+std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt, int threads) {
+    const int64_t n = hi - lo;
+    if (threads < 4 || n < 200000) return admit_range(b, lo, hi, opt);   // (two threads lose to one: the pieces' reads are moved once more)
+    const int nt = (int)std::min<int64_t>(threads, n / 50000);
+    std::vector<int64_t> cut((size_t)nt + 1);
+    cut[0] = lo; cut[(size_t)nt] = hi;
+    for (int t = 1; t < nt; t++) {
+        int64_t c = std::max(cut[(size_t)t - 1], lo + n * t / nt);
+        while (c < hi && c > lo && b.first[c] == b.first[c - 1]) c++;   // never inside the records of one start position
+        cut[(size_t)t] = c;
+    }
+    std::vector<std::vector<HostRead>> parts((size_t)nt);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back([&, t]() { parts[(size_t)t] = admit_range(b, cut[(size_t)t], cut[(size_t)t + 1], opt); });
+    parts[0] = admit_range(b, cut[0], cut[1], opt);
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    std::vector<size_t> base((size_t)nt);
+    for (int t = 0; t < nt; t++) { base[(size_t)t] = total; total += parts[(size_t)t].size(); }
+    std::vector<HostRead> out(total);
+    th.clear();
+    auto place = [&](int t) { std::move(parts[(size_t)t].begin(), parts[(size_t)t].end(), out.begin() + (ptrdiff_t)base[(size_t)t]); std::vector<HostRead>().swap(parts[(size_t)t]); };
+    for (int t = 1; t < nt; t++) th.emplace_back(place, t);
+    place(0);
+    for (auto& x : th) x.join();
+    return out;
+}
+
+namespace {
+std::vector<HostRead> admit_range(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt) {
     std::vector<HostRead> out;
     out.reserve((size_t)(hi - lo));
     int filter = 0x4;
@@ -250,13 +287,14 @@ std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi,
     int64_t last_seen = -1;
     std::vector<HostRead> prim, sec;
     int group_start = INT_MIN;
-    std::unordered_map<int, int> per_rg;
+    std::vector<std::pair<int, int>> per_rg;   // (read group, alignments admitted at this start): a handful of groups, searched linearly
     auto flush = [&]() {
         per_rg.clear();
         for (auto* lst : {&prim, &sec}) {
             for (auto& r : *lst) {
-                auto it = per_rg.find(r.rg);
-                if (it == per_rg.end()) per_rg[r.rg] = 1;
+                auto it = per_rg.begin();
+                while (it != per_rg.end() && it->first != r.rg) ++it;
+                if (it == per_rg.end()) per_rg.emplace_back(r.rg, 1);
                 else if (opt.max_alns_per_start <= 0 || it->second < opt.max_alns_per_start) it->second++;
                 else continue;
                 // 5' end is the alignment start for + strand reads, the end for - strand reads (RA:613-644)
@@ -314,6 +352,7 @@ std::vector<HostRead> admit_sequence(const BatchView& b, int64_t lo, int64_t hi,
     flush();
     return out;
 }
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
 // several inputs: APG.processFiles

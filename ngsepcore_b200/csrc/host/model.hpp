@@ -102,7 +102,7 @@ struct AdmissionOptions {
 
 // Applies the record filter of RAFR:219-354 (flag set from APG:363-375), the duplicate-record rule and the per-read-
 // group same-start cap of APG:407-433 to the records of one sequence; returns the admitted reads in pileup order.
-std::vector<HostRead> admit_sequence(const BatchView& b, int64_t rec_lo, int64_t rec_hi, const AdmissionOptions& opt);
+std::vector<HostRead> admit_sequence(const BatchView& b, int64_t rec_lo, int64_t rec_hi, const AdmissionOptions& opt, int threads = 1);
 
 // AlignmentsPileupGenerator.processFiles / chooseNextAln (APG:212-289): the order in which the records of several
 // coordinate-sorted inputs are consumed.  Each input is first reduced to the records its own reader hands over (RAFR:219-354

@@ -283,6 +283,7 @@ protected:
     bool strs_loaded_ = false;
     std::vector<std::vector<KnownVariant>> known_;   // -knownVariants: per sequence
     bool known_loaded_ = false;
+    int inner_threads_ = 1;                          // host threads one sequence may use for its own stages (set per run)
     bool known_mode() const { return known_loaded_ && n_known_ > 0; }   // SSVPL:147: an empty input list means discovery
     size_t n_known_ = 0;
     void emit_known_text(SeqJob& job);

@@ -280,3 +280,25 @@ def test_known_variants_loader_and_empty_list(oracle, tmp_path):
     bad.set_genome(genome)
     with pytest.raises(Exception):
         bad.run(batch)
+
+
+def test_admission_inside_one_sequence_on_several_threads(oracle, tmp_path, monkeypatch):
+    """A run with fewer sequences than host threads admits a long sequence piece by piece (cut where the start position changes:
+    the duplicate-record rule and the per-start cap never look across such a cut).  Same host-made records on one thread, on
+    eight, and from the oracle; with a cap of one alignment per start, thousands of start groups lose reads."""
+    contigs = [("chrL", 700000)]
+    genome, batch, _ = simulate.simulate(contigs=contigs, seeds=(91, 92, 93), depth=32, indel_rate=1e-3)
+    assert batch.n > 200000
+    fa, sam = str(tmp_path / "r.fa"), str(tmp_path / "r.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-maxAlnsPerStartPos", "1"))
+    want_lines = [l for l in want.splitlines() if "TYPE=INDEL" in l or "TYPE=STR" in l]
+    outs = []
+    for n in ("1", "8"):
+        monkeypatch.setenv("NGSEP_HOST_THREADS", n)
+        det = hostapi.Detector(host_only=True, maxAlnsPerStartPos=1)
+        det.set_genome(genome)
+        outs.append([l for l in det.run(batch).splitlines() if not l.startswith("#")])
+        assert det.stats().admitted < batch.n
+    assert outs[0] == outs[1] == want_lines and len(want_lines) > 300
