@@ -56,6 +56,7 @@ struct Slot {
     DevBuf<uint2> d_ent;                      //                       ... and the resolved entries of its open columns
     DevBuf<uint16_t> d_group;                 // multi-sample contexts: read-group id per record
     DevBuf<uint32_t> d_gidx, d_goff, d_gblk;          //                        records indexed by read group (launch_group_index)
+    DevBuf<ngsep_read_hdr> d_mhdr; DevBuf<uint8_t> d_ev;   //                     headers with quality offsets + evidence bytes (launch_build_evidence)
     DevBuf<ngsep_pop_site> d_sites;           //                        population sites (cap = tile.cap_calls) ...
     DevBuf<ngsep_sample_call> d_scalls;       //                        ... x n_samples sample calls
     DevBuf<int32_t> d_counts;
@@ -81,6 +82,7 @@ struct Slot {
         d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
         d_site_pos.release(); d_site_alleles.release();
         d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release(); d_ent.release();
+        d_mhdr.release(); d_ev.release();
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
@@ -390,6 +392,8 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
             CK(c->d_cub.reserve(cub_bytes + 256), "sort scratch alloc");
         }
         CK(s->d_gidx.reserve(n + 16), "group index alloc");
+        CK(s->d_mhdr.reserve(n + 16), "evidence header alloc");
+        CK(s->d_ev.reserve((size_t)t->n_qual * (8u / qual_bits) + 64), "evidence alloc");
         CK(s->d_goff.reserve((size_t)c->hp.n_groups + 4), "group offsets alloc");
         CK(s->d_gblk.reserve(((size_t)c->hp.n_groups + 1) * ((size_t)group_blocks(t->n_reads) + 1) + 16), "group block table alloc");
         CK(launch_group_index(s->d_group.p, c->d_gins.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
@@ -419,6 +423,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     std::memcpy(d.qual_dict, t->qual_dict, 16);
     d.gidx = multi ? s->d_gidx.p : nullptr; d.goff = multi ? s->d_goff.p : nullptr;
     d.gblk = multi ? s->d_gblk.p : nullptr; d.n_gblk = multi ? group_blocks(t->n_reads) : 0;
+    d.mhdr = multi ? s->d_mhdr.p : nullptr; d.ev = multi ? s->d_ev.p : nullptr; d.ev_mul = 32u / qual_bits;
     d.n_reads = t->n_reads; d.max_span = span; d.max_back = t->max_back < 0 ? 0 : t->max_back;
     d.tile_first = t->tile_first; d.tile_last = t->tile_last; d.seq_idx = t->seq_idx;
     d.ref2 = ref.ref2; d.ref_n = ref.ref_n; d.ref_l = ref.ref_l; d.ref_len = ref.len;
@@ -465,6 +470,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     s->grid = std::min(d.n_windows, c->sm_count * c->ctas_per_sm);   // persistent CTAs
     s->pin->tile = s->tile;
     CK(cudaMemcpyAsync(s->d_tile, &s->pin->tile, sizeof(TileDev), cudaMemcpyHostToDevice, c->stream), "tile descriptor copy");
+    if (multi) launch_build_evidence(d, s->d_mhdr.p, s->d_ev.p, c->params.max_base_qs, c->stream);   // (after the staging check: it trusts the offsets)
     launch_window_index(d, s->d_win.p, 0, c->stream);   // depends on the staged records only: built once per staging
     CK(cudaGetLastError(), "window index launch");
     s->staged = true;

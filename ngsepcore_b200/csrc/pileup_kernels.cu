@@ -1596,6 +1596,45 @@ __global__ void __launch_bounds__(128) k_indel_tallies(const IndelEventsDev ev, 
     total[k] = c1 - c0;
 }
 
+// Multi-sample staging: the evidence bytes of every SIMPLE record and the headers with their quality offsets (TileDev.mhdr / ev).
+// A column of the sample axis evaluates every covering record once per column — 960 records x 100 columns for a GBS tag —, so what
+// one evaluation touches is what the kernel's L2 traffic is made of: header + evidence byte = two 32-byte sectors instead of header +
+// base word + qoff word + quality byte.
+__global__ void k_build_evidence(const TileDev d, ngsep_read_hdr* __restrict__ mhdr, uint8_t* __restrict__ ev, int max_qs) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= d.n_reads) return;
+    if (d.report && d.report[0]) return;   // the tile failed its staging check: nothing of it is walked
+    const ngsep_read_hdr h = d.hdr[i];
+    const uint32_t* pay = d.payload + h.off;
+    ngsep_read_hdr m = h;
+    if (h.meta & NGSEP_M_SIMPLE) {
+        const int L = (int)(h.meta & 0xffffu);
+        const uint32_t* b2 = pay + 1;
+        const uint32_t qoff = b2[((L + 15) >> 4) + ((L + 31) >> 5)];
+        m.off = qoff;
+        const QualView qual(d);
+        uint32_t* out = (uint32_t*)(ev + (size_t)qoff * d.ev_mul);   // ev_mul is a multiple of 4: word stores
+        for (int k0 = 0; k0 < L; k0 += 4) {
+            uint32_t w = 0u;
+            for (int k = k0; k < min(L, k0 + 4); k++) {
+                int q = (int)qual.at(qoff, (uint32_t)k) - 33;
+                q = min(30, q);                                     // CH:91
+                uint32_t e = 0u;                                    // CH:214-216: a call that is not counted
+                if (q > 3) { if (q > max_qs) q = max_qs; e = 0x80u | ((uint32_t)q << 2) | ((b2[k >> 4] >> ((k & 15) * 2)) & 3u); }   // CH:217-219
+                w |= e << (8 * (k - k0));
+            }
+            out[k0 >> 2] = w;
+        }
+    } else {
+        m.off = view_record(h, pay).qoff;
+    }
+    mhdr[i] = m;
+}
+
+void launch_build_evidence(const TileDev& d, ngsep_read_hdr* mhdr, uint8_t* ev, int max_qs, cudaStream_t s) {
+    if (d.n_reads > 0) k_build_evidence<<<(d.n_reads + 127) / 128, 128, 0, s>>>(d, mhdr, ev, max_qs);
+}
+
 // First entry of read-group list g that is >= want.  gblk[g][b] = the answer for want = b * kGroupBlock (built at
 // staging), so the search only looks at the few list entries that fall into one block of record indexes.
 constexpr int kGroupBlockShift = 8, kGroupBlock = 1 << kGroupBlockShift;
@@ -1683,8 +1722,20 @@ __global__ void __launch_bounds__(kThr, 1024 / kThr) k_genotype_columns_multi(co
                     for (int u = 0; u < kInFlight; u++) {
                         code[u] = 0u;
                         if (ka + u < kb) {
-                            const ngsep_read_hdr h = R.header((int)__ldg(lst + ka + u));
-                            code[u] = lane_eval(h, R.payload(h), qv, pos, max_qs);
+                            const int idx = (int)__ldg(lst + ka + u);
+                            const int4 mh = __ldg((const int4*)(d.mhdr + idx));   // first | meta | ign_start, ign_end | qoff
+                            if ((uint32_t)mh.y & NGSEP_M_SIMPLE) {
+                                // one match block as long as the read (RA:842-871 needs no payload): the header and ONE evidence byte
+                                const int L = (int)((uint32_t)mh.y & 0xffffu), off = pos - mh.x;
+                                const int ign_s = (int)(int16_t)(mh.z & 0xffff), ign_e = (int)(int16_t)((uint32_t)mh.z >> 16);
+                                if (off >= 0 && off < L && off >= ign_s && (L - off) > ign_e) {                  // RA:782-784
+                                    const uint32_t e = __ldg(d.ev + (size_t)(uint32_t)mh.w * d.ev_mul + (size_t)off);
+                                    code[u] = kCodeCall | ((e & 0x80u) ? (kCodeCounted | (e & 0x7fu)) : 0u) | (((uint32_t)mh.y & NGSEP_M_NEG) ? kCodeNeg : 0u);
+                                }
+                            } else {
+                                const ngsep_read_hdr h = R.header(idx);
+                                code[u] = lane_eval(h, R.payload(h), qv, pos, max_qs);
+                            }
                         }
                     }
 #pragma unroll

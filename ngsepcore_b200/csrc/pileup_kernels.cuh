@@ -45,6 +45,10 @@ struct TileDev {
     const uint32_t* goff;        //                        [n_groups + 2] list offsets into gidx; list n_groups = records outside every sample
     const uint32_t* gblk;        //                        [n_groups + 1][n_gblk + 1] list position of the first record index >= b * 256
     int n_gblk;
+    // multi-sample contexts: what a (record, column) evaluation needs of a SIMPLE record in two sectors instead of four (k_build_evidence):
+    // mhdr = the record headers with `off` replaced by the record's qoff; ev[qoff * ev_mul + k] = the evidence of read base k
+    // (0: a call that is not counted; else 0x80 | quality << 2 | base, the quality rules of CH:91, 214-219 already applied)
+    const ngsep_read_hdr* mhdr; const uint8_t* ev; uint32_t ev_mul;
     const uint8_t* qual;         // phred+33 bytes (or qual_bits-bit codes into qual_dict), addressed through the records' qoff (only the genotype kernels read them)
     uint32_t qual_bits;          // 8 = bytes, 2 / 4 = codes
     uint32_t qual_dict[4];       // code -> phred+33 byte, four codes per word
@@ -126,6 +130,7 @@ int genotype_multi_ctas_per_sm(int n_samples);
 size_t group_index_temp_bytes(int n);
 cudaError_t launch_group_index(const uint16_t* group, const uint8_t* in_sample /* [n_groups]: the read group belongs to a sample */, int n, int n_groups, uint16_t* keys_tmp, uint32_t* vals_tmp, void* cub_tmp, size_t cub_bytes,
                                uint32_t* gidx, uint32_t* goff, uint32_t* gblk, cudaStream_t s);
+void launch_build_evidence(const TileDev& d, ngsep_read_hdr* mhdr, uint8_t* ev, int max_qs, cudaStream_t s);
 int group_blocks(int n);   // blocks of record indexes in the per-group block table
 void launch_ref_pack(const char* ascii, int64_t len, uint32_t* ref2, uint32_t* ref_n, uint32_t* ref_l, cudaStream_t s);
 
