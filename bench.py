@@ -201,7 +201,7 @@ def run_gpu(args):
     slots = []
     for ci, t in enumerate(tiles):
         if t["hdr"].size:
-            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"]))
+            slots.append(ctx.resident_add(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=t["layout"]))
 
     def barrier():
         if dist is not None:
@@ -238,7 +238,7 @@ def run_gpu(args):
             if pending == IN_FLIGHT:
                 c, _, st = ctx.fetch(sort=False)
                 n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
-            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"])
+            ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=t["layout"])
             pending += 1
         while pending:
             c, _, st = ctx.fetch(sort=False)

@@ -115,6 +115,9 @@ int ngsep_relative_allele_counts(int n_seqs, const char* const* names, const int
                                  int min_base_qs, int secondary, int device, char** text);
 /* How the quality array of the tile the calling thread packed last (ngsep_host_pack / ngsep_ssvd_pack) is coded: the values for
  * ngsep_tile.qual_bits and ngsep_tile.qual_dict. */
+/* ... and how its payload is laid out: the values for ngsep_tile.layout and ngsep_tile.n_words (the detector packs NGSEP_LAYOUT_COMPACT tiles —
+ * ngsep_ssvd_pack returns the compact stream, its length is the n_words it reports = ngsep_tile.n_wire_words —, ngsep_host_pack the full layout). */
+int ngsep_host_pack_layout(uint32_t* layout, uint64_t* n_words_full);
 int ngsep_host_pack_quality(uint32_t* qual_bits, uint8_t* qual_dict16);
 
 #ifdef __cplusplus

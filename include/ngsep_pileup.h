@@ -113,8 +113,17 @@ typedef struct ngsep_tile {
                                       alike (CountsHelper.java:91,214-219), so a tile whose qualities fall into at most 4 / 16 such
                                       classes (binned Illumina qualities do) travels at 2 / 4 bits per base with identical results */
     uint8_t qual_dict[16];
-    uint32_t reserved;
+    uint32_t layout;               /* NGSEP_LAYOUT_*: how `payload` is laid out on the caller's side                              */
+    uint64_t n_wire_words;         /* NGSEP_LAYOUT_COMPACT: words in `payload` (n_words stays the length of the full layout)     */
 } ngsep_tile;
+
+#define NGSEP_LAYOUT_FULL 0u       /* payload as described above: n_words words                                                */
+#define NGSEP_LAYOUT_COMPACT 1u    /* what need not cross the bus does not: the payload of a record flagged NGSEP_M_SIMPLE is
+                                      [bases2, qoff] only — its CIGAR word (len*8+3) and its low-quality mask (a function of the
+                                      qualities) are rebuilt on the device —, every other record's payload is unchanged; hdr.off are
+                                      offsets into this stream (n_wire_words words).  The device expands the stream to the full layout at
+                                      staging (one scan + one pass), so everything behind the copy is the same.  20 of the 96 bytes of a
+                                      100-bp read with 2-bit quality codes stay on the host.                                      */
 
 /* One SNV-path decision for one position.  Field semantics follow VariantDiscoverySNVQAlgorithm.discoverSNV
  * (VD:100-222) and the filter of SingleSampleVariantPileupListener.discoverVariant (SSVPL:223). */
@@ -320,7 +329,7 @@ int ngsep_host_register(void* ptr, size_t bytes);
 int ngsep_host_unregister(void* ptr);
 
 /* Library/ABI version (major*1000+minor) and the compute capability the kernels were built for. */
-int ngsep_abi_version(void);   /* 2003: + ngsep_tile_sites (known sites); 2002: + ngsep_tile.qual_bits / qual_dict; 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
+int ngsep_abi_version(void);   /* 2004: + ngsep_tile.layout / n_wire_words (compact wire layout), ngsep_indel_tallies, ngsep_tile_allele_counts; 2003: + ngsep_tile_sites (known sites); 2002: + ngsep_tile.qual_bits / qual_dict; 2001: + sample axis (ngsep_samples_set, ngsep_tile_fetch_pop); 2000: quality bytes in their own array */
 int ngsep_built_sm(void);
 
 #ifdef __cplusplus

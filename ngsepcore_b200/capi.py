@@ -32,7 +32,7 @@ class Tile(C.Structure):
     _fields_ = [("seq_idx", C.c_int32), ("tile_first", C.c_int32), ("tile_last", C.c_int32), ("n_reads", C.c_int32),
                 ("max_span", C.c_int32), ("max_back", C.c_int32), ("n_words", C.c_uint64), ("hdr", C.c_void_p),
                 ("payload", C.c_void_p), ("group", C.c_void_p), ("qual", C.c_void_p), ("n_qual", C.c_uint64),
-                ("qual_bits", C.c_uint32), ("qual_dict", C.c_uint8 * 16), ("reserved", C.c_uint32)]
+                ("qual_bits", C.c_uint32), ("qual_dict", C.c_uint8 * 16), ("layout", C.c_uint32), ("n_wire_words", C.c_uint64)]
 
 
 class SynthParams(C.Structure):
@@ -164,18 +164,20 @@ class Context:
         b = np.ascontiguousarray(bases, np.uint8)
         self._check(self.lib.ngsep_ref_upload(self.h, seq_idx, b.ctypes.data, b.size), "ngsep_ref_upload")
 
-    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group=None, quality=None) -> Tile:
-        """quality: None = `qual` holds phred+33 bytes; (bits, dict16) = 2- / 4-bit codes (ngsep_tile.qual_bits / qual_dict)."""
+    def _tile(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group=None, quality=None, layout=None) -> Tile:
+        """quality: None = `qual` holds phred+33 bytes; (bits, dict16) = 2- / 4-bit codes (ngsep_tile.qual_bits / qual_dict).
+        layout: None = `payload` is the full layout; (1, n_words_full) = the compact wire stream (ngsep_tile.layout / n_words)."""
         hdr = np.ascontiguousarray(hdr, HDR_DTYPE)
         payload = np.ascontiguousarray(payload, np.uint32)
         qual = np.ascontiguousarray(qual, np.uint8)
         group = None if group is None else np.ascontiguousarray(group, np.uint16)
         self._keep = (getattr(self, "_keep", []) + [hdr, payload, qual, group])[-16:]   # buffers of the tiles still in flight
         bits, qdict = (0, bytes(16)) if quality is None else (int(quality[0]), bytes(quality[1]))
-        return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, payload.size,
+        lay, n_full = (0, payload.size) if layout is None or not layout[0] else (int(layout[0]), int(layout[1]))
+        return Tile(seq_idx, tile_first, tile_last, hdr.shape[0], max_span, max_back, n_full,
                     hdr.ctypes.data if hdr.size else None, payload.ctypes.data if payload.size else None,
                     group.ctypes.data if group is not None and group.size else None,
-                    qual.ctypes.data if qual.size else None, qual.size, bits, (C.c_uint8 * 16)(*qdict), 0)
+                    qual.ctypes.data if qual.size else None, qual.size, bits, (C.c_uint8 * 16)(*qdict), lay, payload.size)
 
     def samples_set(self, sample_groups, n_groups: int, min_allele_depth_freq: float = 0.0) -> None:
         """sample_groups: per sample, the read-group ids in the order PR.getAlleleCalls(span, Set) visits them."""
@@ -215,14 +217,14 @@ class Context:
         codes = np.ascontiguousarray([sum(b << (2 * k) for k, b in enumerate(a)) | (len(a) << 8) for a in alleles], np.uint16)
         self._check(self.lib.ngsep_tile_sites(self.h, len(pos), pos.ctypes.data, codes.ctypes.data), "ngsep_tile_sites")
 
-    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None) -> None:
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality)
+    def submit(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None, layout=None) -> None:
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality, layout)
         self._check(self.lib.ngsep_tile_submit(self.h, C.byref(t)), "ngsep_tile_submit")
         self._inflight_npos.append(tile_last - tile_first + 1)
 
-    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None) -> int:
+    def resident_add(self, seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back=0, group=None, quality=None, layout=None) -> int:
         """Stages a tile in HBM for repeated runs; returns its slot."""
-        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality)
+        t = self._tile(seq_idx, tile_first, tile_last, hdr, payload, qual, max_span, max_back, group, quality, layout)
         slot = C.c_int(0)
         self._check(self.lib.ngsep_resident_add(self.h, C.byref(t), C.byref(slot)), "ngsep_resident_add")
         self._slot_npos[slot.value] = tile_last - tile_first + 1

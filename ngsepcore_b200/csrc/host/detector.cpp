@@ -238,7 +238,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             PackedTile& tile = rings_[dev][(size_t)slot[dev]];
             tile.set_pinned(!opt_.synchronous);
             double tp = now_s();
-            if (!pack_reads(plan.reads, r_lo, r_hi, tile, with_groups(), &err_)) { drain(); return NGSEP_EINVAL; }
+            if (!pack_reads(plan.reads, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact())) { drain(); return NGSEP_EINVAL; }
             stats_.pack_s += now_s() - tp;
             if (tile.hdr.empty()) continue;
             double td = now_s();
@@ -616,7 +616,7 @@ int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, 
     SeqPlan plan;
     int rc = plan_sequence(b, seq, lo, hi, plan);
     if (rc != NGSEP_OK) { err_ = plan.err; return rc; }
-    if (!pack_reads(plan.reads, 0, plan.reads.size(), tile, false, &err_)) return NGSEP_EINVAL;
+    if (!pack_reads(plan.reads, 0, plan.reads.size(), tile, false, &err_, 0, wire_compact())) return NGSEP_EINVAL;
     tile_first = plan.win_first;
     tile_last = plan.win_last;
     return NGSEP_OK;

@@ -17,7 +17,12 @@ namespace {
 
 thread_local uint32_t g_last_qual_bits = 8;
 thread_local uint8_t g_last_qual_dict[16] = {0};
-void remember_quality(const PackedTile& t) { g_last_qual_bits = t.qual_bits; std::memcpy(g_last_qual_dict, t.qual_dict, 16); }
+thread_local uint32_t g_last_layout = 0;
+thread_local uint64_t g_last_words_full = 0;
+void remember_quality(const PackedTile& t) {
+    g_last_qual_bits = t.qual_bits; std::memcpy(g_last_qual_dict, t.qual_dict, 16);
+    g_last_layout = t.layout; g_last_words_full = t.layout == NGSEP_LAYOUT_COMPACT ? t.n_words_full : (uint64_t)t.payload.size();
+}
 
 struct Handle {
     DetectorOptions opt;
@@ -237,6 +242,13 @@ int ngsep_relative_allele_counts(int n_seqs, const char* const* names, const int
     *text = (char*)std::malloc(out.size() + 1);
     if (!*text) return NGSEP_ENOMEM;
     std::memcpy(*text, out.c_str(), out.size() + 1);
+    return NGSEP_OK;
+}
+
+int ngsep_host_pack_layout(uint32_t* layout, uint64_t* n_words_full) {
+    if (!layout || !n_words_full) return NGSEP_EINVAL;
+    *layout = g_last_layout;
+    *n_words_full = g_last_words_full;
     return NGSEP_OK;
 }
 

@@ -42,6 +42,11 @@ template struct HostBuf<uint32_t>;
 template struct HostBuf<uint16_t>;
 template struct HostBuf<uint8_t>;
 
+bool wire_compact() {
+    const char* e = std::getenv("NGSEP_WIRE_COMPACT");
+    return !(e && std::atoi(e) == 0);
+}
+
 int host_threads() {
     if (const char* e = std::getenv("NGSEP_HOST_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) return v; }
     unsigned hw = std::thread::hardware_concurrency();
@@ -131,6 +136,7 @@ struct Part {
     std::vector<uint32_t> payload;
     std::vector<uint8_t> qual;
     size_t n_hdr = 0, n_pay = 0, n_qual = 0;   // filled sizes (the vectors only grow)
+    size_t n_full = 0;                         // payload words of the records in the full layout (n_pay counts the compact stream when that is packed)
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
     bool bad = false;
@@ -162,7 +168,7 @@ void encode_read(const HostRead& r, ReadBits& o) {
     o.has_n = any_bad != 0;
 }
 
-inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out) {
+inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out, bool compact) {
     const int len = r.L;
     const int nc = (int)st.cigar.size();
     if (len > 0xffff || nc > 0xff) { out.bad = true; return false; }
@@ -175,11 +181,17 @@ inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& 
     h.off = (uint32_t)out.n_pay;
     out.hdr[out.n_hdr++] = h;
     uint32_t* p = out.payload.data() + out.n_pay;
-    if (windowed) { *p++ = (uint32_t)from; *p++ = (uint32_t)to; *p++ = (uint32_t)st.first; }
-    for (int k = 0; k < nc; k++) *p++ = st.cigar[(size_t)k];
-    std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
-    if (rb.has_n) { std::memcpy(p, rb.nm, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw; }
-    std::memcpy(p, rb.lq, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw;
+    out.n_full += (windowed ? 3u : 0u) + (size_t)nc + (size_t)rb.nb + (rb.has_n ? (size_t)rb.nw : 0u) + (size_t)rb.nw + 1u;
+    if (compact && (h.meta & NGSEP_M_SIMPLE)) {
+        // NGSEP_LAYOUT_COMPACT: the CIGAR word and the low-quality mask of a single-block record are rebuilt on the device
+        std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
+    } else {
+        if (windowed) { *p++ = (uint32_t)from; *p++ = (uint32_t)to; *p++ = (uint32_t)st.first; }
+        for (int k = 0; k < nc; k++) *p++ = st.cigar[(size_t)k];
+        std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
+        if (rb.has_n) { std::memcpy(p, rb.nm, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw; }
+        std::memcpy(p, rb.lq, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw;
+    }
     *p++ = qoff;
     out.n_pay = (size_t)(p - out.payload.data());
     out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
@@ -188,8 +200,8 @@ inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& 
     return true;
 }
 
-void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const QualCoder& qc, Part& out) {
-    out.n_hdr = out.n_pay = out.n_qual = 0;
+void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const QualCoder& qc, Part& out, bool compact) {
+    out.n_hdr = out.n_pay = out.n_qual = out.n_full = 0;
     out.max_span = 1; out.max_back = 0; out.aligned_bases = 0; out.bad = false;
     size_t n_rec = 0, n_words = 0, n_q = 0;
     int max_len = 0;
@@ -234,15 +246,15 @@ void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const 
         out.n_qual += padded;
         if (r.L > 0xffff) { out.bad = true; continue; }
         encode_read(r, rb);
-        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, rb, false, 0, 0, qoff, out); continue; }
-        for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out);
-        emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out);
+        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, rb, false, 0, 0, qoff, out, compact); continue; }
+        for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out, compact);
+        emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out, compact);
     }
 }
 
 }  // namespace
 
-bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits) {
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
     out.group.clear();
     const size_t n = hi > lo ? hi - lo : 0;
     const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 8192 + 1));   // small tiles are not worth a thread each
@@ -272,11 +284,12 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
     const QualCoder qc = choose_coder(any, min_qual_bits);
     out.qual_bits = (uint32_t)qc.bits;
     std::memcpy(out.qual_dict, qc.dict, 16);
-    if (nt == 1) pack_range(reads, lo, hi, qc, parts[0]);
+    out.layout = compact ? NGSEP_LAYOUT_COMPACT : NGSEP_LAYOUT_FULL;
+    if (nt == 1) pack_range(reads, lo, hi, qc, parts[0], compact);
     else {
         std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) { size_t a, b; range_of(t, a, b); Part* part = &parts[(size_t)t]; th.emplace_back([&reads, &qc, part, a, b]() { pack_range(reads, a, b, qc, *part); }); }
-        { size_t a, b; range_of(0, a, b); pack_range(reads, a, b, qc, parts[0]); }
+        for (int t = 1; t < nt; t++) { size_t a, b; range_of(t, a, b); Part* part = &parts[(size_t)t]; th.emplace_back([&reads, &qc, part, a, b, compact]() { pack_range(reads, a, b, qc, *part, compact); }); }
+        { size_t a, b; range_of(0, a, b); pack_range(reads, a, b, qc, parts[0], compact); }
         for (auto& x : th) x.join();
     }
     // contiguous ranges were packed independently: payload offsets move by the words in front of the range, quality offsets
@@ -284,7 +297,8 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
     size_t nh = 0, np = 0, nq = 0;
     std::vector<size_t> bh((size_t)nt), bp((size_t)nt), bq((size_t)nt);
     bool bad = false;
-    for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += parts[t].n_hdr; np += parts[t].n_pay; nq += parts[t].n_qual; bad = bad || parts[t].bad; }
+    out.n_words_full = 0;
+    for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += parts[t].n_hdr; np += parts[t].n_pay; nq += parts[t].n_qual; bad = bad || parts[t].bad; out.n_words_full += parts[t].n_full; }
     if (bad) {
         if (err) *err = "read longer than 65535 bases or with more than 255 CIGAR operations (after realignment): not supported by the device layout";
         out.hdr.clear(); out.payload.clear(); out.qual.clear();
@@ -334,7 +348,7 @@ ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
     t.seq_idx = seq_idx; t.tile_first = first; t.tile_last = last;
     t.n_reads = (int)hdr.size();
     t.max_span = max_span; t.max_back = max_back;
-    t.n_words = payload.size();
+    t.n_words = layout == NGSEP_LAYOUT_COMPACT ? n_words_full : payload.size();
     t.hdr = hdr.data();
     t.payload = payload.data();
     t.group = group.size() == hdr.size() && !group.empty() ? group.data() : nullptr;
@@ -342,7 +356,8 @@ ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {
     t.n_qual = qual.size();
     t.qual_bits = qual_bits;
     std::memcpy(t.qual_dict, qual_dict, 16);
-    t.reserved = 0;
+    t.layout = layout;
+    t.n_wire_words = payload.size();
     return t;
 }
 

@@ -185,6 +185,8 @@ struct PackedTile {
     HostBuf<uint8_t> qual;       // phred+33 bytes, one run per read (padded to 4), addressed by the records' qoff
     uint32_t qual_bits = 8;      // how `qual` is coded: 8 = the bytes, 2 / 4 = codes into qual_dict (ngsep_tile.qual_bits)
     uint8_t qual_dict[16] = {0};
+    uint32_t layout = NGSEP_LAYOUT_FULL;   // how `payload` is laid out (ngsep_tile.layout); compact: n_words_full = its length once expanded on the device
+    uint64_t n_words_full = 0;
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
     void set_pinned(bool on) { hdr.pin = payload.pin = group.pin = qual.pin = on; }
@@ -193,7 +195,9 @@ struct PackedTile {
 // Packs reads[lo,hi) (all their versions) in pileup order, on up to host_threads() threads.  Returns false (and leaves `err`)
 // when a record cannot be represented in the device layout (more than 65535 bases or 255 CIGAR operations — also after the
 // realigner rewrote it).
-bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0);
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0,
+                bool compact = false);
+bool wire_compact();   // the detectors pack NGSEP_LAYOUT_COMPACT tiles unless NGSEP_WIRE_COMPACT=0
 int host_threads();   // NGSEP_HOST_THREADS, else the hardware concurrency (at most 32)
 
 struct DetectorOptions {   // option ids of main/CommandsDescriptor.xml:565-703 that affect this path

@@ -49,6 +49,7 @@ constexpr size_t kRing = 4;             // tiles that may be in flight between n
 struct Slot {
     DevBuf<ngsep_read_hdr> d_hdr;
     DevBuf<uint32_t> d_pay;
+    DevBuf<uint32_t> d_wire;                  // NGSEP_LAYOUT_COMPACT: the payload as it crossed the bus, expanded into d_pay at staging
     DevBuf<uint8_t> d_qual;
     DevBuf<WinRange> d_win;
     DevBuf<ngsep_snv_call> d_calls;
@@ -79,7 +80,7 @@ struct Slot {
     bool qual_on_host = false;                // quality bytes stay in the caller's page-locked buffer (read on demand by the genotype kernel)
     unsigned int launches = 0;
     void release() {
-        d_hdr.release(); d_pay.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
+        d_hdr.release(); d_pay.release(); d_wire.release(); d_qual.release(); d_win.release(); d_calls.release(); d_counts.release();
         d_site_pos.release(); d_site_alleles.release();
         d_group.release(); d_sites.release(); d_scalls.release(); d_gidx.release(); d_goff.release(); d_gblk.release(); d_open.release(); d_ent.release();
         d_mhdr.release(); d_ev.release();
@@ -125,6 +126,7 @@ struct Ctx {
     DevBuf<int32_t> d_cov_first, d_cov_last; DevBuf<uint8_t> d_cov_unique; DevBuf<int2> d_cov_diff; DevBuf<unsigned char> d_cov_tmp;   // ngsep_coverage_histogram
     DevBuf<unsigned long long> d_cov_hist;
     DevBuf<uint2> d_allele_out;   // ngsep_tile_allele_counts
+    DevBuf<uint32_t> d_xsize, d_xoff; DevBuf<unsigned char> d_xcub;   // NGSEP_LAYOUT_COMPACT: record lengths / offsets of the full layout, scan scratch (stream-ordered reuse)
     DevBuf<unsigned char> d_ev_in; DevBuf<unsigned char> d_ev_out;   // ngsep_indel_tallies: inputs / outputs + scratch, each one allocation
     DevBuf<uint2> d_ent;     // resolved entries of the open columns (a full list only costs speed: such columns go out as record ranges)
     size_t q_min_cols = 0;   // learned from overflows
@@ -345,6 +347,10 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     if (multi && t->n_reads > 0 && !t->group) return fail(c, NGSEP_EINVAL, "multi-sample context: ngsep_tile.group is required");
     if (t->n_words > 0xfffffff0ull) return fail(c, NGSEP_EINVAL, "tile payload exceeds 16 GiB");
     if (t->qual_bits != 0u && t->qual_bits != 2u && t->qual_bits != 4u && t->qual_bits != 8u) return fail(c, NGSEP_EINVAL, "ngsep_tile.qual_bits must be 0, 2, 4 or 8");
+    if (t->layout != NGSEP_LAYOUT_FULL && t->layout != NGSEP_LAYOUT_COMPACT) return fail(c, NGSEP_EINVAL, "ngsep_tile.layout must be NGSEP_LAYOUT_FULL or NGSEP_LAYOUT_COMPACT");
+    const bool compact = t->layout == NGSEP_LAYOUT_COMPACT && !synth;
+    if (compact && t->n_wire_words > t->n_words) return fail(c, NGSEP_EINVAL, "ngsep_tile.n_wire_words exceeds n_words");
+    const size_t wire_words = compact ? (size_t)t->n_wire_words : (size_t)t->n_words;   // what `payload` holds on the caller's side
     const unsigned int qual_bits = t->qual_bits ? t->qual_bits : 8u;
     CK(cudaSetDevice(c->device), "set device");
     const RefSeq& ref = c->refs[t->seq_idx];
@@ -353,7 +359,7 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     // it where it is and the kernel reads the few bytes it needs in place, over PCIe.  Multi-sample contexts and the
     // EMIT_ALL test hook evaluate every column: they always copy.
     const uint8_t* host_qual = nullptr;
-    if (allow_host_qual && c->lazy_qual && !multi && !(c->params.flags & NGSEP_F_EMIT_ALL) && t->n_reads > 0) host_qual = mapped_host_alias(t->qual, (size_t)t->n_qual);
+    if (allow_host_qual && c->lazy_qual && !multi && !compact && !(c->params.flags & NGSEP_F_EMIT_ALL) && t->n_reads > 0) host_qual = mapped_host_alias(t->qual, (size_t)t->n_qual);
     s->qual_on_host = host_qual != nullptr;
     {   // pipeline slots grow together: a slot takes the largest capacity any of them has needed so far, so that cycling
         // tiles of different sizes through the ring stops reallocating after the first pass
@@ -367,16 +373,17 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
     // The bulk copies run on the COPY stream, the kernels on the context stream: the copies of the next tile overlap the
     // kernels of this one (a slot's buffers are only reused after its tile has been fetched).  Pageable sources are staged by
     // the driver synchronously with the host thread anyway: they stay on the context stream.
-    const bool pinned_src = !synth && t->n_reads > 0 && mapped_host_alias(t->payload, (size_t)t->n_words * 4) != nullptr;
+    const bool pinned_src = !synth && t->n_reads > 0 && mapped_host_alias(t->payload, wire_words * 4) != nullptr;
+    if (compact) CK(s->d_wire.reserve(wire_words + 16), "wire payload alloc");
     cudaStream_t copy_stream = pinned_src ? c->copy_stream : c->stream;
     if (multi && t->n_reads > 0) CK(cudaMemcpyAsync(s->d_group.p, t->group, (size_t)t->n_reads * sizeof(uint16_t), cudaMemcpyHostToDevice, copy_stream), "read-group copy");
     if (synth) launch_synth_tile(*synth, synth_g_lo, t->n_reads, ref.ref2, s->d_hdr.p, s->d_pay.p, s->d_qual.p, copy_stream);   // generated in place: nothing crosses PCIe
     else if (t->n_reads > 0) {
         CK(cudaMemcpyAsync(s->d_hdr.p, t->hdr, (size_t)t->n_reads * sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, copy_stream), "hdr copy");
-        CK(cudaMemcpyAsync(s->d_pay.p, t->payload, (size_t)t->n_words * 4, cudaMemcpyHostToDevice, copy_stream), "payload copy");
+        CK(cudaMemcpyAsync(compact ? s->d_wire.p : s->d_pay.p, t->payload, wire_words * 4, cudaMemcpyHostToDevice, copy_stream), "payload copy");
         if (!host_qual) CK(cudaMemcpyAsync(s->d_qual.p, t->qual, (size_t)t->n_qual, cudaMemcpyHostToDevice, copy_stream), "quality copy");
     }
-    s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)t->n_words};
+    s->pin->sentinel = ngsep_read_hdr{INT_MAX, 0u, 0, 0, (uint32_t)wire_words};   // (compact: rewritten to n_words by the expansion)
     CK(cudaMemcpyAsync(s->d_hdr.p + t->n_reads, &s->pin->sentinel, sizeof(ngsep_read_hdr), cudaMemcpyHostToDevice, copy_stream), "sentinel copy");
     if (pinned_src) {
         CK(cudaEventRecord(s->e_copy, c->copy_stream), "copy event");
@@ -399,12 +406,24 @@ int stage_slot(Ctx* c, Slot* s, const ngsep_tile* t, bool allow_host_qual = fals
         CK(launch_group_index(s->d_group.p, c->d_gins.p, t->n_reads, c->hp.n_groups, c->d_gkeys.p, c->d_gvals.p, c->d_cub.p, c->d_cub.cap, s->d_gidx.p, s->d_goff.p, s->d_gblk.p, c->stream),
            "group index launch");
     }
-    s->h2d_bytes = synth ? 0 : (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)t->n_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
+    s->h2d_bytes = synth ? 0 : (uint64_t)t->n_reads * sizeof(ngsep_read_hdr) + (uint64_t)wire_words * 4 + (host_qual ? 0 : (uint64_t)t->n_qual) +
                    (multi ? (uint64_t)t->n_reads * 2 : 0);
     s->n_words = (uint64_t)t->n_words; s->n_qual = (uint64_t)t->n_qual;
     // ordering, offsets, stage fit and the NGSEP_M_SIMPLE promise are checked on the device copy (the host thread only
     // enqueues work: the next tile can be packed / copied meanwhile); a tile that fails gets an empty window index
     CK(cudaMemsetAsync(s->d_report(), 0, 16, c->stream), "report memset");
+    if (compact && t->n_reads > 0) {   // the wire stream -> the full layout, before anything looks at the payload
+        const size_t n = (size_t)t->n_reads, tmp = expand_scan_temp_bytes(t->n_reads);
+        if (c->d_xsize.cap < n + 2 || c->d_xoff.cap < n + 2 || c->d_xcub.cap < tmp + 256) {
+            CK(cudaStreamSynchronize(c->stream), "drain before growing the expansion scratch");
+            CK(c->d_xsize.reserve(n + 2), "expansion alloc"); CK(c->d_xoff.reserve(n + 2), "expansion alloc"); CK(c->d_xcub.reserve(tmp + 256), "expansion alloc");
+        }
+        uint32_t dict4[4];
+        std::memcpy(dict4, t->qual_dict, 16);
+        CK(launch_expand_compact(s->d_hdr.p, t->n_reads, s->d_wire.p, (unsigned long long)wire_words, s->d_pay.p, (unsigned long long)t->n_words, s->d_qual.p,
+                                 (unsigned long long)t->n_qual, qual_bits, dict4, c->d_xsize.p, c->d_xoff.p, c->d_xcub.p, c->d_xcub.cap, s->d_report(), c->stream),
+           "payload expansion");
+    }
     launch_check_headers(s->d_hdr.p, s->d_pay.p, t->n_reads, (unsigned long long)t->n_words, (unsigned long long)t->n_qual, qual_bits, c->cfg.pay_cap_words, s->d_report(), c->stream);
     s->report_read = false;
     s->aligned_bases = 0;
@@ -565,7 +584,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
 
 extern "C" {
 
-int ngsep_abi_version(void) { return 2003; }
+int ngsep_abi_version(void) { return 2004; }
 int ngsep_built_sm(void) { return 100; }
 
 const char* ngsep_last_error(void* ctx) {

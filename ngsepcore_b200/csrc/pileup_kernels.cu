@@ -6,6 +6,7 @@
 
 #include <climits>
 #include <cstdlib>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace ngsep_b200 {
@@ -365,6 +366,7 @@ struct QualView {
     const uint8_t* __restrict__ p;
     uint32_t bits, d0, d1, d2, d3;
     __device__ __forceinline__ QualView(const TileDev& d) : p(d.qual), bits(d.qual_bits), d0(d.qual_dict[0]), d1(d.qual_dict[1]), d2(d.qual_dict[2]), d3(d.qual_dict[3]) {}
+    __device__ __forceinline__ QualView(const uint8_t* q, uint32_t b, uint4 dict) : p(q), bits(b), d0(dict.x), d1(dict.y), d2(dict.z), d3(dict.w) {}
     // phred+33 byte of base `off` of the read whose run starts at 4-byte unit qoff
     __device__ __forceinline__ uint32_t at(uint32_t qoff, uint32_t off) const {
         if (bits == 8u) return p[(size_t)qoff * 4u + (size_t)off];
@@ -2040,6 +2042,83 @@ __global__ void k_check_headers(ngsep_read_hdr* hdr, const uint32_t* __restrict_
         if (L) atomicAdd((unsigned long long*)(report + 2), (unsigned long long)L);
         if (err) atomicOr(report, err);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// NGSEP_LAYOUT_COMPACT: the wire stream -> the full payload layout (one scan between the two kernels)
+// ------------------------------------------------------------------------------------------------------------
+// What need not cross the bus does not: the CIGAR word of a single-block record is len*8+3 and its low-quality mask is a function
+// of its qualities, so a record flagged NGSEP_M_SIMPLE travels as [bases2, qoff].  k_expand_sizes gives every record its length in
+// the full layout (and checks the wire offsets it will follow), an exclusive scan turns the lengths into offsets, k_expand_records
+// writes the full payload and the new hdr.off.  The staging checks (k_check_headers) then run on the result as for any other tile.
+__global__ void k_expand_sizes(const ngsep_read_hdr* __restrict__ hdr, int n, unsigned long long n_wire, uint32_t* __restrict__ sizes, unsigned int* report) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i > n) return;
+    if (i == n) { sizes[n] = 0u; return; }
+    const ngsep_read_hdr h = hdr[i];
+    const unsigned long long next = hdr[i + 1].off;   // the sentinel carries n_wire
+    uint32_t sz = 0u;
+    if (next < h.off || next > n_wire || next - h.off > 0x00ffffffull) atomicOr(report, 2u);
+    else if (h.meta & NGSEP_M_SIMPLE) {
+        const uint32_t L = h.meta & 0xffffu, nb = (L + 15u) >> 4, nw = (L + 31u) >> 5;
+        const bool ok = (h.meta & (0x00ff0000u | NGSEP_M_NMASK | NGSEP_M_WINDOW)) == 0x00010000u && next - h.off == nb + 1ull;
+        if (!ok) atomicOr(report, 8u); else sz = 1u + nb + nw + 1u;
+    } else sz = (uint32_t)(next - h.off);
+    sizes[i] = sz;
+}
+
+__global__ void k_expand_records(ngsep_read_hdr* __restrict__ hdr, int n, const uint32_t* __restrict__ wire, const uint32_t* __restrict__ sizes,
+                                 const uint32_t* __restrict__ offs, uint32_t* __restrict__ payload, unsigned long long n_words_full, const uint8_t* __restrict__ qual,
+                                 unsigned long long n_qual, uint32_t qual_bits, uint4 qual_dict, unsigned int* report) {
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i > n) return;
+    if (report[0]) return;   // the wire offsets cannot be trusted (k_expand_sizes): nothing is expanded, the tile gets an empty window index
+    if (i == n) {
+        if ((unsigned long long)offs[n] != n_words_full) atomicOr(report, 2u);
+        hdr[n].off = (uint32_t)n_words_full;
+        return;
+    }
+    const ngsep_read_hdr h = hdr[i];
+    const uint32_t sz = sizes[i], o = offs[i];
+    if ((unsigned long long)o + sz > n_words_full) { atomicOr(report, 2u); return; }
+    const uint32_t* src = wire + h.off;
+    uint32_t* dst = payload + o;
+    if (h.meta & NGSEP_M_SIMPLE) {
+        const uint32_t L = h.meta & 0xffffu, nb = (L + 15u) >> 4, nw = (L + 31u) >> 5;
+        dst[0] = (L << 3) | 3u;
+        for (uint32_t k = 0; k < nb; k++) dst[1u + k] = src[k];
+        const uint32_t qoff = src[nb];
+        const bool q_ok = (unsigned long long)qoff * 4ull + ((unsigned long long)L * qual_bits + 7ull) / 8ull <= n_qual;
+        if (!q_ok) atomicOr(report, 8u);
+        const QualView qv(qual, qual_bits, qual_dict);
+        for (uint32_t w = 0; w < nw; w++) {
+            uint32_t m = 0u;
+            if (q_ok) for (uint32_t k = 32u * w; k < min(L, 32u * w + 32u); k++) if ((int)qv.at(qoff, k) - 33 <= 3) m |= 1u << (k & 31u);   // CH:214
+            dst[1u + nb + w] = m;
+        }
+        dst[1u + nb + nw] = qoff;
+    } else {
+        for (uint32_t k = 0; k < sz; k++) dst[k] = src[k];
+    }
+    hdr[i].off = o;
+}
+
+size_t expand_scan_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n + 1);
+    return bytes;
+}
+
+cudaError_t launch_expand_compact(ngsep_read_hdr* hdr, int n, const uint32_t* wire, unsigned long long n_wire, uint32_t* payload, unsigned long long n_words_full,
+                                  const uint8_t* qual, unsigned long long n_qual, uint32_t qual_bits, const uint32_t* qual_dict4, uint32_t* sizes, uint32_t* offs,
+                                  void* tmp, size_t tmp_bytes, unsigned int* report, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_expand_sizes<<<(n + 1 + 255) / 256, 256, 0, s>>>(hdr, n, n_wire, sizes, report);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, (const uint32_t*)sizes, offs, n + 1, s);
+    if (e != cudaSuccess) return e;
+    const uint4 dict = make_uint4(qual_dict4[0], qual_dict4[1], qual_dict4[2], qual_dict4[3]);
+    k_expand_records<<<(n + 1 + 127) / 128, 128, 0, s>>>(hdr, n, wire, sizes, offs, payload, n_words_full, qual, n_qual, qual_bits, dict, report);
+    return cudaGetLastError();
 }
 
 void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int qual_bits,

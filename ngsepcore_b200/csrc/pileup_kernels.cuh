@@ -109,6 +109,10 @@ struct LaunchCfg {
 size_t pileup_smem_bytes(const LaunchCfg& cfg);
 void launch_window_index(const TileDev& d, WinRange* out, int tile_idx, cudaStream_t s);
 int pileup_max_ctas_per_sm(size_t smem, int threads, int min_blocks);   // also raises the kernel's dynamic shared-memory limit
+size_t expand_scan_temp_bytes(int n);
+cudaError_t launch_expand_compact(ngsep_read_hdr* hdr, int n, const uint32_t* wire, unsigned long long n_wire, uint32_t* payload, unsigned long long n_words_full,
+                                  const uint8_t* qual, unsigned long long n_qual, uint32_t qual_bits, const uint32_t* qual_dict4, uint32_t* sizes, uint32_t* offs,
+                                  void* tmp, size_t tmp_bytes, unsigned int* report, cudaStream_t s);
 void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, unsigned long long n_words, unsigned long long n_qual, unsigned int qual_bits,
                           unsigned int pay_cap_words, unsigned int* report, cudaStream_t s);
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,

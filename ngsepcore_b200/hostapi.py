@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
 EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_msvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
            "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free",
-           "ngsep_host_merge_order", "ngsep_host_pack_quality", "ngsep_coverage_stats", "ngsep_relative_allele_counts"]
+           "ngsep_host_merge_order", "ngsep_host_pack_quality", "ngsep_coverage_stats", "ngsep_relative_allele_counts", "ngsep_host_pack_layout"]
 
 
 class HostBatch(C.Structure):
@@ -98,6 +98,13 @@ def last_pack_quality():
     d = (C.c_uint8 * 16)()
     load_library().ngsep_host_pack_quality(C.byref(bits), d)
     return int(bits.value), bytes(d)
+
+
+def last_pack_layout():
+    """(layout, n_words_full) of the payload the last pack call of this thread produced (ngsep_tile.layout / n_words)."""
+    layout, full = C.c_uint32(0), C.c_uint64(0)
+    load_library().ngsep_host_pack_layout(C.byref(layout), C.byref(full))
+    return int(layout.value), int(full.value)
 
 
 def decode_quality(qual: np.ndarray, hdr: np.ndarray, payload: np.ndarray, quality) -> np.ndarray:
@@ -301,7 +308,7 @@ class Detector:
             raise NgsepError(f"ngsep_ssvd_pack failed ({rc}): {self.lib.ngsep_ssvd_error(self.h).decode()}")
         return dict(hdr=_take(hdr_p, n_reads.value, HDR_DTYPE, self.lib), payload=_take(pay_p, n_words.value, np.uint32, self.lib),
                     qual=_take(q_p, n_qual.value, np.uint8, self.lib), max_span=span.value, max_back=back.value, first=tf.value, last=tl.value,
-                    aligned_bases=bases.value, quality=last_pack_quality())
+                    aligned_bases=bases.value, quality=last_pack_quality(), layout=last_pack_layout())
 
     def stats(self) -> RunStats:
         s = RunStats()

@@ -20,14 +20,14 @@ def test_header_symbols_exported():
     lib = capi.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ngsep_abi_version() == 2003 and lib.ngsep_built_sm() == 100
+    assert lib.ngsep_abi_version() == 2004 and lib.ngsep_built_sm() == 100
 
 
 def test_struct_layouts_match_header():
     assert capi.HDR_DTYPE.itemsize == 16
     assert capi.CALL_DTYPE.itemsize == 224
     assert C.sizeof(capi.Params) == 32
-    assert C.sizeof(capi.Tile) == 96 and C.sizeof(capi.TileStats) == 64
+    assert C.sizeof(capi.Tile) == 104 and C.sizeof(capi.TileStats) == 64
     assert capi.SITE_DTYPE.itemsize == 44 and capi.SAMPLE_CALL_DTYPE.itemsize == 104   # ngsep_pop_site, ngsep_sample_call
 
 

@@ -237,3 +237,43 @@ def test_known_variants_mode(oracle, tmp_path, depth, opts, det_kw):
     out = str(tmp_path / "out")
     subprocess.check_call([os.path.join(root, "ngsepcore_b200", "ngsep_b200"), "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-knownVariants", kv] + list(opts))
     assert open(out + ".vcf").read() == want
+
+
+def test_compact_wire_layout_gives_the_full_layout_results(oracle, tmp_path, monkeypatch):
+    """NGSEP_LAYOUT_COMPACT (the detectors' default): single-block records cross the bus without their CIGAR word and low-quality mask,
+    the device rebuilds them at staging (one scan + one pass).  Same VCF bytes as the full layout and as the oracle; through the C ABI
+    the same calls from the same sequence packed both ways, fewer bytes copied; a compact tile whose offsets do not add up is refused."""
+    from ngsepcore_b200 import capi
+    genome, batch, fa, sam = _inputs(tmp_path, [("chrA", 250000), ("chrB", 60000)], depth=30, seeds=(451, 452, 453), indel_rate=1e-3, n_frac=0.01)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NGSEP_WIRE_COMPACT", mode)
+        det = hostapi.Detector(tile_len=70000)
+        det.set_genome(genome)
+        outs[mode] = det.run(batch)
+        assert det.stats().covered_positions == gp
+    assert outs["1"] == outs["0"] == want
+    packs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NGSEP_WIRE_COMPACT", mode)
+        d = hostapi.Detector(host_only=True)
+        d.set_genome(genome)
+        packs[mode] = d.pack(batch, 0)
+    res = {}
+    with capi.Context() as ctx:
+        ctx.ref_upload(0, genome["chrA"])
+        for mode, t in packs.items():
+            ctx.submit(0, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=t["layout"])
+            calls, _, st = ctx.fetch()
+            res[mode] = (calls, st.h2d_bytes, st.covered_positions)
+        assert np.array_equal(res["1"][0], res["0"][0]) and res["1"][2] == res["0"][2] and len(res["1"][0]) > 100
+        assert res["1"][1] < 0.85 * res["0"][1]
+        t = packs["1"]
+        bad = t["hdr"].copy()
+        bad["off"][len(bad) // 2] += 1                       # a single-block record whose compact payload is one word short
+        ctx.submit(0, t["first"], t["last"], bad, t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=t["layout"])
+        with pytest.raises(capi.NgsepError):
+            ctx.fetch()
+        with pytest.raises(capi.NgsepError):                 # n_words (full) smaller than the stream it is expanded from
+            ctx.submit(0, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=(1, t["payload"].size - 5))

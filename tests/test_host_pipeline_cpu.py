@@ -302,3 +302,41 @@ def test_admission_inside_one_sequence_on_several_threads(oracle, tmp_path, monk
         outs.append([l for l in det.run(batch).splitlines() if not l.startswith("#")])
         assert det.stats().admitted < batch.n
     assert outs[0] == outs[1] == want_lines and len(want_lines) > 300
+
+
+def test_compact_wire_layout_is_the_full_layout_minus_what_the_device_rebuilds(monkeypatch):
+    """NGSEP_LAYOUT_COMPACT (what the detectors submit): the payload of a record flagged SIMPLE is [bases2, qoff] — its CIGAR word
+    (len*8+3) and low-quality mask stay on the host —, every other record's payload is unchanged, hdr.off index the compact stream,
+    and the reported n_words is the length of the full layout.  Dropping those words from the full packing of the same reads gives
+    the compact stream word for word."""
+    from ngsepcore_b200 import capi
+    genome, batch, _ = simulate.simulate(contigs=[("a", 60000)], depth=20, seeds=(23, 24, 25), indel_rate=2e-3, n_frac=0.01)
+    det = hostapi.Detector(host_only=True)
+    det.set_genome(genome)
+    monkeypatch.setenv("NGSEP_WIRE_COMPACT", "0")
+    full = det.pack(batch, 0)
+    monkeypatch.delenv("NGSEP_WIRE_COMPACT")
+    comp = det.pack(batch, 0)
+    assert full["layout"] == (0, full["payload"].size) and comp["layout"] == (1, full["payload"].size)
+    assert np.array_equal(full["qual"], comp["qual"]) and full["quality"] == comp["quality"]
+    hf, hc = full["hdr"], comp["hdr"]
+    for name in ("first", "meta", "ign_start", "ign_end"):
+        assert np.array_equal(hf[name], hc[name])
+    simple = (hf["meta"] & capi.M_SIMPLE) != 0
+    assert 0.5 < simple.mean() < 1.0                      # indel reads, realigner versions and reads with N keep their payload
+    L = (hf["meta"] & 0xFFFF).astype(np.int64)
+    nb, nw = (L + 15) // 16, (L + 31) // 32
+    end_f = np.concatenate([hf["off"][1:], [full["payload"].size]]).astype(np.int64)
+    size_f = end_f - hf["off"]
+    assert np.array_equal(size_f[simple], (1 + nb + nw + 1)[simple])
+    size_c = np.where(simple, nb + 1, size_f)
+    off_c = np.concatenate([[0], np.cumsum(size_c)[:-1]])
+    assert np.array_equal(off_c, hc["off"]) and int(size_c.sum()) == comp["payload"].size
+    keep = np.ones(full["payload"].size, bool)
+    for i in np.nonzero(simple)[0]:
+        o = int(hf["off"][i])
+        assert full["payload"][o] == (L[i] << 3 | 3)
+        keep[o] = False
+        keep[o + 1 + nb[i]: o + 1 + nb[i] + nw[i]] = False
+    assert np.array_equal(full["payload"][keep], comp["payload"])
+    assert comp["payload"].nbytes < 0.75 * full["payload"].nbytes
