@@ -94,4 +94,35 @@ def cli():
     print("bad", bad)
 
 
-{"single": single, "multi": multi, "cli": cli}[MODE]()
+def known():
+    """-knownVariants: the host-made records (the input variants that are not SNVs) against the oracle's."""
+    from tests.known_util import make_known_vcf
+    lib = ou.load_oracle()
+    d = tempfile.mkdtemp()
+    bad = 0
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        rng = np.random.default_rng(seed)
+        kw = dict(depth=float(rng.choice([2, 6, 15, 40])), indel_rate=float(rng.choice([5e-4, 2e-3, 5e-3])), snv_rate=3e-3, indel_jitter=float(rng.choice([0.0, 0.3, 0.8])),
+                  n_read_groups=int(rng.integers(1, 3)), paired=bool(rng.integers(0, 2)))
+        opts, detkw = [((), {}), (("-minQuality", "10"), dict(minQuality=10)), (("-maxBaseQS", "25", "-h", "0.0001"), dict(maxBaseQS=25, h=0.0001)),
+                       (("-ignore5", "4", "-ignore3", "6"), dict(ignore5=4, ignore3=6)), (("-ploidy", "1"), dict(ploidy=1))][int(rng.integers(0, 5))]
+        contigs = [("chrA", 50000), ("chrB", 20000)]
+        genome, batch, _ = simulate.simulate(contigs=contigs, seeds=(seed * 5 + 1, seed * 5 + 2, seed * 5 + 3), **kw)
+        fa, sam, kv = os.path.join(d, "r.fa"), os.path.join(d, "r.sam"), os.path.join(d, "k.vcf")
+        simulate.write_fasta(fa, genome); simulate.write_sam(sam, batch)
+        disc, _, _, _ = ou.run_ssvd(lib, fa, sam, args=("-minQuality", "0"))
+        make_known_vcf(kv, disc, genome, contigs, rng)
+        want, _, _, _ = ou.run_ssvd(lib, fa, sam, args=("-knownVariants", kv) + opts)
+        def snv(l):
+            t = l.split("\t")
+            return all(len(a) == 1 and a in "ACGT" for a in [t[3]] + t[4].split(","))
+        wl = [l for l in want.splitlines() if not l.startswith("#") and not snv(l)]
+        det = hostapi.Detector(host_only=True, knownVariants=kv, **detkw); det.set_genome(genome)
+        gl = det.run(batch, with_header=False).splitlines()
+        ok = gl == wl
+        print(seed, kw["depth"], opts, len(wl), "OK" if ok else "MISMATCH", flush=True)
+        bad += not ok
+    print("mismatches", bad)
+
+
+{"single": single, "multi": multi, "cli": cli, "known": known}[MODE]()
