@@ -129,6 +129,9 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return jobs[x].hi - jobs[x].lo > jobs[y].hi - jobs[y].lo; });
     // ---- stages 1-2: admission + event pre-pass, every sequence on its own host thread (a run with fewer sequences than threads
     // also splits the work inside a sequence) -----------------------------------------------------------------------------------
+    // (measured on the 16-core B200 host, yeast 30x: giving the LONGEST of many sequences threads of its own makes the stage slower,
+    // 0.057 -> 0.065 s — the admitted reads are fresh memory and page faults serialise the threads —, so only a run with fewer sequences
+    // than threads splits a sequence)
     inner_threads_ = (jobs.empty() || (int)jobs.size() >= threads) ? 1 : std::max(1, threads / (int)jobs.size());
     double tp = now_s();
     parallel_jobs(jobs.size(), threads, order, [&](size_t k) { jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan); });
