@@ -872,6 +872,7 @@ int ngsep_resident_fetch_pop(void* ctx, int slot, ngsep_pop_site* sites, size_t 
 int ngsep_resident_add(void* ctx, const ngsep_tile* t, int* slot) {
     Ctx* c = (Ctx*)ctx;
     if (!c || !slot) return NGSEP_EINVAL;
+    if (c->next_has_sites) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites declares the sites of a submitted tile: resident tiles have none");
     CK(cudaSetDevice(c->device), "set device");
     Slot* s = nullptr;
     int rc = new_slot(c, &s, c->slots.size());
