@@ -8,15 +8,15 @@ A "step" = one pass of the hot path over the whole workload: BASELINE configs[1]
 30x (2x100 bp), simulated with planted SNVs/indels (ngsepcore_b200/simulate.py), one region tile per sequence, all
 tiles walked by ONE k_pileup_windows launch followed by ONE k_genotype_columns launch (ngsep_resident_run(-1)).
   value  = positions with >= 1 covering admitted read / device time of the step, tiles resident in HBM (CUDA events on
-           the context stream; the step's input is 600 MB in HBM > 126 MB L2, so no step is served from cache);
+           the context stream; the step's input is 344 MB in HBM > 126 MB L2, so no step is served from cache);
   e2e    = the same metric through the C ABI with HOST buffers: ngsep_tile_submit (H2D from page-locked memory +
            kernels) + ngsep_tile_fetch (D2H of the calls) per tile, all inside the timed region;
   roofline.achieved = ALGORITHMIC bytes (sum_reads(16 + 4 n_cigar + ceil(L/4) + L) + 1 B/reference base +
-           64 B/call) / device time of k_pileup_windows (CUDA events around the launch, same stream).  The kernel does
-           not need every one of those bytes: quality bytes are read only for the few positions that reach the genotype
-           kernel (the window kernel works from a 1-bit "quality <= 3" mask), so the measured DRAM traffic
-           (roofline.traffic, from the committed ncu capture) is BELOW the algorithmic bytes; roofline.frac_of_traffic
-           gives the fraction of peak the kernel's real traffic amounts to.
+           64 B/call) / device time of the WHOLE step, k_pileup_windows + k_genotype_columns (CUDA events around the two
+           launches, same stream); the per-kernel shares sit beside it.  The window kernel does not need every one of those
+           bytes: quality bytes are read only for the few positions that reach the genotype kernel (it works from a 1-bit
+           "quality <= 3" mask), so its measured DRAM traffic (roofline.traffic, from the committed ncu capture) is BELOW the
+           algorithmic bytes; k_pileup_windows.frac_of_traffic gives the fraction of peak that traffic amounts to.
 N > 1 (torchrun): every rank owns one GPU and an independent, equally sized region shard (weak scaling, no data-path
 collective — SURVEY.md 8e); value = positions of all ranks / max-over-ranks time.
 """
@@ -314,11 +314,14 @@ def run_gpu(args):
                     "host_input_bytes_per_step": int(h2d_bytes * world), "same_calls_as_resident_run": bool(n_calls_e2e == calls),
                     "quality_in_place_tiles": int(e2e_in_place),
                     "quality_bits": sorted({int(t["quality"][0]) for t in tiles}),
+                    "wire_layout": sorted({"compact" if t["layout"][0] else "full" for t in tiles}),
                     "note": "h2d_bytes_per_step = bytes ngsep_tile_submit copies (record headers + payload); the quality array (%.0f MB) stays in the "
                             "caller's page-locked buffers and k_genotype_columns reads what it needs in place over PCIe "
                             "(--quality-in-place)" % ((h2d_bytes - e2e_copied) / 1e6) if e2e_in_place else
                             "every host buffer of the step is copied host -> device, the same mode at every N; qualities travel as "
-                            "quality_bits-bit codes (ngsep_tile.qual_bits: the simulated qualities fall into 4 classes the path can tell apart)"},
+                            "quality_bits-bit codes (ngsep_tile.qual_bits: the simulated qualities fall into 4 classes the path can tell apart), "
+                            "single-block records without their CIGAR word and low-quality mask (ngsep_tile.layout compact: rebuilt on the device "
+                            "at staging, inside the timed region)"},
             "pipeline": pipeline,
             "gpu_launches": int(launches_all * args.steps),
             "clocks": clocks,
