@@ -578,10 +578,6 @@ __device__ __forceinline__ int counted_ref_base(const Recs<kGlobal>& R, int idx,
 // (CH:231-249) from the host-supplied tables — bit-identical to the Java doubles — and finalize_warp.
 constexpr int kRegRounds = 4;
 struct GenoCtx { const double* s_tab; const double* s_tab2; const int* s_kmin; int max_qs, min_quality; bool may_skip, emit_all; };
-// s_tab2[(q * 4 + b) * kTabLanes + lane]: what a counted base b of quality q adds to the log-likelihood lane `lane` owns
-// (CH:231-249); row kTabZeroRow is all zeros (a call that is not counted adds nothing)
-constexpr int kTabLanes = 10, kTabZeroRow = 31 * 4, kTab2Size = (kTabZeroRow + 1) * kTabLanes;
-
 __device__ __forceinline__ void count_round(uint32_t code, ColCounts& cc) {
     cc.depth += __popc(__ballot_sync(kFull, (code & kCodeCall) != 0u));   // CH:210 totalCount: every call, whatever its quality or base
     const unsigned ng = __ballot_sync(kFull, (code & kCodeNeg) != 0u);
@@ -1245,17 +1241,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
     __shared__ int s_kmin[kSkipTable];
     const DevParams& prm = *gprm;
     for (int i = threadIdx.x; i < NGSEP_N_TABLES; i += blockDim.x) s_tab[i] = prm.tables[i];
-    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) {
-        // lane l owns L[pa][pb]: lanes 0-3 the homozygous L[l][l], lanes 4-9 the pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3).
-        // A counted base b of quality q adds a_q to the homozygous likelihood of b, c_q to the pairs that hold b, b_q to the rest
-        // (CH:231-249 with f == g == 250: the matrix is symmetric).
-        const int l = i % kTabLanes, row = i / kTabLanes, q = row >> 2, b = row & 3;
-        const int pa = (l < 4) ? l : ((l < 7) ? 0 : ((l < 9) ? 1 : 2));
-        const int pb = (l < 4) ? l : ((l < 7) ? l - 3 : ((l < 9) ? l - 5 : 3));
-        double v = 0.0;
-        if (row < kTabZeroRow) v = (b == pa || b == pb) ? ((l < 4) ? prm.tables[3 * q] : prm.tables[3 * q + 2]) : prm.tables[3 * q + 1];
-        s_tab2[i] = v;
-    }
+    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) s_tab2[i] = prm.tab2[i];   // (filled once per context: DevParams.tab2)
     if (threadIdx.x < kSkipTable) s_kmin[threadIdx.x] = prm.k_min[threadIdx.x];
     __syncthreads();
     const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
@@ -1388,14 +1374,7 @@ __device__ __forceinline__ uint32_t sample_genotype(const SamplePost& P, int dep
 __global__ void __launch_bounds__(256) k_genotype_sites(const TileDev* __restrict__ tiles, const DevParams* __restrict__ gprm) {
     __shared__ double s_tab2[kTab2Size];
     const DevParams& prm = *gprm;
-    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) {   // the table of k_genotype_columns: what a counted base adds to the likelihood a lane owns
-        const int l = i % kTabLanes, row = i / kTabLanes, q = row >> 2, b = row & 3;
-        const int pa = (l < 4) ? l : ((l < 7) ? 0 : ((l < 9) ? 1 : 2));
-        const int pb = (l < 4) ? l : ((l < 7) ? l - 3 : ((l < 9) ? l - 5 : 3));
-        double v = 0.0;
-        if (row < kTabZeroRow) v = (b == pa || b == pb) ? ((l < 4) ? prm.tables[3 * q] : prm.tables[3 * q + 2]) : prm.tables[3 * q + 1];
-        s_tab2[i] = v;
-    }
+    for (int i = threadIdx.x; i < kTab2Size; i += blockDim.x) s_tab2[i] = prm.tab2[i];
     __syncthreads();
     const TileDev& d = tiles[0];
     const int lane = threadIdx.x & 31;

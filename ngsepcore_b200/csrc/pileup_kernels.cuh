@@ -69,6 +69,11 @@ struct TileDev {
     const int32_t* site_pos; const uint16_t* site_alleles; int n_sites;
 };
 
+// tab2[(q * 4 + b) * kTabLanes + l]: what a counted base b of quality q adds to the log-likelihood lane l of the genotype kernels owns
+// (lanes 0-3 the homozygous L[l][l], lanes 4-9 the pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3); CH:231-249 with f == g == 250: the matrix
+// is symmetric); row kTabZeroRow is all zeros (a call that is not counted adds nothing).  Filled once per context.
+constexpr int kTabLanes = 10, kTabZeroRow = 31 * 4, kTab2Size = (kTabZeroRow + 1) * kTabLanes;
+
 struct DevParams {
     int max_base_qs, min_quality;
     unsigned int flags;
@@ -76,6 +81,7 @@ struct DevParams {
     int k_min[16];               // k_min[m]: with m counted non-reference bases, k >= k_min[m] counted reference bases
                                  // prove P(ref,ref) > 1/2; INT_MAX when no k suffices
     double tables[NGSEP_N_TABLES];
+    double tab2[kTab2Size];
     // sample axis (MultisampleVariantsDetector); n_samples == 1: everything below is unused
     int n_samples, n_groups, max_groups_per_sample;
     int column_run;                      // k_genotype_columns_multi: neighbouring list entries one CTA takes in a row
