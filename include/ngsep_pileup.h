@@ -42,7 +42,8 @@ typedef struct ngsep_params {
     int32_t max_base_qs;  /* -maxBaseQS, default 30      discovery/CountsHelper.java:47,217-219                  */
     int32_t min_quality;  /* -minQuality, default 40     discovery/SingleSampleVariantPileupListener.java:50,223 */
     double het_rate;      /* -h, 1e-3 diploid / 1e-6 haploid   discovery/CountsHelper.java:42-43                 */
-    int32_t ploidy;       /* -ploidy, default 2 (device path supports ploidy < 3, SSVPL:238)                    */
+    int32_t ploidy;       /* -ploidy, default 2; >= 3: the pool / polyploid algorithm (SSVPL:240-254): single-sample contexts return
+                             NGSEP_CALL_POOL columns for the host's genotypeVariantPool                                  */
     uint32_t flags;       /* NGSEP_F_*                                                                          */
     int32_t n_samples;    /* 1 = SingleSampleVariantsDetector; >1 = MultisampleVariantsDetector sample axis      */
     int32_t reserved;
@@ -147,6 +148,11 @@ typedef struct ngsep_snv_call {
 #define NGSEP_CALL_HET 1      /* 0/1   CalledSNV heterozygous     VD:181-188 */
 #define NGSEP_CALL_HOMALT 2   /* 1/1   CalledSNV homozygous alt   VD:189-193 */
 #define NGSEP_CALL_TRIALLELIC 3 /* 1/2 MULTISNV                   VD:128-177; a0 = alt, a1 = third allele as ordered by VD:133-139 */
+#define NGSEP_CALL_POOL 5      /* ploidy >= 3 (pools / polyploids, SSVPL:240-254): a column where an alternative base has the support
+                                  createSNVVariantPool asks for (SSVPL:306-319), for the host's genotypeVariantPool (SSVPL:402-503): count /
+                                  depth / strand / ref as always; sample = n, the number of counted bases; their evidence bytes
+                                  (quality << 2 | base, pileup order) fill the logcond field (the first 128) and, for a deeper column, the
+                                  ceil((n - 128) / 224) call slots behind this one, which hold nothing else                      */
 #define NGSEP_CALL_SITE 4      /* a known site (ngsep_tile_sites): VD.genotypeSNV, VD:21-97.  a0 <= a1 are indexes into the SITE's allele list
                                   (a0 == a1: homozygous, 0/0 included), -1,-1 = undecided (gq 0: no call, gq == 0, or gq < minQuality, SSVPL:388);
                                   count / depth / logcond as always; sample = index of the site in the list given to ngsep_tile_sites;

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cstring>
 #include <cmath>
 #include <deque>
 #include <queue>
@@ -103,6 +104,7 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         n_known_ = 0;
         for (auto& vs : known_) n_known_ += vs.size();
     }
+    if (opt_.ploidy >= 3 && (known_mode() || with_groups())) { err_ = "ploidy >= 3 (the pool algorithm) is built for the discovery mode of SingleSampleVariantsDetector only"; return NGSEP_EINVAL; }
     if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
     // ---- the sequences of the batch, in file order (APG:310-322 for a query sequence) ------------------------------------
@@ -185,6 +187,25 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         int rc = fetch_tile(ctxs_[dev], *f.job, ts);
         q[dev].pop_front();
         if (rc != NGSEP_OK) return rc;
+        if (opt_.ploidy >= 3 && !known && !with_groups()) {   // pools: the supported columns, each followed by the slots that continue its evidence bytes
+            std::vector<ngsep_snv_call>& snvs = f.job->snvs;
+            size_t k = before;
+            while (k < snvs.size()) {
+                const ngsep_snv_call& c = snvs[k];
+                if (c.kind != NGSEP_CALL_POOL || c.sample < 0) { err_ = "unexpected record from a pool context"; return NGSEP_ESTATE; }
+                const size_t n_ev = (size_t)c.sample, inl = std::min<size_t>(n_ev, 128);
+                const size_t extra = n_ev > 128 ? (n_ev - 128 + sizeof(ngsep_snv_call) - 1) / sizeof(ngsep_snv_call) : 0;
+                if (k + extra >= snvs.size()) { err_ = "truncated pool column"; return NGSEP_ESTATE; }
+                SeqJob::PoolColumn pc;
+                pc.col = c;
+                pc.ev.resize(n_ev);
+                std::memcpy(pc.ev.data(), c.logcond, inl);
+                if (n_ev > 128) std::memcpy(pc.ev.data() + 128, (const uint8_t*)&snvs[k + 1], n_ev - 128);
+                f.job->pool_cols.push_back(std::move(pc));
+                k += 1 + extra;
+            }
+            snvs.resize(before);
+        }
         if (known) {   // record k of a site tile belongs to site k of the list it was submitted with
             std::vector<ngsep_snv_call>& snvs = f.job->snvs;
             for (size_t k = before; k < snvs.size(); k++) {
@@ -437,7 +458,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
 void GpuSingleSampleVariantsDetector::on_span_event(int e, const std::string& ref_upper, const EventOutcome& ev, std::vector<HostRead*>& pileup, SeqPlan& plan,
                                                     int& last_indel_end) {
     IndelCallerOptions io;
-    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
+    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb; io.ploidy = opt_.ploidy;
     IndelRecord rec;
     const bool input_str = ev.str && !ev.new_str;
     if (input_str) plan.suppressed.insert(e);      // no SNV is tried at an input locus when the indel alleles give no call (SSVPL:264)
@@ -494,7 +515,8 @@ int GpuSingleSampleVariantsDetector::tally_span_events(std::vector<SeqJob>& jobs
             ct.diag.assign(diag.begin() + a0, diag.begin() + a0 + n);
             ct.call_index.assign(call_index.begin() + c0, call_index.begin() + c1);
             ct.call_fit.assign(call_fit.begin() + c0, call_fit.begin() + c1);
-            finish_tally(ct, (size_t)n, opt_.het_rate, job.plan.span_tallies[i]);   // the part that hangs on libm stays with the host's
+            if (opt_.ploidy >= 3) { job.plan.span_call_tallies.resize(job.plan.span_inputs.size()); job.plan.span_call_tallies[i] = std::move(ct); }   // pools: finished per hypothesis
+            else finish_tally(ct, (size_t)n, opt_.het_rate, job.plan.span_tallies[i]);   // the part that hangs on libm stays with the host's
         }
     }
     return NGSEP_OK;
@@ -504,7 +526,8 @@ int GpuSingleSampleVariantsDetector::tally_span_events(std::vector<SeqJob>& jobs
 // sequence, in order, with the device's tallies
 void GpuSingleSampleVariantsDetector::resolve_fired_events(SeqPlan& plan) {
     IndelCallerOptions io;
-    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb;
+    io.max_base_qs = opt_.max_base_qs; io.het_rate = opt_.het_rate; io.min_quality = opt_.min_quality; io.csb = opt_.csb; io.ploidy = opt_.ploidy;
+    const bool pool = opt_.ploidy >= 3;
     int last_indel_end = 0;   // SSVPL:143
     for (const SeqPlan::FiredEvent& fe : plan.fired) {
         const int e = fe.e;
@@ -518,7 +541,10 @@ void GpuSingleSampleVariantsDetector::resolve_fired_events(SeqPlan& plan) {
         if (emb || ev.span <= 1) continue;                   // SNV path: the device decides
         if (input_str) plan.suppressed.insert(e);            // no SNV is tried at an input locus when the indel alleles give no call (SSVPL:264)
         IndelRecord rec;
-        if (fe.input >= 0 && finish_indel_call(plan.span_inputs[(size_t)fe.input], plan.span_tallies[(size_t)fe.input], io, rec)) {
+        const bool have = fe.input < 0 ? false
+                          : (pool ? finish_indel_pool(plan.span_inputs[(size_t)fe.input], plan.span_call_tallies[(size_t)fe.input], io, opt_.ploidy, rec)
+                                  : finish_indel_call(plan.span_inputs[(size_t)fe.input], plan.span_tallies[(size_t)fe.input], io, rec));
+        if (have) {
             plan.suppressed.insert(e);
             last_indel_end = rec.last;                       // SSVPL:157-158
             if (rec.last > e) plan.embedded.push_back({e + 1, rec.last});
@@ -528,6 +554,7 @@ void GpuSingleSampleVariantsDetector::resolve_fired_events(SeqPlan& plan) {
     }
     std::vector<SpanEventInput>().swap(plan.span_inputs);
     std::vector<IndelTally>().swap(plan.span_tallies);
+    std::vector<CallTallies>().swap(plan.span_call_tallies);
 }
 
 void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const {
@@ -591,6 +618,22 @@ void GpuSingleSampleVariantsDetector::emit_text(SeqJob& job) {
         if (emb && !opt_.call_embedded) continue;
         lines.push_back({c.pos, c.pos, (int)lines.size(), snv_vcf_line(c, chrom, opt_.ploidy, opt_.csb, emb)});
         job.snv_records++;
+    }
+    if (opt_.ploidy >= 3) {   // pools / polyploids: discoverSNV's pool branch on the columns the device found supported (SSVPL:240-254)
+        std::sort(job.pool_cols.begin(), job.pool_cols.end(), [](const SeqJob::PoolColumn& a, const SeqJob::PoolColumn& c) { return a.col.pos < c.col.pos; });
+        size_t pe = 0;
+        for (auto& pc : job.pool_cols) {
+            const int pos = pc.col.pos;
+            if (suppressed.count(pos)) continue;
+            while (pe < embedded.size() && embedded[pe].second < pos) pe++;
+            const bool emb = pe < embedded.size() && embedded[pe].first <= pos && pos <= embedded[pe].second;
+            if (emb && !opt_.call_embedded) continue;
+            std::vector<int> alleles;
+            PoolCall call;
+            if (!discover_pool_snv(pc.col, pc.ev.data(), opt_.ploidy, opt_.het_rate, opt_.min_quality, alleles, call)) continue;
+            lines.push_back({pos, pos, (int)lines.size(), pool_snv_vcf_line(pos, alleles, call, chrom, opt_.ploidy, emb)});
+            job.snv_records++;
+        }
     }
     for (auto& r : plan.indels) {
         bool mine = true;   // host-made records go to the shard that owns the tile of their position

@@ -340,6 +340,11 @@ bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const Inde
 bool call_indel_at(int pos, const std::string& ref_allele, bool is_str, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt, IndelRecord& out, bool input_str) {
     SpanEventInput in;
     gather_span_event(pos, ref_allele, is_str, input_str, pileup, opt.max_base_qs, in);
+    if (opt.ploidy >= 3) {   // pools / polyploids, SSVPL:281-295
+        CallTallies ct;
+        tally_calls_host(in, opt, ct);
+        return finish_indel_pool(in, ct, opt, opt.ploidy, out);
+    }
     IndelTally t;
     tally_span_event_host(in, opt, t);
     return finish_indel_call(in, t, opt, out);

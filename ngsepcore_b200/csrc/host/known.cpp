@@ -247,5 +247,19 @@ std::string known_indel_vcf_line(const KnownVariant& v, const SampleIndelCall& c
     return s;
 }
 
+// A pool / polyploid SNV call (SSVPL:240-254): a CalledGenomicVariantImpl with a call report and no base counts of its own, so the record
+// takes the ADP format (SSVD:947-952); the variant has no quality; its type is SNV (not written), MULTISNV while three or more alleles
+// stand (SSVPL:326-328), EMBEDDED inside an indel (SSVPL:229).
+std::string pool_snv_vcf_line(int pos, const std::vector<int>& alleles, const PoolCall& c, const std::string& chrom, int ploidy, bool embedded) {
+    static const char B[] = "ACGT";
+    KnownVariant v;
+    v.first = v.last = pos;
+    for (int a : alleles) v.alleles.emplace_back(1, B[a]);
+    v.type = embedded ? 3 : (alleles.size() > 2 ? 2 : 1);
+    SampleIndelCall sc;
+    sc.called = c.called; sc.gq = c.gq; sc.depth = c.depth; sc.has_report = true; sc.counts = c.counts; sc.logc = c.logc;
+    return known_indel_vcf_line(v, sc, chrom, ploidy);
+}
+
 }  // namespace host
 }  // namespace ngsep_b200

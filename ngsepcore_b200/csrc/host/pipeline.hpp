@@ -74,6 +74,7 @@ struct IndelRecord {
     std::vector<int> counts;               // per allele
     std::vector<std::vector<double>> logc; // per allele pair
     int strand_bias = -1;
+    bool pool = false;                     // a pool / polyploid call (SSVPL:281-295): every allele of the variant is listed, the variant has no type and no quality
 };
 
 // One event with a reference span > 1 as the variant listener sees it (SSVPL:257-273): the calls of PR.getAlleleCalls(span) in pileup
@@ -88,7 +89,7 @@ struct IndelTally { int total = 0; std::vector<int> counts; std::vector<std::arr
 // diagonal of logConditionalProbs; per call the allele it counts for (-1: none) and its log-likelihood under that allele
 struct CallTallies { int total = 0; std::vector<int> counts; std::vector<std::array<int, 2>> strand; std::vector<double> diag; std::vector<int> call_index; std::vector<double> call_fit; };
 
-struct IndelCallerOptions { int max_base_qs = 30; double het_rate = 0.001; int min_quality = 40; bool csb = false; };
+struct IndelCallerOptions { int max_base_qs = 30; double het_rate = 0.001; int min_quality = 40; bool csb = false; int ploidy = 2; };
 
 // SingleSampleVariantPileupListener.discoverVariantWithSpan (SSVPL:257-273) up to the SNV fall-back:
 // AlleleCallClustersBuilder + CountsHelper.calculateCountsIndel + VariantDiscoverySNVQAlgorithm.callIndel.
@@ -103,6 +104,14 @@ void tally_calls_host(const SpanEventInput& in, const IndelCallerOptions& opt, C
 void finish_tally(const CallTallies& ct, size_t n_alleles, double het_rate, IndelTally& t);   // mixture terms, posteriors, arg-max genotype
 double indel_log_error();   // log10(0.0001), CH:52
 bool finish_indel_call(const SpanEventInput& in, const IndelTally& t, const IndelCallerOptions& opt, IndelRecord& out);
+
+// Pools / polyploids (ploidy >= 3, pool.cpp): the genotype genotypeVariantPool gives (SSVPL:402-503)
+struct PoolCall { std::vector<int> called; int gq = 0, depth = 0; bool undecided = false; std::vector<int> counts; std::vector<std::vector<double>> logc; };
+// discoverSNV's pool branch (SSVPL:240-254) on a column of kind NGSEP_CALL_POOL and its evidence bytes; alleles: base indexes, reference first
+bool discover_pool_snv(const ngsep_snv_call& col, const uint8_t* ev, int ploidy, double het_rate, int min_quality, std::vector<int>& alleles, PoolCall& out);
+// discoverIndel's pool branch (SSVPL:281-295) + the filter of SSVPL:263 from the event's allele tallies
+bool finish_indel_pool(const SpanEventInput& in, const CallTallies& ct, const IndelCallerOptions& opt, int ploidy, IndelRecord& out);
+std::string pool_snv_vcf_line(int pos, const std::vector<int>& alleles, const PoolCall& c, const std::string& chrom, int ploidy, bool embedded);
 
 // Phred / rounding helpers shared by the host writer (math/PhredScoreHelper.java:31-40)
 long jround(double x);
@@ -244,6 +253,7 @@ struct SeqPlan {
     std::vector<FiredEvent> fired;
     std::vector<SpanEventInput> span_inputs;     // FiredEvent.input indexes these (events with a reference span > 1 and a reference allele)
     std::vector<IndelTally> span_tallies;
+    std::vector<CallTallies> span_call_tallies;  // (pools: the per-call tallies themselves, finished per allele-frequency hypothesis)
     // -knownVariants: the input variants that got a pileup (SSVPL:162-176), as indexes into the sequence's variant list
     std::vector<int> sites;                                      // SNVs: genotyped on the device (ngsep_tile_sites), ascending position
     std::vector<std::pair<int, SampleIndelCall>> known_indels;   // the others: genotyped by the host at their event
@@ -258,6 +268,8 @@ struct SeqJob {
     int64_t lo = 0, hi = 0;                      // records of the batch
     SeqPlan plan;
     std::vector<ngsep_snv_call> snvs;            // single-sample device results
+    struct PoolColumn { ngsep_snv_call col; std::vector<uint8_t> ev; };
+    std::vector<PoolColumn> pool_cols;           // ploidy >= 3: the supported columns of the device with their evidence bytes
     std::vector<ngsep_snv_call> site_calls;      // -knownVariants: the device's record of plan.sites[k] (site_have[k] != 0)
     std::vector<char> site_have;
     std::vector<ngsep_pop_site> sites;           // multi-sample device results ...

@@ -130,7 +130,7 @@ std::string indel_vcf_line(const IndelRecord& r, const std::string& chrom, int p
     std::string s = chrom;
     s += "\t"; s += std::to_string(r.pos); s += "\t.\t"; s += r.alleles[0]; s += "\t";
     for (size_t i = 1; i < r.alleles.size(); i++) { if (i > 1) s += ","; s += r.alleles[i]; }
-    s += "\t"; s += std::to_string(r.qual); s += "\t.\t"; s += r.str ? "TYPE=STR" : "TYPE=INDEL";
+    s += "\t"; s += std::to_string(r.qual); s += "\t.\t"; s += r.pool ? "." : (r.str ? "TYPE=STR" : "TYPE=INDEL");   // (a pool variant is a plain GenomicVariantImpl, SSVPL:336)
     s += "\tGT:PL:GQ:DP:ADP:ACN\t";
     append_gt(s, r.called, ploidy);
     // VariantCallReport resolves alleles through a TreeMap name->index: with duplicate names the last index wins

@@ -176,7 +176,7 @@ int clear_counts_dbg(Ctx* c, Slot* s) {
 // position with the EMIT_ALL test hook).  Overflow is detected after the run: the list grows and the run is repeated.
 void queue_need(const Ctx* c, const Slot* s, size_t& cols) {
     const size_t len = (size_t)(s->tile.tile_last - s->tile.tile_first + 1);
-    if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1) cols += len + 1024;   // sample axis: every candidate stays open
+    if ((c->params.flags & NGSEP_F_EMIT_ALL) || c->params.n_samples > 1 || c->params.ploidy >= 3) cols += len + 1024;   // sample axis / pools: every candidate stays open
     else cols += len / 32 + 16384;
 }
 // Entry-list capacity: open columns are a fraction of a percent of the positions and hold `depth` entries each, i.e. a few
@@ -249,6 +249,7 @@ int launch_slot(Ctx* c, Slot* s) {
         s->launches = s->tile.n_windows > 0 ? 2 : 1;
     } else if (s->tile.n_windows > 0) {
         if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(s), c->d_prm, c->params.n_samples, c->multi_grid, c->geno_stream);
+        else if (c->hp.pool_ploidy) launch_pool_columns(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         else launch_genotype(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         s->launches = 2;
     }
@@ -300,6 +301,7 @@ int launch_batch(Ctx* c) {
     CK(cudaEventRecord(c->bm, c->stream), "event record");
     if (c->b_windows > 0) {
         if (c->params.n_samples > 1) launch_genotype_multi(c->d_btiles.p, queue_view(c), c->d_prm, c->params.n_samples, c->multi_grid, c->stream);
+        else if (c->hp.pool_ploidy) launch_pool_columns(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
         else launch_genotype(c->d_btiles.p, queue_view(c), c->d_prm, c->geno_grid, c->stream);
     }
     CK(cudaEventRecord(c->b1, c->stream), "event record");
@@ -596,7 +598,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (!out || !params || !tables) { g_global_err = "null argument"; return NGSEP_EINVAL; }
     *out = nullptr;
     if (n_tables != NGSEP_N_TABLES) { g_global_err = "tables must hold NGSEP_N_TABLES doubles"; return NGSEP_EINVAL; }
-    if (params->ploidy >= 3) { g_global_err = "ploidy >= 3 (pool algorithm, SSVPL:240-254) is not on the device path"; return NGSEP_EINVAL; }
+    if (params->ploidy >= 3 && params->n_samples > 1) { g_global_err = "ploidy >= 3 (pool algorithm, SSVPL:240-254) is built for single-sample contexts only"; return NGSEP_EINVAL; }
     if (params->n_samples < 1 || params->n_samples > 65535) { g_global_err = "n_samples must be in 1..65535"; return NGSEP_EINVAL; }
     if (params->max_base_qs < 4 || params->max_base_qs > 30) { g_global_err = "max_base_qs must be in 4..30 (CountsHelper tables have 31 rows)"; return NGSEP_EINVAL; }
     int n_dev = 0;
@@ -691,6 +693,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
         if (row < kTabZeroRow) v = (b == pa || b == pb) ? ((l < 4) ? tables[3 * q] : tables[3 * q + 2]) : tables[3 * q + 1];
         hp.tab2[i] = v;
     }
+    hp.pool_ploidy = params->ploidy >= 3 ? params->ploidy : 0;
     hp.n_samples = params->n_samples;
     hp.column_run = 1;
     if (const char* s = std::getenv("NGSEP_MULTI_RUN")) { int v = std::atoi(s); if (v >= 1 && v <= 256) hp.column_run = v; }
@@ -782,7 +785,7 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
 int ngsep_tile_sites(void* ctx, int32_t n_sites, const int32_t* pos, const uint16_t* alleles) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
-    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites: single-sample contexts only");
+    if (c->params.n_samples > 1 || c->params.ploidy >= 3) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites: single-sample contexts with ploidy < 3 only");
     if (n_sites < 0 || (n_sites > 0 && (!pos || !alleles))) return fail(c, NGSEP_EINVAL, "ngsep_tile_sites: bad arguments");
     for (int32_t k = 0; k < n_sites; k++) {
         const unsigned n_al = (alleles[k] >> 8) & 7u;

@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(kThr, kMinBlocks) k_pileup_windows(const KArgs
                 const uint32_t ref = (wc.s_ref2[rr >> 4] >> ((rr & 15) * 2)) & 3u;
                 int need = (m_up < (uint32_t)kSkipTable) ? min(s_kmin[m_up], kProofNoNeed) : kProofNoNeed;
                 if (need <= 0) need = 1;
-                if (multi) need = kProofNoNeed;   // sample axis: every candidate goes to k_genotype_columns_multi (no proof is attempted)
+                if (multi || prm.pool_ploidy >= 3) need = kProofNoNeed;   // sample axis / pools: every candidate goes to the genotype stage (no hom-ref proof holds there)
                 if (closed) need = 0;
                 s_list[ci] = (uint32_t)li | (ref << kProofRefShift) | ((uint32_t)need << kProofNeedShift) |
                              ((uint32_t)min((int)(ent >> kListShift), kProofMaxRec) << kProofRecShift);
@@ -1283,6 +1283,105 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
             const ngsep_read_hdr h = R.header(i_lo + k);
             return lane_eval(h, R.payload(h), qual, pos, max_qs);
         }, i_hi - i_lo, d, g, pos, ref, ref_bad, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Pools / polyploids (ploidy >= 3): the columns with a supported alternative allele, with their evidence in pileup order
+// ------------------------------------------------------------------------------------------------------------
+// SingleSampleVariantPileupListener.discoverSNV for ploidy >= DEF_MIN_PLOIDY_POOL_ALGORITHM (SSVPL:240-254).  No hom-ref proof holds
+// for the pool genotyper, so every candidate of the screen comes here (as on the sample axis).  The warp counts the column exactly
+// (PR.getAlleleCalls(1) + the quality rules of CH.updateCounts), applies createSNVVariantPool's support rule (SSVPL:306-319: an
+// alternative base needs max(1, 0.5 / ploidy * counted bases) counted bases) — which closes almost every candidate, a lone sequencing
+// error — and hands the surviving columns to the host WITH THEIR COUNTED BASES IN PILEUP ORDER (one byte each: quality << 2 | base):
+// genotypeVariantPool (SSVPL:402-503) needs one CountsHelper per allele-frequency hypothesis and allele list, each a sum over the same
+// reads in the same order, and its posteriors hang on libm; the host's table sums over these bytes are the reference's doubles.
+// A column's record (kind NGSEP_CALL_POOL) holds counts, depth and the first 128 evidence bytes in its logcond field; a deeper column
+// continues in the call slots behind it, 224 bytes each (`sample` = number of evidence bytes).
+constexpr int kPoolInline = 128;
+template <class CodeAt>
+__device__ __forceinline__ void pool_column(CodeAt code_at, int n, const TileDev& d, int pos, int ref, bool ref_bad, int lane, double pool_frac) {
+    ColCounts cc;
+    for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
+    cc.depth = 0;
+    const bool in_regs = n <= 32 * kRegRounds;
+    uint32_t codes[kRegRounds];
+    if (in_regs) {
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) codes[r] = code_at(32 * r + lane);
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) count_round(codes[r], cc);
+    } else {
+        for (int base = 0; base < n; base += 32) count_round(code_at(base + lane), cc);
+    }
+    if (ref_bad || cc.depth == 0) return;                                     // SSVPL:298-305
+    const int sum = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
+    const double min_count = fmax(1.0, pool_frac * (double)sum);              // SSVPL:311
+    bool supported = false;
+    for (int b = 0; b < 4; b++) if (b != ref && (double)cc.c[b] >= min_count) supported = true;
+    if (!supported) return;                                                   // only the reference allele: no variant (SSVPL:322-331)
+    const unsigned int slots = 1u + (unsigned int)((max(0, sum - kPoolInline) + (int)sizeof(ngsep_snv_call) - 1) / (int)sizeof(ngsep_snv_call));
+    unsigned int slot = 0;
+    if (lane == 0) slot = atomicAdd(d.n_calls, slots);
+    slot = __shfl_sync(kFull, slot, 0);
+    if (slot + slots > d.cap_calls) return;   // host sees n_calls > cap, grows the buffer and reruns
+    ngsep_snv_call* o = &d.calls[slot];
+    if (lane == 0) {
+        o->seq_idx = d.seq_idx; o->pos = pos;
+        o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
+        o->depth = cc.depth;
+        for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
+        o->post_ref = 0.0; o->post_max = 0.0; o->gq = 0; o->qual = 0; o->a0 = -1; o->a1 = -1;
+        o->ref = (int8_t)ref; o->kind = (int8_t)NGSEP_CALL_POOL; o->sample = sum;
+    }
+    uint8_t* ev0 = (uint8_t*)o->logcond;            // the first kPoolInline bytes
+    uint8_t* ev1 = (uint8_t*)(o + 1);               // the rest, in the slots behind
+    int written = 0;
+    auto emit_round = [&](uint32_t code) {
+        const bool counted = (code & kCodeCounted) != 0u;
+        const unsigned int m = __ballot_sync(kFull, counted);
+        if (counted) {
+            const int idx = written + __popc(m & ((1u << lane) - 1u));
+            const uint8_t e = (uint8_t)(code & 0x7fu);                        // quality << 2 | base
+            if (idx < kPoolInline) ev0[idx] = e; else ev1[idx - kPoolInline] = e;
+        }
+        written += __popc(m);
+    };
+    if (in_regs) {
+#pragma unroll
+        for (int r = 0; r < kRegRounds; r++) emit_round(codes[r]);
+    } else {
+        for (int base = 0; base < n; base += 32) emit_round(code_at(base + lane));
+    }
+}
+
+__global__ void __launch_bounds__(256, 4) k_pool_columns(const TileDev* __restrict__ tiles, const ColumnQueue cq, const DevParams* __restrict__ gprm) {
+    const DevParams& prm = *gprm;
+    const bool ignore_lower = (prm.flags & NGSEP_F_IGNORE_LOWER_REF) != 0;
+    const int lane = threadIdx.x & 31, max_qs = prm.max_base_qs;
+    const double pool_frac = 0.5 / (double)prm.pool_ploidy;
+    const unsigned int n_open = min(cq.ctr[2], cq.cap_open);
+    const unsigned int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_open; t += n_warps) {
+        const uint4 oc = cq.open[t];
+        const TileDev& d = tiles[oc.x];
+        const int pos = (int)oc.y;
+        const int64_t gi = (int64_t)pos - 1;
+        if (ignore_lower && ((d.ref_l[gi >> 5] >> (gi & 31)) & 1u)) continue;           // SSVPL:198
+        const bool ref_bad = (d.ref_n[gi >> 5] >> (gi & 31)) & 1u;
+        const int ref = (int)((d.ref2[gi >> 4] >> ((gi & 15) * 2)) & 3u);
+        Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        int i_lo = (int)oc.z, i_hi = (int)oc.z + (int)oc.w;
+        if (oc.w >= kOpenSearch) {
+            i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+            i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
+        }
+        const QualView qual(d);
+        pool_column([&](int k) {
+            if (i_lo + k >= i_hi) return 0u;
+            const ngsep_read_hdr h = R.header(i_lo + k);
+            return lane_eval(h, R.payload(h), qual, pos, max_qs);
+        }, i_hi - i_lo, d, pos, ref, ref_bad, lane, pool_frac);
     }
 }
 
@@ -2140,6 +2239,10 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
     static const int min_blocks = [] { const char* e = getenv("NGSEP_GENO_MIN_BLOCKS"); return e ? atoi(e) : 4; }();
     if (min_blocks >= 6) k_genotype_columns<6><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
     else k_genotype_columns<4><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
+}
+
+void launch_pool_columns(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {
+    k_pool_columns<<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
 }
 
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s) {

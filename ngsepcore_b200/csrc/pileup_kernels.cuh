@@ -78,6 +78,7 @@ struct DevParams {
     int max_base_qs, min_quality;
     unsigned int flags;
     int fast_homref;             // 1: the proven hom-ref skips below are valid for these tables / priors
+    int pool_ploidy;             // >= 3: pools / polyploids (SSVPL:240-254): no hom-ref proof, k_pool_columns instead of k_genotype_columns; else 0
     int k_min[16];               // k_min[m]: with m counted non-reference bases, k >= k_min[m] counted reference bases
                                  // prove P(ref,ref) > 1/2; INT_MAX when no k suffices
     double tables[NGSEP_N_TABLES];
@@ -124,6 +125,7 @@ void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, u
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
+void launch_pool_columns(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s);
 // indel / STR allele tallies (k_indel_tallies): device view of ngsep_indel_events
 struct IndelEventsDev {

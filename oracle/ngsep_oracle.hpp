@@ -179,6 +179,8 @@ struct CountsHelper {
     explicit CountsHelper(const std::vector<std::string>& alleles);
     CountsHelper();
     static CountsHelper snv(const std::vector<PileupAlleleCall>& calls, int8_t max_qs, double het_prop);   // CH:83-95
+    static CountsHelper snv_gt(const std::vector<std::string>& alleles, const std::vector<PileupAlleleCall>& calls, int8_t max_qs, double het_prop);   // CH:86-95
+    std::vector<double> posteriors_major(double het_rate, int major) const;        // CH:450-467
     static CountsHelper indel(const std::vector<std::string>& alleles, const std::vector<PileupAlleleCall>& calls, int8_t max_qs, double het_prop);  // CH:96-105
     void update(const std::string& allele, int8_t q, bool neg);                  // CH:209-251
     void update_indel(const std::string& call, const std::string& quals, bool neg);  // CH:253-304
@@ -309,6 +311,9 @@ public:
     bool discover_snv_at(PileupRecord& p, char ref, CalledVariant& out);                         // SSVPL:234-255
     bool discover_with_span(PileupRecord& p, const std::string& ref_allele, CalledVariant& out); // SSVPL:257-273
     CalledVariant genotype_variant_sample(const GenomicVariant& v, PileupRecord& p, const Sample* s, double h);  // SSVPL:361-391
+    // pools / polyploids (ploidy >= DEF_MIN_PLOIDY_POOL_ALGORITHM = 3)
+    CalledVariant genotype_variant_pool(const GenomicVariant& v, short haplotypes, const std::vector<PileupAlleleCall>& calls, double h);   // SSVPL:402-503
+    bool discover_indel(PileupRecord& p, const std::vector<std::string>& alleles, const std::vector<PileupAlleleCall>& calls, CalledVariant& out);   // SSVPL:275-296
 };
 
 // ---- discovery/AlignmentsPileupGenerator.java ---------------------------------
@@ -368,6 +373,8 @@ private:
 // ---- discovery/MultisampleVariantsDetector.java (oracle/ngsep_oracle_multi.cpp) ----------------------------------
 std::vector<std::string> java_string_hashset_order(const std::vector<std::string>& keys_in_insertion_order);
 bool load_samples_from_headers(const std::vector<std::vector<std::string>>& header_lines_per_file, short ploidy, std::vector<Sample>& out, std::string& err);  // MSVD:492-516
+GenomicVariant make_new_variant(const GenomicVariant& v, const std::vector<std::string>& new_alleles);   // SSVPL:346-359 (alleles in iteration order)
+bool alleles_same_length(const std::vector<std::string>& alleles);   // SSVPL:339-345
 bool create_snv_variant_pool(const PileupRecord& p, const CountsHelper& h, char reference, double min_allele_depth_freq, GenomicVariant& out);  // SSVPL:297-332
 std::string english_fmt(double v);   // main/io/ParseUtils.java:29
 std::string diversity_info(size_t n_alleles, const std::vector<std::vector<int8_t>>& called_idx, const std::vector<std::vector<short>>& copy_numbers);  // VCFRecord.java:288-301

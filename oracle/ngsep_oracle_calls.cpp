@@ -131,6 +131,27 @@ CountsHelper CountsHelper::snv(const std::vector<PileupAlleleCall>& calls, int8_
     return h;
 }
 
+CountsHelper CountsHelper::snv_gt(const std::vector<std::string>& al, const std::vector<PileupAlleleCall>& calls, int8_t max_qs, double hp) {  // CH:86-95
+    CountsHelper h(al);
+    if (max_qs > 0) h.max_base_qs = max_qs;
+    h.het_prop = hp;
+    for (auto& c : calls) {
+        int8_t q = (int8_t)std::min(30, (int)(unsigned char)c.quals[0] - 33);
+        h.update(c.allele().substr(0, 1), q, c.neg);
+    }
+    return h;
+}
+
+std::vector<double> CountsHelper::posteriors_major(double het_rate, int major) const {  // CH:450-467
+    int n = (int)alleles.size();
+    double lp_het = std::log10(het_rate / (n - 1));
+    double lp_hom = std::log10(1 - het_rate);
+    std::vector<double> ev((size_t)n);
+    for (int j = 0; j < n; j++) ev[(size_t)j] = logc[(size_t)major][(size_t)j] + (j == major ? lp_hom : lp_het);
+    posterior_from_events(ev);
+    return ev;
+}
+
 CountsHelper CountsHelper::indel(const std::vector<std::string>& al, const std::vector<PileupAlleleCall>& calls, int8_t max_qs, double hp) {  // CH:96-105
     CountsHelper h(al);
     if (max_qs > 0) h.max_base_qs = max_qs;

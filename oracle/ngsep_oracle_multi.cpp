@@ -108,9 +108,16 @@ bool create_snv_variant_pool(const PileupRecord& p, const CountsHelper& h, char 
     return false;
 }
 
-static bool alleles_same_length(const std::vector<std::string>& a) {  // SSVPL:339-345
+bool alleles_same_length(const std::vector<std::string>& a) {  // SSVPL:339-345
     for (auto& s : a) if (s.size() != a[0].size()) return false;
     return true;
+}
+
+GenomicVariant make_new_variant(const GenomicVariant& v, const std::vector<std::string>& new_alleles) {  // SSVPL:346-359
+    std::vector<std::string> alleles = {v.alleles[0]};
+    for (auto& a : new_alleles) if (a != v.alleles[0]) alleles.push_back(a);
+    if (v.is_snv() && alleles.size() == 2) return make_snv_class(v.seq, v.first, v.alleles[0][0], alleles[1][0]);
+    return make_impl_variant(v.seq, v.first, alleles);   // type stays TYPE_UNDETERMINED
 }
 
 static GenomicVariant make_new_variant_static(const GenomicVariant& v, const std::set<std::string>& new_alleles) {  // SSVPL:346-359

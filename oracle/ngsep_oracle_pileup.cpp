@@ -409,15 +409,114 @@ bool SingleSampleVariantPileupListener::discover_snv_at(PileupRecord& p, char re
     auto calls = p.allele_calls(1, (const std::string*)nullptr);
     CountsHelper h = CountsHelper::snv(calls, max_base_qs, 0.5);
     if (counts_dump) counts_dump->push_back({p.pos, h.counts[0], h.counts[1], h.counts[2], h.counts[3], h.total});
-    if (sample.ploidy >= 3) throw std::runtime_error("pool algorithm (ploidy>=3) is out of the oracle's scope");
-    return discover_snv(h, p.seq, p.pos, ref, het_rate, csb, out);
+    if (sample.ploidy < 3) return discover_snv(h, p.seq, p.pos, ref, het_rate, csb, out);
+    // pools / polyploids, SSVPL:240-254
+    GenomicVariant v;
+    if (!create_snv_variant_pool(p, h, ref, 0.5 / (double)sample.ploidy, v)) return false;
+    CalledVariant call = genotype_variant_pool(v, sample.ploidy, calls, het_rate);
+    if (v.is_biallelic()) { out = call; return true; }
+    if (call.undecided() || call.hom_ref()) return false;
+    auto idx = call.called_indexes();
+    if (idx.size() > 2) { out = call; return true; }
+    if (idx.size() == 2 && idx[0] != 0) { out = call; return true; }
+    std::vector<std::string> new_alleles = {v.alleles[0]};   // LinkedHashSet: the reference, then the called alleles
+    for (int8_t i : idx) if (std::find(new_alleles.begin(), new_alleles.end(), v.alleles[(size_t)i]) == new_alleles.end()) new_alleles.push_back(v.alleles[(size_t)i]);
+    GenomicVariant nv = make_new_variant(v, new_alleles);
+    out = genotype_variant_pool(nv, sample.ploidy, calls, het_rate);
+    return true;
+}
+
+bool SingleSampleVariantPileupListener::discover_indel(PileupRecord& p, const std::vector<std::string>& alleles, const std::vector<PileupAlleleCall>& calls, CalledVariant& out) {  // SSVPL:275-296
+    CountsHelper h = CountsHelper::indel(alleles, calls, max_base_qs, 0.5);
+    if (sample.ploidy < 3) return call_indel(p, h, nullptr, het_rate, csb, out);
+    if (h.alleles.size() == 1 || h.total == 0) return false;                      // createIndelVariantPool, SSVPL:333-338
+    GenomicVariant indel;
+    indel.seq = p.seq; indel.first = p.pos; indel.alleles = h.alleles; indel.len = (int)h.alleles[0].size(); indel.last = p.pos + indel.len - 1;
+    if (alleles_same_length(indel.alleles)) return false;
+    CalledVariant call = genotype_variant_pool(indel, sample.ploidy, calls, het_rate);
+    if (indel.is_biallelic()) { out = call; return true; }
+    if (call.undecided() || call.hom_ref()) return false;
+    auto idx = call.called_indexes();
+    if (idx.size() > 2) { out = call; return true; }
+    if (idx.size() == 2 && idx[0] != 0) { out = call; return true; }
+    std::vector<std::string> new_alleles = {indel.alleles[0]};
+    for (int8_t i : idx) if (std::find(new_alleles.begin(), new_alleles.end(), indel.alleles[(size_t)i]) == new_alleles.end()) new_alleles.push_back(indel.alleles[(size_t)i]);
+    GenomicVariant nv = make_new_variant(indel, new_alleles);
+    if (alleles_same_length(nv.alleles)) return false;
+    out = genotype_variant_pool(nv, sample.ploidy, calls, het_rate);
+    return true;
+}
+
+// Simple algorithm based on pool thresholds to genotype a variant in a pool, SSVPL:402-503
+CalledVariant SingleSampleVariantPileupListener::genotype_variant_pool(const GenomicVariant& v, short haplotypes, const std::vector<PileupAlleleCall>& calls, double h) {
+    double step = 1.0 / (double)haplotypes;
+    const std::vector<std::string>& alleles = v.alleles;
+    std::vector<double> freqs;
+    std::vector<CountsHelper> helpers;
+    for (double freq = step; freq < 0.51; freq += step) {
+        freqs.push_back(freq);
+        if (v.is_snv()) helpers.push_back(CountsHelper::snv_gt(alleles, calls, max_base_qs, freq));
+        else helpers.push_back(CountsHelper::indel(alleles, calls, max_base_qs, freq));
+    }
+    const CountsHelper* helper = &helpers[0];
+    const std::vector<int>& counts = helper->counts;
+    int major = -1;
+    for (size_t i = 0; i < counts.size(); i++) if (major == -1 || counts[(size_t)major] < counts[i]) major = (int)i;   // NumberArrays.getIndexMaximum
+    if (counts[(size_t)major] < haplotypes) {
+        CalledVariant u = CalledVariant::make_impl(v, {});
+        u.update_cn_from_counts(haplotypes);
+        return u;
+    }
+    double lp_het = std::log10(h), lp_hom = std::log10(1 - h);
+    std::vector<double> terms(helpers.size() + 1);
+    double term_hom = helper->logc[(size_t)major][(size_t)major] + lp_hom;
+    double max_het_post = 0, min_hom_post = 1, max_freq = 0;
+    int max_freq_idx = 0, max_alt = -1;
+    for (int i = 0; i < (int)alleles.size(); i++) {
+        if (i == major) continue;
+        terms[0] = term_hom;
+        for (size_t j = 0; j < freqs.size(); j++) terms[j + 1] = helpers[j].logc[(size_t)major][(size_t)i] + lp_het;
+        CountsHelper::posterior_from_events(terms);
+        int idx_max = -1;
+        for (size_t k = 0; k < terms.size(); k++) if (idx_max == -1 || terms[(size_t)idx_max] < terms[k]) idx_max = (int)k;
+        if (idx_max == 0) min_hom_post = std::min(min_hom_post, terms[0]);
+        else if (max_alt == -1 || max_het_post < terms[(size_t)idx_max]) {
+            max_het_post = terms[(size_t)idx_max];
+            max_freq_idx = idx_max - 1;
+            max_freq = freqs[(size_t)max_freq_idx];
+            max_alt = i;
+        }
+    }
+    std::vector<int8_t> called = {(int8_t)major};
+    if (max_alt != -1) called.push_back((int8_t)max_alt);
+    std::sort(called.begin(), called.end());
+    CalledVariant call = CalledVariant::make_impl(v, called);
+    call.depth = helper->total;
+    std::vector<short> acn(alleles.size(), 0);
+    if (max_alt == -1) {
+        call.gq = phred_score(1 - min_hom_post);
+        acn[(size_t)major] = haplotypes;
+    } else {
+        helper = &helpers[(size_t)max_freq_idx];
+        auto post = helper->posteriors_major(h, major);
+        call.gq = phred_score(1 - post[(size_t)max_alt]);
+        short alt_cn = (short)java_round(max_freq * haplotypes);
+        if (alt_cn == 0) alt_cn++;
+        else if (alt_cn == haplotypes) alt_cn--;
+        acn[(size_t)max_alt] = alt_cn;
+        acn[(size_t)major] = (short)(haplotypes - alt_cn);
+    }
+    call.alleles_cn = acn;                                   // setAllelesCopyNumber: also the total copy number (Impl:204-226)
+    { int t = 0; for (short c : acn) t += c; call.total_cn = (short)t; }
+    call.has_report = true; call.rep_alleles = alleles; call.rep_counts = counts; call.rep_has_counts = true;   // counts of the FIRST helper (SSVPL:497)
+    call.rep_logc = helper->logc; call.rep_has_logc = true;
+    return call;
 }
 
 bool SingleSampleVariantPileupListener::discover_with_span(PileupRecord& p, const std::string& ref_allele, CalledVariant& out) {  // SSVPL:257-273
     auto calls = p.allele_calls((int)ref_allele.size(), (const std::string*)nullptr);
     auto alleles = cluster_allele_calls(calls, ref_allele, max_base_qs);
-    CountsHelper h = CountsHelper::indel(alleles, calls, max_base_qs, 0.5);  // discoverIndel SSVPL:275-279
-    bool have = call_indel(p, h, nullptr, het_rate, csb, out);
+    bool have = discover_indel(p, alleles, calls, out);
     if (have && (out.undecided() || out.hom_ref() || min_quality > out.gq)) have = false;
     if (!p.input_str() && !have) {
         if (p.new_str) { p.str = false; p.new_str = false; }

@@ -277,3 +277,32 @@ def test_compact_wire_layout_gives_the_full_layout_results(oracle, tmp_path, mon
             ctx.fetch()
         with pytest.raises(capi.NgsepError):                 # n_words (full) smaller than the stream it is expanded from
             ctx.submit(0, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=(1, t["payload"].size - 5))
+
+
+@pytest.mark.parametrize("ploidy,depth,opts,det_kw", [
+    (4, 40, (), {}),
+    (3, 25, ("-minQuality", "20", "-embeddedSNVs"), dict(minQuality=20, embeddedSNVs=True)),
+    (8, 220, ("-maxBaseQS", "25", "-maxAlnsPerStartPos", "0"), dict(maxBaseQS=25, maxAlnsPerStartPos=0)),   # columns deeper than one call slot holds
+])
+def test_pools_and_polyploids(oracle, tmp_path, ploidy, depth, opts, det_kw):
+    """-ploidy >= 3, the pool / polyploid algorithm of SingleSampleVariantPileupListener (SSVPL:240-254, 281-295, 402-503).  No hom-ref
+    proof holds for it: every candidate of the screen reaches k_pool_columns, which counts the column, applies createSNVVariantPool's
+    support rule and hands the surviving columns over with their counted bases in pileup order (NGSEP_CALL_POOL); the host builds the
+    helpers of every allele-frequency hypothesis from them and genotypes the pool.  Whole detector (one tile, many tiles) and the CLI
+    against the oracle, byte for byte; records are ADP-format CalledGenomicVariantImpl records without variant quality."""
+    contigs = [("chrA", 160000), ("chrB", 50000)] if depth < 100 else [("chrA", 30000)]
+    genome, batch, fa, sam = _inputs(tmp_path, contigs, depth=depth, seeds=(511 + ploidy, 512, 513), indel_rate=1e-3, snv_rate=3e-3)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam, args=("-ploidy", str(ploidy)) + opts)
+    body = _body(want)
+    assert len(body) > (300 if depth < 100 else 60) and all(l.split("\t")[8] == "GT:PL:GQ:DP:ADP:ACN" and l.split("\t")[5] == "0" for l in body)
+    det = hostapi.Detector(ploidy=ploidy, **det_kw)
+    det.set_genome(genome)
+    assert det.run(batch) == want
+    assert det.stats().covered_positions == gp
+    tiled = hostapi.Detector(ploidy=ploidy, tile_len=20000, **det_kw)
+    tiled.set_genome(genome)
+    assert tiled.run(batch) == want
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "out")
+    subprocess.check_call([os.path.join(root, "ngsepcore_b200", "ngsep_b200"), "SingleSampleVariantsDetector", "-i", sam, "-r", fa, "-o", out, "-ploidy", str(ploidy)] + list(opts))
+    assert open(out + ".vcf").read() == want

@@ -340,3 +340,25 @@ def test_compact_wire_layout_is_the_full_layout_minus_what_the_device_rebuilds(m
         keep[o + 1 + nb[i]: o + 1 + nb[i] + nw[i]] = False
     assert np.array_equal(full["payload"][keep], comp["payload"])
     assert comp["payload"].nbytes < 0.75 * full["payload"].nbytes
+
+
+@pytest.mark.parametrize("seed,depth,ploidy,opts,det_kw", [
+    (61, 40, 4, (), {}),
+    (71, 25, 3, ("-minQuality", "20"), dict(minQuality=20)),
+    (81, 60, 6, ("-maxBaseQS", "25", "-h", "0.01"), dict(maxBaseQS=25, h=0.01)),
+])
+def test_pool_indel_records_match_oracle(oracle, tmp_path, seed, depth, ploidy, opts, det_kw):
+    """Pools / polyploids (-ploidy >= 3): discoverIndel's pool branch (SSVPL:281-295) — createIndelVariantPool, genotypeVariantPool
+    (SSVPL:402-503) with one CountsHelper per allele-frequency hypothesis k / ploidy, the second round with the reduced allele list —
+    on the host, from the per-call allele tallies.  Host stages only: the indel records (no TYPE: a pool variant is a plain
+    GenomicVariantImpl) against the oracle's; the SNV half needs the device (test_gpu_detector_parity.py::test_pools_and_polyploids)."""
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 80000), ("chrB", 30000)], depth=depth, seeds=(seed, seed + 1, seed + 2), indel_rate=2e-3, snv_rate=3e-3)
+    fa, sam = str(tmp_path / "r.fa"), str(tmp_path / "r.sam")
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    want, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-ploidy", str(ploidy)) + opts)
+    want_lines = [l for l in want.splitlines() if not l.startswith("#") and not _is_snv_record(l)]
+    assert len(want_lines) > 100 and all("TYPE=" not in l and l.split("\t")[5] == "0" for l in want_lines)
+    det = hostapi.Detector(host_only=True, ploidy=ploidy, **det_kw)
+    det.set_genome(genome)
+    assert [l for l in det.run(batch).splitlines() if not l.startswith("#")] == want_lines
