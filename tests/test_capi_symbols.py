@@ -43,7 +43,7 @@ def test_bad_arguments_rejected():
     p = capi.Params(30, 40, 0.001, 2, 0, 1, 0)
     t = capi.host_tables()
     assert lib.ngsep_ctx_create(0, C.byref(p), t.ctypes.data_as(C.POINTER(C.c_double)), 3, C.byref(h)) == -1
-    p3 = capi.Params(30, 40, 0.001, 3, 0, 1, 0)
+    p3 = capi.Params(30, 40, 0.001, 3, 0, 2, 0)      # the pool algorithm (ploidy >= 3) exists for single-sample contexts only
     assert lib.ngsep_ctx_create(0, C.byref(p3), t.ctypes.data_as(C.POINTER(C.c_double)), 95, C.byref(h)) == -1
     assert b"ploidy" in lib.ngsep_last_error(None)
 
