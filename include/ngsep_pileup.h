@@ -152,7 +152,8 @@ typedef struct ngsep_snv_call {
                                   createSNVVariantPool asks for (SSVPL:306-319), for the host's genotypeVariantPool (SSVPL:402-503): count /
                                   depth / strand / ref as always; sample = n, the number of counted bases; their evidence bytes
                                   (quality << 2 | base, pileup order) fill the logcond field (the first 128) and, for a deeper column, the
-                                  ceil((n - 128) / 224) call slots behind this one, which hold nothing else                      */
+                                  ceil((n - 128) / 224) call slots behind this one, which hold nothing else.  A tile with known sites
+                                  (ngsep_tile_sites) returns one such column per site, whatever it holds, post_max = the site's index  */
 #define NGSEP_CALL_SITE 4      /* a known site (ngsep_tile_sites): VD.genotypeSNV, VD:21-97.  a0 <= a1 are indexes into the SITE's allele list
                                   (a0 == a1: homozygous, 0/0 included), -1,-1 = undecided (gq 0: no call, gq == 0, or gq < minQuality, SSVPL:388);
                                   count / depth / logcond as always; sample = index of the site in the list given to ngsep_tile_sites;

@@ -104,7 +104,7 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         n_known_ = 0;
         for (auto& vs : known_) n_known_ += vs.size();
     }
-    if (opt_.ploidy >= 3 && (known_mode() || with_groups())) { err_ = "ploidy >= 3 (the pool algorithm) is built for the discovery mode of SingleSampleVariantsDetector only"; return NGSEP_EINVAL; }
+    if (opt_.ploidy >= 3 && with_groups()) { err_ = "ploidy >= 3 (the pool algorithm) is built for SingleSampleVariantsDetector only"; return NGSEP_EINVAL; }
     if (with_header) out += header_text();
     stats_.records += (uint64_t)b.n;
     // ---- the sequences of the batch, in file order (APG:310-322 for a query sequence) ------------------------------------
@@ -206,7 +206,25 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             }
             snvs.resize(before);
         }
-        if (known) {   // record k of a site tile belongs to site k of the list it was submitted with
+        if (known && opt_.ploidy >= 3) {   // pools: one NGSEP_CALL_POOL column per site (post_max = its index), continuation slots behind
+            std::vector<ngsep_snv_call>& snvs = f.job->snvs;
+            size_t k = before;
+            while (k < snvs.size()) {
+                const ngsep_snv_call& c = snvs[k];
+                const size_t n_ev = (size_t)std::max(0, c.sample), inl = std::min<size_t>(n_ev, 128);
+                const size_t extra = n_ev > 128 ? (n_ev - 128 + sizeof(ngsep_snv_call) - 1) / sizeof(ngsep_snv_call) : 0;
+                const long site = (long)c.post_max;
+                if (c.kind != NGSEP_CALL_POOL || site < 0 || (size_t)site >= f.n_sites || k + extra >= snvs.size()) { err_ = "unexpected record from a tile of known sites"; return NGSEP_ESTATE; }
+                const size_t idx = f.site_base + (size_t)site;
+                f.job->site_calls[idx] = c;
+                f.job->site_have[idx] = 1;
+                f.job->site_ev[idx].resize(n_ev);
+                std::memcpy(f.job->site_ev[idx].data(), c.logcond, inl);
+                if (n_ev > 128) std::memcpy(f.job->site_ev[idx].data() + 128, (const uint8_t*)&snvs[k + 1], n_ev - 128);
+                k += 1 + extra;
+            }
+            snvs.resize(before);
+        } else if (known) {   // record k of a site tile belongs to site k of the list it was submitted with
             std::vector<ngsep_snv_call>& snvs = f.job->snvs;
             for (size_t k = before; k < snvs.size(); k++) {
                 const ngsep_snv_call& c = snvs[k];
@@ -236,7 +254,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         const int64_t tlen = tile_len();
         int tile_no = 0;
         const std::vector<KnownVariant>* kvars = (known && (size_t)seq < known_.size()) ? &known_[(size_t)seq] : nullptr;
-        if (known) { job.site_calls.assign(plan.sites.size(), ngsep_snv_call{}); job.site_have.assign(plan.sites.size(), 0); }
+        if (known) { job.site_calls.assign(plan.sites.size(), ngsep_snv_call{}); job.site_have.assign(plan.sites.size(), 0); job.site_ev.assign(plan.sites.size(), {}); }
         size_t site_next = 0;
         for (int64_t tf = plan.win_first; tf <= plan.win_last; tf += tlen, tile_no++) {
             const int tl = (int)std::min<int64_t>(plan.win_last, tf + tlen - 1);
@@ -349,7 +367,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         }
         for (const KnownVariant& v : kvars) heap.push(v.first);
         IndelCallerOptions kio;
-        kio.max_base_qs = opt_.max_base_qs; kio.het_rate = opt_.het_rate; kio.min_quality = opt_.min_quality; kio.csb = false;
+        kio.max_base_qs = opt_.max_base_qs; kio.het_rate = opt_.het_rate; kio.min_quality = opt_.min_quality; kio.csb = false; kio.ploidy = opt_.ploidy;
         auto locus_at = [&](int pos) -> const StrLocus* {
             auto it = std::upper_bound(loci.begin(), loci.end(), pos, [](int v, const StrLocus& l) { return v < l.first; });
             if (it == loci.begin()) return nullptr;
@@ -412,7 +430,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
                 for (; it != kvars.end() && it->first == e; ++it) {
                     const int vi = (int)(it - kvars.begin());
                     if (it->is_snv) plan.sites.push_back(vi);
-                    else plan.known_indels.push_back({vi, genotype_known_indel_at(e, it->alleles, pileup, kio)});
+                    else plan.known_indels.push_back({vi, opt_.ploidy >= 3 ? genotype_known_indel_pool_at(e, it->alleles, pileup, kio) : genotype_known_indel_at(e, it->alleles, pileup, kio)});
                 }
                 continue;
             }
@@ -579,9 +597,18 @@ void GpuSingleSampleVariantsDetector::emit_known_text(SeqJob& job) {
         if (mine) {
             if (take_site) {
                 const bool have = si < job.site_have.size() && job.site_have[si];
-                if (have || opt_.host_only) {   // (host-only test runs report the host-made records only)
-                    if (!opt_.host_only) { job.text += known_snv_vcf_line(v, &job.site_calls[si], chrom, opt_.ploidy); job.snv_records++; }
-                } else job.text += known_snv_vcf_line(v, nullptr, chrom, opt_.ploidy), job.snv_records++;   // no record of the tile reaches the site
+                if (opt_.host_only) {   // (host-only test runs report the host-made records only)
+                } else if (opt_.ploidy >= 3) {   // the pool branch of genotypeVariantSample (SSVPL:366-370) on the site's column
+                    std::vector<int> al;
+                    for (auto& a : v.alleles) al.push_back(dna_index(a[0]));
+                    const ngsep_snv_call* col = have ? &job.site_calls[si] : nullptr;
+                    SampleIndelCall sc = genotype_known_snv_pool(col, have ? job.site_ev[si].data() : nullptr, al, opt_.ploidy, opt_.het_rate, opt_.min_quality);
+                    job.text += known_pool_snv_vcf_line(v, col, sc, chrom, opt_.ploidy);
+                    job.snv_records++;
+                } else {
+                    job.text += known_snv_vcf_line(v, have ? &job.site_calls[si] : nullptr, chrom, opt_.ploidy);   // (nullptr: no record of the tile reaches the site)
+                    job.snv_records++;
+                }
             } else job.text += known_indel_vcf_line(v, plan.known_indels[ii].second, chrom, opt_.ploidy);
         }
         if (take_site) si++; else ii++;

@@ -261,5 +261,33 @@ std::string pool_snv_vcf_line(int pos, const std::vector<int>& alleles, const Po
     return known_indel_vcf_line(v, sc, chrom, ploidy);
 }
 
+// A known SNV genotyped as a pool (SSVPL:366-370): a CalledGenomicVariantImpl with a call report AND all base counts (setAllCounts), so the
+// record takes the BSDP format; an undecided result of genotypeVariantPool carries neither depth nor report (SSVPL:432-436).
+std::string known_pool_snv_vcf_line(const KnownVariant& v, const ngsep_snv_call* col, const SampleIndelCall& c, const std::string& chrom, int ploidy) {
+    std::string s;
+    record_head(s, v, chrom);
+    s += "\tGT:PL:GQ:DP:BSDP:ACN\t";
+    const size_t n = v.alleles.size();
+    append_gt(s, c.called, ploidy);
+    s += ":";
+    bool firstv = true;
+    for (size_t j = 0; j < n; j++) for (size_t i = 0; i <= j; i++) {
+        if (!firstv) s += ",";
+        firstv = false;
+        s += std::to_string(c.has_report ? jround(-10 * c.logc[i][j]) : 0L);
+    }
+    s += ":"; s += std::to_string(c.gq);
+    s += ":"; s += std::to_string(c.depth);
+    s += ":";
+    for (int i = 0; i < 4; i++) { if (i) s += ","; s += std::to_string(col ? col->count[i] : 0); }
+    std::vector<int> rep(n, 0);
+    if (c.has_report) rep = c.counts;
+    std::vector<int> cn = impl_copy_numbers(c.called, rep, c.has_report, ploidy, n);
+    s += ":";
+    append_copy_numbers(s, cn, c.called.empty(), ploidy);
+    s += "\n";
+    return s;
+}
+
 }  // namespace host
 }  // namespace ngsep_b200

@@ -150,6 +150,10 @@ int call_population_indel_at(int pos, const std::string& ref_allele, bool is_str
 // SSVPL.genotypeVariantSample for a known variant that is not an SNV (SSVPL:378-388): PR.getAlleleCalls(reference allele length) +
 // CountsHelper.calculateCountsIndel over the variant's alleles + VD.callIndel with the variant given, then minQuality => undecided.
 SampleIndelCall genotype_known_indel_at(int pos, const std::vector<std::string>& alleles, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt);
+// ... with ploidy >= 3: the pool branch of genotypeVariantSample (SSVPL:366-377), pool.cpp
+SampleIndelCall genotype_known_snv_pool(const ngsep_snv_call* col, const uint8_t* ev, const std::vector<int>& alleles, int ploidy, double het_rate, int min_quality);
+SampleIndelCall genotype_known_indel_pool_at(int pos, const std::vector<std::string>& alleles, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt);
+std::string known_pool_snv_vcf_line(const KnownVariant& v, const ngsep_snv_call* col, const SampleIndelCall& c, const std::string& chrom, int ploidy);
 // VCF records of a -knownVariants run (SSVD:933-968): c == nullptr: no record gave a call (an undecided call without data, VD:23-27)
 std::string known_snv_vcf_line(const KnownVariant& v, const ngsep_snv_call* c, const std::string& chrom, int ploidy);
 std::string known_indel_vcf_line(const KnownVariant& v, const SampleIndelCall& c, const std::string& chrom, int ploidy);
@@ -272,6 +276,7 @@ struct SeqJob {
     std::vector<PoolColumn> pool_cols;           // ploidy >= 3: the supported columns of the device with their evidence bytes
     std::vector<ngsep_snv_call> site_calls;      // -knownVariants: the device's record of plan.sites[k] (site_have[k] != 0)
     std::vector<char> site_have;
+    std::vector<std::vector<uint8_t>> site_ev;   // ... with ploidy >= 3: the evidence bytes of the site's column
     std::vector<ngsep_pop_site> sites;           // multi-sample device results ...
     std::vector<ngsep_sample_call> scalls;       // ... n_samples per site
     uint64_t snv_records = 0;

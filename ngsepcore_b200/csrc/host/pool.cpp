@@ -237,5 +237,39 @@ bool finish_indel_pool(const SpanEventInput& in, const CallTallies& ct, const In
     return true;
 }
 
+// SSVPL.genotypeVariantSample's pool branch (SSVPL:366-377) + minQuality => undecided (SSVPL:386-388) for a known SNV: col / ev = the site's
+// NGSEP_CALL_POOL column (nullptr: no record reaches the site), alleles = the variant's alleles as base indexes.
+SampleIndelCall genotype_known_snv_pool(const ngsep_snv_call* col, const uint8_t* ev, const std::vector<int>& alleles, int ploidy, double het_rate, int min_quality) {
+    static const uint8_t none = 0;
+    PoolCall call = genotype_pool(snv_helpers(col ? ev : &none, col ? col->sample : 0, col ? col->depth : 0, alleles, ploidy), ploidy, het_rate);
+    SampleIndelCall sc;
+    if (call.undecided) return sc;                      // SSVPL:432-436: no depth, no report
+    sc.called = call.called; sc.gq = call.gq; sc.depth = call.depth; sc.has_report = true; sc.counts = call.counts; sc.logc = call.logc;
+    if (min_quality > sc.gq) { sc.called.clear(); sc.gq = 0; }
+    return sc;
+}
+
+// ... and for a known variant that is not an SNV (SSVPL:376-377): PR.getAlleleCalls(reference allele length) against the variant's alleles
+SampleIndelCall genotype_known_indel_pool_at(int pos, const std::vector<std::string>& alleles, std::vector<HostRead*>& pileup, const IndelCallerOptions& opt) {
+    SpanEventInput in;
+    in.pos = pos; in.ref_allele = alleles[0]; in.alleles = alleles;
+    const int span = (int)alleles[0].size();
+    for (HostRead* r : pileup) {
+        SpanCall c;
+        if (!r->span_call(pos, pos + span - 1, c.allele, c.quals)) continue;
+        c.allele = upper(c.allele);
+        c.neg = r->neg;
+        in.calls.push_back(std::move(c));
+    }
+    CallTallies ct;
+    tally_calls_host(in, opt, ct);
+    PoolCall call = genotype_pool(indel_helpers(ct, alleles.size(), opt.ploidy), opt.ploidy, opt.het_rate);
+    SampleIndelCall sc;
+    if (call.undecided) return sc;
+    sc.called = call.called; sc.gq = call.gq; sc.depth = call.depth; sc.has_report = true; sc.counts = call.counts; sc.logc = call.logc;
+    if (opt.min_quality > sc.gq) { sc.called.clear(); sc.gq = 0; }
+    return sc;
+}
+
 }  // namespace host
 }  // namespace ngsep_b200

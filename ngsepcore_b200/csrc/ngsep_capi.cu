@@ -245,7 +245,8 @@ int launch_slot(Ctx* c, Slot* s) {
     // tile (staging kernels, window kernel) meanwhile.  Genotype launches are ordered among themselves (shared scratch).
     CK(cudaStreamWaitEvent(c->geno_stream, s->em, 0), "wait for the window kernel");
     if (s->tile.site_pos) {   // known sites: genotyped, nothing is discovered (the window kernel has only counted the covered positions)
-        launch_genotype_sites(s->d_tile, c->d_prm, s->tile.n_sites, c->geno_grid, c->geno_stream);
+        if (c->hp.pool_ploidy) launch_pool_sites(s->d_tile, c->d_prm, s->tile.n_sites, c->geno_grid, c->geno_stream);   // pools: the sites' evidence for the host's genotypeVariantPool
+        else launch_genotype_sites(s->d_tile, c->d_prm, s->tile.n_sites, c->geno_grid, c->geno_stream);
         s->launches = s->tile.n_windows > 0 ? 2 : 1;
     } else if (s->tile.n_windows > 0) {
         if (c->params.n_samples > 1) launch_genotype_multi(s->d_tile, queue_view(s), c->d_prm, c->params.n_samples, c->multi_grid, c->geno_stream);
@@ -785,7 +786,7 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
 int ngsep_tile_sites(void* ctx, int32_t n_sites, const int32_t* pos, const uint16_t* alleles) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
-    if (c->params.n_samples > 1 || c->params.ploidy >= 3) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites: single-sample contexts with ploidy < 3 only");
+    if (c->params.n_samples > 1) return fail(c, NGSEP_ESTATE, "ngsep_tile_sites: single-sample contexts only");
     if (n_sites < 0 || (n_sites > 0 && (!pos || !alleles))) return fail(c, NGSEP_EINVAL, "ngsep_tile_sites: bad arguments");
     for (int32_t k = 0; k < n_sites; k++) {
         const unsigned n_al = (alleles[k] >> 8) & 7u;

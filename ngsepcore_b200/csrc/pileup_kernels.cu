@@ -1299,8 +1299,9 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_genotype_columns(const Tile
 // A column's record (kind NGSEP_CALL_POOL) holds counts, depth and the first 128 evidence bytes in its logcond field; a deeper column
 // continues in the call slots behind it, 224 bytes each (`sample` = number of evidence bytes).
 constexpr int kPoolInline = 128;
+// site >= 0: a known site (-knownVariants with ploidy >= 3, SSVPL:366-370): the column is handed over whatever it holds, post_max = site
 template <class CodeAt>
-__device__ __forceinline__ void pool_column(CodeAt code_at, int n, const TileDev& d, int pos, int ref, bool ref_bad, int lane, double pool_frac) {
+__device__ __forceinline__ void pool_column(CodeAt code_at, int n, const TileDev& d, int pos, int ref, bool ref_bad, int lane, double pool_frac, int site = -1) {
     ColCounts cc;
     for (int b = 0; b < 4; b++) { cc.c[b] = 0; cc.sn[b] = 0; }
     cc.depth = 0;
@@ -1314,12 +1315,14 @@ __device__ __forceinline__ void pool_column(CodeAt code_at, int n, const TileDev
     } else {
         for (int base = 0; base < n; base += 32) count_round(code_at(base + lane), cc);
     }
-    if (ref_bad || cc.depth == 0) return;                                     // SSVPL:298-305
     const int sum = cc.c[0] + cc.c[1] + cc.c[2] + cc.c[3];
-    const double min_count = fmax(1.0, pool_frac * (double)sum);              // SSVPL:311
-    bool supported = false;
-    for (int b = 0; b < 4; b++) if (b != ref && (double)cc.c[b] >= min_count) supported = true;
-    if (!supported) return;                                                   // only the reference allele: no variant (SSVPL:322-331)
+    if (site < 0) {
+        if (ref_bad || cc.depth == 0) return;                                 // SSVPL:298-305
+        const double min_count = fmax(1.0, pool_frac * (double)sum);          // SSVPL:311
+        bool supported = false;
+        for (int b = 0; b < 4; b++) if (b != ref && (double)cc.c[b] >= min_count) supported = true;
+        if (!supported) return;                                               // only the reference allele: no variant (SSVPL:322-331)
+    }
     const unsigned int slots = 1u + (unsigned int)((max(0, sum - kPoolInline) + (int)sizeof(ngsep_snv_call) - 1) / (int)sizeof(ngsep_snv_call));
     unsigned int slot = 0;
     if (lane == 0) slot = atomicAdd(d.n_calls, slots);
@@ -1331,7 +1334,7 @@ __device__ __forceinline__ void pool_column(CodeAt code_at, int n, const TileDev
         o->count[0] = cc.c[0]; o->count[1] = cc.c[1]; o->count[2] = cc.c[2]; o->count[3] = cc.c[3];
         o->depth = cc.depth;
         for (int b = 0; b < 4; b++) { o->strand[2 * b] = cc.sn[b]; o->strand[2 * b + 1] = cc.c[b] - cc.sn[b]; }
-        o->post_ref = 0.0; o->post_max = 0.0; o->gq = 0; o->qual = 0; o->a0 = -1; o->a1 = -1;
+        o->post_ref = 0.0; o->post_max = (double)site; o->gq = 0; o->qual = 0; o->a0 = -1; o->a1 = -1;
         o->ref = (int8_t)ref; o->kind = (int8_t)NGSEP_CALL_POOL; o->sample = sum;
     }
     uint8_t* ev0 = (uint8_t*)o->logcond;            // the first kPoolInline bytes
@@ -2239,6 +2242,30 @@ void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevPar
     static const int min_blocks = [] { const char* e = getenv("NGSEP_GENO_MIN_BLOCKS"); return e ? atoi(e) : 4; }();
     if (min_blocks >= 6) k_genotype_columns<6><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
     else k_genotype_columns<4><<<grid, 256, 0, s>>>(d_tiles, cq, dprm);
+}
+
+// -knownVariants with ploidy >= 3: every known SNV site of the tile as an NGSEP_CALL_POOL column (one warp per site)
+__global__ void __launch_bounds__(256, 4) k_pool_sites(const TileDev* __restrict__ tiles, const DevParams* __restrict__ gprm) {
+    const DevParams& prm = *gprm;
+    const TileDev& d = tiles[0];
+    const int lane = threadIdx.x & 31, max_qs = prm.max_base_qs;
+    const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int t = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); t < d.n_sites; t += n_warps) {
+        const int pos = d.site_pos[t];
+        Recs<true> R; R.hdr = d.hdr; R.pay = d.payload; R.pay_base = 0u; R.n = d.n_reads;
+        const int i_lo = warp_lower_bound(R, pos - d.max_span + 1, lane);
+        const int i_hi = warp_lower_bound(R, pos + d.max_back + 1, lane);
+        const QualView qual(d);
+        pool_column([&](int k) {
+            if (i_lo + k >= i_hi) return 0u;
+            const ngsep_read_hdr h = R.header(i_lo + k);
+            return lane_eval(h, R.payload(h), qual, pos, max_qs);
+        }, i_hi - i_lo, d, pos, (int)(d.site_alleles[t] & 3u), false, lane, 0.0, t);
+    }
+}
+
+void launch_pool_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s) {
+    k_pool_sites<<<max(1, min(max_grid, (n_sites + 7) / 8)), 256, 0, s>>>(d_tile, dprm);
 }
 
 void launch_pool_columns(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s) {

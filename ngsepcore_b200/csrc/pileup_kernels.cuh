@@ -125,6 +125,7 @@ void launch_check_headers(ngsep_read_hdr* hdr, const uint32_t* payload, int n, u
 void launch_pileup(const TileDev* d_tiles, const WinRange* d_win, int n_windows, const DevParams* dprm, const ColumnQueue& cq, const LaunchCfg& cfg,
                    int grid, size_t smem, cudaStream_t s);
 void launch_genotype(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
+void launch_pool_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s);
 void launch_pool_columns(const TileDev* d_tiles, const ColumnQueue& cq, const DevParams* dprm, int grid, cudaStream_t s);
 void launch_genotype_sites(const TileDev* d_tile, const DevParams* dprm, int n_sites, int max_grid, cudaStream_t s);
 // indel / STR allele tallies (k_indel_tallies): device view of ngsep_indel_events

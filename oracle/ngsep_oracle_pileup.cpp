@@ -528,13 +528,19 @@ bool SingleSampleVariantPileupListener::discover_with_span(PileupRecord& p, cons
 CalledVariant SingleSampleVariantPileupListener::genotype_variant_sample(const GenomicVariant& v, PileupRecord& p, const Sample* s, double h) {  // SSVPL:361-391
     const std::string& ref_allele = v.alleles[0];
     short ploidy = s ? s->ploidy : sample.ploidy;
-    if (ploidy >= 3) throw std::runtime_error("pool algorithm (ploidy>=3) is out of the oracle's scope");
     auto calls = p.allele_calls((int)ref_allele.size(), s ? &s->read_groups : nullptr);
     CalledVariant cv;
     if (v.is_snv()) {
         CountsHelper hs = CountsHelper::snv(calls, max_base_qs, 0.5);
-        cv = genotype_snv(v, hs, h, false);
-        cv.update_cn_from_counts(ploidy);
+        if (ploidy >= 3) {   // SSVPL:367-370
+            cv = genotype_variant_pool(v, ploidy, calls, h);
+            cv.has_all_counts = true; cv.all_counts = hs.counts;
+        } else {
+            cv = genotype_snv(v, hs, h, false);
+            cv.update_cn_from_counts(ploidy);
+        }
+    } else if (ploidy >= 3) {   // SSVPL:376-377
+        cv = genotype_variant_pool(v, ploidy, calls, h);
     } else {
         CountsHelper hi = CountsHelper::indel(v.alleles, calls, max_base_qs, 0.5);
         call_indel(p, hi, &v, h, false, cv);

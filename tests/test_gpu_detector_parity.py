@@ -197,6 +197,8 @@ def test_known_strs_mode(oracle, tmp_path, opts, det_kw):
 @pytest.mark.parametrize("depth,opts,det_kw", [
     (25, (), {}),
     (3, ("-minQuality", "10", "-maxBaseQS", "25"), dict(minQuality=10, maxBaseQS=25)),     # gaps in the cover, shallow columns, undecided calls
+    (40, ("-ploidy", "4"), dict(ploidy=4)),               # the pool branch of genotypeVariantSample (SSVPL:366-377): sites come back as evidence columns
+    (170, ("-ploidy", "6", "-minQuality", "30", "-maxAlnsPerStartPos", "0"), dict(ploidy=6, minQuality=30, maxAlnsPerStartPos=0)),   # ... deeper than one call slot
 ])
 def test_known_variants_mode(oracle, tmp_path, depth, opts, det_kw):
     """-knownVariants (SSVD:897-905; the genotyping half of the reference's per-sample pipeline, training/runGenotyping): the detector
@@ -206,17 +208,17 @@ def test_known_variants_mode(oracle, tmp_path, depth, opts, det_kw):
     SNVs, SNVs inside indel spans, variants sharing a position, input STRs, uncovered positions and records the reader drops.
     Whole detector (one tile, many tiles, synchronous) and the CLI against the oracle, byte for byte."""
     from tests.known_util import make_known_vcf
-    contigs = [("chrA", 200000), ("chrB", 90000)]
+    contigs = [("chrA", 200000), ("chrB", 90000)] if depth < 100 else [("chrA", 60000), ("chrB", 20000)]
     genome, batch, truth = simulate.simulate(contigs=contigs, depth=depth, seeds=(341, 342, 343), indel_rate=1e-3, snv_rate=2e-3)
     fa, sam, kv = str(tmp_path / "ref.fa"), str(tmp_path / "reads.sam"), str(tmp_path / "known.vcf")
     simulate.write_fasta(fa, genome)
     simulate.write_sam(sam, batch)
     discovered, _, _, _ = ou.run_ssvd(oracle, fa, sam, args=("-minQuality", "0"))
-    assert make_known_vcf(kv, discovered, genome, contigs, np.random.default_rng(depth), extra_per_contig=400) > 1000
+    assert make_known_vcf(kv, discovered, genome, contigs, np.random.default_rng(depth), extra_per_contig=400) > (1000 if depth < 100 else 500)
     want, _, gp, _ = ou.run_ssvd(oracle, fa, sam, args=("-knownVariants", kv) + opts)
     body = _body(want)
     gts = [l.split("\t")[9].split(":")[0] for l in body]
-    assert len(body) > 1000 and gts.count("0/0") > 50 and gts.count("./.") > 20 and sum("," in l.split("\t")[4] for l in body) > 50
+    assert len(body) > (1000 if depth < 100 else 500) and gts.count("0/0") > 50 and gts.count("./.") > 10 and sum("," in l.split("\t")[4] for l in body) > 50
     det = hostapi.Detector(knownVariants=kv, **det_kw)
     det.set_genome(genome)
     assert det.run(batch) == want

@@ -236,6 +236,7 @@ def _is_snv_record(line):
     (4, dict(indel_rate=1e-3, depth=12), (), {}),
     (5, dict(indel_rate=3e-3, depth=2), ("-minQuality", "20"), dict(minQuality=20)),                 # coverage gaps: variants without a pileup, empty pileups
     (6, dict(indel_rate=2e-3, depth=20, indel_jitter=0.6), ("-querySeq", "chrA", "-first", "5000", "-last", "41000"), dict(querySeq="chrA", first=5000, last=41000)),
+    (7, dict(indel_rate=1e-3, depth=30), ("-ploidy", "4"), dict(ploidy=4)),      # the pool branch of genotypeVariantSample (SSVPL:376-377)
 ])
 def test_known_variants_host_records_match_oracle(oracle, tmp_path, seed, kw, opts, det_kw):
     """-knownVariants (SSVD:897-905): the input variants are the realigner's fixed events (IRPL:89-99, 141-157) and every one of them
