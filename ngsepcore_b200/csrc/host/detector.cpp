@@ -11,6 +11,8 @@
 #include <atomic>
 #include <chrono>
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <deque>
@@ -689,7 +691,9 @@ int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, 
     SeqPlan plan;
     int rc = plan_sequence(b, seq, lo, hi, plan);
     if (rc != NGSEP_OK) { err_ = plan.err; return rc; }
+    const double tpk = now_s();
     if (!pack_reads(plan.reads, 0, plan.reads.size(), tile, false, &err_, 0, wire_compact())) return NGSEP_EINVAL;
+    if (std::getenv("NGSEP_TIMING")) std::fprintf(stderr, "pack_sequence: prepass %.4f s, pack %.4f s\n", plan.stats.prepass_s, now_s() - tpk);
     tile_first = plan.win_first;
     tile_last = plan.win_last;
     return NGSEP_OK;

@@ -7,6 +7,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "pipeline.hpp"
 
@@ -130,6 +133,101 @@ QualCoder choose_coder(const bool* seen, int min_bits = 0) {
 }
 inline size_t qual_run_bytes(int L, int bits) { return ((((size_t)L * (size_t)bits + 7) / 8) + 3) & ~(size_t)3; }
 
+// ---- 32 bases / qualities at a time (AVX2, chosen at run time; the 8-at-a-time code above is the portable path) ------------
+#if defined(__x86_64__)
+#define NGSEP_HAVE_AVX2_PATH 1
+inline bool have_avx2() {
+    static const bool on = [] { const char* e = std::getenv("NGSEP_NO_AVX2"); return !(e && std::atoi(e) != 0) && __builtin_cpu_supports("avx2"); }();
+    return on;
+}
+// 32 two-bit values (one per byte of x, each 0..3) -> 64 bits, value k at bits 2k
+__attribute__((target("avx2"))) inline uint64_t squeeze2_avx2(__m256i x) {
+    const __m256i y = _mm256_maddubs_epi16(x, _mm256_set1_epi16(0x0401));        // x0 + 4 x1 per 16-bit element
+    const __m256i z = _mm256_madd_epi16(y, _mm256_set1_epi32(0x00100001));       // y0 + 16 y1 per 32-bit element: one byte of output
+    const __m256i g = _mm256_shuffle_epi8(z, _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                                             0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1));
+    return (uint64_t)(uint32_t)_mm256_extract_epi32(g, 0) | ((uint64_t)(uint32_t)_mm256_extract_epi32(g, 4) << 32);
+}
+// the quality class (qual_class) of 32 quality characters
+__attribute__((target("avx2"))) inline __m256i qual_class_avx2(__m256i c) {
+    __m256i t = _mm256_min_epu8(_mm256_subs_epu8(c, _mm256_set1_epi8(33)), _mm256_set1_epi8(30));
+    return _mm256_and_si256(t, _mm256_cmpgt_epi8(t, _mm256_set1_epi8(3)));
+}
+// bases2 / N mask / low-quality mask of one read (encode_read's arrays, already zeroed)
+__attribute__((target("avx2"))) void encode_bits_avx2(const uint8_t* bases, const uint8_t* quals, int len, uint32_t* b2, uint32_t* nm, uint32_t* lq, uint32_t* any_bad) {
+    const __m256i up = _mm256_set1_epi8((char)0xDF);
+    for (int i = 0; i < len; i += 32) {
+        const int n = std::min(32, len - i);
+        __m256i v, q;
+        if (n == 32) { v = _mm256_loadu_si256((const __m256i*)(bases + i)); q = _mm256_loadu_si256((const __m256i*)(quals + i)); }
+        else {
+            alignas(32) uint8_t tb[32], tq[32];
+            std::memset(tb, 'A', 32); std::memset(tq, 0xff, 32);
+            std::memcpy(tb, bases + i, (size_t)n); std::memcpy(tq, quals + i, (size_t)n);
+            v = _mm256_load_si256((const __m256i*)tb); q = _mm256_load_si256((const __m256i*)tq);
+        }
+        const __m256i u = _mm256_and_si256(v, up);
+        const __m256i ok = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(u, _mm256_set1_epi8('A')), _mm256_cmpeq_epi8(u, _mm256_set1_epi8('C'))),
+                                           _mm256_or_si256(_mm256_cmpeq_epi8(u, _mm256_set1_epi8('G')), _mm256_cmpeq_epi8(u, _mm256_set1_epi8('T'))));
+        const uint32_t bad = ~(uint32_t)_mm256_movemask_epi8(ok);
+        __m256i x = _mm256_and_si256(_mm256_srli_epi16(v, 1), _mm256_set1_epi8(3));          // A 0, C 1, G 3, T 2
+        x = _mm256_xor_si256(x, _mm256_and_si256(_mm256_srli_epi16(x, 1), _mm256_set1_epi8(1)));   // A 0, C 1, G 2, T 3
+        x = _mm256_and_si256(x, ok);                                                           // anything else: code 0, bit in the N mask
+        const uint64_t c = squeeze2_avx2(x);
+        b2[i >> 4] = (uint32_t)c;
+        if (n > 16) b2[(i >> 4) + 1] = (uint32_t)(c >> 32);
+        if (bad) { *any_bad |= bad; nm[i >> 5] = bad; }
+        const __m256i ge37 = _mm256_cmpeq_epi8(_mm256_max_epu8(q, _mm256_set1_epi8(37)), q);
+        lq[i >> 5] = ~(uint32_t)_mm256_movemask_epi8(ge37);
+    }
+}
+// which quality classes occur in q[0, n): bit k of the result = class k
+__attribute__((target("avx2"))) uint32_t scan_classes_avx2(const uint8_t* q, size_t n) {
+    const __m256i bit_lut = _mm256_setr_epi8(1, 2, 4, 8, 16, 32, 64, (char)128, 1, 2, 4, 8, 16, 32, 64, (char)128, 1, 2, 4, 8, 16, 32, 64, (char)128, 1, 2, 4, 8, 16, 32, 64, (char)128);
+    __m256i a0 = _mm256_setzero_si256(), a1 = a0, a2 = a0, a3 = a0;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i cls = qual_class_avx2(_mm256_loadu_si256((const __m256i*)(q + i)));
+        const __m256i bit = _mm256_shuffle_epi8(bit_lut, _mm256_and_si256(cls, _mm256_set1_epi8(7)));
+        const __m256i grp = _mm256_and_si256(_mm256_srli_epi16(cls, 3), _mm256_set1_epi8(3));
+        a0 = _mm256_or_si256(a0, _mm256_and_si256(bit, _mm256_cmpeq_epi8(grp, _mm256_setzero_si256())));
+        a1 = _mm256_or_si256(a1, _mm256_and_si256(bit, _mm256_cmpeq_epi8(grp, _mm256_set1_epi8(1))));
+        a2 = _mm256_or_si256(a2, _mm256_and_si256(bit, _mm256_cmpeq_epi8(grp, _mm256_set1_epi8(2))));
+        a3 = _mm256_or_si256(a3, _mm256_and_si256(bit, _mm256_cmpeq_epi8(grp, _mm256_set1_epi8(3))));
+    }
+    uint32_t m = 0;
+    alignas(32) uint8_t t[4][32];
+    _mm256_store_si256((__m256i*)t[0], a0); _mm256_store_si256((__m256i*)t[1], a1); _mm256_store_si256((__m256i*)t[2], a2); _mm256_store_si256((__m256i*)t[3], a3);
+    for (int g = 0; g < 4; g++) { uint8_t o = 0; for (int k = 0; k < 32; k++) o |= t[g][k]; m |= (uint32_t)o << (8 * g); }
+    for (; i < n; i++) m |= 1u << qual_class(q[i]);
+    return m;
+}
+// the 2- / 4-bit codes of the first (L & ~31) qualities of a read; returns how many qualities it coded (a multiple of 32)
+__attribute__((target("avx2"))) int code_quals_avx2(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* out) {
+    alignas(32) uint8_t tbl[32];
+    for (int k = 0; k < 32; k++) tbl[k] = k < 31 ? qc.code_of[k == 0 ? 33 : 33 + k] : 0;   // (code_of is constant over a class; 33 + k is a member of class k >= 4, 33 of class 0)
+    const __m256i t0 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)tbl)), t1 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)(tbl + 16)));
+    int i = 0;
+    for (; i + 32 <= L; i += 32) {
+        const __m256i cls = qual_class_avx2(_mm256_loadu_si256((const __m256i*)(quals + i)));
+        const __m256i code = _mm256_blendv_epi8(_mm256_shuffle_epi8(t0, cls), _mm256_shuffle_epi8(t1, _mm256_and_si256(cls, _mm256_set1_epi8(15))), _mm256_cmpgt_epi8(cls, _mm256_set1_epi8(15)));
+        if (qc.bits == 2) {
+            const uint64_t c = squeeze2_avx2(code);
+            std::memcpy(out + (i >> 2), &c, 8);
+        } else {
+            const __m256i y = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x1001));   // c0 + 16 c1 per 16-bit element
+            const __m256i pk = _mm256_packus_epi16(y, y);                              // per 128-bit half: its eight bytes, twice
+            const uint64_t lo = (uint64_t)_mm256_extract_epi64(pk, 0), hi = (uint64_t)_mm256_extract_epi64(pk, 2);
+            std::memcpy(out + (i >> 1), &lo, 8);
+            std::memcpy(out + (i >> 1) + 8, &hi, 8);
+        }
+    }
+    return i;
+}
+#else
+inline bool have_avx2() { return false; }
+#endif
+
 // Per-thread output of a contiguous range of reads.
 struct Part {
     std::vector<ngsep_read_hdr> hdr;
@@ -145,27 +243,55 @@ struct Part {
 // bases2 / N mask / low-quality mask of one read, computed once and shared by its versions
 struct ReadBits { uint32_t* b2; uint32_t* nm; uint32_t* lq; int nb, nw; bool has_n; };
 
-void encode_read(const HostRead& r, ReadBits& o) {
-    const int len = r.L;
+void encode_bits(const uint8_t* bases, const uint8_t* quals, int len, ReadBits& o) {
     o.nb = (len + 15) / 16; o.nw = (len + 31) / 32;
     std::memset(o.b2, 0, sizeof(uint32_t) * (size_t)(o.nb + 2 * o.nw));
     o.nm = o.b2 + o.nb; o.lq = o.nm + o.nw;
     uint32_t any_bad = 0;
+#ifdef NGSEP_HAVE_AVX2_PATH
+    if (have_avx2()) { encode_bits_avx2(bases, quals, len, o.b2, o.nm, o.lq, &any_bad); o.has_n = any_bad != 0; return; }
+#endif
     const CodeLut& L = lut();
     for (int i = 0; i < len; i += 8) {
         const int n = std::min(8, len - i);
         uint32_t bad;
-        uint32_t c = encode8(load8(r.bases + i, n, 'A'), &bad);
+        uint32_t c = encode8(load8(bases + i, n, 'A'), &bad);
         if (bad) {   // rare: a base outside ACGT — its code is 0 and its bit goes to the N mask
             c = 0;
-            for (int k = 0; k < n; k++) c |= (uint32_t)(L.v[r.bases[i + k]] & 3u) << (2 * k);
+            for (int k = 0; k < n; k++) c |= (uint32_t)(L.v[bases[i + k]] & 3u) << (2 * k);
             any_bad |= bad;
             o.nm[i >> 5] |= bad << (i & 31);
         }
         o.b2[i >> 4] |= c << ((i & 15) * 2);
-        o.lq[i >> 5] |= lowq8(load8(r.quals + i, n, 0xff)) << (i & 31);
+        o.lq[i >> 5] |= lowq8(load8(quals + i, n, 0xff)) << (i & 31);
     }
     o.has_n = any_bad != 0;
+}
+inline void encode_read(const HostRead& r, ReadBits& o) { encode_bits(r.bases, r.quals, r.L, o); }
+
+// one read's qualities into the tile's quality array (padded run of qual_run_bytes): the bytes, or their 2- / 4-bit codes
+inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* q, size_t padded) {
+    if (qc.bits == 8) {
+        std::memcpy(q, quals, (size_t)L);
+        for (size_t k = (size_t)L; k < padded; k++) q[k] = (uint8_t)'!';
+        return;
+    }
+    int i = 0;
+#ifdef NGSEP_HAVE_AVX2_PATH
+    if (have_avx2()) i = code_quals_avx2(quals, L, qc, q);
+#endif
+    if (qc.bits == 2) {
+        size_t o = (size_t)i >> 2;
+        for (; i + 4 <= L; i += 4, o++)
+            q[o] = (uint8_t)(qc.code_of[quals[i]] | (qc.code_of[quals[i + 1]] << 2) | (qc.code_of[quals[i + 2]] << 4) | (qc.code_of[quals[i + 3]] << 6));
+        if (i < L) { uint8_t b = 0; for (int k = 0; i + k < L; k++) b |= (uint8_t)(qc.code_of[quals[i + k]] << (2 * k)); q[o++] = b; }
+        for (; o < padded; o++) q[o] = 0;
+    } else {
+        size_t o = (size_t)i >> 1;
+        for (; i + 2 <= L; i += 2, o++) q[o] = (uint8_t)(qc.code_of[quals[i]] | (qc.code_of[quals[i + 1]] << 4));
+        if (i < L) q[o++] = qc.code_of[quals[i]];
+        for (; o < padded; o++) q[o] = 0;
+    }
 }
 
 inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out, bool compact) {
@@ -226,23 +352,7 @@ void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const 
         const uint32_t qoff = (uint32_t)(out.n_qual / 4);
         uint8_t* q = out.qual.data() + out.n_qual;
         const size_t padded = qual_run_bytes(r.L, qc.bits);
-        if (qc.bits == 8) {
-            std::memcpy(q, r.quals, (size_t)r.L);
-            for (size_t k = (size_t)r.L; k < padded; k++) q[k] = (uint8_t)'!';
-        } else if (qc.bits == 2) {
-            int i = 0;
-            size_t o = 0;
-            for (; i + 4 <= r.L; i += 4, o++)
-                q[o] = (uint8_t)(qc.code_of[r.quals[i]] | (qc.code_of[r.quals[i + 1]] << 2) | (qc.code_of[r.quals[i + 2]] << 4) | (qc.code_of[r.quals[i + 3]] << 6));
-            if (i < r.L) { uint8_t b = 0; for (int k = 0; i + k < r.L; k++) b |= (uint8_t)(qc.code_of[r.quals[i + k]] << (2 * k)); q[o++] = b; }
-            for (; o < padded; o++) q[o] = 0;
-        } else {
-            int i = 0;
-            size_t o = 0;
-            for (; i + 2 <= r.L; i += 2, o++) q[o] = (uint8_t)(qc.code_of[r.quals[i]] | (qc.code_of[r.quals[i + 1]] << 4));
-            if (i < r.L) q[o++] = qc.code_of[r.quals[i]];
-            for (; o < padded; o++) q[o] = 0;
-        }
+        code_quality_run(r.quals, r.L, qc, q, padded);
         out.n_qual += padded;
         if (r.L > 0xffff) { out.bad = true; continue; }
         encode_read(r, rb);
@@ -269,6 +379,13 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
         range_of(t, a, b);
         unsigned char hit[256];
         std::memset(hit, 0, sizeof hit);
+#ifdef NGSEP_HAVE_AVX2_PATH
+        if (have_avx2()) {   // the classes that occur, each reported through a character of the class (choose_coder only looks at classes)
+            uint32_t m = 0;
+            for (size_t i = a; i < b; i++) m |= scan_classes_avx2(reads[i].quals, (size_t)reads[i].L);
+            for (int k = 0; k < 31; k++) if ((m >> k) & 1u) hit[33 + k] = 1;
+        } else
+#endif
         for (size_t i = a; i < b; i++) { const uint8_t* q = reads[i].quals; const int L = reads[i].L; for (int k = 0; k < L; k++) hit[q[k]] = 1; }
         for (int c = 0; c < 256; c++) seen[(size_t)t][(size_t)c] = hit[c] != 0;
     };

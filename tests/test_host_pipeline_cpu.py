@@ -146,6 +146,30 @@ def test_threaded_packer_equals_single_thread(monkeypatch):
         assert (ref["max_span"], ref["max_back"], ref["aligned_bases"]) == (t["max_span"], t["max_back"], t["aligned_bases"])
 
 
+def test_vector_packer_equals_portable_packer(tmp_path):
+    """The packer codes 32 bases / qualities at a time where the host has AVX2 (chosen at run time); NGSEP_NO_AVX2=1 keeps the
+    portable 8-at-a-time code.  Both give the same bytes: odd read lengths, bases outside ACGT, 2- / 4- / 8-bit quality modes."""
+    import hashlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pack_digest.py"
+    script.write_text(
+        "import sys, hashlib\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from ngsepcore_b200 import hostapi, simulate\n"
+        "for L, qv in ((101, None), (77, (2, 11, 15, 22, 27, 33, 37, 40)), (150, tuple(range(2, 42))), (31, None), (64, None)):\n"
+        "    kw = {} if qv is None else dict(qual_vals=qv)\n"
+        "    genome, batch, _ = simulate.simulate(contigs=[('a', 30000)], depth=12, seeds=(23, 24, 25), n_frac=0.02, read_len=L, indel_rate=1e-3, **kw)\n"
+        "    det = hostapi.Detector(host_only=True); det.set_genome(genome)\n"
+        "    t = det.pack(batch, 0)\n"
+        "    print(L, t['quality'][0], t['layout'], *[hashlib.sha1(t[k].tobytes()).hexdigest() for k in ('hdr', 'payload', 'qual')])\n")
+    outs = []
+    for no_avx2 in ("0", "1"):
+        env = dict(os.environ, NGSEP_NO_AVX2=no_avx2)
+        outs.append(subprocess.run([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, text=True, check=True).stdout)
+    assert outs[0] == outs[1] and len(outs[0].splitlines()) == 5
+    assert {l.split()[1] for l in outs[0].splitlines()} == {"2", "4", "8"}
+
+
 def test_merge_batches_follows_process_files(oracle, tmp_path):
     """hostapi.merge_batches = AlignmentsPileupGenerator.processFiles (APG:212-289): one batch per input file, consumed in the
     reference's order (k-way merge by sequence, first, last; ties to the lowest input).  The oracle reads the three SAM files;
