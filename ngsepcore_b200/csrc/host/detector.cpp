@@ -156,13 +156,13 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         if (rc != NGSEP_OK) return rc;
     }
     // ---- stage 4: ordered merge + text, per sequence ------------------------------------------------------------------------
-    parallel_jobs(jobs.size(), threads, order, [&](size_t k) { if (!jobs[k].plan.reads.empty()) emit_text(jobs[k]); });
+    parallel_jobs(jobs.size(), threads, order, [&](size_t k) { if (!jobs[k].plan.lite.empty()) emit_text(jobs[k]); });
     size_t bytes = 0;
     for (auto& job : jobs) bytes += job.text.size();
     out.reserve(out.size() + bytes);
     for (auto& job : jobs) { out += job.text; stats_.snv_calls += job.snv_records; }
     {   // the plans hold millions of small allocations: release them on the host threads as well
-        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { SeqPlan().reads.swap(jobs[k].plan.reads); });
+        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { std::vector<LiteRead>().swap(jobs[k].plan.lite); std::deque<HostRead>().swap(jobs[k].plan.heavy); });
     }
     stats_.total_s += now_s() - t0;
     return NGSEP_OK;
@@ -251,7 +251,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
     size_t dealt = 0;
     for (auto& job : jobs) {
         SeqPlan& plan = job.plan;
-        if (plan.reads.empty()) continue;
+        if (plan.lite.empty()) continue;
         const int seq = job.seq;
         const int64_t tlen = tile_len();
         int tile_no = 0;
@@ -282,7 +282,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             PackedTile& tile = rings_[dev][(size_t)slot[dev]];
             tile.set_pinned(!opt_.synchronous);
             double tp = now_s();
-            if (!pack_reads(plan.reads, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact())) { drain(); return NGSEP_EINVAL; }
+            if (!pack_plan_reads(plan, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact())) { drain(); return NGSEP_EINVAL; }
             stats_.pack_s += now_s() - tp;
             if (tile.hdr.empty()) continue;
             double td = now_s();
@@ -325,7 +325,7 @@ int GpuSingleSampleVariantsDetector::fetch_tile(void* ctx, SeqJob& job, ngsep_ti
 int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan) {
     const int seq_len = (int)genome_->seqs[seq].size();
     double t0 = now_s();
-    std::vector<HostRead>& reads = plan.reads;
+    std::vector<LiteRead>& reads = plan.lite;
     std::set<int>& suppressed = plan.suppressed;
     // ---- 1. admission -------------------------------------------------------------------------------------------
     AdmissionOptions ao;
@@ -336,8 +336,21 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
         while (q_hi > q_lo && b.first[q_hi - 1] > opt_.query_last) q_hi--;
     }
     if (opt_.has_query) ao.query_first = opt_.query_first;
-    reads = admit_sequence(b, q_lo, q_hi, ao, inner_threads_);
-    for (auto& r : reads) if (r.L > 0xffff || r.st.cigar.size() > 0xff) { plan.err = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout"; return NGSEP_EINVAL; }
+    plan.batch = &b; plan.rec_base = q_lo; plan.ignore5 = opt_.ignore5; plan.ignore3 = opt_.ignore3;
+    plan.heavy.clear();
+    reads = admit_sequence_lite(b, q_lo, q_hi, ao, inner_threads_);
+    static const char* too_long = "read longer than 65535 bases or with more than 255 CIGAR operations: not supported by the device layout";
+    for (const LiteRead& l : reads) if (b.base_off[q_lo + l.rec + 1] - b.base_off[q_lo + l.rec] > 0xffff) { plan.err = too_long; return NGSEP_EINVAL; }
+    // the HostRead of a read, made when the read needs one: any CIGAR but one match block (at admission into the sweep), or the
+    // first event that finds the read in its pileup
+    auto heavy_of = [&](LiteRead& l) -> HostRead* {
+        if (l.heavy < 0) {
+            plan.heavy.push_back(make_read(b, q_lo + l.rec, ao));
+            l.heavy = (int32_t)plan.heavy.size() - 1;
+            plan.heavy.back().derive();
+        }
+        return &plan.heavy[(size_t)l.heavy];
+    };
     plan.stats.admitted += reads.size();
     if (reads.empty()) { plan.win_first = 1; plan.win_last = seq_len; return NGSEP_OK; }
     const int win_first = plan.win_first = opt_.has_query ? std::max(1, opt_.query_first) : 1;
@@ -350,9 +363,12 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     int last_indel_end = 0;                           // SSVPL:143
     {
         std::priority_queue<int, std::vector<int>, std::greater<int>> heap;
-        std::vector<HostRead*> active, pileup;
+        std::vector<uint32_t> active;      // indexes into `reads`
+        std::vector<HostRead*> pileup;
         std::vector<ReadState> before;
         size_t next = 0;
+        auto cur_first = [&](const LiteRead& l) { return l.heavy >= 0 ? plan.heavy[(size_t)l.heavy].st.first : l.first; };
+        auto cur_last = [&](const LiteRead& l) { return l.heavy >= 0 ? plan.heavy[(size_t)l.heavy].st.last : l.last; };
         // -knownSTRs: every input locus is an event at its first position, whether a read anchors an indel there or not, and the
         // positions behind it are embedded (IRPL:89-99); indels inside a locus are not events of their own
         static const std::vector<StrLocus> no_loci;
@@ -377,24 +393,27 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
             return pos <= it->last ? &*it : nullptr;
         };
         while (next < reads.size() || !heap.empty()) {
-            int s = next < reads.size() ? reads[next].admit_first : INT_MAX;
+            int s = next < reads.size() ? reads[next].first : INT_MAX;
             int e = heap.empty() ? INT_MAX : heap.top();
             if (s <= e) {  // every read starting at or before an event is pending when the event is processed (APG:377-403)
-                HostRead& r = reads[next++];
-                r.derive();
-                active.push_back(&r);
-                for (auto& a : r.anchors) heap.push(a.pos);
+                LiteRead& l = reads[next];
+                if (l.heavy == kLiteComplex) {   // (a single match block anchors no indel: nothing to derive)
+                    HostRead* r = heavy_of(l);
+                    if (r->st.cigar.size() > 0xff) { plan.err = too_long; return NGSEP_EINVAL; }
+                    for (auto& a : r->anchors) heap.push(a.pos);
+                }
+                active.push_back((uint32_t)next++);
                 continue;
             }
             while (!heap.empty() && heap.top() == e) heap.pop();
             if (e < win_first || e > win_last) continue;  // no pileup outside the query window (APG:481-484)
             bool prev_covered = false;   // (known variants) was e - 1 under a read?  Then a pileup — an empty one — is still handed out at e
-            if (known && e - 1 >= win_first) for (HostRead* r : active) if (r->st.first <= e - 1 && e - 1 <= r->st.last) { prev_covered = true; break; }
+            if (known && e - 1 >= win_first) for (uint32_t k : active) if (cur_first(reads[k]) <= e - 1 && e - 1 <= cur_last(reads[k])) { prev_covered = true; break; }
             size_t w = 0;
-            for (size_t k = 0; k < active.size(); k++) if (active[k]->st.last >= e) active[w++] = active[k];  // APG:464-471
+            for (size_t k = 0; k < active.size(); k++) if (cur_last(reads[active[k]]) >= e) active[w++] = active[k];  // APG:464-471
             active.resize(w);
             pileup.clear();
-            for (HostRead* r : active) if (r->st.first <= e && e <= r->st.last) pileup.push_back(r);       // PR:154-156
+            for (uint32_t k : active) if (cur_first(reads[k]) <= e && e <= cur_last(reads[k])) pileup.push_back(heavy_of(reads[k]));       // PR:154-156
             const StrLocus* locus = locus_at(e);
             // inside an input locus: embedded, the realigner does nothing (IRPL:96-98)
             bool realign = !(locus && !(locus->starter && locus->first == e));
@@ -466,7 +485,9 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     // reach of every read over all of its versions, to pick the records of a tile (halo = read span)
     plan.max_reach = 1;
     plan.max_back = 0;
-    for (const HostRead& r : reads) {
+    for (const LiteRead& l : reads) {
+        if (l.heavy < 0) { plan.max_reach = std::max(plan.max_reach, l.last - l.first + 1); continue; }
+        const HostRead& r = plan.heavy[(size_t)l.heavy];
         int lastp = r.st.last, firstp = r.st.first;
         for (auto& v : r.closed) { lastp = std::max(lastp, v.st.last); firstp = std::min(firstp, v.st.first); }
         plan.max_reach = std::max(plan.max_reach, lastp - r.admit_first + 1);
@@ -578,9 +599,9 @@ void GpuSingleSampleVariantsDetector::resolve_fired_events(SeqPlan& plan) {
 }
 
 void GpuSingleSampleVariantsDetector::tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const {
-    const auto& reads = plan.reads;
-    r_lo = std::lower_bound(reads.begin(), reads.end(), tf - plan.max_reach + 1, [](const HostRead& r, int v) { return r.admit_first < v; }) - reads.begin();
-    r_hi = std::upper_bound(reads.begin(), reads.end(), tl + plan.max_back, [](int v, const HostRead& r) { return v < r.admit_first; }) - reads.begin();
+    const auto& reads = plan.lite;
+    r_lo = std::lower_bound(reads.begin(), reads.end(), tf - plan.max_reach + 1, [](const LiteRead& r, int v) { return r.first < v; }) - reads.begin();
+    r_hi = std::upper_bound(reads.begin(), reads.end(), tl + plan.max_back, [](int v, const LiteRead& r) { return v < r.first; }) - reads.begin();
 }
 
 // -knownVariants: one record per input variant that met a pileup, in the order of the input list (the listener appends them in that
@@ -689,10 +710,11 @@ int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, 
     int64_t hi = lo;
     while (hi < b.n && b.seq_idx[hi] == seq) hi++;
     SeqPlan plan;
+    inner_threads_ = host_threads();   // one sequence: its admission may use every host thread
     int rc = plan_sequence(b, seq, lo, hi, plan);
     if (rc != NGSEP_OK) { err_ = plan.err; return rc; }
     const double tpk = now_s();
-    if (!pack_reads(plan.reads, 0, plan.reads.size(), tile, false, &err_, 0, wire_compact())) return NGSEP_EINVAL;
+    if (!pack_plan_reads(plan, 0, plan.lite.size(), tile, false, &err_, 0, wire_compact())) return NGSEP_EINVAL;
     if (std::getenv("NGSEP_TIMING")) std::fprintf(stderr, "pack_sequence: prepass %.4f s, pack %.4f s\n", plan.stats.prepass_s, now_s() - tpk);
     tile_first = plan.win_first;
     tile_last = plan.win_last;

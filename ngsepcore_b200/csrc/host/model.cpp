@@ -355,6 +355,127 @@ std::vector<HostRead> admit_range(const BatchView& b, int64_t lo, int64_t hi, co
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------
+// admission without materialising the reads
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+inline bool flagged_multiple(const BatchView& b, int64_t i, int min_mq) {   // RAFR:229-236, 284-291
+    const int flags = b.flags[i];
+    const int nh = b.nh ? b.nh[i] : -1;
+    if (flags & 0x100) return true;
+    if (nh > 1) return true;
+    if (nh == 1) return false;
+    return b.mapq[i] < min_mq;
+}
+
+std::vector<LiteRead> admit_range_lite(const BatchView& b, int64_t base, int64_t lo, int64_t hi, const AdmissionOptions& opt) {
+    std::vector<LiteRead> out;
+    out.reserve((size_t)(hi - lo));
+    int filter = 0x4;
+    if (!opt.secondary) { filter |= 0x100; if (!opt.non_unique_primary) filter |= 0x1000; }
+    int64_t last_seen = -1;
+    struct Pending { LiteRead l; int rg; };
+    std::vector<Pending> prim, sec;
+    int group_start = INT_MIN;
+    std::vector<std::pair<int, int>> per_rg;
+    auto flush = [&]() {
+        per_rg.clear();
+        for (auto* lst : {&prim, &sec}) {
+            for (auto& r : *lst) {
+                auto it = per_rg.begin();
+                while (it != per_rg.end() && it->first != r.rg) ++it;
+                if (it == per_rg.end()) per_rg.emplace_back(r.rg, 1);
+                else if (opt.max_alns_per_start <= 0 || it->second < opt.max_alns_per_start) it->second++;
+                else continue;
+                out.push_back(r.l);
+            }
+        }
+        prim.clear();
+        sec.clear();
+    };
+    for (int64_t i = lo; i < hi; i++) {
+        int flags = b.flags[i];
+        if (last_seen >= 0 && b.name_hash) {   // duplicate record (RAFR:292-306)
+            const int pf = b.flags[last_seen];
+            const bool same = b.first[last_seen] == b.first[i] && ((pf & 1) == (flags & 1)) && (!(pf & 1) || ((pf & 0x40) == (flags & 0x40))) &&
+                              b.name_hash[last_seen] == b.name_hash[i];
+            if (same) continue;
+        }
+        last_seen = i;
+        if (flagged_multiple(b, i, opt.min_mq)) flags |= 0x1000;
+        if (flags & filter) continue;
+        const int64_t c0 = b.cigar_off[i], c1 = b.cigar_off[i + 1];
+        if (c1 <= c0) continue;
+        const int L = (int)(b.base_off[i + 1] - b.base_off[i]);
+        int read_len = 0, ref_len = 0;
+        for (int64_t k = c0; k < c1; k++) {
+            const uint32_t v = b.cigar[k];
+            if (cig_read(v)) read_len += cig_len(v);
+            if (cig_ref(v)) ref_len += cig_len(v);
+        }
+        if (read_len != L || L == 0) continue;
+        Pending p;
+        p.l.rec = (int32_t)(i - base);
+        p.l.first = b.first[i];
+        p.l.last = p.l.first + ref_len - 1;
+        p.l.heavy = (c1 - c0 == 1 && cig_op(b.cigar[c0]) == kOpM) ? kLiteSimple : kLiteComplex;
+        p.rg = b.rg ? b.rg[i] : -1;
+        if (opt.query_first > p.l.last) continue;  // APG:316
+        if (p.l.first != group_start) { flush(); group_start = p.l.first; }
+        if (flags & 0x100) sec.push_back(p); else prim.push_back(p);
+    }
+    flush();
+    return out;
+}
+}  // namespace
+
+HostRead make_read(const BatchView& b, int64_t i, const AdmissionOptions& opt) {
+    HostRead r;
+    const int flags = b.flags[i];
+    r.rec = i;
+    r.L = (int)(b.base_off[i + 1] - b.base_off[i]);
+    r.neg = (flags & 0x10) != 0;
+    r.unique = !flagged_multiple(b, i, opt.min_mq);
+    r.rg = b.rg ? b.rg[i] : -1;
+    r.bases = b.bases + b.base_off[i];
+    r.quals = b.quals + b.base_off[i];
+    r.admit_first = r.st.first = b.first[i];
+    int ref_len = 0;
+    for (int64_t k = b.cigar_off[i]; k < b.cigar_off[i + 1]; k++) {   // equal neighbouring operations collapse (RA:1296-1312)
+        const uint32_t v = b.cigar[k];
+        if (!r.st.cigar.empty() && cig_op(r.st.cigar.back()) == cig_op(v)) r.st.cigar.back() = cig_make(cig_len(r.st.cigar.back()) + cig_len(v), cig_op(v));
+        else r.st.cigar.push_back(v);
+        if (cig_ref(v)) ref_len += cig_len(v);
+    }
+    r.st.last = r.st.first + ref_len - 1;
+    if (r.neg) { r.st.ign_e = opt.ignore5; r.st.ign_s = opt.ignore3; } else { r.st.ign_s = opt.ignore5; r.st.ign_e = opt.ignore3; }   // RA:613-644
+    return r;
+}
+
+std::vector<LiteRead> admit_sequence_lite(const BatchView& b, int64_t lo, int64_t hi, const AdmissionOptions& opt, int threads) {
+    const int64_t n = hi - lo;
+    if (threads < 2 || n < 400000) return admit_range_lite(b, lo, lo, hi, opt);
+    const int nt = (int)std::min<int64_t>(threads, n / 100000);
+    std::vector<int64_t> cut((size_t)nt + 1);
+    cut[0] = lo; cut[(size_t)nt] = hi;
+    for (int t = 1; t < nt; t++) {
+        int64_t c = std::max(cut[(size_t)t - 1], lo + n * t / nt);
+        while (c < hi && c > lo && b.first[c] == b.first[c - 1]) c++;   // never inside the records of one start position
+        cut[(size_t)t] = c;
+    }
+    std::vector<std::vector<LiteRead>> parts((size_t)nt);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back([&, t]() { parts[(size_t)t] = admit_range_lite(b, lo, cut[(size_t)t], cut[(size_t)t + 1], opt); });
+    parts[0] = admit_range_lite(b, lo, cut[0], cut[1], opt);
+    for (auto& x : th) x.join();
+    size_t total = 0;
+    for (auto& p : parts) total += p.size();
+    std::vector<LiteRead> out;
+    out.reserve(total);
+    for (auto& p : parts) out.insert(out.end(), p.begin(), p.end());
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // several inputs: APG.processFiles
 // ------------------------------------------------------------------------------------------------------------
 namespace {

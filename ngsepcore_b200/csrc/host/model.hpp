@@ -111,6 +111,20 @@ std::vector<HostRead> admit_sequence(const BatchView& b, int64_t rec_lo, int64_t
 // out: (input, record) pairs in consumption order.
 void merge_order(const std::vector<BatchView>& inputs, const AdmissionOptions& opt, std::vector<std::pair<int, int64_t>>& out);
 
+// The admitted reads of a sequence as the detectors keep them: 16 bytes per read.  Almost every read is one match block that no
+// event of the realigner pre-pass ever touches; such a read needs no HostRead at all (the packer takes it straight from the
+// batch).  Reads with any other CIGAR, and the reads under an event, are materialised (SeqPlan::heavy).
+struct LiteRead {
+    int32_t rec = 0;               // record index relative to the first record of the sequence in the batch
+    int32_t first = 0, last = 0;   // reference span at admission; first is the ordering key of the pileup
+    int32_t heavy = -1;            // >= 0: index of the read's HostRead; kLiteSimple: one match block, untouched; kLiteComplex: any other CIGAR, not materialised yet
+};
+constexpr int32_t kLiteSimple = -1, kLiteComplex = -2;
+// admit_sequence's decisions (same filters, same order) without building the reads
+std::vector<LiteRead> admit_sequence_lite(const BatchView& b, int64_t rec_lo, int64_t rec_hi, const AdmissionOptions& opt, int threads = 1);
+// the HostRead admit_sequence builds for record rec
+HostRead make_read(const BatchView& b, int64_t rec, const AdmissionOptions& opt);
+
 inline int dna_index(char c) {
     switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; }
     return -1;

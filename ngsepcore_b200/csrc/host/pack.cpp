@@ -6,7 +6,12 @@
 #include <climits>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
+#include <pthread.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
 #endif
@@ -57,6 +62,66 @@ int host_threads() {
 }
 
 namespace {
+
+// f(0) .. f(n - 1) on the calling thread and up to n - 1 helpers.  The helpers are threads that live as long as the process (a tile
+// is packed in three short parallel steps: starting and joining sixteen threads for each of them cost as much as a sixth of the
+// packing itself); a second caller at the same time, or a child process after fork(), starts its own threads as before.
+class Helpers {
+public:
+    void run(int n, const std::function<void(int)>& f) {
+        if (n <= 1) { if (n == 1) f(0); return; }
+        std::unique_lock<std::mutex> own(owner_, std::try_to_lock);
+        if (!own.owns_lock() || dead_.load()) { spawn(n, f); return; }
+        grow(n - 1);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = &f; n_ = n; next_.store(1); left_ = n - 1; gen_++;
+        }
+        cv_.notify_all();
+        f(0);
+        for (;;) { const int k = next_.fetch_add(1); if (k >= n) break; f(k); finish_one(); }
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [&] { return left_ == 0 && in_job_ == 0; });   // (no helper still holds the job: f dies with this call)
+        job_ = nullptr;
+    }
+    static Helpers& get() { static Helpers* h = new Helpers(); return *h; }   // (never destroyed: its threads may outlive static destructors)
+private:
+    Helpers() { pthread_atfork(nullptr, nullptr, [] { get().dead_.store(true); }); }
+    static void spawn(int n, const std::function<void(int)>& f) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < n; t++) th.emplace_back(f, t);
+        f(0);
+        for (auto& x : th) x.join();
+    }
+    void grow(int want) {
+        while ((int)threads_.size() < want) { threads_.emplace_back([this] { loop(); }); threads_.back().detach(); }
+    }
+    void finish_one() { std::lock_guard<std::mutex> g(m_); if (--left_ == 0 && in_job_ == 0) done_.notify_all(); }
+    void loop() {
+        unsigned long seen = 0;
+        for (;;) {
+            const std::function<void(int)>* job;
+            int n;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_; job = job_; n = n_;
+                if (job) in_job_++;
+            }
+            if (!job) continue;
+            for (;;) { const int k = next_.fetch_add(1); if (k >= n) break; (*job)(k); finish_one(); }
+            { std::lock_guard<std::mutex> g(m_); if (--in_job_ == 0 && left_ == 0) done_.notify_all(); }
+        }
+    }
+    std::mutex owner_, m_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    const std::function<void(int)>* job_ = nullptr;
+    int n_ = 0, left_ = 0, in_job_ = 0;
+    unsigned long gen_ = 0;
+    std::atomic<int> next_{0};
+    std::atomic<bool> dead_{false};
+};
 
 struct CodeLut {
     uint8_t v[256];
@@ -112,12 +177,14 @@ struct QualCoder {
     int bits = 8;
     uint8_t code_of[256];
     uint8_t dict[16];
+    alignas(32) uint8_t class_code[32];   // the code of quality class k (qual_class), for the 32-at-a-time coder
 };
 inline int qual_class(int c) { const int q = c - 33; return q <= 3 ? 0 : std::min(30, q); }
 QualCoder choose_coder(const bool* seen, int min_bits = 0) {
     QualCoder qc;
     std::memset(qc.code_of, 0, sizeof qc.code_of);
     std::memset(qc.dict, 0, sizeof qc.dict);
+    std::memset(qc.class_code, 0, sizeof qc.class_code);
     bool present[31] = {false};
     for (int c = 0; c < 256; c++) if (seen[c]) present[qual_class(c)] = true;
     int n = 0, code_of_class[31];
@@ -129,6 +196,7 @@ QualCoder choose_coder(const bool* seen, int min_bits = 0) {
     if (bits == 8) return qc;
     for (int k = 0; k < 31; k++) if (code_of_class[k] >= 0) qc.dict[code_of_class[k]] = (uint8_t)(k == 0 ? 35 : 33 + k);
     for (int c = 0; c < 256; c++) { const int k = code_of_class[qual_class(c)]; qc.code_of[c] = (uint8_t)(k < 0 ? 0 : k); }
+    for (int k = 0; k < 32; k++) qc.class_code[k] = (uint8_t)((k < 31 && code_of_class[k] >= 0) ? code_of_class[k] : 0);
     return qc;
 }
 inline size_t qual_run_bytes(int L, int bits) { return ((((size_t)L * (size_t)bits + 7) / 8) + 3) & ~(size_t)3; }
@@ -204,9 +272,7 @@ __attribute__((target("avx2"))) uint32_t scan_classes_avx2(const uint8_t* q, siz
 }
 // the 2- / 4-bit codes of the first (L & ~31) qualities of a read; returns how many qualities it coded (a multiple of 32)
 __attribute__((target("avx2"))) int code_quals_avx2(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* out) {
-    alignas(32) uint8_t tbl[32];
-    for (int k = 0; k < 32; k++) tbl[k] = k < 31 ? qc.code_of[k == 0 ? 33 : 33 + k] : 0;   // (code_of is constant over a class; 33 + k is a member of class k >= 4, 33 of class 0)
-    const __m256i t0 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)tbl)), t1 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)(tbl + 16)));
+    const __m256i t0 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)qc.class_code)), t1 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)(qc.class_code + 16)));
     int i = 0;
     for (; i + 32 <= L; i += 32) {
         const __m256i cls = qual_class_avx2(_mm256_loadu_si256((const __m256i*)(quals + i)));
@@ -267,7 +333,6 @@ void encode_bits(const uint8_t* bases, const uint8_t* quals, int len, ReadBits& 
     }
     o.has_n = any_bad != 0;
 }
-inline void encode_read(const HostRead& r, ReadBits& o) { encode_bits(r.bases, r.quals, r.L, o); }
 
 // one read's qualities into the tile's quality array (padded run of qual_run_bytes): the bytes, or their 2- / 4-bit codes
 inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* q, size_t padded) {
@@ -294,16 +359,16 @@ inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, u
     }
 }
 
-inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out, bool compact) {
-    const int len = r.L;
-    const int nc = (int)st.cigar.size();
+// One record of the tile.  admit_first: the ordering start; cigar / nc / st_first / ign_*: the read state the record describes
+inline bool emit_record(int admit_first, int len, bool neg, const uint32_t* cigar, int nc, int st_first, int ign_s, int ign_e, const ReadBits& rb, bool windowed, int from,
+                        int to, uint32_t qoff, Part& out, bool compact) {
     if (len > 0xffff || nc > 0xff) { out.bad = true; return false; }
     ngsep_read_hdr h;
-    h.first = r.admit_first;
-    h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (r.neg ? NGSEP_M_NEG : 0u) | (rb.has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
-    if (nc == 1 && !rb.has_n && !windowed && st.cigar[0] == (((uint32_t)len << 3) | 3u)) h.meta |= NGSEP_M_SIMPLE;
-    h.ign_start = (int16_t)st.ign_s;
-    h.ign_end = (int16_t)st.ign_e;
+    h.first = admit_first;
+    h.meta = (uint32_t)len | ((uint32_t)nc << 16) | (neg ? NGSEP_M_NEG : 0u) | (rb.has_n ? NGSEP_M_NMASK : 0u) | (windowed ? NGSEP_M_WINDOW : 0u);
+    if (nc == 1 && !rb.has_n && !windowed && cigar[0] == (((uint32_t)len << 3) | 3u)) h.meta |= NGSEP_M_SIMPLE;
+    h.ign_start = (int16_t)ign_s;
+    h.ign_end = (int16_t)ign_e;
     h.off = (uint32_t)out.n_pay;
     out.hdr[out.n_hdr++] = h;
     uint32_t* p = out.payload.data() + out.n_pay;
@@ -312,33 +377,68 @@ inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& 
         // NGSEP_LAYOUT_COMPACT: the CIGAR word and the low-quality mask of a single-block record are rebuilt on the device
         std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
     } else {
-        if (windowed) { *p++ = (uint32_t)from; *p++ = (uint32_t)to; *p++ = (uint32_t)st.first; }
-        for (int k = 0; k < nc; k++) *p++ = st.cigar[(size_t)k];
+        if (windowed) { *p++ = (uint32_t)from; *p++ = (uint32_t)to; *p++ = (uint32_t)st_first; }
+        for (int k = 0; k < nc; k++) *p++ = cigar[(size_t)k];
         std::memcpy(p, rb.b2, sizeof(uint32_t) * (size_t)rb.nb); p += rb.nb;
         if (rb.has_n) { std::memcpy(p, rb.nm, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw; }
         std::memcpy(p, rb.lq, sizeof(uint32_t) * (size_t)rb.nw); p += rb.nw;
     }
     *p++ = qoff;
     out.n_pay = (size_t)(p - out.payload.data());
-    out.max_span = std::max(out.max_span, ref_last_of(st) - r.admit_first + 1);
-    out.max_back = std::max(out.max_back, r.admit_first - st.first);
+    int ref_last = st_first - 1;
+    for (int k = 0; k < nc; k++) if (cig_ref(cigar[k])) ref_last += cig_len(cigar[k]);
+    out.max_span = std::max(out.max_span, ref_last - admit_first + 1);
+    out.max_back = std::max(out.max_back, admit_first - st_first);
     out.aligned_bases += (uint64_t)len;
     return true;
 }
+inline bool emit_record(const HostRead& r, const ReadState& st, const ReadBits& rb, bool windowed, int from, int to, uint32_t qoff, Part& out, bool compact) {
+    return emit_record(r.admit_first, r.L, r.neg, st.cigar.data(), (int)st.cigar.size(), st.first, st.ign_s, st.ign_e, rb, windowed, from, to, qoff, out, compact);
+}
 
-void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const QualCoder& qc, Part& out, bool compact) {
+// What the packer walks.  Read i of a source is a HostRead (any CIGAR, realigner versions) or — heavy(i) == nullptr — an untouched
+// single-block read that exists only as a record of the batch (PlainRead).
+struct PlainRead { int first = 0, L = 0, rg = -1; bool neg = false; int ign_s = 0, ign_e = 0; const uint8_t* bases = nullptr; const uint8_t* quals = nullptr; };
+struct VectorSource {
+    const std::vector<HostRead>* v;
+    const HostRead* heavy(size_t i) const { return &(*v)[i]; }
+    PlainRead plain(size_t) const { return PlainRead(); }
+};
+struct PlanSource {
+    const SeqPlan* p;
+    const HostRead* heavy(size_t i) const { const int32_t h = p->lite[i].heavy; return h >= 0 ? &p->heavy[(size_t)h] : nullptr; }
+    PlainRead plain(size_t i) const {
+        const LiteRead& l = p->lite[i];
+        const BatchView& b = *p->batch;
+        const int64_t rec = p->rec_base + l.rec;
+        PlainRead r;
+        r.first = l.first; r.L = l.last - l.first + 1; r.rg = b.rg ? b.rg[rec] : -1;
+        r.neg = (b.flags[rec] & 0x10) != 0;
+        if (r.neg) { r.ign_e = p->ignore5; r.ign_s = p->ignore3; } else { r.ign_s = p->ignore5; r.ign_e = p->ignore3; }   // RA:613-644
+        r.bases = b.bases + b.base_off[rec];
+        r.quals = b.quals + b.base_off[rec];
+        return r;
+    }
+};
+
+template <typename Src>
+void pack_range(const Src& src, size_t lo, size_t hi, const QualCoder& qc, Part& out, bool compact) {
     out.n_hdr = out.n_pay = out.n_qual = out.n_full = 0;
     out.max_span = 1; out.max_back = 0; out.aligned_bases = 0; out.bad = false;
     size_t n_rec = 0, n_words = 0, n_q = 0;
     int max_len = 0;
     for (size_t i = lo; i < hi; i++) {   // exact upper bounds: one reservation per array
-        const HostRead& r = reads[i];
-        const size_t per = 3 + (size_t)((r.L + 15) / 16) + 2 * (size_t)((r.L + 31) / 32) + 1;
-        const bool plain = r.closed.empty() && r.st.first == r.admit_first;
-        size_t rec = 1, cig = r.st.cigar.size();
-        if (!plain) { rec += r.closed.size(); for (const Version& v : r.closed) cig += v.st.cigar.size(); }
-        n_rec += rec; n_words += rec * per + cig; n_q += qual_run_bytes(r.L, qc.bits);
-        max_len = std::max(max_len, r.L);
+        const HostRead* hr = src.heavy(i);
+        const int L = hr ? hr->L : src.plain(i).L;
+        const size_t per = 3 + (size_t)((L + 15) / 16) + 2 * (size_t)((L + 31) / 32) + 1;
+        size_t rec = 1, cig = 1;
+        if (hr) {
+            cig = hr->st.cigar.size();
+            const bool plain = hr->closed.empty() && hr->st.first == hr->admit_first;
+            if (!plain) { rec += hr->closed.size(); for (const Version& v : hr->closed) cig += v.st.cigar.size(); }
+        }
+        n_rec += rec; n_words += rec * per + cig; n_q += qual_run_bytes(L, qc.bits);
+        max_len = std::max(max_len, L);
     }
     if (out.hdr.size() < n_rec) out.hdr.resize(n_rec + n_rec / 8);
     if (out.payload.size() < n_words) out.payload.resize(n_words + n_words / 8);
@@ -347,24 +447,34 @@ void pack_range(const std::vector<HostRead>& reads, size_t lo, size_t hi, const 
     ReadBits rb{};
     rb.b2 = scratch.data();
     for (size_t i = lo; i < hi; i++) {
-        const HostRead& r = reads[i];
+        const HostRead* hr = src.heavy(i);
+        PlainRead pr;
+        if (!hr) pr = src.plain(i);
+        const int L = hr ? hr->L : pr.L;
+        const uint8_t* bases = hr ? hr->bases : pr.bases;
+        const uint8_t* quals = hr ? hr->quals : pr.quals;
         // the read's qualities go once into the quality array (every version of the read points at them)
         const uint32_t qoff = (uint32_t)(out.n_qual / 4);
         uint8_t* q = out.qual.data() + out.n_qual;
-        const size_t padded = qual_run_bytes(r.L, qc.bits);
-        code_quality_run(r.quals, r.L, qc, q, padded);
+        const size_t padded = qual_run_bytes(L, qc.bits);
+        code_quality_run(quals, L, qc, q, padded);
         out.n_qual += padded;
-        if (r.L > 0xffff) { out.bad = true; continue; }
-        encode_read(r, rb);
+        if (L > 0xffff) { out.bad = true; continue; }
+        encode_bits(bases, quals, L, rb);
+        if (!hr) {
+            const uint32_t cig = ((uint32_t)L << 3) | (uint32_t)kOpM;
+            emit_record(pr.first, L, pr.neg, &cig, 1, pr.first, pr.ign_s, pr.ign_e, rb, false, 0, 0, qoff, out, compact);
+            continue;
+        }
+        const HostRead& r = *hr;
         if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, rb, false, 0, 0, qoff, out, compact); continue; }
         for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out, compact);
         emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out, compact);
     }
 }
 
-}  // namespace
-
-bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
+template <typename Src>
+bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
     out.group.clear();
     const size_t n = hi > lo ? hi - lo : 0;
     const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 8192 + 1));   // small tiles are not worth a thread each
@@ -379,36 +489,28 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
         range_of(t, a, b);
         unsigned char hit[256];
         std::memset(hit, 0, sizeof hit);
+        uint32_t m = 0;
+        const bool vec = have_avx2();
+        for (size_t i = a; i < b; i++) {
+            const HostRead* hr = src.heavy(i);
+            const uint8_t* q; int L;
+            if (hr) { q = hr->quals; L = hr->L; } else { const PlainRead pr = src.plain(i); q = pr.quals; L = pr.L; }
 #ifdef NGSEP_HAVE_AVX2_PATH
-        if (have_avx2()) {   // the classes that occur, each reported through a character of the class (choose_coder only looks at classes)
-            uint32_t m = 0;
-            for (size_t i = a; i < b; i++) m |= scan_classes_avx2(reads[i].quals, (size_t)reads[i].L);
-            for (int k = 0; k < 31; k++) if ((m >> k) & 1u) hit[33 + k] = 1;
-        } else
+            if (vec) { m |= scan_classes_avx2(q, (size_t)L); continue; }   // the classes that occur (choose_coder only looks at classes)
 #endif
-        for (size_t i = a; i < b; i++) { const uint8_t* q = reads[i].quals; const int L = reads[i].L; for (int k = 0; k < L; k++) hit[q[k]] = 1; }
+            for (int k = 0; k < L; k++) hit[q[k]] = 1;
+        }
+        if (vec) for (int k = 0; k < 31; k++) if ((m >> k) & 1u) hit[33 + k] = 1;   // ... each reported through a character of the class
         for (int c = 0; c < 256; c++) seen[(size_t)t][(size_t)c] = hit[c] != 0;
     };
-    if (nt == 1) scan(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(scan, t);
-        scan(0);
-        for (auto& x : th) x.join();
-    }
+    Helpers::get().run(nt, scan);
     bool any[256];
     for (int c = 0; c < 256; c++) { any[c] = false; for (int t = 0; t < nt; t++) any[c] = any[c] || seen[(size_t)t][(size_t)c]; }
     const QualCoder qc = choose_coder(any, min_qual_bits);
     out.qual_bits = (uint32_t)qc.bits;
     std::memcpy(out.qual_dict, qc.dict, 16);
     out.layout = compact ? NGSEP_LAYOUT_COMPACT : NGSEP_LAYOUT_FULL;
-    if (nt == 1) pack_range(reads, lo, hi, qc, parts[0], compact);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) { size_t a, b; range_of(t, a, b); Part* part = &parts[(size_t)t]; th.emplace_back([&reads, &qc, part, a, b, compact]() { pack_range(reads, a, b, qc, *part, compact); }); }
-        { size_t a, b; range_of(0, a, b); pack_range(reads, a, b, qc, parts[0], compact); }
-        for (auto& x : th) x.join();
-    }
+    Helpers::get().run(nt, [&](int t) { size_t a, b; range_of(t, a, b); pack_range(src, a, b, qc, parts[(size_t)t], compact); });
     // contiguous ranges were packed independently: payload offsets move by the words in front of the range, quality offsets
     // (the last payload word of every record) by the quality words in front of it
     size_t nh = 0, np = 0, nq = 0;
@@ -438,26 +540,32 @@ bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, Packed
             oh[i] = h;
         }
     };
-    if (nt == 1) place(0);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nt; t++) th.emplace_back(place, t);
-        place(0);
-        for (auto& x : th) x.join();
-    }
+    Helpers::get().run(nt, place);
     for (int t = 0; t < nt; t++) { out.max_span = std::max(out.max_span, parts[t].max_span); out.max_back = std::max(out.max_back, parts[t].max_back); out.aligned_bases += parts[t].aligned_bases; }
     if (with_groups) {   // one id per record (every version of a read carries the read's group)
         out.group.resize(out.hdr.size());
         size_t k = 0;
         for (size_t i = lo; i < hi; i++) {
-            const HostRead& r = reads[i];
-            const size_t n_rec = (r.closed.empty() && r.st.first == r.admit_first) ? 1 : r.closed.size() + 1;
-            const uint16_t g = (r.rg >= 0 && r.rg < 0xffff) ? (uint16_t)r.rg : (uint16_t)0xffff;
+            const HostRead* hr = src.heavy(i);
+            size_t n_rec = 1;
+            int rg;
+            if (hr) { n_rec = (hr->closed.empty() && hr->st.first == hr->admit_first) ? 1 : hr->closed.size() + 1; rg = hr->rg; }
+            else rg = src.plain(i).rg;
+            const uint16_t g = (rg >= 0 && rg < 0xffff) ? (uint16_t)rg : (uint16_t)0xffff;
             for (size_t v = 0; v < n_rec && k < out.hdr.size(); v++, k++) out.group[k] = g;
         }
         for (; k < out.hdr.size(); k++) out.group[k] = (uint16_t)0xffff;
     }
     return true;
+}
+
+}  // namespace
+
+bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
+    return pack_source(VectorSource{&reads}, lo, hi, out, with_groups, err, min_qual_bits, compact);
+}
+bool pack_plan_reads(const SeqPlan& plan, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
+    return pack_source(PlanSource{&plan}, lo, hi, out, with_groups, err, min_qual_bits, compact);
 }
 
 ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {

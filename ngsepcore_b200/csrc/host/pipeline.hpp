@@ -5,6 +5,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <deque>
 #include <functional>
 #include <map>
 #include <set>
@@ -210,6 +211,10 @@ struct PackedTile {
 // realigner rewrote it).
 bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0,
                 bool compact = false);
+struct SeqPlan;
+// ... the same for reads[lo,hi) of a plan (SeqPlan::lite): untouched single-block reads are packed straight from the batch
+bool pack_plan_reads(const SeqPlan& plan, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0,
+                     bool compact = false);
 bool wire_compact();   // the detectors pack NGSEP_LAYOUT_COMPACT tiles unless NGSEP_WIRE_COMPACT=0
 int host_threads();   // NGSEP_HOST_THREADS, else the hardware concurrency (at most 32)
 
@@ -246,7 +251,13 @@ constexpr int kAutoTileLen = 2000000;
 
 // Outcome of the host stages for one sequence (admission + event pre-pass).
 struct SeqPlan {
-    std::vector<HostRead> reads;                 // pileup order, with versions
+    // The admitted reads in pileup order, 16 bytes each; the reads that are more than one untouched match block — any other CIGAR, or
+    // a place in the pileup of a realigner event — have a HostRead in `heavy` (a deque: its elements never move)
+    std::vector<LiteRead> lite;
+    std::deque<HostRead> heavy;
+    const BatchView* batch = nullptr;            // the records behind `lite` (valid for the run that made the plan)
+    int64_t rec_base = 0;                        // LiteRead.rec counts from this record of the batch
+    int ignore5 = 0, ignore3 = 0;                // RA:613-644 for the reads without a HostRead
     std::vector<IndelRecord> indels;             // host-made indel / STR calls
     std::vector<PopIndelRecord> pop_indels;      // the same for a multi-sample run
     std::set<int> suppressed;                    // positions whose device SNV decision must not be reported

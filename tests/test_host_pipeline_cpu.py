@@ -146,6 +146,33 @@ def test_threaded_packer_equals_single_thread(monkeypatch):
         assert (ref["max_span"], ref["max_back"], ref["aligned_bases"]) == (t["max_span"], t["max_back"], t["aligned_bases"])
 
 
+def test_plan_without_materialised_reads_packs_the_same_tile(monkeypatch):
+    """The detectors keep an admitted read as 16 bytes (LiteRead) and build its HostRead only when the read has any CIGAR but one
+    match block or lies under a realigner event; untouched reads are packed straight from the batch.  On an input without indels
+    the tile must be, byte for byte, what admit_sequence + pack_reads (every read materialised) give — with the per-start cap,
+    ignored ends, low MAPQ records, bases outside ACGT and a query window."""
+    monkeypatch.setenv("NGSEP_WIRE_COMPACT", "0")
+    genome, batch, _ = simulate.simulate(contigs=[("a", 60000), ("b", 30000)], depth=25, seeds=(33, 34, 35), n_frac=0.02, low_mapq_frac=0.1, indel_rate=0.0,
+                                         read_len=93, n_read_groups=3)
+    det = hostapi.Detector(host_only=True, maxAlnsPerStartPos=2, ignore5=2, ignore3=4)
+    det.set_genome(genome)
+    for ci in range(2):
+        h1, p1, q1, s1, nb = hostapi.pack_sequence(batch, ci, max_alns_per_start=2, ignore5=2, ignore3=4)
+        t = det.pack(batch, ci)
+        assert h1.shape[0] > 5000
+        assert np.array_equal(h1, t["hdr"]) and np.array_equal(p1, t["payload"]) and np.array_equal(q1, t["qual"])
+        assert (s1, nb) == (t["max_span"], t["aligned_bases"])
+    # the admission of one long sequence (> 400 k records) on several threads, cut where the start position changes
+    genome, batch, _ = simulate.simulate(contigs=[("long", 1500000)], depth=30, seeds=(36, 37, 38), low_mapq_frac=0.05, indel_rate=0.0)
+    assert batch.n > 400000
+    want = hostapi.pack_sequence(batch, 0, max_alns_per_start=2, ignore5=2, ignore3=4)
+    det.set_genome(genome)
+    for threads in ("1", "4"):
+        monkeypatch.setenv("NGSEP_HOST_THREADS", threads)
+        t = det.pack(batch, 0)
+        assert np.array_equal(want[0], t["hdr"]) and np.array_equal(want[1], t["payload"]) and np.array_equal(want[2], t["qual"])
+
+
 def test_vector_packer_equals_portable_packer(tmp_path):
     """The packer codes 32 bases / qualities at a time where the host has AVX2 (chosen at run time); NGSEP_NO_AVX2=1 keeps the
     portable 8-at-a-time code.  Both give the same bytes: odd read lengths, bases outside ACGT, 2- / 4- / 8-bit quality modes."""
