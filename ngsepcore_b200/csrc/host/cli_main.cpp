@@ -4,6 +4,8 @@
 // Reads SAM text or BAM (the reference reads SAM/BAM/CRAM through htsjdk, RAFR:171-183; both are decoded natively here),
 // writes <prefix>.vcf like SSVD:926.  Errors follow the reference: a missing -i / -r is reported as in SSVD:595-596,
 // an unknown option prints usage and exits 1 (CommandsDescriptor.java:441-445).
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -11,6 +13,8 @@
 #include <malloc.h>
 #include <iostream>
 #include <iterator>
+#include <string_view>
+#include <thread>
 #include <unordered_map>
 
 #include <zlib.h>
@@ -21,6 +25,19 @@ using namespace ngsep_b200::host;
 
 namespace {
 
+// std::allocator whose value-less construct() leaves the storage as it is: resize() of a byte array then touches no page (the
+// threads that fill the array do, each its own part)
+template <typename T>
+struct NoInitAlloc : std::allocator<T> {
+    template <typename U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <typename U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <typename U, typename... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+using ByteArray = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 struct OwnedBatch {
     std::vector<int32_t> seq_idx, first;
     std::vector<uint16_t> flags;
@@ -28,7 +45,7 @@ struct OwnedBatch {
     std::vector<int16_t> rg, nh;
     std::vector<int64_t> cigar_off{0}, base_off{0};
     std::vector<uint32_t> cigar;
-    std::vector<uint8_t> bases, quals;
+    ByteArray bases, quals;
     std::vector<uint64_t> name_hash;
     BatchView view() const {
         BatchView v;
@@ -36,6 +53,10 @@ struct OwnedBatch {
         v.rg = rg.data(); v.nh = nh.data(); v.cigar_off = cigar_off.data(); v.cigar = cigar.data(); v.base_off = base_off.data();
         v.bases = bases.data(); v.quals = quals.data(); v.name_hash = name_hash.empty() ? nullptr : name_hash.data();
         return v;
+    }
+    void swap_storage(OwnedBatch& o) {   // (used to release a batch's arrays)
+        seq_idx.swap(o.seq_idx); first.swap(o.first); flags.swap(o.flags); mapq.swap(o.mapq); rg.swap(o.rg); nh.swap(o.nh); cigar_off.swap(o.cigar_off);
+        base_off.swap(o.base_off); cigar.swap(o.cigar); bases.swap(o.bases); quals.swap(o.quals); name_hash.swap(o.name_hash);
     }
     void append_from(const OwnedBatch& o, size_t i, int16_t new_rg) {   // record i of o, without its name hash
         seq_idx.push_back(o.seq_idx[i]); first.push_back(o.first[i]); flags.push_back(o.flags[i]); mapq.push_back(o.mapq[i]);
@@ -174,12 +195,43 @@ bool load_sam_text(std::istream& in, Loader& ld) {
     return true;
 }
 
-// BGZF: a series of gzip members with a "BC" extra field holding the block size (SAM specification section 4.1)
-bool bgzf_inflate(const std::string& path, std::vector<unsigned char>& out, std::string& err) {
+// f(t) for t in [0, n) on n threads (the calling one included)
+template <typename F>
+void on_threads(int n, F&& f) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < n; t++) th.emplace_back(f, t);
+    f(0);
+    for (auto& x : th) x.join();
+}
+
+// Bytes that are not cleared when they are allocated (the inflated file: 1 GB and more, written once by the inflating threads)
+struct RawBytes {
+    unsigned char* p = nullptr;
+    size_t n = 0;
+    RawBytes() = default;
+    RawBytes(const RawBytes&) = delete;
+    RawBytes& operator=(const RawBytes&) = delete;
+    ~RawBytes() { std::free(p); }
+    bool alloc(size_t k) { std::free(p); p = (unsigned char*)std::malloc(k ? k : 1); n = p ? k : 0; return p != nullptr; }
+    size_t size() const { return n; }
+    const unsigned char* data() const { return p; }
+    unsigned char operator[](size_t i) const { return p[i]; }
+};
+
+// BGZF: a series of gzip members with a "BC" extra field holding the block size (SAM specification section 4.1).  The members are
+// independent deflate streams whose inflated sizes stand in their trailers: one pass finds the blocks and where their bytes go,
+// then the blocks are inflated on all host threads.
+bool bgzf_inflate(const std::string& path, RawBytes& out, std::string& err) {
     std::ifstream in(path, std::ios::binary);
     if (!in) { err = "cannot open " + path; return false; }
-    std::vector<unsigned char> raw((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
-    size_t p = 0;
+    in.seekg(0, std::ios::end);
+    const std::streamoff file_size = in.tellg();
+    in.seekg(0);
+    std::vector<unsigned char, NoInitAlloc<unsigned char>> raw((size_t)std::max<std::streamoff>(0, file_size));
+    if (!raw.empty() && !in.read((char*)raw.data(), (std::streamsize)raw.size())) { err = "cannot read " + path; return false; }
+    struct Block { size_t cdata, clen, isize, out; };
+    std::vector<Block> blocks;
+    size_t p = 0, total = 0;
     while (p + 18 <= raw.size()) {
         if (raw[p] != 0x1f || raw[p + 1] != 0x8b || raw[p + 2] != 8 || !(raw[p + 3] & 4)) { err = path + ": not a BGZF file"; return false; }
         const size_t xlen = raw[p + 10] | (raw[p + 11] << 8);
@@ -192,27 +244,43 @@ bool bgzf_inflate(const std::string& path, std::vector<unsigned char>& out, std:
         }
         // header (12) + extra field + at least an empty deflate stream + CRC32 and ISIZE (8) must fit the block, the block the file
         if (!bsize || bsize < xlen + 20 || p + bsize > raw.size()) { err = path + ": truncated BGZF block"; return false; }
-        const size_t cdata = p + 12 + xlen, clen = bsize - xlen - 20;
         const size_t isize = raw[p + bsize - 4] | (raw[p + bsize - 3] << 8) | (raw[p + bsize - 2] << 16) | ((size_t)raw[p + bsize - 1] << 24);
         if (isize > 65536) { err = path + ": corrupt BGZF block"; return false; }   // a BGZF block inflates to at most 64 KiB
-        if (isize) {
-            const size_t o = out.size();
-            out.resize(o + isize);
-            z_stream zs{};
-            if (inflateInit2(&zs, -15) != Z_OK) { err = "zlib init failed"; return false; }
-            zs.next_in = raw.data() + cdata; zs.avail_in = (uInt)clen;
-            zs.next_out = out.data() + o; zs.avail_out = (uInt)isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.total_out != isize) { err = path + ": corrupt BGZF block"; return false; }
-        }
+        if (isize) blocks.push_back({p + 12 + xlen, bsize - xlen - 20, isize, total});
+        total += isize;
         p += bsize;
     }
+    if (!out.alloc(total)) { err = path + ": not enough memory for the inflated file"; return false; }
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), blocks.size() / 16 + 1));
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    on_threads(nt, [&](int) {
+        z_stream zs{};
+        if (inflateInit2(&zs, -15) != Z_OK) { failed.store(true); return; }
+        for (;;) {
+            const size_t k0 = next.fetch_add(16);
+            if (k0 >= blocks.size() || failed.load()) break;
+            for (size_t k = k0; k < std::min(blocks.size(), k0 + 16); k++) {
+                const Block& bl = blocks[k];
+                inflateReset(&zs);
+                zs.next_in = raw.data() + bl.cdata; zs.avail_in = (uInt)bl.clen;
+                zs.next_out = out.p + bl.out; zs.avail_out = (uInt)bl.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.total_out != bl.isize) { failed.store(true); break; }
+            }
+        }
+        inflateEnd(&zs);
+    });
+    if (failed.load()) { err = path + ": corrupt BGZF block"; return false; }
     return true;
 }
 
+// The records of a BAM file, decoded on all host threads.  One pass finds the record boundaries; contiguous ranges of records are
+// then decoded independently into parts of the batch; the parts are laid side by side.  Read-group ids get the index the
+// sequential reader gives them — the order of their first appearance in the file (RAFR:184-197 for the header's) — because the
+// parts are merged in file order.
 bool load_bam(const std::string& path, Loader& ld) {
-    std::vector<unsigned char> d;
+    RawBytes d;
     if (!bgzf_inflate(path, d, ld.err)) return false;
     auto u32 = [&](size_t o) { return (uint32_t)d[o] | ((uint32_t)d[o + 1] << 8) | ((uint32_t)d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24); };
     auto u16 = [&](size_t o) { return (uint32_t)d[o] | ((uint32_t)d[o + 1] << 8); };
@@ -247,81 +315,180 @@ bool load_bam(const std::string& path, Loader& ld) {
         if ((long)ld.g.seqs[it->second].size() != l_ref) { ld.err = "Inconsistent length in file header. Sequence " + name; return false; }
         ref_to_seq[r] = it->second;
     }
+    // ---- record boundaries (one pass over the block sizes) ------------------------------------------------------------------
+    std::vector<size_t> rec_at;
+    while (p + 4 <= d.size()) {
+        const size_t block = u32(p);
+        if (p + 4 + block > d.size() || block < 32) { ld.err = path + ": truncated BAM record"; return false; }
+        rec_at.push_back(p + 4);
+        p += 4 + block;
+    }
+    // ---- the records, range by range ------------------------------------------------------------------------------------------
+    struct Part { OwnedBatch b; std::vector<std::string> rg_ids; std::unordered_map<std::string, int> rg_index; std::string err; };
+    const size_t n_rec = rec_at.size();
+    size_t part_records = 20000;   // a part is not worth a thread below this (NGSEP_BAM_PART_RECORDS: test hook)
+    if (const char* e = std::getenv("NGSEP_BAM_PART_RECORDS")) { const long v = std::atol(e); if (v >= 1) part_records = (size_t)v; }
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n_rec / part_records + 1));
+    std::vector<Part> parts((size_t)nt);
     static const char kSeq[] = "=ACMGRSVTWYHKDBN";
     static const int kOp[9] = {kOpM, kOpI, kOpD, kOpN, kOpS, kOpH, kOpP, kOpM, kOpX};   // BAM MIDNSHP=X -> the reference's codes
-    while (p + 4 <= d.size()) {
-        const size_t block = u32(p); p += 4;
-        if (p + block > d.size() || block < 32) { ld.err = path + ": truncated BAM record"; return false; }
-        const size_t q = p;
-        const int ref_id = (int)u32(q), pos = (int)u32(q + 4) + 1;
-        const size_t l_name = d[q + 8];
-        const int mapq = d[q + 9];
-        const size_t n_cig = u16(q + 12);
-        const int flag = (int)u16(q + 14);
-        const size_t l_seq = u32(q + 16);
-        // every length of the fixed part against the record block (block <= the bytes left in the file, checked above)
-        if (l_seq > block || 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq > block) { ld.err = path + ": truncated BAM record"; return false; }
-        const size_t rec_end = q + block;
-        size_t o = q + 32;
-        std::string qname((const char*)d.data() + o, l_name ? l_name - 1 : 0); o += l_name;
-        std::vector<uint32_t> cg;
-        bool bad = false;
-        for (size_t k = 0; k < n_cig; k++, o += 4) { const uint32_t v = u32(o); if ((v & 15u) > 8u) bad = true; else cg.push_back(cig_make((int)(v >> 4), kOp[v & 15u])); }
-        std::string seq(l_seq, 'N'), qual;
-        for (size_t k = 0; k < l_seq; k++) { const unsigned char by = d[o + (k >> 1)]; seq[k] = kSeq[(k & 1) ? (by & 15) : (by >> 4)]; }
-        o += (l_seq + 1) / 2;
-        if (l_seq && d[o] != 0xff) { qual.resize(l_seq); for (size_t k = 0; k < l_seq; k++) qual[k] = (char)std::min(126, (int)d[o + k] + 33); }
-        o += l_seq;
-        const std::string* rg = nullptr;
-        std::string rg_id;
-        int nh = -1;
-        bool aux_bad = false;
-        while (o + 3 <= rec_end) {   // optional fields; every value is checked against the end of the record before it is read
-            const char t0 = (char)d[o], t1 = (char)d[o + 1], ty = (char)d[o + 2];
-            o += 3;
-            long ival = 0; bool is_int = true;
-            size_t need = 0;
-            switch (ty) {
-                case 'A': case 'c': case 'C': need = 1; break;
-                case 's': case 'S': need = 2; break;
-                case 'i': case 'I': case 'f': need = 4; break;
-                case 'B': need = 5; break;
-                default: break;
-            }
-            if (need > rec_end - o) { aux_bad = true; break; }
-            switch (ty) {
-                case 'A': case 'c': ival = (int8_t)d[o]; o += 1; break;
-                case 'C': ival = d[o]; o += 1; break;
-                case 's': ival = (int16_t)u16(o); o += 2; break;
-                case 'S': ival = u16(o); o += 2; break;
-                case 'i': ival = (int32_t)u32(o); o += 4; break;
-                case 'I': ival = u32(o); o += 4; break;
-                case 'f': is_int = false; o += 4; break;
-                case 'Z': case 'H': {
-                    size_t e = o;
-                    while (e < rec_end && d[e]) e++;
-                    if (e >= rec_end) { aux_bad = true; break; }   // no terminator inside the record
-                    if (t0 == 'R' && t1 == 'G' && ty == 'Z') { rg_id.assign((const char*)d.data() + o, e - o); rg = &rg_id; }
-                    o = e + 1; is_int = false; break;
-                }
-                case 'B': {
-                    const char sub = (char)d[o];
-                    const size_t cnt = u32(o + 1);
-                    const size_t w = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
-                    o += 5;
-                    if (cnt > (rec_end - o) / w) { aux_bad = true; break; }
-                    o += cnt * w; is_int = false; break;
-                }
-                default: o = rec_end; is_int = false; break;
-            }
-            if (aux_bad) break;
-            if (is_int && t0 == 'N' && t1 == 'H' && ty != 'A') nh = (int)std::min(32000L, std::max(-1L, ival));
+    struct SeqPairs { char c[256][2]; SeqPairs() { for (int v = 0; v < 256; v++) { c[v][0] = kSeq[v >> 4]; c[v][1] = kSeq[v & 15]; } } };
+    static const SeqPairs pairs;
+    on_threads(nt, [&](int t) {
+        Part& part = parts[(size_t)t];
+        OwnedBatch& b = part.b;
+        const size_t r0 = n_rec * (size_t)t / (size_t)nt, r1 = n_rec * (size_t)(t + 1) / (size_t)nt;
+        if (r1 > r0) {   // (the arrays are sized from the bytes of the range: an upper bound of everything they hold)
+            const size_t bytes = (r1 < n_rec ? rec_at[r1] : d.size()) - rec_at[r0];
+            b.seq_idx.reserve(r1 - r0); b.first.reserve(r1 - r0); b.flags.reserve(r1 - r0); b.mapq.reserve(r1 - r0); b.rg.reserve(r1 - r0); b.nh.reserve(r1 - r0);
+            b.cigar_off.reserve(r1 - r0 + 1); b.base_off.reserve(r1 - r0 + 1); b.name_hash.reserve(r1 - r0);
+            b.bases.reserve(bytes); b.quals.reserve(bytes);
         }
-        if (aux_bad) { ld.err = path + ": truncated BAM record (optional fields)"; return false; }
-        p = q + block;
-        if (bad || ref_id < 0 || (size_t)ref_id >= n_ref) continue;   // unplaced record / unknown operation: skipped like in the SAM reader
-        ld.record(qname, flag, ref_to_seq[ref_id], pos, mapq, cg, l_seq ? seq : std::string(), qual, l_seq > 0, rg, nh);
+        std::vector<uint32_t> cg;
+        for (size_t r = r0; r < r1; r++) {
+            const size_t q = rec_at[r];
+            const size_t block = u32(q - 4);
+            const int ref_id = (int)u32(q), pos = (int)u32(q + 4) + 1;
+            const size_t l_name = d[q + 8];
+            const int mapq = d[q + 9];
+            const size_t n_cig = u16(q + 12);
+            const int flag = (int)u16(q + 14);
+            const size_t l_seq = u32(q + 16);
+            // every length of the fixed part against the record block (block <= the bytes left in the file, checked above)
+            if (l_seq > block || 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq > block) { part.err = path + ": truncated BAM record"; return; }
+            const size_t rec_end = q + block;
+            size_t o = q + 32;
+            const size_t name_at = o, name_len = l_name ? l_name - 1 : 0;
+            o += l_name;
+            cg.clear();
+            bool bad = false;
+            for (size_t k = 0; k < n_cig; k++, o += 4) { const uint32_t v = u32(o); if ((v & 15u) > 8u) bad = true; else cg.push_back(cig_make((int)(v >> 4), kOp[v & 15u])); }
+            const size_t seq_at = o;
+            o += (l_seq + 1) / 2;
+            const size_t qual_at = o;
+            o += l_seq;
+            size_t rg_at = 0, rg_len = 0;
+            bool has_rg = false;
+            int nh = -1;
+            while (o + 3 <= rec_end) {   // optional fields; every value is checked against the end of the record before it is read
+                const char t0 = (char)d[o], t1 = (char)d[o + 1], ty = (char)d[o + 2];
+                o += 3;
+                long ival = 0; bool is_int = true;
+                size_t need = 0;
+                switch (ty) {
+                    case 'A': case 'c': case 'C': need = 1; break;
+                    case 's': case 'S': need = 2; break;
+                    case 'i': case 'I': case 'f': need = 4; break;
+                    case 'B': need = 5; break;
+                    default: break;
+                }
+                bool aux_bad = need > rec_end - o;
+                if (!aux_bad) switch (ty) {
+                    case 'A': case 'c': ival = (int8_t)d[o]; o += 1; break;
+                    case 'C': ival = d[o]; o += 1; break;
+                    case 's': ival = (int16_t)u16(o); o += 2; break;
+                    case 'S': ival = u16(o); o += 2; break;
+                    case 'i': ival = (int32_t)u32(o); o += 4; break;
+                    case 'I': ival = u32(o); o += 4; break;
+                    case 'f': is_int = false; o += 4; break;
+                    case 'Z': case 'H': {
+                        size_t e = o;
+                        while (e < rec_end && d[e]) e++;
+                        if (e >= rec_end) { aux_bad = true; break; }   // no terminator inside the record
+                        if (t0 == 'R' && t1 == 'G' && ty == 'Z') { rg_at = o; rg_len = e - o; has_rg = true; }
+                        o = e + 1; is_int = false; break;
+                    }
+                    case 'B': {
+                        const char sub = (char)d[o];
+                        const size_t cnt = u32(o + 1);
+                        const size_t w = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4);
+                        o += 5;
+                        if (cnt > (rec_end - o) / w) { aux_bad = true; break; }
+                        o += cnt * w; is_int = false; break;
+                    }
+                    default: o = rec_end; is_int = false; break;
+                }
+                if (aux_bad) { part.err = path + ": truncated BAM record (optional fields)"; return; }
+                if (is_int && t0 == 'N' && t1 == 'H' && ty != 'A') nh = (int)std::min(32000L, std::max(-1L, ival));
+            }
+            if (bad || ref_id < 0 || (size_t)ref_id >= n_ref) continue;   // unplaced record / unknown operation: skipped like in the SAM reader
+            // ---- Loader::record, into the part -------------------------------------------------------------------------------
+            b.seq_idx.push_back(ref_to_seq[(size_t)ref_id]);
+            b.first.push_back(pos);
+            b.flags.push_back((uint16_t)flag);
+            b.mapq.push_back((uint8_t)std::min(255, mapq));
+            int16_t rg = -1;
+            if (has_rg) {   // index local to the part; the merge below turns it into the file-wide one
+                std::string id((const char*)d.data() + rg_at, rg_len);
+                auto ins = part.rg_index.emplace(id, (int)part.rg_ids.size());
+                if (ins.second) part.rg_ids.push_back(id);
+                rg = (int16_t)ins.first->second;
+            }
+            b.rg.push_back(rg);
+            b.nh.push_back((int16_t)std::max(-1, std::min(32000, nh)));
+            b.cigar.insert(b.cigar.end(), cg.begin(), cg.end());
+            b.cigar_off.push_back((int64_t)b.cigar.size());
+            if (l_seq) {
+                const size_t at = b.bases.size();
+                b.bases.resize(at + l_seq);
+                b.quals.resize(at + l_seq);
+                uint8_t* bs = b.bases.data() + at;
+                uint8_t* qs = b.quals.data() + at;
+                const unsigned char* sp = d.data() + seq_at;
+                size_t k = 0;
+                for (; k + 2 <= l_seq; k += 2) { const unsigned char by = sp[k >> 1]; bs[k] = (uint8_t)pairs.c[by][0]; bs[k + 1] = (uint8_t)pairs.c[by][1]; }
+                if (k < l_seq) bs[k] = (uint8_t)pairs.c[sp[k >> 1]][0];
+                const unsigned char* qp = d.data() + qual_at;
+                if (qp[0] == 0xff) std::memset(qs, '+', l_seq);                                           // no qualities: RA:1025
+                else for (size_t j = 0; j < l_seq; j++) qs[j] = (uint8_t)std::min(126, (int)qp[j] + 33);
+            }
+            b.base_off.push_back((int64_t)b.bases.size());
+            b.name_hash.push_back(std::hash<std::string_view>()(std::string_view((const char*)d.data() + name_at, name_len)));
+        }
+    });
+    for (auto& part : parts) if (!part.err.empty()) { ld.err = part.err; return false; }   // (the first one in file order)
+    // ---- the parts side by side ------------------------------------------------------------------------------------------------
+    OwnedBatch& out = ld.b;
+    std::vector<size_t> rec0((size_t)nt + 1, out.first.size()), cig0((size_t)nt + 1, out.cigar.size()), base0((size_t)nt + 1, out.bases.size());
+    std::vector<std::vector<int16_t>> rg_map((size_t)nt);
+    for (int t = 0; t < nt; t++) {
+        Part& part = parts[(size_t)t];
+        rec0[(size_t)t + 1] = rec0[(size_t)t] + part.b.first.size();
+        cig0[(size_t)t + 1] = cig0[(size_t)t] + part.b.cigar.size();
+        base0[(size_t)t + 1] = base0[(size_t)t] + part.b.bases.size();
+        for (const std::string& id : part.rg_ids) {   // Loader::record's table, in the order of first appearance
+            auto r = ld.rg_of().emplace(id, (int)ld.rg_of().size());
+            if (ld.rgs && r.second) { ld.rgs->ids.push_back(id); ld.rgs->samples.push_back(std::string(1, '\0')); }   // on records only: no sample
+            rg_map[(size_t)t].push_back((int16_t)r.first->second);
+        }
     }
+    const size_t n_all = rec0[(size_t)nt];
+    out.seq_idx.resize(n_all); out.first.resize(n_all); out.flags.resize(n_all); out.mapq.resize(n_all); out.rg.resize(n_all); out.nh.resize(n_all);
+    out.name_hash.resize(n_all); out.cigar_off.resize(n_all + 1); out.base_off.resize(n_all + 1);
+    out.cigar.resize(cig0[(size_t)nt]); out.bases.resize(base0[(size_t)nt]); out.quals.resize(base0[(size_t)nt]);
+    on_threads(nt, [&](int t) {
+        OwnedBatch& b = parts[(size_t)t].b;
+        const size_t n = b.first.size(), at = rec0[(size_t)t];
+        if (!n) return;
+        std::memcpy(out.seq_idx.data() + at, b.seq_idx.data(), n * sizeof(int32_t));
+        std::memcpy(out.first.data() + at, b.first.data(), n * sizeof(int32_t));
+        std::memcpy(out.flags.data() + at, b.flags.data(), n * sizeof(uint16_t));
+        std::memcpy(out.mapq.data() + at, b.mapq.data(), n);
+        std::memcpy(out.nh.data() + at, b.nh.data(), n * sizeof(int16_t));
+        std::memcpy(out.name_hash.data() + at, b.name_hash.data(), n * sizeof(uint64_t));
+        const std::vector<int16_t>& m = rg_map[(size_t)t];
+        for (size_t i = 0; i < n; i++) out.rg[at + i] = b.rg[i] < 0 ? (int16_t)-1 : m[(size_t)b.rg[i]];
+        for (size_t i = 0; i < n; i++) {   // (a part's offset arrays start with their own 0)
+            out.cigar_off[at + i + 1] = (int64_t)cig0[(size_t)t] + b.cigar_off[i + 1];
+            out.base_off[at + i + 1] = (int64_t)base0[(size_t)t] + b.base_off[i + 1];
+        }
+        if (!b.cigar.empty()) std::memcpy(out.cigar.data() + cig0[(size_t)t], b.cigar.data(), b.cigar.size() * sizeof(uint32_t));
+        if (!b.bases.empty()) {
+            std::memcpy(out.bases.data() + base0[(size_t)t], b.bases.data(), b.bases.size());
+            std::memcpy(out.quals.data() + base0[(size_t)t], b.quals.data(), b.quals.size());
+        }
+        OwnedBatch().swap_storage(b);
+    });
     return true;
 }
 
@@ -330,9 +497,12 @@ bool load_alignments(const std::string& path, const Genome& g, OwnedBatch& b, st
     unsigned char magic[2] = {0, 0};
     { std::ifstream probe(path, std::ios::binary); if (!probe) { err = "cannot open " + path; return false; } probe.read((char*)magic, 2); }
     bool ok;
+    const auto t_load = std::chrono::steady_clock::now();
     if (magic[0] == 0x1f && magic[1] == 0x8b) ok = load_bam(path, ld);   // BGZF (htsjdk picks the reader from the file content too)
     else { std::ifstream in(path); ok = load_sam_text(in, ld); }
     if (!ok) err = ld.err;
+    if (std::getenv("NGSEP_TIMING"))
+        std::fprintf(stderr, "load_alignments %s: %.3f s, %zu records\n", path.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count(), b.first.size());
     return ok;
 }
 

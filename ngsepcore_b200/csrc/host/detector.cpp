@@ -144,17 +144,20 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         if (job.rc != NGSEP_OK) { err_ = job.plan.err; return job.rc; }
         stats_.add_host(job.plan.stats);
     }
+    const double t_plan = now_s();
     if (deferred_tallies() && !known_mode()) {
         rc = tally_span_events(jobs);
         if (rc != NGSEP_OK) return rc;
         parallel_jobs(jobs.size(), threads, order, [&](size_t k) { resolve_fired_events(jobs[k].plan); });
         for (auto& job : jobs) stats_.indel_calls += job.plan.stats.indel_calls_late;
     }
+    const double t_tally = now_s();
     // ---- stage 3: the device -------------------------------------------------------------------------------------------
     if (!opt_.host_only) {
         rc = run_device(jobs);
         if (rc != NGSEP_OK) return rc;
     }
+    const double t_dev = now_s();
     // ---- stage 4: ordered merge + text, per sequence ------------------------------------------------------------------------
     parallel_jobs(jobs.size(), threads, order, [&](size_t k) { if (!jobs[k].plan.lite.empty()) emit_text(jobs[k]); });
     size_t bytes = 0;
@@ -165,6 +168,9 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         parallel_jobs(jobs.size(), threads, order, [&](size_t k) { std::vector<LiteRead>().swap(jobs[k].plan.lite); std::deque<HostRead>().swap(jobs[k].plan.heavy); });
     }
     stats_.total_s += now_s() - t0;
+    if (std::getenv("NGSEP_TIMING"))
+        std::fprintf(stderr, "run: setup %.4f  plan %.4f  tallies %.4f  device loop %.4f  text + release %.4f  total %.4f s\n", tp - t0, t_plan - tp, t_tally - t_plan, t_dev - t_tally,
+                     now_s() - t_dev, now_s() - t0);
     return NGSEP_OK;
 }
 

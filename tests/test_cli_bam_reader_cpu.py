@@ -42,15 +42,18 @@ def test_bam_and_sam_decode_to_the_same_batch(tmp_path):
     n = bam_util.sam_to_bam(sam, bam)
     assert n > 15000
     outs = {}
-    for tag, path in (("sam", sam), ("bam", bam)):
+    # "bam": one thread decodes the whole file; "bam_parts": ranges of 1500 records on six threads, laid side by side afterwards
+    for tag, path, env in (("sam", sam, {}), ("bam", bam, {"NGSEP_HOST_THREADS": "1"}), ("bam_parts", bam, {"NGSEP_HOST_THREADS": "6", "NGSEP_BAM_PART_RECORDS": "1500"})):
         prefix, dump = str(tmp_path / f"out_{tag}"), str(tmp_path / f"dump_{tag}.bin")
         subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", prefix, "--host-only", "--dump-batch", dump],
-                              stderr=subprocess.DEVNULL)
+                              stderr=subprocess.DEVNULL, env=dict(os.environ, **env))
         outs[tag] = (_read_dump(dump), open(prefix + ".vcf").read())
     names = ["seq_idx", "first", "flags", "mapq", "rg", "nh", "cigar_off", "cigar", "base_off", "bases", "quals", "name_hash"]
     assert len(outs["sam"][0]) == len(names)
-    for name, a, b in zip(names, outs["sam"][0], outs["bam"][0]):
-        assert a == b, name
+    for tag in ("bam", "bam_parts"):
+        for name, a, b in zip(names, outs["sam"][0], outs[tag][0]):
+            assert a == b, (tag, name)
+        assert outs["sam"][1] == outs[tag][1]
     assert len(outs["sam"][0][1]) // 4 == n
     body = [l for l in outs["sam"][1].splitlines() if not l.startswith("#")]
     assert len(body) > 20 and outs["sam"][1] == outs["bam"][1]
