@@ -646,6 +646,8 @@ int main(int argc, char** argv) {
     }
     if (in.empty()) { std::fprintf(stderr, "The input file with alignments is a required parameter\n"); return 2; }
     if (ref.empty()) { std::fprintf(stderr, "The reference genome file is a required parameter\n"); return 2; }
+    GpuSingleSampleVariantsDetector det(o);
+    det.warm_up();   // the device contexts come up while the inputs are read
     Genome g;
     if (!load_fasta(ref, g)) { std::fprintf(stderr, "cannot read %s\n", ref.c_str()); return 2; }
     OwnedBatch b;
@@ -659,7 +661,6 @@ int main(int argc, char** argv) {
         put(b.cigar_off.data(), b.cigar_off.size() * 8); put(b.cigar.data(), b.cigar.size() * 4); put(b.base_off.data(), b.base_off.size() * 8);
         put(b.bases.data(), b.bases.size()); put(b.quals.data(), b.quals.size()); put(b.name_hash.data(), b.name_hash.size() * 8);
     }
-    GpuSingleSampleVariantsDetector det(o);
     det.set_genome(&g);
     std::string vcf;
     int rc = det.run(b.view(), vcf, true);

@@ -15,6 +15,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <deque>
 #include <queue>
 #include <set>
@@ -34,6 +37,7 @@ GpuSingleSampleVariantsDetector::GpuSingleSampleVariantsDetector(const DetectorO
 }
 
 GpuSingleSampleVariantsDetector::~GpuSingleSampleVariantsDetector() {
+    if (warm_.joinable()) warm_.join();
     rings_.clear();   // page-locked buffers go first (they unregister themselves)
     for (void* c : ctxs_) if (c) ngsep_ctx_destroy(c);
 }
@@ -41,6 +45,11 @@ GpuSingleSampleVariantsDetector::~GpuSingleSampleVariantsDetector() {
 void GpuSingleSampleVariantsDetector::set_genome(const Genome* g) {
     genome_ = g;
     ref_uploaded_.assign((size_t)std::max(1, opt_.n_devices), std::vector<bool>(g->seqs.size(), false));
+}
+
+void GpuSingleSampleVariantsDetector::warm_up() {
+    if (opt_.host_only || warm_.joinable() || !ctxs_.empty()) return;
+    warm_ = std::thread([this]() { ensure_ctx(); });   // (a failure is found again, and reported, by run()'s own ensure_ctx)
 }
 
 int GpuSingleSampleVariantsDetector::ensure_ctx() {
@@ -55,7 +64,6 @@ int GpuSingleSampleVariantsDetector::ensure_ctx() {
     ctx_ = ctxs_[0];
     rings_.resize((size_t)n);
     for (auto& r : rings_) r.resize((size_t)kHostRing);
-    if (ref_uploaded_.size() != (size_t)n && genome_) ref_uploaded_.assign((size_t)n, std::vector<bool>(genome_->seqs.size(), false));
     return NGSEP_OK;
 }
 
@@ -94,8 +102,10 @@ void parallel_jobs(size_t n, int threads, const std::vector<size_t>& order, F&& 
 int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, bool with_header) {
     double t0 = now_s();
     if (!genome_) { err_ = "The reference genome file is a required parameter"; return NGSEP_EINVAL; }  // SSVD:596
+    if (warm_.joinable()) warm_.join();
     int rc = opt_.host_only ? NGSEP_OK : ensure_ctx();
     if (rc != NGSEP_OK) return rc;
+    if (ref_uploaded_.size() != (size_t)std::max(1, opt_.n_devices)) ref_uploaded_.assign((size_t)std::max(1, opt_.n_devices), std::vector<bool>(genome_->seqs.size(), false));
     if (!opt_.known_strs.empty() && opt_.known_variants.empty() && !strs_loaded_) {   // SSVD:906-913 (the else branch of -knownVariants)
         if (!load_known_strs(opt_.known_strs, *genome_, strs_, err_)) return NGSEP_EINVAL;
         strs_loaded_ = true;
@@ -138,26 +148,78 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     // than threads splits a sequence)
     inner_threads_ = (jobs.empty() || (int)jobs.size() >= threads) ? 1 : std::max(1, threads / (int)jobs.size());
     double tp = now_s();
-    parallel_jobs(jobs.size(), threads, order, [&](size_t k) { jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan); });
-    stats_.prepass_s += now_s() - tp;
-    for (auto& job : jobs) {
-        if (job.rc != NGSEP_OK) { err_ = job.plan.err; return job.rc; }
-        stats_.add_host(job.plan.stats);
-    }
-    const double t_plan = now_s();
-    if (deferred_tallies() && !known_mode()) {
-        rc = tally_span_events(jobs);
+    double t_plan = tp, t_tally = tp, t_dev = tp;
+    auto after_plans = [&]() -> int {
+        for (auto& job : jobs) {
+            if (job.rc != NGSEP_OK) { err_ = job.plan.err; return job.rc; }
+            stats_.add_host(job.plan.stats);
+        }
+        return NGSEP_OK;
+    };
+    auto tallies = [&]() -> int {
+        if (deferred_tallies() && !known_mode()) {
+            int r = tally_span_events(jobs);
+            if (r != NGSEP_OK) return r;
+            parallel_jobs(jobs.size(), threads, order, [&](size_t k) { resolve_fired_events(jobs[k].plan); });
+            for (auto& job : jobs) stats_.indel_calls += job.plan.stats.indel_calls_late;
+        }
+        return NGSEP_OK;
+    };
+    if (opt_.host_only || opt_.synchronous) {
+        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan); });
+        stats_.prepass_s += now_s() - tp;
+        t_plan = now_s();
+        rc = after_plans();
         if (rc != NGSEP_OK) return rc;
-        parallel_jobs(jobs.size(), threads, order, [&](size_t k) { resolve_fired_events(jobs[k].plan); });
-        for (auto& job : jobs) stats_.indel_calls += job.plan.stats.indel_calls_late;
-    }
-    const double t_tally = now_s();
-    // ---- stage 3: the device -------------------------------------------------------------------------------------------
-    if (!opt_.host_only) {
-        rc = run_device(jobs);
+        rc = tallies();
         if (rc != NGSEP_OK) return rc;
+        t_tally = now_s();
+        // ---- stage 3: the device ---------------------------------------------------------------------------------------
+        if (!opt_.host_only) {
+            size_t k = 0;
+            rc = run_device(jobs, [&]() -> long { return k < jobs.size() ? (long)k++ : -1L; });
+            if (rc != NGSEP_OK) return rc;
+        }
+        t_dev = now_s();
+    } else {
+        // The sequences are planned on the host threads while this thread already packs and submits the tiles of the sequences whose
+        // plan is ready (in the order they get ready: the results stay with their sequence): the planning stage lasts as long as its
+        // longest sequence, and packing fills the cores the short ones leave idle.
+        std::mutex mq;
+        std::condition_variable cvq;
+        std::deque<size_t> ready;
+        size_t handed = 0;
+        bool failed = false;
+        double plan_wall = 0;
+        std::thread planner([&]() {
+            parallel_jobs(jobs.size(), threads, order, [&](size_t k) {
+                jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan);
+                { std::lock_guard<std::mutex> g(mq); ready.push_back(k); if (jobs[k].rc != NGSEP_OK) failed = true; }
+                cvq.notify_one();
+            });
+            plan_wall = now_s() - tp;
+        });
+        rc = run_device(jobs, [&]() -> long {
+            std::unique_lock<std::mutex> g(mq);
+            if (handed == jobs.size()) return -1L;
+            cvq.wait(g, [&] { return !ready.empty(); });
+            if (failed) return -1L;   // a sequence could not be planned: nothing more is submitted
+            const size_t k = ready.front();
+            ready.pop_front();
+            handed++;
+            return (long)k;
+        });
+        planner.join();
+        stats_.prepass_s += plan_wall;
+        t_plan = t_tally = now_s();
+        const int prc = after_plans();
+        if (prc != NGSEP_OK) return prc;
+        if (rc != NGSEP_OK) return rc;
+        t_dev = now_s();
+        rc = tallies();   // (one device call for the events of every sequence: after the last plan)
+        if (rc != NGSEP_OK) return rc;
+        t_tally = now_s();
     }
-    const double t_dev = now_s();
     // ---- stage 4: ordered merge + text, per sequence ------------------------------------------------------------------------
     parallel_jobs(jobs.size(), threads, order, [&](size_t k) { if (!jobs[k].plan.lite.empty()) emit_text(jobs[k]); });
     size_t bytes = 0;
@@ -169,8 +231,9 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
     }
     stats_.total_s += now_s() - t0;
     if (std::getenv("NGSEP_TIMING"))
-        std::fprintf(stderr, "run: setup %.4f  plan %.4f  tallies %.4f  device loop %.4f  text + release %.4f  total %.4f s\n", tp - t0, t_plan - tp, t_tally - t_plan, t_dev - t_tally,
-                     now_s() - t_dev, now_s() - t0);
+        std::fprintf(stderr, "run: setup %.4f  planning (wall) %.4f  device loop %.4f  tallies %.4f  text + release %.4f  total %.4f s%s\n", tp - t0, stats_.prepass_s,
+                     (opt_.host_only || opt_.synchronous) ? t_dev - t_tally : t_dev - tp, (opt_.host_only || opt_.synchronous) ? t_tally - t_plan : t_tally - t_dev,
+                     now_s() - std::max(t_dev, t_tally), now_s() - t0, (opt_.host_only || opt_.synchronous) ? "" : "  (planning runs under the device loop)");
     return NGSEP_OK;
 }
 
@@ -178,7 +241,7 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
 // the devices still work on the tiles before it (ngsep_tile_submit only enqueues copies and kernels).  With several devices
 // the tiles are dealt to them in turn; every device has its own context, ring and tiles in flight, and the calls of all of
 // them meet again in the per-sequence merge (no collective: SURVEY 8e).
-int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
+int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs, const std::function<long()>& next_job) {
     const size_t n_dev = ctxs_.size();
     struct InFlight { SeqJob* job; size_t site_base, n_sites; };   // (-knownVariants: the tile's piece of plan.sites)
     std::vector<std::deque<InFlight>> q(n_dev);
@@ -187,6 +250,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
     std::vector<uint16_t> site_codes;
     std::vector<int> slot(n_dev, 0);
     const size_t max_in_flight = opt_.synchronous ? 1 : (size_t)kHostRing - 1;
+    double submit_s = 0, fetch_s = 0;   // (NGSEP_TIMING)
     auto fetch_oldest = [&](size_t dev) -> int {
         double td = now_s();
         ngsep_tile_stats ts{};
@@ -243,6 +307,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             snvs.resize(before);
         }
         stats_.device_s += now_s() - td;
+        fetch_s += now_s() - td;
         stats_.covered_positions += ts.covered_positions;
         stats_.candidate_positions += ts.candidate_positions;
         stats_.aligned_bases += ts.aligned_bases;
@@ -255,7 +320,9 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
         for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { ngsep_tile_stats ts{}; fetch_tile(ctxs_[dev], *q[dev].front().job, ts); q[dev].pop_front(); }
     };
     size_t dealt = 0;
-    for (auto& job : jobs) {
+    for (long jk = next_job(); jk >= 0; jk = next_job()) {
+        SeqJob& job = jobs[(size_t)jk];
+        if (job.rc != NGSEP_OK) continue;
         SeqPlan& plan = job.plan;
         if (plan.lite.empty()) continue;
         const int seq = job.seq;
@@ -305,12 +372,15 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs) {
             if (rc == NGSEP_OK) rc = ngsep_tile_submit(ctxs_[dev], &tv);
             if (rc != NGSEP_OK) { err_ = ngsep_last_error(ctxs_[dev]); drain(); return rc; }
             stats_.device_s += now_s() - td;
+            submit_s += now_s() - td;
             q[dev].push_back(InFlight{&job, site_base, n_sites});
             slot[dev] = (slot[dev] + 1) % kHostRing;
             dealt++;
         }
     }
+    const double t_drain = now_s();
     for (size_t dev = 0; dev < n_dev; dev++) while (!q[dev].empty()) { int rc = fetch_oldest(dev); if (rc != NGSEP_OK) { drain(); return rc; } }
+    if (std::getenv("NGSEP_TIMING")) std::fprintf(stderr, "device loop: %zu tiles, submit %.4f s, fetch %.4f s (of which the last tiles in flight %.4f s)\n", dealt, submit_s, fetch_s, now_s() - t_drain);
     return NGSEP_OK;
 }
 

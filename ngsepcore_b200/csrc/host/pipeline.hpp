@@ -10,6 +10,7 @@
 #include <map>
 #include <set>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -301,6 +302,9 @@ public:
     explicit GpuSingleSampleVariantsDetector(const DetectorOptions& o);
     virtual ~GpuSingleSampleVariantsDetector();
     void set_genome(const Genome* g);                 // setGenome, SSVD:161-163
+    // Starts creating the device contexts on a thread of their own (CUDA start-up takes most of a second): a caller that still has its
+    // inputs to read calls this first; run() waits for it.  Optional.
+    void warm_up();
     // Processes a coordinate-sorted batch; appends VCF text (header included when with_header) to out.
     int run(const BatchView& batch, std::string& out, bool with_header = true);
     const RunStats& stats() const { return stats_; }
@@ -315,6 +319,7 @@ protected:
     bool strs_loaded_ = false;
     std::vector<std::vector<KnownVariant>> known_;   // -knownVariants: per sequence
     bool known_loaded_ = false;
+    std::thread warm_;                               // warm_up()'s thread
     int inner_threads_ = 1;                          // host threads one sequence may use for its own stages (set per run)
     bool known_mode() const { return known_loaded_ && n_known_ > 0; }   // SSVPL:147: an empty input list means discovery
     size_t n_known_ = 0;
@@ -343,7 +348,8 @@ protected:
     int plan_sequence(const BatchView& b, int seq, int64_t lo, int64_t hi, SeqPlan& plan);
     void tile_records(const SeqPlan& plan, int tf, int tl, size_t& r_lo, size_t& r_hi) const;
     int tile_len() const { return opt_.tile_len > 0 ? opt_.tile_len : kAutoTileLen; }
-    int run_device(std::vector<SeqJob>& jobs);
+    // packs and submits the tiles of the sequences next_job() hands out (an index into jobs, -1: no more), fetches what comes back
+    int run_device(std::vector<SeqJob>& jobs, const std::function<long()>& next_job);
 public:
     int pack_sequence(const BatchView& b, int seq, PackedTile& tile, int& tile_first, int& tile_last);
 };
