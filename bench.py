@@ -232,25 +232,25 @@ def run_gpu(args):
     IN_FLIGHT = 3   # tiles between ngsep_tile_submit and ngsep_tile_fetch (the C ABI pipelines up to 4)
 
     def e2e_step():
-        n_calls, pending, copied, in_place = 0, 0, 0, 0
+        n_calls, pending, copied, in_place, back = 0, 0, 0, 0, 0
         for ci, t in enumerate(tiles):
             if not t["hdr"].size:
                 continue
             if pending == IN_FLIGHT:
                 c, _, st = ctx.fetch(sort=False)
-                n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
+                n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place; back += st.d2h_bytes
             ctx.submit(ci, t["first"], t["last"], t["hdr"], t["payload"], t["qual"], t["max_span"], t["max_back"], quality=t["quality"], layout=t["layout"])
             pending += 1
         while pending:
             c, _, st = ctx.fetch(sort=False)
-            n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place
-        return n_calls, copied, in_place
+            n_calls += len(c); pending -= 1; copied += st.h2d_bytes; in_place += st.quality_in_place; back += st.d2h_bytes
+        return n_calls, copied, in_place, back
     for _ in range(3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n_calls_e2e, e2e_copied, e2e_in_place = e2e_step()
+        n_calls_e2e, e2e_copied, e2e_in_place, e2e_back = e2e_step()
     e2e_s = time.perf_counter() - t0
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -274,8 +274,8 @@ def run_gpu(args):
                             "sequences in parallel on the host threads (prepass_s = wall time of that stage), tiles packed into page-locked ring "
                             "buffers with up to three tiles in flight (pack_s, device_s = host time spent packing / blocked in submit + fetch), VCF text"}
 
-    (covered_all, bases_all, h2d_all, calls_all, launches_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
-        dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
+    (covered_all, bases_all, h2d_all, calls_all, launches_all, d2h_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
+        dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches, e2e_back], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -311,7 +311,7 @@ def run_gpu(args):
                                          "quality bytes are only read for the columns that reach k_genotype_columns",
                          "peak_source": peak_src},
             "e2e": {"value": covered_all * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
-                    "d2h_bytes_per_step": int(calls_all * 224 + 36 * len(slots) * world), "ms_per_step": e2e_s / args.steps * 1e3,
+                    "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_s / args.steps * 1e3,
                     "host_input_bytes_per_step": int(h2d_bytes * world), "same_calls_as_resident_run": bool(n_calls_e2e == calls),
                     "quality_in_place_tiles": int(e2e_in_place),
                     "quality_bits": sorted({int(t["quality"][0]) for t in tiles}),

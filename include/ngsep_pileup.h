@@ -202,7 +202,8 @@ typedef struct ngsep_tile_stats {
     uint32_t open_columns;       /* positions the window kernel left to k_genotype_columns (whole launch) */
     uint64_t h2d_bytes;          /* bytes of the tile copied host -> device at staging                     */
     uint32_t quality_in_place;   /* 1: the quality bytes stayed in the caller's page-locked buffer and were read on demand */
-    uint32_t reserved;
+    uint32_t d2h_bytes;          /* bytes the tile's fetch brought back device -> host (counters, staging report, call records; a pipelined tile's
+                                    first call slots travel behind its kernels whether they are filled or not)  */
 } ngsep_tile_stats;
 
 /* Context = one GPU + its streams (kernels, bulk copies, genotype kernels of pipelined tiles) + the device-resident reference.  Replaces the construction of

@@ -21,9 +21,9 @@ public final class NgsepPileupNative implements AutoCloseable {
 	public static final int F_STRAND_BIAS = 0x1, F_IGNORE_LOWER_REF = 0x2, F_EMIT_ALL = 0x8, F_QUALITY_IN_PLACE = 0x10;
 	public static final int M_NEG = 0x01000000, M_NMASK = 0x02000000, M_WINDOW = 0x04000000, M_SIMPLE = 0x10000000;
 	public static final int N_TABLES = 95, CALL_BYTES = 224, SITE_BYTES = 44, SAMPLE_CALL_BYTES = 104, HDR_BYTES = 16;
-	/** Indexes into the long[10] statistics array the fetch methods fill. */
+	/** Indexes into the statistics array the fetch methods fill (a long[11]; a shorter array gets the leading entries). */
 	public static final int ST_COVERED = 0, ST_CANDIDATES = 1, ST_CALLS = 2, ST_ALIGNED_BASES = 3, ST_KERNEL_US = 4, ST_WINDOW_KERNEL_US = 5, ST_LAUNCHES = 6,
-			ST_OPEN_COLUMNS = 7, ST_H2D_BYTES = 8, ST_QUALITY_IN_PLACE = 9;
+			ST_OPEN_COLUMNS = 7, ST_H2D_BYTES = 8, ST_QUALITY_IN_PLACE = 9, ST_D2H_BYTES = 10;
 
 	// ---- one native method per C entry point (jni/ngsep_pileup_jni.c) -----------------------------------------------------
 	static native long ctxCreate(int device, int maxBaseQS, int minQuality, double hetRate, int ploidy, int flags, int nSamples, double[] tables) throws IOException;

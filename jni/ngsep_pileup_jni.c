@@ -27,11 +27,12 @@ static void throw_io(JNIEnv* env, void* ctx, int rc, const char* what) {
 static void* direct(JNIEnv* env, jobject buf) { return buf ? (*env)->GetDirectBufferAddress(env, buf) : NULL; }
 static void fill_stats(JNIEnv* env, jlongArray out, const ngsep_tile_stats* s) {
     if (!out) return;
-    /* covered, candidates, calls, aligned bases, kernel microseconds, window-kernel microseconds, launches, open columns, H2D bytes, quality in place */
-    jlong v[10] = {(jlong)s->covered_positions, (jlong)s->candidate_positions, (jlong)s->calls, (jlong)s->aligned_bases, (jlong)(s->kernel_ms * 1000.0f),
-                   (jlong)(s->pileup_ms * 1000.0f), (jlong)s->kernel_launches, (jlong)s->open_columns, (jlong)s->h2d_bytes, (jlong)s->quality_in_place};
+    /* covered, candidates, calls, aligned bases, kernel microseconds, window-kernel microseconds, launches, open columns, H2D bytes, quality in place, D2H bytes */
+    jlong v[11] = {(jlong)s->covered_positions, (jlong)s->candidate_positions, (jlong)s->calls, (jlong)s->aligned_bases, (jlong)(s->kernel_ms * 1000.0f),
+                   (jlong)(s->pileup_ms * 1000.0f), (jlong)s->kernel_launches, (jlong)s->open_columns, (jlong)s->h2d_bytes, (jlong)s->quality_in_place,
+                   (jlong)s->d2h_bytes};
     jsize n = (*env)->GetArrayLength(env, out);
-    (*env)->SetLongArrayRegion(env, out, 0, n < 10 ? n : 10, v);
+    (*env)->SetLongArrayRegion(env, out, 0, n < 11 ? n : 11, v);
 }
 static void fill_tile(JNIEnv* env, ngsep_tile* t, jint seq, jint first, jint last, jint nReads, jint maxSpan, jint maxBack, jobject hdr, jobject payload,
                       jlong nWords, jobject qual, jlong nQual, jobject group) {

@@ -43,7 +43,7 @@ class SynthParams(C.Structure):
 class TileStats(C.Structure):
     _fields_ = [("covered_positions", C.c_uint64), ("candidate_positions", C.c_uint64), ("calls", C.c_uint64),
                 ("aligned_bases", C.c_uint64), ("kernel_ms", C.c_float), ("pileup_ms", C.c_float), ("kernel_launches", C.c_uint32), ("open_columns", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("quality_in_place", C.c_uint32), ("reserved", C.c_uint32)]
+                ("h2d_bytes", C.c_uint64), ("quality_in_place", C.c_uint32), ("d2h_bytes", C.c_uint32)]
 
 
 HDR_DTYPE = np.dtype([("first", "<i4"), ("meta", "<u4"), ("ign_start", "<i2"), ("ign_end", "<i2"), ("off", "<u4")])

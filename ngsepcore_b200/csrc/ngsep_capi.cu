@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,7 +72,12 @@ struct Slot {
     cudaEvent_t e0 = nullptr, em = nullptr, e1 = nullptr;   // before the pileup kernel / between the two kernels / after
     cudaEvent_t e_copy = nullptr;                           // the tile's host -> device copies (copy stream) are done
     TileDev tile{};
-    struct Pinned { ngsep_read_hdr sentinel; TileDev tile; }* pin = nullptr;   // page-locked: small copies stay asynchronous
+    struct Pinned { ngsep_read_hdr sentinel; TileDev tile; unsigned char meta[32]; unsigned int rep[4]; }* pin = nullptr;   // page-locked: small copies stay asynchronous
+    // A pipelined tile's results come back behind its kernels, on their stream: counters and staging report into `pin`, the first
+    // kPrefetchCalls call records into pin_calls.  ngsep_tile_fetch then waits for the tile's event and reads host memory: a
+    // synchronous copy at fetch time queues behind the bulk copies of the tiles submitted since (0.2 ms each, measured).
+    ngsep_snv_call* pin_calls = nullptr;
+    bool prefetched = false;
     bool staged = false, launched = false, in_batch = false, pipelined = false;
     int grid = 0;
     uint64_t aligned_bases = 0;
@@ -87,6 +93,8 @@ struct Slot {
         if (d_tile) cudaFree(d_tile);
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
+        if (pin_calls) cudaFreeHost(pin_calls);
+        pin_calls = nullptr;
         if (e_copy) cudaEventDestroy(e_copy);
         if (e0) cudaEventDestroy(e0);
         if (em) cudaEventDestroy(em);
@@ -96,6 +104,7 @@ struct Slot {
 };
 
 struct Ctx {
+    double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // NGSEP_TIMING: host seconds in stage / launch (submit) and event wait / counters / report / calls (fetch)
     int device = 0;
     cudaStream_t stream = nullptr;            // every kernel of the context
     cudaStream_t copy_stream = nullptr;       // bulk host -> device copies of staged tiles
@@ -225,6 +234,8 @@ int queue_overflowed(Ctx* c, int* grew) {
     return NGSEP_OK;
 }
 
+constexpr size_t kPrefetchCalls = 2048;   // call records of a pipelined tile that travel behind its kernels (a 2 Mb tile holds about 2000 SNV calls)
+
 // one tile: pileup kernel + genotype kernel
 int launch_slot(Ctx* c, Slot* s) {
     if (!s->staged) return fail(c, NGSEP_ESTATE, "no tile staged");
@@ -253,6 +264,18 @@ int launch_slot(Ctx* c, Slot* s) {
         else if (c->hp.pool_ploidy) launch_pool_columns(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         else launch_genotype(s->d_tile, queue_view(s), c->d_prm, c->geno_grid, c->geno_stream);
         s->launches = 2;
+    }
+    s->prefetched = false;
+    if (s->pipelined) {
+        static_assert(sizeof(s->pin->meta) == kMetaStride, "meta layout");
+        CK(cudaMemcpyAsync(s->pin->meta, s->d_counters, kMetaStride, cudaMemcpyDeviceToHost, c->geno_stream), "counters copy");
+        CK(cudaMemcpyAsync(s->pin->rep, s->d_report(), 16, cudaMemcpyDeviceToHost, c->geno_stream), "report copy");
+        if (c->params.n_samples == 1 && s->tile.calls) {
+            if (!s->pin_calls) CK(cudaHostAlloc((void**)&s->pin_calls, kPrefetchCalls * sizeof(ngsep_snv_call), cudaHostAllocDefault), "call prefetch buffer");
+            const size_t k = std::min<size_t>(kPrefetchCalls, s->tile.cap_calls);
+            CK(cudaMemcpyAsync(s->pin_calls, s->tile.calls, k * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost, c->geno_stream), "call prefetch");
+        }
+        s->prefetched = true;
     }
     CK(cudaEventRecord(s->e1, c->geno_stream), "event record");
     CK(cudaGetLastError(), "kernel launch");
@@ -314,11 +337,14 @@ int launch_batch(Ctx* c) {
     return NGSEP_OK;
 }
 
+inline double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // Reads the staging report of a tile whose staging work has completed on the device.
-int read_report(Ctx* c, Slot* s) {
+int read_report(Ctx* c, Slot* s, const unsigned int* host_copy = nullptr) {
     if (s->report_read) return NGSEP_OK;
     struct { unsigned int err, pad; unsigned long long bases; } rep;
-    CK(cudaMemcpy(&rep, s->d_report(), sizeof(rep), cudaMemcpyDeviceToHost), "report copy");
+    if (host_copy) std::memcpy(&rep, host_copy, sizeof(rep));
+    else CK(cudaMemcpy(&rep, s->d_report(), sizeof(rep), cudaMemcpyDeviceToHost), "report copy");
     s->report_read = true;
     s->aligned_bases = rep.bases;
     if (rep.err & 1u) return fail(c, NGSEP_EINVAL, "records are not sorted by start");
@@ -514,10 +540,16 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
     static_assert(sizeof(Meta) == kMetaStride, "meta layout");
     for (int attempt = 0; attempt < 4; attempt++) {
         // a pipelined tile waits for ITS kernels only: later tiles may already be copying on the same stream
+        const double tf0 = host_now();
         if (s->in_batch) CK(cudaStreamSynchronize(c->stream), "tile kernels");
         else CK(cudaEventSynchronize(s->e1), "tile kernels");
-        CK(cudaMemcpy(&meta, s->d_counters, sizeof(meta), cudaMemcpyDeviceToHost), "counters copy");
-        { int rrc = read_report(c, s); if (rrc != NGSEP_OK) return rrc; }
+        const double tf1 = host_now();
+        const bool pre = s->prefetched && !s->in_batch;   // counters, report and the first calls are in page-locked host memory already
+        if (pre) std::memcpy(&meta, s->pin->meta, sizeof(meta));
+        else CK(cudaMemcpy(&meta, s->d_counters, sizeof(meta), cudaMemcpyDeviceToHost), "counters copy");
+        const double tf2 = host_now();
+        { int rrc = read_report(c, s, pre ? s->pin->rep : nullptr); if (rrc != NGSEP_OK) return rrc; }
+        c->tm[2] += tf1 - tf0; c->tm[3] += tf2 - tf1; c->tm[4] += host_now() - tf2;
         int grew = 0;
         if (s->in_batch) {
             int rc = queue_overflowed(c, &grew);
@@ -545,6 +577,9 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         if (rc != NGSEP_OK) return rc;
     }
     const unsigned int n = meta.n_calls;
+    // device -> host bytes of this fetch: counters + staging report, and the call records (a pipelined tile's first slots came behind its kernels)
+    size_t d2h = kMetaStride + 16;
+    if (s->prefetched && !s->in_batch && s->pin_calls) d2h += std::min<size_t>(kPrefetchCalls, s->tile.cap_calls) * sizeof(ngsep_snv_call);
     if (stats) {
         float ms = 0.f, pms = 0.f;
         if (s->in_batch) {   // the whole batch: its tiles share the launches
@@ -560,6 +595,7 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         stats->aligned_bases = s->aligned_bases;
         stats->h2d_bytes = s->h2d_bytes;
         stats->quality_in_place = s->qual_on_host ? 1u : 0u;
+        stats->d2h_bytes = 0;   // (completed below, once the call records have been brought back)
         stats->kernel_ms = ms;
         stats->pileup_ms = pms;
         stats->kernel_launches = s->launches;
@@ -572,14 +608,22 @@ int fetch_slot(Ctx* c, Slot* s, ngsep_snv_call* out, size_t cap, size_t* n_out, 
         if (!sites || !scalls) return fail(c, NGSEP_EINVAL, "null output buffer");
         CK(cudaMemcpy(sites, s->d_sites.p, (size_t)n * sizeof(ngsep_pop_site), cudaMemcpyDeviceToHost), "site copy");
         CK(cudaMemcpy(scalls, s->d_scalls.p, (size_t)n * (size_t)c->params.n_samples * sizeof(ngsep_sample_call), cudaMemcpyDeviceToHost), "sample call copy");
+        d2h += (size_t)n * (sizeof(ngsep_pop_site) + (size_t)c->params.n_samples * sizeof(ngsep_sample_call));
     } else if (n > 0) {
         if (!out) return fail(c, NGSEP_EINVAL, "null output buffer");
-        CK(cudaMemcpy(out, s->d_calls.p, (size_t)n * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost), "calls copy");
+        const double tc0 = host_now();
+        size_t have = 0;
+        if (s->prefetched && !s->in_batch && s->pin_calls) { have = std::min<size_t>(n, kPrefetchCalls); std::memcpy(out, s->pin_calls, have * sizeof(ngsep_snv_call)); }
+        if (n > have) CK(cudaMemcpy(out + have, s->d_calls.p + have, ((size_t)n - have) * sizeof(ngsep_snv_call), cudaMemcpyDeviceToHost), "calls copy");
+        d2h += ((size_t)n - have) * sizeof(ngsep_snv_call);
+        c->tm[5] += host_now() - tc0;
     }
     if (counts_dbg && s->tile.counts_dbg) {
         size_t m = (size_t)(s->tile.tile_last - s->tile.tile_first + 1) * 5;
         CK(cudaMemcpy(counts_dbg, s->tile.counts_dbg, m * sizeof(int32_t), cudaMemcpyDeviceToHost), "counts copy");
+        d2h += m * sizeof(int32_t);
     }
+    if (stats) stats->d2h_bytes = (uint32_t)std::min<size_t>(d2h, 0xffffffffull);
     return NGSEP_OK;
 }
 
@@ -713,6 +757,9 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
 int ngsep_ctx_destroy(void* ctx) {
     Ctx* c = (Ctx*)ctx;
     if (!c) return NGSEP_EINVAL;
+    if (std::getenv("NGSEP_TIMING"))
+        std::fprintf(stderr, "context: host seconds in submit: stage %.4f launch %.4f; in fetch: event wait %.4f counters %.4f report %.4f calls %.4f\n", c->tm[0], c->tm[1], c->tm[2], c->tm[3],
+                     c->tm[4], c->tm[5]);
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->geno_stream) cudaStreamSynchronize(c->geno_stream);
@@ -774,10 +821,13 @@ int ngsep_tile_submit(void* ctx, const ngsep_tile* t) {
     if (!c) return NGSEP_EINVAL;
     if (c->ring_count == c->ring.size()) return fail(c, NGSEP_ESTATE, "too many tiles in flight: call ngsep_tile_fetch first");
     Slot* s = c->ring[c->ring_head];
+    const double ts0 = host_now();
     int rc = stage_slot(c, s, t, true);
     if (rc != NGSEP_OK) return rc;
+    const double ts1 = host_now();
     rc = launch_slot(c, s);
     if (rc != NGSEP_OK) return rc;
+    c->tm[0] += ts1 - ts0; c->tm[1] += host_now() - ts1;
     c->ring_head = (c->ring_head + 1) % c->ring.size();
     c->ring_count++;
     return NGSEP_OK;
