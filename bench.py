@@ -260,19 +260,24 @@ def run_gpu(args):
     if not args.no_pipeline:
         det2 = hostapi.Detector(device=device)
         det2.set_genome(genome)
-        det2.run(batch)                      # warm-up: context creation, device allocations, first-touch of the buffers
-        s0 = det2.stats()
-        w0 = (s0.covered_positions, s0.prepass_s, s0.pack_s, s0.device_s)
-        t0 = time.perf_counter()
-        vcf = det2.run(batch)
-        pipeline_s = time.perf_counter() - t0
-        st2 = det2.stats()
-        pipeline = {"value": (st2.covered_positions - w0[0]) / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": st2.prepass_s - w0[1],
-                    "pack_s": st2.pack_s - w0[2], "device_s": st2.device_s - w0[3], "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
-                    "host_threads": min(32, os.cpu_count() or 1),
-                    "note": "whole detector from decoded records (second run of the detector object): admission + realigner pre-pass of all "
-                            "sequences in parallel on the host threads (prepass_s = wall time of that stage), tiles packed into page-locked ring "
-                            "buffers with up to three tiles in flight (pack_s, device_s = host time spent packing / blocked in submit + fetch), VCF text"}
+        runs = []
+        for _ in range(6):                   # run 1: context creation, device allocations, page-locked buffers sized; runs 2 .. 6 are what a long-lived detector does
+            s0 = det2.stats()
+            w0 = (s0.covered_positions, s0.prepass_s, s0.pack_s, s0.device_s)
+            t0 = time.perf_counter()
+            vcf = det2.run(batch)
+            dt = time.perf_counter() - t0
+            st2 = det2.stats()
+            runs.append((dt, st2.covered_positions - w0[0], st2.prepass_s - w0[1], st2.pack_s - w0[2], st2.device_s - w0[3]))
+        later = sorted(runs[2:])
+        pipeline_s, pcov, ppre, ppack, pdev = later[len(later) // 2]      # the median of runs 3 .. 6
+        pipeline = {"value": pcov / pipeline_s, "unit": UNIT, "seconds": pipeline_s, "prepass_s": ppre,
+                    "pack_s": ppack, "device_s": pdev, "vcf_records": len([l for l in vcf.splitlines() if l and l[0] != "#"]),
+                    "host_threads": min(32, os.cpu_count() or 1), "run_seconds": [round(r[0], 4) for r in runs],
+                    "note": "whole detector from decoded records to VCF text, one detector object run six times (run_seconds; the first run creates the "
+                            "device context and sizes the page-locked buffers): the median of runs 3 .. 6.  Admission + realigner pre-pass of the "
+                            "sequences on the host threads (prepass_s = wall time of that stage, which runs under the device loop), tiles packed into "
+                            "page-locked ring buffers with up to three tiles in flight (pack_s, device_s = host time spent packing / in submit + fetch), VCF text"}
 
     (covered_all, bases_all, h2d_all, calls_all, launches_all, d2h_all), (total_ms, e2e_s, pileup_ms, kernels_ms) = reduce_over_ranks(
         dist, "cuda", sums=[covered, aligned_bases, e2e_copied, calls, launches, e2e_back], maxima=[total_ms, e2e_s, pileup_ms, kernels_ms])

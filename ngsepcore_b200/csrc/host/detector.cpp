@@ -354,6 +354,13 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs, const
             while (q[dev].size() >= max_in_flight) { int rc = fetch_oldest(dev); if (rc != NGSEP_OK) { drain(); return rc; } }
             PackedTile& tile = rings_[dev][(size_t)slot[dev]];
             tile.set_pinned(!opt_.synchronous);
+            {   // the buffers of a ring grow together (a buffer takes the largest capacity any of them has needed): tiles of different
+                // sizes cycling through the ring stop re-registering page-locked memory after the first few
+                size_t ch = 0, cp = 0, cq = 0, cg = 0;
+                for (const PackedTile& r : rings_[dev]) { ch = std::max(ch, r.hdr.cap); cp = std::max(cp, r.payload.cap); cq = std::max(cq, r.qual.cap); cg = std::max(cg, r.group.cap); }
+                tile.hdr.reserve(ch, true); tile.payload.reserve(cp, true); tile.qual.reserve(cq, true);
+                if (with_groups()) tile.group.reserve(cg, true);
+            }
             double tp = now_s();
             if (!pack_plan_reads(plan, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact())) { drain(); return NGSEP_EINVAL; }
             stats_.pack_s += now_s() - tp;

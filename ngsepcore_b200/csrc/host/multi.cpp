@@ -19,8 +19,6 @@ namespace ngsep_b200 {
 namespace host {
 
 namespace {
-double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
 // Iteration order of a java.util.HashSet<String> holding `keys` (distinct, given in insertion order): String.hashCode,
 // HashMap's hash spreading, table of 16 doubling past a load of 0.75, bins in insertion order.
 std::vector<int> java_hashset_order(const std::vector<std::string>& keys) {

@@ -31,14 +31,14 @@ void HostBuf<T>::release() {
     p = nullptr; n = cap = 0; registered = false;
 }
 template <typename T>
-void HostBuf<T>::reserve(size_t want) {
+void HostBuf<T>::reserve(size_t want, bool exact) {
     if (want <= cap && (registered || !pin || cap == 0)) return;
     if (want <= cap && pin && !registered) {   // asked to pin after the allocation
         registered = ngsep_host_register(p, cap * sizeof(T)) == NGSEP_OK;
         return;
     }
     release();
-    size_t c = std::max<size_t>(want + want / 4, 1024);
+    size_t c = std::max<size_t>(exact ? want : want + want / 4, 1024);
     size_t bytes = (c * sizeof(T) + 4095) & ~(size_t)4095;
     p = (T*)std::aligned_alloc(4096, bytes);
     if (!p) throw std::bad_alloc();

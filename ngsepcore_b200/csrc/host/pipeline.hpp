@@ -178,7 +178,7 @@ struct HostBuf {
     }
     ~HostBuf() { release(); }
     void release();
-    void reserve(size_t want);                       // (discards the contents when it has to grow)
+    void reserve(size_t want, bool exact = false);   // (discards the contents when it has to grow; exact: without the growth margin)
     void resize(size_t k) { reserve(k); n = k; }
     void clear() { n = 0; }
     T* data() { return p; }

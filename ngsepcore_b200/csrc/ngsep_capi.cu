@@ -104,6 +104,7 @@ struct Slot {
 };
 
 struct Ctx {
+    bool prefetch_results = true;   // NGSEP_PREFETCH=0: a pipelined tile's results are copied when they are fetched (A/B switch)
     double tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // NGSEP_TIMING: host seconds in stage / launch (submit) and event wait / counters / report / calls (fetch)
     int device = 0;
     cudaStream_t stream = nullptr;            // every kernel of the context
@@ -266,7 +267,7 @@ int launch_slot(Ctx* c, Slot* s) {
         s->launches = 2;
     }
     s->prefetched = false;
-    if (s->pipelined) {
+    if (s->pipelined && c->prefetch_results) {
         static_assert(sizeof(s->pin->meta) == kMetaStride, "meta layout");
         CK(cudaMemcpyAsync(s->pin->meta, s->d_counters, kMetaStride, cudaMemcpyDeviceToHost, c->geno_stream), "counters copy");
         CK(cudaMemcpyAsync(s->pin->rep, s->d_report(), 16, cudaMemcpyDeviceToHost, c->geno_stream), "report copy");
@@ -662,6 +663,7 @@ int ngsep_ctx_create(int device, const ngsep_params* params, const double* table
     if (const char* s = std::getenv("NGSEP_PAY_CAP_WORDS")) { int v = std::atoi(s); if (v >= 1024 && v <= 50000) c->cfg.pay_cap_words = (unsigned)(v & ~3); }
     if (const char* s = std::getenv("NGSEP_STAGES")) { int v = std::atoi(s); if (v == 1 || v == 2) c->cfg.n_stages = v; }
     if (const char* s = std::getenv("NGSEP_L2_PREFETCH")) c->cfg.l2_prefetch = std::atoi(s) != 0;
+    if (const char* s = std::getenv("NGSEP_PREFETCH")) c->prefetch_results = std::atoi(s) != 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
