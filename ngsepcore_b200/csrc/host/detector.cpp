@@ -251,6 +251,8 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs, const
     std::vector<int> slot(n_dev, 0);
     const size_t max_in_flight = opt_.synchronous ? 1 : (size_t)kHostRing - 1;
     double submit_s = 0, fetch_s = 0;   // (NGSEP_TIMING)
+    const char* hint_env = std::getenv("NGSEP_PACK_HINT");   // =0: every tile finds its own quality classes (A/B switch)
+    QualHint* const hint = (hint_env && std::atoi(hint_env) == 0) ? nullptr : &qual_hint_;
     auto fetch_oldest = [&](size_t dev) -> int {
         double td = now_s();
         ngsep_tile_stats ts{};
@@ -362,7 +364,7 @@ int GpuSingleSampleVariantsDetector::run_device(std::vector<SeqJob>& jobs, const
                 if (with_groups()) tile.group.reserve(cg, true);
             }
             double tp = now_s();
-            if (!pack_plan_reads(plan, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact())) { drain(); return NGSEP_EINVAL; }
+            if (!pack_plan_reads(plan, r_lo, r_hi, tile, with_groups(), &err_, 0, wire_compact(), hint)) { drain(); return NGSEP_EINVAL; }
             stats_.pack_s += now_s() - tp;
             if (tile.hdr.empty()) continue;
             double td = now_s();
@@ -797,7 +799,8 @@ int GpuSingleSampleVariantsDetector::pack_sequence(const BatchView& b, int seq, 
     int rc = plan_sequence(b, seq, lo, hi, plan);
     if (rc != NGSEP_OK) { err_ = plan.err; return rc; }
     const double tpk = now_s();
-    if (!pack_plan_reads(plan, 0, plan.lite.size(), tile, false, &err_, 0, wire_compact())) return NGSEP_EINVAL;
+    // (NGSEP_PACK_HINT=1, test hook: this one-tile entry point hands the quality coding on from call to call like run_device does from tile to tile)
+    if (!pack_plan_reads(plan, 0, plan.lite.size(), tile, false, &err_, 0, wire_compact(), (std::getenv("NGSEP_PACK_HINT") && std::atoi(std::getenv("NGSEP_PACK_HINT")) != 0) ? &qual_hint_ : nullptr)) return NGSEP_EINVAL;
     if (std::getenv("NGSEP_TIMING")) std::fprintf(stderr, "pack_sequence: prepass %.4f s, pack %.4f s\n", plan.stats.prepass_s, now_s() - tpk);
     tile_first = plan.win_first;
     tile_last = plan.win_last;

@@ -178,6 +178,7 @@ struct QualCoder {
     uint8_t code_of[256];
     uint8_t dict[16];
     alignas(32) uint8_t class_code[32];   // the code of quality class k (qual_class), for the 32-at-a-time coder
+    alignas(32) uint8_t class_known[32];  // 0xff: class k has a code (a coder taken over from an earlier tile may meet classes it has none for)
 };
 inline int qual_class(int c) { const int q = c - 33; return q <= 3 ? 0 : std::min(30, q); }
 QualCoder choose_coder(const bool* seen, int min_bits = 0) {
@@ -185,6 +186,7 @@ QualCoder choose_coder(const bool* seen, int min_bits = 0) {
     std::memset(qc.code_of, 0, sizeof qc.code_of);
     std::memset(qc.dict, 0, sizeof qc.dict);
     std::memset(qc.class_code, 0, sizeof qc.class_code);
+    std::memset(qc.class_known, 0xff, sizeof qc.class_known);
     bool present[31] = {false};
     for (int c = 0; c < 256; c++) if (seen[c]) present[qual_class(c)] = true;
     int n = 0, code_of_class[31];
@@ -196,7 +198,14 @@ QualCoder choose_coder(const bool* seen, int min_bits = 0) {
     if (bits == 8) return qc;
     for (int k = 0; k < 31; k++) if (code_of_class[k] >= 0) qc.dict[code_of_class[k]] = (uint8_t)(k == 0 ? 35 : 33 + k);
     for (int c = 0; c < 256; c++) { const int k = code_of_class[qual_class(c)]; qc.code_of[c] = (uint8_t)(k < 0 ? 0 : k); }
-    for (int k = 0; k < 32; k++) qc.class_code[k] = (uint8_t)((k < 31 && code_of_class[k] >= 0) ? code_of_class[k] : 0);
+    for (int k = 0; k < 32; k++) { qc.class_code[k] = (uint8_t)((k < 31 && code_of_class[k] >= 0) ? code_of_class[k] : 0); qc.class_known[k] = (k < 31 && code_of_class[k] >= 0) ? 0xff : 0; }
+    return qc;
+}
+// the coder an earlier tile used, from its dictionary (code c stands for the class of dict[c])
+QualCoder coder_from_dict(int bits, const uint8_t* dict) {
+    bool seen[256] = {false};
+    for (int c = 0; c < (1 << bits) && c < 16; c++) if (dict[c]) seen[dict[c]] = true;
+    QualCoder qc = choose_coder(seen, bits);
     return qc;
 }
 inline size_t qual_run_bytes(int L, int bits) { return ((((size_t)L * (size_t)bits + 7) / 8) + 3) & ~(size_t)3; }
@@ -271,12 +280,16 @@ __attribute__((target("avx2"))) uint32_t scan_classes_avx2(const uint8_t* q, siz
     return m;
 }
 // the 2- / 4-bit codes of the first (L & ~31) qualities of a read; returns how many qualities it coded (a multiple of 32)
-__attribute__((target("avx2"))) int code_quals_avx2(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* out) {
+__attribute__((target("avx2"))) int code_quals_avx2(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* out, bool* unknown) {
+    const __m256i k0 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)qc.class_known)), k1 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)(qc.class_known + 16)));
+    __m256i all_known = _mm256_set1_epi8((char)0xff);
     const __m256i t0 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)qc.class_code)), t1 = _mm256_broadcastsi128_si256(_mm_load_si128((const __m128i*)(qc.class_code + 16)));
     int i = 0;
     for (; i + 32 <= L; i += 32) {
         const __m256i cls = qual_class_avx2(_mm256_loadu_si256((const __m256i*)(quals + i)));
-        const __m256i code = _mm256_blendv_epi8(_mm256_shuffle_epi8(t0, cls), _mm256_shuffle_epi8(t1, _mm256_and_si256(cls, _mm256_set1_epi8(15))), _mm256_cmpgt_epi8(cls, _mm256_set1_epi8(15)));
+        const __m256i hi16 = _mm256_cmpgt_epi8(cls, _mm256_set1_epi8(15)), low4 = _mm256_and_si256(cls, _mm256_set1_epi8(15));
+        const __m256i code = _mm256_blendv_epi8(_mm256_shuffle_epi8(t0, cls), _mm256_shuffle_epi8(t1, low4), hi16);
+        all_known = _mm256_and_si256(all_known, _mm256_blendv_epi8(_mm256_shuffle_epi8(k0, cls), _mm256_shuffle_epi8(k1, low4), hi16));
         if (qc.bits == 2) {
             const uint64_t c = squeeze2_avx2(code);
             std::memcpy(out + (i >> 2), &c, 8);
@@ -288,6 +301,7 @@ __attribute__((target("avx2"))) int code_quals_avx2(const uint8_t* quals, int L,
             std::memcpy(out + (i >> 1) + 8, &hi, 8);
         }
     }
+    if (_mm256_movemask_epi8(_mm256_cmpeq_epi8(all_known, _mm256_set1_epi8((char)0xff))) != -1) *unknown = true;
     return i;
 }
 #else
@@ -299,11 +313,13 @@ struct Part {
     std::vector<ngsep_read_hdr> hdr;
     std::vector<uint32_t> payload;
     std::vector<uint8_t> qual;
+    std::vector<uint16_t> group;               // read-group id per record (only when the tile carries groups)
     size_t n_hdr = 0, n_pay = 0, n_qual = 0;   // filled sizes (the vectors only grow)
     size_t n_full = 0;                         // payload words of the records in the full layout (n_pay counts the compact stream when that is packed)
     int max_span = 1, max_back = 0;
     uint64_t aligned_bases = 0;
     bool bad = false;
+    bool unknown_quality = false;              // a quality class the tile's coder has no code for (a coder taken over from an earlier tile)
 };
 
 // bases2 / N mask / low-quality mask of one read, computed once and shared by its versions
@@ -335,7 +351,7 @@ void encode_bits(const uint8_t* bases, const uint8_t* quals, int len, ReadBits& 
 }
 
 // one read's qualities into the tile's quality array (padded run of qual_run_bytes): the bytes, or their 2- / 4-bit codes
-inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* q, size_t padded) {
+inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, uint8_t* q, size_t padded, bool* unknown) {
     if (qc.bits == 8) {
         std::memcpy(q, quals, (size_t)L);
         for (size_t k = (size_t)L; k < padded; k++) q[k] = (uint8_t)'!';
@@ -343,8 +359,9 @@ inline void code_quality_run(const uint8_t* quals, int L, const QualCoder& qc, u
     }
     int i = 0;
 #ifdef NGSEP_HAVE_AVX2_PATH
-    if (have_avx2()) i = code_quals_avx2(quals, L, qc, q);
+    if (have_avx2()) i = code_quals_avx2(quals, L, qc, q, unknown);
 #endif
+    for (int k = i; k < L; k++) if (!qc.class_known[qual_class(quals[k])]) *unknown = true;   // (the qualities the loops below code one by one)
     if (qc.bits == 2) {
         size_t o = (size_t)i >> 2;
         for (; i + 4 <= L; i += 4, o++)
@@ -422,9 +439,9 @@ struct PlanSource {
 };
 
 template <typename Src>
-void pack_range(const Src& src, size_t lo, size_t hi, const QualCoder& qc, Part& out, bool compact) {
+void pack_range(const Src& src, size_t lo, size_t hi, const QualCoder& qc, Part& out, bool compact, bool with_groups) {
     out.n_hdr = out.n_pay = out.n_qual = out.n_full = 0;
-    out.max_span = 1; out.max_back = 0; out.aligned_bases = 0; out.bad = false;
+    out.max_span = 1; out.max_back = 0; out.aligned_bases = 0; out.bad = false; out.unknown_quality = false;
     size_t n_rec = 0, n_words = 0, n_q = 0;
     int max_len = 0;
     for (size_t i = lo; i < hi; i++) {   // exact upper bounds: one reservation per array
@@ -443,6 +460,7 @@ void pack_range(const Src& src, size_t lo, size_t hi, const QualCoder& qc, Part&
     if (out.hdr.size() < n_rec) out.hdr.resize(n_rec + n_rec / 8);
     if (out.payload.size() < n_words) out.payload.resize(n_words + n_words / 8);
     if (out.qual.size() < n_q) out.qual.resize(n_q + n_q / 8);
+    if (with_groups && out.group.size() < n_rec) out.group.resize(n_rec + n_rec / 8);
     std::vector<uint32_t> scratch((size_t)((max_len + 15) / 16 + 2 * ((max_len + 31) / 32)) + 4);
     ReadBits rb{};
     rb.b2 = scratch.data();
@@ -457,24 +475,32 @@ void pack_range(const Src& src, size_t lo, size_t hi, const QualCoder& qc, Part&
         const uint32_t qoff = (uint32_t)(out.n_qual / 4);
         uint8_t* q = out.qual.data() + out.n_qual;
         const size_t padded = qual_run_bytes(L, qc.bits);
-        code_quality_run(quals, L, qc, q, padded);
+        code_quality_run(quals, L, qc, q, padded, &out.unknown_quality);
         out.n_qual += padded;
         if (L > 0xffff) { out.bad = true; continue; }
         encode_bits(bases, quals, L, rb);
+        const size_t first_rec = out.n_hdr;
         if (!hr) {
             const uint32_t cig = ((uint32_t)L << 3) | (uint32_t)kOpM;
             emit_record(pr.first, L, pr.neg, &cig, 1, pr.first, pr.ign_s, pr.ign_e, rb, false, 0, 0, qoff, out, compact);
-            continue;
+        } else {
+            const HostRead& r = *hr;
+            if (r.closed.empty() && r.st.first == r.admit_first) emit_record(r, r.st, rb, false, 0, 0, qoff, out, compact);
+            else {
+                for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out, compact);
+                emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out, compact);
+            }
         }
-        const HostRead& r = *hr;
-        if (r.closed.empty() && r.st.first == r.admit_first) { emit_record(r, r.st, rb, false, 0, 0, qoff, out, compact); continue; }
-        for (const Version& v : r.closed) emit_record(r, v.st, rb, true, v.from, v.to, qoff, out, compact);
-        emit_record(r, r.st, rb, true, r.cur_from, INT_MAX, qoff, out, compact);
+        if (with_groups) {   // one id per record: every version of a read carries the read's group
+            const int rg = hr ? hr->rg : pr.rg;
+            const uint16_t g = (rg >= 0 && rg < 0xffff) ? (uint16_t)rg : (uint16_t)0xffff;
+            for (size_t k = first_rec; k < out.n_hdr; k++) out.group[k] = g;
+        }
     }
 }
 
 template <typename Src>
-bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
+bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact, QualHint* hint = nullptr) {
     out.group.clear();
     const size_t n = hi > lo ? hi - lo : 0;
     const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 8192 + 1));   // small tiles are not worth a thread each
@@ -503,20 +529,29 @@ bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool wit
         if (vec) for (int k = 0; k < 31; k++) if ((m >> k) & 1u) hit[33 + k] = 1;   // ... each reported through a character of the class
         for (int c = 0; c < 256; c++) seen[(size_t)t][(size_t)c] = hit[c] != 0;
     };
-    Helpers::get().run(nt, scan);
-    bool any[256];
-    for (int c = 0; c < 256; c++) { any[c] = false; for (int t = 0; t < nt; t++) any[c] = any[c] || seen[(size_t)t][(size_t)c]; }
-    const QualCoder qc = choose_coder(any, min_qual_bits);
+    // The coder of the previous tile is taken over when the caller keeps one (tiles of one run share their quality alphabet): the
+    // pass over the qualities that finds the tile's classes is skipped, and the packing itself notices a class without a code —
+    // the tile is then packed again the long way.
+    const bool speculate = hint && hint->valid && (hint->bits == 2 || hint->bits == 4) && (int)hint->bits >= min_qual_bits;
+    QualCoder qc;
+    if (speculate) qc = coder_from_dict((int)hint->bits, hint->dict);
+    else {
+        Helpers::get().run(nt, scan);
+        bool any[256];
+        for (int c = 0; c < 256; c++) { any[c] = false; for (int t = 0; t < nt; t++) any[c] = any[c] || seen[(size_t)t][(size_t)c]; }
+        qc = choose_coder(any, min_qual_bits);
+    }
     out.qual_bits = (uint32_t)qc.bits;
     std::memcpy(out.qual_dict, qc.dict, 16);
     out.layout = compact ? NGSEP_LAYOUT_COMPACT : NGSEP_LAYOUT_FULL;
-    Helpers::get().run(nt, [&](int t) { size_t a, b; range_of(t, a, b); pack_range(src, a, b, qc, parts[(size_t)t], compact); });
+    Helpers::get().run(nt, [&](int t) { size_t a, b; range_of(t, a, b); pack_range(src, a, b, qc, parts[(size_t)t], compact, with_groups); });
     // contiguous ranges were packed independently: payload offsets move by the words in front of the range, quality offsets
     // (the last payload word of every record) by the quality words in front of it
     size_t nh = 0, np = 0, nq = 0;
     std::vector<size_t> bh((size_t)nt), bp((size_t)nt), bq((size_t)nt);
     bool bad = false;
     out.n_words_full = 0;
+    if (speculate) for (int t = 0; t < nt; t++) if (parts[t].unknown_quality) { hint->valid = false; return pack_source(src, lo, hi, out, with_groups, err, min_qual_bits, compact, hint); }
     for (int t = 0; t < nt; t++) { bh[t] = nh; bp[t] = np; bq[t] = nq; nh += parts[t].n_hdr; np += parts[t].n_pay; nq += parts[t].n_qual; bad = bad || parts[t].bad; out.n_words_full += parts[t].n_full; }
     if (bad) {
         if (err) *err = "read longer than 65535 bases or with more than 255 CIGAR operations (after realignment): not supported by the device layout";
@@ -524,6 +559,7 @@ bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool wit
         return false;
     }
     out.hdr.resize(nh); out.payload.resize(np); out.qual.resize(nq);
+    if (with_groups) out.group.resize(nh);
     out.max_span = 1; out.max_back = 0; out.aligned_bases = 0;
     auto place = [&](int t) {
         Part& p = parts[(size_t)t];
@@ -532,6 +568,7 @@ bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool wit
         uint32_t* op = out.payload.data() + bp[t];
         std::memcpy(op, p.payload.data(), p.n_pay * sizeof(uint32_t));
         std::memcpy(out.qual.data() + bq[t], p.qual.data(), p.n_qual);
+        if (with_groups && p.n_hdr) std::memcpy(out.group.data() + bh[t], p.group.data(), p.n_hdr * sizeof(uint16_t));
         for (size_t i = 0; i < p.n_hdr; i++) {
             ngsep_read_hdr h = p.hdr[i];
             const size_t end = (i + 1 < p.n_hdr) ? p.hdr[i + 1].off : p.n_pay;
@@ -541,21 +578,8 @@ bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool wit
         }
     };
     Helpers::get().run(nt, place);
+    if (hint) { hint->valid = true; hint->bits = out.qual_bits; std::memcpy(hint->dict, out.qual_dict, 16); }
     for (int t = 0; t < nt; t++) { out.max_span = std::max(out.max_span, parts[t].max_span); out.max_back = std::max(out.max_back, parts[t].max_back); out.aligned_bases += parts[t].aligned_bases; }
-    if (with_groups) {   // one id per record (every version of a read carries the read's group)
-        out.group.resize(out.hdr.size());
-        size_t k = 0;
-        for (size_t i = lo; i < hi; i++) {
-            const HostRead* hr = src.heavy(i);
-            size_t n_rec = 1;
-            int rg;
-            if (hr) { n_rec = (hr->closed.empty() && hr->st.first == hr->admit_first) ? 1 : hr->closed.size() + 1; rg = hr->rg; }
-            else rg = src.plain(i).rg;
-            const uint16_t g = (rg >= 0 && rg < 0xffff) ? (uint16_t)rg : (uint16_t)0xffff;
-            for (size_t v = 0; v < n_rec && k < out.hdr.size(); v++, k++) out.group[k] = g;
-        }
-        for (; k < out.hdr.size(); k++) out.group[k] = (uint16_t)0xffff;
-    }
     return true;
 }
 
@@ -564,8 +588,8 @@ bool pack_source(const Src& src, size_t lo, size_t hi, PackedTile& out, bool wit
 bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
     return pack_source(VectorSource{&reads}, lo, hi, out, with_groups, err, min_qual_bits, compact);
 }
-bool pack_plan_reads(const SeqPlan& plan, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact) {
-    return pack_source(PlanSource{&plan}, lo, hi, out, with_groups, err, min_qual_bits, compact);
+bool pack_plan_reads(const SeqPlan& plan, size_t lo, size_t hi, PackedTile& out, bool with_groups, std::string* err, int min_qual_bits, bool compact, QualHint* hint) {
+    return pack_source(PlanSource{&plan}, lo, hi, out, with_groups, err, min_qual_bits, compact, hint);
 }
 
 ngsep_tile PackedTile::view(int seq_idx, int first, int last) const {

@@ -212,10 +212,13 @@ struct PackedTile {
 // realigner rewrote it).
 bool pack_reads(const std::vector<HostRead>& reads, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0,
                 bool compact = false);
+// How the previous tile's qualities were coded (PackedTile.qual_bits / qual_dict): a caller that packs tile after tile hands it on, and
+// the packer skips its pass over the qualities as long as the tiles keep to the same classes
+struct QualHint { bool valid = false; uint32_t bits = 8; uint8_t dict[16] = {0}; };
 struct SeqPlan;
 // ... the same for reads[lo,hi) of a plan (SeqPlan::lite): untouched single-block reads are packed straight from the batch
 bool pack_plan_reads(const SeqPlan& plan, size_t lo, size_t hi, PackedTile& out, bool with_groups = false, std::string* err = nullptr, int min_qual_bits = 0,
-                     bool compact = false);
+                     bool compact = false, QualHint* hint = nullptr);
 bool wire_compact();   // the detectors pack NGSEP_LAYOUT_COMPACT tiles unless NGSEP_WIRE_COMPACT=0
 int host_threads();   // NGSEP_HOST_THREADS, else the hardware concurrency (at most 32)
 
@@ -320,6 +323,7 @@ protected:
     std::vector<std::vector<KnownVariant>> known_;   // -knownVariants: per sequence
     bool known_loaded_ = false;
     std::thread warm_;                               // warm_up()'s thread
+    QualHint qual_hint_;                             // the quality coding of the last tile packed (run_device, pack_sequence)
     int inner_threads_ = 1;                          // host threads one sequence may use for its own stages (set per run)
     bool known_mode() const { return known_loaded_ && n_known_ > 0; }   // SSVPL:147: an empty input list means discovery
     size_t n_known_ = 0;

@@ -173,6 +173,36 @@ def test_plan_without_materialised_reads_packs_the_same_tile(monkeypatch):
         assert np.array_equal(want[0], t["hdr"]) and np.array_equal(want[1], t["payload"]) and np.array_equal(want[2], t["qual"])
 
 
+def test_quality_coder_taken_over_from_the_previous_tile(monkeypatch):
+    """run_device hands the quality coding of a tile on to the next one (QualHint): the packer then skips its pass over the
+    qualities and notices a class without a code while it packs.  Same alphabet: the same bytes as a fresh scan.  A tile with a
+    new class: packed again the long way (4-bit codes here), decoding to the classes of the original qualities.  A tile that
+    uses fewer classes than the coder knows: still decodes right."""
+    monkeypatch.setenv("NGSEP_PACK_HINT", "1")
+    mk = lambda seeds, **kw: simulate.simulate(contigs=[("a", 40000)], depth=15, seeds=seeds, n_frac=0.01, read_len=101, **kw)
+    genome, b1, _ = mk((13, 14, 15))
+    _, b2, _ = mk((13, 14, 16), genome=genome)
+    _, b3, _ = mk((13, 14, 17), genome=genome, qual_vals=(2, 11, 15, 22, 27, 33, 37, 40))
+    _, b4, _ = mk((13, 14, 18), genome=genome, qual_vals=(15, 37))
+    det = hostapi.Detector(host_only=True); det.set_genome(genome)
+    fresh = lambda b: (lambda d: (d.set_genome(genome), d.pack(b, 0))[1])(hostapi.Detector(host_only=True))
+    t1, t2 = det.pack(b1, 0), det.pack(b2, 0)          # t2 is packed with t1's coder
+    f2 = fresh(b2)
+    assert t1["quality"][0] == 2 and t2["quality"] == f2["quality"]
+    for k in ("hdr", "payload", "qual"):
+        assert np.array_equal(t2[k], f2[k]), k
+    t3, f3 = det.pack(b3, 0), fresh(b3)                # new classes: the long way, like a fresh detector
+    assert t3["quality"][0] == 4 and t3["quality"] == f3["quality"] and np.array_equal(t3["qual"], f3["qual"])
+    t4 = det.pack(b4, 0)                               # two of the eight classes: t3's coder still fits
+    assert t4["quality"] == t3["quality"]
+    monkeypatch.setenv("NGSEP_QUAL_BITS", "8")
+    monkeypatch.delenv("NGSEP_PACK_HINT")
+    t8 = fresh(b4)
+    got = hostapi.decode_quality(t4["qual"], t4["hdr"], t4["payload"], t4["quality"])
+    want = hostapi.decode_quality(t8["qual"], t8["hdr"], t8["payload"], t8["quality"])
+    assert np.array_equal(_quality_class(got), _quality_class(want))
+
+
 def test_vector_packer_equals_portable_packer(tmp_path):
     """The packer codes 32 bases / qualities at a time where the host has AVX2 (chosen at run time); NGSEP_NO_AVX2=1 keeps the
     portable 8-at-a-time code.  Both give the same bytes: odd read lengths, bases outside ACGT, 2- / 4- / 8-bit quality modes."""
