@@ -11,3 +11,5 @@ if [ -f scratch_in/big.bam ]; then
   for i in 1 2 3; do ( time NGSEP_TIMING=1 ngsepcore_b200/ngsep_b200 SingleSampleVariantsDetector -i scratch_in/big.bam -r scratch_in/big.fa -o gpurun_out/cli_big ) 2>&1 | grep -E "load_al|^run:|device loop|real|^context"; done
   md5sum gpurun_out/cli_big.vcf; rm -f gpurun_out/cli_big.vcf
 fi
+timeout 600 python scripts/bench_multisample.py > gpurun_out/bench_ms.json 2> gpurun_out/bench_ms.err; echo "bench ms rc=$?"; cat gpurun_out/bench_ms.json; tail -2 gpurun_out/bench_ms.err
+timeout 600 python scripts/bench_multisample.py --mode wgs --samples 24 --depth 8 --contigs 2 --contig-len 600000 --oracle-bp 30000 > gpurun_out/bench_ms_wgs.json 2> gpurun_out/bench_ms_wgs.err; echo "bench wgs rc=$?"; cat gpurun_out/bench_ms_wgs.json; tail -2 gpurun_out/bench_ms_wgs.err
