@@ -183,29 +183,32 @@ int GpuSingleSampleVariantsDetector::run(const BatchView& b, std::string& out, b
         t_dev = now_s();
     } else {
         // The sequences are planned on the host threads while this thread already packs and submits the tiles of the sequences whose
-        // plan is ready (in the order they get ready: the results stay with their sequence): the planning stage lasts as long as its
-        // longest sequence, and packing fills the cores the short ones leave idle.
+        // plan is ready.  Both go through the sequences shortest first: the planners (sixteen at a time, each several times faster
+        // than the packing of its sequence) stay ahead of this thread from the first small sequence on, the long sequences are
+        // planned while the short ones are packed, and the tiles reach the ring in the same order in every run — a slot sees the
+        // same tile sizes again, so nothing is re-allocated or re-registered after the first run.
+        std::vector<size_t> asc(order.rbegin(), order.rend());
+        std::stable_sort(asc.begin(), asc.end(), [&](size_t x, size_t y) { return jobs[x].hi - jobs[x].lo < jobs[y].hi - jobs[y].lo; });
         std::mutex mq;
         std::condition_variable cvq;
-        std::deque<size_t> ready;
+        std::vector<char> ready(jobs.size(), 0);
         size_t handed = 0;
         bool failed = false;
         double plan_wall = 0;
         std::thread planner([&]() {
-            parallel_jobs(jobs.size(), threads, order, [&](size_t k) {
+            parallel_jobs(jobs.size(), threads, asc, [&](size_t k) {
                 jobs[k].rc = plan_sequence(b, jobs[k].seq, jobs[k].lo, jobs[k].hi, jobs[k].plan);
-                { std::lock_guard<std::mutex> g(mq); ready.push_back(k); if (jobs[k].rc != NGSEP_OK) failed = true; }
-                cvq.notify_one();
+                { std::lock_guard<std::mutex> g(mq); ready[k] = 1; if (jobs[k].rc != NGSEP_OK) failed = true; }
+                cvq.notify_all();
             });
             plan_wall = now_s() - tp;
         });
         rc = run_device(jobs, [&]() -> long {
             std::unique_lock<std::mutex> g(mq);
             if (handed == jobs.size()) return -1L;
-            cvq.wait(g, [&] { return !ready.empty(); });
+            const size_t k = asc[handed];
+            cvq.wait(g, [&] { return ready[k] != 0 || failed; });
             if (failed) return -1L;   // a sequence could not be planned: nothing more is submitted
-            const size_t k = ready.front();
-            ready.pop_front();
             handed++;
             return (long)k;
         });
