@@ -71,17 +71,34 @@ struct OwnedBatch {
 
 struct RgTable { std::vector<std::string> ids, samples; std::unordered_map<std::string, int> index; };
 
+// FASTA: the whole file in one read, lines found with memchr (a 3 Gb genome is 50 M lines: no stream, no string per line)
 bool load_fasta(const std::string& path, Genome& g) {
-    std::ifstream in(path);
+    std::ifstream in(path, std::ios::binary);
     if (!in) return false;
-    std::string line;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (!line.empty() && line[0] == '>') {
-            size_t e = line.find_first_of(" \t");  // sequences/io/FastaFileReader.java:176-185
-            g.names.push_back(line.substr(1, e == std::string::npos ? std::string::npos : e - 1));
+    in.seekg(0, std::ios::end);
+    const std::streamoff file_size = in.tellg();
+    in.seekg(0);
+    std::vector<char, NoInitAlloc<char>> raw((size_t)std::max<std::streamoff>(0, file_size));
+    if (!raw.empty() && !in.read(raw.data(), (std::streamsize)raw.size())) return false;
+    const char* p = raw.data();
+    const char* const end = p + raw.size();
+    while (p < end) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        const char* e = nl ? nl : end;
+        const char* next = nl ? nl + 1 : end;
+        if (e > p && e[-1] == '\r') e--;
+        if (e > p && *p == '>') {
+            const char* s = p + 1;
+            const char* t = s;
+            while (t < e && *t != ' ' && *t != '\t') t++;   // sequences/io/FastaFileReader.java:176-185
+            g.names.emplace_back(s, (size_t)(t - s));
             g.seqs.emplace_back();
-        } else if (!g.seqs.empty()) g.seqs.back() += line;
+            // the sequence's bases up to the next header: reserved once
+            const char* h = next;
+            while (h < end) { if (*h == '>') break; const char* n2 = (const char*)std::memchr(h, '\n', (size_t)(end - h)); if (!n2) { h = end; break; } h = n2 + 1; }
+            g.seqs.back().reserve((size_t)(h - next));
+        } else if (e > p && !g.seqs.empty()) g.seqs.back().append(p, (size_t)(e - p));
+        p = next;
     }
     return true;
 }

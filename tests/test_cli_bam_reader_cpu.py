@@ -59,6 +59,29 @@ def test_bam_and_sam_decode_to_the_same_batch(tmp_path):
     assert len(body) > 20 and outs["sam"][1] == outs["bam"][1]
 
 
+def test_fasta_reader_line_forms(tmp_path):
+    """The CLI's FASTA reader (one read of the file, lines found with memchr): descriptions after the name, CR LF line ends, another
+    line width, text in front of the first header and no newline at the end give the same genome — the same host-made records."""
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 30000), ("chrB", 9000)], depth=15, seeds=(181, 182, 183), indel_rate=3e-3, lower_frac=0.1)
+    fa, fa2, sam = (str(tmp_path / n) for n in ("r.fa", "r2.fa", "p.sam"))
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    with open(fa2, "wb") as o:
+        o.write(b"stray text\r\n")
+        for k, (name, seq) in enumerate(genome.items()):
+            o.write(b">" + name.encode() + (b" a description\twith a tab" if k == 0 else b"") + b"\r\n")
+            raw = bytes(seq)
+            for i in range(0, len(raw), 53):
+                last = k == len(genome) - 1 and i + 53 >= len(raw)
+                o.write(raw[i:i + 53] + (b"" if last else b"\r\n"))
+    outs = []
+    for f in (fa, fa2):
+        prefix = str(tmp_path / ("o_" + os.path.basename(f)))
+        subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", sam, "-r", f, "-o", prefix, "--host-only", "-ignoreLowerCaseRef"], stderr=subprocess.DEVNULL)
+        outs.append(open(prefix + ".vcf").read())
+    assert outs[0] == outs[1] and sum(1 for l in outs[0].splitlines() if not l.startswith("#")) > 20
+
+
 def test_bam_reader_rejects_garbage(tmp_path):
     fa = str(tmp_path / "r.fa")
     simulate.write_fasta(fa, {"c": np.frombuffer(b"ACGT" * 50, np.uint8)})
