@@ -115,6 +115,23 @@ def test_pipelined_run_equals_synchronous_run(oracle, tmp_path):
         assert s1.tiles == (16 if tile_len else 4)
 
 
+def test_results_behind_the_kernels_equal_copies_at_fetch(oracle, tmp_path, monkeypatch):
+    """A pipelined tile's counters, staging report and first 2048 call records come back behind its kernels into page-locked memory
+    (ngsep_tile_fetch reads host memory); NGSEP_PREFETCH=0 copies them when they are fetched, as before.  Same records either way —
+    with a tile that holds more than 2048 calls (the rest is copied at fetch time), with many small tiles, and for the oracle."""
+    genome, batch, fa, sam = _inputs(tmp_path, [("chrA", 260000), ("chrB", 60000)], depth=25, seeds=(461, 462, 463), snv_rate=1.2e-2, indel_rate=3e-4)
+    want, _, gp, _ = ou.run_ssvd(oracle, fa, sam)
+    assert sum(1 for l in _body(want) if l.startswith("chrA\t")) > 2500
+    for prefetch in ("1", "0"):
+        monkeypatch.setenv("NGSEP_PREFETCH", prefetch)       # (read when the context is created)
+        for tile_len in (0, 20000):
+            det = hostapi.Detector(tile_len=tile_len)
+            det.set_genome(genome)
+            assert det.run(batch) == want, (prefetch, tile_len)
+            assert det.stats().covered_positions == gp
+            det.close()
+
+
 @pytest.mark.parametrize("alphabet,bits", [((2, 11, 15, 22, 27, 33, 37, 40), 4), (tuple(range(2, 42)), 8), (None, 2)])
 def test_quality_code_modes_give_the_oracle_records(oracle, tmp_path, monkeypatch, alphabet, bits):
     """Qualities travel host -> device as 2- / 4-bit codes when the tile's qualities fall into at most 4 / 16 classes the path can
