@@ -109,10 +109,14 @@ void ngsep_host_free(void* p);
  * device (ngsep_coverage_histogram), the printed table (depth, positions, positions counting unique alignments only; "More") as text. */
 int ngsep_coverage_stats(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_mq, int device, char** text);
 /* RelativeAlleleCountsCalculator module (discovery/RelativeAlleleCountsCalculator.java:209-243, 246-290; option ids -i -o -m -M -q -s of
- * main/CommandsDescriptor.xml:805-847; -frs / -srs are not built): admission with maxRD alignments per start position on the host, the
+ * main/CommandsDescriptor.xml:805-847): admission with maxRD alignments per start position on the host, the
  * allele counts of every position per region tile on the device (ngsep_tile_allele_counts), the three distributions of the report as text. */
 int ngsep_relative_allele_counts(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_rd, int max_rd,
                                  int min_base_qs, int secondary, int device, char** text);
+/* ... with the region files of -frs (regions to filter) and -srs (regions to select), NULL = none (RelativeAlleleCountsCalculator.java:131-161,
+ * 247-254; genome/io/SimpleGenomicRegionFileHandler.java:57-80: sequence, first, last in the first three blank- or tab-separated fields). */
+int ngsep_relative_allele_counts_regions(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* batch, int min_rd, int max_rd,
+                                         int min_base_qs, int secondary, const char* regions_to_filter, const char* regions_to_select, int device, char** text);
 /* How the quality array of the tile the calling thread packed last (ngsep_host_pack / ngsep_ssvd_pack) is coded: the values for
  * ngsep_tile.qual_bits and ngsep_tile.qual_dict. */
 /* ... and how its payload is laid out: the values for ngsep_tile.layout and ngsep_tile.n_words (the detector packs NGSEP_LAYOUT_COMPACT tiles —

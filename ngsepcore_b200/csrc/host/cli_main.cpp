@@ -533,7 +533,7 @@ void merge_inputs(const std::vector<OwnedBatch>& files, const AdmissionOptions& 
 }
 
 void usage() {
-    std::fprintf(stderr, "usage: ngsep_b200 RelativeAlleleCountsCalculator -i <alignments.sam|.bam> -r <genome.fa> [-o <out.txt>] [-m minRD] [-M maxRD] [-q minBaseQS] [-s]\n");
+    std::fprintf(stderr, "usage: ngsep_b200 RelativeAlleleCountsCalculator -i <alignments.sam|.bam> -r <genome.fa> [-o <out.txt>] [-m minRD] [-M maxRD] [-q minBaseQS] [-s] [-frs regionsToFilter] [-srs regionsToSelect]\n");
     std::fprintf(stderr, "usage: ngsep_b200 CoverageStats -i <alignments.sam|.bam> -r <genome.fa> [-o <out.txt>] [-minMQ N]\n");
     std::fprintf(stderr, "usage: ngsep_b200 MultisampleVariantsDetector -r <genome.fa> -o <out.vcf> [options] <alignments.sam|.bam>*\n"
                          "       ngsep_b200 SingleSampleVariantsDetector -i <alignments.sam|.bam> -r <genome.fa> -o <outputPrefix>\n"
@@ -551,8 +551,8 @@ int main(int argc, char** argv) {
     mallopt(M_MMAP_THRESHOLD, 1 << 30);
     mallopt(M_TRIM_THRESHOLD, 1 << 30);
     if (argc >= 2 && (!std::strcmp(argv[1], "RelativeAlleleCountsCalculator") || !std::strcmp(argv[1], "RelativeAlleleCounts"))) {
-        // RelativeAlleleCountsCalculator (main/CommandsDescriptor.xml:805-847: -i, -o, -r, -m, -M, -q, -s; -frs / -srs are not built)
-        std::string in, ref, out;
+        // RelativeAlleleCountsCalculator (main/CommandsDescriptor.xml:805-847: -i, -o, -r, -m, -M, -q, -s, -frs, -srs)
+        std::string in, ref, out, frs, srs;
         int min_rd = 10, max_rd = 1000, min_bq = 20, device = 0;
         bool secondary = false;
         for (int i = 2; i < argc; i++) {
@@ -561,6 +561,7 @@ int main(int argc, char** argv) {
             if (a == "-i") in = val(); else if (a == "-r") ref = val(); else if (a == "-o") out = val();
             else if (a == "-m") min_rd = std::atoi(val()); else if (a == "-M") max_rd = std::atoi(val()); else if (a == "-q") min_bq = std::atoi(val());
             else if (a == "-s") secondary = true; else if (a == "--device") device = std::atoi(val());
+            else if (a == "-frs") frs = val(); else if (a == "-srs") srs = val();
             else { std::fprintf(stderr, "Unrecognized option %s\n", a.c_str()); usage(); return 1; }
         }
         if (in.empty()) { std::fprintf(stderr, "The alignments input file is a required parameter\n"); return 2; }   // RelativeAlleleCountsCalculator.java:183
@@ -570,7 +571,7 @@ int main(int argc, char** argv) {
         OwnedBatch b;
         std::string err, text;
         if (!load_alignments(in, g, b, err)) { std::fprintf(stderr, "%s\n", err.c_str()); return 2; }
-        int rc = run_relative_allele_counts(g, b.view(), min_rd, max_rd, min_bq, secondary, device, text, err);
+        int rc = run_relative_allele_counts(g, b.view(), min_rd, max_rd, min_bq, secondary, device, text, err, frs, srs);
         if (rc != 0) { std::fprintf(stderr, "ngsep_b200: %s (code %d)\n", err.c_str(), rc); return 3; }
         if (out.empty()) std::fwrite(text.data(), 1, text.size(), stdout);
         else { std::ofstream os(out); os << text; }

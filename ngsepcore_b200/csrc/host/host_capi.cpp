@@ -233,11 +233,17 @@ int ngsep_coverage_stats(int n_seqs, const char* const* names, const int64_t* le
 
 int ngsep_relative_allele_counts(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* b, int min_rd, int max_rd, int min_base_qs,
                                  int secondary, int device, char** text) {
+    return ngsep_relative_allele_counts_regions(n_seqs, names, lengths, b, min_rd, max_rd, min_base_qs, secondary, nullptr, nullptr, device, text);
+}
+
+int ngsep_relative_allele_counts_regions(int n_seqs, const char* const* names, const int64_t* lengths, const ngsep_host_batch* b, int min_rd, int max_rd,
+                                         int min_base_qs, int secondary, const char* regions_to_filter, const char* regions_to_select, int device, char** text) {
     if (n_seqs <= 0 || !names || !lengths || !b || !text) return NGSEP_EINVAL;
     Genome g;
     for (int i = 0; i < n_seqs; i++) { g.names.emplace_back(names[i]); g.seqs.emplace_back((size_t)lengths[i], 'N'); }   // only the lengths matter here
     std::string out, err;
-    int rc = run_relative_allele_counts(g, view_of(b), min_rd, max_rd, min_base_qs, secondary != 0, device, out, err);
+    int rc = run_relative_allele_counts(g, view_of(b), min_rd, max_rd, min_base_qs, secondary != 0, device, out, err, regions_to_filter ? regions_to_filter : "",
+                                        regions_to_select ? regions_to_select : "");
     if (rc != NGSEP_OK) return rc;
     *text = (char*)std::malloc(out.size() + 1);
     if (!*text) return NGSEP_ENOMEM;

@@ -386,8 +386,9 @@ std::vector<int> impl_copy_numbers(const std::vector<int>& called, const std::ve
 void append_gt(std::string& s, const std::vector<int>& called, int ploidy);   // VCFFileWriter.java:171-199
 
 // RelativeAlleleCountsCalculator.runProcess + printResults over a batch (allele_counts.cpp): the report text goes to `out`
+// regions_to_filter / regions_to_select: the -frs / -srs region files ("" = none)
 int run_relative_allele_counts(const Genome& genome, const BatchView& b, int min_rd, int max_rd, int min_base_qs, bool secondary, int device, std::string& out,
-                               std::string& err);
+                               std::string& err, const std::string& regions_to_filter = std::string(), const std::string& regions_to_select = std::string());
 // CoverageStatisticsCalculator.processFile + printCoverageStats over a batch (coverage.cpp): the table text goes to `out`
 int run_coverage_stats(const Genome& genome, const BatchView& b, int min_mq, int device, std::string& out, std::string& err);
 

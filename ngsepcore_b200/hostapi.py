@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsep_host.so")
 EXPORTS = ["ngsep_detector_options_default", "ngsep_ssvd_create", "ngsep_msvd_create", "ngsep_ssvd_destroy", "ngsep_ssvd_error", "ngsep_ssvd_set_genome",
            "ngsep_ssvd_run", "ngsep_ssvd_vcf", "ngsep_ssvd_stats", "ngsep_ssvd_pack", "ngsep_host_pack", "ngsep_host_free",
-           "ngsep_host_merge_order", "ngsep_host_pack_quality", "ngsep_coverage_stats", "ngsep_relative_allele_counts", "ngsep_host_pack_layout"]
+           "ngsep_host_merge_order", "ngsep_host_pack_quality", "ngsep_coverage_stats", "ngsep_relative_allele_counts", "ngsep_relative_allele_counts_regions", "ngsep_host_pack_layout"]
 
 
 class HostBatch(C.Structure):
@@ -76,6 +76,8 @@ def load_library() -> C.CDLL:
     lib.ngsep_host_pack_quality.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)]
     lib.ngsep_relative_allele_counts.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                  C.POINTER(C.c_void_p)]
+    lib.ngsep_relative_allele_counts_regions.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.c_int,
+                                                         C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     lib.ngsep_coverage_stats.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.POINTER(HostBatch), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     lib.ngsep_host_merge_order.argtypes = [C.c_int, C.POINTER(HostBatch), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_int64)]
@@ -207,16 +209,19 @@ def merge_batches(batches, minMQ: int = 20, p: bool = False, s: bool = False) ->
                           _gather_ranges(quals, b_start[cat_idx], bl_o), names, samples)
 
 
-def relative_allele_counts(batch: AlignmentBatch, m: int = 10, M: int = 1000, q: int = 20, s: bool = False, device: int = 0) -> str:
+def relative_allele_counts(batch: AlignmentBatch, m: int = 10, M: int = 1000, q: int = 20, s: bool = False, device: int = 0, frs: str | None = None,
+                           srs: str | None = None) -> str:
     """GPU drop-in for the RelativeAlleleCountsCalculator module (reference: src/ngsep/discovery/RelativeAlleleCountsCalculator.java; keyword
-    names = its option ids: -m minRD, -M maxRD, -q minBaseQualityScore, -s secondary alignments): the report text."""
+    names = its option ids: -m minRD, -M maxRD, -q minBaseQualityScore, -s secondary alignments, -frs / -srs files with the regions to
+    filter / to select): the report text."""
     lib = load_library()
     hb, keep = _host_batch(batch)
     n = len(batch.contig_names)
     names = (C.c_char_p * n)(*[x.encode() for x in batch.contig_names])
     lens = (C.c_int64 * n)(*[int(l) for l in batch.contig_lengths])
     text = C.c_void_p()
-    rc = lib.ngsep_relative_allele_counts(n, names, lens, C.byref(hb), m, M, q, int(s), device, C.byref(text))
+    rc = lib.ngsep_relative_allele_counts_regions(n, names, lens, C.byref(hb), m, M, q, int(s), frs.encode() if frs else None, srs.encode() if srs else None, device,
+                                                  C.byref(text))
     if rc != 0:
         raise NgsepError(f"ngsep_relative_allele_counts failed ({rc})")
     out = C.string_at(text).decode()

@@ -342,8 +342,53 @@ struct Distribution {
 
 // ---- discovery/RelativeAlleleCountsCalculator.java -----------------------------------------------------------------------------
 // The listener (onPileup :246-290, onSequenceStart :309-320, printResults :221-243) on the generator runProcess configures for it
-// (:209-219): secondary alignments on request, maxRD alignments per start position.  (Regions to filter / select: not restated.)
+// (:209-219): secondary alignments on request, maxRD alignments per start position.
+//
+// Regions to filter / select (-frs, -srs; :131-161, onPileup :247-254): region files read by
+// genome/io/SimpleGenomicRegionFileHandler.loadRegions (:57-80: items = line.split(" |\t"); sequence, Integer.parseInt(first),
+// Integer.parseInt(last); a line that does not parse is skipped with a warning), looked up with findSpanningRegions(sequence,
+// position): the regions of that sequence with first <= position <= last.
+struct OracleRegions {
+    std::map<std::string, std::vector<std::pair<int, int>>> of_seq;
+    bool given = false;
+    static bool parse_int(const std::string& t, int& v) {   // Integer.parseInt: optional sign, decimal digits, int range
+        if (t.empty()) return false;
+        size_t i = (t[0] == '-' || t[0] == '+') ? 1 : 0;
+        if (i == t.size()) return false;
+        long long x = 0;
+        for (; i < t.size(); i++) { if (t[i] < '0' || t[i] > '9') return false; x = x * 10 + (t[i] - '0'); if (x > 2147483648LL) return false; }
+        if (t[0] == '-') x = -x;
+        if (x > 2147483647LL || x < -2147483648LL) return false;
+        v = (int)x;
+        return true;
+    }
+    bool load(const char* path) {
+        if (!path || !*path) return true;
+        std::ifstream in(path);
+        if (!in) return false;
+        given = true;
+        std::string line;
+        while (std::getline(in, line)) {
+            if (!line.empty() && line.back() == '\r') line.pop_back();
+            std::vector<std::string> items(1);
+            for (char c : line) { if (c == ' ' || c == '\t') items.emplace_back(); else items.back() += c; }
+            while (!items.empty() && items.back().empty()) items.pop_back();   // String.split drops trailing empty strings
+            int first, last;
+            if (items.size() < 3 || !parse_int(items[1], first) || !parse_int(items[2], last)) continue;
+            of_seq[items[0]].push_back({first, last});
+        }
+        return true;
+    }
+    bool spanning(const std::string& seq, int pos) const {
+        auto it = of_seq.find(seq);
+        if (it == of_seq.end()) return false;
+        for (auto& r : it->second) if (r.first <= pos && pos <= r.second) return true;
+        return false;
+    }
+};
+
 struct RelativeAlleleCountsCalculator : PileupListener {
+    OracleRegions filter, select;
     int min_rd = 10, min_bq = 20;
     const ReferenceGenome* genome = nullptr;
     Distribution dist_prop{0, 0.5, 0.01}, dist_num{1, 10, 1};
@@ -351,6 +396,8 @@ struct RelativeAlleleCountsCalculator : PileupListener {
     std::vector<Distribution> per_seq;
     bool cur = false;
     void on_pileup(PileupRecord& p) override {
+        if (filter.given && filter.spanning(p.seq, p.pos)) return;    // :247-250
+        if (select.given && !select.spanning(p.seq, p.pos)) return;   // :251-254
         auto calls = p.allele_calls(1, (const std::string*)nullptr);
         if ((int)calls.size() < min_rd) return;
         std::map<std::string, int> counts;   // TreeMap
@@ -401,13 +448,20 @@ struct RelativeAlleleCountsCalculator : PileupListener {
     }
 };
 
+char* oracle_run_relative_allele_counts_regions(const char* fasta_path, const char* sam_path, int min_rd, int max_rd, int min_bq, int secondary, const char* frs,
+                                                const char* srs, double* seconds);
 char* oracle_run_relative_allele_counts(const char* fasta_path, const char* sam_path, int min_rd, int max_rd, int min_bq, int secondary, double* seconds) {
+    return oracle_run_relative_allele_counts_regions(fasta_path, sam_path, min_rd, max_rd, min_bq, secondary, nullptr, nullptr, seconds);
+}
+char* oracle_run_relative_allele_counts_regions(const char* fasta_path, const char* sam_path, int min_rd, int max_rd, int min_bq, int secondary, const char* frs,
+                                                const char* srs, double* seconds) {
     ReferenceGenome genome = ReferenceGenome::load_fasta(fasta_path);
     std::ifstream sam(sam_path);
     if (!sam) return nullptr;
     auto t0 = std::chrono::steady_clock::now();
     RelativeAlleleCountsCalculator calc;
     calc.min_rd = min_rd; calc.min_bq = min_bq; calc.genome = &genome;
+    if (!calc.filter.load(frs) || !calc.select.load(srs)) return nullptr;
     AlignmentsPileupGenerator gen;
     gen.secondary = secondary != 0;      // setProcessSecondaryAlignments(secondaryAlns)
     gen.max_alns_per_start = max_rd;     // setMaxAlnsPerStartPos(maxRD)

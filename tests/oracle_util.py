@@ -40,6 +40,8 @@ def load_oracle():
     lib.oracle_run_coverage_stats.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
     lib.oracle_run_relative_allele_counts.restype = C.c_void_p
     lib.oracle_run_relative_allele_counts.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    lib.oracle_run_relative_allele_counts_regions.restype = C.c_void_p
+    lib.oracle_run_relative_allele_counts_regions.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.POINTER(C.c_double)]
     lib.oracle_english_fmt.argtypes = [C.c_double, C.c_char_p]
     lib.oracle_string_hashset_order.argtypes = [C.c_int, C.POINTER(C.c_char_p), ip]
     lib.oracle_diversity_info.argtypes = [C.c_int, C.c_int, ip, ip, C.c_char_p]
@@ -106,10 +108,11 @@ def run_coverage_stats(lib, fasta, sam, min_mq=20):
     return text, sec.value
 
 
-def run_relative_allele_counts(lib, fasta, sam, min_rd=10, max_rd=1000, min_bq=20, secondary=False):
-    """The oracle's RelativeAlleleCountsCalculator on a SAM file -> (report text, seconds)."""
+def run_relative_allele_counts(lib, fasta, sam, min_rd=10, max_rd=1000, min_bq=20, secondary=False, frs=None, srs=None):
+    """The oracle's RelativeAlleleCountsCalculator on a SAM file -> (report text, seconds).  frs / srs: region files to filter / select."""
     sec = C.c_double(0)
-    res = lib.oracle_run_relative_allele_counts(fasta.encode(), sam.encode(), min_rd, max_rd, min_bq, int(secondary), C.byref(sec))
+    res = lib.oracle_run_relative_allele_counts_regions(fasta.encode(), sam.encode(), min_rd, max_rd, min_bq, int(secondary), frs.encode() if frs else None,
+                                                        srs.encode() if srs else None, C.byref(sec))
     if not res:
         raise RuntimeError("oracle RelativeAlleleCounts run failed")
     text = C.string_at(res).decode()

@@ -36,6 +36,33 @@ def test_plain_alignments_match_the_oracle(oracle, tmp_path):
     assert count > 400000 and float(lines[1].split("\t")[1]) < count        # positions with a second allele exist
 
 
+def test_regions_to_filter_and_to_select(oracle, tmp_path):
+    """-frs / -srs (RelativeAlleleCountsCalculator.java:131-161, 247-254): positions inside a region to filter are skipped, with regions
+    to select only the positions inside one of them count.  Region files as SimpleGenomicRegionFileHandler reads them: tabs or single
+    blanks, extra columns, overlapping and nested regions, a sequence the genome does not have, lines that do not parse (two blanks in
+    a row, words for numbers, too few fields), a region with first > last.  Python binding and CLI, each against the oracle."""
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 180000), ("chrB", 60000)], depth=22, seeds=(451, 452, 453), indel_rate=1e-3, snv_rate=5e-3)
+    fa, sam, frs, srs = (str(tmp_path / n) for n in ("r.fa", "r.sam", "filter.txt", "select.txt"))
+    simulate.write_fasta(fa, genome)
+    simulate.write_sam(sam, batch)
+    open(frs, "w").write("chrA\t1000\t30000\textra column\nchrA 20000 45000\nchrA\t21000\t22000\nchrB\t59000\t70000\nchrZ\t1\t100000\n"
+                         "chrA  50000 60000\nchrA\tfifty\t60000\nchrB\t100\nchrB\t9000\t8000\n\nchrA\t+170000\t175000\r\n")
+    open(srs, "w").write("chrA\t10000\t120000\nchrB\t1\t30000\nchrB\t25000\t31000\n")
+    base, _ = ou.run_relative_allele_counts(oracle, fa, sam)
+    count = lambda text: int([l for l in text.splitlines() if l.startswith("Count")][0].split("\t")[1])
+    seen = set()
+    for kw in (dict(frs=frs), dict(srs=srs), dict(frs=frs, srs=srs, m=5, q=25)):
+        want, _ = ou.run_relative_allele_counts(oracle, fa, sam, min_rd=kw.get("m", 10), min_bq=kw.get("q", 20), frs=kw.get("frs"), srs=kw.get("srs"))
+        assert hostapi.relative_allele_counts(batch, **kw) == want, kw
+        assert 1000 < count(want) < count(base)
+        seen.add(count(want))
+        out = str(tmp_path / "rac.txt")
+        opts = [x for k, v in kw.items() for x in ("-" + k, str(v))]
+        subprocess.check_call([CLI, "RelativeAlleleCountsCalculator", "-i", sam, "-r", fa, "-o", out] + opts, stderr=subprocess.DEVNULL)
+        assert open(out).read() == want, opts
+    assert len(seen) == 3
+
+
 def test_mutated_records_through_the_cli(oracle, tmp_path):
     from tests.test_gpu_sam_torture import _mutate
     genome, batch, _ = simulate.simulate(contigs=[("chrA", 120000), ("chrB", 30000)], depth=25, seeds=(431, 432, 433), indel_rate=1e-3, n_read_groups=2)
