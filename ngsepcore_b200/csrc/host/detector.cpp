@@ -574,6 +574,7 @@ int GpuSingleSampleVariantsDetector::plan_sequence(const BatchView& b, int seq, 
     plan.max_reach = 1;
     plan.max_back = 0;
     for (const LiteRead& l : reads) {
+        if (l.heavy == kLiteComplex) { plan.err = "internal error: a read with a CIGAR of its own left the sweep without its HostRead"; return NGSEP_ESTATE; }
         if (l.heavy < 0) { plan.max_reach = std::max(plan.max_reach, l.last - l.first + 1); continue; }
         const HostRead& r = plan.heavy[(size_t)l.heavy];
         int lastp = r.st.last, firstp = r.st.first;
