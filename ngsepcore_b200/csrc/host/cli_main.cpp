@@ -292,6 +292,189 @@ bool bgzf_inflate(const std::string& path, RawBytes& out, std::string& err) {
     return true;
 }
 
+// What a reader thread decodes: a contiguous range of records as a batch of its own, read-group ids numbered locally in the order of
+// their first appearance in the range.
+struct Part { OwnedBatch b; std::vector<std::string> rg_ids; std::unordered_map<std::string, int> rg_index; std::string err; };
+
+// The parts of a file, in file order, appended to the loader's batch; read-group ids get the index the sequential reader gives them
+// (Loader::record: the order of their first appearance in the file), the first error in file order is the file's error.
+bool merge_parts(Loader& ld, std::vector<Part>& parts) {
+    const int nt = (int)parts.size();
+    for (auto& part : parts) if (!part.err.empty()) { ld.err = part.err; return false; }   // (the first one in file order)
+    // ---- the parts side by side ------------------------------------------------------------------------------------------------
+    OwnedBatch& out = ld.b;
+    std::vector<size_t> rec0((size_t)nt + 1, out.first.size()), cig0((size_t)nt + 1, out.cigar.size()), base0((size_t)nt + 1, out.bases.size());
+    std::vector<std::vector<int16_t>> rg_map((size_t)nt);
+    for (int t = 0; t < nt; t++) {
+        Part& part = parts[(size_t)t];
+        rec0[(size_t)t + 1] = rec0[(size_t)t] + part.b.first.size();
+        cig0[(size_t)t + 1] = cig0[(size_t)t] + part.b.cigar.size();
+        base0[(size_t)t + 1] = base0[(size_t)t] + part.b.bases.size();
+        for (const std::string& id : part.rg_ids) {   // Loader::record's table, in the order of first appearance
+            auto r = ld.rg_of().emplace(id, (int)ld.rg_of().size());
+            if (ld.rgs && r.second) { ld.rgs->ids.push_back(id); ld.rgs->samples.push_back(std::string(1, '\0')); }   // on records only: no sample
+            rg_map[(size_t)t].push_back((int16_t)r.first->second);
+        }
+    }
+    const size_t n_all = rec0[(size_t)nt];
+    out.seq_idx.resize(n_all); out.first.resize(n_all); out.flags.resize(n_all); out.mapq.resize(n_all); out.rg.resize(n_all); out.nh.resize(n_all);
+    out.name_hash.resize(n_all); out.cigar_off.resize(n_all + 1); out.base_off.resize(n_all + 1);
+    out.cigar.resize(cig0[(size_t)nt]); out.bases.resize(base0[(size_t)nt]); out.quals.resize(base0[(size_t)nt]);
+    on_threads(nt, [&](int t) {
+        OwnedBatch& b = parts[(size_t)t].b;
+        const size_t n = b.first.size(), at = rec0[(size_t)t];
+        if (!n) return;
+        std::memcpy(out.seq_idx.data() + at, b.seq_idx.data(), n * sizeof(int32_t));
+        std::memcpy(out.first.data() + at, b.first.data(), n * sizeof(int32_t));
+        std::memcpy(out.flags.data() + at, b.flags.data(), n * sizeof(uint16_t));
+        std::memcpy(out.mapq.data() + at, b.mapq.data(), n);
+        std::memcpy(out.nh.data() + at, b.nh.data(), n * sizeof(int16_t));
+        std::memcpy(out.name_hash.data() + at, b.name_hash.data(), n * sizeof(uint64_t));
+        const std::vector<int16_t>& m = rg_map[(size_t)t];
+        for (size_t i = 0; i < n; i++) out.rg[at + i] = b.rg[i] < 0 ? (int16_t)-1 : m[(size_t)b.rg[i]];
+        for (size_t i = 0; i < n; i++) {   // (a part's offset arrays start with their own 0)
+            out.cigar_off[at + i + 1] = (int64_t)cig0[(size_t)t] + b.cigar_off[i + 1];
+            out.base_off[at + i + 1] = (int64_t)base0[(size_t)t] + b.base_off[i + 1];
+        }
+        if (!b.cigar.empty()) std::memcpy(out.cigar.data() + cig0[(size_t)t], b.cigar.data(), b.cigar.size() * sizeof(uint32_t));
+        if (!b.bases.empty()) {
+            std::memcpy(out.bases.data() + base0[(size_t)t], b.bases.data(), b.bases.size());
+            std::memcpy(out.quals.data() + base0[(size_t)t], b.quals.data(), b.quals.size());
+        }
+        OwnedBatch().swap_storage(b);
+    });
+    return true;
+}
+
+// SAM text on all host threads: the file in one read, the header lines at its top handled one by one (Loader::header_line), the
+// alignment lines cut into ranges at line ends and decoded into parts like BAM records.  A file with an '@' line below its first
+// alignment line (the sequential reader takes it as a header line wherever it stands), a small file, or one thread: the
+// sequential reader.
+bool load_sam_parallel(const std::string& path, Loader& ld, bool& handled) {
+    handled = false;
+    const int threads = host_threads();
+    if (threads < 2) return true;
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return true;
+    in.seekg(0, std::ios::end);
+    const std::streamoff file_size = in.tellg();
+    in.seekg(0);
+    size_t part_records = 20000;
+    if (const char* e = std::getenv("NGSEP_BAM_PART_RECORDS")) { const long v = std::atol(e); if (v >= 1) part_records = (size_t)v; }
+    if (file_size < (std::streamoff)(part_records * 200)) return true;   // (about one part: not worth it)
+    std::vector<char, NoInitAlloc<char>> raw((size_t)file_size);
+    if (!in.read(raw.data(), (std::streamsize)raw.size())) return true;
+    const char* const base = raw.data();
+    const char* const end = base + raw.size();
+    // the header block
+    const char* p = base;
+    std::vector<std::pair<const char*, const char*>> header;
+    while (p < end && (*p == '@' || *p == '\n')) {
+        const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+        const char* e = nl ? nl : end;
+        if (e > p) header.emplace_back(p, e);
+        p = nl ? nl + 1 : end;
+    }
+    const char* const body = p;
+    for (const char* q = body; q < end;) {   // an '@' line further down: leave the file to the sequential reader
+        const char* nl = (const char*)std::memchr(q, '\n', (size_t)(end - q));
+        if (!nl) break;
+        if (nl + 1 < end && nl[1] == '@') return true;
+        q = nl + 1;
+    }
+    handled = true;
+    for (auto& h : header) if (!ld.header_line(std::string(h.first, h.second))) return false;
+    const size_t body_bytes = (size_t)(end - body);
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads, body_bytes / (part_records * 200) + 1));
+    std::vector<const char*> cut((size_t)nt + 1, end);
+    cut[0] = body;
+    for (int t = 1; t < nt; t++) {
+        const char* q = body + body_bytes * (size_t)t / (size_t)nt;
+        if (q < cut[(size_t)t - 1]) q = cut[(size_t)t - 1];
+        const char* nl = (const char*)std::memchr(q, '\n', (size_t)(end - q));
+        cut[(size_t)t] = nl ? nl + 1 : end;
+    }
+    std::vector<Part> parts((size_t)nt);
+    on_threads(nt, [&](int t) {
+        Part& part = parts[(size_t)t];
+        OwnedBatch& b = part.b;
+        const char* q = cut[(size_t)t];
+        const char* const stop = cut[(size_t)t + 1];
+        {
+            const size_t bytes = (size_t)(stop - q), guess = bytes / 150 + 16;
+            b.seq_idx.reserve(guess); b.first.reserve(guess); b.flags.reserve(guess); b.mapq.reserve(guess); b.rg.reserve(guess); b.nh.reserve(guess);
+            b.cigar_off.reserve(guess + 1); b.base_off.reserve(guess + 1); b.name_hash.reserve(guess); b.cigar.reserve(guess * 2);
+            b.bases.reserve(bytes / 2 + 16); b.quals.reserve(bytes / 2 + 16);
+        }
+        std::vector<std::string_view> f;
+        std::vector<uint32_t> cg;
+        std::string key;
+        while (q < stop) {
+            const char* nl = (const char*)std::memchr(q, '\n', (size_t)(stop - q));
+            const char* e = nl ? nl : stop;
+            const char* next = nl ? nl + 1 : stop;
+            if (e == q) { q = next; continue; }
+            f.clear();
+            for (const char* s0 = q;;) {
+                const char* tab = (const char*)std::memchr(s0, '\t', (size_t)(e - s0));
+                f.emplace_back(s0, (size_t)((tab ? tab : e) - s0));
+                if (!tab) break;
+                s0 = tab + 1;
+            }
+            q = next;
+            if (f.size() < 11) continue;
+            key.assign(f[2].data(), f[2].size());
+            auto it = ld.seq_of.find(key);
+            if (it == ld.seq_of.end()) continue;  // unmapped / unknown reference
+            cg.clear();
+            if (f[5] != "*") {
+                int n = 0; bool bad = false;
+                for (char c : f[5]) {
+                    if (c >= '0' && c <= '9') n = n * 10 + (c - '0');
+                    else { const char* codes = "HDIMPNSX"; const char* pc = std::strchr(codes, c); int op = (pc && c) ? (int)(pc - codes) : (c == '=' ? 3 : -1); if (op < 0) { bad = true; break; } cg.push_back(cig_make(n, op)); n = 0; }
+                }
+                if (bad) continue;
+            }
+            bool has_rg = false;
+            std::string_view rg_id;
+            int nh = -1;
+            for (size_t k = 11; k < f.size(); k++) {
+                if (f[k].size() >= 5 && !std::memcmp(f[k].data(), "RG:Z:", 5)) { rg_id = f[k].substr(5); has_rg = true; }
+                else if (f[k].size() >= 5 && !std::memcmp(f[k].data(), "NH:i:", 5)) nh = std::atoi(std::string(f[k].substr(5)).c_str());
+            }
+            auto to_int = [](std::string_view v) { return std::atoi(std::string(v).c_str()); };
+            // ---- Loader::record, into the part ---------------------------------------------------------------------------------
+            b.seq_idx.push_back(it->second);
+            b.first.push_back(to_int(f[3]));
+            b.flags.push_back((uint16_t)to_int(f[1]));
+            b.mapq.push_back((uint8_t)std::min(255, to_int(f[4])));
+            int16_t rg = -1;
+            if (has_rg) {
+                key.assign(rg_id.data(), rg_id.size());
+                auto ins = part.rg_index.emplace(key, (int)part.rg_ids.size());
+                if (ins.second) part.rg_ids.push_back(key);
+                rg = (int16_t)ins.first->second;
+            }
+            b.rg.push_back(rg);
+            b.nh.push_back((int16_t)std::max(-1, std::min(32000, nh)));
+            b.cigar.insert(b.cigar.end(), cg.begin(), cg.end());
+            b.cigar_off.push_back((int64_t)b.cigar.size());
+            if (f[9] != "*") {
+                const size_t L = f[9].size(), at = b.bases.size();
+                b.bases.resize(at + L);
+                b.quals.resize(at + L);
+                std::memcpy(b.bases.data() + at, f[9].data(), L);
+                uint8_t* qs = b.quals.data() + at;
+                if (f[10] == "*" || f[10].empty()) std::memset(qs, '+', L);                           // RA:1025
+                else for (size_t k = 0; k < L; k++) qs[k] = k < f[10].size() ? (uint8_t)std::min(127, (int)(unsigned char)f[10][k]) : (uint8_t)38;   // RA:581-595
+            }
+            b.base_off.push_back((int64_t)b.bases.size());
+            b.name_hash.push_back(std::hash<std::string_view>()(f[0]));
+        }
+    });
+    return merge_parts(ld, parts);
+}
+
 // The records of a BAM file, decoded on all host threads.  One pass finds the record boundaries; contiguous ranges of records are
 // then decoded independently into parts of the batch; the parts are laid side by side.  Read-group ids get the index the
 // sequential reader gives them — the order of their first appearance in the file (RAFR:184-197 for the header's) — because the
@@ -341,7 +524,6 @@ bool load_bam(const std::string& path, Loader& ld) {
         p += 4 + block;
     }
     // ---- the records, range by range ------------------------------------------------------------------------------------------
-    struct Part { OwnedBatch b; std::vector<std::string> rg_ids; std::unordered_map<std::string, int> rg_index; std::string err; };
     const size_t n_rec = rec_at.size();
     size_t part_records = 20000;   // a part is not worth a thread below this (NGSEP_BAM_PART_RECORDS: test hook)
     if (const char* e = std::getenv("NGSEP_BAM_PART_RECORDS")) { const long v = std::atol(e); if (v >= 1) part_records = (size_t)v; }
@@ -463,50 +645,7 @@ bool load_bam(const std::string& path, Loader& ld) {
             b.name_hash.push_back(std::hash<std::string_view>()(std::string_view((const char*)d.data() + name_at, name_len)));
         }
     });
-    for (auto& part : parts) if (!part.err.empty()) { ld.err = part.err; return false; }   // (the first one in file order)
-    // ---- the parts side by side ------------------------------------------------------------------------------------------------
-    OwnedBatch& out = ld.b;
-    std::vector<size_t> rec0((size_t)nt + 1, out.first.size()), cig0((size_t)nt + 1, out.cigar.size()), base0((size_t)nt + 1, out.bases.size());
-    std::vector<std::vector<int16_t>> rg_map((size_t)nt);
-    for (int t = 0; t < nt; t++) {
-        Part& part = parts[(size_t)t];
-        rec0[(size_t)t + 1] = rec0[(size_t)t] + part.b.first.size();
-        cig0[(size_t)t + 1] = cig0[(size_t)t] + part.b.cigar.size();
-        base0[(size_t)t + 1] = base0[(size_t)t] + part.b.bases.size();
-        for (const std::string& id : part.rg_ids) {   // Loader::record's table, in the order of first appearance
-            auto r = ld.rg_of().emplace(id, (int)ld.rg_of().size());
-            if (ld.rgs && r.second) { ld.rgs->ids.push_back(id); ld.rgs->samples.push_back(std::string(1, '\0')); }   // on records only: no sample
-            rg_map[(size_t)t].push_back((int16_t)r.first->second);
-        }
-    }
-    const size_t n_all = rec0[(size_t)nt];
-    out.seq_idx.resize(n_all); out.first.resize(n_all); out.flags.resize(n_all); out.mapq.resize(n_all); out.rg.resize(n_all); out.nh.resize(n_all);
-    out.name_hash.resize(n_all); out.cigar_off.resize(n_all + 1); out.base_off.resize(n_all + 1);
-    out.cigar.resize(cig0[(size_t)nt]); out.bases.resize(base0[(size_t)nt]); out.quals.resize(base0[(size_t)nt]);
-    on_threads(nt, [&](int t) {
-        OwnedBatch& b = parts[(size_t)t].b;
-        const size_t n = b.first.size(), at = rec0[(size_t)t];
-        if (!n) return;
-        std::memcpy(out.seq_idx.data() + at, b.seq_idx.data(), n * sizeof(int32_t));
-        std::memcpy(out.first.data() + at, b.first.data(), n * sizeof(int32_t));
-        std::memcpy(out.flags.data() + at, b.flags.data(), n * sizeof(uint16_t));
-        std::memcpy(out.mapq.data() + at, b.mapq.data(), n);
-        std::memcpy(out.nh.data() + at, b.nh.data(), n * sizeof(int16_t));
-        std::memcpy(out.name_hash.data() + at, b.name_hash.data(), n * sizeof(uint64_t));
-        const std::vector<int16_t>& m = rg_map[(size_t)t];
-        for (size_t i = 0; i < n; i++) out.rg[at + i] = b.rg[i] < 0 ? (int16_t)-1 : m[(size_t)b.rg[i]];
-        for (size_t i = 0; i < n; i++) {   // (a part's offset arrays start with their own 0)
-            out.cigar_off[at + i + 1] = (int64_t)cig0[(size_t)t] + b.cigar_off[i + 1];
-            out.base_off[at + i + 1] = (int64_t)base0[(size_t)t] + b.base_off[i + 1];
-        }
-        if (!b.cigar.empty()) std::memcpy(out.cigar.data() + cig0[(size_t)t], b.cigar.data(), b.cigar.size() * sizeof(uint32_t));
-        if (!b.bases.empty()) {
-            std::memcpy(out.bases.data() + base0[(size_t)t], b.bases.data(), b.bases.size());
-            std::memcpy(out.quals.data() + base0[(size_t)t], b.quals.data(), b.quals.size());
-        }
-        OwnedBatch().swap_storage(b);
-    });
-    return true;
+    return merge_parts(ld, parts);
 }
 
 bool load_alignments(const std::string& path, const Genome& g, OwnedBatch& b, std::string& err, RgTable* rgs = nullptr) {
@@ -516,7 +655,11 @@ bool load_alignments(const std::string& path, const Genome& g, OwnedBatch& b, st
     bool ok;
     const auto t_load = std::chrono::steady_clock::now();
     if (magic[0] == 0x1f && magic[1] == 0x8b) ok = load_bam(path, ld);   // BGZF (htsjdk picks the reader from the file content too)
-    else { std::ifstream in(path); ok = load_sam_text(in, ld); }
+    else {
+        bool handled = false;
+        ok = load_sam_parallel(path, ld, handled);
+        if (!handled) { std::ifstream in(path); ok = load_sam_text(in, ld); }
+    }
     if (!ok) err = ld.err;
     if (std::getenv("NGSEP_TIMING"))
         std::fprintf(stderr, "load_alignments %s: %.3f s, %zu records\n", path.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count(), b.first.size());

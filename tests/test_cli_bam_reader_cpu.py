@@ -42,15 +42,16 @@ def test_bam_and_sam_decode_to_the_same_batch(tmp_path):
     n = bam_util.sam_to_bam(sam, bam)
     assert n > 15000
     outs = {}
-    # "bam": one thread decodes the whole file; "bam_parts": ranges of 1500 records on six threads, laid side by side afterwards
-    for tag, path, env in (("sam", sam, {}), ("bam", bam, {"NGSEP_HOST_THREADS": "1"}), ("bam_parts", bam, {"NGSEP_HOST_THREADS": "6", "NGSEP_BAM_PART_RECORDS": "1500"})):
+    # "sam" / "bam": one thread reads the whole file; "..._parts": ranges of about 1500 records on six threads, laid side by side afterwards
+    parts = {"NGSEP_HOST_THREADS": "6", "NGSEP_BAM_PART_RECORDS": "1500"}
+    for tag, path, env in (("sam", sam, {"NGSEP_HOST_THREADS": "1"}), ("sam_parts", sam, parts), ("bam", bam, {"NGSEP_HOST_THREADS": "1"}), ("bam_parts", bam, parts)):
         prefix, dump = str(tmp_path / f"out_{tag}"), str(tmp_path / f"dump_{tag}.bin")
         subprocess.check_call([CLI, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", prefix, "--host-only", "--dump-batch", dump],
                               stderr=subprocess.DEVNULL, env=dict(os.environ, **env))
         outs[tag] = (_read_dump(dump), open(prefix + ".vcf").read())
     names = ["seq_idx", "first", "flags", "mapq", "rg", "nh", "cigar_off", "cigar", "base_off", "bases", "quals", "name_hash"]
     assert len(outs["sam"][0]) == len(names)
-    for tag in ("bam", "bam_parts"):
+    for tag in ("sam_parts", "bam", "bam_parts"):
         for name, a, b in zip(names, outs["sam"][0], outs[tag][0]):
             assert a == b, (tag, name)
         assert outs["sam"][1] == outs[tag][1]
