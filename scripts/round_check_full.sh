@@ -1,5 +1,5 @@
 #!/bin/bash
-# What the driver runs at round end (build, GPU tests, smoke, bench line, reference arm) + the CLI from a BAM file when scratch_in/ holds one
+# What the driver runs at round end (build, GPU tests, smoke, bench line, reference arm) + the CLI from a BAM file when scratch_in/big.bam (+ big.fa) exists + the sample-axis benches
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build_check.log 2>&1 || { tail -20 gpurun_out/build_check.log; exit 1; }
