@@ -1,6 +1,7 @@
 """CPU fuzz of the host pipeline against the oracle (no GPU): random simulation parameters and option sets; compares the
 host-made indel / STR records (host_only mode) with the oracle's.  Round 1: 85 single-sample, 85 multi-sample and 30 CLI seeds, no
-mismatch.   python scripts/fuzz_host_vs_oracle.py single|multi|cli FIRST_SEED LAST_SEED"""
+mismatch.   python scripts/fuzz_host_vs_oracle.py single|multi|cli|known|bam FIRST_SEED LAST_SEED
+(bam: corrupted BAM files through the CLI's reader, one thread and many small parts on six threads: a clean error or a decode, never a crash.)"""
 import sys
 MODE = sys.argv.pop(1)
 import sys, os, tempfile, numpy as np
@@ -94,6 +95,51 @@ def cli():
     print("bad", bad)
 
 
+def bam():
+    """Random corruption of a BAM stream (bytes flipped anywhere in the first records / the header, truncation at a random place) through the CLI's reader
+    in --host-only mode, decoded by one thread and as many small parts on six threads: exit code 0 (decoded) or 2 (the reader's error), and the same one both ways."""
+    import struct, subprocess, zlib
+    from tests import bam_util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "ngsepcore_b200", "ngsep_b200")
+    d = tempfile.mkdtemp()
+    genome, batch, _ = simulate.simulate(contigs=[("chrA", 12000)], depth=12, seeds=(171, 172, 173), indel_rate=2e-3, n_read_groups=2)
+    fa, sam, bamf = os.path.join(d, "r.fa"), os.path.join(d, "p.sam"), os.path.join(d, "p.bam")
+    simulate.write_fasta(fa, genome); simulate.write_sam(sam, batch)
+    bam_util.sam_to_bam(sam, bamf)
+    raw = open(bamf, "rb").read()
+    stream, p = bytearray(), 0
+    while p < len(raw):
+        bsize = struct.unpack_from("<H", raw, p + 16)[0] + 1
+        stream += zlib.decompress(raw[p + 18:p + bsize - 8], -15)
+        p += bsize
+    bad = 0
+    modes = (dict(NGSEP_HOST_THREADS="1"), dict(NGSEP_HOST_THREADS="6", NGSEP_BAM_PART_RECORDS="40"))
+    for seed in range(int(sys.argv[1]), int(sys.argv[2])):
+        rng = np.random.default_rng(seed)
+        s = bytearray(stream)
+        kind = int(rng.integers(0, 3))
+        if kind == 0:       # bytes flipped in the header and the first records
+            for _ in range(int(rng.integers(1, 6))): s[int(rng.integers(0, min(len(s), 6000)))] = int(rng.integers(0, 256))
+        elif kind == 1:     # bytes flipped anywhere
+            for _ in range(int(rng.integers(1, 12))): s[int(rng.integers(0, len(s)))] = int(rng.integers(0, 256))
+        else:               # truncation
+            s = s[:int(rng.integers(1, len(s)))]
+        path = os.path.join(d, "c.bam")
+        with open(path, "wb") as o:
+            for i in range(0, len(s), 60000): o.write(bam_util._bgzf_block(bytes(s[i:i + 60000])))
+            o.write(bam_util._bgzf_block(b""))
+        rcs, outs = [], []
+        for env in modes:
+            rc = subprocess.call([exe, "SingleSampleVariantsDetector", "-i", path, "-r", fa, "-o", os.path.join(d, "o"), "--host-only"], stderr=subprocess.DEVNULL,
+                                 env=dict(os.environ, **env), timeout=120)
+            rcs.append(rc); outs.append(open(os.path.join(d, "o.vcf")).read() if rc == 0 else None)
+        ok = rcs[0] in (0, 2) and rcs[0] == rcs[1] and outs[0] == outs[1]
+        bad += not ok
+        print(seed, ("head", "any", "cut")[kind], rcs, "OK" if ok else "MISMATCH", flush=True)
+    print("bad", bad)
+
+
 def known():
     """-knownVariants: the host-made records (the input variants that are not SNVs) against the oracle's."""
     from tests.known_util import make_known_vcf
@@ -125,4 +171,4 @@ def known():
     print("mismatches", bad)
 
 
-{"single": single, "multi": multi, "cli": cli, "known": known}[MODE]()
+{"single": single, "multi": multi, "cli": cli, "known": known, "bam": bam}[MODE]()
