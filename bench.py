@@ -257,7 +257,7 @@ def run_gpu(args):
 
     # ---- whole detector from decoded records (host stages + device + VCF text), informational --------------------------------
     pipeline = None
-    if not args.no_pipeline:
+    if not args.no_pipeline and rank == 0:   # (one rank: the detector uses every host thread, N of them at once would time their contention)
         det2 = hostapi.Detector(device=device)
         det2.set_genome(genome)
         runs = []
