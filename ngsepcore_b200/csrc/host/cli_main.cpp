@@ -672,7 +672,34 @@ void merge_inputs(const std::vector<OwnedBatch>& files, const AdmissionOptions& 
     for (auto& f : files) views.push_back(f.view());
     std::vector<std::pair<int, int64_t>> order;
     merge_order(views, opt, order);
-    for (auto& o : order) out.append_from(files[(size_t)o.first], (size_t)o.second, files[(size_t)o.first].rg[(size_t)o.second]);
+    // every record's place in the merged arrays, then the records copied on all host threads (a population run merges tens of millions)
+    const size_t n = order.size(), rec0 = out.first.size();
+    std::vector<int64_t> co(n + 1), bo(n + 1);
+    co[0] = (int64_t)out.cigar.size(); bo[0] = (int64_t)out.bases.size();
+    for (size_t i = 0; i < n; i++) {
+        const OwnedBatch& f = files[(size_t)order[i].first];
+        const size_t r = (size_t)order[i].second;
+        co[i + 1] = co[i] + (f.cigar_off[r + 1] - f.cigar_off[r]);
+        bo[i + 1] = bo[i] + (f.base_off[r + 1] - f.base_off[r]);
+    }
+    out.seq_idx.resize(rec0 + n); out.first.resize(rec0 + n); out.flags.resize(rec0 + n); out.mapq.resize(rec0 + n); out.rg.resize(rec0 + n); out.nh.resize(rec0 + n);
+    out.cigar_off.resize(rec0 + n + 1); out.base_off.resize(rec0 + n + 1);
+    out.cigar.resize((size_t)co[n]); out.bases.resize((size_t)bo[n]); out.quals.resize((size_t)bo[n]);
+    const int nt = (int)std::max<size_t>(1, std::min<size_t>((size_t)host_threads(), n / 50000 + 1));
+    on_threads(nt, [&](int t) {
+        for (size_t i = n * (size_t)t / (size_t)nt; i < n * (size_t)(t + 1) / (size_t)nt; i++) {
+            const OwnedBatch& f = files[(size_t)order[i].first];
+            const size_t r = (size_t)order[i].second, at = rec0 + i;
+            out.seq_idx[at] = f.seq_idx[r]; out.first[at] = f.first[r]; out.flags[at] = f.flags[r]; out.mapq[at] = f.mapq[r]; out.rg[at] = f.rg[r]; out.nh[at] = f.nh[r];
+            out.cigar_off[at + 1] = co[i + 1]; out.base_off[at + 1] = bo[i + 1];
+            const size_t nc = (size_t)(co[i + 1] - co[i]), nb = (size_t)(bo[i + 1] - bo[i]);
+            if (nc) std::memcpy(out.cigar.data() + co[i], f.cigar.data() + f.cigar_off[r], nc * sizeof(uint32_t));
+            if (nb) {
+                std::memcpy(out.bases.data() + bo[i], f.bases.data() + f.base_off[r], nb);
+                std::memcpy(out.quals.data() + bo[i], f.quals.data() + f.base_off[r], nb);
+            }
+        }
+    });
 }
 
 void usage() {

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <climits>
 #include <cstring>
+#include <atomic>
+#include <queue>
 #include <thread>
 #include <unordered_map>
 
@@ -509,25 +511,42 @@ void merge_order(const std::vector<BatchView>& inputs, const AdmissionOptions& o
     const size_t n = inputs.size();
     std::vector<std::vector<int64_t>> keep(n);
     std::vector<std::vector<int>> last(n);
-    for (size_t f = 0; f < n; f++) reader_survivors(inputs[f], opt, keep[f], last[f]);
+    {   // the inputs are independent up to here: one thread each (a population run has a file per sample)
+        const unsigned hw = std::thread::hardware_concurrency();
+        const size_t nt = std::min<size_t>(n, std::max(1u, std::min(32u, hw ? hw : 1u)));
+        std::atomic<size_t> next{0};
+        auto work = [&]() { for (;;) { const size_t f = next.fetch_add(1); if (f >= n) return; reader_survivors(inputs[f], opt, keep[f], last[f]); } };
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+    }
+    // chooseNextAln (APG:262-289) looks at the head of every input and keeps the smallest by (sequence, first, last), the lowest input
+    // on ties: a heap over the heads with the input index as the last key gives the same order in O(log n) per record
+    struct Head { int seq, first, last, file; };
+    auto after = [](const Head& a, const Head& b) {   // a comes after b
+        if (a.seq != b.seq) return a.seq > b.seq;
+        if (a.first != b.first) return a.first > b.first;
+        if (a.last != b.last) return a.last > b.last;
+        return a.file > b.file;
+    };
+    std::priority_queue<Head, std::vector<Head>, decltype(after)> heap(after);
     std::vector<size_t> head(n, 0);
+    auto push = [&](size_t f) {
+        if (head[f] >= keep[f].size()) return;
+        const int64_t i = keep[f][head[f]];
+        heap.push(Head{inputs[f].seq_idx[i], inputs[f].first[i], last[f][head[f]], (int)f});
+    };
+    size_t total = 0;
+    for (size_t f = 0; f < n; f++) { total += keep[f].size(); push(f); }
     out.clear();
-    while (true) {
-        int best = -1;
-        for (size_t f = 0; f < n; f++) {
-            if (head[f] >= keep[f].size()) continue;
-            if (best < 0) { best = (int)f; continue; }
-            const BatchView& A = inputs[best]; const BatchView& B = inputs[f];
-            const int64_t ia = keep[best][head[best]], ib = keep[f][head[f]];
-            bool greater;   // cmp.compare(answer, current) > 0
-            if (A.seq_idx[ia] != B.seq_idx[ib]) greater = A.seq_idx[ia] > B.seq_idx[ib];
-            else if (A.first[ia] != B.first[ib]) greater = A.first[ia] > B.first[ib];
-            else greater = last[best][head[best]] > last[f][head[f]];
-            if (greater) best = (int)f;
-        }
-        if (best < 0) break;
-        out.push_back({best, keep[best][head[best]]});
-        head[best]++;
+    out.reserve(total);
+    while (!heap.empty()) {
+        const size_t f = (size_t)heap.top().file;
+        heap.pop();
+        out.push_back({(int)f, keep[f][head[f]]});
+        head[f]++;
+        push(f);
     }
 }
 
