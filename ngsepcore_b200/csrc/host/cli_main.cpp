@@ -812,7 +812,13 @@ int main(int argc, char** argv) {
         ao.min_mq = o.min_mq; ao.secondary = o.secondary; ao.non_unique_primary = o.non_unique_primary;
         OwnedBatch merged;
         const OwnedBatch* b = files.empty() ? &merged : &files[0];
-        if (files.size() > 1) { merge_inputs(files, ao, merged); b = &merged; }   // one input: processFile, no merge (APG:216-219)
+        if (files.size() > 1) {   // one input: processFile, no merge (APG:216-219)
+            const auto t_merge = std::chrono::steady_clock::now();
+            merge_inputs(files, ao, merged);
+            b = &merged;
+            if (std::getenv("NGSEP_TIMING"))
+                std::fprintf(stderr, "merge of %zu inputs: %.3f s, %zu records\n", files.size(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t_merge).count(), merged.first.size());
+        }
         // samples: the read groups of the headers only (a group seen on records alone belongs to no sample)
         std::vector<std::string> hdr_ids, hdr_sms;
         std::vector<int> hdr_index;
